@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the residual hot path (BASELINE.json metric: residual evals/s and Gfaces/s on a
+10M-cell hybrid mesh; % of HBM roofline).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one evaluation of FlowFV::compute_residual(u, r, gettimesteps=true, dt) on the synthetic
+10M-cell hybrid tri/quad Gaussian-bump channel with the north-star headline numerics
+Roe + weighted least squares + Venkatakrishnan. `value` is device-resident throughput; `e2e` goes
+through the host-buffer C-ABI entry (H2D of u, D2H of r and dt inside the timed region).
+The reference arm (--impl reference) times the CPU oracle (the reference's loops restated, OpenMP,
+all host threads) on a bounded sample of the same mesh family.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+NUMERICS = {
+    # name: (flux, gradient, reconstruction, limiter_param, per-cell algorithmic bytes of pass A, of pass B)
+    "roe-wls-venkat": ("ROE", "LEASTSQUARES", "VENKATAKRISHNAN", 2.0, 144 + 32 + 8, 160),
+    "hllc-gg-bj": ("HLLC", "GREENGAUSS", "BARTHJESPERSEN", 0.0, 144 + 8, 160),
+}
+BCS = [(2, "slipwall", (0.0, 0.0)), (3, "inflowoutflow", (0.0, 0.0)), (4, "inflowoutflow", (0.0, 0.0))]
+MINF = 0.2
+
+
+def lattice_for(cells):
+    """Base lattice of the bump channel (aspect 2.67) whose hybrid mesh has ~`cells` cells (x 4/3 from splitting)."""
+    nbase = cells/(1.0 + 1.0/3.0)
+    ny = int(round((nbase/2.6667)**0.5))
+    nx = int(round(2.6667*ny))
+    return nx, ny
+
+
+def algorithmic_bytes(numerics, nc, nf):
+    """pass A = c_A*N_c + 16*N_f (face midpoints), pass B = 160*N_c + 48*N_f."""
+    cA, cB = NUMERICS[numerics][4], NUMERICS[numerics][5]
+    return cA*nc + 16*nf, cB*nc + 48*nf
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5+k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_case(cells, numerics, tile, rank=0, world=1):
+    """Host mesh (Hilbert-ordered, so the device numbering is the identity), its arrays and the state."""
+    from fvens_b200 import lib, synth
+    nx, ny = lattice_for(cells)
+    arrs = synth.bump_channel(nx, ny, seed=12345 + rank)
+    um = lib.UMesh.from_arrays(*arrs)
+    perm = um.hilbert_ordering()          # the reference's `-mesh_reorder` step, with a locality order
+    um.reorder_cells(perm)
+    coords, nnode, inpoel, bface = arrs
+    nnode, inpoel = nnode[perm], inpoel[perm]
+    rc = synth.cell_centres(coords, nnode, inpoel)
+    u = synth.perturbed_state(rc, 1.4, MINF)
+    return um, (coords, nnode, inpoel, bface), u, (nx, ny)
+
+
+def cpu_reference(cells, numerics, steps, warmup):
+    """Oracle (restated reference loops, OpenMP) on the host cores. Returns (Gfaces/s, ms/step, info)."""
+    import orc
+    from fvens_b200 import lib
+    um, arrs, u, (nx, ny) = build_case(cells, numerics, 512)
+    om = orc.Mesh.from_arrays(*arrs)
+    flux, grad, recon, lp = NUMERICS[numerics][:4]
+    phys = lib.make_physics(1.4, MINF, 288.15, 5000.0, 0.72, 0.0)
+    threads = os.cpu_count() or 1
+    orc.set_threads(threads)
+    of = orc.Flow(om, phys, lib.FLUX[flux], lib.GRAD[grad], lib.RECON[recon], lp, True, 0,
+                  [(t, lib.BC[ty], v) for (t, ty, v) in BCS])
+    for _ in range(warmup):
+        of.residual(u)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        of.residual(u)
+    dt = (time.perf_counter() - t0)/steps
+    info = {"cells": om.nelem, "faces": om.naface, "cores": orc.num_threads(),
+            "sample": f"bump channel {nx}x{ny} base lattice = {om.nelem} cells / {om.naface} faces "
+                      f"(same generator and numerics as the GPU workload, {steps} evaluations after {warmup} warm-up)"}
+    return om.naface/dt/1e9, dt*1e3, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=float, default=10.0e6)
+    ap.add_argument("--numerics", default="roe-wls-venkat", choices=list(NUMERICS))
+    ap.add_argument("--tile", type=int, default=512)
+    ap.add_argument("--cpu-cells", type=float, default=1.0e6, help="size of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    flux, grad, recon, lp = NUMERICS[args.numerics][:4]
+    workload = (f"synthetic hybrid tri/quad Gaussian-bump channel, {args.cells/1e6:g}M cells per GPU, "
+                f"{flux}+{grad}+{recon} second-order residual with local time steps (BASELINE configs[2] mesh, "
+                f"north-star headline numerics)")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import __graft_entry__ as g
+        g.build(quiet=True)
+        gf, ms, info = cpu_reference(args.cpu_cells, args.numerics, max(1, min(args.steps, 20)), max(1, min(args.warmup, 3)))
+        line = {"impl": "reference", "metric": "Gfaces/s", "value": gf, "unit": "Gfaces/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload, "timed_on": info["sample"]},
+                "residual_evals_per_s": 1e3/ms,
+                "cpu_baseline": {"value": gf, "unit": "Gfaces/s", "cores": info["cores"], "kind": "port",
+                                 "sample": info["sample"]},
+                "e2e": {"value": gf, "unit": "Gfaces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    from fvens_b200 import lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        g.build(quiet=True)
+    if world > 1:
+        dist.barrier()
+    lib.load()
+
+    um, arrs, u, (nx, ny) = build_case(args.cells, args.numerics, args.tile, rank, world)
+    dm = lib.DeviceMesh(um, reorder="none", tile_cells=args.tile, device=local_rank)
+    phys = lib.make_physics(1.4, MINF, 288.15, 5000.0, 0.72, 0.0)
+    fl = lib.FlowFV(dm, phys, flux, grad, recon, lp, True, 0, BCS)
+    nc, nf = um.nelem, um.naface
+    du = torch.from_numpy(u).cuda()
+    res = torch.empty_like(du)
+    dtm = torch.empty(nc, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        fl.compute_residual(du, res, True, dtm, accumulate=False, stream=stream)
+    barrier()
+    fl.timing(True)
+    launches0 = fl.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        fl.compute_residual(du, res, True, dtm, accumulate=False, stream=stream)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = fl.launch_count() - launches0
+    ms_cell, ms_face, ntimed = fl.timing(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item()/args.steps
+
+    # sanity: the timed output is a real residual (finite, non-trivial)
+    chk = float(res.abs().max().item())
+    assert np.isfinite(chk) and chk > 0.0
+
+    # end to end through the host-buffer entry point, pinned host memory
+    hu = torch.from_numpy(u).pin_memory()
+    hres = torch.empty((nc, 4), dtype=torch.float64).pin_memory()
+    hdt = torch.empty(nc, dtype=torch.float64).pin_memory()
+    for _ in range(2):
+        fl.compute_residual_host(hu.data_ptr(), hres.data_ptr(), True, hdt.data_ptr(), accumulate=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        fl.compute_residual_host(hu.data_ptr(), hres.data_ptr(), True, hdt.data_ptr(), accumulate=False)
+    barrier()
+    t_e2e = torch.tensor([(time.perf_counter()-t0)/args.e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    assert torch.equal(hres, res.cpu())
+
+    # fused pseudo-time step (residual + dt + update + norm), device resident
+    u2 = du.clone()
+    n2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        fl.euler_step(u2, 0.5, n2, stream=stream)
+    barrier()
+    s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+    s0.record()
+    nstep = max(5, args.steps//3)
+    for _ in range(nstep):
+        fl.euler_step(u2, 0.5, n2, stream=stream)
+    s1.record()
+    barrier()
+    ms_euler = s0.elapsed_time(s1)/nstep
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    bA, bB = algorithmic_bytes(args.numerics, nc, nf)
+    t_face = ms_face/max(ntimed, 1)*1e-3
+    t_cell = ms_cell/max(ntimed, 1)*1e-3
+    ach_face = bB/t_face/1e9
+    gfaces = world*nf/(ms_step*1e-3)/1e9
+    info = dm.info
+    line = {
+        "metric": "Gfaces/s", "value": gfaces, "unit": "Gfaces/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "cells_per_gpu": nc, "faces_per_gpu": nf, "lattice": [nx, ny],
+                   "tile_cells": info.tile_cells, "cut_face_duplicates": info.ncut_dup, "colours": info.max_colours,
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent shards (no halo yet)",
+                   "l2": "inputs (320 MB state + 640 MB gradients + mesh) exceed the 126 MB L2; no explicit flush"},
+        "residual_evals_per_s": world*1e3/ms_step,
+        "residual_roofline_frac": (bA + bB)/(ms_step*1e-3)/1e9/peak,
+        "euler_step": {"ms_per_step": ms_euler, "Gfaces/s": nf/(ms_euler*1e-3)/1e9,
+                       "note": "fused residual + local dt + forward-Euler update + energy-residual norm"},
+        "kernels_ms": {"gradient_limiter_pass": t_cell*1e3, "face_pass": t_face*1e3, "timed_evals": ntimed},
+        "roofline": {"bound": "hbm", "kernel": "face_kernel (reconstruct + flux + spectral radius + accumulate)",
+                     "achieved": ach_face, "peak": peak, "unit": "GB/s", "frac": ach_face/peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": bB, "peak_source": peak_src,
+                     "cell_pass": {"achieved": bA/t_cell/1e9, "frac": bA/t_cell/1e9/peak, "algorithmic_bytes_per_launch": bA}},
+        "e2e": {"value": world*nf/t_e2e.item()/1e9, "unit": "Gfaces/s", "ms_per_step": t_e2e.item()*1e3,
+                "h2d_bytes_per_step": 32*nc, "d2h_bytes_per_step": 40*nc,
+                "note": "fvg_residual_host on pinned host buffers: H2D u, kernels, D2H residual + dt"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        gf, ms, ci = cpu_reference(args.cpu_cells, args.numerics, 6, 2)
+        line["cpu_baseline"] = {"value": gf, "unit": "Gfaces/s", "cores": ci["cores"], "kind": "port",
+                                "sample": ci["sample"], "ms_per_eval": ms}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,715 @@
+/* extern "C" entry points of libfvens_b200.so other than the device-mesh ones (device_mesh.cu):
+ * host mesh wrappers, flow creation, the residual / pseudo-time orchestration and the test hooks.
+ * Orchestration restates FlowFV::compute_residual (reference src/spatial/flow_spatial.cpp:637-816)
+ * and SteadyForwardEulerSolver::solve (src/ode/aodesolver.cpp:136-282) as a two-pass schedule:
+ *   pass A  cell kernel   cons->prim, boundary ghosts, gradient, limiter  -> limited gradients
+ *   pass B  face kernel   reconstruct, flux, spectral radius, accumulate  -> residual + dt (or u_new)
+ */
+#include "engine.hpp"
+#include "../host/mesh.hpp"
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+struct fvg_umesh { fvens::UMesh<double,2> m; };
+
+namespace fvg {
+
+void rcm_order(int n, int mw, const int *esuel, const int *nnode, std::vector<int> &new2old);
+void hilbert_order(int n, const double *rc, std::vector<int> &new2old);
+
+GasParams make_gas(const fvg_physics &p, double limiter_param)
+{
+	GasParams G;
+	std::memset(&G, 0, sizeof(G));
+	G.g = p.gamma; G.Minf = p.Minf; G.Tinf = p.Tinf; G.Reinf = p.Reinf; G.Pr = p.Pr;
+	G.sCT = 110.5/p.Tinf;
+	G.gm1 = p.gamma - 1.0;
+	G.gM2 = p.gamma*p.Minf*p.Minf;
+	G.pinf = 1.0/(p.gamma*p.Minf*p.Minf);
+	G.uinf[0] = 1.0;
+	G.uinf[1] = std::cos(p.aoa)*std::cos(0.0);
+	G.uinf[2] = std::sin(p.aoa)*std::cos(0.0);
+	G.uinf[3] = G.pinf/(p.gamma - 1.0) + 0.5*1.0*1.0;
+	G.limiter_param = limiter_param;
+	G.nbc = 0;
+	return G;
+}
+
+static FaceLauncher face_launcher(int flux)
+{
+	switch(flux) {
+	case FLUX_LLF: return launch_face_llf;
+	case FLUX_VANLEER: return launch_face_vanleer;
+	case FLUX_AUSM: return launch_face_ausm;
+	case FLUX_AUSMPLUS: return launch_face_ausmplus;
+	case FLUX_ROE: return launch_face_roe;
+	case FLUX_HLL: return launch_face_hll;
+	case FLUX_HLLC: return launch_face_hllc;
+	}
+	return nullptr;
+}
+
+template <typename T>
+static int dev_alloc(fvg_flow *f, T **p, size_t count)
+{
+	void *q = nullptr;
+	FVG_CUDA(cudaMalloc(&q, std::max<size_t>(count, 1)*sizeof(T)));
+	f->allocs.push_back(q);
+	*p = static_cast<T*>(q);
+	return 0;
+}
+
+static int limiter_mode(int recon)
+{
+	if(recon == FVG_RECON_BARTHJESPERSEN) return 1;
+	if(recon == FVG_RECON_VENKATAKRISHNAN) return 2;
+	return 0;
+}
+
+/// Pass A on a device-ordered conserved state: fills f->d_lg and/or f->d_gu
+static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s)
+{
+	const FlowPlan &P = f->plan;
+	if(!P.order2) return 0;
+	CellArgs a;
+	a.m = f->mesh->d; a.gas = f->gas; a.bbc = f->d_bbc; a.u = u; a.ug = nullptr; a.gin = nullptr;
+	a.bnd_policy = P.bnd_policy;
+	int rc;
+	if(P.recon == FVG_RECON_WENO) {
+		a.lg = nullptr; a.gu = f->d_gu;
+		if((rc = launch_cell_kernel(P.gradient, 0, false, a, s)) != 0) return rc;
+		f->launches++;
+		if((rc = launch_weno_kernel(f->mesh->d, f->gas.limiter_param, f->d_gu, f->d_lg, s)) != 0) return rc;
+		f->launches++;
+	}
+	else if(P.recon == FVG_RECON_VANALBADA) {
+		a.lg = nullptr; a.gu = f->d_gu;
+		if((rc = launch_cell_kernel(P.gradient, 0, false, a, s)) != 0) return rc;
+		f->launches++;
+	}
+	else {
+		const int lim = limiter_mode(P.recon);
+		a.lg = f->d_lg;
+		// unlimited gradients are needed separately only when a limiter changes them and the viscous flux wants them
+		a.gu = (P.visc != VISC_NONE && lim != 0) ? f->d_gu : nullptr;
+		if((rc = launch_cell_kernel(P.gradient, lim, false, a, s)) != 0) return rc;
+		f->launches++;
+	}
+	return 0;
+}
+
+static const double *viscous_gradients(const fvg_flow *f)
+{
+	const FlowPlan &P = f->plan;
+	if(P.recon == FVG_RECON_WENO || P.recon == FVG_RECON_VANALBADA) return f->d_gu;
+	if(limiter_mode(P.recon) != 0) return f->d_gu;
+	return f->d_lg;   // no limiter: the stored gradients are the unlimited ones
+}
+
+static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumulate, int gettimesteps,
+                         double *res, double *dtm, double cfl, double *unew, cudaStream_t s)
+{
+	const FlowPlan &P = f->plan;
+	FaceArgs a;
+	a.m = f->mesh->d; a.gas = f->gas; a.bbc = f->d_bbc; a.u = u;
+	a.lg = f->d_lg; a.gu = viscous_gradients(f);
+	a.epilogue = epilogue; a.accumulate = accumulate; a.gettimesteps = gettimesteps;
+	a.res = res; a.dtm = dtm; a.cfl = cfl; a.unew = unew; a.partial = f->d_partial;
+	const int recon = !P.order2 ? FR_FIRST : (P.recon == FVG_RECON_VANALBADA ? FR_MUSCL : FR_LINEAR);
+	FaceLauncher L = face_launcher(P.flux);
+	if(!L) { set_error("unknown flux id"); return FVG_ERR_INVALID; }
+	const int rc = L(recon, P.visc, a, s);
+	if(rc == 0) f->launches++;
+	return rc;
+}
+
+} // namespace fvg
+
+using namespace fvg;
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------ host mesh
+
+static int finish_umesh(std::unique_ptr<fvg_umesh> &h, fvg_umesh **out)
+{
+	h->m.correctBoundaryFaceOrientation();
+	h->m.compute_topological();
+	h->m.compute_areas();
+	h->m.compute_face_data();
+	*out = h.release();
+	return 0;
+}
+
+int fvg_umesh_read(const char *path, fvg_umesh **out)
+{
+	if(!path || !out) { set_error("fvg_umesh_read: null argument"); return FVG_ERR_INVALID; }
+	*out = nullptr;
+	try {
+		std::unique_ptr<fvg_umesh> h(new fvg_umesh{fvens::UMesh<double,2>(fvens::readMesh(path))});
+		return finish_umesh(h, out);
+	} catch(std::exception &e) { set_error(e.what()); return FVG_ERR_IO; }
+}
+
+int fvg_umesh_from_arrays(int npoin, const double *coords, int nelem, const int *nnode,
+                          const int *inpoel, int nbface, const int *bface, fvg_umesh **out)
+{
+	if(!coords || !nnode || !inpoel || !out || (nbface > 0 && !bface) || npoin <= 0 || nelem <= 0) {
+		set_error("fvg_umesh_from_arrays: bad argument"); return FVG_ERR_INVALID;
+	}
+	*out = nullptr;
+	try {
+		fvens::MeshData md;
+		md.npoin = npoin; md.nelem = nelem; md.nbface = nbface;
+		md.nnode.assign(nnode, nnode+nelem); md.nfael = md.nnode;
+		md.maxnnode = 3;
+		for(int i = 0; i < nelem; i++) {
+			if(nnode[i] != 3 && nnode[i] != 4) { set_error("fvg_umesh_from_arrays: cells must have 3 or 4 nodes"); return FVG_ERR_INVALID; }
+			if(nnode[i] == 4) md.maxnnode = 4;
+		}
+		md.maxnfael = md.maxnnode; md.nnofa = 2; md.nbtag = 1; md.ndtag = 0;
+		md.coords.assign(coords, coords + 2*(size_t)npoin);
+		md.inpoel.assign((size_t)nelem*md.maxnnode, -1);
+		for(int i = 0; i < nelem; i++)
+			for(int j = 0; j < nnode[i]; j++) {
+				const int p = inpoel[4*(size_t)i+j];
+				if(p < 0 || p >= npoin) { set_error("fvg_umesh_from_arrays: node index out of range"); return FVG_ERR_INVALID; }
+				md.inpoel[(size_t)i*md.maxnnode+j] = p;
+			}
+		md.bface.assign(bface, bface + 3*(size_t)nbface);
+		std::unique_ptr<fvg_umesh> h(new fvg_umesh{fvens::UMesh<double,2>(md)});
+		return finish_umesh(h, out);
+	} catch(std::exception &e) { set_error(e.what()); return FVG_ERR_INVALID; }
+}
+
+void fvg_umesh_destroy(fvg_umesh *m) { delete m; }
+
+int fvg_umesh_reorder_cells(fvg_umesh *m, const int *perm)
+{
+	if(!m || !perm) { set_error("fvg_umesh_reorder_cells: null argument"); return FVG_ERR_INVALID; }
+	try {
+		const int n = m->m.gnelem();
+		std::vector<char> seen(n, 0);
+		for(int i = 0; i < n; i++) {
+			if(perm[i] < 0 || perm[i] >= n || seen[perm[i]]) { set_error("fvg_umesh_reorder_cells: not a permutation"); return FVG_ERR_INVALID; }
+			seen[perm[i]] = 1;
+		}
+		m->m.reorder_cells(perm);
+		m->m.compute_topological();
+		m->m.compute_areas();
+		m->m.compute_face_data();
+	} catch(std::exception &e) { set_error(e.what()); return FVG_ERR_INVALID; }
+	return 0;
+}
+
+int fvg_umesh_rcm_ordering(const fvg_umesh *m, int *perm)
+{
+	if(!m || !perm) { set_error("fvg_umesh_rcm_ordering: null argument"); return FVG_ERR_INVALID; }
+	std::vector<int> p;
+	rcm_order(m->m.gnelem(), m->m.gmaxnfael(), m->m.esuelData(), m->m.nnodeData(), p);
+	std::memcpy(perm, p.data(), sizeof(int)*p.size());
+	return 0;
+}
+
+int fvg_umesh_hilbert_ordering(const fvg_umesh *m, int *perm)
+{
+	if(!m || !perm) { set_error("fvg_umesh_hilbert_ordering: null argument"); return FVG_ERR_INVALID; }
+	std::vector<double> rc(2*(size_t)m->m.gnelem());
+	m->m.compute_cell_centres(rc.data());
+	std::vector<int> p;
+	hilbert_order(m->m.gnelem(), rc.data(), p);
+	std::memcpy(perm, p.data(), sizeof(int)*p.size());
+	return 0;
+}
+
+int fvg_umesh_view(const fvg_umesh *h, fvg_host_mesh *v)
+{
+	if(!h || !v) { set_error("fvg_umesh_view: null argument"); return FVG_ERR_INVALID; }
+	const fvens::UMesh<double,2> &m = h->m;
+	v->npoin = m.gnpoin(); v->nelem = m.gnelem(); v->nbface = m.gnbface(); v->naface = m.gnaface();
+	v->ninface = m.gninface(); v->nconnface = m.gnConnFace(); v->maxnnode = m.gmaxnnode(); v->nbtag = m.gnbtag();
+	v->coords = m.coordsData(); v->inpoel = m.inpoelData(); v->nnode = m.nnodeData();
+	v->esuel = m.esuelData(); v->elemface = m.elemfaceData(); v->intfac = m.intfacData();
+	v->btags = m.btagsData(); v->facemetric = m.facemetricData(); v->area = m.areaData();
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------ flow
+
+int fvg_flow_create(fvg_mesh *mesh, const fvg_physics *phys, const fvg_numerics *num,
+                    const fvg_bc *bcs, int nbc, fvg_flow **out)
+{
+	if(!mesh || !phys || !num || !out || (nbc > 0 && !bcs)) { set_error("fvg_flow_create: null argument"); return FVG_ERR_INVALID; }
+	*out = nullptr;
+	if(nbc > MAX_BC) { set_error("fvg_flow_create: at most 16 boundary conditions"); return FVG_ERR_UNSUPPORTED; }
+	if(num->flux < 0 || num->flux >= FLUX_COUNT) { set_error("fvg_flow_create: unknown flux"); return FVG_ERR_INVALID; }
+	if(num->gradient < 0 || num->gradient > 2) { set_error("fvg_flow_create: unknown gradient scheme"); return FVG_ERR_INVALID; }
+	if(num->reconstruction < 0 || num->reconstruction > 4) { set_error("fvg_flow_create: unknown reconstruction"); return FVG_ERR_INVALID; }
+	if(!(phys->gamma > 1.0) || !(phys->Minf > 0.0)) { set_error("fvg_flow_create: gamma must exceed 1 and Minf must be positive"); return FVG_ERR_INVALID; }
+	if(mesh->device < 0) { set_error("fvg_flow_create: the mesh was built host-only (device = -2) and has no device arrays"); return FVG_ERR_INVALID; }
+	FVG_CUDA(cudaSetDevice(mesh->device));
+
+	std::unique_ptr<fvg_flow> f(new fvg_flow);
+	f->mesh = mesh;
+	f->phys = *phys;
+	f->gas = make_gas(*phys, num->limiter_param);
+	f->gas.nbc = nbc;
+	for(int i = 0; i < nbc; i++) {
+		if(bcs[i].type < 0 || bcs[i].type > 7 || bcs[i].type == PERIODIC_BC) {
+			// reference: create_const_flowBCs throws for types without a FlowBC class (abc.cpp:493-494)
+			set_error("fvg_flow_create: boundary condition type " + std::to_string(bcs[i].type) + " is not available");
+			return FVG_ERR_UNSUPPORTED;
+		}
+		f->gas.bc[i].tag = bcs[i].tag; f->gas.bc[i].type = bcs[i].type;
+		f->gas.bc[i].v0 = bcs[i].vals[0]; f->gas.bc[i].v1 = bcs[i].vals[1];
+	}
+	FlowPlan &P = f->plan;
+	P.flux = num->flux; P.gradient = num->gradient; P.recon = num->reconstruction;
+	P.order2 = num->order2 ? 1 : 0; P.bnd_policy = num->bnd_policy;
+	P.visc = !phys->viscous_sim ? VISC_NONE : (phys->const_visc ? VISC_CONST : VISC_SUTHERLAND);
+	const bool limited = limiter_mode(P.recon) != 0;
+	P.need_lg = P.order2 && P.recon != FVG_RECON_VANALBADA;
+	P.need_gu = P.order2 && (P.recon == FVG_RECON_WENO || P.recon == FVG_RECON_VANALBADA ||
+	                         (P.visc != VISC_NONE && limited));
+
+	// boundary face -> BC table index; every marker present in the mesh needs a BC
+	// (reference: bcs.at(tag) throws std::out_of_range in compute_boundary_state, flow_spatial.cpp:92)
+	const int nb = mesh->d.nbface, n = mesh->d.ncell;
+	std::vector<int> bbc(nb);
+	for(int b = 0; b < nb; b++) {
+		int k = -1;
+		for(int i = 0; i < nbc; i++) if(bcs[i].tag == mesh->h_btag[b]) k = i;
+		if(k < 0) { set_error("fvg_flow_create: no boundary condition for marker " + std::to_string(mesh->h_btag[b])); return FVG_ERR_INVALID; }
+		bbc[b] = k;
+	}
+	int rc;
+	if((rc = dev_alloc(f.get(), &f->d_bbc, nb)) != 0) return rc;
+	if(nb) FVG_CUDA(cudaMemcpy(f->d_bbc, bbc.data(), sizeof(int)*nb, cudaMemcpyHostToDevice));
+	if(P.need_lg && (rc = dev_alloc(f.get(), &f->d_lg, 8*(size_t)n)) != 0) return rc;
+	if(P.need_gu && (rc = dev_alloc(f.get(), &f->d_gu, 8*(size_t)n)) != 0) return rc;
+	if((rc = dev_alloc(f.get(), &f->d_partial, mesh->d.ntile)) != 0) return rc;
+	if((rc = dev_alloc(f.get(), &f->d_norm, 1)) != 0) return rc;
+	FVG_CUDA(cudaMallocHost((void**)&f->h_norm, sizeof(double)));
+	*out = f.release();
+	return 0;
+}
+
+void fvg_flow_destroy(fvg_flow *f)
+{
+	if(!f) return;
+	for(void *p : f->allocs) cudaFree(p);
+	if(f->h_norm) cudaFreeHost(f->h_norm);
+	delete f;
+}
+
+int fvg_flow_launch_count(const fvg_flow *f, long long *count)
+{
+	if(!f || !count) { set_error("fvg_flow_launch_count: null argument"); return FVG_ERR_INVALID; }
+	*count = f->launches;
+	return 0;
+}
+
+/// records a timing event on the stream when per-pass timing is enabled
+static int mark(fvg_flow *f, cudaStream_t s)
+{
+	if(!f->timing) return 0;
+	cudaEvent_t e;
+	FVG_CUDA(cudaEventCreate(&e));
+	f->ev.push_back(e);
+	FVG_CUDA(cudaEventRecord(e, s));
+	return 0;
+}
+
+int fvg_flow_timing(fvg_flow *f, int enable, double *h_out3)
+{
+	if(!f) { set_error("fvg_flow_timing: null argument"); return FVG_ERR_INVALID; }
+	double cell = 0, face = 0; int n = 0;
+	int rc = 0;
+	if(!f->ev.empty()) {
+		const cudaError_t e = cudaDeviceSynchronize();
+		if(e != cudaSuccess) rc = cuda_fail(e, "cudaDeviceSynchronize", __FILE__, __LINE__);
+		for(size_t k = 0; rc == 0 && k + 3 <= f->ev.size(); k += 3) {
+			float a = 0, b = 0;
+			cudaEventElapsedTime(&a, f->ev[k], f->ev[k+1]);
+			cudaEventElapsedTime(&b, f->ev[k+1], f->ev[k+2]);
+			cell += a; face += b; n++;
+		}
+		for(cudaEvent_t e2 : f->ev) cudaEventDestroy(e2);
+		f->ev.clear();
+	}
+	if(h_out3) { h_out3[0] = cell; h_out3[1] = face; h_out3[2] = n; }
+	f->timing = enable != 0;
+	return rc;
+}
+
+/// lazily allocated scratch
+static int ensure(fvg_flow *f, double **p, size_t count) { return *p ? 0 : dev_alloc(f, p, count); }
+
+int fvg_residual(fvg_flow *f, const double *d_u, double *d_res, int accumulate, int gettimesteps,
+                 double *d_dtm, void *stream)
+{
+	if(!f || !d_u || !d_res || (gettimesteps && !d_dtm)) { set_error("fvg_residual: null argument"); return FVG_ERR_INVALID; }
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	const DMesh &D = f->mesh->d;
+	const int n = D.ncell;
+	int rc;
+	if(f->mesh->identity_perm) {
+		if((rc = mark(f, s)) != 0) return rc;
+		if((rc = run_gradient_pass(f, d_u, s)) != 0) return rc;
+		if((rc = mark(f, s)) != 0) return rc;
+		if((rc = run_face_pass(f, d_u, EP_RESIDUAL, accumulate, gettimesteps, d_res, d_dtm, 0.0, nullptr, s)) != 0) return rc;
+		return mark(f, s);
+	}
+	// renumbered mesh: gather the state into device order, scatter the results back
+	if((rc = ensure(f, &f->d_uperm, 4*(size_t)n)) != 0) return rc;
+	if((rc = ensure(f, &f->d_rperm, 4*(size_t)n)) != 0) return rc;
+	if((rc = ensure(f, &f->d_dtperm, n)) != 0) return rc;
+	if((rc = launch_permute_rows(d_u, f->d_uperm, D.new2old, n, 4, true, false, s)) != 0) return rc;
+	if((rc = run_gradient_pass(f, f->d_uperm, s)) != 0) return rc;
+	if((rc = run_face_pass(f, f->d_uperm, EP_RESIDUAL, 0, gettimesteps, f->d_rperm, f->d_dtperm, 0.0, nullptr, s)) != 0) return rc;
+	if((rc = launch_permute_rows(f->d_rperm, d_res, D.new2old, n, 4, false, accumulate != 0, s)) != 0) return rc;
+	if(gettimesteps && (rc = launch_permute_rows(f->d_dtperm, d_dtm, D.new2old, n, 1, false, false, s)) != 0) return rc;
+	f->launches += gettimesteps ? 3 : 2;
+	return 0;
+}
+
+int fvg_residual_host(fvg_flow *f, const double *h_u, double *h_res, int accumulate, int gettimesteps, double *h_dtm)
+{
+	if(!f || !h_u || !h_res || (gettimesteps && !h_dtm)) { set_error("fvg_residual_host: null argument"); return FVG_ERR_INVALID; }
+	FVG_CUDA(cudaSetDevice(f->mesh->device));
+	const size_t n = f->mesh->d.ncell;
+	int rc;
+	if((rc = ensure(f, &f->d_hu, 4*n)) != 0) return rc;
+	if((rc = ensure(f, &f->d_hr, 4*n)) != 0) return rc;
+	if((rc = ensure(f, &f->d_hdt, n)) != 0) return rc;
+	cudaStream_t s = nullptr;
+	FVG_CUDA(cudaMemcpyAsync(f->d_hu, h_u, 4*n*sizeof(double), cudaMemcpyHostToDevice, s));
+	// the reference adds into the caller's residual: upload it and accumulate on the device
+	if(accumulate) FVG_CUDA(cudaMemcpyAsync(f->d_hr, h_res, 4*n*sizeof(double), cudaMemcpyHostToDevice, s));
+	if((rc = fvg_residual(f, f->d_hu, f->d_hr, accumulate, gettimesteps, f->d_hdt, s)) != 0) return rc;
+	FVG_CUDA(cudaMemcpyAsync(h_res, f->d_hr, 4*n*sizeof(double), cudaMemcpyDeviceToHost, s));
+	if(gettimesteps) FVG_CUDA(cudaMemcpyAsync(h_dtm, f->d_hdt, n*sizeof(double), cudaMemcpyDeviceToHost, s));
+	FVG_CUDA(cudaStreamSynchronize(s));
+	return 0;
+}
+
+/// Scratch copy of a reference-ordered cell array in device order (or the array itself)
+static int to_device_order(fvg_flow *f, const double *src, int width, double **scratch, const double **out, cudaStream_t s)
+{
+	if(f->mesh->identity_perm) { *out = src; return 0; }
+	const int n = f->mesh->d.ncell;
+	FVG_CUDA(cudaMallocAsync((void**)scratch, sizeof(double)*(size_t)n*width, s));
+	const int rc = launch_permute_rows(src, *scratch, f->mesh->d.new2old, n, width, true, false, s);
+	*out = *scratch;
+	f->launches++;
+	return rc;
+}
+
+int fvg_gradients(fvg_flow *f, const double *d_uprim, const double *d_ug, double *d_grad, void *stream)
+{
+	if(!f || !d_uprim || !d_grad || (f->mesh->d.nbface > 0 && !d_ug)) { set_error("fvg_gradients: null argument"); return FVG_ERR_INVALID; }
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	const DMesh &D = f->mesh->d;
+	double *su = nullptr, *sg = nullptr;
+	const double *u = nullptr;
+	int rc = to_device_order(f, d_uprim, 4, &su, &u, s);
+	CellArgs a;
+	a.m = D; a.gas = f->gas; a.bbc = f->d_bbc; a.u = u; a.ug = d_ug; a.gin = nullptr;
+	a.lg = nullptr; a.bnd_policy = f->plan.bnd_policy;
+	if(rc == 0 && !f->mesh->identity_perm) {
+		const cudaError_t e = cudaMallocAsync((void**)&sg, sizeof(double)*8*(size_t)D.ncell, s);
+		if(e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+	}
+	a.gu = f->mesh->identity_perm ? d_grad : sg;
+	if(rc == 0) { rc = launch_cell_kernel(f->plan.gradient, 0, true, a, s); f->launches++; }
+	if(rc == 0 && !f->mesh->identity_perm) { rc = launch_permute_rows(sg, d_grad, D.new2old, D.ncell, 8, false, false, s); f->launches++; }
+	if(su) cudaFreeAsync(su, s);
+	if(sg) cudaFreeAsync(sg, s);
+	return rc;
+}
+
+int fvg_face_values(fvg_flow *f, const double *d_uprim, const double *d_ug, const double *d_grad,
+                    double *d_ufl, double *d_ufr, void *stream)
+{
+	if(!f || !d_uprim || !d_grad || !d_ufl || !d_ufr || (f->mesh->d.nbface > 0 && !d_ug)) { set_error("fvg_face_values: null argument"); return FVG_ERR_INVALID; }
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	const DMesh &D = f->mesh->d;
+	const FlowPlan &P = f->plan;
+	double *su = nullptr, *sg = nullptr, *slg = nullptr;
+	const double *u = nullptr, *g = nullptr;
+	int rc = to_device_order(f, d_uprim, 4, &su, &u, s);
+	if(rc == 0) rc = to_device_order(f, d_grad, 8, &sg, &g, s);
+	FaceValArgs fa;
+	fa.m = D; fa.up = u; fa.ug = d_ug; fa.ufl = d_ufl; fa.ufr = d_ufr; fa.muscl = 0; fa.g = g;
+	if(rc == 0 && P.recon != FVG_RECON_NONE && P.recon != FVG_RECON_VANALBADA) {
+		const cudaError_t e = cudaMallocAsync((void**)&slg, sizeof(double)*8*(size_t)D.ncell, s);
+		if(e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+		if(rc == 0 && P.recon == FVG_RECON_WENO) { rc = launch_weno_kernel(D, f->gas.limiter_param, g, slg, s); f->launches++; }
+		else if(rc == 0) {
+			CellArgs a;
+			a.m = D; a.gas = f->gas; a.bbc = f->d_bbc; a.u = u; a.ug = d_ug; a.gin = g; a.lg = slg; a.gu = nullptr;
+			a.bnd_policy = P.bnd_policy;
+			rc = launch_cell_kernel(3 /*given*/, limiter_mode(P.recon), true, a, s); f->launches++;
+		}
+		fa.g = slg;
+	}
+	if(P.recon == FVG_RECON_VANALBADA) fa.muscl = 1;
+	if(rc == 0) { rc = launch_face_values(fa, s); f->launches++; }
+	if(su) cudaFreeAsync(su, s);
+	if(sg) cudaFreeAsync(sg, s);
+	if(slg) cudaFreeAsync(slg, s);
+	return rc;
+}
+
+int fvg_boundary_states(fvg_flow *f, const double *d_ins, double *d_gs, void *stream)
+{
+	if(!f || !d_ins || !d_gs) { set_error("fvg_boundary_states: null argument"); return FVG_ERR_INVALID; }
+	const int rc = launch_boundary_states(f->mesh->d, f->gas, f->d_bbc, d_ins, d_gs, static_cast<cudaStream_t>(stream));
+	if(rc == 0) f->launches++;
+	return rc;
+}
+
+int fvg_get_gradients(fvg_flow *f, const double *d_u, double *d_grads, void *stream)
+{
+	if(!f || !d_u || !d_grads) { set_error("fvg_get_gradients: null argument"); return FVG_ERR_INVALID; }
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	const DMesh &D = f->mesh->d;
+	double *su = nullptr, *sug = nullptr, *sg = nullptr;
+	const double *u = nullptr;
+	int rc = to_device_order(f, d_u, 4, &su, &u, s);
+	if(rc == 0) {
+		const cudaError_t e = cudaMallocAsync((void**)&sug, sizeof(double)*4*(size_t)std::max(D.nbface, 1), s);
+		if(e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+	}
+	// conserved ghost states from the conserved cell states; then the gradient scheme on conserved variables
+	if(rc == 0) { rc = launch_boundary_prim_ghosts(D, f->gas, f->d_bbc, u, sug, false, s); f->launches++; }
+	if(rc == 0 && !f->mesh->identity_perm) {
+		const cudaError_t e = cudaMallocAsync((void**)&sg, sizeof(double)*8*(size_t)D.ncell, s);
+		if(e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+	}
+	CellArgs a;
+	a.m = D; a.gas = f->gas; a.bbc = f->d_bbc; a.u = u; a.ug = sug; a.gin = nullptr; a.lg = nullptr;
+	a.gu = f->mesh->identity_perm ? d_grads : sg; a.bnd_policy = f->plan.bnd_policy;
+	if(rc == 0) { rc = launch_cell_kernel(f->plan.gradient, 0, true, a, s); f->launches++; }
+	if(rc == 0 && !f->mesh->identity_perm) { rc = launch_permute_rows(sg, d_grads, D.new2old, D.ncell, 8, false, false, s); f->launches++; }
+	if(su) cudaFreeAsync(su, s);
+	if(sug) cudaFreeAsync(sug, s);
+	if(sg) cudaFreeAsync(sg, s);
+	return rc;
+}
+
+int fvg_surface_data(fvg_flow *f, const double *d_u, const double *d_grads, int marker, double *h_out3)
+{
+	if(!f || !d_u || !d_grads || !h_out3) { set_error("fvg_surface_data: null argument"); return FVG_ERR_INVALID; }
+	cudaStream_t s = nullptr;
+	double *su = nullptr, *sg = nullptr, *d4 = nullptr;
+	const double *u = nullptr, *g = nullptr;
+	int rc = to_device_order(f, d_u, 4, &su, &u, s);
+	if(rc == 0) rc = to_device_order(f, d_grads, 8, &sg, &g, s);
+	if(rc == 0) { const cudaError_t e = cudaMalloc((void**)&d4, 4*sizeof(double)); if(e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
+	if(rc == 0) { rc = launch_surface_data(f->mesh->d, f->gas, f->phys.aoa, u, g, marker, d4, s); f->launches++; }
+	double h4[4] = {0,0,0,0};
+	if(rc == 0) { const cudaError_t e = cudaMemcpy(h4, d4, sizeof(h4), cudaMemcpyDeviceToHost); if(e != cudaSuccess) rc = cuda_fail(e, "D2H", __FILE__, __LINE__); }
+	h_out3[0] = h4[0]; h_out3[1] = h4[1]; h_out3[2] = h4[2];
+	if(su) cudaFreeAsync(su, s);
+	if(sg) cudaFreeAsync(sg, s);
+	cudaFree(d4);
+	return rc;
+}
+
+int fvg_entropy_error(fvg_flow *f, const double *d_u, double *h_out)
+{
+	if(!f || !d_u || !h_out) { set_error("fvg_entropy_error: null argument"); return FVG_ERR_INVALID; }
+	double *su = nullptr;
+	const double *u = nullptr;
+	int rc = to_device_order(f, d_u, 4, &su, &u, nullptr);
+	if(rc == 0) rc = launch_entropy(f->mesh->d, f->gas, u, f->d_norm, nullptr);
+	if(su) cudaFreeAsync(su, nullptr);
+	if(rc != 0) return rc;
+	f->launches += 2;
+	double v = 0;
+	FVG_CUDA(cudaMemcpy(&v, f->d_norm, sizeof(double), cudaMemcpyDeviceToHost));
+	*h_out = std::sqrt(v);
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------ pseudo-time
+
+/// One fused step on device-ordered buffers: reads uin, writes uout, norm^2 -> f->d_norm
+static int step_device_order(fvg_flow *f, const double *uin, double *uout, double cfl, cudaStream_t s)
+{
+	int rc;
+	if((rc = mark(f, s)) != 0) return rc;
+	if((rc = run_gradient_pass(f, uin, s)) != 0) return rc;
+	if((rc = mark(f, s)) != 0) return rc;
+	if((rc = run_face_pass(f, uin, EP_STEP, 0, 1, nullptr, nullptr, cfl, uout, s)) != 0) return rc;
+	if((rc = mark(f, s)) != 0) return rc;
+	if((rc = launch_final_norm(f->d_partial, f->mesh->d.ntile, f->d_norm, s)) != 0) return rc;
+	f->launches++;
+	return 0;
+}
+
+int fvg_euler_step(fvg_flow *f, double *d_u, double cfl, double *d_resnorm2, void *stream)
+{
+	if(!f || !d_u) { set_error("fvg_euler_step: null argument"); return FVG_ERR_INVALID; }
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	const DMesh &D = f->mesh->d;
+	const size_t n = D.ncell;
+	int rc;
+	if((rc = ensure(f, &f->d_u2, 4*n)) != 0) return rc;
+	if(f->mesh->identity_perm) {
+		if((rc = step_device_order(f, d_u, f->d_u2, cfl, s)) != 0) return rc;
+		FVG_CUDA(cudaMemcpyAsync(d_u, f->d_u2, 4*n*sizeof(double), cudaMemcpyDeviceToDevice, s));
+	} else {
+		if((rc = ensure(f, &f->d_uperm, 4*n)) != 0) return rc;
+		if((rc = launch_permute_rows(d_u, f->d_uperm, D.new2old, (int)n, 4, true, false, s)) != 0) return rc;
+		if((rc = step_device_order(f, f->d_uperm, f->d_u2, cfl, s)) != 0) return rc;
+		if((rc = launch_permute_rows(f->d_u2, d_u, D.new2old, (int)n, 4, false, false, s)) != 0) return rc;
+		f->launches += 2;
+	}
+	if(d_resnorm2) FVG_CUDA(cudaMemcpyAsync(d_resnorm2, f->d_norm, sizeof(double), cudaMemcpyDeviceToDevice, s));
+	return 0;
+}
+
+int fvg_forward_euler_solve(fvg_flow *f, double *d_u, double cfl, double tol, int maxiter,
+                            int check_every, int *h_steps, double *h_hist)
+{
+	if(!f || !d_u || !h_steps) { set_error("fvg_forward_euler_solve: null argument"); return FVG_ERR_INVALID; }
+	if(check_every < 1) check_every = 1;
+	*h_steps = 0;
+	if(maxiter <= 0) return 0;
+	FVG_CUDA(cudaSetDevice(f->mesh->device));
+	cudaStream_t s = nullptr;
+	const DMesh &D = f->mesh->d;
+	const size_t n = D.ncell;
+	int rc;
+	if((rc = ensure(f, &f->d_u2, 4*n)) != 0) return rc;
+	if((rc = ensure(f, &f->d_uperm, 4*n)) != 0) return rc;
+	// state lives in device order in two ping-pong buffers for the whole loop
+	double *cur = f->d_uperm, *nxt = f->d_u2;
+	if(f->mesh->identity_perm) FVG_CUDA(cudaMemcpyAsync(cur, d_u, 4*n*sizeof(double), cudaMemcpyDeviceToDevice, s));
+	else { if((rc = launch_permute_rows(d_u, cur, D.new2old, (int)n, 4, true, false, s)) != 0) return rc; f->launches++; }
+
+	double *d_hist = nullptr;
+	FVG_CUDA(cudaMalloc((void**)&d_hist, sizeof(double)*(size_t)maxiter));
+	std::vector<double> hist((size_t)maxiter);
+	int step = 0, status = FVG_OK;
+	double initres = 1.0;
+	// batches of check_every steps are enqueued back to back; their norms are read afterwards
+	// (check_every = 1 is the reference's loop: one host read of the norm per step)
+	while(rc == 0) {
+		const int batch = std::min(check_every, maxiter - step);
+		for(int k = 0; k < batch && rc == 0; k++) {
+			rc = step_device_order(f, cur, nxt, cfl, s);
+			if(rc == 0) {
+				const cudaError_t e = cudaMemcpyAsync(d_hist + step + k, f->d_norm, sizeof(double), cudaMemcpyDeviceToDevice, s);
+				if(e != cudaSuccess) rc = cuda_fail(e, "norm copy", __FILE__, __LINE__);
+			}
+			std::swap(cur, nxt);
+		}
+		if(rc != 0) break;
+		cudaError_t e = cudaMemcpyAsync(hist.data() + step, d_hist + step, sizeof(double)*batch, cudaMemcpyDeviceToHost, s);
+		if(e == cudaSuccess) e = cudaStreamSynchronize(s);
+		if(e != cudaSuccess) { rc = cuda_fail(e, "norm read-back", __FILE__, __LINE__); break; }
+		bool stop = false;
+		for(int k = 0; k < batch; k++) {
+			const double resi = std::sqrt(hist[step+k]);
+			hist[step+k] = resi;
+			if(step + k == 0) initres = resi;
+			if(stop) continue;
+			if(!std::isfinite(resi)) { status = FVG_ERR_NUMERICAL; stop = true; }
+			else if(!(resi/initres > tol)) stop = true;
+		}
+		step += batch;
+		if(step >= maxiter) { if(status == FVG_OK) status = FVG_ERR_TOLERANCE; stop = true; }
+		if(stop) break;
+	}
+	if(rc == 0) {
+		*h_steps = step;
+		if(h_hist) std::memcpy(h_hist, hist.data(), sizeof(double)*step);
+		if(f->mesh->identity_perm) {
+			const cudaError_t e = cudaMemcpyAsync(d_u, cur, 4*n*sizeof(double), cudaMemcpyDeviceToDevice, s);
+			if(e != cudaSuccess) rc = cuda_fail(e, "state copy", __FILE__, __LINE__);
+		} else { rc = launch_permute_rows(cur, d_u, D.new2old, (int)n, 4, false, false, s); f->launches++; }
+		const cudaError_t e2 = cudaStreamSynchronize(s);
+		if(rc == 0 && e2 != cudaSuccess) rc = cuda_fail(e2, "stream sync", __FILE__, __LINE__);
+	}
+	cudaFree(d_hist);
+	if(rc != 0) return rc;
+	if(status == FVG_ERR_NUMERICAL) set_error("forward Euler: residual norm is not finite");
+	if(status == FVG_ERR_TOLERANCE) set_error("forward Euler: exceeded max iterations");
+	return status;
+}
+
+// ------------------------------------------------------------------------------------ pointwise hooks
+
+namespace {
+struct DevBuf {
+	double *p = nullptr;
+	~DevBuf() { if(p) cudaFree(p); }
+	int put(const double *h, size_t n) {
+		FVG_CUDA(cudaMalloc((void**)&p, std::max<size_t>(n,1)*sizeof(double)));
+		if(h && n) FVG_CUDA(cudaMemcpy(p, h, n*sizeof(double), cudaMemcpyHostToDevice));
+		return 0;
+	}
+	int get(double *h, size_t n) { if(n) FVG_CUDA(cudaMemcpy(h, p, n*sizeof(double), cudaMemcpyDeviceToHost)); return 0; }
+};
+}
+
+int fvg_flux_pointwise(int flux_id, const fvg_physics *phys, int n, const double *h_ul,
+                       const double *h_ur, const double *h_n, double *h_out)
+{
+	if(!phys || n < 0 || (n > 0 && (!h_ul || !h_ur || !h_n || !h_out))) { set_error("fvg_flux_pointwise: bad argument"); return FVG_ERR_INVALID; }
+	const GasParams G = make_gas(*phys, 0.0);
+	DevBuf a, b, c, o;
+	int rc;
+	if((rc = a.put(h_ul, 4*(size_t)n)) || (rc = b.put(h_ur, 4*(size_t)n)) || (rc = c.put(h_n, 2*(size_t)n)) || (rc = o.put(nullptr, 4*(size_t)n))) return rc;
+	if((rc = launch_pointwise_flux(flux_id, G, n, a.p, b.p, c.p, o.p, nullptr)) != 0) return rc;
+	FVG_CUDA(cudaDeviceSynchronize());
+	return o.get(h_out, 4*(size_t)n);
+}
+
+int fvg_bc_pointwise(const fvg_bc *bc, const fvg_physics *phys, int n, const double *h_ins,
+                     const double *h_n, double *h_out)
+{
+	if(!bc || !phys || n < 0 || (n > 0 && (!h_ins || !h_n || !h_out))) { set_error("fvg_bc_pointwise: bad argument"); return FVG_ERR_INVALID; }
+	if(bc->type < 0 || bc->type > 7 || bc->type == PERIODIC_BC) { set_error("fvg_bc_pointwise: boundary condition type not available"); return FVG_ERR_UNSUPPORTED; }
+	GasParams G = make_gas(*phys, 0.0);
+	G.nbc = 1; G.bc[0].tag = bc->tag; G.bc[0].type = bc->type; G.bc[0].v0 = bc->vals[0]; G.bc[0].v1 = bc->vals[1];
+	DevBuf a, c, o;
+	int rc;
+	if((rc = a.put(h_ins, 4*(size_t)n)) || (rc = c.put(h_n, 2*(size_t)n)) || (rc = o.put(nullptr, 4*(size_t)n))) return rc;
+	if((rc = launch_pointwise_bc(G, n, a.p, c.p, o.p, nullptr)) != 0) return rc;
+	FVG_CUDA(cudaDeviceSynchronize());
+	return o.get(h_out, 4*(size_t)n);
+}
+
+int fvg_viscous_flux_pointwise(const fvg_physics *phys, int order2, int n, const double *h_n,
+                               const double *h_rcl, const double *h_rcr, const double *h_ucl,
+                               const double *h_ucr, const double *h_gl, const double *h_gr,
+                               const double *h_ul, const double *h_ur, double *h_out)
+{
+	if(!phys || n < 0 || (n > 0 && (!h_n || !h_rcl || !h_rcr || !h_ucl || !h_ucr || !h_ul || !h_ur || !h_out)) ||
+	   (order2 && n > 0 && (!h_gl || !h_gr))) { set_error("fvg_viscous_flux_pointwise: bad argument"); return FVG_ERR_INVALID; }
+	const GasParams G = make_gas(*phys, 0.0);
+	DevBuf nn, rl, rr, cl, cr, gl, gr, ul, ur, o;
+	int rc;
+	const size_t N = n;
+	if((rc = nn.put(h_n, 2*N)) || (rc = rl.put(h_rcl, 2*N)) || (rc = rr.put(h_rcr, 2*N)) || (rc = cl.put(h_ucl, 4*N)) ||
+	   (rc = cr.put(h_ucr, 4*N)) || (rc = gl.put(order2 ? h_gl : nullptr, 8*N)) || (rc = gr.put(order2 ? h_gr : nullptr, 8*N)) ||
+	   (rc = ul.put(h_ul, 4*N)) || (rc = ur.put(h_ur, 4*N)) || (rc = o.put(nullptr, 4*N))) return rc;
+	if((rc = launch_pointwise_visc(G, order2 != 0, phys->const_visc != 0, n, nn.p, rl.p, rr.p, cl.p, cr.p, gl.p, gr.p, ul.p, ur.p, o.p, nullptr)) != 0) return rc;
+	FVG_CUDA(cudaDeviceSynchronize());
+	return o.get(h_out, 4*N);
+}
+
+int fvg_freestream(const fvg_physics *phys, double *h_uinf4)
+{
+	if(!phys || !h_uinf4) { set_error("fvg_freestream: null argument"); return FVG_ERR_INVALID; }
+	const GasParams G = make_gas(*phys, 0.0);
+	for(int k = 0; k < 4; k++) h_uinf4[k] = G.uinf[k];
+	return 0;
+}
+
+} // extern "C"

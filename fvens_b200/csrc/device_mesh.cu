@@ -1,0 +1,396 @@
+/* Device mesh construction: cell renumbering (Hilbert curve / reverse Cuthill-McKee), tiling, the
+ * per-tile face streams with their edge colouring, geometry precomputation, upload.
+ *
+ * Geometry restated from the reference (src/ relative): cell centres mesh/mesh.cpp:317-328, face
+ * midpoints and ghost centres spatial/aspatial.cpp:37-119, least-squares matrices
+ * spatial/agradientschemes.cpp:219-317, Venkatakrishnan length spatial/limitedlinearreconstruction.cpp:189-205.
+ * Orientation (left/right cell, normal) of every face is carried over from the reference numbering
+ * and is NOT re-derived from the device numbering.
+ */
+#include "engine.hpp"
+#include <algorithm>
+#include <numeric>
+#include <cmath>
+#include <cstring>
+#include <queue>
+
+namespace fvg {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+const std::string &last_error() { return g_last_error; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+	g_last_error = std::string("CUDA error '") + cudaGetErrorString(e) + "' in " + what + " at " + file
+	               + ":" + std::to_string(line);
+	return FVG_ERR_CUDA;
+}
+
+/// Hilbert curve index of (x,y) on a 2^order x 2^order grid
+static inline uint64_t hilbert_d(uint32_t x, uint32_t y, int order)
+{
+	const uint32_t n = 1u << order;
+	uint64_t d = 0;
+	for(uint32_t s = n >> 1; s > 0; s >>= 1) {
+		const uint32_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
+		d += (uint64_t)s*s*((3*rx) ^ ry);
+		if(ry == 0) {
+			if(rx == 1) { x = n-1-x; y = n-1-y; }
+			std::swap(x, y);
+		}
+	}
+	return d;
+}
+
+void hilbert_order(int n, const double *rc, std::vector<int> &new2old)
+{
+	double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+	for(int i = 0; i < n; i++)
+		for(int d = 0; d < 2; d++) { lo[d] = std::min(lo[d], rc[2*i+d]); hi[d] = std::max(hi[d], rc[2*i+d]); }
+	const int order = 20;
+	const double span = std::max(std::max(hi[0]-lo[0], hi[1]-lo[1]), 1e-300);
+	const double scale = ((double)((1u << order) - 1))/span;
+	std::vector<std::pair<uint64_t,int>> keys((size_t)n);
+	for(int i = 0; i < n; i++) {
+		const uint32_t x = (uint32_t)((rc[2*i]-lo[0])*scale), y = (uint32_t)((rc[2*i+1]-lo[1])*scale);
+		keys[i] = std::make_pair(hilbert_d(x, y, order), i);
+	}
+	std::sort(keys.begin(), keys.end());
+	new2old.resize(n);
+	for(int i = 0; i < n; i++) new2old[i] = keys[i].second;
+}
+
+/// Reverse Cuthill-McKee on the cell adjacency graph (esuel), components started from a
+/// minimum-degree cell. perm[new] = old.
+void rcm_order(int n, int mw, const int *esuel, const int *nnode, std::vector<int> &new2old)
+{
+	std::vector<int> deg(n, 0);
+	for(int i = 0; i < n; i++)
+		for(int j = 0; j < nnode[i]; j++) { const int e = esuel[(size_t)i*mw+j]; if(e >= 0 && e < n) deg[i]++; }
+	std::vector<int> order_by_deg(n);
+	std::iota(order_by_deg.begin(), order_by_deg.end(), 0);
+	std::stable_sort(order_by_deg.begin(), order_by_deg.end(), [&](int a, int b){ return deg[a] < deg[b]; });
+	std::vector<char> seen(n, 0);
+	std::vector<int> cm; cm.reserve(n);
+	for(int s : order_by_deg) {
+		if(seen[s]) continue;
+		seen[s] = 1;
+		size_t head = cm.size();
+		cm.push_back(s);
+		while(head < cm.size()) {
+			const int c = cm[head++];
+			int nb[4], k = 0;
+			for(int j = 0; j < nnode[c]; j++) {
+				const int e = esuel[(size_t)c*mw+j];
+				if(e >= 0 && e < n && !seen[e]) { seen[e] = 1; nb[k++] = e; }
+			}
+			for(int p = 1; p < k; p++)     // insertion sort by (degree, index); k <= 4
+				for(int q = p; q > 0 && (deg[nb[q]] < deg[nb[q-1]] || (deg[nb[q]] == deg[nb[q-1]] && nb[q] < nb[q-1])); q--)
+					std::swap(nb[q], nb[q-1]);
+			for(int q = 0; q < k; q++) cm.push_back(nb[q]);
+		}
+	}
+	new2old.assign(cm.rbegin(), cm.rend());
+}
+
+template <typename T>
+static int upload(fvg_mesh *m, const std::vector<T> &h, const T **dptr)
+{
+	if(m->device < 0) { *dptr = nullptr; return 0; }   // host-only inspection build
+	void *p = nullptr;
+	const size_t bytes = std::max<size_t>(h.size(), 1)*sizeof(T);
+	FVG_CUDA(cudaMalloc(&p, bytes));
+	m->allocs.push_back(p);
+	if(!h.empty()) FVG_CUDA(cudaMemcpy(p, h.data(), h.size()*sizeof(T), cudaMemcpyHostToDevice));
+	*dptr = static_cast<const T*>(p);
+	return 0;
+}
+
+static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m)
+{
+	const int n = hm->nelem, nb = hm->nbface, nf = hm->naface, mw = hm->maxnnode;
+	if(n <= 0 || nf <= 0 || !hm->coords || !hm->inpoel || !hm->nnode || !hm->esuel || !hm->elemface ||
+	   !hm->intfac || !hm->facemetric || !hm->area || (nb > 0 && !hm->btags)) {
+		set_error("fvg_mesh_create: incomplete host mesh");
+		return FVG_ERR_INVALID;
+	}
+	if(hm->nconnface != 0) {
+		set_error("fvg_mesh_create: connectivity faces are handled by the partitioned-mesh entry point");
+		return FVG_ERR_UNSUPPORTED;
+	}
+	if(mw < 3 || mw > 4) { set_error("fvg_mesh_create: maxnnode must be 3 or 4"); return FVG_ERR_INVALID; }
+	int TC = opts && opts->tile_cells > 0 ? opts->tile_cells : 512;
+	if(TC % 32 != 0 || TC > 2048) { set_error("fvg_mesh_create: tile_cells must be a multiple of 32, <= 2048"); return FVG_ERR_INVALID; }
+	const int reorder = opts ? opts->reorder : FVG_REORDER_NONE;
+
+	// ---- geometry in reference numbering
+	std::vector<double> rc(2*(size_t)n);
+	for(int i = 0; i < n; i++)
+		for(int d = 0; d < 2; d++) {
+			double c = 0;
+			for(int j = 0; j < hm->nnode[i]; j++) c += hm->coords[2*(size_t)hm->inpoel[(size_t)i*mw+j]+d];
+			rc[2*(size_t)i+d] = c/(double)hm->nnode[i];
+		}
+
+	// ---- permutation
+	std::vector<int> &new2old = m->h_new2old, &old2new = m->h_old2new;
+	if(reorder == FVG_REORDER_HILBERT) hilbert_order(n, rc.data(), new2old);
+	else if(reorder == FVG_REORDER_RCM) rcm_order(n, mw, hm->esuel, hm->nnode, new2old);
+	else if(reorder == FVG_REORDER_NONE) { new2old.resize(n); std::iota(new2old.begin(), new2old.end(), 0); }
+	else { set_error("fvg_mesh_create: unknown reorder option"); return FVG_ERR_INVALID; }
+	old2new.resize(n);
+	for(int i = 0; i < n; i++) old2new[new2old[i]] = i;
+	m->identity_perm = true;
+	for(int i = 0; i < n; i++) if(new2old[i] != i) { m->identity_perm = false; break; }
+	m->reorder = reorder;
+
+	const int ntile = (n + TC - 1)/TC;
+
+	// ---- face streams: count, fill in reference face order, colour, sort by colour
+	std::vector<int> fsoff((size_t)ntile+1, 0);
+	auto faceL = [&](int f) { return old2new[hm->intfac[4*(size_t)f]]; };
+	auto faceR = [&](int f) { return f < nb ? -2 - f : old2new[hm->intfac[4*(size_t)f+1]]; };
+	long long distsum = 0;
+	for(int f = 0; f < nf; f++) {
+		const int L = faceL(f), R = faceR(f);
+		fsoff[L/TC+1]++;
+		if(R >= 0) {
+			if(R/TC != L/TC) fsoff[R/TC+1]++;
+			distsum += std::abs(L-R);
+		}
+	}
+	for(int t = 0; t < ntile; t++) fsoff[t+1] += fsoff[t];
+	const int ns = fsoff[ntile];
+	m->ncut_dup = ns - nf;
+	m->mean_nbr_dist = nf > nb ? (double)distsum/(double)(nf-nb) : 0.0;
+
+	std::vector<int> sface((size_t)ns);        // reference face of each entry, -1-f for duplicates
+	{
+		std::vector<int> pos(fsoff.begin(), fsoff.end()-1);
+		for(int f = 0; f < nf; f++) {
+			const int L = faceL(f), R = faceR(f);
+			sface[pos[L/TC]++] = f;
+			if(R >= 0 && R/TC != L/TC) sface[pos[R/TC]++] = -1-f;
+		}
+	}
+	std::vector<int> fcoloff((size_t)ntile*(MAXCOL+1), 0);
+	std::vector<int> scolour((size_t)ns);
+	m->max_colours = 0;
+	{
+		std::vector<unsigned char> used(TC);
+		std::vector<int> tmp;
+		for(int t = 0; t < ntile; t++) {
+			const int c0 = t*TC, e0 = fsoff[t], e1 = fsoff[t+1];
+			std::fill(used.begin(), used.end(), 0);
+			int cnt[MAXCOL] = {0};
+			for(int e = e0; e < e1; e++) {
+				const int f = sface[e] >= 0 ? sface[e] : -1-sface[e];
+				const int L = faceL(f), R = faceR(f);
+				unsigned mask = 0;
+				if(L/TC == t) mask |= used[L-c0];
+				if(R >= 0 && R/TC == t) mask |= used[R-c0];
+				int c = 0;
+				while(mask & (1u << c)) c++;
+				if(c >= MAXCOL) { set_error("fvg_mesh_create: edge colouring needs more than 8 colours"); return FVG_ERR_INVALID; }
+				if(L/TC == t) used[L-c0] |= (unsigned char)(1u << c);
+				if(R >= 0 && R/TC == t) used[R-c0] |= (unsigned char)(1u << c);
+				scolour[e] = c; cnt[c]++;
+				m->max_colours = std::max(m->max_colours, c+1);
+			}
+			int *co = &fcoloff[(size_t)t*(MAXCOL+1)];
+			co[0] = e0;
+			for(int c = 0; c < MAXCOL; c++) co[c+1] = co[c] + cnt[c];
+			// stable counting sort of the segment by colour
+			tmp.assign(sface.begin()+e0, sface.begin()+e1);
+			int pos[MAXCOL];
+			for(int c = 0; c < MAXCOL; c++) pos[c] = co[c];
+			std::vector<int> ctmp(scolour.begin()+e0, scolour.begin()+e1);
+			for(int k = 0; k < e1-e0; k++) { const int c = ctmp[k]; sface[pos[c]] = tmp[k]; scolour[pos[c]] = c; pos[c]++; }
+		}
+	}
+
+	// ---- per-entry arrays
+	std::vector<int> fL((size_t)ns), fR((size_t)ns);
+	std::vector<double2> fn((size_t)ns), fgr((size_t)ns);
+	std::vector<double> flen((size_t)ns);
+	std::vector<int> own_entry((size_t)nf), dup_entry((size_t)nf, -1);
+	m->h_fref.resize(ns); m->h_fcolour = scolour; m->h_ftile.resize(ns);
+	for(int t = 0; t < ntile; t++)
+		for(int e = fsoff[t]; e < fsoff[t+1]; e++) {
+			const int f = sface[e] >= 0 ? sface[e] : -1-sface[e];
+			fL[e] = faceL(f); fR[e] = faceR(f);
+			fn[e] = make_double2(hm->facemetric[3*(size_t)f], hm->facemetric[3*(size_t)f+1]);
+			flen[e] = hm->facemetric[3*(size_t)f+2];
+			const int p0 = hm->intfac[4*(size_t)f+2], p1 = hm->intfac[4*(size_t)f+3];
+			double g[2];
+			for(int d = 0; d < 2; d++) {
+				double s = 0;
+				s += hm->coords[2*(size_t)p0+d];
+				s += hm->coords[2*(size_t)p1+d];
+				g[d] = s/2;
+			}
+			fgr[e] = make_double2(g[0], g[1]);
+			if(sface[e] >= 0) own_entry[f] = e; else dup_entry[f] = e;
+			m->h_fref[e] = sface[e]; m->h_ftile[e] = t;
+		}
+
+	// ---- per-cell arrays in device order
+	std::vector<int4> nbr((size_t)n), cface((size_t)n);
+	std::vector<double2> drc((size_t)n);
+	std::vector<double> area((size_t)n), clength((size_t)n);
+	for(int i = 0; i < n; i++) {
+		const int o = new2old[i];
+		int a[4] = {-1,-1,-1,-1}, c[4] = {0,0,0,0};
+		for(int j = 0; j < hm->nnode[o]; j++) {
+			const int e = hm->esuel[(size_t)o*mw+j];
+			const int f = hm->elemface[(size_t)o*mw+j];
+			if(e < 0 || f < 0 || f >= nf) { set_error("fvg_mesh_create: inconsistent esuel/elemface"); return FVG_ERR_INVALID; }
+			a[j] = e < n ? old2new[e] : -2 - (e - n);
+			if(e >= n && (e-n != f || f >= nb)) { set_error("fvg_mesh_create: boundary ghost index does not match its face"); return FVG_ERR_INVALID; }
+			const bool isL = hm->intfac[4*(size_t)f] == o;
+			if(!isL && (f < nb || hm->intfac[4*(size_t)f+1] != o)) { set_error("fvg_mesh_create: elemface/intfac mismatch"); return FVG_ERR_INVALID; }
+			// the copy of the face that lives in this cell's tile
+			int entry = own_entry[f];
+			if(!isL && dup_entry[f] >= 0) entry = dup_entry[f];
+			c[j] = entry | (isL ? 0 : (int)0x80000000u);
+		}
+		nbr[i] = make_int4(a[0], a[1], a[2], a[3]);
+		cface[i] = make_int4(c[0], c[1], c[2], c[3]);
+		drc[i] = make_double2(rc[2*(size_t)o], rc[2*(size_t)o+1]);
+		area[i] = hm->area[o];
+		double l2 = 0;
+		const int nn = hm->nnode[o];
+		for(int j = 0; j < nn; j++) {
+			const int p = hm->inpoel[(size_t)o*mw+j], q = hm->inpoel[(size_t)o*mw+(j+1)%nn];
+			double s = 0;
+			for(int d = 0; d < 2; d++) { const double t = hm->coords[2*(size_t)p+d] - hm->coords[2*(size_t)q+d]; s += t*t; }
+			if(l2 < s) l2 = s;
+		}
+		clength[i] = std::sqrt(l2);
+	}
+
+	// ---- boundary arrays (reference boundary-face order)
+	std::vector<int> bcell((size_t)nb), bentry((size_t)nb);
+	std::vector<double2> rcbp((size_t)nb);
+	m->h_btag.resize(nb);
+	for(int b = 0; b < nb; b++) {
+		const int o = hm->intfac[4*(size_t)b];
+		bcell[b] = old2new[o];
+		bentry[b] = own_entry[b];
+		m->h_btag[b] = hm->btags[(size_t)b*hm->nbtag];
+		const double2 mid = fgr[own_entry[b]];
+		rcbp[b] = make_double2(2.0*mid.x - rc[2*(size_t)o], 2.0*mid.y - rc[2*(size_t)o+1]);
+	}
+
+	// ---- least-squares matrices: accumulate in reference face order, invert as adj/det
+	std::vector<double4> V((size_t)n);
+	{
+		std::vector<double> A(4*(size_t)n, 0.0);
+		for(int f = 0; f < nf; f++) {
+			const int ie = hm->intfac[4*(size_t)f];
+			double dr[2];
+			if(f < nb) { dr[0] = rc[2*(size_t)ie] - rcbp[f].x; dr[1] = rc[2*(size_t)ie+1] - rcbp[f].y; }
+			else { const int je = hm->intfac[4*(size_t)f+1]; dr[0] = rc[2*(size_t)ie] - rc[2*(size_t)je]; dr[1] = rc[2*(size_t)ie+1] - rc[2*(size_t)je+1]; }
+			double w2 = 0;
+			for(int d = 0; d < 2; d++) w2 += dr[d]*dr[d];
+			w2 = 1.0/w2;
+			for(int p = 0; p < 2; p++) for(int q = 0; q < 2; q++) {
+				A[4*(size_t)ie+2*p+q] += w2*dr[p]*dr[q];
+				if(f >= nb) A[4*(size_t)hm->intfac[4*(size_t)f+1]+2*p+q] += w2*dr[p]*dr[q];
+			}
+		}
+		for(int i = 0; i < n; i++) {
+			const int o = new2old[i];
+			const double a = A[4*(size_t)o], b = A[4*(size_t)o+1], c = A[4*(size_t)o+2], d = A[4*(size_t)o+3];
+			const double idet = 1.0/(a*d - c*b);
+			V[i] = make_double4(d*idet, -b*idet, -c*idet, a*idet);
+		}
+	}
+
+	// ---- upload
+	DMesh &D = m->d;
+	D.ncell = n; D.nbface = nb; D.naface = nf; D.ntile = ntile; D.TC = TC; D.nstream = ns;
+	int rcode;
+#define UP(vec, field) if((rcode = upload(m, vec, &D.field)) != 0) return rcode;
+	UP(nbr, nbr) UP(cface, cface) UP(drc, rc) UP(area, area) UP(V, wlsV) UP(clength, clength)
+	UP(fsoff, fsoff) UP(fcoloff, fcoloff) UP(fL, fL) UP(fR, fR) UP(fn, fn) UP(flen, flen) UP(fgr, fgr)
+	UP(m->h_fref, fref) UP(bcell, bcell) UP(bentry, bentry) UP(m->h_btag, btag) UP(rcbp, rcbp)
+	if(m->identity_perm) { D.new2old = nullptr; D.old2new = nullptr; }
+	else { UP(new2old, new2old) UP(old2new, old2new) }
+#undef UP
+	return 0;
+}
+
+} // namespace fvg
+
+using namespace fvg;
+
+extern "C" {
+
+const char *fvg_last_error(void) { return last_error().c_str(); }
+
+int fvg_device_count(int *count)
+{
+	if(!count) { set_error("fvg_device_count: null argument"); return FVG_ERR_INVALID; }
+	*count = 0;
+	FVG_CUDA(cudaGetDeviceCount(count));
+	if(*count <= 0) { set_error("no CUDA device visible"); return FVG_ERR_CUDA; }
+	return 0;
+}
+
+int fvg_mesh_create(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh **out)
+{
+	if(!hm || !out) { set_error("fvg_mesh_create: null argument"); return FVG_ERR_INVALID; }
+	*out = nullptr;
+	if(opts && opts->device >= 0) FVG_CUDA(cudaSetDevice(opts->device));
+	fvg_mesh *m = new fvg_mesh;
+	if(opts && opts->device == -2) m->device = -2;
+	else {
+		const cudaError_t e = cudaGetDevice(&m->device);
+		if(e != cudaSuccess) { delete m; return cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__); }
+	}
+	int rc;
+	try { rc = build(hm, opts, m); }
+	catch(std::exception &ex) { set_error(std::string("fvg_mesh_create: ") + ex.what()); rc = FVG_ERR_INVALID; }
+	if(rc != 0) { fvg_mesh_destroy(m); return rc; }
+	*out = m;
+	return 0;
+}
+
+void fvg_mesh_destroy(fvg_mesh *m)
+{
+	if(!m) return;
+	for(void *p : m->allocs) cudaFree(p);
+	delete m;
+}
+
+int fvg_mesh_get_info(const fvg_mesh *m, fvg_mesh_info *info)
+{
+	if(!m || !info) { set_error("fvg_mesh_get_info: null argument"); return FVG_ERR_INVALID; }
+	info->ncell = m->d.ncell; info->nbface = m->d.nbface; info->naface = m->d.naface;
+	info->ntile = m->d.ntile; info->tile_cells = m->d.TC; info->nstream = m->d.nstream;
+	info->ncut_dup = m->ncut_dup; info->max_colours = m->max_colours; info->reorder = m->reorder;
+	info->mean_neighbour_distance = m->mean_nbr_dist;
+	return 0;
+}
+
+int fvg_mesh_permutation(const fvg_mesh *m, int *cell_new2old)
+{
+	if(!m || !cell_new2old) { set_error("fvg_mesh_permutation: null argument"); return FVG_ERR_INVALID; }
+	std::memcpy(cell_new2old, m->h_new2old.data(), sizeof(int)*m->h_new2old.size());
+	return 0;
+}
+
+int fvg_mesh_stream(const fvg_mesh *m, int *entry_face, int *entry_colour, int *entry_tile)
+{
+	if(!m) { set_error("fvg_mesh_stream: null argument"); return FVG_ERR_INVALID; }
+	for(int e = 0; e < m->d.nstream; e++) {
+		if(entry_face) entry_face[e] = m->h_fref[e] >= 0 ? m->h_fref[e] : -1-m->h_fref[e];
+		if(entry_colour) entry_colour[e] = m->h_fcolour[e];
+		if(entry_tile) entry_tile[e] = m->h_ftile[e];
+	}
+	return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,183 @@
+/* Internal declarations shared by the translation units of libfvens_b200.so. Not part of the ABI. */
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <cstdint>
+#include "gas.cuh"
+#include "../../include/fvens_b200.h"
+
+namespace fvg {
+
+constexpr int MAXCOL = 8;          ///< greedy edge colouring of a degree-4 graph needs at most 7
+constexpr int FACE_BLOCK = 256;    ///< threads per CTA of the face kernel
+constexpr int CELL_BLOCK = 128;    ///< threads per CTA of the cell kernels
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define FVG_CUDA(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) \
+	return ::fvg::cuda_fail(e_, #call, __FILE__, __LINE__); } while(0)
+
+/// Device-resident mesh in device (renumbered) cell order. All pointers are device memory.
+struct DMesh {
+	int ncell, nbface, naface, ntile, TC, nstream;
+	// per cell
+	const int4 *nbr;        ///< local face j -> neighbour cell; -1 none; <= -2 boundary face b = -2-v
+	const int4 *cface;      ///< local face j -> stream entry (own tile's copy); bit 31 set if the cell is the entry's right cell
+	const double2 *rc;      ///< cell centres
+	const double *area;
+	const double4 *wlsV;    ///< inverse least-squares matrices (V00, V01, V10, V11)
+	const double *clength;  ///< Venkatakrishnan length scale (longest edge)
+	// per tile
+	const int *fsoff;       ///< [ntile+1] stream segment of each tile
+	const int *fcoloff;     ///< [ntile][MAXCOL+1] colour boundaries inside the segment (absolute entry ids)
+	// per stream entry
+	const int *fL, *fR;     ///< left / right cell; fR <= -2 marks boundary face b = -2-fR
+	const double2 *fn;      ///< unit normal, left -> right
+	const double *flen;
+	const double2 *fgr;     ///< face midpoint
+	const int *fref;        ///< reference face id (intfac index); the duplicate copy of a cut face carries -1-id
+	// per boundary face (reference order)
+	const int *bcell;       ///< device index of the interior cell
+	const int *bentry;      ///< stream entry
+	const int *btag;        ///< first boundary marker
+	const double2 *rcbp;    ///< ghost cell centre
+	// permutation (null when identity)
+	const int *new2old;
+	const int *old2new;
+};
+
+} // namespace fvg
+
+/// Opaque handles of the ABI
+struct fvg_umesh;
+
+struct fvg_mesh {
+	fvg::DMesh d;
+	int device = 0;
+	int reorder = 0;
+	bool identity_perm = true;
+	int ncut_dup = 0, max_colours = 0;
+	double mean_nbr_dist = 0;
+	std::vector<void*> allocs;                 ///< everything cudaMalloc'ed for this mesh
+	// host copies kept for the test hooks and for flow set-up
+	std::vector<int> h_new2old, h_old2new;
+	std::vector<int> h_fref, h_fcolour, h_ftile;
+	std::vector<int> h_btag;
+};
+
+namespace fvg {
+
+/// Which scratch arrays a flow needs
+struct FlowPlan {
+	int flux, gradient, recon, order2, bnd_policy, visc;   // visc = ViscMode
+	bool need_lg;     ///< limited (or plain) gradients consumed by the face kernel's linear reconstruction
+	bool need_gu;     ///< unlimited gradients (MUSCL, WENO input, viscous flux)
+};
+
+} // namespace fvg
+
+struct fvg_flow {
+	fvg_mesh *mesh = nullptr;
+	fvg::GasParams gas;
+	fvg::FlowPlan plan;
+	fvg_physics phys;
+	int *d_bbc = nullptr;          ///< [nbface] index into gas.bc
+	double *d_lg = nullptr;        ///< [ncell][8] limited gradients
+	double *d_gu = nullptr;        ///< [ncell][8] unlimited gradients
+	double *d_uperm = nullptr;     ///< [ncell][4] scratch state in device order (non-identity permutations)
+	double *d_rperm = nullptr;     ///< [ncell][4] scratch residual in device order
+	double *d_dtperm = nullptr;    ///< [ncell]
+	double *d_u2 = nullptr;        ///< [ncell][4] second state buffer for the fused step
+	double *d_partial = nullptr;   ///< [ntile] per-tile partial norms
+	double *d_norm = nullptr;      ///< [1]
+	double *h_norm = nullptr;      ///< pinned [1]
+	double *d_hu = nullptr, *d_hr = nullptr, *d_hdt = nullptr;   ///< staging for the host-buffer entry point
+	std::vector<void*> allocs;
+	long long launches = 0;
+	// optional per-pass timing (CUDA events on the launching stream)
+	bool timing = false;
+	std::vector<cudaEvent_t> ev;   ///< triples: before pass A, between A and B, after B
+};
+
+namespace fvg {
+
+// ---- launchers (kernels_cell.cu) ---------------------------------------------------------------
+struct CellArgs {
+	DMesh m;
+	GasParams gas;
+	const int *bbc;
+	const double *u;       ///< [ncell][4] conserved (or primitive when prim_in)
+	const double *ug;      ///< [nbface][4] primitive ghost states (prim_in only)
+	const double *gin;     ///< given gradients (GRAD_GIVEN only)
+	double *lg;            ///< out: limited gradients (may be null)
+	double *gu;            ///< out: unlimited gradients (may be null)
+	int bnd_policy;
+};
+int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaStream_t s);
+int launch_weno_kernel(const DMesh &m, double lambda, const double *gu, double *lg, cudaStream_t s);
+
+struct FaceValArgs {
+	DMesh m;
+	const double *up;      ///< primitive cell states, device order
+	const double *ug;      ///< primitive ghost states [nbface][4]
+	const double *g;       ///< gradients used for extrapolation (limited, or unlimited for MUSCL)
+	double *ufl, *ufr;     ///< [naface][4], reference face order
+	int muscl;
+};
+int launch_face_values(const FaceValArgs &a, cudaStream_t s);
+
+int launch_permute_rows(const double *src, double *dst, const int *idx, int n, int width, bool gather,
+                        bool accumulate, cudaStream_t s);
+int launch_boundary_states(const DMesh &m, const GasParams &g, const int *bbc, const double *ins,
+                           double *gs, cudaStream_t s);
+int launch_cons2prim(const GasParams &g, const double *u, double *p, int n, cudaStream_t s);
+int launch_boundary_prim_ghosts(const DMesh &m, const GasParams &g, const int *bbc, const double *u,
+                                double *ug, bool prim_out, cudaStream_t s);
+int launch_final_norm(const double *partial, int n, double *out, cudaStream_t s);
+int launch_surface_data(const DMesh &m, const GasParams &g, double aoa, const double *u, const double *grads,
+                        int marker, double *out4, cudaStream_t s);
+int launch_entropy(const DMesh &m, const GasParams &g, const double *u, double *out, cudaStream_t s);
+int launch_pointwise_flux(int flux, const GasParams &g, int n, const double *ul, const double *ur,
+                          const double *nrm, double *out, cudaStream_t s);
+int launch_pointwise_bc(const GasParams &g, int n, const double *ins, const double *nrm, double *out,
+                        cudaStream_t s);
+int launch_pointwise_visc(const GasParams &g, bool order2, bool constvisc, int n, const double *nrm,
+                          const double *rcl, const double *rcr, const double *ucl, const double *ucr,
+                          const double *gl, const double *gr, const double *ul, const double *ur,
+                          double *out, cudaStream_t s);
+
+// ---- face kernel (face_kernel.cuh, one translation unit per flux) -------------------------------
+enum FaceRecon { FR_FIRST = 0, FR_LINEAR = 1, FR_MUSCL = 2 };
+enum FaceEpilogue { EP_RESIDUAL = 0, EP_STEP = 1 };
+
+struct FaceArgs {
+	DMesh m;
+	GasParams gas;
+	const int *bbc;
+	const double *u;       ///< [ncell][4] conserved, device order
+	const double *lg;      ///< gradients for the linear reconstruction
+	const double *gu;      ///< unlimited gradients (MUSCL, viscous)
+	// epilogue
+	int epilogue;          ///< FaceEpilogue
+	int accumulate;        ///< EP_RESIDUAL: add into res instead of overwriting
+	int gettimesteps;
+	double *res;           ///< [ncell][4]
+	double *dtm;           ///< [ncell]
+	double cfl;            ///< EP_STEP
+	double *unew;          ///< EP_STEP: [ncell][4]
+	double *partial;       ///< EP_STEP: [ntile] sum of r_E^2*area
+};
+typedef int (*FaceLauncher)(int recon, int visc, const FaceArgs &a, cudaStream_t s);
+int launch_face_llf(int recon, int visc, const FaceArgs &a, cudaStream_t s);
+int launch_face_vanleer(int recon, int visc, const FaceArgs &a, cudaStream_t s);
+int launch_face_ausm(int recon, int visc, const FaceArgs &a, cudaStream_t s);
+int launch_face_ausmplus(int recon, int visc, const FaceArgs &a, cudaStream_t s);
+int launch_face_roe(int recon, int visc, const FaceArgs &a, cudaStream_t s);
+int launch_face_hll(int recon, int visc, const FaceArgs &a, cudaStream_t s);
+int launch_face_hllc(int recon, int visc, const FaceArgs &a, cudaStream_t s);
+
+GasParams make_gas(const fvg_physics &p, double limiter_param);
+
+} // namespace fvg

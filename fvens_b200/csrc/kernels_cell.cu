@@ -1,0 +1,584 @@
+/* Cell-centred kernels: gradients (Green-Gauss, weighted least squares), slope limiters
+ * (Barth-Jespersen, Venkatakrishnan, WENO), the unfused plug-in kernels behind fvg_gradients /
+ * fvg_face_values, and the small utility kernels. Reference restated (src/ relative):
+ *   spatial/agradientschemes.cpp:62-214 (GG), 219-440 (WLS)
+ *   spatial/limitedlinearreconstruction.cpp:28-105 (WENO), 117-176 (BJ), 179-268 (Venkatakrishnan)
+ *   spatial/areconstruction.cpp:52-103, spatial/musclreconstruction.cpp:35-130
+ *   spatial/flow_spatial.cpp:74-112, 131-310, 659-700; spatial/aoutput.cpp:28-63
+ * The gradient + limiter pass is a cell-gather: one thread per cell walks its <= 4 faces, so there
+ * is no scatter at all (the reference scatters from faces with omp atomics).
+ */
+#include "engine.hpp"
+#include "face_kernel.cuh"   // ld4 / st4 / extrapolation helpers
+
+namespace fvg {
+
+enum { GM_ZERO = 0, GM_GG = 1, GM_WLS = 2, GM_GIVEN = 3 };
+
+__device__ __forceinline__ double rsqrt_exact(double x) { return 1.0/sqrt(x); }
+enum { LM_NONE = 0, LM_BJ = 1, LM_VENKAT = 2 };
+
+template <int GRAD, int LIM, bool PRIM_IN>
+__global__ void __launch_bounds__(CELL_BLOCK)
+cell_kernel(const CellArgs A)
+{
+	const DMesh &M = A.m;
+	const int i = blockIdx.x*CELL_BLOCK + threadIdx.x;
+	if(i >= M.ncell) return;
+
+	const int4 nb4 = M.nbr[i];
+	const int4 cf4 = M.cface[i];
+	const int nb[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+	const int cf[4] = {cf4.x, cf4.y, cf4.z, cf4.w};
+	const double2 rci = M.rc[i];
+	double ui[4], pi[4];
+	ld4(A.u + 4*(size_t)i, ui);
+	if(PRIM_IN) { for(int k = 0; k < 4; k++) pi[k] = ui[k]; }
+	else cons2prim(A.gas, ui, pi);
+
+	double acc[8] = {0,0,0,0,0,0,0,0};   // GG: gradient sums; WLS: right-hand side. Index d + 2*v
+	double dmin[4] = {0,0,0,0}, dmax[4] = {0,0,0,0};
+	const double ainv = GRAD == GM_GG ? 1.0/M.area[i] : 0.0;
+
+	if(GRAD == GM_GG || GRAD == GM_WLS || LIM != LM_NONE) {
+		#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			const int nj = nb[j];
+			if(nj == -1) continue;
+			double pj[4];
+			double2 rj;
+			bool use_for_limiter = true;
+			if(nj >= 0) {
+				double uj[4];
+				ld4(A.u + 4*(size_t)nj, uj);
+				if(PRIM_IN) { for(int k = 0; k < 4; k++) pj[k] = uj[k]; }
+				else cons2prim(A.gas, uj, pj);
+				rj = M.rc[nj];
+			} else {
+				const int b = -2 - nj;
+				if(PRIM_IN) ld4(A.ug + 4*(size_t)b, pj);
+				else {
+					const double2 n = M.fn[cf[j] & 0x7fffffff];
+					double gs[4];
+					ghost_state(A.gas, A.gas.bc[A.bbc[b]], ui, n.x, n.y, gs);
+					cons2prim(A.gas, gs, pj);
+				}
+				rj = M.rcbp[b];
+				use_for_limiter = A.bnd_policy == 0;
+			}
+			if(GRAD == GM_WLS) {
+				const double dx = rci.x - rj.x, dy = rci.y - rj.y;
+				const double w = 1.0/(dx*dx + dy*dy);
+				const double wx = w*dx, wy = w*dy;
+				#pragma unroll
+				for(int v = 0; v < 4; v++) {
+					const double du = pi[v] - pj[v];
+					acc[2*v] += wx*du;
+					acc[2*v+1] += wy*du;
+				}
+			}
+			if(GRAD == GM_GG) {
+				const int e = cf[j] & 0x7fffffff;
+				const bool isR = cf[j] < 0;
+				const double2 mid = M.fgr[e];
+				const double2 n = M.fn[e];
+				const double len = M.flen[e];
+				// inverse distances of the face midpoint to the two centres
+				const double di = rsqrt_exact((mid.x-rci.x)*(mid.x-rci.x) + (mid.y-rci.y)*(mid.y-rci.y));
+				const double dj = rsqrt_exact((mid.x-rj.x)*(mid.x-rj.x) + (mid.y-rj.y)*(mid.y-rj.y));
+				const double sgn = isR ? -1.0 : 1.0;
+				const double isum = 1.0/(di + dj);
+				#pragma unroll
+				for(int v = 0; v < 4; v++) {
+					const double ut = (pi[v]*di + pj[v]*dj)*isum*len;
+					acc[2*v] += sgn*(ut*n.x)*ainv;
+					acc[2*v+1] += sgn*(ut*n.y)*ainv;
+				}
+			}
+			if(LIM != LM_NONE && use_for_limiter) {
+				#pragma unroll
+				for(int v = 0; v < 4; v++) {
+					const double du = pj[v] - pi[v];
+					dmax[v] = fmax(dmax[v], du);
+					dmin[v] = fmin(dmin[v], du);
+				}
+			}
+		}
+	}
+
+	double g[8];
+	if(GRAD == GM_WLS) {
+		const double4 V = M.wlsV[i];
+		#pragma unroll
+		for(int v = 0; v < 4; v++) {
+			g[2*v]   = V.x*acc[2*v] + V.y*acc[2*v+1];
+			g[2*v+1] = V.z*acc[2*v] + V.w*acc[2*v+1];
+		}
+	}
+	else if(GRAD == GM_GG) { for(int k = 0; k < 8; k++) g[k] = acc[k]; }
+	else if(GRAD == GM_GIVEN) { ld4(A.gin + 8*(size_t)i, g); ld4(A.gin + 8*(size_t)i + 4, g+4); }
+	else { for(int k = 0; k < 8; k++) g[k] = 0.0; }
+
+	if(A.gu) { st4(A.gu + 8*(size_t)i, g); st4(A.gu + 8*(size_t)i + 4, g+4); }
+	if(!A.lg) return;
+
+	if(LIM != LM_NONE) {
+		double lim[4] = {1.0, 1.0, 1.0, 1.0};
+		double eps2 = 0.0;
+		if(LIM == LM_VENKAT) {
+			const double kh = A.gas.limiter_param*M.clength[i];
+			eps2 = kh*kh*kh;
+		}
+		#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			if(nb[j] == -1) continue;
+			const double2 mid = M.fgr[cf[j] & 0x7fffffff];
+			const double dx = mid.x - rci.x, dy = mid.y - rci.y;
+			#pragma unroll
+			for(int v = 0; v < 4; v++) {
+				const double uface = pi[v] + g[2*v]*dx + g[2*v+1]*dy;
+				const double dm = uface - pi[v];
+				double phi;
+				if(LIM == LM_VENKAT) {
+					const double dp = dm < 0.0 ? dmin[v] : dmax[v];
+					phi = (dp*dp + 2.0*dp*dm + eps2)/(dp*dp + dp*dm + 2.0*dm*dm + eps2);
+				} else {
+					if(dm > 0.0) phi = fmin(1.0, dmax[v]/dm);
+					else if(dm < 0.0) phi = fmin(1.0, dmin[v]/dm);
+					else phi = 1.0;
+				}
+				lim[v] = fmin(lim[v], phi);
+			}
+		}
+		#pragma unroll
+		for(int v = 0; v < 4; v++) { g[2*v] *= lim[v]; g[2*v+1] *= lim[v]; }
+	}
+	st4(A.lg + 8*(size_t)i, g); st4(A.lg + 8*(size_t)i + 4, g+4);
+}
+
+template <int GRAD, int LIM, bool PRIM_IN>
+static int launch_cell(const CellArgs &a, cudaStream_t s)
+{
+	const int nblk = (a.m.ncell + CELL_BLOCK - 1)/CELL_BLOCK;
+	cell_kernel<GRAD,LIM,PRIM_IN><<<nblk, CELL_BLOCK, 0, s>>>(a);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "cell_kernel launch", __FILE__, __LINE__);
+	return 0;
+}
+
+int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaStream_t s)
+{
+#define C(G,L,P) if(grad == G && lim == L && prim_in == P) return launch_cell<G,L,P>(a, s);
+	C(GM_ZERO,LM_NONE,false) C(GM_ZERO,LM_BJ,false) C(GM_ZERO,LM_VENKAT,false)
+	C(GM_GG,LM_NONE,false) C(GM_GG,LM_BJ,false) C(GM_GG,LM_VENKAT,false)
+	C(GM_WLS,LM_NONE,false) C(GM_WLS,LM_BJ,false) C(GM_WLS,LM_VENKAT,false)
+	C(GM_ZERO,LM_NONE,true) C(GM_GG,LM_NONE,true) C(GM_WLS,LM_NONE,true)
+	C(GM_GIVEN,LM_NONE,true) C(GM_GIVEN,LM_BJ,true) C(GM_GIVEN,LM_VENKAT,true)
+#undef C
+	set_error("cell kernel: unsupported gradient/limiter combination");
+	return FVG_ERR_INVALID;
+}
+
+// ------------------------------------------------------------------------------------------------
+// WENO: weighted average of the cell's and its interior neighbours' gradients
+
+__global__ void __launch_bounds__(CELL_BLOCK)
+weno_kernel(const DMesh M, const double lambda, const double *__restrict__ gu, double *__restrict__ lg)
+{
+	const int i = blockIdx.x*CELL_BLOCK + threadIdx.x;
+	if(i >= M.ncell) return;
+	const double epsilon = 1.0e-5;
+	const int4 nb4 = M.nbr[i];
+	const int nb[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+	double g[8], out[8], wsum[4];
+	ld4(gu + 8*(size_t)i, g); ld4(gu + 8*(size_t)i + 4, g+4);
+	#pragma unroll
+	for(int v = 0; v < 4; v++) {
+		const double q = g[2*v]*g[2*v] + g[2*v+1]*g[2*v+1] + epsilon;
+		const double q2 = q*q;
+		const double w = lambda/(q2*q2);
+		wsum[v] = w; out[2*v] = w*g[2*v]; out[2*v+1] = w*g[2*v+1];
+	}
+	#pragma unroll
+	for(int j = 0; j < 4; j++) {
+		if(nb[j] < 0) continue;
+		double h[8];
+		ld4(gu + 8*(size_t)nb[j], h); ld4(gu + 8*(size_t)nb[j] + 4, h+4);
+		#pragma unroll
+		for(int v = 0; v < 4; v++) {
+			const double q = h[2*v]*h[2*v] + h[2*v+1]*h[2*v+1] + epsilon;
+			const double q2 = q*q;
+			const double w = 1.0/(q2*q2);
+			wsum[v] += w; out[2*v] += w*h[2*v]; out[2*v+1] += w*h[2*v+1];
+		}
+	}
+	#pragma unroll
+	for(int v = 0; v < 4; v++) { out[2*v] /= wsum[v]; out[2*v+1] /= wsum[v]; }
+	st4(lg + 8*(size_t)i, out); st4(lg + 8*(size_t)i + 4, out+4);
+}
+
+int launch_weno_kernel(const DMesh &m, double lambda, const double *gu, double *lg, cudaStream_t s)
+{
+	weno_kernel<<<(m.ncell + CELL_BLOCK - 1)/CELL_BLOCK, CELL_BLOCK, 0, s>>>(m, lambda, gu, lg);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "weno_kernel launch", __FILE__, __LINE__);
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// unfused face values (plug-in parity with SolutionReconstruction::compute_face_values)
+
+__global__ void __launch_bounds__(FACE_BLOCK)
+face_values_kernel(const FaceValArgs A)
+{
+	const DMesh &M = A.m;
+	const int e = blockIdx.x*FACE_BLOCK + threadIdx.x;
+	if(e >= M.nstream) return;
+	const int L = M.fL[e], R = M.fR[e];
+	// only the copy that lives in the left cell's tile writes (duplicates carry -1-f)
+	const int f = M.fref[e];
+	if(f < 0) return;
+	const double2 gr = M.fgr[e];
+	const double2 rl = M.rc[L];
+	double pl[4], pr[4], out[4];
+	ld4(A.up + 4*(size_t)L, pl);
+	if(!A.muscl) {
+		extrapolate4(pl, A.g + 8*(size_t)L, gr.x - rl.x, gr.y - rl.y, out);
+		st4(A.ufl + 4*(size_t)f, out);
+		if(R >= 0) {
+			const double2 rr = M.rc[R];
+			ld4(A.up + 4*(size_t)R, pr);
+			extrapolate4(pr, A.g + 8*(size_t)R, gr.x - rr.x, gr.y - rr.y, out);
+			st4(A.ufr + 4*(size_t)f, out);
+		}
+	}
+	else {
+		double2 rr;
+		if(R >= 0) { ld4(A.up + 4*(size_t)R, pr); rr = M.rc[R]; }
+		else { ld4(A.ug + 4*(size_t)(-2-R), pr); rr = M.rcbp[-2-R]; }
+		const double dx = rr.x - rl.x, dy = rr.y - rl.y;
+		double g[8];
+		ld4(A.g + 8*(size_t)L, g); ld4(A.g + 8*(size_t)L + 4, g+4);
+		for(int k = 0; k < 4; k++) {
+			const double dlr = pr[k] - pl[k];
+			out[k] = pl[k] + muscl_term(2.0*(g[2*k]*dx + g[2*k+1]*dy) - dlr, dlr);
+		}
+		st4(A.ufl + 4*(size_t)f, out);
+		if(R >= 0) {
+			ld4(A.g + 8*(size_t)R, g); ld4(A.g + 8*(size_t)R + 4, g+4);
+			for(int k = 0; k < 4; k++) {
+				const double dlr = pr[k] - pl[k];
+				out[k] = pr[k] - muscl_term(2.0*(g[2*k]*dx + g[2*k+1]*dy) - dlr, dlr);
+			}
+			st4(A.ufr + 4*(size_t)f, out);
+		}
+	}
+}
+
+int launch_face_values(const FaceValArgs &a, cudaStream_t s)
+{
+	face_values_kernel<<<(a.m.nstream + FACE_BLOCK - 1)/FACE_BLOCK, FACE_BLOCK, 0, s>>>(a);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "face_values_kernel launch", __FILE__, __LINE__);
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// utilities
+
+/// gather: dst[i] = src[idx[i]]; scatter: dst[idx[i]] (+)= src[i]; rows of `width` doubles
+__global__ void permute_rows_kernel(const double *__restrict__ src, double *__restrict__ dst,
+                                    const int *__restrict__ idx, int n, int width, int gather, int accumulate)
+{
+	const long long k = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(k >= (long long)n*width) return;
+	const int i = (int)(k/width), c = (int)(k%width);
+	const int j = idx[i];
+	if(gather) dst[k] = src[(size_t)j*width + c];
+	else if(accumulate) dst[(size_t)j*width + c] += src[k];
+	else dst[(size_t)j*width + c] = src[k];
+}
+
+int launch_permute_rows(const double *src, double *dst, const int *idx, int n, int width, bool gather,
+                        bool accumulate, cudaStream_t s)
+{
+	const long long tot = (long long)n*width;
+	if(tot == 0) return 0;
+	permute_rows_kernel<<<(unsigned)((tot + 255)/256), 256, 0, s>>>(src, dst, idx, n, width, gather, accumulate);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "permute_rows launch", __FILE__, __LINE__);
+	return 0;
+}
+
+__global__ void boundary_states_kernel(const DMesh M, const GasParams G, const int *__restrict__ bbc,
+                                       const double *__restrict__ ins, double *__restrict__ gs)
+{
+	const int b = blockIdx.x*blockDim.x + threadIdx.x;
+	if(b >= M.nbface) return;
+	const double2 n = M.fn[M.bentry[b]];
+	double in[4], out[4];
+	ld4(ins + 4*(size_t)b, in);
+	ghost_state(G, G.bc[bbc[b]], in, n.x, n.y, out);
+	st4(gs + 4*(size_t)b, out);
+}
+
+int launch_boundary_states(const DMesh &m, const GasParams &g, const int *bbc, const double *ins,
+                           double *gs, cudaStream_t s)
+{
+	if(m.nbface == 0) return 0;
+	boundary_states_kernel<<<(m.nbface + 127)/128, 128, 0, s>>>(m, g, bbc, ins, gs);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "boundary_states launch", __FILE__, __LINE__);
+	return 0;
+}
+
+/// ghost state of each boundary face from the adjacent CELL state (device order), conserved or primitive
+__global__ void boundary_cell_ghosts_kernel(const DMesh M, const GasParams G, const int *__restrict__ bbc,
+                                            const double *__restrict__ u, double *__restrict__ ug, int prim_out)
+{
+	const int b = blockIdx.x*blockDim.x + threadIdx.x;
+	if(b >= M.nbface) return;
+	const double2 n = M.fn[M.bentry[b]];
+	double in[4], out[4];
+	ld4(u + 4*(size_t)M.bcell[b], in);
+	ghost_state(G, G.bc[bbc[b]], in, n.x, n.y, out);
+	if(prim_out) { double p[4]; cons2prim(G, out, p); st4(ug + 4*(size_t)b, p); }
+	else st4(ug + 4*(size_t)b, out);
+}
+
+int launch_boundary_prim_ghosts(const DMesh &m, const GasParams &g, const int *bbc, const double *u,
+                                double *ug, bool prim_out, cudaStream_t s)
+{
+	if(m.nbface == 0) return 0;
+	boundary_cell_ghosts_kernel<<<(m.nbface + 127)/128, 128, 0, s>>>(m, g, bbc, u, ug, prim_out ? 1 : 0);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "boundary_cell_ghosts launch", __FILE__, __LINE__);
+	return 0;
+}
+
+__global__ void cons2prim_kernel(const GasParams G, const double *__restrict__ u, double *__restrict__ p, int n)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	double a[4], b[4];
+	ld4(u + 4*(size_t)i, a);
+	cons2prim(G, a, b);
+	st4(p + 4*(size_t)i, b);
+}
+
+int launch_cons2prim(const GasParams &g, const double *u, double *p, int n, cudaStream_t s)
+{
+	if(n == 0) return 0;
+	cons2prim_kernel<<<(n + 255)/256, 256, 0, s>>>(g, u, p, n);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "cons2prim launch", __FILE__, __LINE__);
+	return 0;
+}
+
+/// Single-block, fixed-order sum of the per-tile partial norms (deterministic)
+__global__ void final_norm_kernel(const double *__restrict__ partial, int n, double *__restrict__ out)
+{
+	__shared__ double s[1024];
+	double acc = 0.0;
+	for(int k = threadIdx.x; k < n; k += 1024) acc += partial[k];
+	s[threadIdx.x] = acc;
+	__syncthreads();
+	for(int o = 512; o > 0; o >>= 1) {
+		if(threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+		__syncthreads();
+	}
+	if(threadIdx.x == 0) out[0] = s[0];
+}
+
+int launch_final_norm(const double *partial, int n, double *out, cudaStream_t s)
+{
+	final_norm_kernel<<<1, 1024, 0, s>>>(partial, n, out);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "final_norm launch", __FILE__, __LINE__);
+	return 0;
+}
+
+/// Cl, Cdp, Cdf numerators and the wetted length, summed in boundary-face order by one thread block
+/// of one warp... the boundary is O(sqrt(N)) faces, so a single CTA with a fixed-order reduction.
+__global__ void surface_kernel(const DMesh M, const GasParams G, const double aoa, const double *__restrict__ u,
+                               const double *__restrict__ grad, const int marker, double *__restrict__ out4)
+{
+	__shared__ double s[4][256];
+	double acc[4] = {0,0,0,0};
+	const double wx = cos(aoa), wy = sin(aoa);
+	for(int b = threadIdx.x; b < M.nbface; b += 256) {
+		if(M.btag[b] != marker) continue;
+		const int e = M.bentry[b];
+		const int c = M.bcell[b];
+		const double2 n = M.fn[e];
+		const double len = M.flen[e];
+		double uc[4], g[8];
+		ld4(u + 4*(size_t)c, uc);
+		ld4(grad + 8*(size_t)c, g); ld4(grad + 8*(size_t)c + 4, g+4);
+		const double p = pressure_cons(G, uc);
+		const double cp = (p - G.pinf)*2.0;
+		const double mu = viscosity_cons(G, uc);
+		// velocity gradients from conserved-variable gradients: d(v_i)/dx_j
+		double gv[2][2];
+		for(int i = 0; i < 2; i++)
+			for(int j = 0; j < 2; j++)
+				gv[i][j] = (g[j + 2*(i+1)]*uc[0] - uc[i+1]*g[j])/(uc[0]*uc[0]);
+		const double nn[2] = {n.x, n.y};
+		const double tx = n.y, ty = -n.x;
+		double fx = 0, fy = 0;
+		for(int j = 0; j < 2; j++) { fx += (gv[0][j] + gv[j][0])*nn[j]; fy += (gv[1][j] + gv[j][1])*nn[j]; }
+		const double tauw = mu*(fx*tx + fy*ty);
+		const double cf = 2.0*tauw;
+		acc[0] += len;
+		acc[1] += cp*(n.x*(-wy) + n.y*wx)*len;
+		acc[2] += cp*(n.x*wx + n.y*wy)*len;
+		acc[3] += cf*(tx*wx + ty*wy)*len;
+	}
+	for(int k = 0; k < 4; k++) s[k][threadIdx.x] = acc[k];
+	__syncthreads();
+	for(int o = 128; o > 0; o >>= 1) {
+		if(threadIdx.x < o) for(int k = 0; k < 4; k++) s[k][threadIdx.x] += s[k][threadIdx.x + o];
+		__syncthreads();
+	}
+	if(threadIdx.x == 0) {
+		out4[0] = s[1][0]/s[0][0]; out4[1] = s[2][0]/s[0][0]; out4[2] = s[3][0]/s[0][0]; out4[3] = s[0][0];
+	}
+}
+
+int launch_surface_data(const DMesh &m, const GasParams &g, double aoa, const double *u, const double *grads,
+                        int marker, double *out4, cudaStream_t s)
+{
+	surface_kernel<<<1, 256, 0, s>>>(m, g, aoa, u, grads, marker, out4);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "surface_kernel launch", __FILE__, __LINE__);
+	return 0;
+}
+
+/// per-block partial sums of ((s - s_inf)/s_inf)^2 * area
+__global__ void entropy_kernel(const DMesh M, const GasParams G, const double *__restrict__ u,
+                               double *__restrict__ partial)
+{
+	__shared__ double s[256];
+	const int i = blockIdx.x*256 + threadIdx.x;
+	double v = 0.0;
+	if(i < M.ncell) {
+		double uc[4];
+		ld4(u + 4*(size_t)i, uc);
+		const double sinf = pressure_cons(G, G.uinf)/pow(G.uinf[0], G.g);
+		const double se = (pressure_cons(G, uc)/pow(uc[0], G.g) - sinf)/sinf;
+		v = se*se*M.area[i];
+	}
+	s[threadIdx.x] = v;
+	__syncthreads();
+	for(int o = 128; o > 0; o >>= 1) {
+		if(threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+		__syncthreads();
+	}
+	if(threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+
+int launch_entropy(const DMesh &m, const GasParams &g, const double *u, double *out, cudaStream_t s)
+{
+	const int nblk = (m.ncell + 255)/256;
+	double *partial = nullptr;
+	FVG_CUDA(cudaMallocAsync(&partial, sizeof(double)*nblk, s));
+	entropy_kernel<<<nblk, 256, 0, s>>>(m, g, u, partial);
+	cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "entropy_kernel launch", __FILE__, __LINE__);
+	const int rc = launch_final_norm(partial, nblk, out, s);
+	FVG_CUDA(cudaFreeAsync(partial, s));
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pointwise test hooks
+
+template <int FLUX>
+__global__ void pw_flux_kernel(const GasParams G, int n, const double *__restrict__ ul,
+                               const double *__restrict__ ur, const double *__restrict__ nrm,
+                               double *__restrict__ out)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	double a[4], b[4], f[4];
+	for(int k = 0; k < 4; k++) { a[k] = ul[4*i+k]; b[k] = ur[4*i+k]; }
+	inviscid_flux<FLUX>(G, a, b, nrm[2*i], nrm[2*i+1], f);
+	for(int k = 0; k < 4; k++) out[4*i+k] = f[k];
+}
+
+int launch_pointwise_flux(int flux, const GasParams &g, int n, const double *ul, const double *ur,
+                          const double *nrm, double *out, cudaStream_t s)
+{
+	if(n == 0) return 0;
+	const int nb = (n + 127)/128;
+	switch(flux) {
+	case FLUX_LLF: pw_flux_kernel<FLUX_LLF><<<nb,128,0,s>>>(g,n,ul,ur,nrm,out); break;
+	case FLUX_VANLEER: pw_flux_kernel<FLUX_VANLEER><<<nb,128,0,s>>>(g,n,ul,ur,nrm,out); break;
+	case FLUX_AUSM: pw_flux_kernel<FLUX_AUSM><<<nb,128,0,s>>>(g,n,ul,ur,nrm,out); break;
+	case FLUX_AUSMPLUS: pw_flux_kernel<FLUX_AUSMPLUS><<<nb,128,0,s>>>(g,n,ul,ur,nrm,out); break;
+	case FLUX_ROE: pw_flux_kernel<FLUX_ROE><<<nb,128,0,s>>>(g,n,ul,ur,nrm,out); break;
+	case FLUX_HLL: pw_flux_kernel<FLUX_HLL><<<nb,128,0,s>>>(g,n,ul,ur,nrm,out); break;
+	case FLUX_HLLC: pw_flux_kernel<FLUX_HLLC><<<nb,128,0,s>>>(g,n,ul,ur,nrm,out); break;
+	default: set_error("unknown flux id"); return FVG_ERR_INVALID;
+	}
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "pw_flux launch", __FILE__, __LINE__);
+	return 0;
+}
+
+__global__ void pw_bc_kernel(const GasParams G, int n, const double *__restrict__ ins,
+                             const double *__restrict__ nrm, double *__restrict__ out)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	double a[4], g[4];
+	for(int k = 0; k < 4; k++) a[k] = ins[4*i+k];
+	ghost_state(G, G.bc[0], a, nrm[2*i], nrm[2*i+1], g);
+	for(int k = 0; k < 4; k++) out[4*i+k] = g[k];
+}
+
+int launch_pointwise_bc(const GasParams &g, int n, const double *ins, const double *nrm, double *out,
+                        cudaStream_t s)
+{
+	if(n == 0) return 0;
+	pw_bc_kernel<<<(n + 127)/128, 128, 0, s>>>(g, n, ins, nrm, out);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "pw_bc launch", __FILE__, __LINE__);
+	return 0;
+}
+
+template <bool ORDER2, bool CV>
+__global__ void pw_visc_kernel(const GasParams G, int n, const double *__restrict__ nrm,
+                               const double *__restrict__ rcl, const double *__restrict__ rcr,
+                               const double *__restrict__ ucl, const double *__restrict__ ucr,
+                               const double *__restrict__ gl, const double *__restrict__ gr,
+                               const double *__restrict__ ul, const double *__restrict__ ur,
+                               double *__restrict__ out)
+{
+	const int i = blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	double a[4], b[4], c[4], d[4], g1[8], g2[8], f[4];
+	for(int k = 0; k < 4; k++) { a[k] = ucl[4*i+k]; b[k] = ucr[4*i+k]; c[k] = ul[4*i+k]; d[k] = ur[4*i+k]; }
+	for(int k = 0; k < 8; k++) { g1[k] = ORDER2 ? gl[8*i+k] : 0.0; g2[k] = ORDER2 ? gr[8*i+k] : 0.0; }
+	viscous_face_flux<ORDER2,CV>(G, nrm[2*i], nrm[2*i+1], rcl[2*i], rcl[2*i+1], rcr[2*i], rcr[2*i+1],
+	                             a, b, g1, g2, c, d, f);
+	for(int k = 0; k < 4; k++) out[4*i+k] = f[k];
+}
+
+int launch_pointwise_visc(const GasParams &g, bool order2, bool cv, int n, const double *nrm,
+                          const double *rcl, const double *rcr, const double *ucl, const double *ucr,
+                          const double *gl, const double *gr, const double *ul, const double *ur,
+                          double *out, cudaStream_t s)
+{
+	if(n == 0) return 0;
+	const int nb = (n + 127)/128;
+	if(order2 && cv) pw_visc_kernel<true,true><<<nb,128,0,s>>>(g,n,nrm,rcl,rcr,ucl,ucr,gl,gr,ul,ur,out);
+	else if(order2) pw_visc_kernel<true,false><<<nb,128,0,s>>>(g,n,nrm,rcl,rcr,ucl,ucr,gl,gr,ul,ur,out);
+	else if(cv) pw_visc_kernel<false,true><<<nb,128,0,s>>>(g,n,nrm,rcl,rcr,ucl,ucr,gl,gr,ul,ur,out);
+	else pw_visc_kernel<false,false><<<nb,128,0,s>>>(g,n,nrm,rcl,rcr,ucl,ucr,gl,gr,ul,ur,out);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "pw_visc launch", __FILE__, __LINE__);
+	return 0;
+}
+
+} // namespace fvg

@@ -1,0 +1,369 @@
+"""ctypes binding of libfvens_b200.so (C ABI declared in include/fvens_b200.h).
+
+This module is plumbing for the Python test-suite and bench.py: it loads the in-tree shared library
+and wraps the handles. There is no Python or CPU implementation of any operator here: if the
+library is missing, or a device entry point fails, the call raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfvens_b200.so")
+
+FLUX = {"LLF": 0, "VANLEER": 1, "AUSM": 2, "AUSMPLUS": 3, "ROE": 4, "HLL": 5, "HLLC": 6}
+GRAD = {"NONE": 0, "ZERO": 0, "GREENGAUSS": 1, "LEASTSQUARES": 2}
+RECON = {"NONE": 0, "WENO": 1, "VANALBADA": 2, "BARTHJESPERSEN": 3, "VENKATAKRISHNAN": 4}
+# spatial/abctypes.hpp:13-22
+BC = {"slipwall": 0, "farfield": 1, "inflowoutflow": 2, "subsonicinflow": 3, "extrapolation": 4,
+      "periodic": 5, "isothermalwall": 6, "adiabaticwall": 7}
+REORDER = {"none": 0, "hilbert": 1, "rcm": 2}
+
+STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "IO", 4: "UNSUPPORTED", 5: "TOLERANCE", 6: "NUMERICAL", 7: "COMM"}
+
+
+class FvgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"fvens_b200 error {code} ({STATUS.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class ToleranceError(FvgError):
+    """Solver hit maxiter (reference: Tolerance_error)."""
+
+
+class NumericalError(FvgError):
+    """Non-finite residual (reference: Numerical_error)."""
+
+
+class HostMeshView(C.Structure):
+    _fields_ = [("npoin", C.c_int), ("nelem", C.c_int), ("nbface", C.c_int), ("naface", C.c_int),
+                ("ninface", C.c_int), ("nconnface", C.c_int), ("maxnnode", C.c_int), ("nbtag", C.c_int),
+                ("coords", C.POINTER(C.c_double)), ("inpoel", C.POINTER(C.c_int)),
+                ("nnode", C.POINTER(C.c_int)), ("esuel", C.POINTER(C.c_int)),
+                ("elemface", C.POINTER(C.c_int)), ("intfac", C.POINTER(C.c_int)),
+                ("btags", C.POINTER(C.c_int)), ("facemetric", C.POINTER(C.c_double)),
+                ("area", C.POINTER(C.c_double))]
+
+
+class MeshOpts(C.Structure):
+    _fields_ = [("reorder", C.c_int), ("tile_cells", C.c_int), ("device", C.c_int)]
+
+
+class MeshInfo(C.Structure):
+    _fields_ = [("ncell", C.c_int), ("nbface", C.c_int), ("naface", C.c_int), ("ntile", C.c_int),
+                ("tile_cells", C.c_int), ("nstream", C.c_int), ("ncut_dup", C.c_int),
+                ("max_colours", C.c_int), ("reorder", C.c_int), ("mean_neighbour_distance", C.c_double)]
+
+
+class Physics(C.Structure):
+    _fields_ = [("gamma", C.c_double), ("Minf", C.c_double), ("Tinf", C.c_double), ("Reinf", C.c_double),
+                ("Pr", C.c_double), ("aoa", C.c_double), ("viscous_sim", C.c_int), ("const_visc", C.c_int)]
+
+
+class Numerics(C.Structure):
+    _fields_ = [("flux", C.c_int), ("gradient", C.c_int), ("reconstruction", C.c_int),
+                ("limiter_param", C.c_double), ("order2", C.c_int), ("bnd_policy", C.c_int)]
+
+
+class BCStruct(C.Structure):
+    _fields_ = [("tag", C.c_int), ("type", C.c_int), ("vals", C.c_double*2)]
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "or `make -C fvens_b200/csrc`. There is no fallback implementation.")
+    lib = C.CDLL(LIB_PATH)
+    lib.fvg_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code == 0:
+        return
+    msg = load().fvg_last_error().decode()
+    if code == 5:
+        raise ToleranceError(code, msg)
+    if code == 6:
+        raise NumericalError(code, msg)
+    raise FvgError(code, msg)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _ptr(t):
+    """Device (torch tensor) or raw integer address -> void*"""
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    assert t.is_cuda and t.is_contiguous() and str(t.dtype) == "torch.float64"
+    return C.c_void_p(t.data_ptr())
+
+
+def make_physics(gamma=1.4, Minf=0.5, Tinf=288.15, Reinf=5000.0, Pr=0.72, aoa=0.0, viscous=False,
+                 const_visc=False):
+    return Physics(gamma, Minf, Tinf, Reinf, Pr, aoa, int(viscous), int(const_visc))
+
+
+def phys_array(p):
+    """The oracle's parameter vector {gamma, Minf, Tinf, Reinf, Pr, aoa}"""
+    return np.array([p.gamma, p.Minf, p.Tinf, p.Reinf, p.Pr, p.aoa])
+
+
+class UMesh:
+    """Host mesh handle = fvens::UMesh<double,2> after constructMesh/preprocessMesh."""
+
+    def __init__(self, handle):
+        self._h = handle
+        v = HostMeshView()
+        check(load().fvg_umesh_view(self._h, C.byref(v)))
+        self.view = v
+        self.npoin, self.nelem, self.nbface, self.naface = v.npoin, v.nelem, v.nbface, v.naface
+        self.ninface, self.maxnnode = v.ninface, v.maxnnode
+
+    @classmethod
+    def read(cls, path):
+        h = C.c_void_p()
+        check(load().fvg_umesh_read(str(path).encode(), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, coords, nnode, inpoel, bface):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        nnode = np.ascontiguousarray(nnode, dtype=np.int32)
+        inpoel = np.ascontiguousarray(inpoel, dtype=np.int32)
+        bface = np.ascontiguousarray(bface, dtype=np.int32)
+        assert inpoel.shape == (len(nnode), 4) and coords.shape[1] == 2 and bface.shape[1] == 3
+        h = C.c_void_p()
+        check(load().fvg_umesh_from_arrays(len(coords), _dp(coords), len(nnode), _ip(nnode), _ip(inpoel),
+                                           len(bface), _ip(bface), C.byref(h)))
+        return cls(h)
+
+    def _arr(self, ptr, shape, dtype):
+        n = int(np.prod(shape))
+        if n == 0:
+            return np.zeros(shape, dtype=dtype)
+        return np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape).copy()
+
+    def arrays(self):
+        """Copies of the derived arrays, names as the reference's accessors."""
+        v = self.view
+        mw = v.maxnnode
+        return dict(
+            coords=self._arr(v.coords, (v.npoin, 2), np.float64),
+            inpoel=self._arr(v.inpoel, (v.nelem, mw), np.int32),
+            nnode=self._arr(v.nnode, (v.nelem,), np.int32),
+            esuel=self._arr(v.esuel, (v.nelem, mw), np.int32),
+            elemface=self._arr(v.elemface, (v.nelem, mw), np.int32),
+            intfac=self._arr(v.intfac, (v.naface, 4), np.int32),
+            btags=self._arr(v.btags, (v.nbface, v.nbtag), np.int32),
+            facemetric=self._arr(v.facemetric, (v.naface, 3), np.float64),
+            area=self._arr(v.area, (v.nelem,), np.float64))
+
+    def reorder_cells(self, perm):
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
+        check(load().fvg_umesh_reorder_cells(self._h, _ip(perm)))
+        self.__init__(self._h)
+
+    def rcm_ordering(self):
+        perm = np.zeros(self.nelem, dtype=np.int32)
+        check(load().fvg_umesh_rcm_ordering(self._h, _ip(perm)))
+        return perm
+
+    def hilbert_ordering(self):
+        perm = np.zeros(self.nelem, dtype=np.int32)
+        check(load().fvg_umesh_hilbert_ordering(self._h, _ip(perm)))
+        return perm
+
+    def close(self):
+        if self._h:
+            load().fvg_umesh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceMesh:
+    def __init__(self, umesh, reorder="hilbert", tile_cells=0, device=-1):
+        self.umesh = umesh
+        opts = MeshOpts(REORDER[reorder] if isinstance(reorder, str) else int(reorder), tile_cells, device)
+        h = C.c_void_p()
+        check(load().fvg_mesh_create(C.byref(umesh.view), C.byref(opts), C.byref(h)))
+        self._h = h
+        info = MeshInfo()
+        check(load().fvg_mesh_get_info(self._h, C.byref(info)))
+        self.info = info
+        self.ncell, self.nbface, self.naface = info.ncell, info.nbface, info.naface
+
+    def permutation(self):
+        p = np.zeros(self.ncell, dtype=np.int32)
+        check(load().fvg_mesh_permutation(self._h, _ip(p)))
+        return p
+
+    def stream(self):
+        n = self.info.nstream
+        f, c, t = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        check(load().fvg_mesh_stream(self._h, _ip(f), _ip(c), _ip(t)))
+        return f, c, t
+
+    def close(self):
+        if self._h:
+            load().fvg_mesh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FlowFV:
+    """Device flow discretisation handle; method names follow the reference's FlowFV."""
+
+    def __init__(self, dmesh, phys, flux="ROE", gradient="LEASTSQUARES", reconstruction="NONE",
+                 limiter_param=1.0, order2=True, bnd_policy=0, bcs=()):
+        self.dmesh = dmesh
+        self.phys = phys
+        num = Numerics(FLUX[flux.upper()], GRAD.get(gradient.upper(), 0), RECON[reconstruction.upper()],
+                       limiter_param, int(order2), bnd_policy)
+        self.num = num
+        arr = (BCStruct*max(len(bcs), 1))()
+        for i, (tag, typ, vals) in enumerate(bcs):
+            arr[i].tag = tag
+            arr[i].type = BC[typ] if isinstance(typ, str) else int(typ)
+            arr[i].vals[0], arr[i].vals[1] = (list(vals) + [0.0, 0.0])[:2]
+        self.bcs = [(a.tag, a.type, (a.vals[0], a.vals[1])) for a in arr[:len(bcs)]]
+        h = C.c_void_p()
+        check(load().fvg_flow_create(dmesh._h, C.byref(phys), C.byref(num), arr, len(bcs), C.byref(h)))
+        self._h = h
+
+    # device-pointer entry points (torch float64 CUDA tensors)
+    def compute_residual(self, u, res, gettimesteps=True, dtm=None, accumulate=True, stream=None):
+        check(load().fvg_residual(self._h, _ptr(u), _ptr(res), int(accumulate), int(gettimesteps), _ptr(dtm),
+                                  C.c_void_p(stream or 0)))
+
+    def compute_residual_host(self, u, res, gettimesteps=True, dtm=None, accumulate=True):
+        """Drop-in mode: host arrays (numpy, or raw addresses of pinned buffers) in and out, H2D/D2H inside."""
+        def hp(a):
+            if a is None:
+                return None
+            if isinstance(a, int):
+                return C.cast(C.c_void_p(a), C.POINTER(C.c_double))
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+            return _dp(a)
+        check(load().fvg_residual_host(self._h, hp(u), hp(res), int(accumulate), int(gettimesteps), hp(dtm)))
+
+    def timing(self, enable=True):
+        """Returns (ms gradient pass, ms face pass, evaluations) since the previous call; (re)arms the timers."""
+        out = np.zeros(3)
+        check(load().fvg_flow_timing(self._h, int(enable), _dp(out)))
+        return out[0], out[1], int(out[2])
+
+    def compute_gradients(self, uprim, ug, grad, stream=None):
+        check(load().fvg_gradients(self._h, _ptr(uprim), _ptr(ug), _ptr(grad), C.c_void_p(stream or 0)))
+
+    def compute_face_values(self, uprim, ug, grad, ufl, ufr, stream=None):
+        check(load().fvg_face_values(self._h, _ptr(uprim), _ptr(ug), _ptr(grad), _ptr(ufl), _ptr(ufr),
+                                     C.c_void_p(stream or 0)))
+
+    def compute_boundary_states(self, ins, gs, stream=None):
+        check(load().fvg_boundary_states(self._h, _ptr(ins), _ptr(gs), C.c_void_p(stream or 0)))
+
+    def getGradients(self, u, grads, stream=None):
+        check(load().fvg_get_gradients(self._h, _ptr(u), _ptr(grads), C.c_void_p(stream or 0)))
+
+    def computeSurfaceData(self, u, grads, marker):
+        out = np.zeros(3)
+        check(load().fvg_surface_data(self._h, _ptr(u), _ptr(grads), int(marker), _dp(out)))
+        return tuple(out)
+
+    def entropy_error(self, u):
+        out = C.c_double(0)
+        check(load().fvg_entropy_error(self._h, _ptr(u), C.byref(out)))
+        return out.value
+
+    def euler_step(self, u, cfl, resnorm2=None, stream=None):
+        check(load().fvg_euler_step(self._h, _ptr(u), C.c_double(cfl), _ptr(resnorm2), C.c_void_p(stream or 0)))
+
+    def solve_forward_euler(self, u, cfl, tol, maxiter, check_every=1):
+        """Returns (status code, steps, history); raises only on hard errors."""
+        steps = C.c_int(0)
+        hist = np.zeros(max(maxiter, 1))
+        code = load().fvg_forward_euler_solve(self._h, _ptr(u), C.c_double(cfl), C.c_double(tol), int(maxiter),
+                                              int(check_every), C.byref(steps), _dp(hist))
+        if code not in (0, 5, 6):
+            check(code)
+        return code, steps.value, hist[:steps.value].copy()
+
+    def launch_count(self):
+        c = C.c_longlong(0)
+        check(load().fvg_flow_launch_count(self._h, C.byref(c)))
+        return c.value
+
+    def close(self):
+        if self._h:
+            load().fvg_flow_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def flux_pointwise(flux, phys, ul, ur, n):
+    ul, ur, n = (np.ascontiguousarray(a, dtype=np.float64) for a in (ul, ur, n))
+    out = np.zeros_like(ul)
+    fid = FLUX[flux.upper()] if isinstance(flux, str) else int(flux)
+    check(load().fvg_flux_pointwise(fid, C.byref(phys), len(ul), _dp(ul), _dp(ur), _dp(n), _dp(out)))
+    return out
+
+
+def bc_pointwise(bctype, vals, phys, ins, n):
+    ins, n = (np.ascontiguousarray(a, dtype=np.float64) for a in (ins, n))
+    out = np.zeros_like(ins)
+    bc = BCStruct(0, BC[bctype] if isinstance(bctype, str) else int(bctype))
+    bc.vals[0], bc.vals[1] = (list(vals) + [0.0, 0.0])[:2]
+    check(load().fvg_bc_pointwise(C.byref(bc), C.byref(phys), len(ins), _dp(ins), _dp(n), _dp(out)))
+    return out
+
+
+def viscous_flux_pointwise(phys, order2, n, rcl, rcr, ucl, ucr, gl, gr, ul, ur):
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (n, rcl, rcr, ucl, ucr, gl, gr, ul, ur)]
+    out = np.zeros_like(arrs[3])
+    check(load().fvg_viscous_flux_pointwise(C.byref(phys), int(order2), len(arrs[0]), *[_dp(a) for a in arrs], _dp(out)))
+    return out
+
+
+def freestream(phys):
+    out = np.zeros(4)
+    check(load().fvg_freestream(C.byref(phys), _dp(out)))
+    return out
+
+
+def device_count():
+    c = C.c_int(0)
+    check(load().fvg_device_count(C.byref(c)))
+    return c.value

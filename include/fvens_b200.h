@@ -1,0 +1,212 @@
+/* fvens_b200 C ABI: the B200 (sm_100a) residual engine behind the FVENS class surface.
+ *
+ * FVENS itself has no C API or FFI: its operator boundary is a set of C++ abstract classes plus
+ * string-keyed factories. Each entry point below replaces one of those C++
+ * interfaces 1:1 and cites it (paths relative to the reference's src/). The C++ host classes in
+ * fvens_b200/host/ (same names and signatures as the reference) are thin wrappers over this ABI.
+ *
+ * Conventions: every function returns 0 on success or an fvg_status code, never throws, never
+ * takes ownership of caller memory. `d_` pointers are device memory on the device the mesh was
+ * created on, `h_` pointers are host memory. `stream` is a cudaStream_t passed as void* (NULL =
+ * the default stream); device-pointer calls are asynchronous on that stream unless stated.
+ * State, residual, gradient and face arrays use the reference's layouts:
+ *   u, res     [nelem][4]  conserved (rho, rho vx, rho vy, rho E)     (PETSc Vec with block size 4)
+ *   dtm        [nelem]
+ *   grad       [nelem][8]  GradBlock_t col-major 2x4: grad[8*i + idim + 2*ivar]  (aconstants.hpp:80-90)
+ *   ufl, ufr   [naface][4] face states in the reference's face numbering (intfac order)
+ *   ug         [nbface][4] boundary ghost states
+ */
+#ifndef FVENS_B200_H
+#define FVENS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+	FVG_OK = 0,
+	FVG_ERR_INVALID = 1,      /* bad argument / inconsistent mesh / unknown BC tag */
+	FVG_ERR_CUDA = 2,         /* CUDA runtime error (see fvg_last_error) */
+	FVG_ERR_IO = 3,           /* mesh file could not be read */
+	FVG_ERR_UNSUPPORTED = 4,  /* option the engine does not implement */
+	FVG_ERR_TOLERANCE = 5,    /* solver hit maxiter   (reference: Tolerance_error, aerrorhandling.hpp) */
+	FVG_ERR_NUMERICAL = 6,    /* non-finite residual  (reference: Numerical_error) */
+	FVG_ERR_COMM = 7          /* peer-memory / halo set-up failure */
+} fvg_status;
+
+/* Message of the last error on the calling thread ("" if none). */
+const char *fvg_last_error(void);
+/* Number of visible CUDA devices; fails (FVG_ERR_CUDA) when there is no usable GPU. */
+int fvg_device_count(int *count);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host mesh = fvens::UMesh<double,2> (mesh/mesh.hpp:25-500) built by constructMesh + preprocessMesh
+ * (mesh/ameshutils.cpp:39-153): read -> correctBoundaryFaceOrientation -> compute_topological ->
+ * compute_areas -> compute_face_data. CPU only, no CUDA calls. */
+typedef struct fvg_umesh fvg_umesh;
+
+/* readMesh (mesh/meshreaders.cpp:35-64): .msh = Gmsh 2.2 ASCII, .su2 = SU2 with integer markers */
+int fvg_umesh_read(const char *path, fvg_umesh **out);
+/* From arrays (MeshData, mesh/meshreaders.hpp:29-56): inpoel [nelem][4] (-1 padded),
+ * bface [nbface][3] = node0, node1, marker. */
+int fvg_umesh_from_arrays(int npoin, const double *coords, int nelem, const int *nnode,
+                          const int *inpoel, int nbface, const int *bface, fvg_umesh **out);
+void fvg_umesh_destroy(fvg_umesh *m);
+/* UMesh::reorder_cells (mesh/mesh.cpp:85-99) followed by the topology/metric rebuild of
+ * preprocessMesh (mesh/ameshutils.cpp:60-100): new cell i = old cell perm[i]. */
+int fvg_umesh_reorder_cells(fvg_umesh *m, const int *perm);
+/* Reverse Cuthill-McKee ordering of the cell adjacency graph, the stand-in for `-mesh_reorder rcm`
+ * (mesh/ameshutils.cpp:246-288, which calls PETSc MatGetOrdering). perm[new] = old. */
+int fvg_umesh_rcm_ordering(const fvg_umesh *m, int *perm);
+/* Hilbert space-filling-curve ordering of the cell centres (the locality order the device mesh uses;
+ * contiguous index ranges are compact patches, which is what both the tiles and the multi-GPU
+ * partitions want). perm[new] = old. */
+int fvg_umesh_hilbert_ordering(const fvg_umesh *m, int *perm);
+
+/* Non-owning view of the reference's mesh arrays (what UMesh's g*() accessors return). */
+typedef struct {
+	int npoin, nelem, nbface, naface, ninface, nconnface;
+	int maxnnode, nbtag;
+	const double *coords;       /* [npoin][2]              gcoords   */
+	const int *inpoel;          /* [nelem][maxnnode]       ginpoel   */
+	const int *nnode;           /* [nelem]                 gnnode (== gnfael for linear cells) */
+	const int *esuel;           /* [nelem][maxnnode]       gesuel: >= nelem+nconnface means physical boundary */
+	const int *elemface;        /* [nelem][maxnnode]       gelemface */
+	const int *intfac;          /* [naface][4] L,R,n0,n1   gintfac   */
+	const int *btags;           /* [nbface][nbtag]         gbtags    */
+	const double *facemetric;   /* [naface][3] nx,ny,len   gfacemetric */
+	const double *area;         /* [nelem]                 garea     */
+} fvg_host_mesh;
+int fvg_umesh_view(const fvg_umesh *m, fvg_host_mesh *view);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device mesh: SoA copy of the arrays above, cells renumbered for locality, faces regrouped into
+ * per-tile streams and edge-coloured inside each tile so that the face->cell accumulation needs no
+ * atomics and is deterministic. Invisible to callers: all API arrays stay in reference numbering. */
+typedef struct fvg_mesh fvg_mesh;
+
+enum { FVG_REORDER_NONE = 0, FVG_REORDER_HILBERT = 1, FVG_REORDER_RCM = 2 };
+typedef struct {
+	int reorder;       /* FVG_REORDER_*; HILBERT = space-filling-curve order of the cell centres */
+	int tile_cells;    /* cells per tile (0 = default 512); multiple of 32, <= 2048 */
+	int device;        /* CUDA device ordinal, -1 = current; -2 = host-only build (renumbering, tiling and
+	                      colouring can be inspected without a GPU; no flow can be created on it) */
+} fvg_mesh_opts;
+
+typedef struct {
+	int ncell, nbface, naface, ntile, tile_cells, nstream, ncut_dup, max_colours, reorder;
+	double mean_neighbour_distance;   /* mean |i-j| over interior faces in device numbering */
+} fvg_mesh_info;
+
+int fvg_mesh_create(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh **out);
+void fvg_mesh_destroy(fvg_mesh *m);
+int fvg_mesh_get_info(const fvg_mesh *m, fvg_mesh_info *info);
+/* cell_new2old[ncell]: device cell i holds reference cell cell_new2old[i]. */
+int fvg_mesh_permutation(const fvg_mesh *m, int *cell_new2old);
+/* Stream entries: reference face id, colour and tile of every entry (test hook for the colouring
+ * validity check: no two entries of one colour in a tile may touch the same tile-owned cell). */
+int fvg_mesh_stream(const fvg_mesh *m, int *entry_face, int *entry_colour, int *entry_tile);
+
+/* ------------------------------------------------------------------------------------------------
+ * Flow discretisation = FlowFV<double,order2,constVisc> (spatial/flow_spatial.hpp:33-55,150-262)
+ * built by create_const_flowSpatialDiscretization (utilities/afactory.cpp:217-270). */
+typedef struct fvg_flow fvg_flow;
+
+/* FlowPhysicsConfig (spatial/flow_spatial.hpp:33-44) minus the BC list */
+typedef struct {
+	double gamma, Minf, Tinf, Reinf, Pr, aoa;
+	int viscous_sim, const_visc;
+} fvg_physics;
+
+/* Factory keys of utilities/afactory.cpp:38-81 (fluxes), 111-127 (gradients), 178-211 (reconstruction) */
+enum { FVG_FLUX_LLF = 0, FVG_FLUX_VANLEER = 1, FVG_FLUX_AUSM = 2, FVG_FLUX_AUSMPLUS = 3,
+       FVG_FLUX_ROE = 4, FVG_FLUX_HLL = 5, FVG_FLUX_HLLC = 6 };
+enum { FVG_GRAD_ZERO = 0, FVG_GRAD_GREENGAUSS = 1, FVG_GRAD_LEASTSQUARES = 2 };
+enum { FVG_RECON_NONE = 0, FVG_RECON_WENO = 1, FVG_RECON_VANALBADA = 2, FVG_RECON_BARTHJESPERSEN = 3,
+       FVG_RECON_VENKATAKRISHNAN = 4 };
+/* Boundary-neighbour policy of the Barth-Jespersen / Venkatakrishnan limiters. The reference reads
+ * out of bounds there; 0 = use the boundary ghost state, 1 = skip (as its WENO does). */
+enum { FVG_BND_GHOST = 0, FVG_BND_SKIP = 1 };
+
+/* FlowNumericsConfig (spatial/flow_spatial.hpp:47-55) with integer keys */
+typedef struct {
+	int flux, gradient, reconstruction;
+	double limiter_param;     /* Venkatakrishnan K / WENO central weight (never parsed by the reference, H2) */
+	int order2;
+	int bnd_policy;
+} fvg_numerics;
+
+/* FlowBCConfig (spatial/abc.hpp:34-40); type = BCType of spatial/abctypes.hpp:13-22:
+ * 0 slip wall, 1 far field, 2 inflow-outflow, 3 subsonic inflow (vals = p0, T0), 4 extrapolation,
+ * 5 periodic (rejected), 6 isothermal wall (vals = tangential velocity, T), 7 adiabatic wall (vals[0] = v_t) */
+typedef struct {
+	int tag, type;
+	double vals[2];
+} fvg_bc;
+
+int fvg_flow_create(fvg_mesh *mesh, const fvg_physics *phys, const fvg_numerics *num,
+                    const fvg_bc *bcs, int nbc, fvg_flow **out);
+void fvg_flow_destroy(fvg_flow *f);
+
+/* Spatial::compute_residual (spatial/aspatial.hpp:62-63, flow_spatial.cpp:637-816): adds -r(u) into
+ * d_res when accumulate != 0 (the reference's contract: caller zeroes), else overwrites it.
+ * d_dtm may be NULL when gettimesteps == 0. */
+int fvg_residual(fvg_flow *f, const double *d_u, double *d_res, int accumulate, int gettimesteps,
+                 double *d_dtm, void *stream);
+/* Same through host buffers (drop-in mode): uploads u (and h_res when accumulate != 0, the reference's
+ * add-into contract), runs the kernels, downloads the residual and the time steps. Synchronous.
+ * Pinned host memory makes the copies run at full PCIe rate but is not required. */
+int fvg_residual_host(fvg_flow *f, const double *h_u, double *h_res, int accumulate, int gettimesteps,
+                      double *h_dtm);
+
+/* GradientScheme::compute_gradients (spatial/agradientschemes.hpp:44-48) on primitive cell states */
+int fvg_gradients(fvg_flow *f, const double *d_uprim, const double *d_ug, double *d_grad, void *stream);
+/* SolutionReconstruction::compute_face_values (spatial/areconstruction.hpp:37-41) */
+int fvg_face_values(fvg_flow *f, const double *d_uprim, const double *d_ug, const double *d_grad,
+                    double *d_ufl, double *d_ufr, void *stream);
+/* FlowFV_base::compute_boundary_states (spatial/flow_spatial.cpp:74-93): ins, gs [nbface][4] conserved */
+int fvg_boundary_states(fvg_flow *f, const double *d_ins, double *d_gs, void *stream);
+/* FlowFV_base::getGradients (spatial/flow_spatial.cpp:96-112): gradients of the CONSERVED variables */
+int fvg_get_gradients(fvg_flow *f, const double *d_u, double *d_grads, void *stream);
+/* FlowFV_base::computeSurfaceData (spatial/flow_spatial.cpp:131-310): out3 = Cl, Cdp, Cdf over the
+ * faces carrying `marker`. Synchronous; h_out3 is host memory. */
+int fvg_surface_data(fvg_flow *f, const double *d_u, const double *d_grads, int marker, double *h_out3);
+/* compute_entropy_cell (spatial/aoutput.cpp:28-63). Synchronous. */
+int fvg_entropy_error(fvg_flow *f, const double *d_u, double *h_out);
+
+/* One pseudo-time step of SteadyForwardEulerSolver::solve (ode/aodesolver.cpp:177-251):
+ * r = -r(u); dt; u += cfl*dt/area*r; *d_resnorm2 = sum_cells r_E^2 * area. Fused: no residual array
+ * is written. d_resnorm2 is one double of device memory (may be NULL). */
+int fvg_euler_step(fvg_flow *f, double *d_u, double cfl, double *d_resnorm2, void *stream);
+/* Whole solve loop: steps until resi/initres <= tol (returns 0), maxiter reached (FVG_ERR_TOLERANCE)
+ * or a non-finite norm (FVG_ERR_NUMERICAL). h_hist (may be NULL) receives the absolute residual norm
+ * of every step (capacity maxiter). check_every >= 1: how often the norm is read back (1 = the
+ * reference's behaviour). Synchronous. */
+int fvg_forward_euler_solve(fvg_flow *f, double *d_u, double cfl, double tol, int maxiter,
+                            int check_every, int *h_steps, double *h_hist);
+
+/* Pointwise test hooks (host buffers; each launches a kernel - there is no CPU path):
+ * InviscidFlux::get_flux (spatial/anumericalflux.hpp:32-34), FlowBC::computeGhostState
+ * (spatial/abc.hpp:72-73), FlowFV::compute_viscous_flux (spatial/flow_spatial.cpp:349-395). */
+int fvg_flux_pointwise(int flux_id, const fvg_physics *phys, int n, const double *h_ul,
+                       const double *h_ur, const double *h_n, double *h_out);
+int fvg_bc_pointwise(const fvg_bc *bc, const fvg_physics *phys, int n, const double *h_ins,
+                     const double *h_n, double *h_out);
+int fvg_viscous_flux_pointwise(const fvg_physics *phys, int order2, int n, const double *h_n,
+                               const double *h_rcl, const double *h_rcr, const double *h_ucl,
+                               const double *h_ucr, const double *h_gl, const double *h_gr,
+                               const double *h_ul, const double *h_ur, double *h_out);
+/* IdealGasPhysics::compute_freestream_state (physics/aphysics.cpp:44-58) */
+int fvg_freestream(const fvg_physics *phys, double *h_uinf4);
+
+/* Per-pass device timing of fvg_residual / fvg_euler_step with CUDA events recorded on the launching
+ * stream. Call with enable = 1 to start, later with h_out3 to read {ms in the gradient/limiter pass,
+ * ms in the face pass, number of evaluations timed} accumulated since the previous call (synchronises). */
+int fvg_flow_timing(fvg_flow *f, int enable, double *h_out3);
+/* Work counters since flow creation: kernels launched by this library for that flow. */
+int fvg_flow_launch_count(const fvg_flow *f, long long *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,232 @@
+"""ctypes wrapper of the CPU oracle (oracle/liborc.so) and of the tier-A reference build
+(oracle/_ref/libfvens_ref_a.so). TEST INFRASTRUCTURE ONLY - never imported by fvens_b200/."""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORC_PATH = os.path.join(ROOT, "oracle", "liborc.so")
+REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libfvens_ref_a.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+_orc = None
+_ref = None
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def orc():
+    global _orc
+    if _orc is None:
+        _orc = C.CDLL(ORC_PATH)
+        _orc.orc_mesh_read.restype = C.c_void_p
+        _orc.orc_mesh_from_arrays.restype = C.c_void_p
+        _orc.orc_flow_create.restype = C.c_void_p
+        _orc.orc_flow_entropy.restype = C.c_double
+    return _orc
+
+
+def have_ref():
+    return os.path.exists(REF_PATH)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(REF_PATH)
+    return _ref
+
+
+def set_threads(n):
+    orc().orc_set_num_threads(int(n))
+
+
+def num_threads():
+    return orc().orc_num_threads()
+
+
+def phys5(p):
+    return np.array([p.gamma, p.Minf, p.Tinf, p.Reinf, p.Pr], dtype=np.float64)
+
+
+def _pw(lib, prefix):
+    return lambda name: getattr(lib, prefix + name)
+
+
+def flux(lib_kind, flux_id, p, ul, ur, n):
+    lib, pre = (orc(), "orc_") if lib_kind == "orc" else (ref(), "ref_")
+    ul, ur, n = (np.ascontiguousarray(a, dtype=np.float64) for a in (ul, ur, n))
+    out = np.zeros_like(ul)
+    ph = phys5(p)
+    getattr(lib, pre + "flux")(int(flux_id), _dp(ph), len(ul), _dp(ul), _dp(ur), _dp(n), _dp(out))
+    return out
+
+
+def ghost_state(lib_kind, bc_type, vals, p, ins, n):
+    lib, pre = (orc(), "orc_") if lib_kind == "orc" else (ref(), "ref_")
+    ins, n = (np.ascontiguousarray(a, dtype=np.float64) for a in (ins, n))
+    out = np.zeros_like(ins)
+    ph = phys5(p)
+    v = np.array((list(vals) + [0.0, 0.0])[:2], dtype=np.float64)
+    getattr(lib, pre + "ghost_state")(int(bc_type), _dp(v), _dp(ph), C.c_double(p.aoa), len(ins), _dp(ins), _dp(n), _dp(out))
+    return out
+
+
+def viscous_flux(p, order2, n, rcl, rcr, ucl, ucr, gl, gr, ul, ur):
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (n, rcl, rcr, ucl, ucr, gl, gr, ul, ur)]
+    out = np.zeros_like(arrs[3])
+    ph = phys5(p)
+    orc().orc_viscous_flux(_dp(ph), int(order2), int(p.const_visc), len(arrs[0]), *[_dp(a) for a in arrs], _dp(out))
+    return out
+
+
+def cons2prim(lib_kind, p, u):
+    lib, pre = (orc(), "orc_") if lib_kind == "orc" else (ref(), "ref_")
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.zeros_like(u)
+    ph = phys5(p)
+    getattr(lib, pre + "cons2prim")(_dp(ph), len(u), _dp(u), _dp(out))
+    return out
+
+
+def prim2cons(lib_kind, p, u):
+    lib, pre = (orc(), "orc_") if lib_kind == "orc" else (ref(), "ref_")
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.zeros_like(u)
+    ph = phys5(p)
+    getattr(lib, pre + "prim2cons")(_dp(ph), len(u), _dp(u), _dp(out))
+    return out
+
+
+def freestream(lib_kind, p):
+    lib, pre = (orc(), "orc_") if lib_kind == "orc" else (ref(), "ref_")
+    out = np.zeros(4)
+    ph = phys5(p)
+    getattr(lib, pre + "freestream")(_dp(ph), C.c_double(p.aoa), _dp(out))
+    return out
+
+
+class Mesh:
+    def __init__(self, handle):
+        if not handle:
+            raise RuntimeError("oracle mesh construction failed")
+        self.h = C.c_void_p(handle)
+        s = np.zeros(5, dtype=np.int32)
+        orc().orc_mesh_sizes(self.h, _ip(s))
+        self.npoin, self.nelem, self.nbface, self.naface, self.ninface = (int(x) for x in s)
+
+    @classmethod
+    def read(cls, path):
+        return cls(orc().orc_mesh_read(str(path).encode()))
+
+    @classmethod
+    def from_arrays(cls, coords, nnode, inpoel, bface):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        nnode = np.ascontiguousarray(nnode, dtype=np.int32)
+        inpoel = np.ascontiguousarray(inpoel, dtype=np.int32)
+        bface = np.ascontiguousarray(bface, dtype=np.int32)
+        return cls(orc().orc_mesh_from_arrays(len(coords), _dp(coords), len(nnode), _ip(nnode), _ip(inpoel),
+                                              len(bface), _ip(bface)))
+
+    def arrays(self):
+        d = dict(coords=np.zeros((self.npoin, 2)), inpoel=np.zeros((self.nelem, 4), dtype=np.int32),
+                 nnode=np.zeros(self.nelem, dtype=np.int32), bface=np.zeros((self.nbface, 3), dtype=np.int32),
+                 esuel=np.zeros((self.nelem, 4), dtype=np.int32), elemface=np.zeros((self.nelem, 4), dtype=np.int32),
+                 intfac=np.zeros((self.naface, 4), dtype=np.int32), btags=np.zeros(self.nbface, dtype=np.int32),
+                 facemetric=np.zeros((self.naface, 3)), area=np.zeros(self.nelem))
+        orc().orc_mesh_get(self.h, _dp(d["coords"]), _ip(d["inpoel"]), _ip(d["nnode"]), _ip(d["bface"]),
+                           _ip(d["esuel"]), _ip(d["elemface"]), _ip(d["intfac"]), _ip(d["btags"]),
+                           _dp(d["facemetric"]), _dp(d["area"]))
+        return d
+
+    def __del__(self):
+        try:
+            orc().orc_mesh_free(self.h)
+        except Exception:
+            pass
+
+
+class Flow:
+    """Oracle FlowFV. bcs: list of (tag, type_id, (v0, v1))."""
+
+    def __init__(self, mesh, p, flux=4, gradient=2, recon=0, limiter_param=1.0, order2=True, bnd_policy=0, bcs=()):
+        self.mesh = mesh
+        ph = np.array([p.gamma, p.Minf, p.Tinf, p.Reinf, p.Pr, p.aoa], dtype=np.float64)
+        io = np.array([p.viscous_sim, p.const_visc, flux, gradient, recon, int(order2), bnd_policy], dtype=np.int32)
+        bt = np.array([[t, ty] for (t, ty, _) in bcs], dtype=np.int32).reshape(-1, 2)
+        bv = np.array([(list(v) + [0.0, 0.0])[:2] for (_, _, v) in bcs], dtype=np.float64).reshape(-1, 2)
+        self.h = C.c_void_p(orc().orc_flow_create(mesh.h, _dp(ph), _ip(io), C.c_double(limiter_param), len(bcs),
+                                                  _ip(bt), _dp(bv)))
+
+    def geometry(self):
+        m = self.mesh
+        rc = np.zeros((m.nelem, 2)); gr = np.zeros((m.naface, 2)); rcbp = np.zeros((m.nbface, 2))
+        orc().orc_flow_geometry(self.h, _dp(rc), _dp(gr), _dp(rcbp), None, None)
+        return rc, gr, rcbp
+
+    def residual(self, u, gettimesteps=True, want_grad=False, want_faces=False):
+        m = self.mesh
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        res = np.zeros((m.nelem, 4)); dtm = np.zeros(m.nelem)
+        grad = np.zeros((m.nelem, 8)) if want_grad else None
+        faces = np.zeros((2, m.naface, 4)) if want_faces else None
+        rc = orc().orc_flow_residual(self.h, _dp(u), _dp(res), int(gettimesteps), _dp(dtm),
+                                     _dp(grad) if want_grad else None, _dp(faces) if want_faces else None)
+        if rc != 0:
+            raise RuntimeError("oracle residual failed")
+        return res, dtm, grad, faces
+
+    def gradients(self, uprim, ug):
+        grad = np.zeros((self.mesh.nelem, 8))
+        uprim = np.ascontiguousarray(uprim); ug = np.ascontiguousarray(ug)
+        orc().orc_flow_gradients(self.h, _dp(uprim), _dp(ug), _dp(grad))
+        return grad
+
+    def face_values(self, uprim, ug, grad):
+        m = self.mesh
+        ufl = np.zeros((m.naface, 4)); ufr = np.zeros((m.naface, 4))
+        uprim = np.ascontiguousarray(uprim); ug = np.ascontiguousarray(ug); grad = np.ascontiguousarray(grad)
+        orc().orc_flow_face_values(self.h, _dp(uprim), _dp(ug), _dp(grad), _dp(ufl), _dp(ufr))
+        return ufl, ufr
+
+    def boundary_states(self, ins):
+        ins = np.ascontiguousarray(ins)
+        gs = np.zeros_like(ins)
+        orc().orc_flow_boundary_states(self.h, _dp(ins), _dp(gs))
+        return gs
+
+    def get_gradients(self, u):
+        u = np.ascontiguousarray(u)
+        g = np.zeros((self.mesh.nelem, 8))
+        orc().orc_flow_get_gradients(self.h, _dp(u), _dp(g))
+        return g
+
+    def surface_data(self, u, grads, marker):
+        out = np.zeros(3)
+        u = np.ascontiguousarray(u); grads = np.ascontiguousarray(grads)
+        orc().orc_flow_surface_data(self.h, _dp(u), _dp(grads), int(marker), _dp(out))
+        return out
+
+    def entropy_error(self, u):
+        u = np.ascontiguousarray(u)
+        return orc().orc_flow_entropy(self.h, _dp(u))
+
+    def forward_euler(self, u, cfl, tol, maxiter):
+        u = np.ascontiguousarray(u, dtype=np.float64).copy()
+        steps = C.c_int(0)
+        hist = np.zeros(max(maxiter, 1))
+        code = orc().orc_forward_euler(self.h, _dp(u), C.c_double(cfl), C.c_double(tol), int(maxiter),
+                                       C.byref(steps), _dp(hist))
+        return code, steps.value, hist[:steps.value].copy(), u
+
+    def __del__(self):
+        try:
+            orc().orc_flow_free(self.h)
+        except Exception:
+            pass
