@@ -10,8 +10,20 @@
 namespace fvg {
 
 constexpr int MAXCOL = 8;          ///< greedy edge colouring of a degree-4 graph needs at most 7
-constexpr int FACE_BLOCK = 256;    ///< threads per CTA of the face kernel
-constexpr int CELL_BLOCK = 128;    ///< threads per CTA of the cell kernels
+#ifndef FVG_FACE_BLOCK
+#define FVG_FACE_BLOCK 256
+#endif
+#ifndef FVG_FACE_MINB
+#define FVG_FACE_MINB 1
+#endif
+#ifndef FVG_CELL_BLOCK
+#define FVG_CELL_BLOCK 128
+#endif
+#ifndef FVG_CELL_MINB
+#define FVG_CELL_MINB 1
+#endif
+constexpr int FACE_BLOCK = FVG_FACE_BLOCK;    ///< threads per CTA of the face kernel
+constexpr int CELL_BLOCK = FVG_CELL_BLOCK;    ///< threads per CTA of the cell kernels
 
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);

@@ -50,7 +50,7 @@ __device__ __forceinline__ double muscl_term(double delta, double dlr) {
 }
 
 template <int FLUX, int RECON, int VISC>
-__global__ void __launch_bounds__(FACE_BLOCK)
+__global__ void __launch_bounds__(FACE_BLOCK, FVG_FACE_MINB)
 face_kernel(const FaceArgs A)
 {
 	extern __shared__ double sm[];

@@ -19,7 +19,7 @@ __device__ __forceinline__ double rsqrt_exact(double x) { return 1.0/sqrt(x); }
 enum { LM_NONE = 0, LM_BJ = 1, LM_VENKAT = 2 };
 
 template <int GRAD, int LIM, bool PRIM_IN>
-__global__ void __launch_bounds__(CELL_BLOCK)
+__global__ void __launch_bounds__(CELL_BLOCK, FVG_CELL_MINB)
 cell_kernel(const CellArgs A)
 {
 	const DMesh &M = A.m;

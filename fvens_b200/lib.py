@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfvens_b200.so")
+LIB_PATH = os.environ.get("FVENS_B200_LIB") or os.path.join(_HERE, "libfvens_b200.so")
 
 FLUX = {"LLF": 0, "VANLEER": 1, "AUSM": 2, "AUSMPLUS": 3, "ROE": 4, "HLL": 5, "HLLC": 6}
 GRAD = {"NONE": 0, "ZERO": 0, "GREENGAUSS": 1, "LEASTSQUARES": 2}
