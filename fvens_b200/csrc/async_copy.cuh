@@ -1,0 +1,52 @@
+/* Asynchronous global->shared staging primitives for sm_100a: 1-D bulk copies through the TMA unit
+ * (cp.async.bulk, completion counted on an mbarrier; SASS: UBLKCP) for contiguous ranges, and 16-byte
+ * cp.async (SASS: LDGSTS) for gathered rows. Neither occupies registers while in flight, which is the
+ * point: the tile kernels issue all of a tile's traffic up front and compute out of shared memory.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace fvg {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+	// make the initialised barrier visible to the async (TMA) proxy
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+/// Spins (with back-off inside try_wait) until the barrier's phase with the given parity completes.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"FVG_WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra FVG_DONE_%=;\n"
+		"bra FVG_WAIT_%=;\n"
+		"FVG_DONE_%=:\n"
+		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+/// Contiguous copy of `bytes` (multiple of 16, both addresses 16-byte aligned) global -> shared.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+/// 16-byte asynchronous copy global -> shared (L2 only: the data is consumed from shared memory)
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+} // namespace fvg

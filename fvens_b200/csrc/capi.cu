@@ -25,6 +25,7 @@ GasParams make_gas(const fvg_physics &p, double limiter_param)
 	G.g = p.gamma; G.Minf = p.Minf; G.Tinf = p.Tinf; G.Reinf = p.Reinf; G.Pr = p.Pr;
 	G.sCT = 110.5/p.Tinf;
 	G.gm1 = p.gamma - 1.0;
+	G.igm1 = 1.0/(p.gamma - 1.0);
 	G.gM2 = p.gamma*p.Minf*p.Minf;
 	G.pinf = 1.0/(p.gamma*p.Minf*p.Minf);
 	G.uinf[0] = 1.0;
@@ -73,7 +74,7 @@ static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s)
 	const FlowPlan &P = f->plan;
 	if(!P.order2) return 0;
 	CellArgs a;
-	a.m = f->mesh->d; a.gas = f->gas; a.bbc = f->d_bbc; a.u = u; a.ug = nullptr; a.gin = nullptr;
+	a.m = f->mesh->d; a.gas = f->gas; a.u = u; a.ug = nullptr; a.gin = nullptr;
 	a.bnd_policy = P.bnd_policy;
 	int rc;
 	if(P.recon == FVG_RECON_WENO) {
@@ -112,7 +113,7 @@ static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumul
 {
 	const FlowPlan &P = f->plan;
 	FaceArgs a;
-	a.m = f->mesh->d; a.gas = f->gas; a.bbc = f->d_bbc; a.u = u;
+	a.m = f->mesh->d; a.gas = f->gas; a.u = u;
 	a.lg = f->d_lg; a.gu = viscous_gradients(f);
 	a.epilogue = epilogue; a.accumulate = accumulate; a.gettimesteps = gettimesteps;
 	a.res = res; a.dtm = dtm; a.cfl = cfl; a.unew = unew; a.partial = f->d_partial;
@@ -254,15 +255,21 @@ int fvg_flow_create(fvg_mesh *mesh, const fvg_physics *phys, const fvg_numerics 
 	f->mesh = mesh;
 	f->phys = *phys;
 	f->gas = make_gas(*phys, num->limiter_param);
-	f->gas.nbc = nbc;
-	for(int i = 0; i < nbc; i++) {
+	for(int i = 0; i < nbc; i++)
 		if(bcs[i].type < 0 || bcs[i].type > 7 || bcs[i].type == PERIODIC_BC) {
 			// reference: create_const_flowBCs throws for types without a FlowBC class (abc.cpp:493-494)
 			set_error("fvg_flow_create: boundary condition type " + std::to_string(bcs[i].type) + " is not available");
 			return FVG_ERR_UNSUPPORTED;
 		}
-		f->gas.bc[i].tag = bcs[i].tag; f->gas.bc[i].type = bcs[i].type;
-		f->gas.bc[i].v0 = bcs[i].vals[0]; f->gas.bc[i].v1 = bcs[i].vals[1];
+	// the BC table is indexed by the mesh's marker slots; every marker present in the mesh needs a BC
+	// (reference: bcs.at(tag) throws std::out_of_range in compute_boundary_state, flow_spatial.cpp:92)
+	f->gas.nbc = (int)mesh->h_markers.size();
+	for(size_t sl = 0; sl < mesh->h_markers.size(); sl++) {
+		int k = -1;
+		for(int i = 0; i < nbc; i++) if(bcs[i].tag == mesh->h_markers[sl]) k = i;
+		if(k < 0) { set_error("fvg_flow_create: no boundary condition for marker " + std::to_string(mesh->h_markers[sl])); return FVG_ERR_INVALID; }
+		f->gas.bc[sl].tag = bcs[k].tag; f->gas.bc[sl].type = bcs[k].type;
+		f->gas.bc[sl].v0 = bcs[k].vals[0]; f->gas.bc[sl].v1 = bcs[k].vals[1];
 	}
 	FlowPlan &P = f->plan;
 	P.flux = num->flux; P.gradient = num->gradient; P.recon = num->reconstruction;
@@ -273,19 +280,8 @@ int fvg_flow_create(fvg_mesh *mesh, const fvg_physics *phys, const fvg_numerics 
 	P.need_gu = P.order2 && (P.recon == FVG_RECON_WENO || P.recon == FVG_RECON_VANALBADA ||
 	                         (P.visc != VISC_NONE && limited));
 
-	// boundary face -> BC table index; every marker present in the mesh needs a BC
-	// (reference: bcs.at(tag) throws std::out_of_range in compute_boundary_state, flow_spatial.cpp:92)
-	const int nb = mesh->d.nbface, n = mesh->d.ncell;
-	std::vector<int> bbc(nb);
-	for(int b = 0; b < nb; b++) {
-		int k = -1;
-		for(int i = 0; i < nbc; i++) if(bcs[i].tag == mesh->h_btag[b]) k = i;
-		if(k < 0) { set_error("fvg_flow_create: no boundary condition for marker " + std::to_string(mesh->h_btag[b])); return FVG_ERR_INVALID; }
-		bbc[b] = k;
-	}
+	const int n = mesh->d.ncell;
 	int rc;
-	if((rc = dev_alloc(f.get(), &f->d_bbc, nb)) != 0) return rc;
-	if(nb) FVG_CUDA(cudaMemcpy(f->d_bbc, bbc.data(), sizeof(int)*nb, cudaMemcpyHostToDevice));
 	if(P.need_lg && (rc = dev_alloc(f.get(), &f->d_lg, 8*(size_t)n)) != 0) return rc;
 	if(P.need_gu && (rc = dev_alloc(f.get(), &f->d_gu, 8*(size_t)n)) != 0) return rc;
 	if((rc = dev_alloc(f.get(), &f->d_partial, mesh->d.ntile)) != 0) return rc;
@@ -415,7 +411,7 @@ int fvg_gradients(fvg_flow *f, const double *d_uprim, const double *d_ug, double
 	const double *u = nullptr;
 	int rc = to_device_order(f, d_uprim, 4, &su, &u, s);
 	CellArgs a;
-	a.m = D; a.gas = f->gas; a.bbc = f->d_bbc; a.u = u; a.ug = d_ug; a.gin = nullptr;
+	a.m = D; a.gas = f->gas; a.u = u; a.ug = d_ug; a.gin = nullptr;
 	a.lg = nullptr; a.bnd_policy = f->plan.bnd_policy;
 	if(rc == 0 && !f->mesh->identity_perm) {
 		const cudaError_t e = cudaMallocAsync((void**)&sg, sizeof(double)*8*(size_t)D.ncell, s);
@@ -448,7 +444,7 @@ int fvg_face_values(fvg_flow *f, const double *d_uprim, const double *d_ug, cons
 		if(rc == 0 && P.recon == FVG_RECON_WENO) { rc = launch_weno_kernel(D, f->gas.limiter_param, g, slg, s); f->launches++; }
 		else if(rc == 0) {
 			CellArgs a;
-			a.m = D; a.gas = f->gas; a.bbc = f->d_bbc; a.u = u; a.ug = d_ug; a.gin = g; a.lg = slg; a.gu = nullptr;
+			a.m = D; a.gas = f->gas; a.u = u; a.ug = d_ug; a.gin = g; a.lg = slg; a.gu = nullptr;
 			a.bnd_policy = P.bnd_policy;
 			rc = launch_cell_kernel(3 /*given*/, limiter_mode(P.recon), true, a, s); f->launches++;
 		}
@@ -465,7 +461,7 @@ int fvg_face_values(fvg_flow *f, const double *d_uprim, const double *d_ug, cons
 int fvg_boundary_states(fvg_flow *f, const double *d_ins, double *d_gs, void *stream)
 {
 	if(!f || !d_ins || !d_gs) { set_error("fvg_boundary_states: null argument"); return FVG_ERR_INVALID; }
-	const int rc = launch_boundary_states(f->mesh->d, f->gas, f->d_bbc, d_ins, d_gs, static_cast<cudaStream_t>(stream));
+	const int rc = launch_boundary_states(f->mesh->d, f->gas, d_ins, d_gs, static_cast<cudaStream_t>(stream));
 	if(rc == 0) f->launches++;
 	return rc;
 }
@@ -483,13 +479,13 @@ int fvg_get_gradients(fvg_flow *f, const double *d_u, double *d_grads, void *str
 		if(e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
 	}
 	// conserved ghost states from the conserved cell states; then the gradient scheme on conserved variables
-	if(rc == 0) { rc = launch_boundary_prim_ghosts(D, f->gas, f->d_bbc, u, sug, false, s); f->launches++; }
+	if(rc == 0) { rc = launch_boundary_prim_ghosts(D, f->gas, u, sug, false, s); f->launches++; }
 	if(rc == 0 && !f->mesh->identity_perm) {
 		const cudaError_t e = cudaMallocAsync((void**)&sg, sizeof(double)*8*(size_t)D.ncell, s);
 		if(e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
 	}
 	CellArgs a;
-	a.m = D; a.gas = f->gas; a.bbc = f->d_bbc; a.u = u; a.ug = sug; a.gin = nullptr; a.lg = nullptr;
+	a.m = D; a.gas = f->gas; a.u = u; a.ug = sug; a.gin = nullptr; a.lg = nullptr;
 	a.gu = f->mesh->identity_perm ? d_grads : sg; a.bnd_policy = f->plan.bnd_policy;
 	if(rc == 0) { rc = launch_cell_kernel(f->plan.gradient, 0, true, a, s); f->launches++; }
 	if(rc == 0 && !f->mesh->identity_perm) { rc = launch_permute_rows(sg, d_grads, D.new2old, D.ncell, 8, false, false, s); f->launches++; }
@@ -508,7 +504,9 @@ int fvg_surface_data(fvg_flow *f, const double *d_u, const double *d_grads, int 
 	int rc = to_device_order(f, d_u, 4, &su, &u, s);
 	if(rc == 0) rc = to_device_order(f, d_grads, 8, &sg, &g, s);
 	if(rc == 0) { const cudaError_t e = cudaMalloc((void**)&d4, 4*sizeof(double)); if(e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
-	if(rc == 0) { rc = launch_surface_data(f->mesh->d, f->gas, f->phys.aoa, u, g, marker, d4, s); f->launches++; }
+	if(rc == 0) { int slot = -1;
+		for(size_t q = 0; q < f->mesh->h_markers.size(); q++) if(f->mesh->h_markers[q] == marker) slot = (int)q;
+		rc = launch_surface_data(f->mesh->d, f->gas, f->phys.aoa, u, g, slot, d4, s); f->launches++; }
 	double h4[4] = {0,0,0,0};
 	if(rc == 0) { const cudaError_t e = cudaMemcpy(h4, d4, sizeof(h4), cudaMemcpyDeviceToHost); if(e != cudaSuccess) rc = cuda_fail(e, "D2H", __FILE__, __LINE__); }
 	h_out3[0] = h4[0]; h_out3[1] = h4[1]; h_out3[2] = h4[2];

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <queue>
+#include <climits>
 
 namespace fvg {
 
@@ -120,8 +121,11 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 		return FVG_ERR_UNSUPPORTED;
 	}
 	if(mw < 3 || mw > 4) { set_error("fvg_mesh_create: maxnnode must be 3 or 4"); return FVG_ERR_INVALID; }
-	int TC = opts && opts->tile_cells > 0 ? opts->tile_cells : 512;
-	if(TC % 32 != 0 || TC > 2048) { set_error("fvg_mesh_create: tile_cells must be a multiple of 32, <= 2048"); return FVG_ERR_INVALID; }
+	const int TC = opts && opts->tile_cells > 0 ? opts->tile_cells : 256;
+	if(TC % 32 != 0 || TC > 1024) { set_error("fvg_mesh_create: tile_cells must be a multiple of 32, <= 1024"); return FVG_ERR_INVALID; }
+	// capacities of a tile's shared-memory staging areas: halo cells and stream entries
+	const int HMAX = std::max(32, (3*TC/8 + 31)/32*32);
+	const int EMAX = (2*TC + TC/8 + 31)/32*32;
 	const int reorder = opts ? opts->reorder : FVG_REORDER_NONE;
 
 	// ---- geometry in reference numbering
@@ -132,6 +136,17 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 			for(int j = 0; j < hm->nnode[i]; j++) c += hm->coords[2*(size_t)hm->inpoel[(size_t)i*mw+j]+d];
 			rc[2*(size_t)i+d] = c/(double)hm->nnode[i];
 		}
+
+	// ---- boundary markers -> slots of the flow's BC table
+	m->h_btag.resize(nb);
+	for(int b = 0; b < nb; b++) m->h_btag[b] = hm->btags[(size_t)b*hm->nbtag];
+	m->h_markers.assign(m->h_btag.begin(), m->h_btag.end());
+	std::sort(m->h_markers.begin(), m->h_markers.end());
+	m->h_markers.erase(std::unique(m->h_markers.begin(), m->h_markers.end()), m->h_markers.end());
+	if((int)m->h_markers.size() > MAX_BC) { set_error("fvg_mesh_create: more than 16 distinct boundary markers"); return FVG_ERR_UNSUPPORTED; }
+	std::vector<int> bslot(nb);
+	for(int b = 0; b < nb; b++)
+		bslot[b] = (int)(std::lower_bound(m->h_markers.begin(), m->h_markers.end(), m->h_btag[b]) - m->h_markers.begin());
 
 	// ---- permutation
 	std::vector<int> &new2old = m->h_new2old, &old2new = m->h_old2new;
@@ -145,140 +160,198 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 	for(int i = 0; i < n; i++) if(new2old[i] != i) { m->identity_perm = false; break; }
 	m->reorder = reorder;
 
-	const int ntile = (n + TC - 1)/TC;
-
-	// ---- face streams: count, fill in reference face order, colour, sort by colour
-	std::vector<int> fsoff((size_t)ntile+1, 0);
 	auto faceL = [&](int f) { return old2new[hm->intfac[4*(size_t)f]]; };
-	auto faceR = [&](int f) { return f < nb ? -2 - f : old2new[hm->intfac[4*(size_t)f+1]]; };
+	auto faceR = [&](int f) { return f < nb ? -1 : old2new[hm->intfac[4*(size_t)f+1]]; };
+	// neighbour (device numbering) of device cell i across local face j: >= 0 cell, -1 boundary
+	auto nbr_of = [&](int i, int j) {
+		const int e = hm->esuel[(size_t)new2old[i]*mw+j];
+		return e < n ? old2new[e] : -1;
+	};
+
+	// ---- tiles: greedy ranges of consecutive cells within the capacities
+	std::vector<int> tcell0(1, 0), thoff(1, 0), thalo;
+	std::vector<int> stamp((size_t)n, -1);
 	long long distsum = 0;
+	{
+		std::vector<int> halo;
+		int s = 0;
+		while(s < n) {
+			int nc = std::min(TC, n - s);
+			const int t = (int)tcell0.size() - 1;
+			for(int attempt = 0; ; attempt++) {
+				halo.clear();
+				int E = 0;
+				const int tag = t*64 + (attempt & 63);      // unique stamp per (tile, attempt)
+				for(int i = s; i < s+nc; i++) {
+					const int nn = hm->nnode[new2old[i]];
+					for(int j = 0; j < nn; j++) {
+						const int q = nbr_of(i, j);
+						if(q < 0) { E++; continue; }
+						if(q >= s && q < s+nc) { if(i < q) E++; continue; }
+						E++;
+						if(stamp[q] != tag) { stamp[q] = tag; halo.push_back(q); }
+					}
+				}
+				if(((int)halo.size() <= HMAX && E <= EMAX) || nc == 1) break;
+				nc = std::max(1, std::min(nc - 1, (int)(nc*0.8)));
+				if(attempt >= 62) {    // stamps would repeat: clear them
+					for(int q : halo) stamp[q] = -1;
+				}
+			}
+			if((int)halo.size() > HMAX) { set_error("fvg_mesh_create: a single cell exceeds the halo capacity"); return FVG_ERR_INVALID; }
+			std::sort(halo.begin(), halo.end());
+			thalo.insert(thalo.end(), halo.begin(), halo.end());
+			thoff.push_back((int)thalo.size());
+			s += nc;
+			tcell0.push_back(s);
+		}
+	}
+	const int ntile = (int)tcell0.size() - 1;
+	std::vector<int> tile_of((size_t)n);
+	for(int t = 0; t < ntile; t++) for(int i = tcell0[t]; i < tcell0[t+1]; i++) tile_of[i] = t;
+
+	// ---- face streams: count (padded to 4), fill in reference face order, colour, sort by colour
+	std::vector<int> fsoff((size_t)ntile+1, 0);
 	for(int f = 0; f < nf; f++) {
 		const int L = faceL(f), R = faceR(f);
-		fsoff[L/TC+1]++;
+		fsoff[tile_of[L]+1]++;
 		if(R >= 0) {
-			if(R/TC != L/TC) fsoff[R/TC+1]++;
+			if(tile_of[R] != tile_of[L]) fsoff[tile_of[R]+1]++;
 			distsum += std::abs(L-R);
 		}
 	}
-	for(int t = 0; t < ntile; t++) fsoff[t+1] += fsoff[t];
+	int ncopies = 0;
+	for(int t = 0; t < ntile; t++) { ncopies += fsoff[t+1]; fsoff[t+1] = fsoff[t] + (fsoff[t+1] + 3)/4*4; }
 	const int ns = fsoff[ntile];
-	m->ncut_dup = ns - nf;
+	m->ncut_dup = ncopies - nf;
 	m->mean_nbr_dist = nf > nb ? (double)distsum/(double)(nf-nb) : 0.0;
 
-	std::vector<int> sface((size_t)ns);        // reference face of each entry, -1-f for duplicates
+	const int PAD = INT_MIN;
+	std::vector<int> sface((size_t)ns, PAD);    // reference face of each entry, -1-f for duplicates, PAD for padding
 	{
 		std::vector<int> pos(fsoff.begin(), fsoff.end()-1);
 		for(int f = 0; f < nf; f++) {
 			const int L = faceL(f), R = faceR(f);
-			sface[pos[L/TC]++] = f;
-			if(R >= 0 && R/TC != L/TC) sface[pos[R/TC]++] = -1-f;
+			sface[pos[tile_of[L]]++] = f;
+			if(R >= 0 && tile_of[R] != tile_of[L]) sface[pos[tile_of[R]]++] = -1-f;
 		}
 	}
 	std::vector<int> fcoloff((size_t)ntile*(MAXCOL+1), 0);
-	std::vector<int> scolour((size_t)ns);
+	std::vector<int> scolour((size_t)ns, MAXCOL-1);
 	m->max_colours = 0;
 	{
 		std::vector<unsigned char> used(TC);
-		std::vector<int> tmp;
+		std::vector<int> tmp, ctmp;
 		for(int t = 0; t < ntile; t++) {
-			const int c0 = t*TC, e0 = fsoff[t], e1 = fsoff[t+1];
+			const int c0 = tcell0[t], e0 = fsoff[t], e1 = fsoff[t+1];
 			std::fill(used.begin(), used.end(), 0);
 			int cnt[MAXCOL] = {0};
 			for(int e = e0; e < e1; e++) {
+				if(sface[e] == PAD) { scolour[e] = MAXCOL-1; cnt[MAXCOL-1]++; continue; }   // padding sorts last
 				const int f = sface[e] >= 0 ? sface[e] : -1-sface[e];
 				const int L = faceL(f), R = faceR(f);
 				unsigned mask = 0;
-				if(L/TC == t) mask |= used[L-c0];
-				if(R >= 0 && R/TC == t) mask |= used[R-c0];
+				if(tile_of[L] == t) mask |= used[L-c0];
+				if(R >= 0 && tile_of[R] == t) mask |= used[R-c0];
 				int c = 0;
 				while(mask & (1u << c)) c++;
 				if(c >= MAXCOL) { set_error("fvg_mesh_create: edge colouring needs more than 8 colours"); return FVG_ERR_INVALID; }
-				if(L/TC == t) used[L-c0] |= (unsigned char)(1u << c);
-				if(R >= 0 && R/TC == t) used[R-c0] |= (unsigned char)(1u << c);
+				if(tile_of[L] == t) used[L-c0] |= (unsigned char)(1u << c);
+				if(R >= 0 && tile_of[R] == t) used[R-c0] |= (unsigned char)(1u << c);
 				scolour[e] = c; cnt[c]++;
 				m->max_colours = std::max(m->max_colours, c+1);
 			}
 			int *co = &fcoloff[(size_t)t*(MAXCOL+1)];
 			co[0] = e0;
 			for(int c = 0; c < MAXCOL; c++) co[c+1] = co[c] + cnt[c];
-			// stable counting sort of the segment by colour
 			tmp.assign(sface.begin()+e0, sface.begin()+e1);
+			ctmp.assign(scolour.begin()+e0, scolour.begin()+e1);
 			int pos[MAXCOL];
 			for(int c = 0; c < MAXCOL; c++) pos[c] = co[c];
-			std::vector<int> ctmp(scolour.begin()+e0, scolour.begin()+e1);
 			for(int k = 0; k < e1-e0; k++) { const int c = ctmp[k]; sface[pos[c]] = tmp[k]; scolour[pos[c]] = c; pos[c]++; }
 		}
 	}
 
-	// ---- per-entry arrays
-	std::vector<int> fL((size_t)ns), fR((size_t)ns);
-	std::vector<double2> fn((size_t)ns), fgr((size_t)ns);
-	std::vector<double> flen((size_t)ns);
+	// ---- per-entry arrays with tile-local cell indices
+	std::vector<unsigned> &fLR = m->h_fLR;
+	fLR.assign((size_t)ns, LR_PAD);
+	std::vector<double2> fn((size_t)ns, make_double2(1.0, 0.0)), fgr((size_t)ns, make_double2(0.0, 0.0));
+	std::vector<double> flen((size_t)ns, 0.0);
 	std::vector<int> own_entry((size_t)nf), dup_entry((size_t)nf, -1);
-	m->h_fref.resize(ns); m->h_fcolour = scolour; m->h_ftile.resize(ns);
+	m->h_fref.assign(ns, PAD); m->h_fcolour = scolour; m->h_ftile.resize(ns);
+	auto local_of = [&](int t, int g) -> unsigned {
+		if(tile_of[g] == t) return (unsigned)(g - tcell0[t]);
+		const int *hb = &thalo[thoff[t]], *he = &thalo[thoff[t+1]];
+		const int *it = std::lower_bound(hb, he, g);
+		return (unsigned)((tcell0[t+1]-tcell0[t]) + (int)(it - hb));
+	};
 	for(int t = 0; t < ntile; t++)
 		for(int e = fsoff[t]; e < fsoff[t+1]; e++) {
+			m->h_ftile[e] = t;
+			if(sface[e] == PAD) continue;
 			const int f = sface[e] >= 0 ? sface[e] : -1-sface[e];
-			fL[e] = faceL(f); fR[e] = faceR(f);
+			const int L = faceL(f), R = faceR(f);
+			const unsigned lL = local_of(t, L);
+			const unsigned lR = R >= 0 ? local_of(t, R) : (LR_BND | (unsigned)bslot[f]);
+			fLR[e] = lL | (lR << 16);
 			fn[e] = make_double2(hm->facemetric[3*(size_t)f], hm->facemetric[3*(size_t)f+1]);
 			flen[e] = hm->facemetric[3*(size_t)f+2];
 			const int p0 = hm->intfac[4*(size_t)f+2], p1 = hm->intfac[4*(size_t)f+3];
 			double g[2];
 			for(int d = 0; d < 2; d++) {
-				double s = 0;
-				s += hm->coords[2*(size_t)p0+d];
-				s += hm->coords[2*(size_t)p1+d];
-				g[d] = s/2;
+				double sum = 0;
+				sum += hm->coords[2*(size_t)p0+d];
+				sum += hm->coords[2*(size_t)p1+d];
+				g[d] = sum/2;
 			}
 			fgr[e] = make_double2(g[0], g[1]);
 			if(sface[e] >= 0) own_entry[f] = e; else dup_entry[f] = e;
-			m->h_fref[e] = sface[e]; m->h_ftile[e] = t;
+			m->h_fref[e] = sface[e];
 		}
 
 	// ---- per-cell arrays in device order
-	std::vector<int4> nbr((size_t)n), cface((size_t)n);
+	std::vector<uint4> cloc((size_t)n);
 	std::vector<double2> drc((size_t)n);
 	std::vector<double> area((size_t)n), clength((size_t)n);
 	for(int i = 0; i < n; i++) {
-		const int o = new2old[i];
-		int a[4] = {-1,-1,-1,-1}, c[4] = {0,0,0,0};
+		const int o = new2old[i], t = tile_of[i];
+		unsigned a[4] = {NB_NONE, NB_NONE, NB_NONE, NB_NONE}, c[4] = {0,0,0,0};
 		for(int j = 0; j < hm->nnode[o]; j++) {
 			const int e = hm->esuel[(size_t)o*mw+j];
 			const int f = hm->elemface[(size_t)o*mw+j];
 			if(e < 0 || f < 0 || f >= nf) { set_error("fvg_mesh_create: inconsistent esuel/elemface"); return FVG_ERR_INVALID; }
-			a[j] = e < n ? old2new[e] : -2 - (e - n);
 			if(e >= n && (e-n != f || f >= nb)) { set_error("fvg_mesh_create: boundary ghost index does not match its face"); return FVG_ERR_INVALID; }
+			a[j] = e < n ? local_of(t, old2new[e]) : NB_BND;
 			const bool isL = hm->intfac[4*(size_t)f] == o;
 			if(!isL && (f < nb || hm->intfac[4*(size_t)f+1] != o)) { set_error("fvg_mesh_create: elemface/intfac mismatch"); return FVG_ERR_INVALID; }
 			// the copy of the face that lives in this cell's tile
 			int entry = own_entry[f];
 			if(!isL && dup_entry[f] >= 0) entry = dup_entry[f];
-			c[j] = entry | (isL ? 0 : (int)0x80000000u);
+			if(m->h_ftile[entry] != t) { set_error("fvg_mesh_create: internal error, face copy not in the cell's tile"); return FVG_ERR_INVALID; }
+			c[j] = (unsigned)(entry - fsoff[t]) | (isL ? 0u : 0x8000u);
 		}
-		nbr[i] = make_int4(a[0], a[1], a[2], a[3]);
-		cface[i] = make_int4(c[0], c[1], c[2], c[3]);
+		cloc[i] = make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), c[0] | (c[1] << 16), c[2] | (c[3] << 16));
 		drc[i] = make_double2(rc[2*(size_t)o], rc[2*(size_t)o+1]);
 		area[i] = hm->area[o];
 		double l2 = 0;
 		const int nn = hm->nnode[o];
 		for(int j = 0; j < nn; j++) {
 			const int p = hm->inpoel[(size_t)o*mw+j], q = hm->inpoel[(size_t)o*mw+(j+1)%nn];
-			double s = 0;
-			for(int d = 0; d < 2; d++) { const double t = hm->coords[2*(size_t)p+d] - hm->coords[2*(size_t)q+d]; s += t*t; }
-			if(l2 < s) l2 = s;
+			double sum = 0;
+			for(int d = 0; d < 2; d++) { const double tt = hm->coords[2*(size_t)p+d] - hm->coords[2*(size_t)q+d]; sum += tt*tt; }
+			if(l2 < sum) l2 = sum;
 		}
 		clength[i] = std::sqrt(l2);
 	}
 
 	// ---- boundary arrays (reference boundary-face order)
-	std::vector<int> bcell((size_t)nb), bentry((size_t)nb);
+	std::vector<int> bcell((size_t)nb);
 	std::vector<double2> rcbp((size_t)nb);
-	m->h_btag.resize(nb);
+	m->h_bentry.resize(nb);
 	for(int b = 0; b < nb; b++) {
 		const int o = hm->intfac[4*(size_t)b];
 		bcell[b] = old2new[o];
-		bentry[b] = own_entry[b];
-		m->h_btag[b] = hm->btags[(size_t)b*hm->nbtag];
+		m->h_bentry[b] = own_entry[b];
 		const double2 mid = fgr[own_entry[b]];
 		rcbp[b] = make_double2(2.0*mid.x - rc[2*(size_t)o], 2.0*mid.y - rc[2*(size_t)o+1]);
 	}
@@ -310,15 +383,17 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 
 	// ---- upload
 	DMesh &D = m->d;
-	D.ncell = n; D.nbface = nb; D.naface = nf; D.ntile = ntile; D.TC = TC; D.nstream = ns;
+	D.ncell = n; D.nbface = nb; D.naface = nf; D.ntile = ntile; D.TC = TC; D.HMAX = HMAX; D.EMAX = EMAX; D.nstream = ns;
 	int rcode;
 #define UP(vec, field) if((rcode = upload(m, vec, &D.field)) != 0) return rcode;
-	UP(nbr, nbr) UP(cface, cface) UP(drc, rc) UP(area, area) UP(V, wlsV) UP(clength, clength)
-	UP(fsoff, fsoff) UP(fcoloff, fcoloff) UP(fL, fL) UP(fR, fR) UP(fn, fn) UP(flen, flen) UP(fgr, fgr)
-	UP(m->h_fref, fref) UP(bcell, bcell) UP(bentry, bentry) UP(m->h_btag, btag) UP(rcbp, rcbp)
+	UP(cloc, cloc) UP(drc, rc) UP(area, area) UP(V, wlsV) UP(clength, clength)
+	UP(tcell0, tcell0) UP(thoff, thoff) UP(thalo, thalo)
+	UP(fsoff, fsoff) UP(fcoloff, fcoloff) UP(fLR, fLR) UP(fn, fn) UP(flen, flen) UP(fgr, fgr)
+	UP(m->h_fref, fref) UP(bcell, bcell) UP(m->h_bentry, bentry) UP(bslot, bslot) UP(rcbp, rcbp)
 	if(m->identity_perm) { D.new2old = nullptr; D.old2new = nullptr; }
 	else { UP(new2old, new2old) UP(old2new, old2new) }
 #undef UP
+	m->h_tcell0 = tcell0;
 	return 0;
 }
 
@@ -382,11 +457,18 @@ int fvg_mesh_permutation(const fvg_mesh *m, int *cell_new2old)
 	return 0;
 }
 
+int fvg_mesh_tile_offsets(const fvg_mesh *m, int *tile_cell0)
+{
+	if(!m || !tile_cell0) { set_error("fvg_mesh_tile_offsets: null argument"); return FVG_ERR_INVALID; }
+	std::memcpy(tile_cell0, m->h_tcell0.data(), sizeof(int)*m->h_tcell0.size());
+	return 0;
+}
+
 int fvg_mesh_stream(const fvg_mesh *m, int *entry_face, int *entry_colour, int *entry_tile)
 {
 	if(!m) { set_error("fvg_mesh_stream: null argument"); return FVG_ERR_INVALID; }
 	for(int e = 0; e < m->d.nstream; e++) {
-		if(entry_face) entry_face[e] = m->h_fref[e] >= 0 ? m->h_fref[e] : -1-m->h_fref[e];
+		if(entry_face) entry_face[e] = m->h_fref[e] == INT_MIN ? -1 : (m->h_fref[e] >= 0 ? m->h_fref[e] : -1-m->h_fref[e]);
 		if(entry_colour) entry_colour[e] = m->h_fcolour[e];
 		if(entry_tile) entry_tile[e] = m->h_ftile[e];
 	}

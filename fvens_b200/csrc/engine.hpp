@@ -14,13 +14,13 @@ constexpr int MAXCOL = 8;          ///< greedy edge colouring of a degree-4 grap
 #define FVG_FACE_BLOCK 256
 #endif
 #ifndef FVG_FACE_MINB
-#define FVG_FACE_MINB 1
+#define FVG_FACE_MINB 3
 #endif
 #ifndef FVG_CELL_BLOCK
-#define FVG_CELL_BLOCK 128
+#define FVG_CELL_BLOCK 256
 #endif
 #ifndef FVG_CELL_MINB
-#define FVG_CELL_MINB 1
+#define FVG_CELL_MINB 3
 #endif
 constexpr int FACE_BLOCK = FVG_FACE_BLOCK;    ///< threads per CTA of the face kernel
 constexpr int CELL_BLOCK = FVG_CELL_BLOCK;    ///< threads per CTA of the cell kernels
@@ -32,33 +32,48 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 	return ::fvg::cuda_fail(e_, #call, __FILE__, __LINE__); } while(0)
 
 /// Device-resident mesh in device (renumbered) cell order. All pointers are device memory.
+///
+/// Cells are grouped into TILES of consecutive cells (at most TC own cells, at most HMAX distinct
+/// out-of-tile neighbour cells = the tile's HALO, at most EMAX faces). Inside a tile everything is
+/// addressed with 16-bit LOCAL indices: own cell k -> k, halo cell h -> ncell_of_tile + h. Each tile
+/// has a contiguous FACE STREAM segment (every face touching one of its own cells; a face cut by a
+/// tile boundary has a copy in both tiles), sorted by colour, start and length padded to 4 entries.
 struct DMesh {
-	int ncell, nbface, naface, ntile, TC, nstream;
+	int ncell, nbface, naface, ntile, TC, HMAX, EMAX, nstream;
 	// per cell
-	const int4 *nbr;        ///< local face j -> neighbour cell; -1 none; <= -2 boundary face b = -2-v
-	const int4 *cface;      ///< local face j -> stream entry (own tile's copy); bit 31 set if the cell is the entry's right cell
+	const uint4 *cloc;      ///< x,y: local index of the neighbour across local face 0..3 (4 x u16; NB_NONE / NB_BND);
+	                        ///< z,w: local stream entry of local face 0..3 (4 x u16, bit 15 set if the cell is the entry's right cell)
 	const double2 *rc;      ///< cell centres
 	const double *area;
 	const double4 *wlsV;    ///< inverse least-squares matrices (V00, V01, V10, V11)
 	const double *clength;  ///< Venkatakrishnan length scale (longest edge)
 	// per tile
-	const int *fsoff;       ///< [ntile+1] stream segment of each tile
+	const int *tcell0;      ///< [ntile+1] first own cell of each tile
+	const int *thoff;       ///< [ntile+1] offsets into thalo
+	const int *thalo;       ///< halo cell ids (device numbering), ascending within a tile
+	const int *fsoff;       ///< [ntile+1] stream segment of each tile (multiples of 4)
 	const int *fcoloff;     ///< [ntile][MAXCOL+1] colour boundaries inside the segment (absolute entry ids)
 	// per stream entry
-	const int *fL, *fR;     ///< left / right cell; fR <= -2 marks boundary face b = -2-fR
+	const unsigned *fLR;    ///< local left | local right << 16; right >= LR_BND: boundary face with BC table index (right & 15);
+	                        ///< LR_PAD: padding entry
 	const double2 *fn;      ///< unit normal, left -> right
 	const double *flen;
 	const double2 *fgr;     ///< face midpoint
-	const int *fref;        ///< reference face id (intfac index); the duplicate copy of a cut face carries -1-id
+	const int *fref;        ///< reference face id (intfac index); duplicate copy of a cut face: -1-id; padding: INT_MIN
 	// per boundary face (reference order)
 	const int *bcell;       ///< device index of the interior cell
 	const int *bentry;      ///< stream entry
-	const int *btag;        ///< first boundary marker
+	const int *bslot;       ///< slot of the face's marker in the flow's BC table (sorted distinct markers)
 	const double2 *rcbp;    ///< ghost cell centre
 	// permutation (null when identity)
 	const int *new2old;
 	const int *old2new;
 };
+
+constexpr unsigned NB_NONE = 0xFFFFu;   ///< no such local face (4th slot of a triangle)
+constexpr unsigned NB_BND = 0xFFFEu;    ///< neighbour is a physical boundary ghost
+constexpr unsigned LR_BND = 0xFFE0u;    ///< right field of a boundary entry = LR_BND | bc index
+constexpr unsigned LR_PAD = 0xFFFFFFFFu;
 
 } // namespace fvg
 
@@ -77,6 +92,10 @@ struct fvg_mesh {
 	std::vector<int> h_new2old, h_old2new;
 	std::vector<int> h_fref, h_fcolour, h_ftile;
 	std::vector<int> h_btag;
+	std::vector<unsigned> h_fLR;               ///< kept so that flow creation can patch in the BC indices
+	std::vector<int> h_bentry;
+	std::vector<int> h_markers;                ///< sorted distinct boundary markers = slots of the BC table
+	std::vector<int> h_tcell0;
 };
 
 namespace fvg {
@@ -95,7 +114,6 @@ struct fvg_flow {
 	fvg::GasParams gas;
 	fvg::FlowPlan plan;
 	fvg_physics phys;
-	int *d_bbc = nullptr;          ///< [nbface] index into gas.bc
 	double *d_lg = nullptr;        ///< [ncell][8] limited gradients
 	double *d_gu = nullptr;        ///< [ncell][8] unlimited gradients
 	double *d_uperm = nullptr;     ///< [ncell][4] scratch state in device order (non-identity permutations)
@@ -119,7 +137,6 @@ namespace fvg {
 struct CellArgs {
 	DMesh m;
 	GasParams gas;
-	const int *bbc;
 	const double *u;       ///< [ncell][4] conserved (or primitive when prim_in)
 	const double *ug;      ///< [nbface][4] primitive ghost states (prim_in only)
 	const double *gin;     ///< given gradients (GRAD_GIVEN only)
@@ -142,14 +159,14 @@ int launch_face_values(const FaceValArgs &a, cudaStream_t s);
 
 int launch_permute_rows(const double *src, double *dst, const int *idx, int n, int width, bool gather,
                         bool accumulate, cudaStream_t s);
-int launch_boundary_states(const DMesh &m, const GasParams &g, const int *bbc, const double *ins,
+int launch_boundary_states(const DMesh &m, const GasParams &g, const double *ins,
                            double *gs, cudaStream_t s);
 int launch_cons2prim(const GasParams &g, const double *u, double *p, int n, cudaStream_t s);
-int launch_boundary_prim_ghosts(const DMesh &m, const GasParams &g, const int *bbc, const double *u,
+int launch_boundary_prim_ghosts(const DMesh &m, const GasParams &g, const double *u,
                                 double *ug, bool prim_out, cudaStream_t s);
 int launch_final_norm(const double *partial, int n, double *out, cudaStream_t s);
 int launch_surface_data(const DMesh &m, const GasParams &g, double aoa, const double *u, const double *grads,
-                        int marker, double *out4, cudaStream_t s);
+                        int slot, double *out4, cudaStream_t s);
 int launch_entropy(const DMesh &m, const GasParams &g, const double *u, double *out, cudaStream_t s);
 int launch_pointwise_flux(int flux, const GasParams &g, int n, const double *ul, const double *ur,
                           const double *nrm, double *out, cudaStream_t s);
@@ -167,7 +184,6 @@ enum FaceEpilogue { EP_RESIDUAL = 0, EP_STEP = 1 };
 struct FaceArgs {
 	DMesh m;
 	GasParams gas;
-	const int *bbc;
 	const double *u;       ///< [ncell][4] conserved, device order
 	const double *lg;      ///< gradients for the linear reconstruction
 	const double *gu;      ///< unlimited gradients (MUSCL, viscous)

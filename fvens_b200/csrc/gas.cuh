@@ -38,6 +38,7 @@ struct GasParams {
 	double Minf, Tinf, Reinf, Pr;
 	double sCT;      ///< Sutherland constant over Tinf (110.5/Tinf)
 	double gm1;      ///< g-1
+	double igm1;     ///< 1/(g-1)
 	double gM2;      ///< g*Minf^2
 	double pinf;     ///< 1/(g Minf^2)
 	double uinf[4];
@@ -47,18 +48,49 @@ struct GasParams {
 };
 
 // ---------------------------------------------------------------------------------------------
+// FP64 reciprocal / square root without the IEEE slow paths: the SFU seed (rcp.approx / rsqrt.approx,
+// relative error < 2^-22) refined by two Newton steps in FMA arithmetic. Results are within ~1 ulp of
+// the correctly rounded value; every use is on strictly positive, normal-range arguments (densities,
+// pressures, distances), so no special-case branches are needed. This is what keeps the hot kernels
+// free of the BSSY/BSYNC-wrapped subroutine calls that `/` and sqrt() compile to.
+
+__device__ __forceinline__ double frcp(double x) {
+	double y;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	double e = fma(-x, y, 1.0);
+	y = fma(y, e, y);
+	e = fma(-x, y, 1.0);
+	return fma(y, e, y);
+}
+__device__ __forceinline__ double frsqrt(double x) {
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	const double h = 0.5*x;
+	double e = fma(-h*y, y, 0.5);
+	y = fma(y, e, y);
+	e = fma(-h*y, y, 0.5);
+	return fma(y, e, y);
+}
+/// sqrt(x) for x > 0: x * rsqrt(x) with one correction step
+__device__ __forceinline__ double fsqrt(double x) {
+	const double r = frsqrt(x);
+	const double s = x*r;
+	return fma(0.5*r, fma(-s, s, x), s);
+}
+
+// ---------------------------------------------------------------------------------------------
 // basic gas relations on conserved variables u = (rho, rho vx, rho vy, rho E)
 
 __device__ __forceinline__ double pressure_cons(const GasParams &G, const double u[4]) {
 	return G.gm1*(u[3] - 0.5*(u[1]*u[1] + u[2]*u[2])/u[0]);
 }
 __device__ __forceinline__ void cons2prim(const GasParams &G, const double u[4], double p[4]) {
-	const double ir = 1.0/u[0];
+	const double ir = frcp(u[0]);
 	const double pr = G.gm1*(u[3] - 0.5*(u[1]*u[1] + u[2]*u[2])*ir);
 	p[0] = u[0]; p[1] = u[1]*ir; p[2] = u[2]*ir; p[3] = pr;
 }
 __device__ __forceinline__ void prim2cons(const GasParams &G, const double p[4], double u[4]) {
-	const double e = p[3]/G.gm1 + 0.5*p[0]*(p[1]*p[1] + p[2]*p[2]);
+	const double e = p[3]*G.igm1 + 0.5*p[0]*(p[1]*p[1] + p[2]*p[2]);
 	u[0] = p[0]; u[1] = p[0]*p[1]; u[2] = p[0]*p[2]; u[3] = e;
 }
 __device__ __forceinline__ double temperature(const GasParams &G, double rho, double p) {
@@ -83,12 +115,27 @@ template <bool WITH_C>
 __device__ __forceinline__ Side load_side(const GasParams &G, const double u[4], double nx, double ny) {
 	Side s;
 	s.r = u[0]; s.mx = u[1]; s.my = u[2]; s.E = u[3];
-	const double ir = 1.0/u[0];
+	const double ir = frcp(u[0]);
 	s.vx = u[1]*ir; s.vy = u[2]*ir;
 	s.vn = s.vx*nx + s.vy*ny;
 	s.p = G.gm1*(u[3] - 0.5*u[0]*(s.vx*s.vx + s.vy*s.vy));
 	s.H = (u[3] + s.p)*ir;
-	s.c = WITH_C ? sqrt(G.g*s.p*ir) : 0.0;
+	s.c = WITH_C ? fsqrt(G.g*s.p*ir) : 0.0;
+	return s;
+}
+
+/// Side straight from a primitive state (rho, vx, vy, p): skips the prim->cons->prim round trip the
+/// reference makes between reconstruction and flux (flow_spatial.cpp:740-754); differs at round-off only.
+template <bool WITH_C>
+__device__ __forceinline__ Side side_from_prim(const GasParams &G, const double p[4], double nx, double ny) {
+	Side s;
+	s.r = p[0]; s.vx = p[1]; s.vy = p[2]; s.p = p[3];
+	s.mx = p[0]*p[1]; s.my = p[0]*p[2];
+	s.E = p[3]*G.igm1 + 0.5*p[0]*(p[1]*p[1] + p[2]*p[2]);
+	s.vn = p[1]*nx + p[2]*ny;
+	const double ir = frcp(p[0]);
+	s.H = (s.E + s.p)*ir;
+	s.c = WITH_C ? fsqrt(G.g*s.p*ir) : 0.0;
 	return s;
 }
 
@@ -104,15 +151,15 @@ struct RoeAvg { double R, rho, vx, vy, vm2, vn, H, c; };
 __device__ __forceinline__ RoeAvg roe_average(const GasParams &G, const Side &a, const Side &b,
                                               double nx, double ny) {
 	RoeAvg q;
-	q.R = sqrt(b.r/a.r);
+	q.R = fsqrt(b.r*frcp(a.r));
 	q.rho = q.R*a.r;
-	const double iw = 1.0/(q.R + 1.0);
+	const double iw = frcp(q.R + 1.0);
 	q.vx = (q.R*b.vx + a.vx)*iw;
 	q.vy = (q.R*b.vy + a.vy)*iw;
 	q.H = (q.R*b.H + a.H)*iw;
 	q.vm2 = q.vx*q.vx + q.vy*q.vy;
 	q.vn = q.vx*nx + q.vy*ny;
-	q.c = sqrt(G.gm1*(q.H - 0.5*q.vm2));
+	q.c = fsqrt(G.gm1*(q.H - 0.5*q.vm2));
 	return q;
 }
 
@@ -137,14 +184,14 @@ __device__ __forceinline__ void flux_from_sides(const GasParams &G, const Side &
 	}
 	else if(FLUX == FLUX_VANLEER) {
 		const double g = G.g;
-		const double Ma = a.vn/a.c, Mb = b.vn/b.c;
+		const double Ma = a.vn*frcp(a.c), Mb = b.vn*frcp(b.c);
 		const double ie = 1.0/(2.0*(g*g - 1.0));
 		double fp[4], fm[4];
 		if(Ma < -1.0) { fp[0] = fp[1] = fp[2] = fp[3] = 0.0; }
 		else if(Ma > 1.0) normal_flux(a, nx, ny, fp);
 		else {
 			const double vm2 = a.vx*a.vx + a.vy*a.vy;
-			const double t = (2.0*a.c - a.vn)/g;
+			const double t = (2.0*a.c - a.vn)*(1.0/g);
 			const double w = G.gm1*a.vn + 2.0*a.c;
 			fp[0] = a.r*a.c*(Ma + 1.0)*(Ma + 1.0)*0.25;
 			fp[1] = fp[0]*(a.vx + nx*t);
@@ -155,7 +202,7 @@ __device__ __forceinline__ void flux_from_sides(const GasParams &G, const Side &
 		else if(Mb < -1.0) normal_flux(b, nx, ny, fm);
 		else {
 			const double vm2 = b.vx*b.vx + b.vy*b.vy;
-			const double t = (-2.0*b.c - b.vn)/g;
+			const double t = (-2.0*b.c - b.vn)*(1.0/g);
 			const double w = G.gm1*b.vn - 2.0*b.c;
 			fm[0] = -b.r*b.c*(Mb - 1.0)*(Mb - 1.0)*0.25;
 			fm[1] = fm[0]*(b.vx + nx*t);
@@ -165,7 +212,7 @@ __device__ __forceinline__ void flux_from_sides(const GasParams &G, const Side &
 		for(int k = 0; k < 4; k++) f[k] = fp[k] + fm[k];
 	}
 	else if(FLUX == FLUX_AUSM) {
-		const double Ma = a.vn/a.c, Mb = b.vn/b.c;
+		const double Ma = a.vn*frcp(a.c), Mb = b.vn*frcp(b.c);
 		double ML, MR, pL, pR;
 		if(fabs(Ma) <= 1.0) { ML = 0.25*(Ma + 1.0)*(Ma + 1.0); pL = ML*a.p*(2.0 - Ma); }
 		else if(Ma < -1.0) { ML = 0.0; pL = 0.0; }
@@ -184,14 +231,15 @@ __device__ __forceinline__ void flux_from_sides(const GasParams &G, const Side &
 		const double g = G.g;
 		const double k = 2.0*G.gm1/(g + 1.0);
 		const double vm2a = a.vx*a.vx + a.vy*a.vy, vm2b = b.vx*b.vx + b.vy*b.vy;
-		const double cs2a = (a.c*a.c/G.gm1 + 0.5*vm2a)*k;
-		const double cs2b = (b.c*b.c/G.gm1 + 0.5*vm2b)*k;
-		const double csa = sqrt(cs2a), csb = sqrt(cs2b);
+		const double igm1 = 1.0/G.gm1;
+		const double cs2a = (a.c*a.c*igm1 + 0.5*vm2a)*k;
+		const double cs2b = (b.c*b.c*igm1 + 0.5*vm2b)*k;
+		const double csa = fsqrt(cs2a), csb = fsqrt(cs2b);
 		const double corra = csa > a.vn ? csa : a.vn;
 		const double corrb = csb > -b.vn ? csb : -b.vn;
-		const double cta = csa*csa/corra, ctb = csb*csb/corrb;
+		const double cta = csa*csa*frcp(corra), ctb = csb*csb*frcp(corrb);
 		const double ch = cta < ctb ? cta : ctb;
-		const double ich = 1.0/ch;
+		const double ich = frcp(ch);
 		const double Ma = a.vn*ich, Mb = b.vn*ich;
 		double ML, MR, pL, pR;
 		if(fabs(Ma) <= 1.0) {
@@ -219,14 +267,14 @@ __device__ __forceinline__ void flux_from_sides(const GasParams &G, const Side &
 		double l0 = fabs(q.vn - q.c), l1 = fabs(q.vn), l3 = fabs(q.vn + q.c);
 		const double delta = 1.0e-4*q.c;
 		if(l0 < delta || l1 < delta || l3 < delta) {
-			const double i2d = 1.0/(2.0*delta), d2 = delta*delta;
+			const double i2d = frcp(2.0*delta), d2 = delta*delta;
 			if(l0 < delta) l0 = (l0*l0 + d2)*i2d;
 			if(l1 < delta) l1 = (l1*l1 + d2)*i2d;
 			if(l3 < delta) l3 = (l3*l3 + d2)*i2d;
 		}
 		const double dvn = b.vn - a.vn, dp = b.p - a.p, dr = b.r - a.r;
 		const double dvx = b.vx - a.vx, dvy = b.vy - a.vy;
-		const double ic2 = 1.0/(q.c*q.c);
+		const double ic2 = frcp(q.c*q.c);
 		const double rc = q.rho*q.c;
 		const double a0 = l0*(dp - rc*dvn)*(0.5*ic2);
 		const double a1 = l1*(dr - dp*ic2);
@@ -251,7 +299,7 @@ __device__ __forceinline__ void flux_from_sides(const GasParams &G, const Side &
 		double sr = b.vn + b.c; if(sr < q.vn + q.c) sr = q.vn + q.c;
 		const double sr0 = sr > 0.0 ? 0.0 : sr;
 		const double sl0 = sl > 0.0 ? 0.0 : sl;
-		const double is = 1.0/(sr - sl);
+		const double is = frcp(sr - sl);
 		const double t1 = (sr0 - sl0)*is, t2 = 1.0 - t1;
 		const double t3 = 0.5*(sr*fabs(sl) - sl*fabs(sr))*is;
 		f[0] = t1*b.vn*b.r + t2*a.vn*a.r - t3*(b.r - a.r);
@@ -264,12 +312,12 @@ __device__ __forceinline__ void flux_from_sides(const GasParams &G, const Side &
 		double sl = a.vn - a.c; if(sl > q.vn - q.c) sl = q.vn - q.c;
 		double sr = b.vn + b.c; if(sr < q.vn + q.c) sr = q.vn + q.c;
 		const double mb = b.r*(sr - b.vn), ma = a.r*(sl - a.vn);
-		const double sm = (mb*b.vn - ma*a.vn + a.p - b.p)/(mb - ma);
+		const double sm = (mb*b.vn - ma*a.vn + a.p - b.p)*frcp(mb - ma);
 		if(sl > 0.0) normal_flux(a, nx, ny, f);
 		else if(sm > 0.0) {
 			normal_flux(a, nx, ny, f);
 			const double pst = a.r*(a.vn - sl)*(a.vn - sm) + a.p;
-			const double k = 1.0/(sl - sm);
+			const double k = frcp(sl - sm);
 			const double w = sl - a.vn;
 			f[0] += sl*(a.r*w*k - a.r);
 			f[1] += sl*((w*a.mx + (pst - a.p)*nx)*k - a.mx);
@@ -279,7 +327,7 @@ __device__ __forceinline__ void flux_from_sides(const GasParams &G, const Side &
 		else if(sr >= 0.0) {
 			normal_flux(b, nx, ny, f);
 			const double pst = b.r*(b.vn - sr)*(b.vn - sm) + b.p;
-			const double k = 1.0/(sr - sm);
+			const double k = frcp(sr - sm);
 			const double w = sr - b.vn;
 			f[0] += sr*(b.r*w*k - b.r);
 			f[1] += sr*((w*b.mx + (pst - b.p)*nx)*k - b.mx);
@@ -303,46 +351,54 @@ __device__ __forceinline__ void inviscid_flux(const GasParams &G, const double u
 // ---------------------------------------------------------------------------------------------
 // boundary ghost states
 
-__device__ __forceinline__ void ghost_state(const GasParams &G, const BCEntry &bc, const double ins[4],
-                                            double nx, double ny, double gs[4])
+/// The few gas constants the boundary conditions need, passed BY VALUE to the out-of-line routine below
+/// (passing the kernel-parameter struct by reference would make the compiler copy it to the stack).
+struct BCGas { double g, gm1, gM2, pinf, Minf; double u0, u1, u2, u3; };
+
+/// Out of line on purpose: boundary faces are O(sqrt(N)), and inlining the eight-way switch (with its pow,
+/// sqrt and divisions) into the face and cell kernels costs every interior face registers and code size.
+static __device__ __noinline__ double4 ghost_state_ool(const BCGas B, const int type, const double v0, const double v1,
+                                                       const double4 in4, const double nx, const double ny)
 {
-	switch(bc.type) {
+	const double ins[4] = {in4.x, in4.y, in4.z, in4.w};
+	double gs[4];
+	switch(type) {
 	case INFLOW_OUTFLOW_BC: {
 		const double ir = 1.0/ins[0];
 		const double vn = (ins[1]*nx + ins[2]*ny)*ir;
 		const double m2 = ins[1]*ins[1] + ins[2]*ins[2];
-		const double p = G.gm1*(ins[3] - 0.5*m2*ir);
-		const double c = sqrt(G.g*p*ir);
+		const double p = B.gm1*(ins[3] - 0.5*m2*ir);
+		const double c = sqrt(B.g*p*ir);
 		const double Mn = vn/c;
-		if(Mn <= 0.0) { gs[0] = G.uinf[0]; gs[1] = G.uinf[1]; gs[2] = G.uinf[2]; gs[3] = G.uinf[3]; }
+		if(Mn <= 0.0) { gs[0] = B.u0; gs[1] = B.u1; gs[2] = B.u2; gs[3] = B.u3; }
 		else if(Mn < 1.0) {
 			gs[0] = ins[0]; gs[1] = ins[1]; gs[2] = ins[2];
-			gs[3] = G.pinf/G.gm1 + 0.5*ins[0]*(m2/(ins[0]*ins[0]));
+			gs[3] = B.pinf/B.gm1 + 0.5*ins[0]*(m2/(ins[0]*ins[0]));
 		}
 		else { gs[0] = ins[0]; gs[1] = ins[1]; gs[2] = ins[2]; gs[3] = ins[3]; }
 		break;
 	}
 	case SUBSONIC_INFLOW_BC: {
-		const double g = G.g, ptot = bc.v0, ttot = bc.v1;
+		const double g = B.g, ptot = v0, ttot = v1;
 		const double ir = 1.0/ins[0];
 		const double m2 = ins[1]*ins[1] + ins[2]*ins[2];
-		const double p = G.gm1*(ins[3] - 0.5*m2*ir);
+		const double p = B.gm1*(ins[3] - 0.5*m2*ir);
 		const double ci = sqrt(g*p*ir);
 		const double Rm = (ins[1]*nx + ins[2]*ny)*ir - ci/(2.0*g - 1.0);
-		const double co2 = ci*ci + 0.5*G.gm1*m2/(ins[0]*ins[0]);
-		const double q = sqrt((g + 1.0)*co2/(G.gm1*Rm*Rm) - 0.5*G.gm1);
-		const double cg = -Rm*G.gm1/(g + 1.0)*(1.0 + q);
+		const double co2 = ci*ci + 0.5*B.gm1*m2/(ins[0]*ins[0]);
+		const double q = sqrt((g + 1.0)*co2/(B.gm1*Rm*Rm) - 0.5*B.gm1);
+		const double cg = -Rm*B.gm1/(g + 1.0)*(1.0 + q);
 		const double tg = ttot*cg*cg/co2;
-		const double pg = ptot*pow(tg/ttot, g/G.gm1);
-		gs[0] = G.gM2*pg/tg;
-		const double vg = sqrt(2.0/G.gm1*(co2 - cg*cg));
+		const double pg = ptot*pow(tg/ttot, g/B.gm1);
+		gs[0] = B.gM2*pg/tg;
+		const double vg = sqrt(2.0/B.gm1*(co2 - cg*cg));
 		gs[1] = gs[0]*(vg*nx);
 		gs[2] = gs[0]*(vg*ny);
-		gs[3] = pg/G.gm1 + 0.5*gs[0]*(vg*vg);
+		gs[3] = pg/B.gm1 + 0.5*gs[0]*(vg*vg);
 		break;
 	}
 	case FARFIELD_BC:
-		gs[0] = G.uinf[0]; gs[1] = G.uinf[1]; gs[2] = G.uinf[2]; gs[3] = G.uinf[3];
+		gs[0] = B.u0; gs[1] = B.u1; gs[2] = B.u2; gs[3] = B.u3;
 		break;
 	case SLIP_WALL_BC: {
 		const double vn = (ins[1]*nx + ins[2]*ny)/ins[0];
@@ -353,7 +409,7 @@ __device__ __forceinline__ void ghost_state(const GasParams &G, const BCEntry &b
 		break;
 	}
 	case ADIABATIC_WALL_BC: {
-		const double tm = bc.v0*ins[0];
+		const double tm = v0*ins[0];
 		gs[0] = ins[0];
 		gs[1] = 2.0*tm*ny - ins[1];
 		gs[2] = -2.0*tm*nx - ins[2];
@@ -361,20 +417,29 @@ __device__ __forceinline__ void ghost_state(const GasParams &G, const BCEntry &b
 		break;
 	}
 	case ISOTHERMAL_WALL_BC: {
-		const double vt = bc.v0, Tw = bc.v1;
+		const double vt = v0, Tw = v1;
 		const double ir = 1.0/ins[0];
-		const double p = G.gm1*(ins[3] - 0.5*(ins[1]*ins[1] + ins[2]*ins[2])*ir);
-		const double Tg = 2.0*Tw - p*ir*G.gM2;
+		const double p = B.gm1*(ins[3] - 0.5*(ins[1]*ins[1] + ins[2]*ins[2])*ir);
+		const double Tg = 2.0*Tw - p*ir*B.gM2;
 		gs[0] = ins[0];
 		gs[1] = gs[0]*(2.0*vt*ny - ins[1]*ir);
 		gs[2] = gs[0]*(-2.0*vt*nx - ins[2]*ir);
 		const double vm2 = (gs[1]*gs[1] + gs[2]*gs[2])/(gs[0]*gs[0]);
-		gs[3] = gs[0]*(Tg/(G.g*G.gm1*G.Minf*G.Minf) + 0.5*vm2);
+		gs[3] = gs[0]*(Tg/(B.g*B.gm1*B.Minf*B.Minf) + 0.5*vm2);
 		break;
 	}
 	default: // EXTRAPOLATION_BC (and anything unknown is rejected at flow creation)
 		gs[0] = ins[0]; gs[1] = ins[1]; gs[2] = ins[2]; gs[3] = ins[3];
 	}
+	return make_double4(gs[0], gs[1], gs[2], gs[3]);
+}
+
+__device__ __forceinline__ void ghost_state(const GasParams &G, const BCEntry &bc, const double ins[4],
+                                            double nx, double ny, double gs[4])
+{
+	const BCGas B = {G.g, G.gm1, G.gM2, G.pinf, G.Minf, G.uinf[0], G.uinf[1], G.uinf[2], G.uinf[3]};
+	const double4 r = ghost_state_ool(B, bc.type, bc.v0, bc.v1, make_double4(ins[0], ins[1], ins[2], ins[3]), nx, ny);
+	gs[0] = r.x; gs[1] = r.y; gs[2] = r.z; gs[3] = r.w;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -14,153 +14,236 @@
 namespace fvg {
 
 enum { GM_ZERO = 0, GM_GG = 1, GM_WLS = 2, GM_GIVEN = 3 };
-
-__device__ __forceinline__ double rsqrt_exact(double x) { return 1.0/sqrt(x); }
 enum { LM_NONE = 0, LM_BJ = 1, LM_VENKAT = 2 };
 
+/// Shared-memory carve-up of the cell kernel
+struct CellSmem {
+	int sp, src, sgr, sn, slen, bar, total;
+	__host__ __device__ CellSmem(int TC, int HMAX, int EMAX, bool mids, bool metrics) {
+		const int CAPC = TC + HMAX;
+		int o = 0;
+		sp = o; o += CAPC*32;
+		src = o; o += CAPC*16;
+		sgr = o; o += mids ? EMAX*16 : 0;
+		sn = o; o += metrics ? EMAX*16 : 0;
+		slen = o; o += metrics ? EMAX*8 : 0;
+		bar = o; o += 8;
+		total = o;
+	}
+};
+
+/** Gradient + limiter pass, one CTA per tile. The tile's cell states and centres (own cells by TMA bulk
+ * copy, halo cells by cp.async gathers) and the face midpoints of its stream are staged in shared
+ * memory; conserved states are converted to primitive ONCE per staged cell (the reference converts the
+ * whole field in a separate pass, flow_spatial.cpp:697-699). Then one thread per own cell gathers its
+ * <= 4 neighbours from shared memory: no scatter, no atomics. */
 template <int GRAD, int LIM, bool PRIM_IN>
 __global__ void __launch_bounds__(CELL_BLOCK, FVG_CELL_MINB)
 cell_kernel(const CellArgs A)
 {
+	extern __shared__ __align__(128) unsigned char smraw[];
 	const DMesh &M = A.m;
-	const int i = blockIdx.x*CELL_BLOCK + threadIdx.x;
-	if(i >= M.ncell) return;
+	constexpr bool MIDS = LIM != LM_NONE || GRAD == GM_GG;
+	constexpr bool METRICS = GRAD == GM_GG;
+	const CellSmem S(M.TC, M.HMAX, M.EMAX, MIDS, METRICS);
+	double *const sp = reinterpret_cast<double*>(smraw + S.sp);
+	double2 *const src = reinterpret_cast<double2*>(smraw + S.src);
+	double2 *const sgr = reinterpret_cast<double2*>(smraw + S.sgr);
+	double2 *const sn = reinterpret_cast<double2*>(smraw + S.sn);
+	double *const slen = reinterpret_cast<double*>(smraw + S.slen);
+	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);
 
-	const int4 nb4 = M.nbr[i];
-	const int4 cf4 = M.cface[i];
-	const int nb[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
-	const int cf[4] = {cf4.x, cf4.y, cf4.z, cf4.w};
-	const double2 rci = M.rc[i];
-	double ui[4], pi[4];
-	ld4(A.u + 4*(size_t)i, ui);
-	if(PRIM_IN) { for(int k = 0; k < 4; k++) pi[k] = ui[k]; }
-	else cons2prim(A.gas, ui, pi);
+	const int t = blockIdx.x, tid = threadIdx.x;
+	const int c0 = M.tcell0[t], nc = M.tcell0[t+1] - c0;
+	const int h0 = M.thoff[t], nh = M.thoff[t+1] - h0;
+	const int e0 = M.fsoff[t], ne = M.fsoff[t+1] - e0;
+	constexpr bool NEED_NBRS = GRAD == GM_GG || GRAD == GM_WLS || LIM != LM_NONE;
 
-	double acc[8] = {0,0,0,0,0,0,0,0};   // GG: gradient sums; WLS: right-hand side. Index d + 2*v
-	double dmin[4] = {0,0,0,0}, dmax[4] = {0,0,0,0};
-	const double ainv = GRAD == GM_GG ? 1.0/M.area[i] : 0.0;
-
-	if(GRAD == GM_GG || GRAD == GM_WLS || LIM != LM_NONE) {
-		#pragma unroll
-		for(int j = 0; j < 4; j++) {
-			const int nj = nb[j];
-			if(nj == -1) continue;
-			double pj[4];
-			double2 rj;
-			bool use_for_limiter = true;
-			if(nj >= 0) {
-				double uj[4];
-				ld4(A.u + 4*(size_t)nj, uj);
-				if(PRIM_IN) { for(int k = 0; k < 4; k++) pj[k] = uj[k]; }
-				else cons2prim(A.gas, uj, pj);
-				rj = M.rc[nj];
-			} else {
-				const int b = -2 - nj;
-				if(PRIM_IN) ld4(A.ug + 4*(size_t)b, pj);
-				else {
-					const double2 n = M.fn[cf[j] & 0x7fffffff];
-					double gs[4];
-					ghost_state(A.gas, A.gas.bc[A.bbc[b]], ui, n.x, n.y, gs);
-					cons2prim(A.gas, gs, pj);
-				}
-				rj = M.rcbp[b];
-				use_for_limiter = A.bnd_policy == 0;
-			}
-			if(GRAD == GM_WLS) {
-				const double dx = rci.x - rj.x, dy = rci.y - rj.y;
-				const double w = 1.0/(dx*dx + dy*dy);
-				const double wx = w*dx, wy = w*dy;
-				#pragma unroll
-				for(int v = 0; v < 4; v++) {
-					const double du = pi[v] - pj[v];
-					acc[2*v] += wx*du;
-					acc[2*v+1] += wy*du;
-				}
-			}
-			if(GRAD == GM_GG) {
-				const int e = cf[j] & 0x7fffffff;
-				const bool isR = cf[j] < 0;
-				const double2 mid = M.fgr[e];
-				const double2 n = M.fn[e];
-				const double len = M.flen[e];
-				// inverse distances of the face midpoint to the two centres
-				const double di = rsqrt_exact((mid.x-rci.x)*(mid.x-rci.x) + (mid.y-rci.y)*(mid.y-rci.y));
-				const double dj = rsqrt_exact((mid.x-rj.x)*(mid.x-rj.x) + (mid.y-rj.y)*(mid.y-rj.y));
-				const double sgn = isR ? -1.0 : 1.0;
-				const double isum = 1.0/(di + dj);
-				#pragma unroll
-				for(int v = 0; v < 4; v++) {
-					const double ut = (pi[v]*di + pj[v]*dj)*isum*len;
-					acc[2*v] += sgn*(ut*n.x)*ainv;
-					acc[2*v+1] += sgn*(ut*n.y)*ainv;
-				}
-			}
-			if(LIM != LM_NONE && use_for_limiter) {
-				#pragma unroll
-				for(int v = 0; v < 4; v++) {
-					const double du = pj[v] - pi[v];
-					dmax[v] = fmax(dmax[v], du);
-					dmin[v] = fmin(dmin[v], du);
-				}
-			}
+	if(tid == 0) mbar_init(bar, 1);
+	__syncthreads();
+	if(tid == 0) {
+		unsigned bytes = (unsigned)nc*(32u + 16u);
+		if(MIDS) bytes += (unsigned)ne*16u;
+		if(METRICS) bytes += (unsigned)ne*(16u + 8u);
+		mbar_expect_tx(bar, bytes);
+		bulk_g2s(sp, A.u + 4*(size_t)c0, (unsigned)nc*32u, bar);
+		bulk_g2s(src, M.rc + c0, (unsigned)nc*16u, bar);
+		if(MIDS) bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
+		if(METRICS) { bulk_g2s(sn, M.fn + e0, (unsigned)ne*16u, bar); bulk_g2s(slen, M.flen + e0, (unsigned)ne*8u, bar); }
+	}
+	if(NEED_NBRS) {
+		for(int k = tid; k < nh*3; k += CELL_BLOCK) {
+			const int h = k/3, piece = k - 3*h;
+			const size_t g = (size_t)M.thalo[h0 + h];
+			const int row = nc + h;
+			if(piece < 2) cp_async16(sp + 4*row + 2*piece, A.u + 4*g + 2*piece);
+			else cp_async16(src + row, M.rc + g);
 		}
+		cp_async_commit();
+	}
+	// the first cell's own metadata is fetched while the copies are in flight
+	uint4 cl = make_uint4(0,0,0,0);
+	double4 V = make_double4(0,0,0,0);
+	if(tid < nc) {
+		cl = M.cloc[c0 + tid];
+		if(GRAD == GM_WLS) V = M.wlsV[c0 + tid];
+	}
+	cp_async_wait_all();
+	mbar_wait(bar, 0);
+	__syncthreads();
+	if(!PRIM_IN) {
+		const int nrows = NEED_NBRS ? nc + nh : nc;
+		for(int k = tid; k < nrows; k += CELL_BLOCK) {
+			double uc[4], up[4];
+			lds4(sp + 4*k, uc);
+			cons2prim(A.gas, uc, up);
+			*reinterpret_cast<double2*>(sp + 4*k) = make_double2(up[0], up[1]);
+			*reinterpret_cast<double2*>(sp + 4*k + 2) = make_double2(up[2], up[3]);
+		}
+		__syncthreads();
 	}
 
-	double g[8];
-	if(GRAD == GM_WLS) {
-		const double4 V = M.wlsV[i];
-		#pragma unroll
-		for(int v = 0; v < 4; v++) {
-			g[2*v]   = V.x*acc[2*v] + V.y*acc[2*v+1];
-			g[2*v+1] = V.z*acc[2*v] + V.w*acc[2*v+1];
+	for(int k = tid; k < nc; k += CELL_BLOCK) {
+		const int i = c0 + k;
+		if(k != tid) {
+			cl = M.cloc[i];
+			if(GRAD == GM_WLS) V = M.wlsV[i];
 		}
-	}
-	else if(GRAD == GM_GG) { for(int k = 0; k < 8; k++) g[k] = acc[k]; }
-	else if(GRAD == GM_GIVEN) { ld4(A.gin + 8*(size_t)i, g); ld4(A.gin + 8*(size_t)i + 4, g+4); }
-	else { for(int k = 0; k < 8; k++) g[k] = 0.0; }
+		const unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
+		const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
+		const double2 rci = src[k];
+		double pi[4];
+		lds4(sp + 4*k, pi);
 
-	if(A.gu) { st4(A.gu + 8*(size_t)i, g); st4(A.gu + 8*(size_t)i + 4, g+4); }
-	if(!A.lg) return;
+		double acc[8] = {0,0,0,0,0,0,0,0};   // GG: gradient sums; WLS: right-hand side. Index d + 2*v
+		double dmin[4] = {0,0,0,0}, dmax[4] = {0,0,0,0};
+		const double ainv = GRAD == GM_GG ? frcp(M.area[i]) : 0.0;
 
-	if(LIM != LM_NONE) {
-		double lim[4] = {1.0, 1.0, 1.0, 1.0};
-		double eps2 = 0.0;
-		if(LIM == LM_VENKAT) {
-			const double kh = A.gas.limiter_param*M.clength[i];
-			eps2 = kh*kh*kh;
+		if(NEED_NBRS) {
+			#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				const unsigned nj = nb[j];
+				if(nj == NB_NONE) continue;
+				const int le = (int)(cf[j] & 0x7FFFu);
+				double pj[4];
+				double2 rj;
+				bool use_for_limiter = true;
+				if(nj != NB_BND) {
+					lds4(sp + 4*nj, pj);
+					rj = src[nj];
+				} else {
+					const double2 mid = M.fgr[e0 + le];
+					if(PRIM_IN) ld4(A.ug + 4*(size_t)M.fref[e0 + le], pj);
+					else {
+						const double2 n = M.fn[e0 + le];
+						const unsigned slot = (M.fLR[e0 + le] >> 16) & 15u;
+						double ui[4], gs[4];
+						prim2cons(A.gas, pi, ui);
+						ghost_state(A.gas, A.gas.bc[slot], ui, n.x, n.y, gs);
+						cons2prim(A.gas, gs, pj);
+					}
+					rj = make_double2(2.0*mid.x - rci.x, 2.0*mid.y - rci.y);      // ghost centre (aspatial.cpp:98-119)
+					use_for_limiter = A.bnd_policy == 0;
+				}
+				if(GRAD == GM_WLS) {
+					const double dx = rci.x - rj.x, dy = rci.y - rj.y;
+					const double w = frcp(dx*dx + dy*dy);
+					const double wx = w*dx, wy = w*dy;
+					#pragma unroll
+					for(int v = 0; v < 4; v++) {
+						const double du = pi[v] - pj[v];
+						acc[2*v] += wx*du;
+						acc[2*v+1] += wy*du;
+					}
+				}
+				if(GRAD == GM_GG) {
+					const bool isR = (cf[j] & 0x8000u) != 0;
+					const double2 mid = sgr[le];
+					const double2 n = sn[le];
+					const double len = slen[le];
+					// inverse distances of the face midpoint to the two centres
+					const double di = frsqrt((mid.x-rci.x)*(mid.x-rci.x) + (mid.y-rci.y)*(mid.y-rci.y));
+					const double dj = frsqrt((mid.x-rj.x)*(mid.x-rj.x) + (mid.y-rj.y)*(mid.y-rj.y));
+					const double sgn = isR ? -1.0 : 1.0;
+					const double isum = frcp(di + dj);
+					#pragma unroll
+					for(int v = 0; v < 4; v++) {
+						const double ut = (pi[v]*di + pj[v]*dj)*isum*len;
+						acc[2*v] += sgn*(ut*n.x)*ainv;
+						acc[2*v+1] += sgn*(ut*n.y)*ainv;
+					}
+				}
+				if(LIM != LM_NONE && use_for_limiter) {
+					#pragma unroll
+					for(int v = 0; v < 4; v++) {
+						const double du = pj[v] - pi[v];
+						dmax[v] = fmax(dmax[v], du);
+						dmin[v] = fmin(dmin[v], du);
+					}
+				}
+			}
 		}
-		#pragma unroll
-		for(int j = 0; j < 4; j++) {
-			if(nb[j] == -1) continue;
-			const double2 mid = M.fgr[cf[j] & 0x7fffffff];
-			const double dx = mid.x - rci.x, dy = mid.y - rci.y;
+
+		double g[8];
+		if(GRAD == GM_WLS) {
 			#pragma unroll
 			for(int v = 0; v < 4; v++) {
-				const double uface = pi[v] + g[2*v]*dx + g[2*v+1]*dy;
-				const double dm = uface - pi[v];
-				double phi;
-				if(LIM == LM_VENKAT) {
-					const double dp = dm < 0.0 ? dmin[v] : dmax[v];
-					phi = (dp*dp + 2.0*dp*dm + eps2)/(dp*dp + dp*dm + 2.0*dm*dm + eps2);
-				} else {
-					if(dm > 0.0) phi = fmin(1.0, dmax[v]/dm);
-					else if(dm < 0.0) phi = fmin(1.0, dmin[v]/dm);
-					else phi = 1.0;
-				}
-				lim[v] = fmin(lim[v], phi);
+				g[2*v]   = V.x*acc[2*v] + V.y*acc[2*v+1];
+				g[2*v+1] = V.z*acc[2*v] + V.w*acc[2*v+1];
 			}
 		}
-		#pragma unroll
-		for(int v = 0; v < 4; v++) { g[2*v] *= lim[v]; g[2*v+1] *= lim[v]; }
+		else if(GRAD == GM_GG) { for(int q = 0; q < 8; q++) g[q] = acc[q]; }
+		else if(GRAD == GM_GIVEN) { ld4(A.gin + 8*(size_t)i, g); ld4(A.gin + 8*(size_t)i + 4, g+4); }
+		else { for(int q = 0; q < 8; q++) g[q] = 0.0; }
+
+		if(A.gu) { st4(A.gu + 8*(size_t)i, g); st4(A.gu + 8*(size_t)i + 4, g+4); }
+		if(!A.lg) continue;
+
+		if(LIM != LM_NONE) {
+			double lim[4] = {1.0, 1.0, 1.0, 1.0};
+			double eps2 = 0.0;
+			if(LIM == LM_VENKAT) {
+				const double kh = A.gas.limiter_param*M.clength[i];
+				eps2 = kh*kh*kh;
+			}
+			#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				if(nb[j] == NB_NONE) continue;
+				const double2 mid = sgr[cf[j] & 0x7FFFu];
+				const double dx = mid.x - rci.x, dy = mid.y - rci.y;
+				#pragma unroll
+				for(int v = 0; v < 4; v++) {
+					const double uface = pi[v] + g[2*v]*dx + g[2*v+1]*dy;
+					const double dm = uface - pi[v];
+					double phi;
+					if(LIM == LM_VENKAT) {
+						const double dp = dm < 0.0 ? dmin[v] : dmax[v];
+						phi = (dp*dp + 2.0*dp*dm + eps2)*frcp(dp*dp + dp*dm + 2.0*dm*dm + eps2);
+					} else {
+						if(dm > 0.0) phi = fmin(1.0, dmax[v]/dm);
+						else if(dm < 0.0) phi = fmin(1.0, dmin[v]/dm);
+						else phi = 1.0;
+					}
+					lim[v] = fmin(lim[v], phi);
+				}
+			}
+			#pragma unroll
+			for(int v = 0; v < 4; v++) { g[2*v] *= lim[v]; g[2*v+1] *= lim[v]; }
+		}
+		st4(A.lg + 8*(size_t)i, g); st4(A.lg + 8*(size_t)i + 4, g+4);
 	}
-	st4(A.lg + 8*(size_t)i, g); st4(A.lg + 8*(size_t)i + 4, g+4);
 }
 
 template <int GRAD, int LIM, bool PRIM_IN>
 static int launch_cell(const CellArgs &a, cudaStream_t s)
 {
-	const int nblk = (a.m.ncell + CELL_BLOCK - 1)/CELL_BLOCK;
-	cell_kernel<GRAD,LIM,PRIM_IN><<<nblk, CELL_BLOCK, 0, s>>>(a);
+	const CellSmem S(a.m.TC, a.m.HMAX, a.m.EMAX, LIM != LM_NONE || GRAD == GM_GG, GRAD == GM_GG);
+	if(S.total > 48*1024) {
+		const cudaError_t ea = cudaFuncSetAttribute(cell_kernel<GRAD,LIM,PRIM_IN>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
+		if(ea != cudaSuccess) return cuda_fail(ea, "cell_kernel smem attribute", __FILE__, __LINE__);
+	}
+	cell_kernel<GRAD,LIM,PRIM_IN><<<a.m.ntile, CELL_BLOCK, S.total, s>>>(a);
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "cell_kernel launch", __FILE__, __LINE__);
 	return 0;
@@ -180,104 +263,122 @@ int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaS
 }
 
 // ------------------------------------------------------------------------------------------------
-// WENO: weighted average of the cell's and its interior neighbours' gradients
+// WENO: weighted average of the cell's and its interior neighbours' gradients (one CTA per tile)
 
 __global__ void __launch_bounds__(CELL_BLOCK)
 weno_kernel(const DMesh M, const double lambda, const double *__restrict__ gu, double *__restrict__ lg)
 {
-	const int i = blockIdx.x*CELL_BLOCK + threadIdx.x;
-	if(i >= M.ncell) return;
+	const int t = blockIdx.x;
+	const int c0 = M.tcell0[t], nc = M.tcell0[t+1] - c0;
 	const double epsilon = 1.0e-5;
-	const int4 nb4 = M.nbr[i];
-	const int nb[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
-	double g[8], out[8], wsum[4];
-	ld4(gu + 8*(size_t)i, g); ld4(gu + 8*(size_t)i + 4, g+4);
-	#pragma unroll
-	for(int v = 0; v < 4; v++) {
-		const double q = g[2*v]*g[2*v] + g[2*v+1]*g[2*v+1] + epsilon;
-		const double q2 = q*q;
-		const double w = lambda/(q2*q2);
-		wsum[v] = w; out[2*v] = w*g[2*v]; out[2*v+1] = w*g[2*v+1];
-	}
-	#pragma unroll
-	for(int j = 0; j < 4; j++) {
-		if(nb[j] < 0) continue;
-		double h[8];
-		ld4(gu + 8*(size_t)nb[j], h); ld4(gu + 8*(size_t)nb[j] + 4, h+4);
+	for(int k = threadIdx.x; k < nc; k += CELL_BLOCK) {
+		const int i = c0 + k;
+		const uint4 cl = M.cloc[i];
+		const unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
+		double g[8], out[8], wsum[4];
+		ld4(gu + 8*(size_t)i, g); ld4(gu + 8*(size_t)i + 4, g+4);
 		#pragma unroll
 		for(int v = 0; v < 4; v++) {
-			const double q = h[2*v]*h[2*v] + h[2*v+1]*h[2*v+1] + epsilon;
+			const double q = g[2*v]*g[2*v] + g[2*v+1]*g[2*v+1] + epsilon;
 			const double q2 = q*q;
-			const double w = 1.0/(q2*q2);
-			wsum[v] += w; out[2*v] += w*h[2*v]; out[2*v+1] += w*h[2*v+1];
+			const double w = lambda/(q2*q2);
+			wsum[v] = w; out[2*v] = w*g[2*v]; out[2*v+1] = w*g[2*v+1];
 		}
+		#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			if(nb[j] >= NB_BND) continue;
+			const size_t q_id = (size_t)tile_global(M, t, c0, nc, nb[j]);
+			double h[8];
+			ld4(gu + 8*q_id, h); ld4(gu + 8*q_id + 4, h+4);
+			#pragma unroll
+			for(int v = 0; v < 4; v++) {
+				const double q = h[2*v]*h[2*v] + h[2*v+1]*h[2*v+1] + epsilon;
+				const double q2 = q*q;
+				const double w = 1.0/(q2*q2);
+				wsum[v] += w; out[2*v] += w*h[2*v]; out[2*v+1] += w*h[2*v+1];
+			}
+		}
+		#pragma unroll
+		for(int v = 0; v < 4; v++) { out[2*v] /= wsum[v]; out[2*v+1] /= wsum[v]; }
+		st4(lg + 8*(size_t)i, out); st4(lg + 8*(size_t)i + 4, out+4);
 	}
-	#pragma unroll
-	for(int v = 0; v < 4; v++) { out[2*v] /= wsum[v]; out[2*v+1] /= wsum[v]; }
-	st4(lg + 8*(size_t)i, out); st4(lg + 8*(size_t)i + 4, out+4);
 }
 
 int launch_weno_kernel(const DMesh &m, double lambda, const double *gu, double *lg, cudaStream_t s)
 {
-	weno_kernel<<<(m.ncell + CELL_BLOCK - 1)/CELL_BLOCK, CELL_BLOCK, 0, s>>>(m, lambda, gu, lg);
+	weno_kernel<<<m.ntile, CELL_BLOCK, 0, s>>>(m, lambda, gu, lg);
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "weno_kernel launch", __FILE__, __LINE__);
 	return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// unfused face values (plug-in parity with SolutionReconstruction::compute_face_values)
+// unfused face values (plug-in parity with SolutionReconstruction::compute_face_values), CTA per tile
+
+__device__ __forceinline__ void extrapolate4g(const double pc[4], const double *g, double dx, double dy, double pf[4]) {
+	double ga[4], gb[4];
+	ld4(g, ga); ld4(g+4, gb);
+	pf[0] = pc[0] + ga[0]*dx + ga[1]*dy;
+	pf[1] = pc[1] + ga[2]*dx + ga[3]*dy;
+	pf[2] = pc[2] + gb[0]*dx + gb[1]*dy;
+	pf[3] = pc[3] + gb[2]*dx + gb[3]*dy;
+}
 
 __global__ void __launch_bounds__(FACE_BLOCK)
 face_values_kernel(const FaceValArgs A)
 {
 	const DMesh &M = A.m;
-	const int e = blockIdx.x*FACE_BLOCK + threadIdx.x;
-	if(e >= M.nstream) return;
-	const int L = M.fL[e], R = M.fR[e];
-	// only the copy that lives in the left cell's tile writes (duplicates carry -1-f)
-	const int f = M.fref[e];
-	if(f < 0) return;
-	const double2 gr = M.fgr[e];
-	const double2 rl = M.rc[L];
-	double pl[4], pr[4], out[4];
-	ld4(A.up + 4*(size_t)L, pl);
-	if(!A.muscl) {
-		extrapolate4(pl, A.g + 8*(size_t)L, gr.x - rl.x, gr.y - rl.y, out);
-		st4(A.ufl + 4*(size_t)f, out);
-		if(R >= 0) {
-			const double2 rr = M.rc[R];
-			ld4(A.up + 4*(size_t)R, pr);
-			extrapolate4(pr, A.g + 8*(size_t)R, gr.x - rr.x, gr.y - rr.y, out);
-			st4(A.ufr + 4*(size_t)f, out);
+	const int t = blockIdx.x;
+	const int c0 = M.tcell0[t], nc = M.tcell0[t+1] - c0;
+	for(int e = M.fsoff[t] + threadIdx.x; e < M.fsoff[t+1]; e += FACE_BLOCK) {
+		// only the copy that lives in the left cell's tile writes (duplicates carry -1-f, padding INT_MIN)
+		const int f = M.fref[e];
+		if(f < 0) continue;
+		const unsigned LR = M.fLR[e];
+		const bool bnd = (LR >> 16) >= LR_BND;
+		const size_t L = (size_t)tile_global(M, t, c0, nc, LR & 0xFFFFu);
+		const size_t R = bnd ? 0 : (size_t)tile_global(M, t, c0, nc, LR >> 16);
+		const double2 gr = M.fgr[e];
+		const double2 rl = M.rc[L];
+		double pl[4], pr[4], out[4];
+		ld4(A.up + 4*L, pl);
+		if(!A.muscl) {
+			extrapolate4g(pl, A.g + 8*L, gr.x - rl.x, gr.y - rl.y, out);
+			st4(A.ufl + 4*(size_t)f, out);
+			if(!bnd) {
+				const double2 rr = M.rc[R];
+				ld4(A.up + 4*R, pr);
+				extrapolate4g(pr, A.g + 8*R, gr.x - rr.x, gr.y - rr.y, out);
+				st4(A.ufr + 4*(size_t)f, out);
+			}
 		}
-	}
-	else {
-		double2 rr;
-		if(R >= 0) { ld4(A.up + 4*(size_t)R, pr); rr = M.rc[R]; }
-		else { ld4(A.ug + 4*(size_t)(-2-R), pr); rr = M.rcbp[-2-R]; }
-		const double dx = rr.x - rl.x, dy = rr.y - rl.y;
-		double g[8];
-		ld4(A.g + 8*(size_t)L, g); ld4(A.g + 8*(size_t)L + 4, g+4);
-		for(int k = 0; k < 4; k++) {
-			const double dlr = pr[k] - pl[k];
-			out[k] = pl[k] + muscl_term(2.0*(g[2*k]*dx + g[2*k+1]*dy) - dlr, dlr);
-		}
-		st4(A.ufl + 4*(size_t)f, out);
-		if(R >= 0) {
-			ld4(A.g + 8*(size_t)R, g); ld4(A.g + 8*(size_t)R + 4, g+4);
+		else {
+			double2 rr;
+			if(!bnd) { ld4(A.up + 4*R, pr); rr = M.rc[R]; }
+			else { ld4(A.ug + 4*(size_t)f, pr); rr = M.rcbp[f]; }
+			const double dx = rr.x - rl.x, dy = rr.y - rl.y;
+			double g[8];
+			ld4(A.g + 8*L, g); ld4(A.g + 8*L + 4, g+4);
 			for(int k = 0; k < 4; k++) {
 				const double dlr = pr[k] - pl[k];
-				out[k] = pr[k] - muscl_term(2.0*(g[2*k]*dx + g[2*k+1]*dy) - dlr, dlr);
+				out[k] = pl[k] + muscl_term(2.0*(g[2*k]*dx + g[2*k+1]*dy) - dlr, dlr);
 			}
-			st4(A.ufr + 4*(size_t)f, out);
+			st4(A.ufl + 4*(size_t)f, out);
+			if(!bnd) {
+				ld4(A.g + 8*R, g); ld4(A.g + 8*R + 4, g+4);
+				for(int k = 0; k < 4; k++) {
+					const double dlr = pr[k] - pl[k];
+					out[k] = pr[k] - muscl_term(2.0*(g[2*k]*dx + g[2*k+1]*dy) - dlr, dlr);
+				}
+				st4(A.ufr + 4*(size_t)f, out);
+			}
 		}
 	}
 }
 
 int launch_face_values(const FaceValArgs &a, cudaStream_t s)
 {
-	face_values_kernel<<<(a.m.nstream + FACE_BLOCK - 1)/FACE_BLOCK, FACE_BLOCK, 0, s>>>(a);
+	face_values_kernel<<<a.m.ntile, FACE_BLOCK, 0, s>>>(a);
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "face_values_kernel launch", __FILE__, __LINE__);
 	return 0;
@@ -310,7 +411,7 @@ int launch_permute_rows(const double *src, double *dst, const int *idx, int n, i
 	return 0;
 }
 
-__global__ void boundary_states_kernel(const DMesh M, const GasParams G, const int *__restrict__ bbc,
+__global__ void boundary_states_kernel(const DMesh M, const GasParams G,
                                        const double *__restrict__ ins, double *__restrict__ gs)
 {
 	const int b = blockIdx.x*blockDim.x + threadIdx.x;
@@ -318,22 +419,22 @@ __global__ void boundary_states_kernel(const DMesh M, const GasParams G, const i
 	const double2 n = M.fn[M.bentry[b]];
 	double in[4], out[4];
 	ld4(ins + 4*(size_t)b, in);
-	ghost_state(G, G.bc[bbc[b]], in, n.x, n.y, out);
+	ghost_state(G, G.bc[M.bslot[b]], in, n.x, n.y, out);
 	st4(gs + 4*(size_t)b, out);
 }
 
-int launch_boundary_states(const DMesh &m, const GasParams &g, const int *bbc, const double *ins,
+int launch_boundary_states(const DMesh &m, const GasParams &g, const double *ins,
                            double *gs, cudaStream_t s)
 {
 	if(m.nbface == 0) return 0;
-	boundary_states_kernel<<<(m.nbface + 127)/128, 128, 0, s>>>(m, g, bbc, ins, gs);
+	boundary_states_kernel<<<(m.nbface + 127)/128, 128, 0, s>>>(m, g, ins, gs);
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "boundary_states launch", __FILE__, __LINE__);
 	return 0;
 }
 
 /// ghost state of each boundary face from the adjacent CELL state (device order), conserved or primitive
-__global__ void boundary_cell_ghosts_kernel(const DMesh M, const GasParams G, const int *__restrict__ bbc,
+__global__ void boundary_cell_ghosts_kernel(const DMesh M, const GasParams G,
                                             const double *__restrict__ u, double *__restrict__ ug, int prim_out)
 {
 	const int b = blockIdx.x*blockDim.x + threadIdx.x;
@@ -341,16 +442,16 @@ __global__ void boundary_cell_ghosts_kernel(const DMesh M, const GasParams G, co
 	const double2 n = M.fn[M.bentry[b]];
 	double in[4], out[4];
 	ld4(u + 4*(size_t)M.bcell[b], in);
-	ghost_state(G, G.bc[bbc[b]], in, n.x, n.y, out);
+	ghost_state(G, G.bc[M.bslot[b]], in, n.x, n.y, out);
 	if(prim_out) { double p[4]; cons2prim(G, out, p); st4(ug + 4*(size_t)b, p); }
 	else st4(ug + 4*(size_t)b, out);
 }
 
-int launch_boundary_prim_ghosts(const DMesh &m, const GasParams &g, const int *bbc, const double *u,
+int launch_boundary_prim_ghosts(const DMesh &m, const GasParams &g, const double *u,
                                 double *ug, bool prim_out, cudaStream_t s)
 {
 	if(m.nbface == 0) return 0;
-	boundary_cell_ghosts_kernel<<<(m.nbface + 127)/128, 128, 0, s>>>(m, g, bbc, u, ug, prim_out ? 1 : 0);
+	boundary_cell_ghosts_kernel<<<(m.nbface + 127)/128, 128, 0, s>>>(m, g, u, ug, prim_out ? 1 : 0);
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "boundary_cell_ghosts launch", __FILE__, __LINE__);
 	return 0;
@@ -401,13 +502,13 @@ int launch_final_norm(const double *partial, int n, double *out, cudaStream_t s)
 /// Cl, Cdp, Cdf numerators and the wetted length, summed in boundary-face order by one thread block
 /// of one warp... the boundary is O(sqrt(N)) faces, so a single CTA with a fixed-order reduction.
 __global__ void surface_kernel(const DMesh M, const GasParams G, const double aoa, const double *__restrict__ u,
-                               const double *__restrict__ grad, const int marker, double *__restrict__ out4)
+                               const double *__restrict__ grad, const int slot, double *__restrict__ out4)
 {
 	__shared__ double s[4][256];
 	double acc[4] = {0,0,0,0};
 	const double wx = cos(aoa), wy = sin(aoa);
 	for(int b = threadIdx.x; b < M.nbface; b += 256) {
-		if(M.btag[b] != marker) continue;
+		if(M.bslot[b] != slot) continue;
 		const int e = M.bentry[b];
 		const int c = M.bcell[b];
 		const double2 n = M.fn[e];
@@ -446,9 +547,9 @@ __global__ void surface_kernel(const DMesh M, const GasParams G, const double ao
 }
 
 int launch_surface_data(const DMesh &m, const GasParams &g, double aoa, const double *u, const double *grads,
-                        int marker, double *out4, cudaStream_t s)
+                        int slot, double *out4, cudaStream_t s)
 {
-	surface_kernel<<<1, 256, 0, s>>>(m, g, aoa, u, grads, marker, out4);
+	surface_kernel<<<1, 256, 0, s>>>(m, g, aoa, u, grads, slot, out4);
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "surface_kernel launch", __FILE__, __LINE__);
 	return 0;

@@ -220,6 +220,11 @@ class DeviceMesh:
         check(load().fvg_mesh_permutation(self._h, _ip(p)))
         return p
 
+    def tile_offsets(self):
+        t = np.zeros(self.info.ntile+1, dtype=np.int32)
+        check(load().fvg_mesh_tile_offsets(self._h, _ip(t)))
+        return t
+
     def stream(self):
         n = self.info.nstream
         f, c, t = (np.zeros(n, dtype=np.int32) for _ in range(3))

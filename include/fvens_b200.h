@@ -88,7 +88,9 @@ typedef struct fvg_mesh fvg_mesh;
 enum { FVG_REORDER_NONE = 0, FVG_REORDER_HILBERT = 1, FVG_REORDER_RCM = 2 };
 typedef struct {
 	int reorder;       /* FVG_REORDER_*; HILBERT = space-filling-curve order of the cell centres */
-	int tile_cells;    /* cells per tile (0 = default 512); multiple of 32, <= 2048 */
+	int tile_cells;    /* maximum own cells per tile (0 = default 256); multiple of 32, <= 1024. Tiles are
+	                      consecutive cell ranges, shortened where needed so that their halo (distinct
+	                      out-of-tile neighbours) and face stream fit the shared-memory staging areas */
 	int device;        /* CUDA device ordinal, -1 = current; -2 = host-only build (renumbering, tiling and
 	                      colouring can be inspected without a GPU; no flow can be created on it) */
 } fvg_mesh_opts;
@@ -103,7 +105,9 @@ void fvg_mesh_destroy(fvg_mesh *m);
 int fvg_mesh_get_info(const fvg_mesh *m, fvg_mesh_info *info);
 /* cell_new2old[ncell]: device cell i holds reference cell cell_new2old[i]. */
 int fvg_mesh_permutation(const fvg_mesh *m, int *cell_new2old);
-/* Stream entries: reference face id, colour and tile of every entry (test hook for the colouring
+/* tile_cell0[ntile+1]: device cells [tile_cell0[t], tile_cell0[t+1]) are tile t's own cells. */
+int fvg_mesh_tile_offsets(const fvg_mesh *m, int *tile_cell0);
+/* Stream entries: reference face id (-1 for padding entries), colour and tile of every entry (test hook for the colouring
  * validity check: no two entries of one colour in a tile may touch the same tile-owned cell). */
 int fvg_mesh_stream(const fvg_mesh *m, int *entry_face, int *entry_colour, int *entry_tile);
 

@@ -126,35 +126,55 @@ def test_tiling_and_colouring_are_valid(reorder, tile):
     old2new = np.empty_like(new2old); old2new[new2old] = np.arange(um.nelem)
     face, colour, tile_of = dm.stream()
     info = dm.info
-    assert info.nstream == um.naface + info.ncut_dup and info.max_colours <= 8
-    # every face appears once per tile it touches
+    t0 = dm.tile_offsets()
+    assert t0[0] == 0 and t0[-1] == um.nelem and (np.diff(t0) > 0).all() and np.diff(t0).max() <= tile
+    cell_tile = np.repeat(np.arange(info.ntile), np.diff(t0))
+    real = face >= 0
+    assert real.sum() == um.naface + info.ncut_dup and info.max_colours <= 8
+    assert (np.diff(np.concatenate(([0], np.cumsum(np.bincount(tile_of, minlength=info.ntile))))) % 4 == 0).all()
+
+    def tiles_of_face(f):
+        L = old2new[a["intfac"][f, 0]]
+        ts = {int(cell_tile[L])}
+        if f >= um.nbface:
+            ts.add(int(cell_tile[old2new[a["intfac"][f, 1]]]))
+        return ts
+    # every face appears exactly once in every tile it touches
     seen = {}
-    for e in range(info.nstream):
-        f = face[e]
-        L = old2new[a["intfac"][f, 0]]
-        R = old2new[a["intfac"][f, 1]] if f >= um.nbface else -1
-        tiles = {L//tile} | ({R//tile} if R >= 0 else set())
-        assert tile_of[e] in tiles
-        seen.setdefault(f, set()).add(int(tile_of[e]))
-        # no two entries of one (tile, colour) touch the same tile-owned cell
-    for f, ts in seen.items():
-        L = old2new[a["intfac"][f, 0]]
-        R = old2new[a["intfac"][f, 1]] if f >= um.nbface else -1
-        assert ts == ({L//tile} | ({R//tile} if R >= 0 else set()))
+    for e in np.nonzero(real)[0]:
+        f = int(face[e])
+        assert int(tile_of[e]) in tiles_of_face(f)
+        assert int(tile_of[e]) not in seen.setdefault(f, set())
+        seen[f].add(int(tile_of[e]))
     assert len(seen) == um.naface
+    for f, ts in seen.items():
+        assert ts == tiles_of_face(f)
+    # no two entries of one (tile, colour) touch the same tile-owned cell
     used = set()
-    for e in range(info.nstream):
-        f = face[e]; t = tile_of[e]
+    for e in np.nonzero(real)[0]:
+        f = int(face[e]); t = int(tile_of[e])
         cells = [old2new[a["intfac"][f, 0]]] + ([old2new[a["intfac"][f, 1]]] if f >= um.nbface else [])
         for c in cells:
-            if c//tile == t:
-                key = (int(t), int(colour[e]), int(c))
+            if cell_tile[c] == t:
+                key = (t, int(colour[e]), int(c))
                 assert key not in used
                 used.add(key)
-    # entries of a tile are sorted by colour
+    # entries of a tile are sorted by colour (padding last)
     for t in range(info.ntile):
         cs = colour[tile_of == t]
         assert (np.diff(cs) >= 0).all()
+
+
+def test_tiles_shrink_to_fit_the_halo_capacity():
+    # a shuffled numbering makes almost every neighbour a halo cell: tiles must shrink, not fail
+    rng = np.random.default_rng(5)
+    coords, nnode, inpoel, bface = synth.square(40, tri_fraction=0.3)
+    sh = rng.permutation(len(nnode))
+    um = lib.UMesh.from_arrays(coords, nnode[sh], inpoel[sh], bface)
+    dm = lib.DeviceMesh(um, reorder="none", tile_cells=256, device=-2)
+    assert np.diff(dm.tile_offsets()).max() < 100
+    dm2 = lib.DeviceMesh(um, reorder="hilbert", tile_cells=256, device=-2)
+    assert np.diff(dm2.tile_offsets()).mean() > 200
 
 
 def test_hilbert_order_makes_compact_tiles():
