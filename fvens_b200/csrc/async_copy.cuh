@@ -42,6 +42,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 	             :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+/// Asks the TMA unit to pull `bytes` (multiple of 16, 16-byte aligned) of global memory into L2; no destination,
+/// no completion tracking. Used to warm L2 with the operands of the tile that will run a wave later.
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, unsigned bytes) {
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src_gmem), "r"(bytes) : "memory");
+}
+
 /// 16-byte asynchronous copy global -> shared (L2 only: the data is consumed from shared memory)
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");

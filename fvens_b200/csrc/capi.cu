@@ -76,6 +76,7 @@ static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s)
 	CellArgs a;
 	a.m = f->mesh->d; a.gas = f->gas; a.u = u; a.ug = nullptr; a.gin = nullptr;
 	a.bnd_policy = P.bnd_policy;
+	a.prefetch_distance = f->prefetch_distance;
 	int rc;
 	if(P.recon == FVG_RECON_WENO) {
 		a.lg = nullptr; a.gu = f->d_gu;
@@ -117,6 +118,7 @@ static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumul
 	a.lg = f->d_lg; a.gu = viscous_gradients(f);
 	a.epilogue = epilogue; a.accumulate = accumulate; a.gettimesteps = gettimesteps;
 	a.res = res; a.dtm = dtm; a.cfl = cfl; a.unew = unew; a.partial = f->d_partial;
+	a.prefetch_distance = f->prefetch_distance;
 	const int recon = !P.order2 ? FR_FIRST : (P.recon == FVG_RECON_VANALBADA ? FR_MUSCL : FR_LINEAR);
 	FaceLauncher L = face_launcher(P.flux);
 	if(!L) { set_error("unknown flux id"); return FVG_ERR_INVALID; }
@@ -287,6 +289,14 @@ int fvg_flow_create(fvg_mesh *mesh, const fvg_physics *phys, const fvg_numerics 
 	if((rc = dev_alloc(f.get(), &f->d_partial, mesh->d.ntile)) != 0) return rc;
 	if((rc = dev_alloc(f.get(), &f->d_norm, 1)) != 0) return rc;
 	FVG_CUDA(cudaMallocHost((void**)&f->h_norm, sizeof(double)));
+	{
+		// L2 prefetch distance = about one wave of resident CTAs (overridable for experiments)
+		int sms = 148;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, mesh->device);
+		const char *env = getenv("FVG_PREFETCH_WAVES");
+		const double waves = env ? atof(env) : 1.0;
+		f->prefetch_distance = (int)(waves*3*sms);
+	}
 	*out = f.release();
 	return 0;
 }
@@ -412,7 +422,7 @@ int fvg_gradients(fvg_flow *f, const double *d_uprim, const double *d_ug, double
 	int rc = to_device_order(f, d_uprim, 4, &su, &u, s);
 	CellArgs a;
 	a.m = D; a.gas = f->gas; a.u = u; a.ug = d_ug; a.gin = nullptr;
-	a.lg = nullptr; a.bnd_policy = f->plan.bnd_policy;
+	a.lg = nullptr; a.bnd_policy = f->plan.bnd_policy; a.prefetch_distance = 0;
 	if(rc == 0 && !f->mesh->identity_perm) {
 		const cudaError_t e = cudaMallocAsync((void**)&sg, sizeof(double)*8*(size_t)D.ncell, s);
 		if(e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
@@ -445,7 +455,7 @@ int fvg_face_values(fvg_flow *f, const double *d_uprim, const double *d_ug, cons
 		else if(rc == 0) {
 			CellArgs a;
 			a.m = D; a.gas = f->gas; a.u = u; a.ug = d_ug; a.gin = g; a.lg = slg; a.gu = nullptr;
-			a.bnd_policy = P.bnd_policy;
+			a.bnd_policy = P.bnd_policy; a.prefetch_distance = 0;
 			rc = launch_cell_kernel(3 /*given*/, limiter_mode(P.recon), true, a, s); f->launches++;
 		}
 		fa.g = slg;
@@ -486,7 +496,7 @@ int fvg_get_gradients(fvg_flow *f, const double *d_u, double *d_grads, void *str
 	}
 	CellArgs a;
 	a.m = D; a.gas = f->gas; a.u = u; a.ug = sug; a.gin = nullptr; a.lg = nullptr;
-	a.gu = f->mesh->identity_perm ? d_grads : sg; a.bnd_policy = f->plan.bnd_policy;
+	a.gu = f->mesh->identity_perm ? d_grads : sg; a.bnd_policy = f->plan.bnd_policy; a.prefetch_distance = 0;
 	if(rc == 0) { rc = launch_cell_kernel(f->plan.gradient, 0, true, a, s); f->launches++; }
 	if(rc == 0 && !f->mesh->identity_perm) { rc = launch_permute_rows(sg, d_grads, D.new2old, D.ncell, 8, false, false, s); f->launches++; }
 	if(su) cudaFreeAsync(su, s);

@@ -126,6 +126,7 @@ struct fvg_flow {
 	double *d_hu = nullptr, *d_hr = nullptr, *d_hdt = nullptr;   ///< staging for the host-buffer entry point
 	std::vector<void*> allocs;
 	long long launches = 0;
+	int prefetch_distance = 0;
 	// optional per-pass timing (CUDA events on the launching stream)
 	bool timing = false;
 	std::vector<cudaEvent_t> ev;   ///< triples: before pass A, between A and B, after B
@@ -143,6 +144,7 @@ struct CellArgs {
 	double *lg;            ///< out: limited gradients (may be null)
 	double *gu;            ///< out: unlimited gradients (may be null)
 	int bnd_policy;
+	int prefetch_distance; ///< tiles ahead whose operands are pulled into L2 (0 = off)
 };
 int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaStream_t s);
 int launch_weno_kernel(const DMesh &m, double lambda, const double *gu, double *lg, cudaStream_t s);
@@ -196,6 +198,7 @@ struct FaceArgs {
 	double cfl;            ///< EP_STEP
 	double *unew;          ///< EP_STEP: [ncell][4]
 	double *partial;       ///< EP_STEP: [ntile] sum of r_E^2*area
+	int prefetch_distance; ///< tiles ahead whose operands are pulled into L2 (0 = off)
 };
 typedef int (*FaceLauncher)(int recon, int visc, const FaceArgs &a, cudaStream_t s);
 int launch_face_llf(int recon, int visc, const FaceArgs &a, cudaStream_t s);

@@ -5,17 +5,10 @@
  * and, with the EP_STEP epilogue, the update + norm of SteadyForwardEulerSolver::solve
  * (src/ode/aodesolver.cpp:204-223).
  *
- * One CTA per tile. All of the tile's operands are staged in shared memory first, with copies that
- * hold no registers while in flight: the tile's own cells (state, gradients, centres) and its face
- * stream are contiguous in memory and arrive as 1-D TMA bulk copies counted on an mbarrier; the halo
- * cells (out-of-tile neighbours) are gathered with 16-byte cp.async. The flux phase then runs entirely
- * out of shared memory with 16-bit tile-local indices. Several CTAs are resident per SM, so one
- * tile's staging overlaps its neighbours' arithmetic.
- *
- * Faces cut by a tile boundary appear in both tiles and are evaluated identically in both. The face
- * stream is sorted by colour; no two faces of one colour share a tile cell, so after each colour
- * round a __syncthreads() is all the ordering the shared-memory accumulation needs. No atomics,
- * and the summation order per cell (colour order) is fixed => bitwise reproducible.
+ * One CTA per tile of consecutive cells; see the comment on face_kernel below for the three phases.
+ * Faces cut by a tile boundary appear in both tiles' streams and are evaluated identically in both
+ * (same left/right roles, same expression), so the scheme stays exactly conservative. Each cell's
+ * residual is the sum of its faces' fluxes in local-face order: no atomics, bitwise reproducible.
  */
 #pragma once
 #include "engine.hpp"
@@ -66,280 +59,302 @@ __device__ __forceinline__ double muscl_term(double delta, double dlr) {
 	return phi*0.25*((1.0 - k*phi)*delta + (1.0 + k*phi)*dlr);
 }
 
-/// Shared-memory carve-up of the face kernel for the given capacities (host and device agree through this)
+/// Shared-memory carve-up of the face kernel for the given capacity (host and device agree through this)
 struct FaceSmem {
-	int su, sg, src, sn, sgr, slen, sres, sLR, bar, total;   // byte offsets
-	__host__ __device__ FaceSmem(int TC, int HMAX, int EMAX, bool grads, bool centres) {
-		const int CAPC = TC + HMAX;
+	int fsL, fsR, sn, sgr, slen, sLR, bar, total;   // byte offsets
+	__host__ __device__ FaceSmem(int EMAX, bool mids) {
 		int o = 0;
-		su = o; o += CAPC*32;
-		sg = o; o += grads ? CAPC*64 : 0;
-		src = o; o += centres ? CAPC*16 : 0;
+		fsL = o; o += EMAX*32;
+		fsR = o; o += EMAX*32;
 		sn = o; o += EMAX*16;
-		sgr = o; o += grads ? EMAX*16 : 0;
+		sgr = o; o += mids ? EMAX*16 : 0;
 		slen = o; o += EMAX*8;
-		sres = o; o += 5*TC*8;
 		sLR = o; o += EMAX*4;
-		bar = (o + 7)/8*8; o = bar + 8;
+		bar = o; o += 8;
 		total = o;
 	}
 };
 
+/// primitive face state of one side whose cell is NOT a tile cell (halo): gathered from global memory
+template <int RECON>
+__device__ __forceinline__ void halo_side_state(const FaceArgs &A, const double *gsrc, size_t g, double2 gr, double pf[4])
+{
+	double uc[4];
+	ld4(A.u + 4*g, uc);
+	if(RECON == FR_FIRST) { for(int k = 0; k < 4; k++) pf[k] = uc[k]; return; }
+	double pc[4];
+	cons2prim(A.gas, uc, pc);
+	if(RECON == FR_MUSCL) { for(int k = 0; k < 4; k++) pf[k] = pc[k]; return; }
+	const double2 rc = A.m.rc[g];
+	double ga[4], gb[4];
+	ld4(gsrc + 8*g, ga); ld4(gsrc + 8*g + 4, gb);
+	const double dx = gr.x - rc.x, dy = gr.y - rc.y;
+	pf[0] = pc[0] + ga[0]*dx + ga[1]*dy;
+	pf[1] = pc[1] + ga[2]*dx + ga[3]*dy;
+	pf[2] = pc[2] + gb[0]*dx + gb[1]*dy;
+	pf[3] = pc[3] + gb[2]*dx + gb[3]*dy;
+}
+
+/** One CTA per tile, three phases separated by two barriers:
+ *  A  one thread per own cell: load its state / limited gradient / centre straight from global memory
+ *     (consecutive cells => fully coalesced 32-byte rows), convert to primitive ONCE, extrapolate to each
+ *     of its <= 4 faces and deposit the face state in the left or right slot of that face's stream entry
+ *     in shared memory.
+ *  B  one thread per stream entry (consecutive entries => conflict-free shared-memory rows): read both
+ *     face states (a side belonging to a halo cell is gathered from global memory instead), boundary ghost,
+ *     numerical flux, spectral radii; the flux overwrites the entry's slots.
+ *  C  one thread per own cell: sum the fluxes of its faces in local-face order (deterministic, no
+ *     atomics, no scatter), then the residual / time-step or the fused forward-Euler epilogue.
+ *  The entry metadata (normals, lengths, midpoints, local indices) is contiguous per tile and arrives by
+ *  1-D TMA bulk copies issued before phase A. */
 template <int FLUX, int RECON, int VISC>
 __global__ void __launch_bounds__(FACE_BLOCK, FVG_FACE_MINB)
 face_kernel(const FaceArgs A)
 {
 	extern __shared__ __align__(128) unsigned char smraw[];
 	const DMesh &M = A.m;
-	constexpr bool GRADS = RECON != FR_FIRST;
-	constexpr bool CENTRES = RECON != FR_FIRST || VISC != VISC_NONE;
-	const FaceSmem S(M.TC, M.HMAX, M.EMAX, GRADS, CENTRES);
-	double *const su = reinterpret_cast<double*>(smraw + S.su);
-	double *const sg = reinterpret_cast<double*>(smraw + S.sg);
-	double2 *const src = reinterpret_cast<double2*>(smraw + S.src);
+	constexpr bool MIDS = RECON != FR_FIRST;
+	const FaceSmem S(M.EMAX, MIDS);
+	double *const fsL = reinterpret_cast<double*>(smraw + S.fsL);
+	double *const fsR = reinterpret_cast<double*>(smraw + S.fsR);
 	double2 *const sn = reinterpret_cast<double2*>(smraw + S.sn);
 	double2 *const sgr = reinterpret_cast<double2*>(smraw + S.sgr);
 	double *const slen = reinterpret_cast<double*>(smraw + S.slen);
-	double *const res_s = reinterpret_cast<double*>(smraw + S.sres);   // [4][TC] then integ [TC]
 	unsigned *const sLR = reinterpret_cast<unsigned*>(smraw + S.sLR);
 	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);
-	__shared__ int coloff[MAXCOL+1];
 	__shared__ double red_s[FACE_BLOCK/32];
 
-	const int TC = M.TC;
 	const int t = blockIdx.x, tid = threadIdx.x;
 	const int c0 = M.tcell0[t], nc = M.tcell0[t+1] - c0;
-	const int h0 = M.thoff[t], nh = M.thoff[t+1] - h0;
+	const int h0 = M.thoff[t];
 	const int e0 = M.fsoff[t], ne = M.fsoff[t+1] - e0;
 	const double *const gsrc = RECON == FR_MUSCL ? A.gu : A.lg;     // gradients used by the reconstruction
 
-	// ---- stage the tile
+	// ---- entry metadata by TMA
 	if(tid == 0) mbar_init(bar, 1);
 	__syncthreads();
 	if(tid == 0) {
-		unsigned bytes = (unsigned)nc*32u + (unsigned)ne*(16u + 8u + 4u);
-		if(GRADS) bytes += (unsigned)nc*64u + (unsigned)ne*16u;
-		if(CENTRES) bytes += (unsigned)nc*16u;
-		mbar_expect_tx(bar, bytes);
-		bulk_g2s(su, A.u + 4*(size_t)c0, (unsigned)nc*32u, bar);
-		if(GRADS) bulk_g2s(sg, gsrc + 8*(size_t)c0, (unsigned)nc*64u, bar);
-		if(CENTRES) bulk_g2s(src, M.rc + c0, (unsigned)nc*16u, bar);
+		mbar_expect_tx(bar, (unsigned)ne*(16u + 8u + 4u + (MIDS ? 16u : 0u)));
 		bulk_g2s(sLR, M.fLR + e0, (unsigned)ne*4u, bar);
 		bulk_g2s(sn, M.fn + e0, (unsigned)ne*16u, bar);
 		bulk_g2s(slen, M.flen + e0, (unsigned)ne*8u, bar);
-		if(GRADS) bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
+		if(MIDS) bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
 	}
-	{
-		// halo rows in 16-byte pieces: 2 of the state, 4 of the gradients, 1 of the centre
-		constexpr int NP = 2 + (GRADS ? 4 : 0) + (CENTRES ? 1 : 0);
-		for(int k = tid; k < nh*NP; k += FACE_BLOCK) {
-			const int h = k/NP, piece = k - h*NP;
-			const size_t g = (size_t)M.thalo[h0 + h];
-			const int row = nc + h;
-			if(piece < 2) cp_async16(su + 4*row + 2*piece, A.u + 4*g + 2*piece);
-			else if(GRADS && piece < 6) cp_async16(sg + 8*row + 2*(piece-2), gsrc + 8*g + 2*(piece-2));
-			else cp_async16(src + row, M.rc + g);
-		}
-		cp_async_commit();
-	}
-	for(int k = tid; k < 5*TC; k += FACE_BLOCK) res_s[k] = 0.0;
-	if(tid <= MAXCOL) coloff[tid] = M.fcoloff[t*(MAXCOL+1) + tid] - e0;
-	cp_async_wait_all();
-	mbar_wait(bar, 0);
-	__syncthreads();
-	if(RECON != FR_FIRST) {
-		// conserved -> primitive once per staged cell (the reconstruction works on primitive variables)
-		for(int k = tid; k < nc + nh; k += FACE_BLOCK) {
-			double uc[4], up[4];
-			lds4(su + 4*k, uc);
-			cons2prim(A.gas, uc, up);
-			*reinterpret_cast<double2*>(su + 4*k) = make_double2(up[0], up[1]);
-			*reinterpret_cast<double2*>(su + 4*k + 2) = make_double2(up[2], up[3]);
-		}
-		__syncthreads();
+	if(tid == 32 && A.prefetch_distance > 0 && t + A.prefetch_distance < M.ntile) {
+		// warm L2 with the operands of the tile that runs about one wave of CTAs later
+		const int tp = t + A.prefetch_distance;
+		const int pc0 = M.tcell0[tp], pnc = M.tcell0[tp+1] - pc0;
+		const int pe0 = M.fsoff[tp], pne = M.fsoff[tp+1] - pe0;
+		bulk_prefetch_l2(A.u + 4*(size_t)pc0, (unsigned)pnc*32u);
+		bulk_prefetch_l2(M.cloc + pc0, (unsigned)pnc*16u);
+		if(RECON != FR_FIRST) { bulk_prefetch_l2(gsrc + 8*(size_t)pc0, (unsigned)pnc*64u); bulk_prefetch_l2(M.rc + pc0, (unsigned)pnc*16u); }
+		bulk_prefetch_l2(M.fLR + pe0, (unsigned)pne*4u);
+		bulk_prefetch_l2(M.fn + pe0, (unsigned)pne*16u);
+		bulk_prefetch_l2(M.flen + pe0, (unsigned)pne*8u);
+		if(MIDS) bulk_prefetch_l2(M.fgr + pe0, (unsigned)pne*16u);
+		bulk_prefetch_l2(M.area + (pc0 & ~1), (unsigned)((pnc + 3) & ~1)*8u);
 	}
 
-	// ---- fluxes, one stream entry per thread and round
-	for(int base = 0; base < ne; base += FACE_BLOCK) {
-		const int e = base + tid;
-		const unsigned LR = e < ne ? sLR[e] : LR_PAD;
-		const bool valid = LR != LR_PAD;
+	// ---- phase A: face states of the own cells
+	uint4 cl0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);     // metadata of cell `tid`, kept for phase C
+	double ar0 = 1.0;
+	if(tid < nc) ar0 = M.area[c0 + tid];
+	for(int k0 = 0; k0 < nc; k0 += FACE_BLOCK) {
+		const int k = k0 + tid;
+		uint4 cl = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);
+		double uc[4] = {1,0,0,1}, ga[4] = {0,0,0,0}, gb[4] = {0,0,0,0};
+		double2 rc = make_double2(0,0);
+		if(k < nc) {
+			const size_t i = (size_t)(c0 + k);
+			cl = M.cloc[i];
+			ld4(A.u + 4*i, uc);
+			if(RECON == FR_LINEAR) { ld4(gsrc + 8*i, ga); ld4(gsrc + 8*i + 4, gb); rc = M.rc[i]; }
+		}
+		if(k0 == 0) { cl0 = cl; mbar_wait(bar, 0); }     // midpoints needed from here on
+		if(k < nc) {
+			double pc[4];
+			if(RECON == FR_FIRST) { for(int q = 0; q < 4; q++) pc[q] = uc[q]; }
+			else cons2prim(A.gas, uc, pc);
+			const unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
+			const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
+			#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				if(j == 3 && nb[3] == NB_NONE) break;      // only the fourth slot can be empty (triangles)
+				const int e = (int)(cf[j] & 0x7FFFu);
+				double pf[4];
+				if(RECON == FR_LINEAR) {
+					const double2 gr = sgr[e];
+					const double dx = gr.x - rc.x, dy = gr.y - rc.y;
+					pf[0] = pc[0] + ga[0]*dx + ga[1]*dy;
+					pf[1] = pc[1] + ga[2]*dx + ga[3]*dy;
+					pf[2] = pc[2] + gb[0]*dx + gb[1]*dy;
+					pf[3] = pc[3] + gb[2]*dx + gb[3]*dy;
+				} else { for(int q = 0; q < 4; q++) pf[q] = pc[q]; }
+				double *const dst = ((cf[j] & 0x8000u) ? fsR : fsL) + 4*e;
+				*reinterpret_cast<double2*>(dst) = make_double2(pf[0], pf[1]);
+				*reinterpret_cast<double2*>(dst + 2) = make_double2(pf[2], pf[3]);
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---- phase B: fluxes, one stream entry per thread and round
+	for(int e = tid; e < ne; e += FACE_BLOCK) {
+		const unsigned LR = sLR[e];
+		if(LR == LR_PAD) continue;
 		const unsigned L = LR & 0xFFFFu, Rf = LR >> 16;
 		const bool bnd = Rf >= LR_BND;
-		double f[4] = {0,0,0,0};
-		double sri = 0, srj = 0;
-		if(valid) {
-			const double2 nrm = sn[e];
-			const double len = slen[e];
-			const double nx = nrm.x, ny = nrm.y;
-			const BCEntry &bc = A.gas.bc[Rf & 15u];
-			double ucl[4], ucr[4];      // conserved cell states (right = ghost of the cell state on a boundary)
-			double pl[4];               // primitive left cell state (second order)
-			Side a, bs;
-			if(RECON == FR_FIRST) lds4(su + 4*L, ucl);
-			else {
-				lds4(su + 4*L, pl);
-				if(VISC != VISC_NONE || RECON == FR_MUSCL) prim2cons(A.gas, pl, ucl);
-			}
-			if(RECON == FR_FIRST) {
-				if(bnd) ghost_state(A.gas, bc, ucl, nx, ny, ucr);
-				else lds4(su + 4*Rf, ucr);
-				a = load_side<true>(A.gas, ucl, nx, ny);
-				bs = load_side<true>(A.gas, ucr, nx, ny);
-			}
-			else {
-				const double2 gr = sgr[e];
-				const double2 rl = src[L];
-				double pfl[4], pfr[4];
-				if(RECON == FR_LINEAR) {
-					extrapolate4(pl, sg + 8*L, gr.x - rl.x, gr.y - rl.y, pfl);
-					a = side_from_prim<true>(A.gas, pfl, nx, ny);
-					if(bnd) {
-						const double ul[4] = {a.r, a.mx, a.my, a.E};
-						double ur[4];
-						ghost_state(A.gas, bc, ul, nx, ny, ur);
-						bs = load_side<true>(A.gas, ur, nx, ny);
-						if(VISC != VISC_NONE) ghost_state(A.gas, bc, ucl, nx, ny, ucr);
-					} else {
-						const double2 rr = src[Rf];
-						double pr[4];
-						lds4(su + 4*Rf, pr);
-						if(VISC != VISC_NONE) prim2cons(A.gas, pr, ucr);
-						extrapolate4(pr, sg + 8*Rf, gr.x - rr.x, gr.y - rr.y, pfr);
-						bs = side_from_prim<true>(A.gas, pfr, nx, ny);
-					}
-				}
-				else { // MUSCL with Van Albada limiter
-					double pr[4];
-					double2 rr;
-					if(bnd) {
-						ghost_state(A.gas, bc, ucl, nx, ny, ucr);
-						cons2prim(A.gas, ucr, pr);
-						rr = make_double2(2.0*gr.x - rl.x, 2.0*gr.y - rl.y);     // ghost centre (aspatial.cpp:98-119)
-					} else {
-						lds4(su + 4*Rf, pr);
-						if(VISC != VISC_NONE) prim2cons(A.gas, pr, ucr);
-						rr = src[Rf];
-					}
-					const double dx = rr.x - rl.x, dy = rr.y - rl.y;
-					double ga[4], gb[4];
-					lds4(sg + 8*L, ga); lds4(sg + 8*L + 4, gb);
-					const double gLx[4] = {ga[0], ga[2], gb[0], gb[2]}, gLy[4] = {ga[1], ga[3], gb[1], gb[3]};
-					for(int k = 0; k < 4; k++) {
-						const double dlr = pr[k] - pl[k];
-						const double dm = 2.0*(gLx[k]*dx + gLy[k]*dy) - dlr;
-						pfl[k] = pl[k] + muscl_term(dm, dlr);
-					}
-					a = side_from_prim<true>(A.gas, pfl, nx, ny);
-					if(bnd) {
-						const double ul[4] = {a.r, a.mx, a.my, a.E};
-						double ur[4];
-						ghost_state(A.gas, bc, ul, nx, ny, ur);
-						bs = load_side<true>(A.gas, ur, nx, ny);
-					} else {
-						lds4(sg + 8*Rf, ga); lds4(sg + 8*Rf + 4, gb);
-						const double gRx[4] = {ga[0], ga[2], gb[0], gb[2]}, gRy[4] = {ga[1], ga[3], gb[1], gb[3]};
-						for(int k = 0; k < 4; k++) {
-							const double dlr = pr[k] - pl[k];
-							const double dp = 2.0*(gRx[k]*dx + gRy[k]*dy) - dlr;
-							pfr[k] = pr[k] - muscl_term(dp, dlr);
-						}
-						bs = side_from_prim<true>(A.gas, pfr, nx, ny);
-					}
-				}
-			}
+		const double2 nrm = sn[e];
+		const double len = slen[e];
+		const double nx = nrm.x, ny = nrm.y;
+		const BCEntry &bc = A.gas.bc[Rf & 15u];
+		double sl[4], sr[4];       // face states: conserved (first order) / primitive; MUSCL: cell states
+		if(L < (unsigned)nc) lds4(fsL + 4*e, sl);
+		else halo_side_state<RECON>(A, gsrc, (size_t)M.thalo[h0 + (int)L - nc], MIDS ? sgr[e] : make_double2(0,0), sl);
+		if(!bnd) {
+			if(Rf < (unsigned)nc) lds4(fsR + 4*e, sr);
+			else halo_side_state<RECON>(A, gsrc, (size_t)M.thalo[h0 + (int)Rf - nc], MIDS ? sgr[e] : make_double2(0,0), sr);
+		}
+		const int gidL = (VISC != VISC_NONE || RECON == FR_MUSCL) ? tile_global(M, t, c0, nc, L) : 0;
+		const int gidR = (VISC != VISC_NONE || RECON == FR_MUSCL) ? (bnd ? gidL : tile_global(M, t, c0, nc, Rf)) : 0;
 
-			flux_from_sides<FLUX>(A.gas, a, bs, nx, ny, f);
-			for(int k = 0; k < 4; k++) f[k] *= len;
-			sri = (fabs(a.vn) + a.c)*len;
-			srj = (fabs(bs.vn) + bs.c)*len;
-
+		Side a, bs;
+		double ucl[4], ucr[4];      // conserved cell states for the viscous flux (right = ghost of the cell state)
+		if(RECON == FR_FIRST) {
+			if(bnd) ghost_state(A.gas, bc, sl, nx, ny, sr);
+			a = load_side<true>(A.gas, sl, nx, ny);
+			bs = load_side<true>(A.gas, sr, nx, ny);
+			if(VISC != VISC_NONE) for(int q = 0; q < 4; q++) { ucl[q] = sl[q]; ucr[q] = sr[q]; }
+		}
+		else if(RECON == FR_LINEAR) {
+			a = side_from_prim<true>(A.gas, sl, nx, ny);
+			if(bnd) {
+				const double ul[4] = {a.r, a.mx, a.my, a.E};
+				double ur[4];
+				ghost_state(A.gas, bc, ul, nx, ny, ur);
+				bs = load_side<true>(A.gas, ur, nx, ny);
+			} else bs = side_from_prim<true>(A.gas, sr, nx, ny);
 			if(VISC != VISC_NONE) {
-				const double ul[4] = {a.r, a.mx, a.my, a.E}, ur[4] = {bs.r, bs.mx, bs.my, bs.E};
-				const double2 rl = src[L];
-				double2 rr;
-				if(bnd) {
-					const double2 gr = M.fgr[e0 + e];
-					rr = make_double2(2.0*gr.x - rl.x, 2.0*gr.y - rl.y);
-				} else rr = src[Rf];
-				double gl[8], grr[8], vf[4];
-				const int gidL = tile_global(M, t, c0, nc, L);
-				const int gidR = bnd ? gidL : tile_global(M, t, c0, nc, Rf);
-				if(RECON != FR_FIRST) {
-					// the unlimited gradients may differ from the staged (limited) ones: read them from global memory
-					ld4(A.gu + 8*(size_t)gidL, gl); ld4(A.gu + 8*(size_t)gidL + 4, gl+4);
-					if(bnd) for(int k = 0; k < 8; k++) grr[k] = gl[k];
-					else { ld4(A.gu + 8*(size_t)gidR, grr); ld4(A.gu + 8*(size_t)gidR + 4, grr+4); }
+				ld4(A.u + 4*(size_t)gidL, ucl);
+				if(bnd) ghost_state(A.gas, bc, ucl, nx, ny, ucr);
+				else ld4(A.u + 4*(size_t)gidR, ucr);
+			}
+		}
+		else { // MUSCL with Van Albada limiter: sl, sr are the primitive CELL states
+			const double2 gr = sgr[e];
+			const double2 rl = M.rc[gidL];
+			double2 rr;
+			if(bnd) {
+				prim2cons(A.gas, sl, ucl);
+				ghost_state(A.gas, bc, ucl, nx, ny, ucr);
+				cons2prim(A.gas, ucr, sr);
+				rr = make_double2(2.0*gr.x - rl.x, 2.0*gr.y - rl.y);     // ghost centre (aspatial.cpp:98-119)
+			} else {
+				rr = M.rc[gidR];
+				if(VISC != VISC_NONE) { prim2cons(A.gas, sl, ucl); prim2cons(A.gas, sr, ucr); }
+			}
+			const double dx = rr.x - rl.x, dy = rr.y - rl.y;
+			double ga[4], gb[4], pfl[4], pfr[4];
+			ld4(gsrc + 8*(size_t)gidL, ga); ld4(gsrc + 8*(size_t)gidL + 4, gb);
+			{
+				const double gx[4] = {ga[0], ga[2], gb[0], gb[2]}, gy[4] = {ga[1], ga[3], gb[1], gb[3]};
+				for(int q = 0; q < 4; q++) {
+					const double dlr = sr[q] - sl[q];
+					pfl[q] = sl[q] + muscl_term(2.0*(gx[q]*dx + gy[q]*dy) - dlr, dlr);
 				}
-				viscous_face_flux<RECON != FR_FIRST, VISC == VISC_CONST>(A.gas, nx, ny, rl.x, rl.y, rr.x, rr.y,
-					ucl, ucr, gl, grr, ul, ur, vf);
-				for(int k = 0; k < 4; k++) f[k] += vf[k]*len;
-				const double mui = VISC == VISC_CONST ? 1.0/A.gas.Reinf : viscosity_cons(A.gas, ul);
-				const double muj = VISC == VISC_CONST ? 1.0/A.gas.Reinf : viscosity_cons(A.gas, ur);
-				const double coi = fmax(4.0/(3.0*ul[0]), A.gas.g/ul[0]);
-				const double coj = fmax(4.0/(3.0*ur[0]), A.gas.g/ur[0]);
-				sri += coi*mui/A.gas.Pr*len*len/M.area[gidL];
-				if(!bnd) srj += coj*muj/A.gas.Pr*len*len/M.area[gidR];
+			}
+			a = side_from_prim<true>(A.gas, pfl, nx, ny);
+			if(bnd) {
+				const double ul[4] = {a.r, a.mx, a.my, a.E};
+				double ur[4];
+				ghost_state(A.gas, bc, ul, nx, ny, ur);
+				bs = load_side<true>(A.gas, ur, nx, ny);
+			} else {
+				ld4(gsrc + 8*(size_t)gidR, ga); ld4(gsrc + 8*(size_t)gidR + 4, gb);
+				const double gx[4] = {ga[0], ga[2], gb[0], gb[2]}, gy[4] = {ga[1], ga[3], gb[1], gb[3]};
+				for(int q = 0; q < 4; q++) {
+					const double dlr = sr[q] - sl[q];
+					pfr[q] = sr[q] - muscl_term(2.0*(gx[q]*dx + gy[q]*dy) - dlr, dlr);
+				}
+				bs = side_from_prim<true>(A.gas, pfr, nx, ny);
 			}
 		}
 
-		// colour rounds of this chunk
-		int myc = 0, clo = 0, chi = 0;
-		{
-			const int last = min(base + FACE_BLOCK, ne) - 1;
-			#pragma unroll
-			for(int c = 1; c < MAXCOL; c++) {
-				if(e >= coloff[c]) myc = c;
-				if(base >= coloff[c]) clo = c;
-				if(last >= coloff[c]) chi = c;
+		double f[4];
+		flux_from_sides<FLUX>(A.gas, a, bs, nx, ny, f);
+		for(int q = 0; q < 4; q++) f[q] *= len;
+		double sri = (fabs(a.vn) + a.c)*len;
+		double srj = (fabs(bs.vn) + bs.c)*len;
+
+		if(VISC != VISC_NONE) {
+			const double ul[4] = {a.r, a.mx, a.my, a.E}, ur[4] = {bs.r, bs.mx, bs.my, bs.E};
+			const double2 rl = M.rc[gidL];
+			double2 rr;
+			if(bnd) {
+				const double2 gr = M.fgr[e0 + e];
+				rr = make_double2(2.0*gr.x - rl.x, 2.0*gr.y - rl.y);
+			} else rr = M.rc[gidR];
+			double gl[8], grr[8], vf[4];
+			if(RECON != FR_FIRST) {
+				ld4(A.gu + 8*(size_t)gidL, gl); ld4(A.gu + 8*(size_t)gidL + 4, gl+4);
+				if(bnd) for(int q = 0; q < 8; q++) grr[q] = gl[q];
+				else { ld4(A.gu + 8*(size_t)gidR, grr); ld4(A.gu + 8*(size_t)gidR + 4, grr+4); }
 			}
+			viscous_face_flux<RECON != FR_FIRST, VISC == VISC_CONST>(A.gas, nx, ny, rl.x, rl.y, rr.x, rr.y,
+				ucl, ucr, gl, grr, ul, ur, vf);
+			for(int q = 0; q < 4; q++) f[q] += vf[q]*len;
+			const double mui = VISC == VISC_CONST ? 1.0/A.gas.Reinf : viscosity_cons(A.gas, ul);
+			const double muj = VISC == VISC_CONST ? 1.0/A.gas.Reinf : viscosity_cons(A.gas, ur);
+			const double coi = fmax(4.0/(3.0*ul[0]), A.gas.g/ul[0]);
+			const double coj = fmax(4.0/(3.0*ur[0]), A.gas.g/ur[0]);
+			sri += coi*mui/A.gas.Pr*len*len/M.area[gidL];
+			if(!bnd) srj += coj*muj/A.gas.Pr*len*len/M.area[gidR];
 		}
-		const bool inL = valid && L < (unsigned)nc;
-		const bool inR = valid && Rf < (unsigned)nc;
-		for(int c = clo; c <= chi; c++) {
-			if(myc == c) {
-				if(inL) {
-					res_s[L] -= f[0]; res_s[TC+L] -= f[1]; res_s[2*TC+L] -= f[2]; res_s[3*TC+L] -= f[3];
-					res_s[4*TC+L] += sri;
-				}
-				if(inR) {
-					res_s[Rf] += f[0]; res_s[TC+Rf] += f[1]; res_s[2*TC+Rf] += f[2]; res_s[3*TC+Rf] += f[3];
-					res_s[4*TC+Rf] += srj;
-				}
-			}
-			__syncthreads();
-		}
+		// the entry's slots now carry its flux and the two spectral radii
+		*reinterpret_cast<double2*>(fsL + 4*e) = make_double2(f[0], f[1]);
+		*reinterpret_cast<double2*>(fsL + 4*e + 2) = make_double2(f[2], f[3]);
+		*reinterpret_cast<double2*>(fsR + 4*e) = make_double2(sri, srj);
 	}
+	__syncthreads();
 
-	// ---- epilogue: one thread per tile cell
-	if(A.epilogue == EP_RESIDUAL) {
-		for(int k = tid; k < nc; k += FACE_BLOCK) {
-			const size_t c = (size_t)(c0 + k);
-			double r[4] = {res_s[k], res_s[TC+k], res_s[2*TC+k], res_s[3*TC+k]};
+	// ---- phase C: per-cell sums in local-face order, then the epilogue
+	double part = 0.0;
+	for(int k = tid; k < nc; k += FACE_BLOCK) {
+		const size_t c = (size_t)(c0 + k);
+		const uint4 cl = k == tid ? cl0 : M.cloc[c];
+		const double ar = k == tid ? ar0 : M.area[c];
+		const unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
+		const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
+		double r[4] = {0,0,0,0}, integ = 0.0;
+		#pragma unroll
+		for(int j = 0; j < 4; j++) {
+			if(j == 3 && nb[3] == NB_NONE) break;
+			const int e = (int)(cf[j] & 0x7FFFu);
+			double f[4];
+			lds4(fsL + 4*e, f);
+			const double2 sr = *reinterpret_cast<const double2*>(fsR + 4*e);
+			if(cf[j] & 0x8000u) { r[0] += f[0]; r[1] += f[1]; r[2] += f[2]; r[3] += f[3]; integ += sr.y; }
+			else { r[0] -= f[0]; r[1] -= f[1]; r[2] -= f[2]; r[3] -= f[3]; integ += sr.x; }
+		}
+		if(A.epilogue == EP_RESIDUAL) {
 			if(A.accumulate) {
 				double o[4];
 				ld4c(A.res + 4*c, o);
 				for(int v = 0; v < 4; v++) r[v] += o[v];
 			}
 			st4(A.res + 4*c, r);
-			if(A.gettimesteps) A.dtm[c] = M.area[c]/res_s[4*TC+k];
-		}
-	}
-	else {
-		double part = 0.0;
-		for(int k = tid; k < nc; k += FACE_BLOCK) {
-			const size_t c = (size_t)(c0 + k);
-			const double ar = M.area[c];
-			const double dt = ar/res_s[4*TC+k];
+			if(A.gettimesteps) A.dtm[c] = ar/integ;
+		} else {
+			const double dt = ar/integ;
 			const double fac = A.cfl*dt/ar;
 			double uo[4];
-			if(RECON == FR_FIRST) lds4(su + 4*k, uo);
-			else { double po[4]; lds4(su + 4*k, po); prim2cons(A.gas, po, uo); }
-			const double rE = res_s[3*TC+k];
-			uo[0] += fac*res_s[k]; uo[1] += fac*res_s[TC+k]; uo[2] += fac*res_s[2*TC+k]; uo[3] += fac*rE;
+			ld4(A.u + 4*c, uo);
+			uo[0] += fac*r[0]; uo[1] += fac*r[1]; uo[2] += fac*r[2]; uo[3] += fac*r[3];
 			st4(A.unew + 4*c, uo);
-			part += rE*rE*ar;
+			part += r[3]*r[3]*ar;
 		}
+	}
+	if(A.epilogue == EP_STEP) {
 		// fixed-order block reduction: warp shuffle tree, then thread 0 sums the warp partials in order
 		for(int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
 		if((tid & 31) == 0) red_s[tid >> 5] = part;
@@ -355,7 +370,7 @@ face_kernel(const FaceArgs A)
 template <int FLUX, int RECON, int VISC>
 static int launch_one(const FaceArgs &a, cudaStream_t s)
 {
-	const FaceSmem S(a.m.TC, a.m.HMAX, a.m.EMAX, RECON != FR_FIRST, RECON != FR_FIRST || VISC != VISC_NONE);
+	const FaceSmem S(a.m.EMAX, RECON != FR_FIRST);
 	const size_t smem = (size_t)S.total;
 	if(smem > 48*1024) {
 		const cudaError_t ea = cudaFuncSetAttribute(face_kernel<FLUX,RECON,VISC>,

@@ -71,6 +71,18 @@ cell_kernel(const CellArgs A)
 		if(MIDS) bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
 		if(METRICS) { bulk_g2s(sn, M.fn + e0, (unsigned)ne*16u, bar); bulk_g2s(slen, M.flen + e0, (unsigned)ne*8u, bar); }
 	}
+	if(tid == 32 && A.prefetch_distance > 0 && t + A.prefetch_distance < M.ntile) {
+		const int tp = t + A.prefetch_distance;
+		const int pc0 = M.tcell0[tp], pnc = M.tcell0[tp+1] - pc0;
+		const int pe0 = M.fsoff[tp], pne = M.fsoff[tp+1] - pe0;
+		bulk_prefetch_l2(A.u + 4*(size_t)pc0, (unsigned)pnc*32u);
+		bulk_prefetch_l2(M.rc + pc0, (unsigned)pnc*16u);
+		bulk_prefetch_l2(M.cloc + pc0, (unsigned)pnc*16u);
+		{ const int ph0 = M.thoff[tp] & ~3, ph1 = (M.thoff[tp+1] + 3) & ~3; if(ph1 > ph0) bulk_prefetch_l2(M.thalo + ph0, (unsigned)(ph1 - ph0)*4u); }
+		if(GRAD == GM_WLS) bulk_prefetch_l2(M.wlsV + pc0, (unsigned)pnc*32u);
+		if(MIDS) bulk_prefetch_l2(M.fgr + pe0, (unsigned)pne*16u);
+		if(METRICS) { bulk_prefetch_l2(M.fn + pe0, (unsigned)pne*16u); bulk_prefetch_l2(M.flen + pe0, (unsigned)pne*8u); }
+	}
 	if(NEED_NBRS) {
 		for(int k = tid; k < nh*3; k += CELL_BLOCK) {
 			const int h = k/3, piece = k - 3*h;
@@ -123,7 +135,7 @@ cell_kernel(const CellArgs A)
 			#pragma unroll
 			for(int j = 0; j < 4; j++) {
 				const unsigned nj = nb[j];
-				if(nj == NB_NONE) continue;
+				if(j == 3 && nj == NB_NONE) break;      // only the fourth slot can be empty (triangles)
 				const int le = (int)(cf[j] & 0x7FFFu);
 				double pj[4];
 				double2 rj;
@@ -208,7 +220,7 @@ cell_kernel(const CellArgs A)
 			}
 			#pragma unroll
 			for(int j = 0; j < 4; j++) {
-				if(nb[j] == NB_NONE) continue;
+				if(j == 3 && nb[3] == NB_NONE) break;
 				const double2 mid = sgr[cf[j] & 0x7FFFu];
 				const double dx = mid.x - rci.x, dy = mid.y - rci.y;
 				#pragma unroll

@@ -1,12 +1,14 @@
 #!/bin/bash
-# Times the residual with differently-built copies of the library (launch bounds / block sizes) and tile sizes.
-# usage: tools/variant_sweep.sh "<lib:tile> ..."   (lib = path of a .so or "default")
+# Times the residual with differently-built copies of the library (launch bounds / block sizes), tile sizes and
+# environment knobs. usage: tools/variant_sweep.sh "<lib:tile[:ENV=val]> ..."   (lib = path of a .so or "default")
 for spec in $1; do
-  lib=${spec%%:*}; tile=${spec#*:}
+  IFS=: read lib tile envs <<< "$spec"
   if [ "$lib" != "default" ]; then export FVENS_B200_LIB=$lib; else unset FVENS_B200_LIB; fi
+  if [ -n "$envs" ]; then export $envs; fi
   python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 1 --tile $tile 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('$spec', 'ms/step %.3f' % d['ms_per_step'], 'cell %.3f face %.3f' % (d['kernels_ms']['gradient_limiter_pass'], d['kernels_ms']['face_pass']), 'euler %.3f' % d['euler_step']['ms_per_step'], 'frac %.3f' % d['residual_roofline_frac'])
 "
+  if [ -n "$envs" ]; then unset ${envs%%=*}; fi
 done
