@@ -282,7 +282,7 @@ int fvg_flow_create(fvg_mesh *mesh, const fvg_physics *phys, const fvg_numerics 
 	P.need_gu = P.order2 && (P.recon == FVG_RECON_WENO || P.recon == FVG_RECON_VANALBADA ||
 	                         (P.visc != VISC_NONE && limited));
 
-	const int n = mesh->d.ncell;
+	const int n = mesh->d.ncell + mesh->d.nghost;      // gradient rows exist for the ghosts too (filled by the halo exchange)
 	int rc;
 	if(P.need_lg && (rc = dev_alloc(f.get(), &f->d_lg, 8*(size_t)n)) != 0) return rc;
 	if(P.need_gu && (rc = dev_alloc(f.get(), &f->d_gu, 8*(size_t)n)) != 0) return rc;
@@ -356,6 +356,7 @@ int fvg_residual(fvg_flow *f, const double *d_u, double *d_res, int accumulate, 
                  double *d_dtm, void *stream)
 {
 	if(!f || !d_u || !d_res || (gettimesteps && !d_dtm)) { set_error("fvg_residual: null argument"); return FVG_ERR_INVALID; }
+	if(f->mesh->nranks > 1) { set_error("fvg_residual: a subdomain mesh needs the ghost gradients exchanged between the passes; use fvg_gradient_pass / fvg_face_pass"); return FVG_ERR_UNSUPPORTED; }
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	const DMesh &D = f->mesh->d;
 	const int n = D.ncell;
@@ -542,6 +543,82 @@ int fvg_entropy_error(fvg_flow *f, const double *d_u, double *h_out)
 	return 0;
 }
 
+// ------------------------------------------------------------------------------------ multi-GPU pieces
+
+int fvg_partition_sfc(const fvg_umesh *m, int nranks, int *cell_rank)
+{
+	if(!m || !cell_rank || nranks < 1) { set_error("fvg_partition_sfc: bad argument"); return FVG_ERR_INVALID; }
+	const int n = m->m.gnelem();
+	std::vector<double> rc(2*(size_t)n);
+	m->m.compute_cell_centres(rc.data());
+	std::vector<int> order;
+	hilbert_order(n, rc.data(), order);
+	for(int k = 0; k < n; k++) cell_rank[order[k]] = (int)(((long long)k*nranks)/n);
+	return 0;
+}
+
+int fvg_halo_pack(const fvg_mesh *m, const double *d_src, int width, double *d_sendbuf, void *stream)
+{
+	if(!m || !d_src || (m->d.nsend > 0 && !d_sendbuf) || width < 1) { set_error("fvg_halo_pack: bad argument"); return FVG_ERR_INVALID; }
+	return launch_halo_pack(m->d, d_src, width, d_sendbuf, static_cast<cudaStream_t>(stream));
+}
+
+int fvg_flow_use_buffers(fvg_flow *f, double *d_lg, double *d_gu)
+{
+	if(!f) { set_error("fvg_flow_use_buffers: null argument"); return FVG_ERR_INVALID; }
+	if((f->plan.need_lg && !d_lg) || (f->plan.need_gu && !d_gu)) { set_error("fvg_flow_use_buffers: this flow needs the buffer that was passed as NULL"); return FVG_ERR_INVALID; }
+	if(d_lg) f->d_lg = d_lg;
+	if(d_gu) f->d_gu = d_gu;
+	return 0;
+}
+
+int fvg_flow_buffers(fvg_flow *f, double **d_lg, double **d_gu)
+{
+	if(!f) { set_error("fvg_flow_buffers: null argument"); return FVG_ERR_INVALID; }
+	if(d_lg) *d_lg = f->d_lg;
+	if(d_gu) *d_gu = f->d_gu;
+	return 0;
+}
+
+int fvg_gradient_pass(fvg_flow *f, const double *d_u, int stage, void *stream)
+{
+	if(!f || !d_u) { set_error("fvg_gradient_pass: null argument"); return FVG_ERR_INVALID; }
+	if(!f->mesh->identity_perm) { set_error("fvg_gradient_pass: split passes need a device-ordered state (reorder none or a subdomain mesh)"); return FVG_ERR_UNSUPPORTED; }
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	const FlowPlan &P = f->plan;
+	if(!P.order2) return 0;
+	if(P.recon != FVG_RECON_WENO) return stage == 0 ? run_gradient_pass(f, d_u, s) : 0;
+	// WENO: stage 0 = unlimited gradients (exchange them), stage 1 = the weighted average
+	CellArgs a;
+	a.m = f->mesh->d; a.gas = f->gas; a.u = d_u; a.ug = nullptr; a.gin = nullptr; a.bnd_policy = P.bnd_policy;
+	a.prefetch_distance = f->prefetch_distance;
+	int rc;
+	if(stage == 0) { a.lg = nullptr; a.gu = f->d_gu; rc = launch_cell_kernel(P.gradient, 0, false, a, s); }
+	else rc = launch_weno_kernel(f->mesh->d, f->gas.limiter_param, f->d_gu, f->d_lg, s);
+	if(rc == 0) f->launches++;
+	return rc;
+}
+
+int fvg_face_pass(fvg_flow *f, const double *d_u, double *d_res, int accumulate, int gettimesteps, double *d_dtm, void *stream)
+{
+	if(!f || !d_u || !d_res || (gettimesteps && !d_dtm)) { set_error("fvg_face_pass: null argument"); return FVG_ERR_INVALID; }
+	if(!f->mesh->identity_perm) { set_error("fvg_face_pass: split passes need a device-ordered state"); return FVG_ERR_UNSUPPORTED; }
+	return run_face_pass(f, d_u, EP_RESIDUAL, accumulate, gettimesteps, d_res, d_dtm, 0.0, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int fvg_euler_face_pass(fvg_flow *f, const double *d_u, double *d_unew, double cfl, double *d_resnorm2, void *stream)
+{
+	if(!f || !d_u || !d_unew) { set_error("fvg_euler_face_pass: null argument"); return FVG_ERR_INVALID; }
+	if(!f->mesh->identity_perm) { set_error("fvg_euler_face_pass: split passes need a device-ordered state"); return FVG_ERR_UNSUPPORTED; }
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	int rc;
+	if((rc = run_face_pass(f, d_u, EP_STEP, 0, 1, nullptr, nullptr, cfl, d_unew, s)) != 0) return rc;
+	if((rc = launch_final_norm(f->d_partial, f->mesh->d.ntile, f->d_norm, s)) != 0) return rc;
+	f->launches++;
+	if(d_resnorm2) FVG_CUDA(cudaMemcpyAsync(d_resnorm2, f->d_norm, sizeof(double), cudaMemcpyDeviceToDevice, s));
+	return 0;
+}
+
 // ------------------------------------------------------------------------------------ pseudo-time
 
 /// One fused step on device-ordered buffers: reads uin, writes uout, norm^2 -> f->d_norm
@@ -561,6 +638,7 @@ static int step_device_order(fvg_flow *f, const double *uin, double *uout, doubl
 int fvg_euler_step(fvg_flow *f, double *d_u, double cfl, double *d_resnorm2, void *stream)
 {
 	if(!f || !d_u) { set_error("fvg_euler_step: null argument"); return FVG_ERR_INVALID; }
+	if(f->mesh->nranks > 1) { set_error("fvg_euler_step: use the split passes on a subdomain mesh"); return FVG_ERR_UNSUPPORTED; }
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	const DMesh &D = f->mesh->d;
 	const size_t n = D.ncell;
@@ -584,6 +662,7 @@ int fvg_forward_euler_solve(fvg_flow *f, double *d_u, double cfl, double tol, in
                             int check_every, int *h_steps, double *h_hist)
 {
 	if(!f || !d_u || !h_steps) { set_error("fvg_forward_euler_solve: null argument"); return FVG_ERR_INVALID; }
+	if(f->mesh->nranks > 1) { set_error("fvg_forward_euler_solve: single-process driver; use the split passes on a subdomain mesh"); return FVG_ERR_UNSUPPORTED; }
 	if(check_every < 1) check_every = 1;
 	*h_steps = 0;
 	if(maxiter <= 0) return 0;

@@ -108,7 +108,15 @@ static int upload(fvg_mesh *m, const std::vector<T> &h, const T **dptr)
 	return 0;
 }
 
-static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m)
+/** Builds the device mesh of one subdomain (or of the whole mesh when cell_rank is null).
+ * Device cell numbering: the rank's own cells first, in the global locality order restricted to the
+ * rank; then its ghost cells (cells of other ranks across a cut face - one layer, as the reference's
+ * connectivity ghosts, src/mesh/mesh.hpp:60-70), grouped by owner rank and sorted by the owner's own
+ * device index, so that a ghost block is exactly what the owner's pack kernel emits for this rank.
+ * Cut faces keep the GLOBAL left/right roles and normal: both ranks evaluate the identical
+ * expression, which keeps the scheme conservative to the last bit and the 1/2/4/8-GPU results equal. */
+static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *cell_rank, int rank, int nranks,
+                 fvg_mesh *m)
 {
 	const int n = hm->nelem, nb = hm->nbface, nf = hm->naface, mw = hm->maxnnode;
 	if(n <= 0 || nf <= 0 || !hm->coords || !hm->inpoel || !hm->nnode || !hm->esuel || !hm->elemface ||
@@ -117,16 +125,19 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 		return FVG_ERR_INVALID;
 	}
 	if(hm->nconnface != 0) {
-		set_error("fvg_mesh_create: connectivity faces are handled by the partitioned-mesh entry point");
+		set_error("fvg_mesh_create: pass the GLOBAL mesh plus a cell->rank map; pre-partitioned host meshes are not accepted");
 		return FVG_ERR_UNSUPPORTED;
 	}
 	if(mw < 3 || mw > 4) { set_error("fvg_mesh_create: maxnnode must be 3 or 4"); return FVG_ERR_INVALID; }
+	if(nranks < 1 || rank < 0 || rank >= nranks) { set_error("fvg_mesh_create: bad rank"); return FVG_ERR_INVALID; }
 	const int TC = opts && opts->tile_cells > 0 ? opts->tile_cells : 256;
 	if(TC % 32 != 0 || TC > 1024) { set_error("fvg_mesh_create: tile_cells must be a multiple of 32, <= 1024"); return FVG_ERR_INVALID; }
 	// capacities of a tile's shared-memory staging areas: halo cells and stream entries
 	const int HMAX = std::max(32, (3*TC/8 + 31)/32*32);
 	const int EMAX = (2*TC + TC/8 + 31)/32*32;
 	const int reorder = opts ? opts->reorder : FVG_REORDER_NONE;
+	auto rank_of = [&](int o) { return cell_rank ? cell_rank[o] : 0; };
+	if(cell_rank) for(int o = 0; o < n; o++) if(cell_rank[o] < 0 || cell_rank[o] >= nranks) { set_error("fvg_mesh_create: cell_rank entry out of range"); return FVG_ERR_INVALID; }
 
 	// ---- geometry in reference numbering
 	std::vector<double> rc(2*(size_t)n);
@@ -137,7 +148,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 			rc[2*(size_t)i+d] = c/(double)hm->nnode[i];
 		}
 
-	// ---- boundary markers -> slots of the flow's BC table
+	// ---- boundary markers -> slots of the flow's BC table (global, so that every rank agrees)
 	m->h_btag.resize(nb);
 	for(int b = 0; b < nb; b++) m->h_btag[b] = hm->btags[(size_t)b*hm->nbtag];
 	m->h_markers.assign(m->h_btag.begin(), m->h_btag.end());
@@ -148,42 +159,84 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 	for(int b = 0; b < nb; b++)
 		bslot[b] = (int)(std::lower_bound(m->h_markers.begin(), m->h_markers.end(), m->h_btag[b]) - m->h_markers.begin());
 
-	// ---- permutation
-	std::vector<int> &new2old = m->h_new2old, &old2new = m->h_old2new;
-	if(reorder == FVG_REORDER_HILBERT) hilbert_order(n, rc.data(), new2old);
-	else if(reorder == FVG_REORDER_RCM) rcm_order(n, mw, hm->esuel, hm->nnode, new2old);
-	else if(reorder == FVG_REORDER_NONE) { new2old.resize(n); std::iota(new2old.begin(), new2old.end(), 0); }
+	// ---- global locality order, then the rank's own cells and ghosts
+	std::vector<int> gorder;
+	if(reorder == FVG_REORDER_HILBERT) hilbert_order(n, rc.data(), gorder);
+	else if(reorder == FVG_REORDER_RCM) rcm_order(n, mw, hm->esuel, hm->nnode, gorder);
+	else if(reorder == FVG_REORDER_NONE) { gorder.resize(n); std::iota(gorder.begin(), gorder.end(), 0); }
 	else { set_error("fvg_mesh_create: unknown reorder option"); return FVG_ERR_INVALID; }
-	old2new.resize(n);
-	for(int i = 0; i < n; i++) old2new[new2old[i]] = i;
-	m->identity_perm = true;
-	for(int i = 0; i < n; i++) if(new2old[i] != i) { m->identity_perm = false; break; }
 	m->reorder = reorder;
 
-	auto faceL = [&](int f) { return old2new[hm->intfac[4*(size_t)f]]; };
-	auto faceR = [&](int f) { return f < nb ? -1 : old2new[hm->intfac[4*(size_t)f+1]]; };
-	// neighbour (device numbering) of device cell i across local face j: >= 0 cell, -1 boundary
+	std::vector<int> rankidx((size_t)n);          // position of every cell inside its owner's own-cell sequence
+	{
+		std::vector<int> cnt(nranks, 0);
+		for(int k = 0; k < n; k++) { const int o = gorder[k]; rankidx[o] = cnt[rank_of(o)]++; }
+	}
+	std::vector<int> &d2g = m->h_new2old, &g2d = m->h_old2new;
+	g2d.assign(n, -1);
+	for(int k = 0; k < n; k++) { const int o = gorder[k]; if(rank_of(o) == rank) { g2d[o] = (int)d2g.size(); d2g.push_back(o); } }
+	const int nown = (int)d2g.size();
+	if(nown == 0) { set_error("fvg_mesh_create: this rank owns no cells"); return FVG_ERR_INVALID; }
+	m->send_counts.assign(nranks, 0); m->recv_counts.assign(nranks, 0);
+	{
+		std::vector<std::pair<long long,int>> ghosts;      // (owner*2^32 + owner's index, old id)
+		std::vector<std::pair<int,int>> sends;             // (peer, my device index)
+		for(int i = 0; i < nown; i++) {
+			const int o = d2g[i];
+			for(int j = 0; j < hm->nnode[o]; j++) {
+				const int e = hm->esuel[(size_t)o*mw+j];
+				if(e < 0 || e >= n || rank_of(e) == rank) continue;
+				ghosts.push_back(std::make_pair(((long long)rank_of(e) << 32) + rankidx[e], e));
+				sends.push_back(std::make_pair(rank_of(e), i));
+			}
+		}
+		std::sort(ghosts.begin(), ghosts.end());
+		ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
+		for(const auto &gst : ghosts) { g2d[gst.second] = (int)d2g.size(); d2g.push_back(gst.second); m->recv_counts[rank_of(gst.second)]++; }
+		std::sort(sends.begin(), sends.end());
+		sends.erase(std::unique(sends.begin(), sends.end()), sends.end());
+		m->h_send_idx.clear();
+		for(const auto &sd : sends) { m->h_send_idx.push_back(sd.second); m->send_counts[sd.first]++; }
+	}
+	const int ntot = (int)d2g.size();
+	m->nghost = ntot - nown;
+	m->nranks = nranks; m->rank = rank;
+	// subdomain meshes expose device-ordered arrays (own rows, then ghost rows): nothing to permute at the API
+	m->identity_perm = true;
+	if(nranks == 1) for(int i = 0; i < nown; i++) if(d2g[i] != i) { m->identity_perm = false; break; }
+
+	// faces that touch an own cell, ascending global id
+	auto is_own = [&](int dev) { return dev >= 0 && dev < nown; };
+	auto faceL = [&](int f) { return g2d[hm->intfac[4*(size_t)f]]; };
+	auto faceR = [&](int f) { return f < nb ? -1 : g2d[hm->intfac[4*(size_t)f+1]]; };
+	std::vector<int> rfaces;
+	for(int f = 0; f < nf; f++) {
+		const int L = faceL(f), R = faceR(f);
+		if(is_own(L) || is_own(R)) rfaces.push_back(f);
+	}
+	const int nrf = (int)rfaces.size();
+	// neighbour (device numbering) of own device cell i across local face j: >= 0 cell (own or ghost), -1 boundary
 	auto nbr_of = [&](int i, int j) {
-		const int e = hm->esuel[(size_t)new2old[i]*mw+j];
-		return e < n ? old2new[e] : -1;
+		const int e = hm->esuel[(size_t)d2g[i]*mw+j];
+		return e < n ? g2d[e] : -1;
 	};
 
-	// ---- tiles: greedy ranges of consecutive cells within the capacities
+	// ---- tiles: greedy ranges of consecutive own cells within the capacities
 	std::vector<int> tcell0(1, 0), thoff(1, 0), thalo;
-	std::vector<int> stamp((size_t)n, -1);
+	std::vector<int> stamp((size_t)ntot, -1);
 	long long distsum = 0;
 	{
 		std::vector<int> halo;
 		int s = 0;
-		while(s < n) {
-			int nc = std::min(TC, n - s);
+		while(s < nown) {
+			int nc = std::min(TC, nown - s);
 			const int t = (int)tcell0.size() - 1;
 			for(int attempt = 0; ; attempt++) {
 				halo.clear();
 				int E = 0;
 				const int tag = t*64 + (attempt & 63);      // unique stamp per (tile, attempt)
 				for(int i = s; i < s+nc; i++) {
-					const int nn = hm->nnode[new2old[i]];
+					const int nn = hm->nnode[d2g[i]];
 					for(int j = 0; j < nn; j++) {
 						const int q = nbr_of(i, j);
 						if(q < 0) { E++; continue; }
@@ -194,9 +247,6 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 				}
 				if(((int)halo.size() <= HMAX && E <= EMAX) || nc == 1) break;
 				nc = std::max(1, std::min(nc - 1, (int)(nc*0.8)));
-				if(attempt >= 62) {    // stamps would repeat: clear them
-					for(int q : halo) stamp[q] = -1;
-				}
 			}
 			if((int)halo.size() > HMAX) { set_error("fvg_mesh_create: a single cell exceeds the halo capacity"); return FVG_ERR_INVALID; }
 			std::sort(halo.begin(), halo.end());
@@ -207,33 +257,36 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 		}
 	}
 	const int ntile = (int)tcell0.size() - 1;
-	std::vector<int> tile_of((size_t)n);
+	std::vector<int> tile_of((size_t)ntot, -1);
 	for(int t = 0; t < ntile; t++) for(int i = tcell0[t]; i < tcell0[t+1]; i++) tile_of[i] = t;
 
 	// ---- face streams: count (padded to 4), fill in reference face order, colour, sort by colour
 	std::vector<int> fsoff((size_t)ntile+1, 0);
-	for(int f = 0; f < nf; f++) {
+	int ninterior = 0;
+	for(int f : rfaces) {
 		const int L = faceL(f), R = faceR(f);
-		fsoff[tile_of[L]+1]++;
-		if(R >= 0) {
-			if(tile_of[R] != tile_of[L]) fsoff[tile_of[R]+1]++;
-			distsum += std::abs(L-R);
-		}
+		const int tL = L >= 0 ? tile_of[L] : -1, tR = R >= 0 ? tile_of[R] : -1;
+		if(tL >= 0) fsoff[tL+1]++;
+		if(tR >= 0 && tR != tL) fsoff[tR+1]++;
+		if(R >= 0) { distsum += std::abs(L-R); ninterior++; }
 	}
 	int ncopies = 0;
 	for(int t = 0; t < ntile; t++) { ncopies += fsoff[t+1]; fsoff[t+1] = fsoff[t] + (fsoff[t+1] + 3)/4*4; }
 	const int ns = fsoff[ntile];
-	m->ncut_dup = ncopies - nf;
-	m->mean_nbr_dist = nf > nb ? (double)distsum/(double)(nf-nb) : 0.0;
+	m->ncut_dup = ncopies - nrf;
+	m->mean_nbr_dist = ninterior ? (double)distsum/(double)ninterior : 0.0;
 
 	const int PAD = INT_MIN;
-	std::vector<int> sface((size_t)ns, PAD);    // reference face of each entry, -1-f for duplicates, PAD for padding
+	std::vector<int> sface((size_t)ns, PAD);    // global face of each entry, -1-f for the second copy, PAD for padding
 	{
 		std::vector<int> pos(fsoff.begin(), fsoff.end()-1);
-		for(int f = 0; f < nf; f++) {
+		for(int f : rfaces) {
 			const int L = faceL(f), R = faceR(f);
-			sface[pos[tile_of[L]]++] = f;
-			if(R >= 0 && tile_of[R] != tile_of[L]) sface[pos[tile_of[R]]++] = -1-f;
+			const int tL = L >= 0 ? tile_of[L] : -1, tR = R >= 0 ? tile_of[R] : -1;
+			if(tL >= 0) {
+				sface[pos[tL]++] = f;
+				if(tR >= 0 && tR != tL) sface[pos[tR]++] = -1-f;
+			} else sface[pos[tR]++] = f;                 // left cell is a ghost: the right cell's tile holds the only copy
 		}
 	}
 	std::vector<int> fcoloff((size_t)ntile*(MAXCOL+1), 0);
@@ -277,7 +330,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 	fLR.assign((size_t)ns, LR_PAD);
 	std::vector<double2> fn((size_t)ns, make_double2(1.0, 0.0)), fgr((size_t)ns, make_double2(0.0, 0.0));
 	std::vector<double> flen((size_t)ns, 0.0);
-	std::vector<int> own_entry((size_t)nf), dup_entry((size_t)nf, -1);
+	std::vector<int> own_entry((size_t)nf, -1), dup_entry((size_t)nf, -1);
 	m->h_fref.assign(ns, PAD); m->h_fcolour = scolour; m->h_ftile.resize(ns);
 	auto local_of = [&](int t, int g) -> unsigned {
 		if(tile_of[g] == t) return (unsigned)(g - tcell0[t]);
@@ -309,29 +362,29 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 			m->h_fref[e] = sface[e];
 		}
 
-	// ---- per-cell arrays in device order
-	std::vector<uint4> cloc((size_t)n);
-	std::vector<double2> drc((size_t)n);
-	std::vector<double> area((size_t)n), clength((size_t)n);
-	for(int i = 0; i < n; i++) {
-		const int o = new2old[i], t = tile_of[i];
+	// ---- per-cell arrays in device order (centres also for the ghosts)
+	std::vector<uint4> cloc((size_t)nown);
+	std::vector<double2> drc((size_t)ntot);
+	std::vector<double> area((size_t)nown), clength((size_t)nown);
+	for(int i = 0; i < ntot; i++) drc[i] = make_double2(rc[2*(size_t)d2g[i]], rc[2*(size_t)d2g[i]+1]);
+	for(int i = 0; i < nown; i++) {
+		const int o = d2g[i], t = tile_of[i];
 		unsigned a[4] = {NB_NONE, NB_NONE, NB_NONE, NB_NONE}, c[4] = {0,0,0,0};
 		for(int j = 0; j < hm->nnode[o]; j++) {
 			const int e = hm->esuel[(size_t)o*mw+j];
 			const int f = hm->elemface[(size_t)o*mw+j];
 			if(e < 0 || f < 0 || f >= nf) { set_error("fvg_mesh_create: inconsistent esuel/elemface"); return FVG_ERR_INVALID; }
 			if(e >= n && (e-n != f || f >= nb)) { set_error("fvg_mesh_create: boundary ghost index does not match its face"); return FVG_ERR_INVALID; }
-			a[j] = e < n ? local_of(t, old2new[e]) : NB_BND;
+			a[j] = e < n ? local_of(t, g2d[e]) : NB_BND;
 			const bool isL = hm->intfac[4*(size_t)f] == o;
 			if(!isL && (f < nb || hm->intfac[4*(size_t)f+1] != o)) { set_error("fvg_mesh_create: elemface/intfac mismatch"); return FVG_ERR_INVALID; }
 			// the copy of the face that lives in this cell's tile
 			int entry = own_entry[f];
 			if(!isL && dup_entry[f] >= 0) entry = dup_entry[f];
-			if(m->h_ftile[entry] != t) { set_error("fvg_mesh_create: internal error, face copy not in the cell's tile"); return FVG_ERR_INVALID; }
+			if(entry < 0 || m->h_ftile[entry] != t) { set_error("fvg_mesh_create: internal error, face copy not in the cell's tile"); return FVG_ERR_INVALID; }
 			c[j] = (unsigned)(entry - fsoff[t]) | (isL ? 0u : 0x8000u);
 		}
 		cloc[i] = make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), c[0] | (c[1] << 16), c[2] | (c[3] << 16));
-		drc[i] = make_double2(rc[2*(size_t)o], rc[2*(size_t)o+1]);
 		area[i] = hm->area[o];
 		double l2 = 0;
 		const int nn = hm->nnode[o];
@@ -344,20 +397,26 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 		clength[i] = std::sqrt(l2);
 	}
 
-	// ---- boundary arrays (reference boundary-face order)
+	// ---- boundary arrays (global boundary-face order; faces of other ranks carry cell -1)
 	std::vector<int> bcell((size_t)nb);
 	std::vector<double2> rcbp((size_t)nb);
-	m->h_bentry.resize(nb);
+	m->h_bentry.assign(nb, 0);
 	for(int b = 0; b < nb; b++) {
 		const int o = hm->intfac[4*(size_t)b];
-		bcell[b] = old2new[o];
-		m->h_bentry[b] = own_entry[b];
-		const double2 mid = fgr[own_entry[b]];
-		rcbp[b] = make_double2(2.0*mid.x - rc[2*(size_t)o], 2.0*mid.y - rc[2*(size_t)o+1]);
+		bcell[b] = is_own(g2d[o]) ? g2d[o] : -1;
+		if(own_entry[b] >= 0) m->h_bentry[b] = own_entry[b];
+		double mid[2];
+		for(int d = 0; d < 2; d++) {
+			double sum = 0;
+			sum += hm->coords[2*(size_t)hm->intfac[4*(size_t)b+2]+d];
+			sum += hm->coords[2*(size_t)hm->intfac[4*(size_t)b+3]+d];
+			mid[d] = sum/2;
+		}
+		rcbp[b] = make_double2(2.0*mid[0] - rc[2*(size_t)o], 2.0*mid[1] - rc[2*(size_t)o+1]);
 	}
 
-	// ---- least-squares matrices: accumulate in reference face order, invert as adj/det
-	std::vector<double4> V((size_t)n);
+	// ---- least-squares matrices: accumulate in reference face order over the GLOBAL mesh, invert as adj/det
+	std::vector<double4> V((size_t)nown);
 	{
 		std::vector<double> A(4*(size_t)n, 0.0);
 		for(int f = 0; f < nf; f++) {
@@ -373,8 +432,8 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 				if(f >= nb) A[4*(size_t)hm->intfac[4*(size_t)f+1]+2*p+q] += w2*dr[p]*dr[q];
 			}
 		}
-		for(int i = 0; i < n; i++) {
-			const int o = new2old[i];
+		for(int i = 0; i < nown; i++) {
+			const int o = d2g[i];
 			const double a = A[4*(size_t)o], b = A[4*(size_t)o+1], c = A[4*(size_t)o+2], d = A[4*(size_t)o+3];
 			const double idet = 1.0/(a*d - c*b);
 			V[i] = make_double4(d*idet, -b*idet, -c*idet, a*idet);
@@ -383,15 +442,17 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh *m
 
 	// ---- upload
 	DMesh &D = m->d;
-	D.ncell = n; D.nbface = nb; D.naface = nf; D.ntile = ntile; D.TC = TC; D.HMAX = HMAX; D.EMAX = EMAX; D.nstream = ns;
+	D.ncell = nown; D.nghost = ntot - nown; D.nbface = nb; D.naface = nf; D.ntile = ntile; D.TC = TC; D.HMAX = HMAX; D.EMAX = EMAX; D.nstream = ns;
+	D.nsend = (int)m->h_send_idx.size();
 	int rcode;
 #define UP(vec, field) if((rcode = upload(m, vec, &D.field)) != 0) return rcode;
 	UP(cloc, cloc) UP(drc, rc) UP(area, area) UP(V, wlsV) UP(clength, clength)
 	UP(tcell0, tcell0) UP(thoff, thoff) UP(thalo, thalo)
 	UP(fsoff, fsoff) UP(fcoloff, fcoloff) UP(fLR, fLR) UP(fn, fn) UP(flen, flen) UP(fgr, fgr)
 	UP(m->h_fref, fref) UP(bcell, bcell) UP(m->h_bentry, bentry) UP(bslot, bslot) UP(rcbp, rcbp)
+	UP(m->h_send_idx, send_idx)
 	if(m->identity_perm) { D.new2old = nullptr; D.old2new = nullptr; }
-	else { UP(new2old, new2old) UP(old2new, old2new) }
+	else { UP(d2g, new2old) D.old2new = nullptr; }
 #undef UP
 	m->h_tcell0 = tcell0;
 	return 0;
@@ -416,6 +477,12 @@ int fvg_device_count(int *count)
 
 int fvg_mesh_create(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh **out)
 {
+	return fvg_mesh_create_part(hm, opts, nullptr, 0, 1, out);
+}
+
+int fvg_mesh_create_part(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *cell_rank, int rank, int nranks,
+                         fvg_mesh **out)
+{
 	if(!hm || !out) { set_error("fvg_mesh_create: null argument"); return FVG_ERR_INVALID; }
 	*out = nullptr;
 	if(opts && opts->device >= 0) FVG_CUDA(cudaSetDevice(opts->device));
@@ -426,7 +493,7 @@ int fvg_mesh_create(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh
 		if(e != cudaSuccess) { delete m; return cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__); }
 	}
 	int rc;
-	try { rc = build(hm, opts, m); }
+	try { rc = build(hm, opts, cell_rank, rank, nranks, m); }
 	catch(std::exception &ex) { set_error(std::string("fvg_mesh_create: ") + ex.what()); rc = FVG_ERR_INVALID; }
 	if(rc != 0) { fvg_mesh_destroy(m); return rc; }
 	*out = m;
@@ -443,6 +510,7 @@ void fvg_mesh_destroy(fvg_mesh *m)
 int fvg_mesh_get_info(const fvg_mesh *m, fvg_mesh_info *info)
 {
 	if(!m || !info) { set_error("fvg_mesh_get_info: null argument"); return FVG_ERR_INVALID; }
+	info->nghost = m->d.nghost; info->rank = m->rank; info->nranks = m->nranks; info->nsend = m->d.nsend;
 	info->ncell = m->d.ncell; info->nbface = m->d.nbface; info->naface = m->d.naface;
 	info->ntile = m->d.ntile; info->tile_cells = m->d.TC; info->nstream = m->d.nstream;
 	info->ncut_dup = m->ncut_dup; info->max_colours = m->max_colours; info->reorder = m->reorder;
@@ -454,6 +522,15 @@ int fvg_mesh_permutation(const fvg_mesh *m, int *cell_new2old)
 {
 	if(!m || !cell_new2old) { set_error("fvg_mesh_permutation: null argument"); return FVG_ERR_INVALID; }
 	std::memcpy(cell_new2old, m->h_new2old.data(), sizeof(int)*m->h_new2old.size());
+	return 0;
+}
+
+int fvg_mesh_halo_lists(const fvg_mesh *m, int *send_counts, int *recv_counts, int *send_idx)
+{
+	if(!m) { set_error("fvg_mesh_halo_lists: null argument"); return FVG_ERR_INVALID; }
+	if(send_counts) std::memcpy(send_counts, m->send_counts.data(), sizeof(int)*m->send_counts.size());
+	if(recv_counts) std::memcpy(recv_counts, m->recv_counts.data(), sizeof(int)*m->recv_counts.size());
+	if(send_idx && !m->h_send_idx.empty()) std::memcpy(send_idx, m->h_send_idx.data(), sizeof(int)*m->h_send_idx.size());
 	return 0;
 }
 

@@ -39,7 +39,9 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 /// has a contiguous FACE STREAM segment (every face touching one of its own cells; a face cut by a
 /// tile boundary has a copy in both tiles), sorted by colour, start and length padded to 4 entries.
 struct DMesh {
-	int ncell, nbface, naface, ntile, TC, HMAX, EMAX, nstream;
+	int ncell;              ///< own cells (tiles, residual rows); state-like arrays have ncell + nghost rows
+	int nghost, nsend;      ///< ghost cells received from / own cells sent to other ranks per exchange
+	int nbface, naface, ntile, TC, HMAX, EMAX, nstream;
 	// per cell
 	const uint4 *cloc;      ///< x,y: local index of the neighbour across local face 0..3 (4 x u16; NB_NONE / NB_BND);
 	                        ///< z,w: local stream entry of local face 0..3 (4 x u16, bit 15 set if the cell is the entry's right cell)
@@ -68,6 +70,7 @@ struct DMesh {
 	// permutation (null when identity)
 	const int *new2old;
 	const int *old2new;
+	const int *send_idx;    ///< [nsend] own cells packed for the peers, grouped by peer rank
 };
 
 constexpr unsigned NB_NONE = 0xFFFFu;   ///< no such local face (4th slot of a triangle)
@@ -96,6 +99,8 @@ struct fvg_mesh {
 	std::vector<int> h_bentry;
 	std::vector<int> h_markers;                ///< sorted distinct boundary markers = slots of the BC table
 	std::vector<int> h_tcell0;
+	int nghost = 0, rank = 0, nranks = 1;
+	std::vector<int> send_counts, recv_counts, h_send_idx;
 };
 
 namespace fvg {
@@ -166,6 +171,7 @@ int launch_boundary_states(const DMesh &m, const GasParams &g, const double *ins
 int launch_cons2prim(const GasParams &g, const double *u, double *p, int n, cudaStream_t s);
 int launch_boundary_prim_ghosts(const DMesh &m, const GasParams &g, const double *u,
                                 double *ug, bool prim_out, cudaStream_t s);
+int launch_halo_pack(const DMesh &m, const double *src, int width, double *dst, cudaStream_t s);
 int launch_final_norm(const double *partial, int n, double *out, cudaStream_t s);
 int launch_surface_data(const DMesh &m, const GasParams &g, double aoa, const double *u, const double *grads,
                         int slot, double *out4, cudaStream_t s);

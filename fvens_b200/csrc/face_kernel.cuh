@@ -88,11 +88,7 @@ __device__ __forceinline__ void halo_side_state(const FaceArgs &A, const double 
 	const double2 rc = A.m.rc[g];
 	double ga[4], gb[4];
 	ld4(gsrc + 8*g, ga); ld4(gsrc + 8*g + 4, gb);
-	const double dx = gr.x - rc.x, dy = gr.y - rc.y;
-	pf[0] = pc[0] + ga[0]*dx + ga[1]*dy;
-	pf[1] = pc[1] + ga[2]*dx + ga[3]*dy;
-	pf[2] = pc[2] + gb[0]*dx + gb[1]*dy;
-	pf[3] = pc[3] + gb[2]*dx + gb[3]*dy;
+	extrapolate_prim(pc, ga, gb, gr.x, gr.y, rc.x, rc.y, pf);
 }
 
 /** One CTA per tile, three phases separated by two barriers:
@@ -184,11 +180,7 @@ face_kernel(const FaceArgs A)
 				double pf[4];
 				if(RECON == FR_LINEAR) {
 					const double2 gr = sgr[e];
-					const double dx = gr.x - rc.x, dy = gr.y - rc.y;
-					pf[0] = pc[0] + ga[0]*dx + ga[1]*dy;
-					pf[1] = pc[1] + ga[2]*dx + ga[3]*dy;
-					pf[2] = pc[2] + gb[0]*dx + gb[1]*dy;
-					pf[3] = pc[3] + gb[2]*dx + gb[3]*dy;
+					extrapolate_prim(pc, ga, gb, gr.x, gr.y, rc.x, rc.y, pf);
 				} else { for(int q = 0; q < 4; q++) pf[q] = pc[q]; }
 				double *const dst = ((cf[j] & 0x8000u) ? fsR : fsL) + 4*e;
 				*reinterpret_cast<double2*>(dst) = make_double2(pf[0], pf[1]);

@@ -84,10 +84,24 @@ __device__ __forceinline__ double fsqrt(double x) {
 __device__ __forceinline__ double pressure_cons(const GasParams &G, const double u[4]) {
 	return G.gm1*(u[3] - 0.5*(u[1]*u[1] + u[2]*u[2])/u[0]);
 }
+/// Written with explicit fma / non-contractable operations: the same cell is converted in different
+/// places (as a tile cell, as a halo cell of the neighbouring tile, as a ghost on another GPU) and all of
+/// them must produce the same bits, whatever the compiler would contract in each context.
 __device__ __forceinline__ void cons2prim(const GasParams &G, const double u[4], double p[4]) {
 	const double ir = frcp(u[0]);
-	const double pr = G.gm1*(u[3] - 0.5*(u[1]*u[1] + u[2]*u[2])*ir);
-	p[0] = u[0]; p[1] = u[1]*ir; p[2] = u[2]*ir; p[3] = pr;
+	const double m2 = fma(u[2], u[2], __dmul_rn(u[1], u[1]));
+	const double ie = fma(__dmul_rn(-0.5, m2), ir, u[3]);
+	p[0] = u[0]; p[1] = __dmul_rn(u[1], ir); p[2] = __dmul_rn(u[2], ir); p[3] = __dmul_rn(G.gm1, ie);
+}
+/// u_face = u_cell + g . (mid - centre) for the four primitive variables (reconstruction_utils.hpp:17-32),
+/// gradients in GradBlock order split in two rows of four; explicit fma order for the same reason as above
+__device__ __forceinline__ void extrapolate_prim(const double pc[4], const double ga[4], const double gb[4],
+                                                 double midx, double midy, double rcx, double rcy, double pf[4]) {
+	const double dx = __dsub_rn(midx, rcx), dy = __dsub_rn(midy, rcy);
+	pf[0] = fma(ga[1], dy, fma(ga[0], dx, pc[0]));
+	pf[1] = fma(ga[3], dy, fma(ga[2], dx, pc[1]));
+	pf[2] = fma(gb[1], dy, fma(gb[0], dx, pc[2]));
+	pf[3] = fma(gb[3], dy, fma(gb[2], dx, pc[3]));
 }
 __device__ __forceinline__ void prim2cons(const GasParams &G, const double p[4], double u[4]) {
 	const double e = p[3]*G.igm1 + 0.5*p[0]*(p[1]*p[1] + p[2]*p[2]);

@@ -423,6 +423,26 @@ int launch_permute_rows(const double *src, double *dst, const int *idx, int n, i
 	return 0;
 }
 
+/// sendbuf[k][:] = src[send_idx[k]][:]
+__global__ void halo_pack_kernel(const double *__restrict__ src, double *__restrict__ dst,
+                                 const int *__restrict__ idx, int n, int width)
+{
+	const long long k = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(k >= (long long)n*width) return;
+	const int i = (int)(k/width), c = (int)(k - (long long)i*width);
+	dst[k] = src[(size_t)idx[i]*width + c];
+}
+
+int launch_halo_pack(const DMesh &m, const double *src, int width, double *dst, cudaStream_t s)
+{
+	const long long tot = (long long)m.nsend*width;
+	if(tot == 0) return 0;
+	halo_pack_kernel<<<(unsigned)((tot + 255)/256), 256, 0, s>>>(src, dst, m.send_idx, m.nsend, width);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "halo_pack launch", __FILE__, __LINE__);
+	return 0;
+}
+
 __global__ void boundary_states_kernel(const DMesh M, const GasParams G,
                                        const double *__restrict__ ins, double *__restrict__ gs)
 {

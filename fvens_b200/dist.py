@@ -1,0 +1,125 @@
+"""Multi-GPU driver: one process per GPU, a subdomain device mesh per rank, ghost rows exchanged between
+the passes. Plumbing only (torch.distributed for the transport); every kernel is in libfvens_b200.so.
+
+Schedule per residual (reference: the three exchanges of SURVEY 2.1 reduced to two, ghost-cell based):
+  1. ghost rows of the state u          (after the update; the reference's VecGhostUpdate of u)
+  2. gradient/limiter pass on own cells
+  3. ghost rows of the limited gradients (+ unlimited ones for WENO / viscous-with-limiter)
+  4. face pass on own cells (cut faces evaluated identically on both ranks)
+The ghost block of a device-ordered array is ordered by source rank, and each rank packs the rows a peer
+needs in that peer's ghost order, so one all-to-all with row splits moves a whole exchange and the receive
+buffer IS the ghost block (no unpack kernel).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import lib
+
+
+class HaloExchange:
+    def __init__(self, dmesh, device, group=None):
+        self.dmesh = dmesh
+        self.group = group
+        self.device = device
+        sc, rc, idx = dmesh.halo_lists()
+        self.send_counts = [int(x) for x in sc]
+        self.recv_counts = [int(x) for x in rc]
+        self.send_idx_host = idx.copy()
+        self.nsend = int(sc.sum())
+        self.ncell, self.nghost = dmesh.ncell, dmesh.nghost
+        self._bufs = {}
+        self.on_gpu = torch.device(device).type == "cuda"
+        if not self.on_gpu:
+            self.send_idx_t = torch.from_numpy(idx.astype(np.int64))
+
+    def _sendbuf(self, width):
+        if width not in self._bufs:
+            self._bufs[width] = torch.empty((max(self.nsend, 1), width), dtype=torch.float64, device=self.device)
+        return self._bufs[width]
+
+    def exchange(self, arr):
+        """arr: [ncell+nghost, width] device-ordered; fills the ghost rows from their owners."""
+        width = arr.shape[1]
+        sb = self._sendbuf(width)
+        if self.on_gpu:
+            self.dmesh.halo_pack(arr, width, sb, stream=torch.cuda.current_stream().cuda_stream)
+        else:   # host-side test path (gloo): same pattern, numpy gather instead of the pack kernel
+            if self.nsend:
+                sb[:self.nsend] = arr[self.send_idx_t]
+        ghost = arr[self.ncell:]
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            try:
+                dist.all_to_all_single(ghost, sb[:self.nsend], self.recv_counts, self.send_counts, group=self.group)
+            except (RuntimeError, NotImplementedError):
+                self._exchange_p2p(ghost, sb)
+        else:
+            assert self.nghost == 0
+
+
+    def _exchange_p2p(self, ghost, sb):
+        ops, so, ro = [], 0, 0
+        rank = dist.get_rank(self.group)
+        for r in range(len(self.send_counts)):
+            if r != rank and self.send_counts[r]:
+                ops.append(dist.P2POp(dist.isend, sb[so:so+self.send_counts[r]], r, group=self.group))
+            if r != rank and self.recv_counts[r]:
+                ops.append(dist.P2POp(dist.irecv, ghost[ro:ro+self.recv_counts[r]], r, group=self.group))
+            so += self.send_counts[r]; ro += self.recv_counts[r]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class DistFlow:
+    """FlowFV on one rank's subdomain + the halo exchanges. Arrays are device-ordered [ncell+nghost, .]."""
+
+    def __init__(self, umesh, cell_rank, rank, nranks, phys, device, reorder="hilbert", tile_cells=256, group=None,
+                 **numerics):
+        self.dmesh = lib.DeviceMesh(umesh, reorder=reorder, tile_cells=tile_cells, device=torch.device(device).index or 0,
+                                    cell_rank=cell_rank, rank=rank, nranks=nranks)
+        self.flow = lib.FlowFV(self.dmesh, phys, **numerics)
+        self.halo = HaloExchange(self.dmesh, device, group)
+        self.ncell, self.nghost = self.dmesh.ncell, self.dmesh.nghost
+        n = self.ncell + self.nghost
+        num = self.flow.num
+        self.order2 = bool(num.order2)
+        self.weno = num.reconstruction == lib.RECON["WENO"]
+        limited = num.reconstruction in (lib.RECON["BARTHJESPERSEN"], lib.RECON["VENKATAKRISHNAN"])
+        self.need_lg = self.order2 and num.reconstruction != lib.RECON["VANALBADA"]
+        self.need_gu = self.order2 and (self.weno or num.reconstruction == lib.RECON["VANALBADA"] or
+                                        (phys.viscous_sim and limited))
+        self.lg = torch.zeros((n, 8), dtype=torch.float64, device=device) if self.need_lg else None
+        self.gu = torch.zeros((n, 8), dtype=torch.float64, device=device) if self.need_gu else None
+        if self.order2:
+            self.flow.use_buffers(self.lg, self.gu)
+        self.global_ids = self.dmesh.permutation()
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _gradients(self, u):
+        if not self.order2:
+            return
+        s = self._stream()
+        self.flow.gradient_pass(u, 0, stream=s)
+        if self.weno:
+            self.halo.exchange(self.gu)
+            self.flow.gradient_pass(u, 1, stream=s)
+        elif self.need_gu:
+            self.halo.exchange(self.gu)
+        if self.need_lg:
+            self.halo.exchange(self.lg)
+
+    def residual(self, u, res, dtm, gettimesteps=True, exchange_state=True):
+        """u [ncell+nghost,4]; res [ncell,4] (overwritten); dtm [ncell]."""
+        if exchange_state:
+            self.halo.exchange(u)
+        self._gradients(u)
+        self.flow.face_pass(u, res, gettimesteps, dtm, accumulate=False, stream=self._stream())
+
+    def euler_step(self, u, unew, cfl, norm2, exchange_state=True):
+        """One forward-Euler step: unew (own rows) from u; norm2 = this rank's sum of r_E^2*area (device scalar)."""
+        if exchange_state:
+            self.halo.exchange(u)
+        self._gradients(u)
+        self.flow.euler_face_pass(u, unew, cfl, norm2, stream=self._stream())

@@ -53,7 +53,8 @@ class MeshOpts(C.Structure):
 class MeshInfo(C.Structure):
     _fields_ = [("ncell", C.c_int), ("nbface", C.c_int), ("naface", C.c_int), ("ntile", C.c_int),
                 ("tile_cells", C.c_int), ("nstream", C.c_int), ("ncut_dup", C.c_int),
-                ("max_colours", C.c_int), ("reorder", C.c_int), ("mean_neighbour_distance", C.c_double)]
+                ("max_colours", C.c_int), ("reorder", C.c_int), ("mean_neighbour_distance", C.c_double),
+                ("nghost", C.c_int), ("nsend", C.c_int), ("rank", C.c_int), ("nranks", C.c_int)]
 
 
 class Physics(C.Structure):
@@ -204,21 +205,40 @@ class UMesh:
 
 
 class DeviceMesh:
-    def __init__(self, umesh, reorder="hilbert", tile_cells=0, device=-1):
+    """Device mesh of the whole host mesh, or (cell_rank given) of one rank's subdomain with its ghost layer."""
+
+    def __init__(self, umesh, reorder="hilbert", tile_cells=0, device=-1, cell_rank=None, rank=0, nranks=1):
         self.umesh = umesh
         opts = MeshOpts(REORDER[reorder] if isinstance(reorder, str) else int(reorder), tile_cells, device)
         h = C.c_void_p()
-        check(load().fvg_mesh_create(C.byref(umesh.view), C.byref(opts), C.byref(h)))
+        if cell_rank is None:
+            check(load().fvg_mesh_create(C.byref(umesh.view), C.byref(opts), C.byref(h)))
+        else:
+            cell_rank = np.ascontiguousarray(cell_rank, dtype=np.int32)
+            assert len(cell_rank) == umesh.nelem
+            check(load().fvg_mesh_create_part(C.byref(umesh.view), C.byref(opts), _ip(cell_rank), int(rank), int(nranks),
+                                              C.byref(h)))
         self._h = h
         info = MeshInfo()
         check(load().fvg_mesh_get_info(self._h, C.byref(info)))
         self.info = info
         self.ncell, self.nbface, self.naface = info.ncell, info.nbface, info.naface
+        self.nghost, self.nranks, self.rank = info.nghost, info.nranks, info.rank
 
     def permutation(self):
-        p = np.zeros(self.ncell, dtype=np.int32)
+        """Global (reference) cell id of every device row: own cells, then ghosts."""
+        p = np.zeros(self.ncell + self.nghost, dtype=np.int32)
         check(load().fvg_mesh_permutation(self._h, _ip(p)))
         return p
+
+    def halo_lists(self):
+        sc = np.zeros(self.nranks, dtype=np.int32); rc = np.zeros(self.nranks, dtype=np.int32)
+        idx = np.zeros(max(self.info.nsend, 1), dtype=np.int32)
+        check(load().fvg_mesh_halo_lists(self._h, _ip(sc), _ip(rc), _ip(idx)))
+        return sc, rc, idx[:self.info.nsend]
+
+    def halo_pack(self, src, width, sendbuf, stream=None):
+        check(load().fvg_halo_pack(self._h, _ptr(src), int(width), _ptr(sendbuf), C.c_void_p(stream or 0)))
 
     def tile_offsets(self):
         t = np.zeros(self.info.ntile+1, dtype=np.int32)
@@ -321,6 +341,22 @@ class FlowFV:
             check(code)
         return code, steps.value, hist[:steps.value].copy()
 
+    # split passes for multi-GPU drivers
+    def use_buffers(self, lg, gu):
+        self._bufs = (lg, gu)      # keep the tensors alive
+        check(load().fvg_flow_use_buffers(self._h, _ptr(lg), _ptr(gu)))
+
+    def gradient_pass(self, u, stage=0, stream=None):
+        check(load().fvg_gradient_pass(self._h, _ptr(u), int(stage), C.c_void_p(stream or 0)))
+
+    def face_pass(self, u, res, gettimesteps=True, dtm=None, accumulate=False, stream=None):
+        check(load().fvg_face_pass(self._h, _ptr(u), _ptr(res), int(accumulate), int(gettimesteps), _ptr(dtm),
+                                   C.c_void_p(stream or 0)))
+
+    def euler_face_pass(self, u, unew, cfl, resnorm2=None, stream=None):
+        check(load().fvg_euler_face_pass(self._h, _ptr(u), _ptr(unew), C.c_double(cfl), _ptr(resnorm2),
+                                         C.c_void_p(stream or 0)))
+
     def launch_count(self):
         c = C.c_longlong(0)
         check(load().fvg_flow_launch_count(self._h, C.byref(c)))
@@ -366,6 +402,13 @@ def freestream(phys):
     out = np.zeros(4)
     check(load().fvg_freestream(C.byref(phys), _dp(out)))
     return out
+
+
+def partition_sfc(umesh, nranks):
+    """cell -> rank map: the Hilbert order of the cells cut into nranks equal chunks."""
+    part = np.zeros(umesh.nelem, dtype=np.int32)
+    check(load().fvg_partition_sfc(umesh._h, int(nranks), _ip(part)))
+    return part
 
 
 def device_count():

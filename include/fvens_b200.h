@@ -98,12 +98,30 @@ typedef struct {
 typedef struct {
 	int ncell, nbface, naface, ntile, tile_cells, nstream, ncut_dup, max_colours, reorder;
 	double mean_neighbour_distance;   /* mean |i-j| over interior faces in device numbering */
+	int nghost, nsend, rank, nranks;  /* subdomain meshes: ghost cells, cells sent per exchange */
 } fvg_mesh_info;
 
 int fvg_mesh_create(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh **out);
+/* One subdomain of a mesh distributed over `nranks` GPUs (one process per GPU). Every rank passes the same
+ * GLOBAL host mesh and cell->rank map; the engine restricts it (the job of the reference's
+ * ReplicatedGlobalMeshPartitioner::restrictMeshToPartitions, mesh/meshpartitioning.cpp:24-159): own cells,
+ * one ghost cell per cell across a cut face, faces. Arrays of such a mesh are in DEVICE order: rows
+ * [0, ncell) are the own cells, rows [ncell, ncell+nghost) the ghosts grouped by owner rank (see
+ * fvg_mesh_permutation for the global ids and fvg_mesh_halo_lists for the exchange pattern). */
+int fvg_mesh_create_part(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *cell_rank, int rank,
+                         int nranks, fvg_mesh **out);
+/* Space-filling-curve partition: the Hilbert order of the cells cut into nranks equal chunks (the stand-in
+ * for the Scotch partition of mesh/meshpartitioning.cpp:432-480; Scotch is not available offline). */
+int fvg_partition_sfc(const fvg_umesh *m, int nranks, int *cell_rank);
 void fvg_mesh_destroy(fvg_mesh *m);
+/* Halo pattern of a subdomain mesh: send_counts[r] own cells go to rank r, recv_counts[r] ghost rows come
+ * from rank r (ghost rows are ordered by source rank, so a recv buffer IS the ghost block); send_idx
+ * (may be NULL) lists the own device cells to pack, grouped by destination rank. */
+int fvg_mesh_halo_lists(const fvg_mesh *m, int *send_counts, int *recv_counts, int *send_idx);
+/* Packs rows of a device-ordered array for the peers: sendbuf[k][:] = src[send_idx[k]][:] (width doubles). */
+int fvg_halo_pack(const fvg_mesh *m, const double *d_src, int width, double *d_sendbuf, void *stream);
 int fvg_mesh_get_info(const fvg_mesh *m, fvg_mesh_info *info);
-/* cell_new2old[ncell]: device cell i holds reference cell cell_new2old[i]. */
+/* cell_new2old[ncell + nghost]: device cell i holds reference (global) cell cell_new2old[i]. */
 int fvg_mesh_permutation(const fvg_mesh *m, int *cell_new2old);
 /* tile_cell0[ntile+1]: device cells [tile_cell0[t], tile_cell0[t+1]) are tile t's own cells. */
 int fvg_mesh_tile_offsets(const fvg_mesh *m, int *tile_cell0);
@@ -162,6 +180,24 @@ int fvg_residual(fvg_flow *f, const double *d_u, double *d_res, int accumulate, 
  * Pinned host memory makes the copies run at full PCIe rate but is not required. */
 int fvg_residual_host(fvg_flow *f, const double *h_u, double *h_res, int accumulate, int gettimesteps,
                       double *h_dtm);
+
+/* The two passes of fvg_residual as separate calls, so that a multi-GPU driver can exchange ghost rows in
+ * between (the reference's gradient halo, spatial/flow_spatial.cpp:711-729, and trace exchange :738,:782):
+ *   fvg_gradient_pass(stage 0)  -> limited gradients of the own cells in the flow's d_lg buffer
+ *                                  (WENO: unlimited gradients in d_gu; exchange them, then stage 1 -> d_lg)
+ *   [exchange the ghost rows of d_lg (and d_gu for viscous runs with a limiter)]
+ *   fvg_face_pass / fvg_euler_face_pass
+ * The state must be device-ordered with valid ghost rows. fvg_flow_buffers returns the gradient buffers
+ * ([ncell+nghost][8] each; NULL if the numerics do not use one). */
+int fvg_gradient_pass(fvg_flow *f, const double *d_u, int stage, void *stream);
+int fvg_face_pass(fvg_flow *f, const double *d_u, double *d_res, int accumulate, int gettimesteps,
+                  double *d_dtm, void *stream);
+int fvg_euler_face_pass(fvg_flow *f, const double *d_u, double *d_unew, double cfl, double *d_resnorm2,
+                        void *stream);
+int fvg_flow_buffers(fvg_flow *f, double **d_lg, double **d_gu);
+/* Makes the flow use caller-owned gradient buffers ([ncell+nghost][8] doubles each, device memory that must
+ * outlive the flow's use of them), e.g. tensors that a communication library can address. */
+int fvg_flow_use_buffers(fvg_flow *f, double *d_lg, double *d_gu);
 
 /* GradientScheme::compute_gradients (spatial/agradientschemes.hpp:44-48) on primitive cell states */
 int fvg_gradients(fvg_flow *f, const double *d_uprim, const double *d_ug, double *d_grad, void *stream);

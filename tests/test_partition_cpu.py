@@ -1,0 +1,109 @@
+"""Host-side logic of the multi-GPU path, without a GPU: the subdomain builder (own cells, one ghost layer,
+send/receive lists) and the exchange pattern over a real 2-process gloo group - the analogue of the
+reference's tests/solvers/testtracevector.cpp (every ghost must receive a value made of its owner's rank and
+the global cell id)."""
+import os
+import sys
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from common import mesh_path
+from fvens_b200 import lib, synth
+
+
+def build_parts(um, nranks, reorder="hilbert", tile=64):
+    part = lib.partition_sfc(um, nranks)
+    return part, [lib.DeviceMesh(um, reorder=reorder, tile_cells=tile, device=-2, cell_rank=part, rank=r, nranks=nranks)
+                  for r in range(nranks)]
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+@pytest.mark.parametrize("mesh", ["2dcylinderhybrid.msh", "bump"])
+def test_subdomains_are_consistent(mesh, nranks):
+    um = lib.UMesh.from_arrays(*synth.bump_channel(40, 15)) if mesh == "bump" else lib.UMesh.read(mesh_path(mesh))
+    a = um.arrays()
+    part, dms = build_parts(um, nranks)
+    assert np.bincount(part, minlength=nranks).min() >= um.nelem//nranks - 1      # balanced
+    owned = np.concatenate([dm.permutation()[:dm.ncell] for dm in dms])
+    assert sorted(owned.tolist()) == list(range(um.nelem))                        # every cell owned exactly once
+    nb = um.nbface
+    for r, dm in enumerate(dms):
+        ids = dm.permutation()
+        own, ghost = ids[:dm.ncell], ids[dm.ncell:]
+        assert (part[own] == r).all() and (part[ghost] != r).all()
+        # ghosts = exactly the cells of other ranks across a face of an own cell
+        expect = set()
+        ownset = set(own.tolist())
+        for L, R in a["intfac"][nb:, :2]:
+            if (L in ownset) != (R in ownset):
+                expect.add(int(R if L in ownset else L))
+        assert set(ghost.tolist()) == expect and len(ghost) == len(expect)
+        # ghosts grouped by owner rank, ascending
+        assert (np.diff(part[ghost]) >= 0).all()
+        sc, rc, idx = dm.halo_lists()
+        assert rc.sum() == dm.nghost and np.array_equal(rc, np.bincount(part[ghost], minlength=nranks))
+        assert sc[r] == 0 and rc[r] == 0 and (idx < dm.ncell).all()
+    # what rank s sends to rank r is, in order, rank r's ghost block from s
+    for r, dr in enumerate(dms):
+        gr = dr.permutation()[dr.ncell:]
+        _, rc, _ = dr.halo_lists()
+        off = np.concatenate(([0], np.cumsum(rc)))
+        for s, ds in enumerate(dms):
+            sc, _, idx = ds.halo_lists()
+            so = np.concatenate(([0], np.cumsum(sc)))
+            sent = ds.permutation()[idx[so[r]:so[r+1]]]
+            assert np.array_equal(sent, gr[off[s]:off[s+1]])
+    # every face of the mesh is evaluated by the ranks owning its cells, and by no one else
+    for r, dm in enumerate(dms):
+        face, _, _ = dm.stream()
+        faces = set(face[face >= 0].tolist())
+        ownset = set(dm.permutation()[:dm.ncell].tolist())
+        expect = {f for f in range(um.naface) if a["intfac"][f, 0] in ownset or (f >= nb and a["intfac"][f, 1] in ownset)}
+        assert faces == expect
+
+
+def _worker(rank, world, port, meshname, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fvens_b200 import lib as L, synth as S
+        from fvens_b200.dist import HaloExchange
+        um = L.UMesh.from_arrays(*S.bump_channel(40, 15))
+        part = L.partition_sfc(um, world)
+        dm = L.DeviceMesh(um, reorder="hilbert", tile_cells=64, device=-2, cell_rank=part, rank=rank, nranks=world)
+        ids = dm.permutation()
+        hx = HaloExchange(dm, "cpu")
+        arr = torch.zeros((dm.ncell + dm.nghost, 4), dtype=torch.float64)
+        own = torch.from_numpy(ids[:dm.ncell].astype(np.float64))
+        for v in range(4):
+            arr[:dm.ncell, v] = rank*1.0e7 + own*10 + v
+        hx.exchange(arr)
+        g = ids[dm.ncell:]
+        expect = np.stack([part[g]*1.0e7 + g*10 + v for v in range(4)], axis=1)
+        ok = bool(np.array_equal(arr[dm.ncell:].numpy(), expect)) and dm.nghost > 0
+        # a 1-double all-reduce like the residual norm
+        t = torch.tensor([float(dm.ncell)], dtype=torch.float64)
+        dist.all_reduce(t)
+        ok = ok and int(t.item()) == um.nelem
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, "bump", q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    results = dict(q.get(timeout=5) for _ in range(world))
+    assert all(p.exitcode == 0 for p in procs)
+    assert results == {r: True for r in range(world)}
