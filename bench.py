@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=float, default=10.0e6)
     ap.add_argument("--numerics", default="roe-wls-venkat", choices=list(NUMERICS))
-    ap.add_argument("--tile", type=int, default=512)
+    ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--cpu-cells", type=float, default=1.0e6, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)

@@ -133,6 +133,39 @@ using namespace fvg;
 
 extern "C" {
 
+// ------------------------------------------------------------------------------------ device memory
+
+int fvg_malloc(void **d_ptr, unsigned long long bytes)
+{
+	if(!d_ptr) { set_error("fvg_malloc: null argument"); return FVG_ERR_INVALID; }
+	*d_ptr = nullptr;
+	FVG_CUDA(cudaMalloc(d_ptr, std::max<size_t>((size_t)bytes, 8)));
+	return 0;
+}
+
+int fvg_free(void *d_ptr)
+{
+	if(d_ptr) FVG_CUDA(cudaFree(d_ptr));
+	return 0;
+}
+
+int fvg_memcpy(void *dst, const void *src, unsigned long long bytes, int kind)
+{
+	if(bytes == 0) return 0;
+	if(!dst || !src || kind < 0 || kind > 2) { set_error("fvg_memcpy: bad argument"); return FVG_ERR_INVALID; }
+	const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+	FVG_CUDA(cudaMemcpy(dst, src, (size_t)bytes, k));
+	return 0;
+}
+
+int fvg_memset(void *d_ptr, int value, unsigned long long bytes)
+{
+	if(bytes == 0) return 0;
+	if(!d_ptr) { set_error("fvg_memset: null argument"); return FVG_ERR_INVALID; }
+	FVG_CUDA(cudaMemset(d_ptr, value, (size_t)bytes));
+	return 0;
+}
+
 // ------------------------------------------------------------------------------------ host mesh
 
 static int finish_umesh(std::unique_ptr<fvg_umesh> &h, fvg_umesh **out)

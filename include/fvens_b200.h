@@ -39,6 +39,15 @@ const char *fvg_last_error(void);
 /* Number of visible CUDA devices; fails (FVG_ERR_CUDA) when there is no usable GPU. */
 int fvg_device_count(int *count);
 
+/* Device memory for host code that does not link the CUDA runtime itself (the C++ class surface in
+ * fvens_b200/host/ holds its device-resident Vecs through these; the reference's counterpart is PETSc's
+ * VecCreate / VecGetArray / VecDestroy, linalg/alinalg.cpp:9-52, linalg/petscutils.hpp). kind: 0 = host to
+ * device, 1 = device to host, 2 = device to device. Copies are synchronous. */
+int fvg_malloc(void **d_ptr, unsigned long long bytes);
+int fvg_free(void *d_ptr);
+int fvg_memcpy(void *dst, const void *src, unsigned long long bytes, int kind);
+int fvg_memset(void *d_ptr, int value, unsigned long long bytes);
+
 /* ------------------------------------------------------------------------------------------------
  * Host mesh = fvens::UMesh<double,2> (mesh/mesh.hpp:25-500) built by constructMesh + preprocessMesh
  * (mesh/ameshutils.cpp:39-153): read -> correctBoundaryFaceOrientation -> compute_topological ->
