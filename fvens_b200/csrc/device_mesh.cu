@@ -233,19 +233,20 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 			const int t = (int)tcell0.size() - 1;
 			for(int attempt = 0; ; attempt++) {
 				halo.clear();
-				int E = 0;
+				int E = 0, nbnd = 0;
 				const int tag = t*64 + (attempt & 63);      // unique stamp per (tile, attempt)
 				for(int i = s; i < s+nc; i++) {
 					const int nn = hm->nnode[d2g[i]];
 					for(int j = 0; j < nn; j++) {
 						const int q = nbr_of(i, j);
-						if(q < 0) { E++; continue; }
+						if(q < 0) { E++; nbnd++; continue; }
 						if(q >= s && q < s+nc) { if(i < q) E++; continue; }
 						E++;
 						if(stamp[q] != tag) { stamp[q] = tag; halo.push_back(q); }
 					}
 				}
-				if(((int)halo.size() <= HMAX && E <= EMAX) || nc == 1) break;
+				// boundary ghost cells are staged like halo cells, so they share the row capacity
+				if(((int)halo.size() + nbnd <= HMAX && E <= EMAX) || nc == 1) break;
 				nc = std::max(1, std::min(nc - 1, (int)(nc*0.8)));
 			}
 			if((int)halo.size() > HMAX) { set_error("fvg_mesh_create: a single cell exceeds the halo capacity"); return FVG_ERR_INVALID; }
@@ -260,7 +261,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	std::vector<int> tile_of((size_t)ntot, -1);
 	for(int t = 0; t < ntile; t++) for(int i = tcell0[t]; i < tcell0[t+1]; i++) tile_of[i] = t;
 
-	// ---- face streams: count (padded to 4), fill in reference face order, colour, sort by colour
+	// ---- face streams: count (padded to 4), fill in reference face order, colour, sort by kind
 	std::vector<int> fsoff((size_t)ntile+1, 0);
 	int ninterior = 0;
 	for(int f : rfaces) {
@@ -289,8 +290,13 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 			} else sface[pos[tR]++] = f;                 // left cell is a ghost: the right cell's tile holds the only copy
 		}
 	}
-	std::vector<int> fcoloff((size_t)ntile*(MAXCOL+1), 0);
+	// Greedy edge colouring per tile (kept as metadata: fvg_mesh_stream exposes it and a test checks that no two
+	// entries of one colour touch the same tile cell). The kernels gather per cell and do not need the colours,
+	// so the stream is ordered by KIND instead: faces with both cells in the tile, then faces cut by the tile
+	// boundary (one side is a halo cell), then physical-boundary faces, then padding. Warps of the flux phase
+	// are then uniform in kind; reference face order is kept inside a kind.
 	std::vector<int> scolour((size_t)ns, MAXCOL-1);
+	std::vector<int2> tbnd((size_t)ntile);      // tile-local index of the first boundary entry, number of boundary entries
 	m->max_colours = 0;
 	{
 		std::vector<unsigned char> used(TC);
@@ -298,9 +304,17 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 		for(int t = 0; t < ntile; t++) {
 			const int c0 = tcell0[t], e0 = fsoff[t], e1 = fsoff[t+1];
 			std::fill(used.begin(), used.end(), 0);
-			int cnt[MAXCOL] = {0};
+			int cnt[4] = {0, 0, 0, 0};
+			auto kind_of = [&](int sf) {
+				if(sf == PAD) return 3;
+				const int f = sf >= 0 ? sf : -1-sf;
+				const int L = faceL(f), R = faceR(f);
+				if(R < 0) return 2;
+				return (tile_of[L] == t && tile_of[R] == t) ? 0 : 1;
+			};
 			for(int e = e0; e < e1; e++) {
-				if(sface[e] == PAD) { scolour[e] = MAXCOL-1; cnt[MAXCOL-1]++; continue; }   // padding sorts last
+				cnt[kind_of(sface[e])]++;
+				if(sface[e] == PAD) continue;
 				const int f = sface[e] >= 0 ? sface[e] : -1-sface[e];
 				const int L = faceL(f), R = faceR(f);
 				unsigned mask = 0;
@@ -311,17 +325,15 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 				if(c >= MAXCOL) { set_error("fvg_mesh_create: edge colouring needs more than 8 colours"); return FVG_ERR_INVALID; }
 				if(tile_of[L] == t) used[L-c0] |= (unsigned char)(1u << c);
 				if(R >= 0 && tile_of[R] == t) used[R-c0] |= (unsigned char)(1u << c);
-				scolour[e] = c; cnt[c]++;
+				scolour[e] = c;
 				m->max_colours = std::max(m->max_colours, c+1);
 			}
-			int *co = &fcoloff[(size_t)t*(MAXCOL+1)];
-			co[0] = e0;
-			for(int c = 0; c < MAXCOL; c++) co[c+1] = co[c] + cnt[c];
+			tbnd[t] = make_int2(cnt[0] + cnt[1], cnt[2]);
 			tmp.assign(sface.begin()+e0, sface.begin()+e1);
 			ctmp.assign(scolour.begin()+e0, scolour.begin()+e1);
-			int pos[MAXCOL];
-			for(int c = 0; c < MAXCOL; c++) pos[c] = co[c];
-			for(int k = 0; k < e1-e0; k++) { const int c = ctmp[k]; sface[pos[c]] = tmp[k]; scolour[pos[c]] = c; pos[c]++; }
+			int pos[4];
+			pos[0] = e0; pos[1] = pos[0] + cnt[0]; pos[2] = pos[1] + cnt[1]; pos[3] = pos[2] + cnt[2];
+			for(int k = 0; k < e1-e0; k++) { const int q = kind_of(tmp[k]); sface[pos[q]] = tmp[k]; scolour[pos[q]] = ctmp[k]; pos[q]++; }
 		}
 	}
 
@@ -448,7 +460,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 #define UP(vec, field) if((rcode = upload(m, vec, &D.field)) != 0) return rcode;
 	UP(cloc, cloc) UP(drc, rc) UP(area, area) UP(V, wlsV) UP(clength, clength)
 	UP(tcell0, tcell0) UP(thoff, thoff) UP(thalo, thalo)
-	UP(fsoff, fsoff) UP(fcoloff, fcoloff) UP(fLR, fLR) UP(fn, fn) UP(flen, flen) UP(fgr, fgr)
+	UP(fsoff, fsoff) UP(tbnd, tbnd) UP(fLR, fLR) UP(fn, fn) UP(flen, flen) UP(fgr, fgr)
 	UP(m->h_fref, fref) UP(bcell, bcell) UP(m->h_bentry, bentry) UP(bslot, bslot) UP(rcbp, rcbp)
 	UP(m->h_send_idx, send_idx)
 	if(m->identity_perm) { D.new2old = nullptr; D.old2new = nullptr; }

@@ -37,7 +37,8 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 /// out-of-tile neighbour cells = the tile's HALO, at most EMAX faces). Inside a tile everything is
 /// addressed with 16-bit LOCAL indices: own cell k -> k, halo cell h -> ncell_of_tile + h. Each tile
 /// has a contiguous FACE STREAM segment (every face touching one of its own cells; a face cut by a
-/// tile boundary has a copy in both tiles), sorted by colour, start and length padded to 4 entries.
+/// tile boundary has a copy in both tiles), ordered by kind (both cells in the tile / cut by the tile
+/// boundary / physical boundary / padding), start and length padded to 4 entries.
 struct DMesh {
 	int ncell;              ///< own cells (tiles, residual rows); state-like arrays have ncell + nghost rows
 	int nghost, nsend;      ///< ghost cells received from / own cells sent to other ranks per exchange
@@ -54,7 +55,7 @@ struct DMesh {
 	const int *thoff;       ///< [ntile+1] offsets into thalo
 	const int *thalo;       ///< halo cell ids (device numbering), ascending within a tile
 	const int *fsoff;       ///< [ntile+1] stream segment of each tile (multiples of 4)
-	const int *fcoloff;     ///< [ntile][MAXCOL+1] colour boundaries inside the segment (absolute entry ids)
+	const int2 *tbnd;       ///< [ntile] x: tile-local index of the first physical-boundary entry, y: how many (halo + these <= HMAX)
 	// per stream entry
 	const unsigned *fLR;    ///< local left | local right << 16; right >= LR_BND: boundary face with BC table index (right & 15);
 	                        ///< LR_PAD: padding entry

@@ -59,35 +59,38 @@ __device__ __forceinline__ double muscl_term(double delta, double dlr) {
 	return phi*0.25*((1.0 - k*phi)*delta + (1.0 + k*phi)*dlr);
 }
 
-/// Shared-memory carve-up of the face kernel for the given capacity (host and device agree through this)
+/// Shared-memory carve-up of the face kernel for the given capacities (host and device agree through this).
+/// Per stream entry: the two face-state slots (later the flux and the spectral radii) and the midpoint;
+/// per halo cell: its state, reconstruction gradient and centre, gathered asynchronously while phase A runs.
 struct FaceSmem {
-	int fsL, fsR, sn, sgr, slen, sLR, bar, total;   // byte offsets
-	__host__ __device__ FaceSmem(int EMAX, bool mids) {
+	int fsL, fsR, sgr, hu, hg, hrc, bar, total;   // byte offsets
+	__host__ __device__ FaceSmem(int EMAX, int HMAX, bool mids) {
 		int o = 0;
 		fsL = o; o += EMAX*32;
 		fsR = o; o += EMAX*32;
-		sn = o; o += EMAX*16;
 		sgr = o; o += mids ? EMAX*16 : 0;
-		slen = o; o += EMAX*8;
-		sLR = o; o += EMAX*4;
+		hu = o; o += HMAX*32;
+		hg = o; o += mids ? HMAX*64 : 0;
+		hrc = o; o += mids ? HMAX*16 : 0;
 		bar = o; o += 8;
 		total = o;
 	}
 };
 
-/// primitive face state of one side whose cell is NOT a tile cell (halo): gathered from global memory
+/// primitive face state of one side whose cell is NOT a tile cell (halo cell h): from the staged halo rows
 template <int RECON>
-__device__ __forceinline__ void halo_side_state(const FaceArgs &A, const double *gsrc, size_t g, double2 gr, double pf[4])
+__device__ __forceinline__ void halo_side_state(const FaceArgs &A, const double *hu, const double *hg, const double2 *hrc,
+                                                int h, double2 gr, double pf[4])
 {
 	double uc[4];
-	ld4(A.u + 4*g, uc);
+	lds4(hu + 4*h, uc);
 	if(RECON == FR_FIRST) { for(int k = 0; k < 4; k++) pf[k] = uc[k]; return; }
 	double pc[4];
 	cons2prim(A.gas, uc, pc);
 	if(RECON == FR_MUSCL) { for(int k = 0; k < 4; k++) pf[k] = pc[k]; return; }
-	const double2 rc = A.m.rc[g];
+	const double2 rc = hrc[h];
 	double ga[4], gb[4];
-	ld4(gsrc + 8*g, ga); ld4(gsrc + 8*g + 4, gb);
+	lds4(hg + 8*h, ga); lds4(hg + 8*h + 4, gb);
 	extrapolate_prim(pc, ga, gb, gr.x, gr.y, rc.x, rc.y, pf);
 }
 
@@ -110,31 +113,41 @@ face_kernel(const FaceArgs A)
 	extern __shared__ __align__(128) unsigned char smraw[];
 	const DMesh &M = A.m;
 	constexpr bool MIDS = RECON != FR_FIRST;
-	const FaceSmem S(M.EMAX, MIDS);
+	const FaceSmem S(M.EMAX, M.HMAX, MIDS);
 	double *const fsL = reinterpret_cast<double*>(smraw + S.fsL);
 	double *const fsR = reinterpret_cast<double*>(smraw + S.fsR);
-	double2 *const sn = reinterpret_cast<double2*>(smraw + S.sn);
 	double2 *const sgr = reinterpret_cast<double2*>(smraw + S.sgr);
-	double *const slen = reinterpret_cast<double*>(smraw + S.slen);
-	unsigned *const sLR = reinterpret_cast<unsigned*>(smraw + S.sLR);
+	double *const hu = reinterpret_cast<double*>(smraw + S.hu);
+	double *const hg = reinterpret_cast<double*>(smraw + S.hg);
+	double2 *const hrc = reinterpret_cast<double2*>(smraw + S.hrc);
 	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);
 	__shared__ double red_s[FACE_BLOCK/32];
 
 	const int t = blockIdx.x, tid = threadIdx.x;
 	const int c0 = M.tcell0[t], nc = M.tcell0[t+1] - c0;
-	const int h0 = M.thoff[t];
+	const int h0 = M.thoff[t], nh = M.thoff[t+1] - h0;
 	const int e0 = M.fsoff[t], ne = M.fsoff[t+1] - e0;
 	const double *const gsrc = RECON == FR_MUSCL ? A.gu : A.lg;     // gradients used by the reconstruction
 
-	// ---- entry metadata by TMA
-	if(tid == 0) mbar_init(bar, 1);
-	__syncthreads();
-	if(tid == 0) {
-		mbar_expect_tx(bar, (unsigned)ne*(16u + 8u + 4u + (MIDS ? 16u : 0u)));
-		bulk_g2s(sLR, M.fLR + e0, (unsigned)ne*4u, bar);
-		bulk_g2s(sn, M.fn + e0, (unsigned)ne*16u, bar);
-		bulk_g2s(slen, M.flen + e0, (unsigned)ne*8u, bar);
-		if(MIDS) bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
+	// ---- face midpoints by TMA; halo rows by 16-byte async gathers (consumed in phase B only)
+	if(MIDS) {
+		if(tid == 0) mbar_init(bar, 1);
+		__syncthreads();
+		if(tid == 0) {
+			mbar_expect_tx(bar, (unsigned)ne*16u);
+			bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
+		}
+	}
+	{
+		constexpr int PIECES = MIDS ? 7 : 2;      // 16-byte pieces per halo cell: 2 of u [+ 4 of the gradient + the centre]
+		for(int k = tid; k < nh*PIECES; k += FACE_BLOCK) {
+			const int h = k/PIECES, piece = k - PIECES*h;
+			const size_t g = (size_t)M.thalo[h0 + h];
+			if(piece < 2) cp_async16(hu + 4*h + 2*piece, A.u + 4*g + 2*piece);
+			else if(piece < 6) cp_async16(hg + 8*h + 2*(piece-2), gsrc + 8*g + 2*(piece-2));
+			else cp_async16(hrc + h, M.rc + g);
+		}
+		cp_async_commit();
 	}
 	if(tid == 32 && A.prefetch_distance > 0 && t + A.prefetch_distance < M.ntile) {
 		// warm L2 with the operands of the tile that runs about one wave of CTAs later
@@ -150,6 +163,11 @@ face_kernel(const FaceArgs A)
 		if(MIDS) bulk_prefetch_l2(M.fgr + pe0, (unsigned)pne*16u);
 		bulk_prefetch_l2(M.area + (pc0 & ~1), (unsigned)((pnc + 3) & ~1)*8u);
 	}
+	// entry metadata of this thread's first flux round, in flight during phase A
+	unsigned LRn = LR_PAD;
+	double2 nrmn = make_double2(1.0, 0.0);
+	double lenn = 0.0;
+	if(tid < ne) { LRn = M.fLR[e0 + tid]; nrmn = M.fn[e0 + tid]; lenn = M.flen[e0 + tid]; }
 
 	// ---- phase A: face states of the own cells
 	uint4 cl0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);     // metadata of cell `tid`, kept for phase C
@@ -166,7 +184,7 @@ face_kernel(const FaceArgs A)
 			ld4(A.u + 4*i, uc);
 			if(RECON == FR_LINEAR) { ld4(gsrc + 8*i, ga); ld4(gsrc + 8*i + 4, gb); rc = M.rc[i]; }
 		}
-		if(k0 == 0) { cl0 = cl; mbar_wait(bar, 0); }     // midpoints needed from here on
+		if(k0 == 0) { cl0 = cl; if(MIDS) mbar_wait(bar, 0); }     // midpoints needed from here on
 		if(k < nc) {
 			double pc[4];
 			if(RECON == FR_FIRST) { for(int q = 0; q < 4; q++) pc[q] = uc[q]; }
@@ -188,24 +206,26 @@ face_kernel(const FaceArgs A)
 			}
 		}
 	}
+	cp_async_wait_all();
 	__syncthreads();
 
-	// ---- phase B: fluxes, one stream entry per thread and round
+	// ---- phase B: fluxes, one stream entry per thread and round; the next round's metadata is loaded first
 	for(int e = tid; e < ne; e += FACE_BLOCK) {
-		const unsigned LR = sLR[e];
+		const unsigned LR = LRn;
+		const double2 nrm = nrmn;
+		const double len = lenn;
+		if(e + FACE_BLOCK < ne) { LRn = M.fLR[e0 + e + FACE_BLOCK]; nrmn = M.fn[e0 + e + FACE_BLOCK]; lenn = M.flen[e0 + e + FACE_BLOCK]; }
 		if(LR == LR_PAD) continue;
 		const unsigned L = LR & 0xFFFFu, Rf = LR >> 16;
 		const bool bnd = Rf >= LR_BND;
-		const double2 nrm = sn[e];
-		const double len = slen[e];
 		const double nx = nrm.x, ny = nrm.y;
 		const BCEntry &bc = A.gas.bc[Rf & 15u];
 		double sl[4], sr[4];       // face states: conserved (first order) / primitive; MUSCL: cell states
 		if(L < (unsigned)nc) lds4(fsL + 4*e, sl);
-		else halo_side_state<RECON>(A, gsrc, (size_t)M.thalo[h0 + (int)L - nc], MIDS ? sgr[e] : make_double2(0,0), sl);
+		else halo_side_state<RECON>(A, hu, hg, hrc, (int)L - nc, MIDS ? sgr[e] : make_double2(0,0), sl);
 		if(!bnd) {
 			if(Rf < (unsigned)nc) lds4(fsR + 4*e, sr);
-			else halo_side_state<RECON>(A, gsrc, (size_t)M.thalo[h0 + (int)Rf - nc], MIDS ? sgr[e] : make_double2(0,0), sr);
+			else halo_side_state<RECON>(A, hu, hg, hrc, (int)Rf - nc, MIDS ? sgr[e] : make_double2(0,0), sr);
 		}
 		const int gidL = (VISC != VISC_NONE || RECON == FR_MUSCL) ? tile_global(M, t, c0, nc, L) : 0;
 		const int gidR = (VISC != VISC_NONE || RECON == FR_MUSCL) ? (bnd ? gidL : tile_global(M, t, c0, nc, Rf)) : 0;
@@ -362,7 +382,7 @@ face_kernel(const FaceArgs A)
 template <int FLUX, int RECON, int VISC>
 static int launch_one(const FaceArgs &a, cudaStream_t s)
 {
-	const FaceSmem S(a.m.EMAX, RECON != FR_FIRST);
+	const FaceSmem S(a.m.EMAX, a.m.HMAX, RECON != FR_FIRST);
 	const size_t smem = (size_t)S.total;
 	if(smem > 48*1024) {
 		const cudaError_t ea = cudaFuncSetAttribute(face_kernel<FLUX,RECON,VISC>,

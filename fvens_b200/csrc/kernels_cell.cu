@@ -100,17 +100,44 @@ cell_kernel(const CellArgs A)
 		cl = M.cloc[c0 + tid];
 		if(GRAD == GM_WLS) V = M.wlsV[c0 + tid];
 	}
+	const int2 tb = M.tbnd[t];                 // boundary entries of the tile: first (tile-local) and count
+	const int grow0 = nc + nh;                 // their ghost cells are staged as rows grow0 .. grow0 + tb.y - 1
 	cp_async_wait_all();
 	mbar_wait(bar, 0);
 	__syncthreads();
-	if(!PRIM_IN) {
-		const int nrows = NEED_NBRS ? nc + nh : nc;
+	{
+		// one pass over the staged rows: cell and halo states become primitive in place; the ghost cell of every
+		// physical-boundary face gets its own row (state from the boundary condition applied to the conserved
+		// state of the adjacent cell, flow_spatial.cpp:659-695; centre mirrored about the face midpoint,
+		// aspatial.cpp:98-119), so that the stencil loop below needs no boundary branch at all
+		const int nrows = NEED_NBRS ? grow0 + tb.y : nc;
 		for(int k = tid; k < nrows; k += CELL_BLOCK) {
-			double uc[4], up[4];
-			lds4(sp + 4*k, uc);
-			cons2prim(A.gas, uc, up);
-			*reinterpret_cast<double2*>(sp + 4*k) = make_double2(up[0], up[1]);
-			*reinterpret_cast<double2*>(sp + 4*k + 2) = make_double2(up[2], up[3]);
+			if(k < grow0) {
+				if(PRIM_IN) continue;
+				double uc[4], up[4];
+				lds4(sp + 4*k, uc);
+				cons2prim(A.gas, uc, up);
+				*reinterpret_cast<double2*>(sp + 4*k) = make_double2(up[0], up[1]);
+				*reinterpret_cast<double2*>(sp + 4*k + 2) = make_double2(up[2], up[3]);
+			} else {
+				const int ge = e0 + tb.x + (k - grow0);
+				const unsigned LR = M.fLR[ge];
+				const int L = (int)(LR & 0xFFFFu);
+				double pj[4];
+				if(PRIM_IN) ld4(A.ug + 4*(size_t)M.fref[ge], pj);
+				else {
+					const double2 n = M.fn[ge];
+					double ui[4], gs[4];
+					ld4(A.u + 4*(size_t)(c0 + L), ui);
+					ghost_state(A.gas, A.gas.bc[(LR >> 16) & 15u], ui, n.x, n.y, gs);
+					cons2prim(A.gas, gs, pj);
+				}
+				const double2 mid = M.fgr[ge];
+				const double2 rl = M.rc[c0 + L];
+				*reinterpret_cast<double2*>(sp + 4*k) = make_double2(pj[0], pj[1]);
+				*reinterpret_cast<double2*>(sp + 4*k + 2) = make_double2(pj[2], pj[3]);
+				src[k] = make_double2(2.0*mid.x - rl.x, 2.0*mid.y - rl.y);
+			}
 		}
 		__syncthreads();
 	}
@@ -121,8 +148,9 @@ cell_kernel(const CellArgs A)
 			cl = M.cloc[i];
 			if(GRAD == GM_WLS) V = M.wlsV[i];
 		}
-		const unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
+		unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
 		const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
+		const bool quad = nb[3] != NB_NONE;       // only the fourth slot can be empty (triangles)
 		const double2 rci = src[k];
 		double pi[4];
 		lds4(sp + 4*k, pi);
@@ -134,29 +162,13 @@ cell_kernel(const CellArgs A)
 		if(NEED_NBRS) {
 			#pragma unroll
 			for(int j = 0; j < 4; j++) {
-				const unsigned nj = nb[j];
-				if(j == 3 && nj == NB_NONE) break;      // only the fourth slot can be empty (triangles)
+				if(j == 3 && !quad) break;
 				const int le = (int)(cf[j] & 0x7FFFu);
+				const bool bndj = nb[j] == NB_BND;
+				const unsigned nj = bndj ? (unsigned)(grow0 + le - tb.x) : nb[j];
 				double pj[4];
-				double2 rj;
-				bool use_for_limiter = true;
-				if(nj != NB_BND) {
-					lds4(sp + 4*nj, pj);
-					rj = src[nj];
-				} else {
-					const double2 mid = M.fgr[e0 + le];
-					if(PRIM_IN) ld4(A.ug + 4*(size_t)M.fref[e0 + le], pj);
-					else {
-						const double2 n = M.fn[e0 + le];
-						const unsigned slot = (M.fLR[e0 + le] >> 16) & 15u;
-						double ui[4], gs[4];
-						prim2cons(A.gas, pi, ui);
-						ghost_state(A.gas, A.gas.bc[slot], ui, n.x, n.y, gs);
-						cons2prim(A.gas, gs, pj);
-					}
-					rj = make_double2(2.0*mid.x - rci.x, 2.0*mid.y - rci.y);      // ghost centre (aspatial.cpp:98-119)
-					use_for_limiter = A.bnd_policy == 0;
-				}
+				lds4(sp + 4*nj, pj);
+				const double2 rj = src[nj];
 				if(GRAD == GM_WLS) {
 					const double dx = rci.x - rj.x, dy = rci.y - rj.y;
 					const double w = frcp(dx*dx + dy*dy);
@@ -185,12 +197,13 @@ cell_kernel(const CellArgs A)
 						acc[2*v+1] += sgn*(ut*n.y)*ainv;
 					}
 				}
-				if(LIM != LM_NONE && use_for_limiter) {
+				if(LIM != LM_NONE && !(bndj && A.bnd_policy != 0)) {
 					#pragma unroll
 					for(int v = 0; v < 4; v++) {
+						// plain selects: fmax/fmin on doubles cost three times as much for their NaN rules
 						const double du = pj[v] - pi[v];
-						dmax[v] = fmax(dmax[v], du);
-						dmin[v] = fmin(dmin[v], du);
+						dmax[v] = du > dmax[v] ? du : dmax[v];
+						dmin[v] = du < dmin[v] ? du : dmin[v];
 					}
 				}
 			}
@@ -212,35 +225,48 @@ cell_kernel(const CellArgs A)
 		if(!A.lg) continue;
 
 		if(LIM != LM_NONE) {
-			double lim[4] = {1.0, 1.0, 1.0, 1.0};
+			// The limiter is the minimum over the faces of a ratio N/D with D > 0 (and of 1). The faces are
+			// compared by cross-multiplication and only the winning ratio is divided: one reciprocal per
+			// variable instead of one per face and variable. The reference divides per face and takes fmin
+			// (limitedlinearreconstruction.cpp:150-170, 244-262); the selected face is the same up to ties.
+			// Variable-outer order keeps the live state small (one variable's running minimum at a time).
 			double eps2 = 0.0;
 			if(LIM == LM_VENKAT) {
 				const double kh = A.gas.limiter_param*M.clength[i];
 				eps2 = kh*kh*kh;
 			}
+			double ddx[4], ddy[4];
 			#pragma unroll
 			for(int j = 0; j < 4; j++) {
-				if(j == 3 && nb[3] == NB_NONE) break;
-				const double2 mid = sgr[cf[j] & 0x7FFFu];
-				const double dx = mid.x - rci.x, dy = mid.y - rci.y;
-				#pragma unroll
-				for(int v = 0; v < 4; v++) {
-					const double uface = pi[v] + g[2*v]*dx + g[2*v+1]*dy;
-					const double dm = uface - pi[v];
-					double phi;
-					if(LIM == LM_VENKAT) {
-						const double dp = dm < 0.0 ? dmin[v] : dmax[v];
-						phi = (dp*dp + 2.0*dp*dm + eps2)*frcp(dp*dp + dp*dm + 2.0*dm*dm + eps2);
-					} else {
-						if(dm > 0.0) phi = fmin(1.0, dmax[v]/dm);
-						else if(dm < 0.0) phi = fmin(1.0, dmin[v]/dm);
-						else phi = 1.0;
-					}
-					lim[v] = fmin(lim[v], phi);
-				}
+				const double2 mid = sgr[(j == 3 && !quad) ? 0 : (cf[j] & 0x7FFFu)];
+				ddx[j] = mid.x - rci.x; ddy[j] = mid.y - rci.y;
 			}
 			#pragma unroll
-			for(int v = 0; v < 4; v++) { g[2*v] *= lim[v]; g[2*v+1] *= lim[v]; }
+			for(int v = 0; v < 4; v++) {
+				double bn = 1.0, bd = 1.0;
+				#pragma unroll
+				for(int j = 0; j < 4; j++) {
+					if(j == 3 && !quad) break;
+					const double uface = pi[v] + g[2*v]*ddx[j] + g[2*v+1]*ddy[j];
+					const double dm = uface - pi[v];
+					double n_, d_;
+					if(LIM == LM_VENKAT) {
+						const double dp = dm < 0.0 ? dmin[v] : dmax[v];
+						const double dp2e = dp*dp + eps2, dpm = dp*dm;
+						n_ = dp2e + 2.0*dpm;
+						d_ = dp2e + dpm + 2.0*dm*dm;
+					} else {
+						// Barth-Jespersen: dmax/dm for dm > 0, dmin/dm for dm < 0 (ratios of like signs), else 1
+						const bool pos = dm > 0.0;
+						n_ = pos ? dmax[v] : -dmin[v];
+						d_ = pos ? dm : -dm;
+						if(dm == 0.0) { n_ = 1.0; d_ = 1.0; }
+					}
+					if(n_*bd < bn*d_) { bn = n_; bd = d_; }
+				}
+				const double lim = bn*frcp(bd);
+				g[2*v] *= lim; g[2*v+1] *= lim;
+			}
 		}
 		st4(A.lg + 8*(size_t)i, g); st4(A.lg + 8*(size_t)i + 4, g+4);
 	}
