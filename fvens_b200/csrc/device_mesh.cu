@@ -296,7 +296,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	// boundary (one side is a halo cell), then physical-boundary faces, then padding. Warps of the flux phase
 	// are then uniform in kind; reference face order is kept inside a kind.
 	std::vector<int> scolour((size_t)ns, MAXCOL-1);
-	std::vector<int2> tbnd((size_t)ntile);      // tile-local index of the first boundary entry, number of boundary entries
+	std::vector<int4> tbnd((size_t)ntile);      // tile-local index of the first cut entry, of the first boundary entry, number of boundary entries, padding
 	m->max_colours = 0;
 	{
 		std::vector<unsigned char> used(TC);
@@ -328,7 +328,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 				scolour[e] = c;
 				m->max_colours = std::max(m->max_colours, c+1);
 			}
-			tbnd[t] = make_int2(cnt[0] + cnt[1], cnt[2]);
+			tbnd[t] = make_int4(cnt[0], cnt[0] + cnt[1], cnt[2], cnt[3]);
 			tmp.assign(sface.begin()+e0, sface.begin()+e1);
 			ctmp.assign(scolour.begin()+e0, scolour.begin()+e1);
 			int pos[4];
@@ -377,7 +377,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	// ---- per-cell arrays in device order (centres also for the ghosts)
 	std::vector<uint4> cloc((size_t)nown);
 	std::vector<double2> drc((size_t)ntot);
-	std::vector<double> area((size_t)nown), clength((size_t)nown);
+	std::vector<double> area((size_t)nown + 1, 1.0), clength((size_t)nown + 1, 1.0);     // one pad entry: tiles copy 16-byte granules
 	for(int i = 0; i < ntot; i++) drc[i] = make_double2(rc[2*(size_t)d2g[i]], rc[2*(size_t)d2g[i]+1]);
 	for(int i = 0; i < nown; i++) {
 		const int o = d2g[i], t = tile_of[i];

@@ -14,7 +14,7 @@ constexpr int MAXCOL = 8;          ///< greedy edge colouring of a degree-4 grap
 #define FVG_FACE_BLOCK 256
 #endif
 #ifndef FVG_FACE_MINB
-#define FVG_FACE_MINB 3
+#define FVG_FACE_MINB 2
 #endif
 #ifndef FVG_CELL_BLOCK
 #define FVG_CELL_BLOCK 256
@@ -55,7 +55,8 @@ struct DMesh {
 	const int *thoff;       ///< [ntile+1] offsets into thalo
 	const int *thalo;       ///< halo cell ids (device numbering), ascending within a tile
 	const int *fsoff;       ///< [ntile+1] stream segment of each tile (multiples of 4)
-	const int2 *tbnd;       ///< [ntile] x: tile-local index of the first physical-boundary entry, y: how many (halo + these <= HMAX)
+	const int4 *tbnd;       ///< [ntile] x: tile-local index of the first cut entry (one side in the halo), y: of the first
+	                        ///< physical-boundary entry, z: number of boundary entries (halo + these <= HMAX), w: padding entries
 	// per stream entry
 	const unsigned *fLR;    ///< local left | local right << 16; right >= LR_BND: boundary face with BC table index (right & 15);
 	                        ///< LR_PAD: padding entry

@@ -63,16 +63,24 @@ __device__ __forceinline__ double muscl_term(double delta, double dlr) {
 /// Per stream entry: the two face-state slots (later the flux and the spectral radii) and the midpoint;
 /// per halo cell: its state, reconstruction gradient and centre, gathered asynchronously while phase A runs.
 struct FaceSmem {
-	int fsL, fsR, sgr, hu, hg, hrc, bar, total;   // byte offsets
-	__host__ __device__ FaceSmem(int EMAX, int HMAX, bool mids) {
+	int fsL, fsR, sgr, sn, slen, sLR, hu, hg, hrc, su, sg, src, scl, sar, bar, total;   // byte offsets
+	__host__ __device__ FaceSmem(int TC, int EMAX, int HMAX, bool mids, bool linear) {
 		int o = 0;
 		fsL = o; o += EMAX*32;
 		fsR = o; o += EMAX*32;
 		sgr = o; o += mids ? EMAX*16 : 0;
+		sn = o; o += EMAX*16;
+		slen = o; o += EMAX*8;
+		sLR = o; o += EMAX*4;
 		hu = o; o += HMAX*32;
 		hg = o; o += mids ? HMAX*64 : 0;
 		hrc = o; o += mids ? HMAX*16 : 0;
-		bar = o; o += 8;
+		su = o; o += TC*32;                    // own cells: state, reconstruction gradient, centre, stencil, area
+		sg = o; o += linear ? TC*64 : 0;
+		src = o; o += linear ? TC*16 : 0;
+		scl = o; o += TC*16;
+		sar = o; o += (TC + 2)*8;
+		bar = o; o += 16;                      // two mbarriers
 		total = o;
 	}
 };
@@ -94,18 +102,19 @@ __device__ __forceinline__ void halo_side_state(const FaceArgs &A, const double 
 	extrapolate_prim(pc, ga, gb, gr.x, gr.y, rc.x, rc.y, pf);
 }
 
-/** One CTA per tile, three phases separated by two barriers:
- *  A  one thread per own cell: load its state / limited gradient / centre straight from global memory
- *     (consecutive cells => fully coalesced 32-byte rows), convert to primitive ONCE, extrapolate to each
- *     of its <= 4 faces and deposit the face state in the left or right slot of that face's stream entry
- *     in shared memory.
- *  B  one thread per stream entry (consecutive entries => conflict-free shared-memory rows): read both
- *     face states (a side belonging to a halo cell is gathered from global memory instead), boundary ghost,
- *     numerical flux, spectral radii; the flux overwrites the entry's slots.
+/** One CTA per tile. Everything the tile reads arrives in shared memory asynchronously - the own cells' rows
+ *  (state, reconstruction gradient, centre, stencil, area) and the stream-entry metadata (midpoints, normals,
+ *  lengths, local indices) by 1-D TMA bulk copies (contiguous per tile), the halo cells' rows by 16-byte
+ *  cp.async gathers - so no thread holds registers for loads in flight, and the second CTA resident on the SM
+ *  computes while this one's copies land. Then three phases separated by two barriers:
+ *  A  one thread per own cell: convert to primitive ONCE, extrapolate to each of its <= 4 faces and deposit
+ *     the face state in the left or right slot of that face's stream entry.
+ *  B  one thread per stream entry (consecutive entries => conflict-free shared-memory rows): both face
+ *     states (a side belonging to a halo cell is reconstructed from the staged halo row), boundary ghost,
+ *     numerical flux, spectral radii; the flux overwrites the entry's slots. Entries are ordered by kind, so
+ *     the halo rows are first needed in a later round and their copies are only waited for there.
  *  C  one thread per own cell: sum the fluxes of its faces in local-face order (deterministic, no
- *     atomics, no scatter), then the residual / time-step or the fused forward-Euler epilogue.
- *  The entry metadata (normals, lengths, midpoints, local indices) is contiguous per tile and arrives by
- *  1-D TMA bulk copies issued before phase A. */
+ *     atomics, no scatter), then the residual / time-step or the fused forward-Euler epilogue. */
 template <int FLUX, int RECON, int VISC>
 __global__ void __launch_bounds__(FACE_BLOCK, FVG_FACE_MINB)
 face_kernel(const FaceArgs A)
@@ -113,42 +122,59 @@ face_kernel(const FaceArgs A)
 	extern __shared__ __align__(128) unsigned char smraw[];
 	const DMesh &M = A.m;
 	constexpr bool MIDS = RECON != FR_FIRST;
-	const FaceSmem S(M.EMAX, M.HMAX, MIDS);
+	constexpr bool LINEAR = RECON == FR_LINEAR;
+	const FaceSmem S(M.TC, M.EMAX, M.HMAX, MIDS, LINEAR);
 	double *const fsL = reinterpret_cast<double*>(smraw + S.fsL);
 	double *const fsR = reinterpret_cast<double*>(smraw + S.fsR);
 	double2 *const sgr = reinterpret_cast<double2*>(smraw + S.sgr);
+	double2 *const sn = reinterpret_cast<double2*>(smraw + S.sn);
+	double *const slen = reinterpret_cast<double*>(smraw + S.slen);
+	unsigned *const sLR = reinterpret_cast<unsigned*>(smraw + S.sLR);
 	double *const hu = reinterpret_cast<double*>(smraw + S.hu);
 	double *const hg = reinterpret_cast<double*>(smraw + S.hg);
 	double2 *const hrc = reinterpret_cast<double2*>(smraw + S.hrc);
-	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);
+	double *const su = reinterpret_cast<double*>(smraw + S.su);
+	double *const sg = reinterpret_cast<double*>(smraw + S.sg);
+	double2 *const src = reinterpret_cast<double2*>(smraw + S.src);
+	uint4 *const scl = reinterpret_cast<uint4*>(smraw + S.scl);
+	double *const sar = reinterpret_cast<double*>(smraw + S.sar);
+	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);       // [0]: phase A inputs, [1]: the rest
 	__shared__ double red_s[FACE_BLOCK/32];
 
 	const int t = blockIdx.x, tid = threadIdx.x;
 	const int c0 = M.tcell0[t], nc = M.tcell0[t+1] - c0;
 	const int h0 = M.thoff[t], nh = M.thoff[t+1] - h0;
 	const int e0 = M.fsoff[t], ne = M.fsoff[t+1] - e0;
+	const int ecut = M.tbnd[t].x;                                   // first entry with a halo side
 	const double *const gsrc = RECON == FR_MUSCL ? A.gu : A.lg;     // gradients used by the reconstruction
+	const int aoff = c0 & 1;                                        // 8-byte rows are copied from the even cell below c0
 
-	// ---- face midpoints by TMA; halo rows by 16-byte async gathers (consumed in phase B only)
-	if(MIDS) {
-		if(tid == 0) mbar_init(bar, 1);
-		__syncthreads();
-		if(tid == 0) {
-			mbar_expect_tx(bar, (unsigned)ne*16u);
-			bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
+	if(tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+	__syncthreads();
+	if(tid == 0) {
+		mbar_expect_tx(bar, (unsigned)nc*(32u + 16u + (LINEAR ? 80u : 0u)) + (MIDS ? (unsigned)ne*16u : 0u));
+		bulk_g2s(su, A.u + 4*(size_t)c0, (unsigned)nc*32u, bar);
+		bulk_g2s(scl, M.cloc + c0, (unsigned)nc*16u, bar);
+		if(LINEAR) { bulk_g2s(sg, gsrc + 8*(size_t)c0, (unsigned)nc*64u, bar); bulk_g2s(src, M.rc + c0, (unsigned)nc*16u, bar); }
+		if(MIDS) bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
+		const unsigned abytes = (unsigned)((nc + aoff + 1) & ~1)*8u;
+		mbar_expect_tx(bar + 1, (unsigned)ne*(16u + 8u + 4u) + abytes);
+		bulk_g2s(sLR, M.fLR + e0, (unsigned)ne*4u, bar + 1);
+		bulk_g2s(sn, M.fn + e0, (unsigned)ne*16u, bar + 1);
+		bulk_g2s(slen, M.flen + e0, (unsigned)ne*8u, bar + 1);
+		bulk_g2s(sar, M.area + (c0 - aoff), abytes, bar + 1);
+	}
+	for(int h = tid; h < nh; h += FACE_BLOCK) {
+		const size_t g = (size_t)M.thalo[h0 + h];
+		cp_async16(hu + 4*h, A.u + 4*g);
+		cp_async16(hu + 4*h + 2, A.u + 4*g + 2);
+		if(MIDS) {
+			#pragma unroll
+			for(int q = 0; q < 4; q++) cp_async16(hg + 8*h + 2*q, gsrc + 8*g + 2*q);
+			cp_async16(hrc + h, M.rc + g);
 		}
 	}
-	{
-		constexpr int PIECES = MIDS ? 7 : 2;      // 16-byte pieces per halo cell: 2 of u [+ 4 of the gradient + the centre]
-		for(int k = tid; k < nh*PIECES; k += FACE_BLOCK) {
-			const int h = k/PIECES, piece = k - PIECES*h;
-			const size_t g = (size_t)M.thalo[h0 + h];
-			if(piece < 2) cp_async16(hu + 4*h + 2*piece, A.u + 4*g + 2*piece);
-			else if(piece < 6) cp_async16(hg + 8*h + 2*(piece-2), gsrc + 8*g + 2*(piece-2));
-			else cp_async16(hrc + h, M.rc + g);
-		}
-		cp_async_commit();
-	}
+	cp_async_commit();
 	if(tid == 32 && A.prefetch_distance > 0 && t + A.prefetch_distance < M.ntile) {
 		// warm L2 with the operands of the tile that runs about one wave of CTAs later
 		const int tp = t + A.prefetch_distance;
@@ -163,29 +189,16 @@ face_kernel(const FaceArgs A)
 		if(MIDS) bulk_prefetch_l2(M.fgr + pe0, (unsigned)pne*16u);
 		bulk_prefetch_l2(M.area + (pc0 & ~1), (unsigned)((pnc + 3) & ~1)*8u);
 	}
-	// entry metadata of this thread's first flux round, in flight during phase A
-	unsigned LRn = LR_PAD;
-	double2 nrmn = make_double2(1.0, 0.0);
-	double lenn = 0.0;
-	if(tid < ne) { LRn = M.fLR[e0 + tid]; nrmn = M.fn[e0 + tid]; lenn = M.flen[e0 + tid]; }
 
 	// ---- phase A: face states of the own cells
-	uint4 cl0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);     // metadata of cell `tid`, kept for phase C
-	double ar0 = 1.0;
-	if(tid < nc) ar0 = M.area[c0 + tid];
-	for(int k0 = 0; k0 < nc; k0 += FACE_BLOCK) {
-		const int k = k0 + tid;
-		uint4 cl = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);
-		double uc[4] = {1,0,0,1}, ga[4] = {0,0,0,0}, gb[4] = {0,0,0,0};
+	mbar_wait(bar, 0);
+	for(int k = tid; k < nc; k += FACE_BLOCK) {
+		const uint4 cl = scl[k];
+		double uc[4], ga[4] = {0,0,0,0}, gb[4] = {0,0,0,0};
 		double2 rc = make_double2(0,0);
-		if(k < nc) {
-			const size_t i = (size_t)(c0 + k);
-			cl = M.cloc[i];
-			ld4(A.u + 4*i, uc);
-			if(RECON == FR_LINEAR) { ld4(gsrc + 8*i, ga); ld4(gsrc + 8*i + 4, gb); rc = M.rc[i]; }
-		}
-		if(k0 == 0) { cl0 = cl; if(MIDS) mbar_wait(bar, 0); }     // midpoints needed from here on
-		if(k < nc) {
+		lds4(su + 4*k, uc);
+		if(LINEAR) { lds4(sg + 8*k, ga); lds4(sg + 8*k + 4, gb); rc = src[k]; }
+		{
 			double pc[4];
 			if(RECON == FR_FIRST) { for(int q = 0; q < 4; q++) pc[q] = uc[q]; }
 			else cons2prim(A.gas, uc, pc);
@@ -206,16 +219,20 @@ face_kernel(const FaceArgs A)
 			}
 		}
 	}
-	cp_async_wait_all();
+	mbar_wait(bar + 1, 0);
 	__syncthreads();
 
-	// ---- phase B: fluxes, one stream entry per thread and round; the next round's metadata is loaded first
-	for(int e = tid; e < ne; e += FACE_BLOCK) {
-		const unsigned LR = LRn;
-		const double2 nrm = nrmn;
-		const double len = lenn;
-		if(e + FACE_BLOCK < ne) { LRn = M.fLR[e0 + e + FACE_BLOCK]; nrmn = M.fn[e0 + e + FACE_BLOCK]; lenn = M.flen[e0 + e + FACE_BLOCK]; }
+	// ---- phase B: fluxes, one stream entry per thread and round. The halo rows are needed from entry `ecut` on:
+	// the round that reaches it first waits for the gathers (uniform across the CTA: the test is on the round)
+	bool halo_ready = false;
+	for(int eb = 0; eb < ne; eb += FACE_BLOCK) {
+		if(!halo_ready && eb + FACE_BLOCK > ecut) { cp_async_wait_all(); __syncthreads(); halo_ready = true; }
+		const int e = eb + tid;
+		if(e >= ne) continue;
+		const unsigned LR = sLR[e];
 		if(LR == LR_PAD) continue;
+		const double2 nrm = sn[e];
+		const double len = slen[e];
 		const unsigned L = LR & 0xFFFFu, Rf = LR >> 16;
 		const bool bnd = Rf >= LR_BND;
 		const double nx = nrm.x, ny = nrm.y;
@@ -333,8 +350,8 @@ face_kernel(const FaceArgs A)
 	double part = 0.0;
 	for(int k = tid; k < nc; k += FACE_BLOCK) {
 		const size_t c = (size_t)(c0 + k);
-		const uint4 cl = k == tid ? cl0 : M.cloc[c];
-		const double ar = k == tid ? ar0 : M.area[c];
+		const uint4 cl = scl[k];
+		const double ar = sar[k + aoff];
 		const unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
 		const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
 		double r[4] = {0,0,0,0}, integ = 0.0;
@@ -360,7 +377,7 @@ face_kernel(const FaceArgs A)
 			const double dt = ar/integ;
 			const double fac = A.cfl*dt/ar;
 			double uo[4];
-			ld4(A.u + 4*c, uo);
+			lds4(su + 4*k, uo);
 			uo[0] += fac*r[0]; uo[1] += fac*r[1]; uo[2] += fac*r[2]; uo[3] += fac*r[3];
 			st4(A.unew + 4*c, uo);
 			part += r[3]*r[3]*ar;
@@ -382,7 +399,7 @@ face_kernel(const FaceArgs A)
 template <int FLUX, int RECON, int VISC>
 static int launch_one(const FaceArgs &a, cudaStream_t s)
 {
-	const FaceSmem S(a.m.EMAX, a.m.HMAX, RECON != FR_FIRST);
+	const FaceSmem S(a.m.TC, a.m.EMAX, a.m.HMAX, RECON != FR_FIRST, RECON == FR_LINEAR);
 	const size_t smem = (size_t)S.total;
 	if(smem > 48*1024) {
 		const cudaError_t ea = cudaFuncSetAttribute(face_kernel<FLUX,RECON,VISC>,

@@ -18,8 +18,8 @@ enum { LM_NONE = 0, LM_BJ = 1, LM_VENKAT = 2 };
 
 /// Shared-memory carve-up of the cell kernel
 struct CellSmem {
-	int sp, src, sgr, sn, slen, bar, total;
-	__host__ __device__ CellSmem(int TC, int HMAX, int EMAX, bool mids, bool metrics) {
+	int sp, src, sgr, sn, slen, scl, sV, sclen, bar, total;
+	__host__ __device__ CellSmem(int TC, int HMAX, int EMAX, bool mids, bool metrics, bool wls, bool venkat) {
 		const int CAPC = TC + HMAX;
 		int o = 0;
 		sp = o; o += CAPC*32;
@@ -27,6 +27,9 @@ struct CellSmem {
 		sgr = o; o += mids ? EMAX*16 : 0;
 		sn = o; o += metrics ? EMAX*16 : 0;
 		slen = o; o += metrics ? EMAX*8 : 0;
+		scl = o; o += TC*16;
+		sV = o; o += wls ? TC*32 : 0;
+		sclen = o; o += venkat ? (TC + 2)*8 : 0;
 		bar = o; o += 8;
 		total = o;
 	}
@@ -45,12 +48,15 @@ cell_kernel(const CellArgs A)
 	const DMesh &M = A.m;
 	constexpr bool MIDS = LIM != LM_NONE || GRAD == GM_GG;
 	constexpr bool METRICS = GRAD == GM_GG;
-	const CellSmem S(M.TC, M.HMAX, M.EMAX, MIDS, METRICS);
+	const CellSmem S(M.TC, M.HMAX, M.EMAX, MIDS, METRICS, GRAD == GM_WLS, LIM == LM_VENKAT);
 	double *const sp = reinterpret_cast<double*>(smraw + S.sp);
 	double2 *const src = reinterpret_cast<double2*>(smraw + S.src);
 	double2 *const sgr = reinterpret_cast<double2*>(smraw + S.sgr);
 	double2 *const sn = reinterpret_cast<double2*>(smraw + S.sn);
 	double *const slen = reinterpret_cast<double*>(smraw + S.slen);
+	const uint4 *const scl = reinterpret_cast<const uint4*>(smraw + S.scl);
+	const double4 *const sV = reinterpret_cast<const double4*>(smraw + S.sV);
+	const double *const sclen = reinterpret_cast<const double*>(smraw + S.sclen);
 	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);
 
 	const int t = blockIdx.x, tid = threadIdx.x;
@@ -62,12 +68,17 @@ cell_kernel(const CellArgs A)
 	if(tid == 0) mbar_init(bar, 1);
 	__syncthreads();
 	if(tid == 0) {
-		unsigned bytes = (unsigned)nc*(32u + 16u);
+		unsigned bytes = (unsigned)nc*(32u + 16u + 16u + (GRAD == GM_WLS ? 32u : 0u)) + (LIM == LM_VENKAT ? (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u : 0u);
 		if(MIDS) bytes += (unsigned)ne*16u;
 		if(METRICS) bytes += (unsigned)ne*(16u + 8u);
 		mbar_expect_tx(bar, bytes);
 		bulk_g2s(sp, A.u + 4*(size_t)c0, (unsigned)nc*32u, bar);
 		bulk_g2s(src, M.rc + c0, (unsigned)nc*16u, bar);
+		// the cells' stencil metadata rides along (consumed from shared memory: no registers held across the staging)
+		bulk_g2s(smraw + S.scl, M.cloc + c0, (unsigned)nc*16u, bar);
+		if(GRAD == GM_WLS) bulk_g2s(smraw + S.sV, M.wlsV + c0, (unsigned)nc*32u, bar);
+		// 8-byte rows: copy whole 16-byte granules starting at the even cell below c0 (the array is padded by one entry)
+		if(LIM == LM_VENKAT) bulk_g2s(smraw + S.sclen, M.clength + (c0 & ~1), (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u, bar);
 		if(MIDS) bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
 		if(METRICS) { bulk_g2s(sn, M.fn + e0, (unsigned)ne*16u, bar); bulk_g2s(slen, M.flen + e0, (unsigned)ne*8u, bar); }
 	}
@@ -93,14 +104,8 @@ cell_kernel(const CellArgs A)
 		}
 		cp_async_commit();
 	}
-	// the first cell's own metadata is fetched while the copies are in flight
-	uint4 cl = make_uint4(0,0,0,0);
-	double4 V = make_double4(0,0,0,0);
-	if(tid < nc) {
-		cl = M.cloc[c0 + tid];
-		if(GRAD == GM_WLS) V = M.wlsV[c0 + tid];
-	}
-	const int2 tb = M.tbnd[t];                 // boundary entries of the tile: first (tile-local) and count
+	const int4 tbq = M.tbnd[t];
+	const int2 tb = make_int2(tbq.y, tbq.z);   // boundary entries of the tile: first (tile-local) and count
 	const int grow0 = nc + nh;                 // their ghost cells are staged as rows grow0 .. grow0 + tb.y - 1
 	cp_async_wait_all();
 	mbar_wait(bar, 0);
@@ -144,10 +149,7 @@ cell_kernel(const CellArgs A)
 
 	for(int k = tid; k < nc; k += CELL_BLOCK) {
 		const int i = c0 + k;
-		if(k != tid) {
-			cl = M.cloc[i];
-			if(GRAD == GM_WLS) V = M.wlsV[i];
-		}
+		const uint4 cl = scl[k];
 		unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
 		const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
 		const bool quad = nb[3] != NB_NONE;       // only the fourth slot can be empty (triangles)
@@ -211,6 +213,7 @@ cell_kernel(const CellArgs A)
 
 		double g[8];
 		if(GRAD == GM_WLS) {
+			const double4 V = sV[k];
 			#pragma unroll
 			for(int v = 0; v < 4; v++) {
 				g[2*v]   = V.x*acc[2*v] + V.y*acc[2*v+1];
@@ -232,7 +235,7 @@ cell_kernel(const CellArgs A)
 			// Variable-outer order keeps the live state small (one variable's running minimum at a time).
 			double eps2 = 0.0;
 			if(LIM == LM_VENKAT) {
-				const double kh = A.gas.limiter_param*M.clength[i];
+				const double kh = A.gas.limiter_param*sclen[k + (c0 & 1)];
 				eps2 = kh*kh*kh;
 			}
 			double ddx[4], ddy[4];
@@ -275,7 +278,7 @@ cell_kernel(const CellArgs A)
 template <int GRAD, int LIM, bool PRIM_IN>
 static int launch_cell(const CellArgs &a, cudaStream_t s)
 {
-	const CellSmem S(a.m.TC, a.m.HMAX, a.m.EMAX, LIM != LM_NONE || GRAD == GM_GG, GRAD == GM_GG);
+	const CellSmem S(a.m.TC, a.m.HMAX, a.m.EMAX, LIM != LM_NONE || GRAD == GM_GG, GRAD == GM_GG, GRAD == GM_WLS, LIM == LM_VENKAT);
 	if(S.total > 48*1024) {
 		const cudaError_t ea = cudaFuncSetAttribute(cell_kernel<GRAD,LIM,PRIM_IN>,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);

@@ -74,3 +74,19 @@ print("by stall samples:")
 for key, b in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:top//2]:
     st = " ".join(f"{h[6:]}:{c}" for h, c in b[2].most_common(4) if c)
     print(f"  {key[0]}:{key[1]:<5d} samples {100*b[0]/max(tot_s,1):5.1f}%  exec {100*b[1]/tot_e:5.1f}%  {st}")
+
+# optional phase summary: FVG_PHASES="name:file:lo-hi,..." groups lines into ranges
+import os
+ph = os.environ.get("FVG_PHASES")
+if ph:
+    print("by phase:")
+    for spec in ph.split(","):
+        name, fn, rng = spec.split(":")
+        lo, hi = (int(x) for x in rng.split("-"))
+        s = sum(b[0] for k, b in by_line.items() if k[0] == fn and lo <= k[1] <= hi)
+        e = sum(b[1] for k, b in by_line.items() if k[0] == fn and lo <= k[1] <= hi)
+        st = collections.Counter()
+        for k, b in by_line.items():
+            if k[0] == fn and lo <= k[1] <= hi:
+                st.update(b[2])
+        print(f"  {name:12s} samples {100*s/max(tot_s,1):5.1f}%  exec {100*e/tot_e:5.1f}%  " + " ".join(f"{h[6:]}:{100*c/max(tot_s,1):.1f}%" for h, c in st.most_common(5)))
