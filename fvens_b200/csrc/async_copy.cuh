@@ -36,6 +36,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+/// Orders this thread's earlier generic-proxy accesses to shared memory (made visible to it by a barrier) before
+/// the async-proxy writes of bulk copies it issues next: needed when a staging buffer is recycled.
+__device__ __forceinline__ void fence_proxy_async() {
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 /// Contiguous copy of `bytes` (multiple of 16, both addresses 16-byte aligned) global -> shared.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -63,7 +63,7 @@ __device__ __forceinline__ double muscl_term(double delta, double dlr) {
 /// Per stream entry: the two face-state slots (later the flux and the spectral radii) and the midpoint;
 /// per halo cell: its state, reconstruction gradient and centre, gathered asynchronously while phase A runs.
 struct FaceSmem {
-	int fsL, fsR, sgr, sn, slen, sLR, hu, hg, hrc, su, sg, src, scl, sar, bar, total;   // byte offsets
+	int fsL, fsR, sgr, sn, slen, sLR, hu, hg, hrc, su, sg, src, scl, sar, cbuf, bar, total;   // byte offsets
 	__host__ __device__ FaceSmem(int TC, int EMAX, int HMAX, bool mids, bool linear) {
 		int o = 0;
 		fsL = o; o += EMAX*32;
@@ -75,11 +75,11 @@ struct FaceSmem {
 		hu = o; o += HMAX*32;
 		hg = o; o += mids ? HMAX*64 : 0;
 		hrc = o; o += mids ? HMAX*16 : 0;
-		su = o; o += TC*32;                    // own cells: state, reconstruction gradient, centre, stencil, area
+		su = o; o += TC*32;                    // own cells: state, reconstruction gradient, centre
 		sg = o; o += linear ? TC*64 : 0;
 		src = o; o += linear ? TC*16 : 0;
-		scl = o; o += TC*16;
-		sar = o; o += (TC + 2)*8;
+		cbuf = TC*16 + (TC + 2)*8;             // stencil + area, two buffers of cbuf bytes
+		scl = o; sar = o + TC*16; o += 2*cbuf;
 		bar = o; o += 16;                      // two mbarriers
 		total = o;
 	}
@@ -102,11 +102,27 @@ __device__ __forceinline__ void halo_side_state(const FaceArgs &A, const double 
 	extrapolate_prim(pc, ga, gb, gr.x, gr.y, rc.x, rc.y, pf);
 }
 
-/** One CTA per tile. Everything the tile reads arrives in shared memory asynchronously - the own cells' rows
- *  (state, reconstruction gradient, centre, stencil, area) and the stream-entry metadata (midpoints, normals,
- *  lengths, local indices) by 1-D TMA bulk copies (contiguous per tile), the halo cells' rows by 16-byte
- *  cp.async gathers - so no thread holds registers for loads in flight, and the second CTA resident on the SM
- *  computes while this one's copies land. Then three phases separated by two barriers:
+/// Descriptor of one tile (all uniform across the CTA)
+struct TileDesc { int c0, nc, h0, nh, e0, ne, ecut; };
+__device__ __forceinline__ TileDesc load_tile_desc(const DMesh &M, int t) {
+	TileDesc D;
+	D.c0 = M.tcell0[t]; D.nc = M.tcell0[t+1] - D.c0;
+	D.h0 = M.thoff[t]; D.nh = M.thoff[t+1] - D.h0;
+	D.e0 = M.fsoff[t]; D.ne = M.fsoff[t+1] - D.e0;
+	D.ecut = M.tbnd[t].x;
+	return D;
+}
+
+/** Persistent CTAs (two per SM), each walking over tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
+ *  Everything a tile reads arrives in shared memory asynchronously - the own cells' rows (state, reconstruction
+ *  gradient, centre, stencil, area) and the stream-entry metadata (midpoints, normals, lengths, local indices)
+ *  by 1-D TMA bulk copies (contiguous per tile), the halo cells' rows by 16-byte cp.async gathers - and the
+ *  copies for the NEXT tile are issued as soon as the current tile's phase that reads a buffer is over, so they
+ *  land while the current tile is still computing:
+ *    group A buffers (state, gradient, centre, midpoints)         read in phase A     -> refilled after phase A
+ *    group B buffers (normals, lengths, local indices, halo rows)  read in phase B     -> refilled after phase B
+ *    group C buffers (stencil, area)                               read in A and C     -> double-buffered
+ *  Per tile, three phases separated by barriers:
  *  A  one thread per own cell: convert to primitive ONCE, extrapolate to each of its <= 4 faces and deposit
  *     the face state in the left or right slot of that face's stream entry.
  *  B  one thread per stream entry (consecutive entries => conflict-free shared-memory rows): both face
@@ -136,69 +152,73 @@ face_kernel(const FaceArgs A)
 	double *const su = reinterpret_cast<double*>(smraw + S.su);
 	double *const sg = reinterpret_cast<double*>(smraw + S.sg);
 	double2 *const src = reinterpret_cast<double2*>(smraw + S.src);
-	uint4 *const scl = reinterpret_cast<uint4*>(smraw + S.scl);
-	double *const sar = reinterpret_cast<double*>(smraw + S.sar);
-	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);       // [0]: phase A inputs, [1]: the rest
+	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);       // [0]: groups A + C, [1]: group B
 	__shared__ double red_s[FACE_BLOCK/32];
 
-	const int t = blockIdx.x, tid = threadIdx.x;
-	const int c0 = M.tcell0[t], nc = M.tcell0[t+1] - c0;
-	const int h0 = M.thoff[t], nh = M.thoff[t+1] - h0;
-	const int e0 = M.fsoff[t], ne = M.fsoff[t+1] - e0;
-	const int ecut = M.tbnd[t].x;                                   // first entry with a halo side
+	const int tid = threadIdx.x;
 	const double *const gsrc = RECON == FR_MUSCL ? A.gu : A.lg;     // gradients used by the reconstruction
-	const int aoff = c0 & 1;                                        // 8-byte rows are copied from the even cell below c0
 
+	// issue helpers (thread 0 only for the bulk copies). 8-byte rows (area) are copied from the even cell below c0.
+	auto issue_AC = [&](const TileDesc &D, int buf) {
+		const unsigned aoff = (unsigned)(D.c0 & 1);
+		const unsigned abytes = (unsigned)((D.nc + aoff + 1) & ~1)*8u;
+		mbar_expect_tx(bar, (unsigned)D.nc*(32u + 16u + (LINEAR ? 80u : 0u)) + (MIDS ? (unsigned)D.ne*16u : 0u) + abytes);
+		bulk_g2s(su, A.u + 4*(size_t)D.c0, (unsigned)D.nc*32u, bar);
+		if(LINEAR) { bulk_g2s(sg, gsrc + 8*(size_t)D.c0, (unsigned)D.nc*64u, bar); bulk_g2s(src, M.rc + D.c0, (unsigned)D.nc*16u, bar); }
+		if(MIDS) bulk_g2s(sgr, M.fgr + D.e0, (unsigned)D.ne*16u, bar);
+		bulk_g2s(smraw + S.scl + buf*S.cbuf, M.cloc + D.c0, (unsigned)D.nc*16u, bar);
+		bulk_g2s(smraw + S.sar + buf*S.cbuf, M.area + (D.c0 - (int)aoff), abytes, bar);
+	};
+	auto issue_B = [&](const TileDesc &D) {
+		mbar_expect_tx(bar + 1, (unsigned)D.ne*(16u + 8u + 4u));
+		bulk_g2s(sLR, M.fLR + D.e0, (unsigned)D.ne*4u, bar + 1);
+		bulk_g2s(sn, M.fn + D.e0, (unsigned)D.ne*16u, bar + 1);
+		bulk_g2s(slen, M.flen + D.e0, (unsigned)D.ne*8u, bar + 1);
+	};
+	// halo rows of a tile: thread h gathers halo cell h (device index g), FACE_BLOCK >= HMAX
+	auto issue_halo = [&](int nh, int g) {
+		if(tid < nh) {
+			cp_async16(hu + 4*tid, A.u + 4*(size_t)g);
+			cp_async16(hu + 4*tid + 2, A.u + 4*(size_t)g + 2);
+			if(MIDS) {
+				#pragma unroll
+				for(int q = 0; q < 4; q++) cp_async16(hg + 8*tid + 2*q, gsrc + 8*(size_t)g + 2*q);
+				cp_async16(hrc + tid, M.rc + g);
+			}
+		}
+		cp_async_commit();
+	};
+
+	int t = blockIdx.x;
+	if(t >= M.ntile) return;
+	TileDesc D = load_tile_desc(M, t);
 	if(tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
 	__syncthreads();
-	if(tid == 0) {
-		mbar_expect_tx(bar, (unsigned)nc*(32u + 16u + (LINEAR ? 80u : 0u)) + (MIDS ? (unsigned)ne*16u : 0u));
-		bulk_g2s(su, A.u + 4*(size_t)c0, (unsigned)nc*32u, bar);
-		bulk_g2s(scl, M.cloc + c0, (unsigned)nc*16u, bar);
-		if(LINEAR) { bulk_g2s(sg, gsrc + 8*(size_t)c0, (unsigned)nc*64u, bar); bulk_g2s(src, M.rc + c0, (unsigned)nc*16u, bar); }
-		if(MIDS) bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
-		const unsigned abytes = (unsigned)((nc + aoff + 1) & ~1)*8u;
-		mbar_expect_tx(bar + 1, (unsigned)ne*(16u + 8u + 4u) + abytes);
-		bulk_g2s(sLR, M.fLR + e0, (unsigned)ne*4u, bar + 1);
-		bulk_g2s(sn, M.fn + e0, (unsigned)ne*16u, bar + 1);
-		bulk_g2s(slen, M.flen + e0, (unsigned)ne*8u, bar + 1);
-		bulk_g2s(sar, M.area + (c0 - aoff), abytes, bar + 1);
-	}
-	for(int h = tid; h < nh; h += FACE_BLOCK) {
-		const size_t g = (size_t)M.thalo[h0 + h];
-		cp_async16(hu + 4*h, A.u + 4*g);
-		cp_async16(hu + 4*h + 2, A.u + 4*g + 2);
-		if(MIDS) {
-			#pragma unroll
-			for(int q = 0; q < 4; q++) cp_async16(hg + 8*h + 2*q, gsrc + 8*g + 2*q);
-			cp_async16(hrc + h, M.rc + g);
-		}
-	}
-	cp_async_commit();
-	if(tid == 32 && A.prefetch_distance > 0 && t + A.prefetch_distance < M.ntile) {
-		// warm L2 with the operands of the tile that runs about one wave of CTAs later
-		const int tp = t + A.prefetch_distance;
-		const int pc0 = M.tcell0[tp], pnc = M.tcell0[tp+1] - pc0;
-		const int pe0 = M.fsoff[tp], pne = M.fsoff[tp+1] - pe0;
-		bulk_prefetch_l2(A.u + 4*(size_t)pc0, (unsigned)pnc*32u);
-		bulk_prefetch_l2(M.cloc + pc0, (unsigned)pnc*16u);
-		if(RECON != FR_FIRST) { bulk_prefetch_l2(gsrc + 8*(size_t)pc0, (unsigned)pnc*64u); bulk_prefetch_l2(M.rc + pc0, (unsigned)pnc*16u); }
-		bulk_prefetch_l2(M.fLR + pe0, (unsigned)pne*4u);
-		bulk_prefetch_l2(M.fn + pe0, (unsigned)pne*16u);
-		bulk_prefetch_l2(M.flen + pe0, (unsigned)pne*8u);
-		if(MIDS) bulk_prefetch_l2(M.fgr + pe0, (unsigned)pne*16u);
-		bulk_prefetch_l2(M.area + (pc0 & ~1), (unsigned)((pnc + 3) & ~1)*8u);
-	}
+	if(tid == 0) { issue_AC(D, 0); issue_B(D); }
+	issue_halo(D.nh, tid < D.nh ? M.thalo[D.h0 + tid] : 0);
 
-	// ---- phase A: face states of the own cells
-	mbar_wait(bar, 0);
-	for(int k = tid; k < nc; k += FACE_BLOCK) {
-		const uint4 cl = scl[k];
-		double uc[4], ga[4] = {0,0,0,0}, gb[4] = {0,0,0,0};
-		double2 rc = make_double2(0,0);
-		lds4(su + 4*k, uc);
-		if(LINEAR) { lds4(sg + 8*k, ga); lds4(sg + 8*k + 4, gb); rc = src[k]; }
-		{
+	for(int it = 0; t < M.ntile; it++) {
+		const unsigned par = (unsigned)(it & 1);
+		const uint4 *const scl = reinterpret_cast<const uint4*>(smraw + S.scl + (int)par*S.cbuf);
+		const double *const sar = reinterpret_cast<const double*>(smraw + S.sar + (int)par*S.cbuf);
+		const int aoff = D.c0 & 1;
+		// the next tile's descriptor and this thread's halo index for it are in flight during phase A
+		const int tn = t + (int)gridDim.x;
+		const bool have_next = tn < M.ntile;
+		TileDesc Dn = D;
+		int gnext = 0;
+		if(have_next) { Dn = load_tile_desc(M, tn); }
+
+		// ---- phase A: face states of the own cells
+		mbar_wait(bar, par);
+		double uc0[4] = {1,0,0,1};           // state of cell `tid`, kept for the fused step epilogue
+		for(int k = tid; k < D.nc; k += FACE_BLOCK) {
+			const uint4 cl = scl[k];
+			double uc[4], ga[4] = {0,0,0,0}, gb[4] = {0,0,0,0};
+			double2 rc = make_double2(0,0);
+			lds4(su + 4*k, uc);
+			if(k == tid) { for(int q = 0; q < 4; q++) uc0[q] = uc[q]; }
+			if(LINEAR) { lds4(sg + 8*k, ga); lds4(sg + 8*k + 4, gb); rc = src[k]; }
 			double pc[4];
 			if(RECON == FR_FIRST) { for(int q = 0; q < 4; q++) pc[q] = uc[q]; }
 			else cons2prim(A.gas, uc, pc);
@@ -218,181 +238,202 @@ face_kernel(const FaceArgs A)
 				*reinterpret_cast<double2*>(dst + 2) = make_double2(pf[2], pf[3]);
 			}
 		}
-	}
-	mbar_wait(bar + 1, 0);
-	__syncthreads();
-
-	// ---- phase B: fluxes, one stream entry per thread and round. The halo rows are needed from entry `ecut` on:
-	// the round that reaches it first waits for the gathers (uniform across the CTA: the test is on the round)
-	bool halo_ready = false;
-	for(int eb = 0; eb < ne; eb += FACE_BLOCK) {
-		if(!halo_ready && eb + FACE_BLOCK > ecut) { cp_async_wait_all(); __syncthreads(); halo_ready = true; }
-		const int e = eb + tid;
-		if(e >= ne) continue;
-		const unsigned LR = sLR[e];
-		if(LR == LR_PAD) continue;
-		const double2 nrm = sn[e];
-		const double len = slen[e];
-		const unsigned L = LR & 0xFFFFu, Rf = LR >> 16;
-		const bool bnd = Rf >= LR_BND;
-		const double nx = nrm.x, ny = nrm.y;
-		const BCEntry &bc = A.gas.bc[Rf & 15u];
-		double sl[4], sr[4];       // face states: conserved (first order) / primitive; MUSCL: cell states
-		if(L < (unsigned)nc) lds4(fsL + 4*e, sl);
-		else halo_side_state<RECON>(A, hu, hg, hrc, (int)L - nc, MIDS ? sgr[e] : make_double2(0,0), sl);
-		if(!bnd) {
-			if(Rf < (unsigned)nc) lds4(fsR + 4*e, sr);
-			else halo_side_state<RECON>(A, hu, hg, hrc, (int)Rf - nc, MIDS ? sgr[e] : make_double2(0,0), sr);
-		}
-		const int gidL = (VISC != VISC_NONE || RECON == FR_MUSCL) ? tile_global(M, t, c0, nc, L) : 0;
-		const int gidR = (VISC != VISC_NONE || RECON == FR_MUSCL) ? (bnd ? gidL : tile_global(M, t, c0, nc, Rf)) : 0;
-
-		Side a, bs;
-		double ucl[4], ucr[4];      // conserved cell states for the viscous flux (right = ghost of the cell state)
-		if(RECON == FR_FIRST) {
-			if(bnd) ghost_state(A.gas, bc, sl, nx, ny, sr);
-			a = load_side<true>(A.gas, sl, nx, ny);
-			bs = load_side<true>(A.gas, sr, nx, ny);
-			if(VISC != VISC_NONE) for(int q = 0; q < 4; q++) { ucl[q] = sl[q]; ucr[q] = sr[q]; }
-		}
-		else if(RECON == FR_LINEAR) {
-			a = side_from_prim<true>(A.gas, sl, nx, ny);
-			if(bnd) {
-				const double ul[4] = {a.r, a.mx, a.my, a.E};
-				double ur[4];
-				ghost_state(A.gas, bc, ul, nx, ny, ur);
-				bs = load_side<true>(A.gas, ur, nx, ny);
-			} else bs = side_from_prim<true>(A.gas, sr, nx, ny);
-			if(VISC != VISC_NONE) {
-				ld4(A.u + 4*(size_t)gidL, ucl);
-				if(bnd) ghost_state(A.gas, bc, ucl, nx, ny, ucr);
-				else ld4(A.u + 4*(size_t)gidR, ucr);
-			}
-		}
-		else { // MUSCL with Van Albada limiter: sl, sr are the primitive CELL states
-			const double2 gr = sgr[e];
-			const double2 rl = M.rc[gidL];
-			double2 rr;
-			if(bnd) {
-				prim2cons(A.gas, sl, ucl);
-				ghost_state(A.gas, bc, ucl, nx, ny, ucr);
-				cons2prim(A.gas, ucr, sr);
-				rr = make_double2(2.0*gr.x - rl.x, 2.0*gr.y - rl.y);     // ghost centre (aspatial.cpp:98-119)
-			} else {
-				rr = M.rc[gidR];
-				if(VISC != VISC_NONE) { prim2cons(A.gas, sl, ucl); prim2cons(A.gas, sr, ucr); }
-			}
-			const double dx = rr.x - rl.x, dy = rr.y - rl.y;
-			double ga[4], gb[4], pfl[4], pfr[4];
-			ld4(gsrc + 8*(size_t)gidL, ga); ld4(gsrc + 8*(size_t)gidL + 4, gb);
-			{
-				const double gx[4] = {ga[0], ga[2], gb[0], gb[2]}, gy[4] = {ga[1], ga[3], gb[1], gb[3]};
-				for(int q = 0; q < 4; q++) {
-					const double dlr = sr[q] - sl[q];
-					pfl[q] = sl[q] + muscl_term(2.0*(gx[q]*dx + gy[q]*dy) - dlr, dlr);
-				}
-			}
-			a = side_from_prim<true>(A.gas, pfl, nx, ny);
-			if(bnd) {
-				const double ul[4] = {a.r, a.mx, a.my, a.E};
-				double ur[4];
-				ghost_state(A.gas, bc, ul, nx, ny, ur);
-				bs = load_side<true>(A.gas, ur, nx, ny);
-			} else {
-				ld4(gsrc + 8*(size_t)gidR, ga); ld4(gsrc + 8*(size_t)gidR + 4, gb);
-				const double gx[4] = {ga[0], ga[2], gb[0], gb[2]}, gy[4] = {ga[1], ga[3], gb[1], gb[3]};
-				for(int q = 0; q < 4; q++) {
-					const double dlr = sr[q] - sl[q];
-					pfr[q] = sr[q] - muscl_term(2.0*(gx[q]*dx + gy[q]*dy) - dlr, dlr);
-				}
-				bs = side_from_prim<true>(A.gas, pfr, nx, ny);
-			}
-		}
-
-		double f[4];
-		flux_from_sides<FLUX>(A.gas, a, bs, nx, ny, f);
-		for(int q = 0; q < 4; q++) f[q] *= len;
-		double sri = (fabs(a.vn) + a.c)*len;
-		double srj = (fabs(bs.vn) + bs.c)*len;
-
-		if(VISC != VISC_NONE) {
-			const double ul[4] = {a.r, a.mx, a.my, a.E}, ur[4] = {bs.r, bs.mx, bs.my, bs.E};
-			const double2 rl = M.rc[gidL];
-			double2 rr;
-			if(bnd) {
-				const double2 gr = M.fgr[e0 + e];
-				rr = make_double2(2.0*gr.x - rl.x, 2.0*gr.y - rl.y);
-			} else rr = M.rc[gidR];
-			double gl[8], grr[8], vf[4];
-			if(RECON != FR_FIRST) {
-				ld4(A.gu + 8*(size_t)gidL, gl); ld4(A.gu + 8*(size_t)gidL + 4, gl+4);
-				if(bnd) for(int q = 0; q < 8; q++) grr[q] = gl[q];
-				else { ld4(A.gu + 8*(size_t)gidR, grr); ld4(A.gu + 8*(size_t)gidR + 4, grr+4); }
-			}
-			viscous_face_flux<RECON != FR_FIRST, VISC == VISC_CONST>(A.gas, nx, ny, rl.x, rl.y, rr.x, rr.y,
-				ucl, ucr, gl, grr, ul, ur, vf);
-			for(int q = 0; q < 4; q++) f[q] += vf[q]*len;
-			const double mui = VISC == VISC_CONST ? 1.0/A.gas.Reinf : viscosity_cons(A.gas, ul);
-			const double muj = VISC == VISC_CONST ? 1.0/A.gas.Reinf : viscosity_cons(A.gas, ur);
-			const double coi = fmax(4.0/(3.0*ul[0]), A.gas.g/ul[0]);
-			const double coj = fmax(4.0/(3.0*ur[0]), A.gas.g/ur[0]);
-			sri += coi*mui/A.gas.Pr*len*len/M.area[gidL];
-			if(!bnd) srj += coj*muj/A.gas.Pr*len*len/M.area[gidR];
-		}
-		// the entry's slots now carry its flux and the two spectral radii
-		*reinterpret_cast<double2*>(fsL + 4*e) = make_double2(f[0], f[1]);
-		*reinterpret_cast<double2*>(fsL + 4*e + 2) = make_double2(f[2], f[3]);
-		*reinterpret_cast<double2*>(fsR + 4*e) = make_double2(sri, srj);
-	}
-	__syncthreads();
-
-	// ---- phase C: per-cell sums in local-face order, then the epilogue
-	double part = 0.0;
-	for(int k = tid; k < nc; k += FACE_BLOCK) {
-		const size_t c = (size_t)(c0 + k);
-		const uint4 cl = scl[k];
-		const double ar = sar[k + aoff];
-		const unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
-		const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
-		double r[4] = {0,0,0,0}, integ = 0.0;
-		#pragma unroll
-		for(int j = 0; j < 4; j++) {
-			if(j == 3 && nb[3] == NB_NONE) break;
-			const int e = (int)(cf[j] & 0x7FFFu);
-			double f[4];
-			lds4(fsL + 4*e, f);
-			const double2 sr = *reinterpret_cast<const double2*>(fsR + 4*e);
-			if(cf[j] & 0x8000u) { r[0] += f[0]; r[1] += f[1]; r[2] += f[2]; r[3] += f[3]; integ += sr.y; }
-			else { r[0] -= f[0]; r[1] -= f[1]; r[2] -= f[2]; r[3] -= f[3]; integ += sr.x; }
-		}
-		if(A.epilogue == EP_RESIDUAL) {
-			if(A.accumulate) {
-				double o[4];
-				ld4c(A.res + 4*c, o);
-				for(int v = 0; v < 4; v++) r[v] += o[v];
-			}
-			st4(A.res + 4*c, r);
-			if(A.gettimesteps) A.dtm[c] = ar/integ;
-		} else {
-			const double dt = ar/integ;
-			const double fac = A.cfl*dt/ar;
-			double uo[4];
-			lds4(su + 4*k, uo);
-			uo[0] += fac*r[0]; uo[1] += fac*r[1]; uo[2] += fac*r[2]; uo[3] += fac*r[3];
-			st4(A.unew + 4*c, uo);
-			part += r[3]*r[3]*ar;
-		}
-	}
-	if(A.epilogue == EP_STEP) {
-		// fixed-order block reduction: warp shuffle tree, then thread 0 sums the warp partials in order
-		for(int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-		if((tid & 31) == 0) red_s[tid >> 5] = part;
+		if(have_next && tid < Dn.nh) gnext = M.thalo[Dn.h0 + tid];
+		mbar_wait(bar + 1, par);
 		__syncthreads();
-		if(tid == 0) {
-			double s = 0.0;
-			for(int w = 0; w < FACE_BLOCK/32; w++) s += red_s[w];
-			A.partial[t] = s;
+		// group A buffers are free: the next tile's phase-A inputs (and its stencil/area into the other C buffer)
+		if(tid == 0 && have_next) { fence_proxy_async(); issue_AC(Dn, (int)(par ^ 1u)); }
+
+		// ---- phase B: fluxes, one stream entry per thread and round. The halo rows are needed from entry `ecut`
+		// on: the round that reaches it first waits for the gathers (uniform across the CTA: the test is on the round)
+		bool halo_ready = false;
+		for(int eb = 0; eb < D.ne; eb += FACE_BLOCK) {
+			if(!halo_ready && eb + FACE_BLOCK > D.ecut) { cp_async_wait_all(); __syncthreads(); halo_ready = true; }
+			const int e = eb + tid;
+			if(e >= D.ne) continue;
+			const unsigned LR = sLR[e];
+			if(LR == LR_PAD) continue;
+			const double2 nrm = sn[e];
+			const double len = slen[e];
+			const unsigned L = LR & 0xFFFFu, Rf = LR >> 16;
+			const bool bnd = Rf >= LR_BND;
+			const double nx = nrm.x, ny = nrm.y;
+			const BCEntry &bc = A.gas.bc[Rf & 15u];
+			double sl[4], sr[4];       // face states: conserved (first order) / primitive; MUSCL: cell states
+			if(L < (unsigned)D.nc) lds4(fsL + 4*e, sl);
+			else halo_side_state<RECON>(A, hu, hg, hrc, (int)L - D.nc, MIDS ? M.fgr[D.e0 + e] : make_double2(0,0), sl);
+			if(!bnd) {
+				if(Rf < (unsigned)D.nc) lds4(fsR + 4*e, sr);
+				else halo_side_state<RECON>(A, hu, hg, hrc, (int)Rf - D.nc, MIDS ? M.fgr[D.e0 + e] : make_double2(0,0), sr);
+			}
+			const int gidL = (VISC != VISC_NONE || RECON == FR_MUSCL) ? tile_global(M, t, D.c0, D.nc, L) : 0;
+			const int gidR = (VISC != VISC_NONE || RECON == FR_MUSCL) ? (bnd ? gidL : tile_global(M, t, D.c0, D.nc, Rf)) : 0;
+
+			Side a, bs;
+			double ucl[4], ucr[4];      // conserved cell states for the viscous flux (right = ghost of the cell state)
+			if(RECON == FR_FIRST) {
+				if(bnd) ghost_state(A.gas, bc, sl, nx, ny, sr);
+				a = load_side<true>(A.gas, sl, nx, ny);
+				bs = load_side<true>(A.gas, sr, nx, ny);
+				if(VISC != VISC_NONE) for(int q = 0; q < 4; q++) { ucl[q] = sl[q]; ucr[q] = sr[q]; }
+			}
+			else if(RECON == FR_LINEAR) {
+				a = side_from_prim<true>(A.gas, sl, nx, ny);
+				if(bnd) {
+					const double ul[4] = {a.r, a.mx, a.my, a.E};
+					double ur[4];
+					ghost_state(A.gas, bc, ul, nx, ny, ur);
+					bs = load_side<true>(A.gas, ur, nx, ny);
+				} else bs = side_from_prim<true>(A.gas, sr, nx, ny);
+				if(VISC != VISC_NONE) {
+					ld4(A.u + 4*(size_t)gidL, ucl);
+					if(bnd) ghost_state(A.gas, bc, ucl, nx, ny, ucr);
+					else ld4(A.u + 4*(size_t)gidR, ucr);
+				}
+			}
+			else { // MUSCL with Van Albada limiter: sl, sr are the primitive CELL states
+				const double2 gr = M.fgr[D.e0 + e];
+				const double2 rl = M.rc[gidL];
+				double2 rr;
+				if(bnd) {
+					prim2cons(A.gas, sl, ucl);
+					ghost_state(A.gas, bc, ucl, nx, ny, ucr);
+					cons2prim(A.gas, ucr, sr);
+					rr = make_double2(2.0*gr.x - rl.x, 2.0*gr.y - rl.y);     // ghost centre (aspatial.cpp:98-119)
+				} else {
+					rr = M.rc[gidR];
+					if(VISC != VISC_NONE) { prim2cons(A.gas, sl, ucl); prim2cons(A.gas, sr, ucr); }
+				}
+				const double dx = rr.x - rl.x, dy = rr.y - rl.y;
+				double ga[4], gb[4], pfl[4], pfr[4];
+				ld4(gsrc + 8*(size_t)gidL, ga); ld4(gsrc + 8*(size_t)gidL + 4, gb);
+				{
+					const double gx[4] = {ga[0], ga[2], gb[0], gb[2]}, gy[4] = {ga[1], ga[3], gb[1], gb[3]};
+					for(int q = 0; q < 4; q++) {
+						const double dlr = sr[q] - sl[q];
+						pfl[q] = sl[q] + muscl_term(2.0*(gx[q]*dx + gy[q]*dy) - dlr, dlr);
+					}
+				}
+				a = side_from_prim<true>(A.gas, pfl, nx, ny);
+				if(bnd) {
+					const double ul[4] = {a.r, a.mx, a.my, a.E};
+					double ur[4];
+					ghost_state(A.gas, bc, ul, nx, ny, ur);
+					bs = load_side<true>(A.gas, ur, nx, ny);
+				} else {
+					ld4(gsrc + 8*(size_t)gidR, ga); ld4(gsrc + 8*(size_t)gidR + 4, gb);
+					const double gx[4] = {ga[0], ga[2], gb[0], gb[2]}, gy[4] = {ga[1], ga[3], gb[1], gb[3]};
+					for(int q = 0; q < 4; q++) {
+						const double dlr = sr[q] - sl[q];
+						pfr[q] = sr[q] - muscl_term(2.0*(gx[q]*dx + gy[q]*dy) - dlr, dlr);
+					}
+					bs = side_from_prim<true>(A.gas, pfr, nx, ny);
+				}
+			}
+
+			double f[4];
+			flux_from_sides<FLUX>(A.gas, a, bs, nx, ny, f);
+			for(int q = 0; q < 4; q++) f[q] *= len;
+			double sri = (fabs(a.vn) + a.c)*len;
+			double srj = (fabs(bs.vn) + bs.c)*len;
+
+			if(VISC != VISC_NONE) {
+				const double ul[4] = {a.r, a.mx, a.my, a.E}, ur[4] = {bs.r, bs.mx, bs.my, bs.E};
+				const double2 rl = M.rc[gidL];
+				double2 rr;
+				if(bnd) {
+					const double2 gr = M.fgr[D.e0 + e];
+					rr = make_double2(2.0*gr.x - rl.x, 2.0*gr.y - rl.y);
+				} else rr = M.rc[gidR];
+				double gl[8], grr[8], vf[4];
+				if(RECON != FR_FIRST) {
+					ld4(A.gu + 8*(size_t)gidL, gl); ld4(A.gu + 8*(size_t)gidL + 4, gl+4);
+					if(bnd) for(int q = 0; q < 8; q++) grr[q] = gl[q];
+					else { ld4(A.gu + 8*(size_t)gidR, grr); ld4(A.gu + 8*(size_t)gidR + 4, grr+4); }
+				}
+				viscous_face_flux<RECON != FR_FIRST, VISC == VISC_CONST>(A.gas, nx, ny, rl.x, rl.y, rr.x, rr.y,
+					ucl, ucr, gl, grr, ul, ur, vf);
+				for(int q = 0; q < 4; q++) f[q] += vf[q]*len;
+				const double mui = VISC == VISC_CONST ? 1.0/A.gas.Reinf : viscosity_cons(A.gas, ul);
+				const double muj = VISC == VISC_CONST ? 1.0/A.gas.Reinf : viscosity_cons(A.gas, ur);
+				const double coi = fmax(4.0/(3.0*ul[0]), A.gas.g/ul[0]);
+				const double coj = fmax(4.0/(3.0*ur[0]), A.gas.g/ur[0]);
+				sri += coi*mui/A.gas.Pr*len*len/M.area[gidL];
+				if(!bnd) srj += coj*muj/A.gas.Pr*len*len/M.area[gidR];
+			}
+			// the entry's slots now carry its flux and the two spectral radii
+			*reinterpret_cast<double2*>(fsL + 4*e) = make_double2(f[0], f[1]);
+			*reinterpret_cast<double2*>(fsL + 4*e + 2) = make_double2(f[2], f[3]);
+			*reinterpret_cast<double2*>(fsR + 4*e) = make_double2(sri, srj);
 		}
+		if(!halo_ready) cp_async_wait_all();
+		__syncthreads();
+		// group B buffers are free: the next tile's entry metadata and halo rows
+		if(have_next) {
+			if(tid == 0) { fence_proxy_async(); issue_B(Dn); }
+			issue_halo(Dn.nh, gnext);
+		}
+
+		// ---- phase C: per-cell sums in local-face order, then the epilogue
+		double part = 0.0;
+		for(int k = tid; k < D.nc; k += FACE_BLOCK) {
+			const size_t c = (size_t)(D.c0 + k);
+			const uint4 cl = scl[k];
+			const double ar = sar[k + aoff];
+			const unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
+			const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
+			// all rows are fetched before the sums start (no branch between the loads); a missing fourth face reads
+			// entry 0 with weight zero. fma(+-1, f, r) is the exact add / subtract, in local-face order.
+			double r[4] = {0,0,0,0}, integ = 0.0;
+			double f[4][4];
+			double2 sr[4];
+			double sg_[4];
+			#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				const bool have = !(j == 3 && nb[3] == NB_NONE);
+				const int e = have ? (int)(cf[j] & 0x7FFFu) : 0;
+				lds4(fsL + 4*e, f[j]);
+				sr[j] = *reinterpret_cast<const double2*>(fsR + 4*e);
+				sg_[j] = !have ? 0.0 : ((cf[j] & 0x8000u) ? 1.0 : -1.0);
+			}
+			#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				#pragma unroll
+				for(int v = 0; v < 4; v++) r[v] = fma(sg_[j], f[j][v], r[v]);
+				integ += sg_[j] > 0.0 ? sr[j].y : (sg_[j] < 0.0 ? sr[j].x : 0.0);
+			}
+			if(A.epilogue == EP_RESIDUAL) {
+				if(A.accumulate) {
+					double o[4];
+					ld4c(A.res + 4*c, o);
+					for(int v = 0; v < 4; v++) r[v] += o[v];
+				}
+				st4(A.res + 4*c, r);
+				if(A.gettimesteps) A.dtm[c] = ar/integ;
+			} else {
+				const double dt = ar/integ;
+				const double fac = A.cfl*dt/ar;
+				double uo[4];
+				if(k == tid) { for(int q = 0; q < 4; q++) uo[q] = uc0[q]; } else ld4(A.u + 4*c, uo);
+				uo[0] += fac*r[0]; uo[1] += fac*r[1]; uo[2] += fac*r[2]; uo[3] += fac*r[3];
+				st4(A.unew + 4*c, uo);
+				part += r[3]*r[3]*ar;
+			}
+		}
+		if(A.epilogue == EP_STEP) {
+			// fixed-order block reduction: warp shuffle tree, then thread 0 sums the warp partials in order
+			for(int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+			if((tid & 31) == 0) red_s[tid >> 5] = part;
+			__syncthreads();
+			if(tid == 0) {
+				double s = 0.0;
+				for(int w = 0; w < FACE_BLOCK/32; w++) s += red_s[w];
+				A.partial[t] = s;
+			}
+		}
+		// phase C reads the flux slots that the next tile's phase A overwrites
+		__syncthreads();
+		t = tn; D = Dn;
 	}
 }
 
@@ -406,7 +447,16 @@ static int launch_one(const FaceArgs &a, cudaStream_t s)
 			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if(ea != cudaSuccess) return cuda_fail(ea, "face_kernel smem attribute", __FILE__, __LINE__);
 	}
-	face_kernel<FLUX,RECON,VISC><<<a.m.ntile, FACE_BLOCK, smem, s>>>(a);
+	if(a.m.HMAX > FACE_BLOCK) { set_error("face kernel: halo capacity exceeds the CTA size"); return FVG_ERR_INVALID; }
+	static int ctas = 0;                      // persistent CTAs: as many as are resident at once
+	if(ctas == 0) {
+		int dev = 0, sms = 0, per = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, face_kernel<FLUX,RECON,VISC>, FACE_BLOCK, smem);
+		ctas = sms*(per > 0 ? per : 1);
+	}
+	face_kernel<FLUX,RECON,VISC><<<a.m.ntile < ctas ? a.m.ntile : ctas, FACE_BLOCK, smem, s>>>(a);
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "face_kernel launch", __FILE__, __LINE__);
 	return 0;
