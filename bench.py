@@ -93,11 +93,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_case(cells, numerics, tile, rank=0, world=1):
+def build_case(cells, numerics, tile):
     """Host mesh (Hilbert-ordered, so the device numbering is the identity), its arrays and the state."""
     from fvens_b200 import lib, synth
     nx, ny = lattice_for(cells)
-    arrs = synth.bump_channel(nx, ny, seed=12345 + rank)
+    arrs = synth.bump_channel(nx, ny, seed=12345)
     um = lib.UMesh.from_arrays(*arrs)
     perm = um.hilbert_ordering()          # the reference's `-mesh_reorder` step, with a locality order
     um.reorder_cells(perm)
@@ -152,7 +152,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     flux, grad, recon, lp = NUMERICS[args.numerics][:4]
-    workload = (f"synthetic hybrid tri/quad Gaussian-bump channel, {args.cells/1e6:g}M cells per GPU, "
+    workload = (f"synthetic hybrid tri/quad Gaussian-bump channel, {args.cells/1e6:g}M cells, "
                 f"{flux}+{grad}+{recon} second-order residual with local time steps (BASELINE configs[2] mesh, "
                 f"north-star headline numerics)")
 
@@ -180,24 +180,46 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         g.build(quiet=True)
     if world > 1:
         dist.barrier()
     lib.load()
 
-    um, arrs, u, (nx, ny) = build_case(args.cells, args.numerics, args.tile, rank, world)
-    dm = lib.DeviceMesh(um, reorder="none", tile_cells=args.tile, device=local_rank)
+    # every rank builds the same global mesh; with N > 1 it is partitioned (strong scaling of the 10M-cell case)
+    um, arrs, u, (nx, ny) = build_case(args.cells, args.numerics, args.tile)
     phys = lib.make_physics(1.4, MINF, 288.15, 5000.0, 0.72, 0.0)
-    fl = lib.FlowFV(dm, phys, flux, grad, recon, lp, True, 0, BCS)
-    nc, nf = um.nelem, um.naface
-    du = torch.from_numpy(u).cuda()
-    res = torch.empty_like(du)
-    dtm = torch.empty(nc, dtype=torch.float64, device="cuda")
+    nc_glob, nf_glob = um.nelem, um.naface
     stream = torch.cuda.current_stream().cuda_stream
+    num = dict(flux=flux, gradient=grad, reconstruction=recon, limiter_param=lp, order2=True)
+    if world == 1:
+        dm = lib.DeviceMesh(um, reorder="none", tile_cells=args.tile, device=local_rank)
+        fl = lib.FlowFV(dm, phys, bcs=BCS, **num)
+        nc = nc_glob
+        du = torch.from_numpy(u).cuda()
+        halo_launches = 0
+
+        def evaluate():
+            fl.compute_residual(du, res, True, dtm, accumulate=False, stream=stream)
+    else:
+        from fvens_b200.dist import DistFlow
+        part = lib.partition_sfc(um, world)
+        df = DistFlow(um, part, rank, world, phys, dev, reorder="none", tile_cells=args.tile, bcs=BCS, **num)
+        dm, fl = df.dmesh, df.flow
+        nc = df.ncell
+        ids = torch.from_numpy(df.global_ids.astype(np.int64))
+        du = torch.zeros((df.ncell + df.nghost, 4), dtype=torch.float64, device=dev)
+        du[:nc] = torch.from_numpy(u[ids[:nc].numpy()]).to(dev)
+        halo_launches = 2          # pack kernels per evaluation (state rows, gradient rows)
+
+        def evaluate():
+            df.residual(du, res, dtm, gettimesteps=True, exchange_state=True)
+    res = torch.empty((nc, 4), dtype=torch.float64, device=dev)
+    dtm = torch.empty(nc, dtype=torch.float64, device=dev)
 
     def barrier():
         if world > 1:
@@ -205,9 +227,10 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        fl.compute_residual(du, res, True, dtm, accumulate=False, stream=stream)
+        evaluate()
     barrier()
-    fl.timing(True)
+    if world == 1:
+        fl.timing(True)
     launches0 = fl.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -216,52 +239,79 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        fl.compute_residual(du, res, True, dtm, accumulate=False, stream=stream)
+        evaluate()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    launches = fl.launch_count() - launches0
-    ms_cell, ms_face, ntimed = fl.timing(False)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    launches = fl.launch_count() - launches0 + halo_launches*args.steps
+    ms_cell, ms_face, ntimed = fl.timing(False) if world == 1 else (0.0, 0.0, 0)
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item()/args.steps
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = tmax.item()/args.steps
 
     # sanity: the timed output is a real residual (finite, non-trivial)
     chk = float(res.abs().max().item())
     assert np.isfinite(chk) and chk > 0.0
 
-    # end to end through the host-buffer entry point, pinned host memory
-    hu = torch.from_numpy(u).pin_memory()
+    # end to end through host buffers (pinned): H2D of the state rows, kernels (+ halo), D2H of residual and dt
+    if world == 1:
+        hu = torch.from_numpy(u).pin_memory()
+    else:
+        hu = torch.from_numpy(u[ids[:nc].numpy()]).pin_memory()
     hres = torch.empty((nc, 4), dtype=torch.float64).pin_memory()
     hdt = torch.empty(nc, dtype=torch.float64).pin_memory()
+
+    def evaluate_e2e():
+        if world == 1:
+            fl.compute_residual_host(hu.data_ptr(), hres.data_ptr(), True, hdt.data_ptr(), accumulate=False)
+        else:
+            du[:nc].copy_(hu, non_blocking=True)
+            evaluate()
+            hres.copy_(res, non_blocking=True)
+            hdt.copy_(dtm, non_blocking=True)
+            torch.cuda.synchronize()
     for _ in range(2):
-        fl.compute_residual_host(hu.data_ptr(), hres.data_ptr(), True, hdt.data_ptr(), accumulate=False)
+        evaluate_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        fl.compute_residual_host(hu.data_ptr(), hres.data_ptr(), True, hdt.data_ptr(), accumulate=False)
+        evaluate_e2e()
     barrier()
-    t_e2e = torch.tensor([(time.perf_counter()-t0)/args.e2e_steps], dtype=torch.float64, device="cuda")
+    t_e2e = torch.tensor([(time.perf_counter()-t0)/args.e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     assert torch.equal(hres, res.cpu())
 
     # fused pseudo-time step (residual + dt + update + norm), device resident
-    u2 = du.clone()
-    n2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    n2 = torch.zeros(1, dtype=torch.float64, device=dev)
+    nstep = max(5, args.steps//3)
+    if world == 1:
+        u2 = du.clone()
+
+        def step():
+            fl.euler_step(u2, 0.5, n2, stream=stream)
+    else:
+        cur = [du.clone(), torch.zeros_like(du)]
+
+        def step():
+            df.euler_step(cur[0], cur[1], 0.5, n2)
+            dist.all_reduce(n2)
+            cur.reverse()
     for _ in range(3):
-        fl.euler_step(u2, 0.5, n2, stream=stream)
+        step()
     barrier()
     s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
     s0.record()
-    nstep = max(5, args.steps//3)
     for _ in range(nstep):
-        fl.euler_step(u2, 0.5, n2, stream=stream)
+        step()
     s1.record()
     barrier()
-    ms_euler = s0.elapsed_time(s1)/nstep
+    teu = torch.tensor([s0.elapsed_time(s1)/nstep], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(teu, op=dist.ReduceOp.MAX)
+    ms_euler = teu.item()
 
     if rank != 0:
         if world > 1:
@@ -275,35 +325,52 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    bA, bB = algorithmic_bytes(args.numerics, nc, nf)
-    t_face = ms_face/max(ntimed, 1)*1e-3
-    t_cell = ms_cell/max(ntimed, 1)*1e-3
-    ach_face = bB/t_face/1e9
-    gfaces = world*nf/(ms_step*1e-3)/1e9
+    bA, bB = algorithmic_bytes(args.numerics, nc_glob, nf_glob)
+    gfaces = nf_glob/(ms_step*1e-3)/1e9
     info = dm.info
+    traffic = None
+    try:        # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"face_kernel:{args.numerics}:{args.tile}")
+    except Exception:
+        pass
     line = {
         "metric": "Gfaces/s", "value": gfaces, "unit": "Gfaces/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "cells_per_gpu": nc, "faces_per_gpu": nf, "lattice": [nx, ny],
-                   "tile_cells": info.tile_cells, "cut_face_duplicates": info.ncut_dup, "colours": info.max_colours,
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent shards (no halo yet)",
-                   "l2": "inputs (320 MB state + 640 MB gradients + mesh) exceed the 126 MB L2; no explicit flush"},
-        "residual_evals_per_s": world*1e3/ms_step,
-        "residual_roofline_frac": (bA + bB)/(ms_step*1e-3)/1e9/peak,
-        "euler_step": {"ms_per_step": ms_euler, "Gfaces/s": nf/(ms_euler*1e-3)/1e9,
-                       "note": "fused residual + local dt + forward-Euler update + energy-residual norm"},
-        "kernels_ms": {"gradient_limiter_pass": t_cell*1e3, "face_pass": t_face*1e3, "timed_evals": ntimed},
-        "roofline": {"bound": "hbm", "kernel": "face_kernel (reconstruct + flux + spectral radius + accumulate)",
-                     "achieved": ach_face, "peak": peak, "unit": "GB/s", "frac": ach_face/peak, "traffic": None,
-                     "algorithmic_bytes_per_launch": bB, "peak_source": peak_src,
-                     "cell_pass": {"achieved": bA/t_cell/1e9, "frac": bA/t_cell/1e9/peak, "algorithmic_bytes_per_launch": bA}},
-        "e2e": {"value": world*nf/t_e2e.item()/1e9, "unit": "Gfaces/s", "ms_per_step": t_e2e.item()*1e3,
+        "config": {"workload": workload, "cells": nc_glob, "faces": nf_glob, "lattice": [nx, ny],
+                   "cells_on_rank0": nc, "ghost_cells_on_rank0": int(info.nghost),
+                   "tile_cells": info.tile_cells, "cut_face_duplicates_rank0": info.ncut_dup,
+                   "parallelism": "single GPU" if world == 1 else
+                   f"{world} GPUs, Hilbert-curve partition, one ghost layer; per evaluation: state halo, gradient pass, "
+                   f"gradient halo, face pass (NCCL all-to-all with row splits)",
+                   "l2": "inputs (320 MB state + 640 MB gradients + 3 GB mesh) exceed the 126 MB L2; no explicit flush"},
+        "residual_evals_per_s": 1e3/ms_step,
+        "residual_roofline_frac": (bA + bB)/(ms_step*1e-3)/1e9/(peak*world),
+        "euler_step": {"ms_per_step": ms_euler, "Gfaces/s": nf_glob/(ms_euler*1e-3)/1e9,
+                       "note": "fused residual + local dt + forward-Euler update + energy-residual norm"
+                               + (" + all-reduce of the norm" if world > 1 else "")},
+        "e2e": {"value": nf_glob/t_e2e.item()/1e9, "unit": "Gfaces/s", "ms_per_step": t_e2e.item()*1e3,
                 "h2d_bytes_per_step": 32*nc, "d2h_bytes_per_step": 40*nc,
-                "note": "fvg_residual_host on pinned host buffers: H2D u, kernels, D2H residual + dt"},
+                "note": "pinned host buffers: H2D u, kernels" + (" + halos" if world > 1 else "") + ", D2H residual + dt"
+                        + (" (bytes are per rank)" if world > 1 else " (fvg_residual_host)")},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if world == 1:
+        t_face = ms_face/max(ntimed, 1)*1e-3
+        t_cell = ms_cell/max(ntimed, 1)*1e-3
+        ach_face = bB/t_face/1e9
+        line["kernels_ms"] = {"gradient_limiter_pass": t_cell*1e3, "face_pass": t_face*1e3, "timed_evals": ntimed}
+        line["roofline"] = {"bound": "hbm", "kernel": "face_kernel (reconstruct + flux + spectral radius + accumulate)",
+                            "achieved": ach_face, "peak": peak, "unit": "GB/s", "frac": ach_face/peak, "traffic": traffic,
+                            "algorithmic_bytes_per_launch": bB, "peak_source": peak_src,
+                            "cell_pass": {"achieved": bA/t_cell/1e9, "frac": bA/t_cell/1e9/peak,
+                                          "algorithmic_bytes_per_launch": bA}}
+    else:
+        ach = (bA + bB)/world/(ms_step*1e-3)/1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "whole evaluation per GPU (cell pass + face pass + halos)",
+                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach/peak, "traffic": None,
+                            "algorithmic_bytes_per_launch": (bA + bB)/world, "peak_source": peak_src}
     if not args.no_cpu_baseline and world == 1:
         gf, ms, ci = cpu_reference(args.cpu_cells, args.numerics, 6, 2)
         line["cpu_baseline"] = {"value": gf, "unit": "Gfaces/s", "cores": ci["cores"], "kind": "port",
