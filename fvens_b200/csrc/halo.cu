@@ -1,0 +1,240 @@
+/* Peer-memory halo exchange over NVLink / NVSwitch: every rank owns a WINDOW (receive areas + arrival flags in
+ * one cudaMalloc allocation) that the other ranks of the box map through CUDA IPC. An exchange is two small
+ * kernels and no host round trip, no collective library:
+ *   send  packs the rows each peer needs (device-mesh send lists) and stores them straight into that peer's
+ *         window, then releases a sequence number into the peer's flag word (st.release.sys);
+ *   recv  acquires the flags of the peers it expects rows from and copies the rows into the ghost block of the
+ *         caller's array.
+ * Replaces the reference's L2TraceVector::updateSharedFacesBegin/End (src/linalg/tracevector.cpp:214-325, MPI
+ * Isend/Irecv of packed face states) and its VecGhostUpdateBegin/End calls (src/ode/aodesolver.cpp:212,247;
+ * src/spatial/flow_spatial.cpp:711-729). Receive areas are double-buffered by sequence parity, so a rank may run
+ * one exchange ahead of a neighbour without overwriting rows the neighbour has not consumed yet (a rank cannot
+ * get two ahead: its next receive needs the neighbour's next send).
+ */
+#include "engine.hpp"
+#include <cstring>
+#include <memory>
+
+struct fvg_halo {
+	fvg_mesh *mesh = nullptr;
+	int nranks = 1, rank = 0, max_width = 0;
+	size_t area_doubles = 0;                 ///< doubles per parity buffer (nghost * max_width)
+	unsigned char *window = nullptr;         ///< local window: header (nranks flags + 1 error word, uint64, padded to 256 B), then [2][area] doubles
+	size_t hdr = 0;                          ///< header bytes (the same on every rank)
+	std::vector<unsigned long long> peer_area;   ///< area_doubles of each peer's window (its parity-buffer stride)
+	unsigned long long *d_peer_area = nullptr;
+	std::vector<unsigned char*> peer;        ///< mapped windows of the peers (nullptr for self / ranks without traffic)
+	std::vector<int> send_off, recv_off;     ///< row offsets of each peer's block in my send list / my ghost range
+	std::vector<int> peer_row0;              ///< row offset of MY block inside peer r's ghost range
+	// device copies of the per-peer tables
+	unsigned char **d_peer = nullptr;
+	int *d_send_off = nullptr, *d_recv_off = nullptr, *d_peer_row0 = nullptr;
+	unsigned *d_arrive = nullptr;            ///< per-peer CTA arrival counters of the send kernel
+	unsigned long long seq = 0;
+	bool connected = false;
+};
+
+namespace fvg {
+
+constexpr int HALO_CTAS_PER_PEER = 4;
+constexpr int HALO_THREADS = 512;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+	asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+/** grid = nranks * HALO_CTAS_PER_PEER. CTAs [r*K, (r+1)*K) serve peer r: they copy rows send_idx[send_off[r] ..
+ * send_off[r+1]) of src into the peer's window at row peer_row0[r], 16 bytes per store; the last of the K CTAs to
+ * finish publishes the sequence number in the peer's flag word for this rank. */
+__global__ void __launch_bounds__(HALO_THREADS)
+halo_send_kernel(const double *__restrict__ src, const int *__restrict__ send_idx, const int *__restrict__ send_off,
+                 const int *__restrict__ peer_row0, unsigned char *const *__restrict__ peer, unsigned *__restrict__ arrive,
+                 const unsigned long long *__restrict__ peer_area, const int width, const size_t hdr, const int rank,
+                 const unsigned long long seq)
+{
+	const int r = blockIdx.x/HALO_CTAS_PER_PEER, sub = blockIdx.x - r*HALO_CTAS_PER_PEER;
+	const int k0 = send_off[r], nrow = send_off[r+1] - k0;
+	if(nrow == 0 || peer[r] == nullptr) return;
+	double *const dst = reinterpret_cast<double*>(peer[r] + hdr) + (seq & 1ull)*peer_area[r] + (size_t)peer_row0[r]*width;
+	const int w2 = width/2;                   // widths are even (4 or 8): rows move as 16-byte pieces
+	const long long tot = (long long)nrow*w2;
+	for(long long q = (long long)sub*HALO_THREADS + threadIdx.x; q < tot; q += (long long)HALO_CTAS_PER_PEER*HALO_THREADS) {
+		const int row = (int)(q/w2), c = (int)(q - (long long)row*w2);
+		const double2 v = *reinterpret_cast<const double2*>(src + (size_t)send_idx[k0 + row]*width + 2*c);
+		*reinterpret_cast<double2*>(dst + (size_t)row*width + 2*c) = v;
+	}
+	__threadfence_system();
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		const unsigned prev = atomicAdd(&arrive[r], 1u);
+		if(prev == HALO_CTAS_PER_PEER - 1) {
+			arrive[r] = 0;
+			__threadfence_system();
+			st_release_sys(reinterpret_cast<unsigned long long*>(peer[r]) + rank, seq);
+		}
+	}
+}
+
+/** Waits until every peer that sends rows has published `seq`, then copies the window's rows into the ghost block
+ * of dst (rows [ncell, ncell + nghost)). A bounded spin: if a peer never arrives the error word is set and the copy
+ * proceeds (the caller reads the status; nothing hangs). */
+__global__ void __launch_bounds__(HALO_THREADS)
+halo_recv_kernel(double *__restrict__ dst, const unsigned char *__restrict__ window, const int *__restrict__ recv_off,
+                 const int ncell, const int nghost, const int width, const size_t area_doubles, const size_t hdr, const int nranks,
+                 const unsigned long long seq, const long long spin_limit)
+{
+	const unsigned long long *const flags = reinterpret_cast<const unsigned long long*>(window);
+	unsigned long long *const err = const_cast<unsigned long long*>(flags) + nranks;
+	if((int)threadIdx.x < nranks) {
+		const int r = threadIdx.x;
+		if(recv_off[r+1] > recv_off[r]) {
+			long long spins = 0;
+			while(ld_acquire_sys(flags + r) < seq) {
+				__nanosleep(64);
+				if(++spins > spin_limit) { atomicExch(err, seq); break; }
+			}
+		}
+	}
+	__syncthreads();
+	const double *const srcw = reinterpret_cast<const double*>(window + hdr) + (seq & 1ull)*area_doubles;
+	const long long tot = (long long)nghost*width/2;
+	double2 *const out = reinterpret_cast<double2*>(dst + (size_t)ncell*width);
+	const double2 *const in = reinterpret_cast<const double2*>(srcw);
+	for(long long q = (long long)blockIdx.x*HALO_THREADS + threadIdx.x; q < tot; q += (long long)gridDim.x*HALO_THREADS)
+		out[q] = in[q];
+}
+
+} // namespace fvg
+
+using namespace fvg;
+
+extern "C" {
+
+int fvg_halo_create(fvg_mesh *mesh, int max_width, fvg_halo **out)
+{
+	if(!mesh || !out || max_width < 2 || (max_width & 1)) { set_error("fvg_halo_create: bad argument (width must be even)"); return FVG_ERR_INVALID; }
+	*out = nullptr;
+	if(mesh->device < 0) { set_error("fvg_halo_create: host-only mesh"); return FVG_ERR_INVALID; }
+	FVG_CUDA(cudaSetDevice(mesh->device));
+	std::unique_ptr<fvg_halo> h(new fvg_halo);
+	h->mesh = mesh; h->nranks = mesh->nranks; h->rank = mesh->rank; h->max_width = max_width;
+	h->area_doubles = (size_t)std::max(mesh->d.nghost, 1)*max_width;
+	h->hdr = (((size_t)h->nranks + 1)*sizeof(unsigned long long) + 255)/256*256;
+	const size_t bytes = h->hdr + 2*h->area_doubles*sizeof(double);
+	FVG_CUDA(cudaMalloc((void**)&h->window, bytes));
+	FVG_CUDA(cudaMemset(h->window, 0, bytes));
+	h->send_off.assign(h->nranks + 1, 0); h->recv_off.assign(h->nranks + 1, 0);
+	for(int r = 0; r < h->nranks; r++) {
+		h->send_off[r+1] = h->send_off[r] + mesh->send_counts[r];
+		h->recv_off[r+1] = h->recv_off[r] + mesh->recv_counts[r];
+	}
+	FVG_CUDA(cudaDeviceSynchronize());
+	*out = h.release();
+	return 0;
+}
+
+int fvg_halo_ipc_handle(fvg_halo *h, void *handle64)
+{
+	if(!h || !handle64) { set_error("fvg_halo_ipc_handle: null argument"); return FVG_ERR_INVALID; }
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	cudaIpcMemHandle_t mh;
+	FVG_CUDA(cudaIpcGetMemHandle(&mh, h->window));
+	std::memcpy(handle64, &mh, 64);
+	return 0;
+}
+
+int fvg_halo_connect(fvg_halo *h, const void *handles, const int *all_recv_counts)
+{
+	if(!h || !handles || !all_recv_counts) { set_error("fvg_halo_connect: null argument"); return FVG_ERR_INVALID; }
+	if(h->connected) { set_error("fvg_halo_connect: already connected"); return FVG_ERR_INVALID; }
+	FVG_CUDA(cudaSetDevice(h->mesh->device));
+	const int n = h->nranks;
+	h->peer.assign(n, nullptr); h->peer_row0.assign(n, 0); h->peer_area.assign(n, 0);
+	for(int r = 0; r < n; r++) {
+		long long ng = 0;
+		for(int q = 0; q < n; q++) ng += all_recv_counts[(size_t)r*n + q];
+		h->peer_area[r] = (unsigned long long)std::max(ng, 1ll)*h->max_width;
+		// my block inside peer r's ghost range starts after the blocks of the ranks below me
+		int off = 0;
+		for(int q = 0; q < h->rank; q++) off += all_recv_counts[(size_t)r*n + q];
+		h->peer_row0[r] = off;
+		if(r == h->rank) continue;
+		if(all_recv_counts[(size_t)r*n + h->rank] != h->mesh->send_counts[r]) {
+			set_error("fvg_halo_connect: send/receive counts of two ranks disagree"); return FVG_ERR_COMM;
+		}
+		if(h->mesh->send_counts[r] == 0) continue;
+		cudaIpcMemHandle_t mh;
+		std::memcpy(&mh, static_cast<const unsigned char*>(handles) + 64*(size_t)r, 64);
+		void *p = nullptr;
+		const cudaError_t e = cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess);
+		if(e != cudaSuccess) { cuda_fail(e, "cudaIpcOpenMemHandle", __FILE__, __LINE__); return FVG_ERR_COMM; }
+		h->peer[r] = static_cast<unsigned char*>(p);
+	}
+	FVG_CUDA(cudaMalloc((void**)&h->d_peer, sizeof(unsigned char*)*n));
+	FVG_CUDA(cudaMalloc((void**)&h->d_send_off, sizeof(int)*(n+1)));
+	FVG_CUDA(cudaMalloc((void**)&h->d_recv_off, sizeof(int)*(n+1)));
+	FVG_CUDA(cudaMalloc((void**)&h->d_peer_row0, sizeof(int)*n));
+	FVG_CUDA(cudaMalloc((void**)&h->d_arrive, sizeof(unsigned)*n));
+	FVG_CUDA(cudaMalloc((void**)&h->d_peer_area, sizeof(unsigned long long)*n));
+	FVG_CUDA(cudaMemcpy(h->d_peer_area, h->peer_area.data(), sizeof(unsigned long long)*n, cudaMemcpyHostToDevice));
+	FVG_CUDA(cudaMemcpy(h->d_peer, h->peer.data(), sizeof(unsigned char*)*n, cudaMemcpyHostToDevice));
+	FVG_CUDA(cudaMemcpy(h->d_send_off, h->send_off.data(), sizeof(int)*(n+1), cudaMemcpyHostToDevice));
+	FVG_CUDA(cudaMemcpy(h->d_recv_off, h->recv_off.data(), sizeof(int)*(n+1), cudaMemcpyHostToDevice));
+	FVG_CUDA(cudaMemcpy(h->d_peer_row0, h->peer_row0.data(), sizeof(int)*n, cudaMemcpyHostToDevice));
+	FVG_CUDA(cudaMemset(h->d_arrive, 0, sizeof(unsigned)*n));
+	h->connected = true;
+	return 0;
+}
+
+int fvg_halo_send(fvg_halo *h, const double *d_arr, int width, void *stream)
+{
+	if(!h || !d_arr || !h->connected) { set_error("fvg_halo_send: not connected / null argument"); return FVG_ERR_INVALID; }
+	if(width < 2 || (width & 1) || width > h->max_width) { set_error("fvg_halo_send: width must be even and within the window's width"); return FVG_ERR_INVALID; }
+	h->seq++;
+	if(h->mesh->d.nsend == 0) return 0;
+	halo_send_kernel<<<h->nranks*HALO_CTAS_PER_PEER, HALO_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+		d_arr, h->mesh->d.send_idx, h->d_send_off, h->d_peer_row0, h->d_peer, h->d_arrive, h->d_peer_area, width, h->hdr,
+		h->rank, h->seq);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "halo_send launch", __FILE__, __LINE__);
+	return 0;
+}
+
+int fvg_halo_recv(fvg_halo *h, double *d_arr, int width, void *stream)
+{
+	if(!h || !d_arr || !h->connected) { set_error("fvg_halo_recv: not connected / null argument"); return FVG_ERR_INVALID; }
+	if(width < 2 || (width & 1) || width > h->max_width) { set_error("fvg_halo_recv: width must be even and within the window's width"); return FVG_ERR_INVALID; }
+	const int ng = h->mesh->d.nghost;
+	if(ng == 0) return 0;
+	const int nblk = std::max(1, std::min(16, (ng*width/2 + HALO_THREADS - 1)/HALO_THREADS));
+	halo_recv_kernel<<<nblk, HALO_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+		d_arr, h->window, h->d_recv_off, h->mesh->d.ncell, ng, width, h->area_doubles, h->hdr, h->nranks, h->seq,
+		/* about two seconds of 64 ns naps */ 30000000ll);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "halo_recv launch", __FILE__, __LINE__);
+	return 0;
+}
+
+int fvg_halo_status(fvg_halo *h, unsigned long long *h_timed_out_seq)
+{
+	if(!h || !h_timed_out_seq) { set_error("fvg_halo_status: null argument"); return FVG_ERR_INVALID; }
+	FVG_CUDA(cudaMemcpy(h_timed_out_seq, h->window + (size_t)h->nranks*sizeof(unsigned long long),
+	                    sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+void fvg_halo_destroy(fvg_halo *h)
+{
+	if(!h) return;
+	for(unsigned char *p : h->peer) if(p) cudaIpcCloseMemHandle(p);
+	cudaFree(h->d_peer); cudaFree(h->d_send_off); cudaFree(h->d_recv_off); cudaFree(h->d_peer_row0); cudaFree(h->d_arrive); cudaFree(h->d_peer_area);
+	cudaFree(h->window);
+	delete h;
+}
+
+} // extern "C"

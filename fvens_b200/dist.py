@@ -10,6 +10,8 @@ The ghost block of a device-ordered array is ordered by source rank, and each ra
 needs in that peer's ghost order, so one all-to-all with row splits moves a whole exchange and the receive
 buffer IS the ghost block (no unpack kernel).
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -70,6 +72,41 @@ class HaloExchange:
             req.wait()
 
 
+class PeerHaloExchange:
+    """Halo exchange through peer-mapped windows over NVLink (fvg_halo_*): two small kernels per exchange, no
+    collective library and no host synchronisation. torch.distributed is used once, at set-up, to all-gather the
+    64-byte IPC handles and the receive counts."""
+
+    def __init__(self, dmesh, device, group=None, max_width=8):
+        self.dmesh = dmesh
+        self.win = lib.PeerHaloWindow(dmesh, max_width)
+        world = dist.get_world_size(group)
+        _, rc, _ = dmesh.halo_lists()
+        mine = torch.zeros(64 + 4*world, dtype=torch.uint8)
+        mine[:64] = torch.frombuffer(bytearray(self.win.handle()), dtype=torch.uint8)
+        mine[64:] = torch.from_numpy(np.ascontiguousarray(rc, dtype=np.int32).view(np.uint8))
+        mine = mine.to(device)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine, group=group)
+        every = [e.cpu().numpy() for e in every]
+        handles = [e[:64].tobytes() for e in every]
+        counts = np.stack([e[64:].view(np.int32) for e in every])
+        self.win.connect(handles, counts)
+        dist.barrier(group=group)
+
+    def exchange(self, arr):
+        """arr: [ncell+nghost, width] device-ordered; fills the ghost rows from their owners."""
+        s = torch.cuda.current_stream().cuda_stream
+        self.win.send(arr, arr.shape[1], stream=s)
+        self.win.recv(arr, arr.shape[1], stream=s)
+
+    def send(self, arr):
+        self.win.send(arr, arr.shape[1], stream=torch.cuda.current_stream().cuda_stream)
+
+    def recv(self, arr):
+        self.win.recv(arr, arr.shape[1], stream=torch.cuda.current_stream().cuda_stream)
+
+
 class DistFlow:
     """FlowFV on one rank's subdomain + the halo exchanges. Arrays are device-ordered [ncell+nghost, .]."""
 
@@ -78,7 +115,10 @@ class DistFlow:
         self.dmesh = lib.DeviceMesh(umesh, reorder=reorder, tile_cells=tile_cells, device=torch.device(device).index or 0,
                                     cell_rank=cell_rank, rank=rank, nranks=nranks)
         self.flow = lib.FlowFV(self.dmesh, phys, **numerics)
-        self.halo = HaloExchange(self.dmesh, device, group)
+        # transport: peer-mapped windows over NVLink on GPUs (FVG_HALO=nccl selects the all-to-all), gloo on the CPU
+        use_peer = torch.device(device).type == "cuda" and nranks > 1 and os.environ.get("FVG_HALO", "peer") == "peer"
+        self.halo = PeerHaloExchange(self.dmesh, device, group) if use_peer else HaloExchange(self.dmesh, device, group)
+        self.halo_kind = "peer" if use_peer else "collective"
         self.ncell, self.nghost = self.dmesh.ncell, self.dmesh.nghost
         n = self.ncell + self.nghost
         num = self.flow.num

@@ -404,6 +404,50 @@ def freestream(phys):
     return out
 
 
+class PeerHaloWindow:
+    """fvg_halo: this rank's peer-memory halo window (see include/fvens_b200.h). The caller all-gathers the
+    handles and receive counts (any transport) and passes them to connect()."""
+
+    def __init__(self, dmesh, max_width=8):
+        self.dmesh = dmesh
+        h = C.c_void_p()
+        check(load().fvg_halo_create(dmesh._h, int(max_width), C.byref(h)))
+        self._h = h
+
+    def handle(self):
+        buf = (C.c_ubyte*64)()
+        check(load().fvg_halo_ipc_handle(self._h, buf))
+        return bytes(buf)
+
+    def connect(self, handles, all_recv_counts):
+        """handles: nranks x 64 bytes; all_recv_counts: [nranks, nranks] int array (row r = rank r's recv counts)."""
+        hb = b"".join(handles)
+        arc = np.ascontiguousarray(all_recv_counts, dtype=np.int32)
+        check(load().fvg_halo_connect(self._h, C.c_char_p(hb), _ip(arc)))
+
+    def send(self, arr, width, stream=None):
+        check(load().fvg_halo_send(self._h, _ptr(arr), int(width), C.c_void_p(stream or 0)))
+
+    def recv(self, arr, width, stream=None):
+        check(load().fvg_halo_recv(self._h, _ptr(arr), int(width), C.c_void_p(stream or 0)))
+
+    def status(self):
+        v = C.c_ulonglong(0)
+        check(load().fvg_halo_status(self._h, C.byref(v)))
+        return int(v.value)
+
+    def close(self):
+        if self._h:
+            load().fvg_halo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def partition_sfc(umesh, nranks):
     """cell -> rank map: the Hilbert order of the cells cut into nranks equal chunks."""
     part = np.zeros(umesh.nelem, dtype=np.int32)

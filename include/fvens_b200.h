@@ -130,6 +130,27 @@ int fvg_mesh_halo_lists(const fvg_mesh *m, int *send_counts, int *recv_counts, i
 /* Packs rows of a device-ordered array for the peers: sendbuf[k][:] = src[send_idx[k]][:] (width doubles). */
 int fvg_halo_pack(const fvg_mesh *m, const double *d_src, int width, double *d_sendbuf, void *stream);
 int fvg_mesh_get_info(const fvg_mesh *m, fvg_mesh_info *info);
+
+/* Peer-memory halo exchange (one process per GPU, all GPUs in one NVLink/NVSwitch box). Each rank owns a window
+ * (receive areas + arrival flags in one device allocation) that its neighbours map through CUDA IPC; an exchange
+ * is a send kernel (pack + direct stores into the neighbours' windows + release of a sequence flag) and a receive
+ * kernel (acquire the flags, copy the rows into the ghost block): no host round trip and no collective library.
+ * The GPU counterpart of the reference's L2TraceVector::updateSharedFacesBegin/End (linalg/tracevector.cpp:214-325)
+ * and of its VecGhostUpdateBegin/End calls (ode/aodesolver.cpp:212,247; spatial/flow_spatial.cpp:711-729).
+ * Set-up: every rank creates its window, the 64-byte handles and the recv_counts rows of fvg_mesh_halo_lists are
+ * all-gathered by the caller (any transport), then fvg_halo_connect maps the neighbours. Every rank must issue the
+ * same sequence of send/recv pairs. max_width and width are even numbers of doubles per row (4 = state, 8 = gradients). */
+typedef struct fvg_halo fvg_halo;
+int fvg_halo_create(fvg_mesh *mesh, int max_width, fvg_halo **out);
+int fvg_halo_ipc_handle(fvg_halo *h, void *handle64);
+/* handles: [nranks][64] bytes; all_recv_counts: [nranks][nranks], row r = rank r's recv_counts */
+int fvg_halo_connect(fvg_halo *h, const void *handles, const int *all_recv_counts);
+/* d_arr: device-ordered array [ncell + nghost][width]; send reads its own rows, recv fills its ghost rows */
+int fvg_halo_send(fvg_halo *h, const double *d_arr, int width, void *stream);
+int fvg_halo_recv(fvg_halo *h, double *d_arr, int width, void *stream);
+/* 0 if every receive so far saw its neighbours arrive; else the sequence number of a receive that gave up waiting */
+int fvg_halo_status(fvg_halo *h, unsigned long long *h_timed_out_seq);
+void fvg_halo_destroy(fvg_halo *h);
 /* cell_new2old[ncell + nghost]: device cell i holds reference (global) cell cell_new2old[i]. */
 int fvg_mesh_permutation(const fvg_mesh *m, int *cell_new2old);
 /* tile_cell0[ntile+1]: device cells [tile_cell0[t], tile_cell0[t+1]) are tile t's own cells. */
