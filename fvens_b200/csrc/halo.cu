@@ -14,6 +14,7 @@
 #include "engine.hpp"
 #include <cstring>
 #include <memory>
+#include <string>
 
 struct fvg_halo {
 	fvg_mesh *mesh = nullptr;
@@ -51,13 +52,13 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 /** grid = nranks * HALO_CTAS_PER_PEER. CTAs [r*K, (r+1)*K) serve peer r: they copy rows send_idx[send_off[r] ..
  * send_off[r+1]) of src into the peer's window at row peer_row0[r], 16 bytes per store; the last of the K CTAs to
  * finish publishes the sequence number in the peer's flag word for this rank. */
-__global__ void __launch_bounds__(HALO_THREADS)
-halo_send_kernel(const double *__restrict__ src, const int *__restrict__ send_idx, const int *__restrict__ send_off,
+__device__ __forceinline__ void
+halo_send_block(const int block, const double *__restrict__ src, const int *__restrict__ send_idx, const int *__restrict__ send_off,
                  const int *__restrict__ peer_row0, unsigned char *const *__restrict__ peer, unsigned *__restrict__ arrive,
                  const unsigned long long *__restrict__ peer_area, const int width, const size_t hdr, const int rank,
                  const unsigned long long seq)
 {
-	const int r = blockIdx.x/HALO_CTAS_PER_PEER, sub = blockIdx.x - r*HALO_CTAS_PER_PEER;
+	const int r = block/HALO_CTAS_PER_PEER, sub = block - r*HALO_CTAS_PER_PEER;
 	const int k0 = send_off[r], nrow = send_off[r+1] - k0;
 	if(nrow == 0 || peer[r] == nullptr) return;
 	double *const dst = reinterpret_cast<double*>(peer[r] + hdr) + (seq & 1ull)*peer_area[r] + (size_t)peer_row0[r]*width;
@@ -83,8 +84,8 @@ halo_send_kernel(const double *__restrict__ src, const int *__restrict__ send_id
 /** Waits until every peer that sends rows has published `seq`, then copies the window's rows into the ghost block
  * of dst (rows [ncell, ncell + nghost)). A bounded spin: if a peer never arrives the error word is set and the copy
  * proceeds (the caller reads the status; nothing hangs). */
-__global__ void __launch_bounds__(HALO_THREADS)
-halo_recv_kernel(double *__restrict__ dst, const unsigned char *__restrict__ window, const int *__restrict__ recv_off,
+__device__ __forceinline__ void
+halo_recv_block(const int block, const int nblocks, double *__restrict__ dst, const unsigned char *__restrict__ window, const int *__restrict__ recv_off,
                  const int ncell, const int nghost, const int width, const size_t area_doubles, const size_t hdr, const int nranks,
                  const unsigned long long seq, const long long spin_limit)
 {
@@ -105,8 +106,31 @@ halo_recv_kernel(double *__restrict__ dst, const unsigned char *__restrict__ win
 	const long long tot = (long long)nghost*width/2;
 	double2 *const out = reinterpret_cast<double2*>(dst + (size_t)ncell*width);
 	const double2 *const in = reinterpret_cast<const double2*>(srcw);
-	for(long long q = (long long)blockIdx.x*HALO_THREADS + threadIdx.x; q < tot; q += (long long)gridDim.x*HALO_THREADS)
+	for(long long q = (long long)block*HALO_THREADS + threadIdx.x; q < tot; q += (long long)nblocks*HALO_THREADS)
 		out[q] = in[q];
+}
+
+struct HaloArgs {
+	const double *src; double *dst;
+	const int *send_idx, *send_off, *peer_row0, *recv_off;
+	unsigned char *const *peer; unsigned *arrive; const unsigned long long *peer_area;
+	const unsigned char *window;
+	int width, rank, nranks, ncell, nghost, nsend_blocks, nrecv_blocks;
+	size_t hdr, area_doubles;
+	unsigned long long seq; long long spin_limit;
+};
+
+/// One launch: the first nsend_blocks CTAs push this rank's rows into the neighbours' windows, the remaining CTAs wait
+/// for the neighbours' rows and unpack them. All CTAs are co-resident (at most 4*nranks + 16), so the waiting ones
+/// cannot starve the pushing ones. Either part may be empty (nsend_blocks = 0: receive only; nrecv_blocks = 0: send only).
+__global__ void __launch_bounds__(HALO_THREADS)
+halo_kernel(const HaloArgs a)
+{
+	if((int)blockIdx.x < a.nsend_blocks)
+		halo_send_block(blockIdx.x, a.src, a.send_idx, a.send_off, a.peer_row0, a.peer, a.arrive, a.peer_area, a.width, a.hdr, a.rank, a.seq);
+	else
+		halo_recv_block(blockIdx.x - a.nsend_blocks, a.nrecv_blocks, a.dst, a.window, a.recv_off, a.ncell, a.nghost, a.width,
+		                a.area_doubles, a.hdr, a.nranks, a.seq, a.spin_limit);
 }
 
 } // namespace fvg
@@ -191,33 +215,39 @@ int fvg_halo_connect(fvg_halo *h, const void *handles, const int *all_recv_count
 	return 0;
 }
 
+static int halo_launch(fvg_halo *h, const double *src, double *dst, int width, bool do_send, bool do_recv, void *stream, const char *who)
+{
+	if(!h || (do_send && !src) || (do_recv && !dst) || !h->connected) { set_error(std::string(who) + ": not connected / null argument"); return FVG_ERR_INVALID; }
+	if(width < 2 || (width & 1) || width > h->max_width) { set_error(std::string(who) + ": width must be even and within the window's width"); return FVG_ERR_INVALID; }
+	if(do_send) h->seq++;
+	HaloArgs a;
+	a.src = src; a.dst = dst; a.send_idx = h->mesh->d.send_idx; a.send_off = h->d_send_off; a.peer_row0 = h->d_peer_row0;
+	a.recv_off = h->d_recv_off; a.peer = h->d_peer; a.arrive = h->d_arrive; a.peer_area = h->d_peer_area; a.window = h->window;
+	a.width = width; a.rank = h->rank; a.nranks = h->nranks; a.ncell = h->mesh->d.ncell; a.nghost = h->mesh->d.nghost;
+	a.hdr = h->hdr; a.area_doubles = h->area_doubles; a.seq = h->seq;
+	a.spin_limit = 30000000ll;                 // about two seconds of 64 ns naps
+	a.nsend_blocks = (do_send && h->mesh->d.nsend > 0) ? h->nranks*HALO_CTAS_PER_PEER : 0;
+	a.nrecv_blocks = (do_recv && a.nghost > 0) ? std::max(1, std::min(16, (a.nghost*width/2 + HALO_THREADS - 1)/HALO_THREADS)) : 0;
+	if(a.nsend_blocks + a.nrecv_blocks == 0) return 0;
+	halo_kernel<<<a.nsend_blocks + a.nrecv_blocks, HALO_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "halo kernel launch", __FILE__, __LINE__);
+	return 0;
+}
+
 int fvg_halo_send(fvg_halo *h, const double *d_arr, int width, void *stream)
 {
-	if(!h || !d_arr || !h->connected) { set_error("fvg_halo_send: not connected / null argument"); return FVG_ERR_INVALID; }
-	if(width < 2 || (width & 1) || width > h->max_width) { set_error("fvg_halo_send: width must be even and within the window's width"); return FVG_ERR_INVALID; }
-	h->seq++;
-	if(h->mesh->d.nsend == 0) return 0;
-	halo_send_kernel<<<h->nranks*HALO_CTAS_PER_PEER, HALO_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-		d_arr, h->mesh->d.send_idx, h->d_send_off, h->d_peer_row0, h->d_peer, h->d_arrive, h->d_peer_area, width, h->hdr,
-		h->rank, h->seq);
-	const cudaError_t e = cudaGetLastError();
-	if(e != cudaSuccess) return cuda_fail(e, "halo_send launch", __FILE__, __LINE__);
-	return 0;
+	return halo_launch(h, d_arr, nullptr, width, true, false, stream, "fvg_halo_send");
 }
 
 int fvg_halo_recv(fvg_halo *h, double *d_arr, int width, void *stream)
 {
-	if(!h || !d_arr || !h->connected) { set_error("fvg_halo_recv: not connected / null argument"); return FVG_ERR_INVALID; }
-	if(width < 2 || (width & 1) || width > h->max_width) { set_error("fvg_halo_recv: width must be even and within the window's width"); return FVG_ERR_INVALID; }
-	const int ng = h->mesh->d.nghost;
-	if(ng == 0) return 0;
-	const int nblk = std::max(1, std::min(16, (ng*width/2 + HALO_THREADS - 1)/HALO_THREADS));
-	halo_recv_kernel<<<nblk, HALO_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-		d_arr, h->window, h->d_recv_off, h->mesh->d.ncell, ng, width, h->area_doubles, h->hdr, h->nranks, h->seq,
-		/* about two seconds of 64 ns naps */ 30000000ll);
-	const cudaError_t e = cudaGetLastError();
-	if(e != cudaSuccess) return cuda_fail(e, "halo_recv launch", __FILE__, __LINE__);
-	return 0;
+	return halo_launch(h, nullptr, d_arr, width, false, true, stream, "fvg_halo_recv");
+}
+
+int fvg_halo_exchange(fvg_halo *h, double *d_arr, int width, void *stream)
+{
+	return halo_launch(h, d_arr, d_arr, width, true, true, stream, "fvg_halo_exchange");
 }
 
 int fvg_halo_status(fvg_halo *h, unsigned long long *h_timed_out_seq)

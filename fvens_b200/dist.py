@@ -85,7 +85,8 @@ class PeerHaloExchange:
         mine = torch.zeros(64 + 4*world, dtype=torch.uint8)
         mine[:64] = torch.frombuffer(bytearray(self.win.handle()), dtype=torch.uint8)
         mine[64:] = torch.from_numpy(np.ascontiguousarray(rc, dtype=np.int32).view(np.uint8))
-        mine = mine.to(device)
+        if dist.get_backend(group) == "nccl":      # NCCL moves device tensors; gloo (single-GPU tests) host tensors
+            mine = mine.to(device)
         every = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(every, mine, group=group)
         every = [e.cpu().numpy() for e in every]
@@ -96,9 +97,7 @@ class PeerHaloExchange:
 
     def exchange(self, arr):
         """arr: [ncell+nghost, width] device-ordered; fills the ghost rows from their owners."""
-        s = torch.cuda.current_stream().cuda_stream
-        self.win.send(arr, arr.shape[1], stream=s)
-        self.win.recv(arr, arr.shape[1], stream=s)
+        self.win.exchange(arr, arr.shape[1], stream=torch.cuda.current_stream().cuda_stream)
 
     def send(self, arr):
         self.win.send(arr, arr.shape[1], stream=torch.cuda.current_stream().cuda_stream)

@@ -431,6 +431,9 @@ class PeerHaloWindow:
     def recv(self, arr, width, stream=None):
         check(load().fvg_halo_recv(self._h, _ptr(arr), int(width), C.c_void_p(stream or 0)))
 
+    def exchange(self, arr, width, stream=None):
+        check(load().fvg_halo_exchange(self._h, _ptr(arr), int(width), C.c_void_p(stream or 0)))
+
     def status(self):
         v = C.c_ulonglong(0)
         check(load().fvg_halo_status(self._h, C.byref(v)))

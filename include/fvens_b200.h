@@ -148,6 +148,8 @@ int fvg_halo_connect(fvg_halo *h, const void *handles, const int *all_recv_count
 /* d_arr: device-ordered array [ncell + nghost][width]; send reads its own rows, recv fills its ghost rows */
 int fvg_halo_send(fvg_halo *h, const double *d_arr, int width, void *stream);
 int fvg_halo_recv(fvg_halo *h, double *d_arr, int width, void *stream);
+/* send + recv in one launch (the pushing and the waiting CTAs are co-resident) */
+int fvg_halo_exchange(fvg_halo *h, double *d_arr, int width, void *stream);
 /* 0 if every receive so far saw its neighbours arrive; else the sequence number of a receive that gave up waiting */
 int fvg_halo_status(fvg_halo *h, unsigned long long *h_timed_out_seq);
 void fvg_halo_destroy(fvg_halo *h);

@@ -17,9 +17,23 @@ from fvens_b200.dist import DistFlow       # noqa: E402
 
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+    # MGPU_SAME_DEVICE=1: every rank uses cuda:0 and gloo carries the set-up traffic and the scalar reductions, so
+    # the whole multi-rank path (subdomain meshes, peer-memory windows over CUDA IPC, split passes) runs on ONE GPU
+    same = os.environ.get("MGPU_SAME_DEVICE", "0") == "1"
+    if same:
+        lr = 0
     torch.cuda.set_device(lr)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     dev = torch.device("cuda", lr)
+    if same:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def allreduce(t):
+        if same:
+            c = t.cpu(); dist.all_reduce(c); t.copy_(c)
+        else:
+            dist.all_reduce(t)
     arrs = synth.bump_channel(120, 45)
     um = lib.UMesh.from_arrays(*arrs)
     rc = synth.cell_centres(arrs[0], arrs[1], arrs[2])
@@ -43,13 +57,13 @@ def main():
         cur, nxt = u.clone(), unew
         for _ in range(5):
             df.euler_step(cur, nxt, 0.4, n2)
-            t = n2.clone(); dist.all_reduce(t)
+            t = n2.clone(); allreduce(t)
             hist.append(float(t.sqrt().item()))
             cur, nxt = nxt, cur
         # gather to rank 0
         full_r = torch.zeros((um.nelem, 4), dtype=torch.float64, device=dev); full_u = torch.zeros_like(full_r)
         full_r[ids[:df.ncell]] = res; full_u[ids[:df.ncell]] = cur[:df.ncell]
-        dist.all_reduce(full_r); dist.all_reduce(full_u)
+        allreduce(full_r); allreduce(full_u)
         if rank == 0:
             dm = lib.DeviceMesh(um, reorder="hilbert", tile_cells=128, device=lr)
             fl = lib.FlowFV(dm, phys, bcs=bcs, **numerics)
