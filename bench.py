@@ -70,9 +70,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def count(self, t0=None):
+        return sum(1 for r in self.rows if len(r) >= 10 and (t0 is None or r[0] >= t0))
+
+    def stop(self, windows):
+        """Summary over the samples that arrived inside one of the (t0, t1) load windows."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -80,17 +84,18 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r[1:] for r in self.rows if len(r) >= 10 and any(a <= r[0] <= b for a, b in windows)]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in rows if r[3].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for k, nm in enumerate(names):
-                    if r[5+k].lower().startswith("active"):
-                        reasons.add(nm)
+        for r in rows:
+            for k, nm in enumerate(names):
+                if r[5+k].lower().startswith("active"):
+                    reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def build_case(cells, numerics, tile):
@@ -135,7 +140,7 @@ def cpu_reference(cells, numerics, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=float, default=10.0e6)
@@ -226,26 +231,50 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi needs a few hundred ms to deliver its first row: start it before the warm-up and wait for it
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        t_wait = time.perf_counter()
+        while sampler.proc and sampler.count() == 0 and time.perf_counter() - t_wait < 5.0:
+            time.sleep(0.02)
     for _ in range(args.warmup):
         evaluate()
     barrier()
     if world == 1:
         fl.timing(True)
     launches0 = fl.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         evaluate()
     e1.record()
     barrier()
+    windows = [(w0, time.perf_counter())]
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = fl.launch_count() - launches0 + halo_launches*args.steps
     ms_cell, ms_face, ntimed = fl.timing(False) if world == 1 else (0.0, 0.0, 0)
+    # a short timed region can end between two nvidia-smi rows (100 ms apart): keep the same kernels running,
+    # untimed, until at least three rows have been taken under this load
+    probe = torch.tensor([0], dtype=torch.int32, device=dev)
+    p0 = time.perf_counter()
+    while True:
+        if rank == 0:
+            have = sum(1 for r in sampler.rows if len(r) >= 10 and r[0] >= w0 + 0.02)
+            probe[0] = 1 if (sampler.proc is None or have >= 3 or time.perf_counter() - p0 > 3.0) else 0
+        if world > 1:
+            dist.broadcast(probe, 0)
+        if int(probe.item()) == 1:
+            break
+        for _ in range(20):
+            evaluate()
+        barrier()
+    windows.append((p0, time.perf_counter()))
+    clocks = sampler.stop(windows) if rank == 0 else None
+    if clocks is not None:
+        clocks["sampled"] = "nvidia-smi every 100 ms during the timed region and an untimed continuation of the same kernels"
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -330,7 +359,7 @@ def main():
     info = dm.info
     traffic = None
     try:        # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"face_kernel:{args.numerics}:{args.tile}")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"face_kernel:{args.numerics}:{args.tile}:{int(args.cells)}")
     except Exception:
         pass
     line = {

@@ -1,0 +1,17 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, the bench line, the ncu launch list of the same command and one full capture of
+# the two passes. Run as: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh <tag>'
+tag=${1:-rXX}
+out=gpurun_out
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/${tag}_smi.txt 2>&1
+( time timeout 600 python -m pytest tests -m gpu -x -q ) > $out/${tag}_pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> $out/${tag}_pytest_gpu.log
+timeout 600 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
+timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
+   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $out/${tag}_launches_bench.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'cell_kernel|face_kernel' -s 6 -c 2 \
+   -f -o $out/${tag}_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $out/${tag}_full.log 2>&1
+python tools/ncu_summary.py $out/${tag}_full.ncu-rep > $out/${tag}_ncu_summary.txt 2>&1
+tail -3 $out/${tag}_pytest_gpu.log; cat $out/${tag}_bench_n1.json; tail -2 $out/${tag}_bench_n1.err
