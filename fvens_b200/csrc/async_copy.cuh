@@ -48,6 +48,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 	             :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+/// 2-D tiled copy through a tensor map (box rows starting at row `row`, all columns) global -> shared. The map's
+/// swizzle mode decides where the 16-byte chunks of a row land (see rows32_chunk / rows64_chunk in face_kernel.cuh);
+/// rows past the end of the global array arrive as zeros and are counted in the transaction bytes.
+__device__ __forceinline__ void tensor_rows_g2s(void *dst_smem, const void *tmap, int row, uint64_t *bar) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+	             :: "r"(smem_u32(dst_smem)), "l"(tmap), "r"(0), "r"(row), "r"(smem_u32(bar)) : "memory");
+}
+
 /// Asks the TMA unit to pull `bytes` (multiple of 16, 16-byte aligned) of global memory into L2; no destination,
 /// no completion tracking. Used to warm L2 with the operands of the tile that will run a wave later.
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, unsigned bytes) {

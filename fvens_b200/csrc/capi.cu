@@ -109,6 +109,37 @@ static const double *viscous_gradients(const fvg_flow *f)
 	return f->d_lg;   // no limiter: the stored gradients are the unlimited ones
 }
 
+int make_row_tensor_map(CUtensorMap *tm, const double *base, size_t nrows, int width, int box_rows)
+{
+	typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+	                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+	                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static EncodeTiled encode = nullptr;
+	if(!encode) {
+		void *fn = nullptr;
+		cudaDriverEntryPointQueryResult qr;
+		const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr);
+		if(e != cudaSuccess || !fn || qr != cudaDriverEntryPointSuccess) {
+			set_error("cuTensorMapEncodeTiled is not available from this driver");
+			return FVG_ERR_CUDA;
+		}
+		encode = reinterpret_cast<EncodeTiled>(fn);
+	}
+	if((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (width != 4 && width != 8) || box_rows < 1 || box_rows > 256) {
+		set_error("tensor map: the array must be 16-byte aligned, rows of 4 or 8 doubles, at most 256 rows per tile");
+		return FVG_ERR_INVALID;
+	}
+	const cuuint64_t gdim[2] = {(cuuint64_t)width, (cuuint64_t)std::max<size_t>(nrows, 1)};
+	const cuuint64_t gstride[1] = {(cuuint64_t)width*8};
+	const cuuint32_t box[2] = {(cuuint32_t)width, (cuuint32_t)box_rows};
+	const cuuint32_t estride[2] = {1, 1};
+	const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estride,
+	                          CU_TENSOR_MAP_INTERLEAVE_NONE, width == 4 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+	                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if(r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return FVG_ERR_CUDA; }
+	return 0;
+}
+
 static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumulate, int gettimesteps,
                          double *res, double *dtm, double cfl, double *unew, cudaStream_t s)
 {
@@ -120,6 +151,9 @@ static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumul
 	a.res = res; a.dtm = dtm; a.cfl = cfl; a.unew = unew; a.partial = f->d_partial;
 	a.prefetch_distance = f->prefetch_distance;
 	const int recon = !P.order2 ? FR_FIRST : (P.recon == FVG_RECON_VANALBADA ? FR_MUSCL : FR_LINEAR);
+	int rt = make_row_tensor_map(&a.tm_u, u, (size_t)a.m.ncell, 4, tile_box_rows(a.m.TC));
+	if(rt == 0 && recon == FR_LINEAR) rt = make_row_tensor_map(&a.tm_g, a.lg, (size_t)a.m.ncell, 8, tile_box_rows(a.m.TC));
+	if(rt != 0) return rt;
 	FaceLauncher L = face_launcher(P.flux);
 	if(!L) { set_error("unknown flux id"); return FVG_ERR_INVALID; }
 	const int rc = L(recon, P.visc, a, s);

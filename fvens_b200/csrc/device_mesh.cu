@@ -14,6 +14,7 @@
 #include <cstring>
 #include <queue>
 #include <climits>
+#include <cstdlib>
 
 namespace fvg {
 
@@ -261,81 +262,186 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	std::vector<int> tile_of((size_t)ntot, -1);
 	for(int t = 0; t < ntile; t++) for(int i = tcell0[t]; i < tcell0[t+1]; i++) tile_of[i] = t;
 
-	// ---- face streams: count (padded to 4), fill in reference face order, colour, sort by kind
-	std::vector<int> fsoff((size_t)ntile+1, 0);
+	// ---- face streams. Raw per-tile entry lists in reference face order first (f, or -1-f for the second copy
+	// of a face cut by a tile boundary), then per tile: kinds, edge colours, shared-memory bank residues, positions.
+	std::vector<int> roff((size_t)ntile+1, 0);
 	int ninterior = 0;
 	for(int f : rfaces) {
 		const int L = faceL(f), R = faceR(f);
 		const int tL = L >= 0 ? tile_of[L] : -1, tR = R >= 0 ? tile_of[R] : -1;
-		if(tL >= 0) fsoff[tL+1]++;
-		if(tR >= 0 && tR != tL) fsoff[tR+1]++;
+		if(tL >= 0) roff[tL+1]++;
+		if(tR >= 0 && tR != tL) roff[tR+1]++;
 		if(R >= 0) { distsum += std::abs(L-R); ninterior++; }
 	}
-	int ncopies = 0;
-	for(int t = 0; t < ntile; t++) { ncopies += fsoff[t+1]; fsoff[t+1] = fsoff[t] + (fsoff[t+1] + 3)/4*4; }
-	const int ns = fsoff[ntile];
+	for(int t = 0; t < ntile; t++) roff[t+1] += roff[t];
+	const int ncopies = roff[ntile];
 	m->ncut_dup = ncopies - nrf;
 	m->mean_nbr_dist = ninterior ? (double)distsum/(double)ninterior : 0.0;
-
-	const int PAD = INT_MIN;
-	std::vector<int> sface((size_t)ns, PAD);    // global face of each entry, -1-f for the second copy, PAD for padding
+	std::vector<int> rent((size_t)ncopies);
 	{
-		std::vector<int> pos(fsoff.begin(), fsoff.end()-1);
+		std::vector<int> pos(roff.begin(), roff.end()-1);
 		for(int f : rfaces) {
 			const int L = faceL(f), R = faceR(f);
 			const int tL = L >= 0 ? tile_of[L] : -1, tR = R >= 0 ? tile_of[R] : -1;
 			if(tL >= 0) {
-				sface[pos[tL]++] = f;
-				if(tR >= 0 && tR != tL) sface[pos[tR]++] = -1-f;
-			} else sface[pos[tR]++] = f;                 // left cell is a ghost: the right cell's tile holds the only copy
+				rent[pos[tL]++] = f;
+				if(tR >= 0 && tR != tL) rent[pos[tR]++] = -1-f;
+			} else rent[pos[tR]++] = f;                  // left cell is a ghost: the right cell's tile holds the only copy
 		}
 	}
+	// local face slot of global face f in own device cell i
+	auto slot_of = [&](int i, int f) {
+		const int o = d2g[i];
+		for(int j = 0; j < hm->nnode[o]; j++) if(hm->elemface[(size_t)o*mw+j] == f) return j;
+		return 0;
+	};
+
 	// Greedy edge colouring per tile (kept as metadata: fvg_mesh_stream exposes it and a test checks that no two
-	// entries of one colour touch the same tile cell). The kernels gather per cell and do not need the colours,
-	// so the stream is ordered by KIND instead: faces with both cells in the tile, then faces cut by the tile
-	// boundary (one side is a halo cell), then physical-boundary faces, then padding. Warps of the flux phase
-	// are then uniform in kind; reference face order is kept inside a kind.
-	std::vector<int> scolour((size_t)ns, MAXCOL-1);
+	// entries of one colour touch the same tile cell). The kernels gather per cell and do not need the colours;
+	// the stream is ordered by KIND: faces with both cells in the tile, then faces cut by the tile boundary (one
+	// side is a halo cell), then physical-boundary faces, then padding.
+	//
+	// Inside the first two kinds the POSITION of an entry is chosen for the shared-memory banks. The kernels keep
+	// per-entry data in arrays of 16-byte elements (midpoints, the two halves of each face state / flux, spectral
+	// radii), so entry e lives in bank group e mod 8. Those arrays are written and read per CELL (phases A and C of
+	// the face kernel, the limiter of the cell kernel): a 128-bit shared-memory access is served per quarter warp,
+	// i.e. the 8 consecutive cells 8q .. 8q+7 access the entries of their local face j together. The entries of such
+	// a (q, j) group are therefore given distinct residues mod 8 - an edge colouring with 8 "bank colours" of the
+	// graph whose vertices are the groups - which makes these scatters and gathers conflict-free; entries are then
+	// placed at 8*i + residue, the unused positions of a residue class are padding entries.
+	const bool bank_colour = !(getenv("FVG_BANK_COLOUR") && atoi(getenv("FVG_BANK_COLOUR")) == 0);
+	std::vector<int> fsoff((size_t)ntile+1, 0);
 	std::vector<int4> tbnd((size_t)ntile);      // tile-local index of the first cut entry, of the first boundary entry, number of boundary entries, padding
+	std::vector<int> epos((size_t)ncopies), ecol((size_t)ncopies, MAXCOL-1);   // tile-local position / edge colour of every raw entry
 	m->max_colours = 0;
+	long long ngroups = 0, nconfl = 0;
+	int emax_seen = 0;
 	{
+		const int NG = (TC/8 + 1)*4;
 		std::vector<unsigned char> used(TC);
-		std::vector<int> tmp, ctmp;
+		std::vector<unsigned char> gcnt((size_t)NG*8);
+		std::vector<int> at((size_t)NG*8);           // entry holding residue c at group g (-1: free)
+		std::vector<int> kind, res, eg, path;
 		for(int t = 0; t < ntile; t++) {
-			const int c0 = tcell0[t], e0 = fsoff[t], e1 = fsoff[t+1];
+			const int c0 = tcell0[t], r0 = roff[t], nr = roff[t+1] - r0;
 			std::fill(used.begin(), used.end(), 0);
-			int cnt[4] = {0, 0, 0, 0};
-			auto kind_of = [&](int sf) {
-				if(sf == PAD) return 3;
+			std::fill(at.begin(), at.end(), -1);
+			kind.assign(nr, 0); res.assign(nr, -1); eg.assign(2*(size_t)nr, -1);
+			int cnt[3] = {0, 0, 0};
+			int rcnt[2][8] = {{0,0,0,0,0,0,0,0},{0,0,0,0,0,0,0,0}};
+			int seq[2] = {0, 0};
+			auto setres = [&](int k, int c) {
+				res[k] = c; rcnt[kind[k]][c]++;
+				for(int s2 = 0; s2 < 2; s2++) if(eg[2*k+s2] >= 0) at[(size_t)eg[2*k+s2]*8+c] = k;
+			};
+			for(int pass = 0; pass < 2; pass++)          // entries with two groups in the tile first: they are the constrained ones
+			for(int k = 0; k < nr; k++) {
+				const int sf = rent[r0+k];
 				const int f = sf >= 0 ? sf : -1-sf;
 				const int L = faceL(f), R = faceR(f);
-				if(R < 0) return 2;
-				return (tile_of[L] == t && tile_of[R] == t) ? 0 : 1;
-			};
-			for(int e = e0; e < e1; e++) {
-				cnt[kind_of(sface[e])]++;
-				if(sface[e] == PAD) continue;
-				const int f = sface[e] >= 0 ? sface[e] : -1-sface[e];
-				const int L = faceL(f), R = faceR(f);
-				unsigned mask = 0;
-				if(tile_of[L] == t) mask |= used[L-c0];
-				if(R >= 0 && tile_of[R] == t) mask |= used[R-c0];
-				int c = 0;
-				while(mask & (1u << c)) c++;
-				if(c >= MAXCOL) { set_error("fvg_mesh_create: edge colouring needs more than 8 colours"); return FVG_ERR_INVALID; }
-				if(tile_of[L] == t) used[L-c0] |= (unsigned char)(1u << c);
-				if(R >= 0 && tile_of[R] == t) used[R-c0] |= (unsigned char)(1u << c);
-				scolour[e] = c;
-				m->max_colours = std::max(m->max_colours, c+1);
+				const bool inL = tile_of[L] == t, inR = R >= 0 && tile_of[R] == t;
+				const int kd = R < 0 ? 2 : ((inL && inR) ? 0 : 1);
+				if(pass == 0) {
+					kind[k] = kd; cnt[kd]++;
+					unsigned mask = 0;
+					if(inL) mask |= used[L-c0];
+					if(inR) mask |= used[R-c0];
+					int c = 0;
+					while(mask & (1u << c)) c++;
+					if(c >= MAXCOL) { set_error("fvg_mesh_create: edge colouring needs more than 8 colours"); return FVG_ERR_INVALID; }
+					if(inL) used[L-c0] |= (unsigned char)(1u << c);
+					if(inR) used[R-c0] |= (unsigned char)(1u << c);
+					ecol[r0+k] = c;
+					m->max_colours = std::max(m->max_colours, c+1);
+				}
+				if(kd == 2 || kd != pass) continue;
+				if(!bank_colour) { res[k] = seq[kd]++ & 7; rcnt[kd][res[k]]++; continue; }
+				const int gL = inL ? ((L-c0) >> 3)*4 + slot_of(L, f) : -1;
+				const int gR = inR ? ((R-c0) >> 3)*4 + slot_of(R, f) : -1;
+				eg[2*k] = gL; eg[2*k+1] = gR;
+				unsigned freeL = 0xFF, freeR = 0xFF;
+				for(int c = 0; c < 8; c++) {
+					if(gL >= 0 && at[(size_t)gL*8+c] >= 0) freeL &= ~(1u << c);
+					if(gR >= 0 && at[(size_t)gR*8+c] >= 0) freeR &= ~(1u << c);
+				}
+				int best = -1;
+				for(int c = 0; c < 8; c++)
+					if((freeL & freeR & (1u << c)) && (best < 0 || rcnt[kd][c] < rcnt[kd][best])) best = c;
+				if(best < 0 && gL >= 0 && gR >= 0) {
+					// no common free residue: a is free at the left group, b at the right one; flip a <-> b along the alternating
+					// path that starts at the right group with a, unless it ends in the left group (then a would be taken there)
+					// (dir 0), or the mirror image: the path that starts at the left group with b, unless it ends in the right one
+					for(int dir = 0; dir < 2 && best < 0; dir++)
+					for(int a = 0; a < 8 && best < 0; a++) {
+						if(!(freeL & (1u << a))) continue;
+						for(int b = 0; b < 8 && best < 0; b++) {
+							if(!(freeR & (1u << b))) continue;
+							path.clear();
+							const int from = dir == 0 ? gR : gL, avoid = dir == 0 ? gL : gR;
+							int cur = from, col = dir == 0 ? a : b, prev = -1;
+							bool ok = true;
+							for(int step = 0; step < 200; step++) {
+								const int e = at[(size_t)cur*8+col];
+								if(e < 0) break;
+								if(e == prev || res[e] != col || std::find(path.begin(), path.end(), e) != path.end()) { ok = false; break; }
+								path.push_back(e);
+								const int other = eg[2*e] == cur ? eg[2*e+1] : eg[2*e];
+								prev = e;
+								if(other < 0) break;               // an entry with one group ends the path
+								cur = other; col = col == a ? b : a;
+								if(cur == avoid || cur == from) { ok = false; break; }
+								if(step == 199) ok = false;
+							}
+							if(!ok) continue;
+							for(int e : path) {
+								const int oc = res[e];
+								rcnt[kind[e]][oc]--;
+								for(int s2 = 0; s2 < 2; s2++) if(eg[2*e+s2] >= 0 && at[(size_t)eg[2*e+s2]*8+oc] == e) at[(size_t)eg[2*e+s2]*8+oc] = -1;
+							}
+							for(int e : path) setres(e, res[e] == a ? b : a);
+							best = dir == 0 ? a : b;
+						}
+					}
+				}
+				if(best < 0) {        // give up: least-loaded residue that is free in at least one of the groups
+					for(int c = 0; c < 8; c++)
+						if(((freeL | freeR) & (1u << c)) && (best < 0 || rcnt[kd][c] < rcnt[kd][best])) best = c;
+					if(best < 0) best = 0;
+				}
+				setres(k, best);
 			}
-			tbnd[t] = make_int4(cnt[0], cnt[0] + cnt[1], cnt[2], cnt[3]);
-			tmp.assign(sface.begin()+e0, sface.begin()+e1);
-			ctmp.assign(scolour.begin()+e0, scolour.begin()+e1);
-			int pos[4];
-			pos[0] = e0; pos[1] = pos[0] + cnt[0]; pos[2] = pos[1] + cnt[1]; pos[3] = pos[2] + cnt[2];
-			for(int k = 0; k < e1-e0; k++) { const int q = kind_of(tmp[k]); sface[pos[q]] = tmp[k]; scolour[pos[q]] = ctmp[k]; pos[q]++; }
+			std::fill(gcnt.begin(), gcnt.end(), 0);
+			for(int k = 0; k < nr; k++)          // an entry whose two cells share a group (same address: a broadcast) counts once
+				for(int s2 = 0; s2 < 2; s2++) if(eg[2*k+s2] >= 0 && !(s2 == 1 && eg[2*k] == eg[2*k+1])) gcnt[(size_t)eg[2*k+s2]*8+res[k]]++;
+			for(size_t g = 0; g < gcnt.size()/8; g++) {
+				int members = 0, distinct = 0;
+				for(int c = 0; c < 8; c++) { members += gcnt[g*8+c]; distinct += gcnt[g*8+c] > 0; }
+				if(members > 0) { ngroups++; if(distinct < members) nconfl++; }
+			}
+			// positions: kind 0 at 8*i + residue from 0, kind 1 likewise after it, boundary entries contiguous after both
+			int seg[2];
+			for(int q = 0; q < 2; q++) { int mx = 0; for(int c = 0; c < 8; c++) mx = std::max(mx, rcnt[q][c]); seg[q] = 8*mx; }
+			int next[2][8];
+			for(int q = 0; q < 2; q++) for(int c = 0; c < 8; c++) next[q][c] = (q == 0 ? 0 : seg[0]) + c;
+			int nextb = seg[0] + seg[1];
+			for(int k = 0; k < nr; k++) {
+				if(kind[k] == 2) epos[r0+k] = nextb++;
+				else { epos[r0+k] = next[kind[k]][res[k]]; next[kind[k]][res[k]] += 8; }
+			}
+			const int len = (nextb + 3)/4*4;
+			tbnd[t] = make_int4(seg[0], seg[0] + seg[1], cnt[2], len - nr);
+			fsoff[t+1] = fsoff[t] + len;
+			emax_seen = std::max(emax_seen, len);
 		}
 	}
+	m->bank_groups = ngroups; m->bank_conflict_groups = nconfl;
+	const int ns = fsoff[ntile];
+	const int EMAX_LAYOUT = std::max(32, (emax_seen + 31)/32*32);      // capacity of the kernels' per-entry staging arrays
+	const int PAD = INT_MIN;
+	std::vector<int> sface((size_t)ns, PAD);    // global face of each entry, -1-f for the second copy, PAD for padding
+	std::vector<int> scolour((size_t)ns, MAXCOL-1);
+	for(int t = 0; t < ntile; t++)
+		for(int k = roff[t]; k < roff[t+1]; k++) { sface[(size_t)fsoff[t] + epos[k]] = rent[k]; scolour[(size_t)fsoff[t] + epos[k]] = ecol[k]; }
 
 	// ---- per-entry arrays with tile-local cell indices
 	std::vector<unsigned> &fLR = m->h_fLR;
@@ -454,7 +560,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 
 	// ---- upload
 	DMesh &D = m->d;
-	D.ncell = nown; D.nghost = ntot - nown; D.nbface = nb; D.naface = nf; D.ntile = ntile; D.TC = TC; D.HMAX = HMAX; D.EMAX = EMAX; D.nstream = ns;
+	D.ncell = nown; D.nghost = ntot - nown; D.nbface = nb; D.naface = nf; D.ntile = ntile; D.TC = TC; D.HMAX = HMAX; D.EMAX = EMAX_LAYOUT; D.nstream = ns;
 	D.nsend = (int)m->h_send_idx.size();
 	int rcode;
 #define UP(vec, field) if((rcode = upload(m, vec, &D.field)) != 0) return rcode;
@@ -527,6 +633,8 @@ int fvg_mesh_get_info(const fvg_mesh *m, fvg_mesh_info *info)
 	info->ntile = m->d.ntile; info->tile_cells = m->d.TC; info->nstream = m->d.nstream;
 	info->ncut_dup = m->ncut_dup; info->max_colours = m->max_colours; info->reorder = m->reorder;
 	info->mean_neighbour_distance = m->mean_nbr_dist;
+	info->entry_capacity = m->d.EMAX; info->halo_capacity = m->d.HMAX;
+	info->bank_groups = m->bank_groups; info->bank_conflict_groups = m->bank_conflict_groups;
 	return 0;
 }
 

@@ -1,6 +1,7 @@
 /* Internal declarations shared by the translation units of libfvens_b200.so. Not part of the ABI. */
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>              // CUtensorMap (type only: the encoder is fetched through the runtime, libcuda is not linked)
 #include <string>
 #include <vector>
 #include <cstdint>
@@ -91,6 +92,7 @@ struct fvg_mesh {
 	int reorder = 0;
 	bool identity_perm = true;
 	int ncut_dup = 0, max_colours = 0;
+	long long bank_groups = 0, bank_conflict_groups = 0;   ///< (quarter-warp, local face) groups of stream entries; those with a repeated bank residue
 	double mean_nbr_dist = 0;
 	std::vector<void*> allocs;                 ///< everything cudaMalloc'ed for this mesh
 	// host copies kept for the test hooks and for flow set-up
@@ -207,7 +209,17 @@ struct FaceArgs {
 	double *unew;          ///< EP_STEP: [ncell][4]
 	double *partial;       ///< EP_STEP: [ntile] sum of r_E^2*area
 	int prefetch_distance; ///< tiles ahead whose operands are pulled into L2 (0 = off)
+	// TMA descriptors of the per-cell row arrays staged per tile: box = TC rows, hardware-swizzled so that
+	// "thread k reads row k" is free of shared-memory bank conflicts (32-byte rows: SWIZZLE_32B, 64-byte: SWIZZLE_64B)
+	CUtensorMap tm_u;      ///< u as [ncell][4]
+	CUtensorMap tm_g;      ///< lg as [ncell][8] (linear reconstruction only)
 };
+/// Rows per TMA box of the per-cell row arrays (a box has at most 256 rows and must tile TC exactly)
+__host__ __device__ inline int tile_box_rows(int TC) {
+	return TC <= 256 ? TC : (TC % 256 == 0 ? 256 : (TC % 128 == 0 ? 128 : (TC % 64 == 0 ? 64 : 32)));
+}
+/// Tensor map over a row-major [nrows][width] FP64 array (width 4 or 8), box = box_rows full rows, swizzle = row size
+int make_row_tensor_map(CUtensorMap *tm, const double *base, size_t nrows, int width, int box_rows);
 typedef int (*FaceLauncher)(int recon, int visc, const FaceArgs &a, cudaStream_t s);
 int launch_face_llf(int recon, int visc, const FaceArgs &a, cudaStream_t s);
 int launch_face_vanleer(int recon, int visc, const FaceArgs &a, cudaStream_t s);

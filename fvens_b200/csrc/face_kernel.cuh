@@ -35,6 +35,18 @@ __device__ __forceinline__ void lds4(const double *p, double v[4]) {
 	v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
+/// 32-byte row kept as two 16-byte planes `stride` elements apart
+__device__ __forceinline__ void ldp4(const double2 *p, int stride, double v[4]) {
+	const double2 a = p[0], b = p[stride];
+	v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+/// Where the TMA swizzle modes put the 16-byte chunk c of row k (buffer at a multiple of 1024 bytes), in doubles from
+/// the start of the buffer. 32-byte rows, SWIZZLE_32B: address bit 4 ^= bit 7; 64-byte rows, SWIZZLE_64B: bits 5:4 ^=
+/// bits 8:7. With these, the 8 threads of a quarter warp reading chunk c of 8 consecutive rows hit 8 distinct bank groups.
+__device__ __forceinline__ int rows32_chunk(int k, int c) { return 4*k + 2*(c ^ ((k >> 2) & 1)); }
+__device__ __forceinline__ int rows64_chunk(int k, int c) { return 8*k + 2*(c ^ ((k >> 1) & 3)); }
+
 /// Device cell index of a tile-local index
 __device__ __forceinline__ int tile_global(const DMesh &M, int t, int c0, int nc, unsigned loc) {
 	return loc < (unsigned)nc ? c0 + (int)loc : M.thalo[M.thoff[t] + (int)loc - nc];
@@ -62,11 +74,17 @@ __device__ __forceinline__ double muscl_term(double delta, double dlr) {
 /// Shared-memory carve-up of the face kernel for the given capacities (host and device agree through this).
 /// Per stream entry: the two face-state slots (later the flux and the spectral radii) and the midpoint;
 /// per halo cell: its state, reconstruction gradient and centre, gathered asynchronously while phase A runs.
+/// Everything indexed by stream entry is an array of 16-BYTE elements (a 32-byte face state is kept as two such
+/// planes): entry e then sits in bank group e mod 8, consecutive entries (phase B) are conflict-free, and the
+/// per-cell scatters / gathers of phases A and C are conflict-free by the placement of the entries (device_mesh.cu).
 struct FaceSmem {
-	int fsL, fsR, sgr, sn, slen, sLR, hu, hg, hrc, su, sg, src, scl, sar, cbuf, bar, total;   // byte offsets
+	int fsL, fsR, sgr, sn, slen, sLR, hu, hg, hrc, su, sg, src, scl, sar, cbuf, bar, red, total;   // byte offsets
 	__host__ __device__ FaceSmem(int TC, int EMAX, int HMAX, bool mids, bool linear) {
 		int o = 0;
-		fsL = o; o += EMAX*32;
+		su = o; o += TC*32;                    // own cells: state, reconstruction gradient (both hardware-swizzled: keep them
+		sg = o; o += linear ? TC*64 : 0;       // first, at multiples of 1024 bytes), centre
+		src = o; o += linear ? TC*16 : 0;
+		fsL = o; o += EMAX*32;                 // planes: [0, EMAX) first half of the state / flux, [EMAX, 2 EMAX) second half
 		fsR = o; o += EMAX*32;
 		sgr = o; o += mids ? EMAX*16 : 0;
 		sn = o; o += EMAX*16;
@@ -75,12 +93,10 @@ struct FaceSmem {
 		hu = o; o += HMAX*32;
 		hg = o; o += mids ? HMAX*64 : 0;
 		hrc = o; o += mids ? HMAX*16 : 0;
-		su = o; o += TC*32;                    // own cells: state, reconstruction gradient, centre
-		sg = o; o += linear ? TC*64 : 0;
-		src = o; o += linear ? TC*16 : 0;
 		cbuf = TC*16 + (TC + 2)*8;             // stencil + area, two buffers of cbuf bytes
 		scl = o; sar = o + TC*16; o += 2*cbuf;
 		bar = o; o += 16;                      // two mbarriers
+		red = o; o += 8*(FACE_BLOCK/32);       // warp partials of the norm
 		total = o;
 	}
 };
@@ -133,15 +149,17 @@ __device__ __forceinline__ TileDesc load_tile_desc(const DMesh &M, int t) {
  *     atomics, no scatter), then the residual / time-step or the fused forward-Euler epilogue. */
 template <int FLUX, int RECON, int VISC>
 __global__ void __launch_bounds__(FACE_BLOCK, FVG_FACE_MINB)
-face_kernel(const FaceArgs A)
+face_kernel(const __grid_constant__ FaceArgs A)
 {
-	extern __shared__ __align__(128) unsigned char smraw[];
+	extern __shared__ __align__(1024) unsigned char smraw[];
 	const DMesh &M = A.m;
 	constexpr bool MIDS = RECON != FR_FIRST;
 	constexpr bool LINEAR = RECON == FR_LINEAR;
 	const FaceSmem S(M.TC, M.EMAX, M.HMAX, MIDS, LINEAR);
-	double *const fsL = reinterpret_cast<double*>(smraw + S.fsL);
-	double *const fsR = reinterpret_cast<double*>(smraw + S.fsR);
+	double2 *const fsL = reinterpret_cast<double2*>(smraw + S.fsL);
+	double2 *const fsR = reinterpret_cast<double2*>(smraw + S.fsR);
+	const int EP = M.EMAX;                                                  // plane stride of fsL / fsR
+	const int BOX = tile_box_rows(M.TC);
 	double2 *const sgr = reinterpret_cast<double2*>(smraw + S.sgr);
 	double2 *const sn = reinterpret_cast<double2*>(smraw + S.sn);
 	double *const slen = reinterpret_cast<double*>(smraw + S.slen);
@@ -153,7 +171,7 @@ face_kernel(const FaceArgs A)
 	double *const sg = reinterpret_cast<double*>(smraw + S.sg);
 	double2 *const src = reinterpret_cast<double2*>(smraw + S.src);
 	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);       // [0]: groups A + C, [1]: group B
-	__shared__ double red_s[FACE_BLOCK/32];
+	double *const red_s = reinterpret_cast<double*>(smraw + S.red);
 
 	const int tid = threadIdx.x;
 	const double *const gsrc = RECON == FR_MUSCL ? A.gu : A.lg;     // gradients used by the reconstruction
@@ -162,9 +180,16 @@ face_kernel(const FaceArgs A)
 	auto issue_AC = [&](const TileDesc &D, int buf) {
 		const unsigned aoff = (unsigned)(D.c0 & 1);
 		const unsigned abytes = (unsigned)((D.nc + aoff + 1) & ~1)*8u;
-		mbar_expect_tx(bar, (unsigned)D.nc*(32u + 16u + (LINEAR ? 80u : 0u)) + (MIDS ? (unsigned)D.ne*16u : 0u) + abytes);
-		bulk_g2s(su, A.u + 4*(size_t)D.c0, (unsigned)D.nc*32u, bar);
-		if(LINEAR) { bulk_g2s(sg, gsrc + 8*(size_t)D.c0, (unsigned)D.nc*64u, bar); bulk_g2s(src, M.rc + D.c0, (unsigned)D.nc*16u, bar); }
+		// state and gradient rows come through tensor maps in whole boxes (rows past the tile belong to the next tile or
+		// are zero fill past the end of the array; either way they are never read)
+		const int nbox = (D.nc + BOX - 1)/BOX;
+		mbar_expect_tx(bar, (unsigned)(nbox*BOX)*(32u + (LINEAR ? 64u : 0u)) + (unsigned)D.nc*(16u + (LINEAR ? 16u : 0u))
+		                    + (MIDS ? (unsigned)D.ne*16u : 0u) + abytes);
+		for(int b = 0; b < nbox; b++) {
+			tensor_rows_g2s(su + 4*b*BOX, &A.tm_u, D.c0 + b*BOX, bar);
+			if(LINEAR) tensor_rows_g2s(sg + 8*b*BOX, &A.tm_g, D.c0 + b*BOX, bar);
+		}
+		if(LINEAR) bulk_g2s(src, M.rc + D.c0, (unsigned)D.nc*16u, bar);
 		if(MIDS) bulk_g2s(sgr, M.fgr + D.e0, (unsigned)D.ne*16u, bar);
 		bulk_g2s(smraw + S.scl + buf*S.cbuf, M.cloc + D.c0, (unsigned)D.nc*16u, bar);
 		bulk_g2s(smraw + S.sar + buf*S.cbuf, M.area + (D.c0 - (int)aoff), abytes, bar);
@@ -191,6 +216,7 @@ face_kernel(const FaceArgs A)
 
 	int t = blockIdx.x;
 	if(t >= M.ntile) return;
+	if(tid == 0 && (smem_u32(smraw) & 1023u) != 0) __trap();      // the swizzle formulas assume this alignment
 	TileDesc D = load_tile_desc(M, t);
 	if(tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
 	__syncthreads();
@@ -216,26 +242,40 @@ face_kernel(const FaceArgs A)
 			const uint4 cl = scl[k];
 			double uc[4], ga[4] = {0,0,0,0}, gb[4] = {0,0,0,0};
 			double2 rc = make_double2(0,0);
-			lds4(su + 4*k, uc);
+			{
+				const double2 a = *reinterpret_cast<const double2*>(su + rows32_chunk(k, 0)), b = *reinterpret_cast<const double2*>(su + rows32_chunk(k, 1));
+				uc[0] = a.x; uc[1] = a.y; uc[2] = b.x; uc[3] = b.y;
+			}
 			if(k == tid) { for(int q = 0; q < 4; q++) uc0[q] = uc[q]; }
-			if(LINEAR) { lds4(sg + 8*k, ga); lds4(sg + 8*k + 4, gb); rc = src[k]; }
+			if(LINEAR) {
+				const double2 g0 = *reinterpret_cast<const double2*>(sg + rows64_chunk(k, 0)), g1 = *reinterpret_cast<const double2*>(sg + rows64_chunk(k, 1));
+				const double2 g2 = *reinterpret_cast<const double2*>(sg + rows64_chunk(k, 2)), g3 = *reinterpret_cast<const double2*>(sg + rows64_chunk(k, 3));
+				ga[0] = g0.x; ga[1] = g0.y; ga[2] = g1.x; ga[3] = g1.y; gb[0] = g2.x; gb[1] = g2.y; gb[2] = g3.x; gb[3] = g3.y;
+				rc = src[k];
+			}
 			double pc[4];
 			if(RECON == FR_FIRST) { for(int q = 0; q < 4; q++) pc[q] = uc[q]; }
 			else cons2prim(A.gas, uc, pc);
 			const unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
 			const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
+			// all midpoints are fetched before the extrapolations start (one shared-memory round trip instead of four)
+			const bool quad = nb[3] != NB_NONE;           // only the fourth slot can be empty (triangles)
+			double2 grj[4];
 			#pragma unroll
 			for(int j = 0; j < 4; j++) {
-				if(j == 3 && nb[3] == NB_NONE) break;      // only the fourth slot can be empty (triangles)
+				grj[j] = make_double2(0, 0);
+				if(RECON == FR_LINEAR && (j < 3 || quad)) grj[j] = sgr[cf[j] & 0x7FFFu];
+			}
+			#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				if(j == 3 && !quad) break;
 				const int e = (int)(cf[j] & 0x7FFFu);
 				double pf[4];
-				if(RECON == FR_LINEAR) {
-					const double2 gr = sgr[e];
-					extrapolate_prim(pc, ga, gb, gr.x, gr.y, rc.x, rc.y, pf);
-				} else { for(int q = 0; q < 4; q++) pf[q] = pc[q]; }
-				double *const dst = ((cf[j] & 0x8000u) ? fsR : fsL) + 4*e;
-				*reinterpret_cast<double2*>(dst) = make_double2(pf[0], pf[1]);
-				*reinterpret_cast<double2*>(dst + 2) = make_double2(pf[2], pf[3]);
+				if(RECON == FR_LINEAR) extrapolate_prim(pc, ga, gb, grj[j].x, grj[j].y, rc.x, rc.y, pf);
+				else { for(int q = 0; q < 4; q++) pf[q] = pc[q]; }
+				double2 *const dst = ((cf[j] & 0x8000u) ? fsR : fsL) + e;
+				dst[0] = make_double2(pf[0], pf[1]);
+				dst[EP] = make_double2(pf[2], pf[3]);
 			}
 		}
 		if(have_next && tid < Dn.nh) gnext = M.thalo[Dn.h0 + tid];
@@ -260,10 +300,10 @@ face_kernel(const FaceArgs A)
 			const double nx = nrm.x, ny = nrm.y;
 			const BCEntry &bc = A.gas.bc[Rf & 15u];
 			double sl[4], sr[4];       // face states: conserved (first order) / primitive; MUSCL: cell states
-			if(L < (unsigned)D.nc) lds4(fsL + 4*e, sl);
+			if(L < (unsigned)D.nc) ldp4(fsL + e, EP, sl);
 			else halo_side_state<RECON>(A, hu, hg, hrc, (int)L - D.nc, MIDS ? M.fgr[D.e0 + e] : make_double2(0,0), sl);
 			if(!bnd) {
-				if(Rf < (unsigned)D.nc) lds4(fsR + 4*e, sr);
+				if(Rf < (unsigned)D.nc) ldp4(fsR + e, EP, sr);
 				else halo_side_state<RECON>(A, hu, hg, hrc, (int)Rf - D.nc, MIDS ? M.fgr[D.e0 + e] : make_double2(0,0), sr);
 			}
 			const int gidL = (VISC != VISC_NONE || RECON == FR_MUSCL) ? tile_global(M, t, D.c0, D.nc, L) : 0;
@@ -362,9 +402,9 @@ face_kernel(const FaceArgs A)
 				if(!bnd) srj += coj*muj/A.gas.Pr*len*len/M.area[gidR];
 			}
 			// the entry's slots now carry its flux and the two spectral radii
-			*reinterpret_cast<double2*>(fsL + 4*e) = make_double2(f[0], f[1]);
-			*reinterpret_cast<double2*>(fsL + 4*e + 2) = make_double2(f[2], f[3]);
-			*reinterpret_cast<double2*>(fsR + 4*e) = make_double2(sri, srj);
+			fsL[e] = make_double2(f[0], f[1]);
+			fsL[e + EP] = make_double2(f[2], f[3]);
+			fsR[e] = make_double2(sri, srj);
 		}
 		if(!halo_ready) cp_async_wait_all();
 		__syncthreads();
@@ -392,8 +432,8 @@ face_kernel(const FaceArgs A)
 			for(int j = 0; j < 4; j++) {
 				const bool have = !(j == 3 && nb[3] == NB_NONE);
 				const int e = have ? (int)(cf[j] & 0x7FFFu) : 0;
-				lds4(fsL + 4*e, f[j]);
-				sr[j] = *reinterpret_cast<const double2*>(fsR + 4*e);
+				ldp4(fsL + e, EP, f[j]);
+				sr[j] = fsR[e];
 				sg_[j] = !have ? 0.0 : ((cf[j] & 0x8000u) ? 1.0 : -1.0);
 			}
 			#pragma unroll

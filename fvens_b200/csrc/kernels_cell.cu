@@ -16,6 +16,12 @@ namespace fvg {
 enum { GM_ZERO = 0, GM_GG = 1, GM_WLS = 2, GM_GIVEN = 3 };
 enum { LM_NONE = 0, LM_BJ = 1, LM_VENKAT = 2 };
 
+/// 32-byte row from shared memory, halves at double offsets o0 and o1 (0 and 2 in either order)
+__device__ __forceinline__ void lds4h(const double *p, int o0, int o1, double v[4]) {
+	const double2 a = *reinterpret_cast<const double2*>(p + o0), b = *reinterpret_cast<const double2*>(p + o1);
+	v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
 /// Shared-memory carve-up of the cell kernel
 struct CellSmem {
 	int sp, src, sgr, sn, slen, scl, sV, sclen, bar, total;
@@ -44,7 +50,7 @@ template <int GRAD, int LIM, bool PRIM_IN>
 __global__ void __launch_bounds__(CELL_BLOCK, FVG_CELL_MINB)
 cell_kernel(const CellArgs A)
 {
-	extern __shared__ __align__(128) unsigned char smraw[];
+	extern __shared__ __align__(1024) unsigned char smraw[];
 	const DMesh &M = A.m;
 	constexpr bool MIDS = LIM != LM_NONE || GRAD == GM_GG;
 	constexpr bool METRICS = GRAD == GM_GG;
@@ -119,11 +125,16 @@ cell_kernel(const CellArgs A)
 		for(int k = tid; k < nrows; k += CELL_BLOCK) {
 			if(k < grow0) {
 				if(PRIM_IN) continue;
-				double uc[4], up[4];
-				lds4(sp + 4*k, uc);
+				// 32-byte rows, one per thread: threads 4..7 of every 8 take the halves in the opposite order, which
+				// spreads a quarter warp over all 32 banks (plain row-order access is a 2-way conflict)
+				const int hb = (tid >> 2) & 1;
+				const double2 h0 = *reinterpret_cast<const double2*>(sp + 4*k + 2*hb);
+				const double2 h1 = *reinterpret_cast<const double2*>(sp + 4*k + 2*(1 - hb));
+				const double uc[4] = {hb ? h1.x : h0.x, hb ? h1.y : h0.y, hb ? h0.x : h1.x, hb ? h0.y : h1.y};
+				double up[4];
 				cons2prim(A.gas, uc, up);
-				*reinterpret_cast<double2*>(sp + 4*k) = make_double2(up[0], up[1]);
-				*reinterpret_cast<double2*>(sp + 4*k + 2) = make_double2(up[2], up[3]);
+				*reinterpret_cast<double2*>(sp + 4*k + 2*hb) = hb ? make_double2(up[2], up[3]) : make_double2(up[0], up[1]);
+				*reinterpret_cast<double2*>(sp + 4*k + 2*(1 - hb)) = hb ? make_double2(up[0], up[1]) : make_double2(up[2], up[3]);
 			} else {
 				const int ge = e0 + tb.x + (k - grow0);
 				const unsigned LR = M.fLR[ge];
@@ -154,8 +165,14 @@ cell_kernel(const CellArgs A)
 		const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
 		const bool quad = nb[3] != NB_NONE;       // only the fourth slot can be empty (triangles)
 		const double2 rci = src[k];
+		// Threads 4..7 of every 8 work on the variables in the order (2,3,0,1): they read the second half of every
+		// 32-byte state row first. Nothing below depends on which variable is which (gradient, limiter and their
+		// inputs are per variable), so the permutation costs nothing and is undone by the store addresses; it makes
+		// the own-row access conflict-free and spreads the neighbour gathers over all 8 bank groups instead of 4.
+		const int hb = (tid >> 2) & 1;
+		const int o0 = 2*hb, o1 = 2 - 2*hb;
 		double pi[4];
-		lds4(sp + 4*k, pi);
+		lds4h(sp + 4*k, o0, o1, pi);
 
 		double acc[8] = {0,0,0,0,0,0,0,0};   // GG: gradient sums; WLS: right-hand side. Index d + 2*v
 		double dmin[4] = {0,0,0,0}, dmax[4] = {0,0,0,0};
@@ -169,7 +186,7 @@ cell_kernel(const CellArgs A)
 				const bool bndj = nb[j] == NB_BND;
 				const unsigned nj = bndj ? (unsigned)(grow0 + le - tb.x) : nb[j];
 				double pj[4];
-				lds4(sp + 4*nj, pj);
+				lds4h(sp + 4*nj, o0, o1, pj);
 				const double2 rj = src[nj];
 				if(GRAD == GM_WLS) {
 					const double dx = rci.x - rj.x, dy = rci.y - rj.y;
@@ -221,10 +238,11 @@ cell_kernel(const CellArgs A)
 			}
 		}
 		else if(GRAD == GM_GG) { for(int q = 0; q < 8; q++) g[q] = acc[q]; }
-		else if(GRAD == GM_GIVEN) { ld4(A.gin + 8*(size_t)i, g); ld4(A.gin + 8*(size_t)i + 4, g+4); }
+		else if(GRAD == GM_GIVEN) { ld4(A.gin + 8*(size_t)i + 2*o0, g); ld4(A.gin + 8*(size_t)i + 2*o1, g+4); }
 		else { for(int q = 0; q < 8; q++) g[q] = 0.0; }
 
-		if(A.gu) { st4(A.gu + 8*(size_t)i, g); st4(A.gu + 8*(size_t)i + 4, g+4); }
+		// GradBlock rows hold (d/dx, d/dy) of variables 0..3 in order: this thread's first two variables are 0,1 or 2,3
+		if(A.gu) { st4(A.gu + 8*(size_t)i + 2*o0, g); st4(A.gu + 8*(size_t)i + 2*o1, g+4); }
 		if(!A.lg) continue;
 
 		if(LIM != LM_NONE) {
@@ -271,7 +289,7 @@ cell_kernel(const CellArgs A)
 				g[2*v] *= lim; g[2*v+1] *= lim;
 			}
 		}
-		st4(A.lg + 8*(size_t)i, g); st4(A.lg + 8*(size_t)i + 4, g+4);
+		st4(A.lg + 8*(size_t)i + 2*o0, g); st4(A.lg + 8*(size_t)i + 2*o1, g+4);
 	}
 }
 

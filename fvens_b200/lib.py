@@ -54,7 +54,9 @@ class MeshInfo(C.Structure):
     _fields_ = [("ncell", C.c_int), ("nbface", C.c_int), ("naface", C.c_int), ("ntile", C.c_int),
                 ("tile_cells", C.c_int), ("nstream", C.c_int), ("ncut_dup", C.c_int),
                 ("max_colours", C.c_int), ("reorder", C.c_int), ("mean_neighbour_distance", C.c_double),
-                ("nghost", C.c_int), ("nsend", C.c_int), ("rank", C.c_int), ("nranks", C.c_int)]
+                ("nghost", C.c_int), ("nsend", C.c_int), ("rank", C.c_int), ("nranks", C.c_int),
+                ("entry_capacity", C.c_int), ("halo_capacity", C.c_int),
+                ("bank_groups", C.c_longlong), ("bank_conflict_groups", C.c_longlong)]
 
 
 class Physics(C.Structure):

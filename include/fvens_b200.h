@@ -108,6 +108,9 @@ typedef struct {
 	int ncell, nbface, naface, ntile, tile_cells, nstream, ncut_dup, max_colours, reorder;
 	double mean_neighbour_distance;   /* mean |i-j| over interior faces in device numbering */
 	int nghost, nsend, rank, nranks;  /* subdomain meshes: ghost cells, cells sent per exchange */
+	int entry_capacity, halo_capacity; /* per-tile staging capacities the kernels size their shared memory with */
+	long long bank_groups, bank_conflict_groups; /* (quarter-warp, local-face) groups of stream entries; groups in which two
+	                                     entries share a shared-memory bank residue (0 = conflict-free scatter/gather) */
 } fvg_mesh_info;
 
 int fvg_mesh_create(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, fvg_mesh **out);

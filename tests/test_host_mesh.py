@@ -159,19 +159,36 @@ def test_tiling_and_colouring_are_valid(reorder, tile):
                 key = (t, int(colour[e]), int(c))
                 assert key not in used
                 used.add(key)
-    # entries of a tile are ordered by kind: both cells in the tile, cut by the tile boundary, physical boundary,
-    # padding (the flux phase of the face kernel relies on warps being uniform in kind)
+    # entries of a tile are ordered by kind: both cells in the tile, cut by the tile boundary, physical boundary
+    # (the flux phase of the face kernel relies on warps being uniform in kind); padding entries may sit inside the
+    # first two kinds (unused positions of a bank residue class) and at the end
+    nconfl = ngroups = 0
     for t in range(info.ntile):
         fs = face[tile_of == t]
         kinds = []
-        for f in fs:
+        groups = {}
+        for p, f in enumerate(fs):
             if f < 0:
-                kinds.append(3)
-            elif f < um.nbface:
+                continue
+            f = int(f)
+            if f < um.nbface:
                 kinds.append(2)
-            else:
-                kinds.append(0 if len(tiles_of_face(int(f))) == 1 else 1)
+                continue
+            kinds.append(0 if len(tiles_of_face(f)) == 1 else 1)
+            # shared-memory bank residues: the entries that the 8 consecutive cells of a quarter warp reach through their
+            # local face j should sit in distinct residue classes mod 8
+            for side in (0, 1):
+                old = int(a["intfac"][f, side])
+                c = int(old2new[old])
+                if cell_tile[c] != t:
+                    continue
+                j = int(np.nonzero(a["elemface"][old] == f)[0][0])
+                groups.setdefault(((c - t0[t]) >> 3, j), {})[p] = p % 8     # keyed by entry: both cells of an entry in one group = one address
         assert (np.diff(kinds) >= 0).all()
+        ngroups += len(groups)
+        nconfl += sum(1 for g in groups.values() if len(set(g.values())) < len(g))
+    assert ngroups == info.bank_groups and nconfl == info.bank_conflict_groups
+    assert nconfl <= 0.03*ngroups
 
 
 def test_tiles_shrink_to_fit_the_halo_capacity():
