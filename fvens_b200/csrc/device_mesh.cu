@@ -136,6 +136,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	// capacities of a tile's shared-memory staging areas: halo cells and stream entries
 	const int HMAX = std::max(32, (3*TC/8 + 31)/32*32);
 	const int EMAX = (2*TC + TC/8 + 31)/32*32;
+	const int LCAP = (2*TC + TC/4 + 31)/32*32;    // cap on a tile's stream segment including bank padding
 	const int reorder = opts ? opts->reorder : FVG_REORDER_NONE;
 	auto rank_of = [&](int o) { return cell_rank ? cell_rank[o] : 0; };
 	if(cell_rank) for(int o = 0; o < n; o++) if(cell_rank[o] < 0 || cell_rank[o] >= nranks) { set_error("fvg_mesh_create: cell_rank entry out of range"); return FVG_ERR_INVALID; }
@@ -410,6 +411,52 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 				}
 				setres(k, best);
 			}
+			// even out the residue classes of each kind (their longest class sets the padding): move entries from the
+			// fullest class to emptier ones where the target residue is still free in the entry's groups
+			for(int q = 0; q < 2 && bank_colour; q++)
+				for(int iter = 0; iter < 64; iter++) {
+					int cmax = 0;
+					for(int c = 1; c < 8; c++) if(rcnt[q][c] > rcnt[q][cmax]) cmax = c;
+					bool moved = false;
+					for(int k = 0; k < nr && !moved; k++) {
+						if(kind[k] != q || res[k] != cmax) continue;
+						int tgt = -1;
+						for(int c = 0; c < 8; c++) {
+							if(rcnt[q][c] + 1 >= rcnt[q][cmax] || (tgt >= 0 && rcnt[q][c] >= rcnt[q][tgt])) continue;
+							bool fr = true;
+							for(int s2 = 0; s2 < 2; s2++) if(eg[2*k+s2] >= 0 && at[(size_t)eg[2*k+s2]*8+c] >= 0) fr = false;
+							if(fr) tgt = c;
+						}
+						if(tgt < 0) continue;
+						rcnt[q][cmax]--;
+						for(int s2 = 0; s2 < 2; s2++) if(eg[2*k+s2] >= 0 && at[(size_t)eg[2*k+s2]*8+cmax] == k) at[(size_t)eg[2*k+s2]*8+cmax] = -1;
+						setres(k, tgt);
+						moved = true;
+					}
+					if(!moved) break;
+				}
+			// positions: kind 0 at 8*i + residue from 0, kind 1 likewise after it, boundary entries contiguous after both
+			int seg[2], nextb = 0;
+			auto place = [&]() {
+				for(int q = 0; q < 2; q++) { int mx = 0; for(int c = 0; c < 8; c++) mx = std::max(mx, rcnt[q][c]); seg[q] = 8*mx; }
+				int next[2][8];
+				for(int q = 0; q < 2; q++) for(int c = 0; c < 8; c++) next[q][c] = (q == 0 ? 0 : seg[0]) + c;
+				nextb = seg[0] + seg[1];
+				for(int k = 0; k < nr; k++) {
+					if(kind[k] == 2) epos[r0+k] = nextb++;
+					else { epos[r0+k] = next[kind[k]][res[k]]; next[kind[k]][res[k]] += 8; }
+				}
+				return (nextb + 7)/8*8;
+			};
+			int len = place();
+			if(len > LCAP) {
+				// the padding would push the kernels' per-entry staging past the shared-memory budget of two CTAs per SM:
+				// this tile keeps its entries densely packed instead (bank conflicts in this tile only)
+				int sq[2] = {0, 0};
+				for(int q = 0; q < 2; q++) for(int c = 0; c < 8; c++) rcnt[q][c] = 0;
+				for(int k = 0; k < nr; k++) if(kind[k] < 2) { res[k] = sq[kind[k]]++ & 7; rcnt[kind[k]][res[k]]++; }
+				len = place();
+			}
 			std::fill(gcnt.begin(), gcnt.end(), 0);
 			for(int k = 0; k < nr; k++)          // an entry whose two cells share a group (same address: a broadcast) counts once
 				for(int s2 = 0; s2 < 2; s2++) if(eg[2*k+s2] >= 0 && !(s2 == 1 && eg[2*k] == eg[2*k+1])) gcnt[(size_t)eg[2*k+s2]*8+res[k]]++;
@@ -418,17 +465,6 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 				for(int c = 0; c < 8; c++) { members += gcnt[g*8+c]; distinct += gcnt[g*8+c] > 0; }
 				if(members > 0) { ngroups++; if(distinct < members) nconfl++; }
 			}
-			// positions: kind 0 at 8*i + residue from 0, kind 1 likewise after it, boundary entries contiguous after both
-			int seg[2];
-			for(int q = 0; q < 2; q++) { int mx = 0; for(int c = 0; c < 8; c++) mx = std::max(mx, rcnt[q][c]); seg[q] = 8*mx; }
-			int next[2][8];
-			for(int q = 0; q < 2; q++) for(int c = 0; c < 8; c++) next[q][c] = (q == 0 ? 0 : seg[0]) + c;
-			int nextb = seg[0] + seg[1];
-			for(int k = 0; k < nr; k++) {
-				if(kind[k] == 2) epos[r0+k] = nextb++;
-				else { epos[r0+k] = next[kind[k]][res[k]]; next[kind[k]][res[k]] += 8; }
-			}
-			const int len = (nextb + 3)/4*4;
 			tbnd[t] = make_int4(seg[0], seg[0] + seg[1], cnt[2], len - nr);
 			fsoff[t+1] = fsoff[t] + len;
 			emax_seen = std::max(emax_seen, len);
@@ -440,8 +476,14 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	const int PAD = INT_MIN;
 	std::vector<int> sface((size_t)ns, PAD);    // global face of each entry, -1-f for the second copy, PAD for padding
 	std::vector<int> scolour((size_t)ns, MAXCOL-1);
-	for(int t = 0; t < ntile; t++)
+	// ford: the positions of a tile's real (non-padding) entries in ascending order; the flux phase walks this list so
+	// that its rounds are full whatever the padding
+	std::vector<unsigned short> ford((size_t)ns, 0);
+	for(int t = 0; t < ntile; t++) {
 		for(int k = roff[t]; k < roff[t+1]; k++) { sface[(size_t)fsoff[t] + epos[k]] = rent[k]; scolour[(size_t)fsoff[t] + epos[k]] = ecol[k]; }
+		int i = 0;
+		for(int e = fsoff[t]; e < fsoff[t+1]; e++) if(sface[e] != PAD) ford[(size_t)fsoff[t] + i++] = (unsigned short)(e - fsoff[t]);
+	}
 
 	// ---- per-entry arrays with tile-local cell indices
 	std::vector<unsigned> &fLR = m->h_fLR;
@@ -567,7 +609,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	UP(cloc, cloc) UP(drc, rc) UP(area, area) UP(V, wlsV) UP(clength, clength)
 	UP(tcell0, tcell0) UP(thoff, thoff) UP(thalo, thalo)
 	UP(fsoff, fsoff) UP(tbnd, tbnd) UP(fLR, fLR) UP(fn, fn) UP(flen, flen) UP(fgr, fgr)
-	UP(m->h_fref, fref) UP(bcell, bcell) UP(m->h_bentry, bentry) UP(bslot, bslot) UP(rcbp, rcbp)
+	UP(ford, ford) UP(m->h_fref, fref) UP(bcell, bcell) UP(m->h_bentry, bentry) UP(bslot, bslot) UP(rcbp, rcbp)
 	UP(m->h_send_idx, send_idx)
 	if(m->identity_perm) { D.new2old = nullptr; D.old2new = nullptr; }
 	else { UP(d2g, new2old) D.old2new = nullptr; }

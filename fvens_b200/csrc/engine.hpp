@@ -64,6 +64,8 @@ struct DMesh {
 	const double2 *fn;      ///< unit normal, left -> right
 	const double *flen;
 	const double2 *fgr;     ///< face midpoint
+	const unsigned short *ford; ///< per tile: tile-local positions of its real (non-padding) entries, ascending; length = stream
+	                        ///< segment, the first (segment - tbnd.w) values are meaningful
 	const int *fref;        ///< reference face id (intfac index); duplicate copy of a cut face: -1-id; padding: INT_MIN
 	// per boundary face (reference order)
 	const int *bcell;       ///< device index of the interior cell

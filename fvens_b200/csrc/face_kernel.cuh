@@ -78,7 +78,7 @@ __device__ __forceinline__ double muscl_term(double delta, double dlr) {
 /// planes): entry e then sits in bank group e mod 8, consecutive entries (phase B) are conflict-free, and the
 /// per-cell scatters / gathers of phases A and C are conflict-free by the placement of the entries (device_mesh.cu).
 struct FaceSmem {
-	int fsL, fsR, sgr, sn, slen, sLR, hu, hg, hrc, su, sg, src, scl, sar, cbuf, bar, red, total;   // byte offsets
+	int fsL, fsR, sgr, sn, slen, sLR, sord, hu, hg, hrc, su, sg, src, scl, sar, cbuf, bar, red, total;   // byte offsets
 	__host__ __device__ FaceSmem(int TC, int EMAX, int HMAX, bool mids, bool linear) {
 		int o = 0;
 		su = o; o += TC*32;                    // own cells: state, reconstruction gradient (both hardware-swizzled: keep them
@@ -90,6 +90,7 @@ struct FaceSmem {
 		sn = o; o += EMAX*16;
 		slen = o; o += EMAX*8;
 		sLR = o; o += EMAX*4;
+		sord = o; o += EMAX*2;
 		hu = o; o += HMAX*32;
 		hg = o; o += mids ? HMAX*64 : 0;
 		hrc = o; o += mids ? HMAX*16 : 0;
@@ -119,13 +120,13 @@ __device__ __forceinline__ void halo_side_state(const FaceArgs &A, const double 
 }
 
 /// Descriptor of one tile (all uniform across the CTA)
-struct TileDesc { int c0, nc, h0, nh, e0, ne, ecut; };
+struct TileDesc { int c0, nc, h0, nh, e0, ne, nreal; };
 __device__ __forceinline__ TileDesc load_tile_desc(const DMesh &M, int t) {
 	TileDesc D;
 	D.c0 = M.tcell0[t]; D.nc = M.tcell0[t+1] - D.c0;
 	D.h0 = M.thoff[t]; D.nh = M.thoff[t+1] - D.h0;
 	D.e0 = M.fsoff[t]; D.ne = M.fsoff[t+1] - D.e0;
-	D.ecut = M.tbnd[t].x;
+	D.nreal = D.ne - M.tbnd[t].w;
 	return D;
 }
 
@@ -164,6 +165,7 @@ face_kernel(const __grid_constant__ FaceArgs A)
 	double2 *const sn = reinterpret_cast<double2*>(smraw + S.sn);
 	double *const slen = reinterpret_cast<double*>(smraw + S.slen);
 	unsigned *const sLR = reinterpret_cast<unsigned*>(smraw + S.sLR);
+	const unsigned short *const sord = reinterpret_cast<const unsigned short*>(smraw + S.sord);
 	double *const hu = reinterpret_cast<double*>(smraw + S.hu);
 	double *const hg = reinterpret_cast<double*>(smraw + S.hg);
 	double2 *const hrc = reinterpret_cast<double2*>(smraw + S.hrc);
@@ -195,8 +197,9 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		bulk_g2s(smraw + S.sar + buf*S.cbuf, M.area + (D.c0 - (int)aoff), abytes, bar);
 	};
 	auto issue_B = [&](const TileDesc &D) {
-		mbar_expect_tx(bar + 1, (unsigned)D.ne*(16u + 8u + 4u));
+		mbar_expect_tx(bar + 1, (unsigned)D.ne*(16u + 8u + 4u + 2u));
 		bulk_g2s(sLR, M.fLR + D.e0, (unsigned)D.ne*4u, bar + 1);
+		bulk_g2s(smraw + S.sord, M.ford + D.e0, (unsigned)D.ne*2u, bar + 1);
 		bulk_g2s(sn, M.fn + D.e0, (unsigned)D.ne*16u, bar + 1);
 		bulk_g2s(slen, M.flen + D.e0, (unsigned)D.ne*8u, bar + 1);
 	};
@@ -280,17 +283,16 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		}
 		if(have_next && tid < Dn.nh) gnext = M.thalo[Dn.h0 + tid];
 		mbar_wait(bar + 1, par);
+		cp_async_wait_all();        // this tile's halo rows: gathered since the previous tile's phase B ended
 		__syncthreads();
 		// group A buffers are free: the next tile's phase-A inputs (and its stencil/area into the other C buffer)
 		if(tid == 0 && have_next) { fence_proxy_async(); issue_AC(Dn, (int)(par ^ 1u)); }
 
-		// ---- phase B: fluxes, one stream entry per thread and round. The halo rows are needed from entry `ecut`
-		// on: the round that reaches it first waits for the gathers (uniform across the CTA: the test is on the round)
-		bool halo_ready = false;
-		for(int eb = 0; eb < D.ne; eb += FACE_BLOCK) {
-			if(!halo_ready && eb + FACE_BLOCK > D.ecut) { cp_async_wait_all(); __syncthreads(); halo_ready = true; }
-			const int e = eb + tid;
-			if(e >= D.ne) continue;
+		// ---- phase B: fluxes, one real stream entry per thread and round (the list `sord` skips the padding entries, so
+		// the rounds are full: consecutive threads still take nearly consecutive entries)
+		for(int ib = 0; ib < D.nreal; ib += FACE_BLOCK) {
+			if(ib + tid >= D.nreal) continue;
+			const int e = (int)sord[ib + tid];
 			const unsigned LR = sLR[e];
 			if(LR == LR_PAD) continue;
 			const double2 nrm = sn[e];
@@ -406,7 +408,6 @@ face_kernel(const __grid_constant__ FaceArgs A)
 			fsL[e + EP] = make_double2(f[2], f[3]);
 			fsR[e] = make_double2(sri, srj);
 		}
-		if(!halo_ready) cp_async_wait_all();
 		__syncthreads();
 		// group B buffers are free: the next tile's entry metadata and halo rows
 		if(have_next) {

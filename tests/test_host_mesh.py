@@ -188,7 +188,8 @@ def test_tiling_and_colouring_are_valid(reorder, tile):
         ngroups += len(groups)
         nconfl += sum(1 for g in groups.values() if len(set(g.values())) < len(g))
     assert ngroups == info.bank_groups and nconfl == info.bank_conflict_groups
-    assert nconfl <= 0.03*ngroups
+    # (tiny tiles fall back to dense packing when the padding would exceed the staging capacity)
+    assert nconfl <= (0.03 if tile >= 128 else 0.15)*ngroups
 
 
 def test_tiles_shrink_to_fit_the_halo_capacity():
