@@ -221,6 +221,10 @@ face_kernel(const __grid_constant__ FaceArgs A)
 	if(t >= M.ntile) return;
 	if(tid == 0 && (smem_u32(smraw) & 1023u) != 0) __trap();      // the swizzle formulas assume this alignment
 	TileDesc D = load_tile_desc(M, t);
+	// descriptors run two tiles ahead of the computation and the next tile's halo index one tile ahead, so that
+	// neither global load is waited for where it is consumed
+	TileDesc Dn = D;
+	if(t + (int)gridDim.x < M.ntile) Dn = load_tile_desc(M, t + (int)gridDim.x);
 	if(tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
 	__syncthreads();
 	if(tid == 0) { issue_AC(D, 0); issue_B(D); }
@@ -234,9 +238,10 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		// the next tile's descriptor and this thread's halo index for it are in flight during phase A
 		const int tn = t + (int)gridDim.x;
 		const bool have_next = tn < M.ntile;
-		TileDesc Dn = D;
 		int gnext = 0;
-		if(have_next) { Dn = load_tile_desc(M, tn); }
+		if(have_next && tid < Dn.nh) gnext = M.thalo[Dn.h0 + tid];
+		TileDesc Dnn = Dn;
+		if(tn + (int)gridDim.x < M.ntile) Dnn = load_tile_desc(M, tn + (int)gridDim.x);
 
 		// ---- phase A: face states of the own cells
 		mbar_wait(bar, par);
@@ -281,7 +286,6 @@ face_kernel(const __grid_constant__ FaceArgs A)
 				dst[EP] = make_double2(pf[2], pf[3]);
 			}
 		}
-		if(have_next && tid < Dn.nh) gnext = M.thalo[Dn.h0 + tid];
 		mbar_wait(bar + 1, par);
 		cp_async_wait_all();        // this tile's halo rows: gathered since the previous tile's phase B ended
 		__syncthreads();
@@ -474,7 +478,7 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		}
 		// phase C reads the flux slots that the next tile's phase A overwrites
 		__syncthreads();
-		t = tn; D = Dn;
+		t = tn; D = Dn; Dn = Dnn;
 	}
 }
 
