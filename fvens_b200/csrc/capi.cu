@@ -7,7 +7,9 @@
  */
 #include "engine.hpp"
 #include "../host/mesh.hpp"
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -69,7 +71,7 @@ static int limiter_mode(int recon)
 }
 
 /// Pass A on a device-ordered conserved state: fills f->d_lg and/or f->d_gu
-static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s)
+static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s, int tile0 = 0, int tile1 = -1)
 {
 	const FlowPlan &P = f->plan;
 	if(!P.order2) return 0;
@@ -77,6 +79,7 @@ static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s)
 	a.m = f->mesh->d; a.gas = f->gas; a.u = u; a.ug = nullptr; a.gin = nullptr;
 	a.bnd_policy = P.bnd_policy;
 	a.prefetch_distance = f->prefetch_distance;
+	a.tile0 = tile0; a.tile1 = tile1;
 	int rc;
 	if(P.recon == FVG_RECON_WENO) {
 		a.lg = nullptr; a.gu = f->d_gu;
@@ -141,7 +144,7 @@ int make_row_tensor_map(CUtensorMap *tm, const double *base, size_t nrows, int w
 }
 
 static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumulate, int gettimesteps,
-                         double *res, double *dtm, double cfl, double *unew, cudaStream_t s)
+                         double *res, double *dtm, double cfl, double *unew, cudaStream_t s, int tile0 = 0, int tile1 = -1)
 {
 	const FlowPlan &P = f->plan;
 	FaceArgs a;
@@ -150,6 +153,7 @@ static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumul
 	a.epilogue = epilogue; a.accumulate = accumulate; a.gettimesteps = gettimesteps;
 	a.res = res; a.dtm = dtm; a.cfl = cfl; a.unew = unew; a.partial = f->d_partial;
 	a.prefetch_distance = f->prefetch_distance;
+	a.tile0 = tile0; a.tile1 = tile1;
 	const int recon = !P.order2 ? FR_FIRST : (P.recon == FVG_RECON_VANALBADA ? FR_MUSCL : FR_LINEAR);
 	int rt = make_row_tensor_map(&a.tm_u, u, (size_t)a.m.ncell, 4, tile_box_rows(a.m.TC));
 	if(rt == 0 && recon == FR_LINEAR) rt = make_row_tensor_map(&a.tm_g, a.lg, (size_t)a.m.ncell, 8, tile_box_rows(a.m.TC));
@@ -373,6 +377,11 @@ void fvg_flow_destroy(fvg_flow *f)
 	if(!f) return;
 	for(void *p : f->allocs) cudaFree(p);
 	if(f->h_norm) cudaFreeHost(f->h_norm);
+	for(cudaEvent_t e : f->pipe.ev_up) cudaEventDestroy(e);
+	for(cudaEvent_t e : f->pipe.ev_face) cudaEventDestroy(e);
+	if(f->pipe.s_in) cudaStreamDestroy(f->pipe.s_in);
+	if(f->pipe.s_run) cudaStreamDestroy(f->pipe.s_run);
+	if(f->pipe.s_out) cudaStreamDestroy(f->pipe.s_out);
 	delete f;
 }
 
@@ -448,6 +457,61 @@ int fvg_residual(fvg_flow *f, const double *d_u, double *d_res, int accumulate, 
 	return 0;
 }
 
+/** Plan of the chunked host-buffer pipeline. The tiles are cut into K ranges of consecutive tiles (compact patches
+ * of the mesh, since tiles follow the locality order). A chunk's gradient pass needs the state rows of its own and
+ * its halo cells, i.e. the uploads of the chunks in deps[c]; its face pass needs the gradient passes of the same
+ * chunks. Uploading the chunks in a sweep along the longer axis of the domain makes these sets complete early, so
+ * the first residual rows travel back to the host while most of the state is still on its way in. */
+static void plan_host_pipe(fvg_flow *f)
+{
+	fvg_flow::HostPipe &P = f->pipe;
+	P.planned = true;
+	P.K = 0;
+	const fvg_mesh *m = f->mesh;
+	const int ntile = m->d.ntile;
+	int K = 48;
+	if(const char *ev = getenv("FVG_HOST_CHUNKS")) K = atoi(ev);
+	K = std::min(std::min(K, 64), ntile/8);
+	if(K < 2 || !m->identity_perm || m->nranks > 1 || m->h_thoff.empty()) return;
+	P.tile0.resize(K+1);
+	for(int c = 0; c <= K; c++) P.tile0[c] = (int)((long long)ntile*c/K);
+	std::vector<int> chunk_of_tile(ntile);
+	for(int c = 0; c < K; c++) for(int t = P.tile0[c]; t < P.tile0[c+1]; t++) chunk_of_tile[t] = c;
+	auto chunk_of_cell = [&](int i) {
+		const int t = (int)(std::upper_bound(m->h_tcell0.begin(), m->h_tcell0.end(), i) - m->h_tcell0.begin()) - 1;
+		return chunk_of_tile[t];
+	};
+	P.deps.assign(K, 0ull);
+	std::vector<double> cx(K, 0.0), cy(K, 0.0);
+	double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+	for(int c = 0; c < K; c++) {
+		P.deps[c] |= 1ull << c;
+		for(int t = P.tile0[c]; t < P.tile0[c+1]; t++)
+			for(int h = m->h_thoff[t]; h < m->h_thoff[t+1]; h++)
+				if(m->h_thalo[h] < m->d.ncell) P.deps[c] |= 1ull << chunk_of_cell(m->h_thalo[h]);
+		const int i0 = m->h_tcell0[P.tile0[c]], i1 = m->h_tcell0[P.tile0[c+1]];
+		for(int i = i0; i < i1; i++) {
+			const double x = m->h_rc[2*(size_t)i], y = m->h_rc[2*(size_t)i+1];
+			cx[c] += x; cy[c] += y;
+			lo[0] = std::min(lo[0], x); hi[0] = std::max(hi[0], x); lo[1] = std::min(lo[1], y); hi[1] = std::max(hi[1], y);
+		}
+		cx[c] /= std::max(1, i1 - i0); cy[c] /= std::max(1, i1 - i0);
+	}
+	const std::vector<double> &key = (hi[0] - lo[0] >= hi[1] - lo[1]) ? cx : cy;
+	P.order.resize(K);
+	for(int c = 0; c < K; c++) P.order[c] = c;
+	std::stable_sort(P.order.begin(), P.order.end(), [&](int a, int b) { return key[a] < key[b]; });
+	bool ok = cudaStreamCreateWithFlags(&P.s_in, cudaStreamNonBlocking) == cudaSuccess
+	       && cudaStreamCreateWithFlags(&P.s_run, cudaStreamNonBlocking) == cudaSuccess
+	       && cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking) == cudaSuccess;
+	P.ev_up.resize(K); P.ev_face.resize(K);
+	for(int c = 0; c < K && ok; c++)
+		ok = cudaEventCreateWithFlags(&P.ev_up[c], cudaEventDisableTiming) == cudaSuccess
+		  && cudaEventCreateWithFlags(&P.ev_face[c], cudaEventDisableTiming) == cudaSuccess;
+	if(!ok) { cudaGetLastError(); return; }
+	P.K = K;
+}
+
 int fvg_residual_host(fvg_flow *f, const double *h_u, double *h_res, int accumulate, int gettimesteps, double *h_dtm)
 {
 	if(!f || !h_u || !h_res || (gettimesteps && !h_dtm)) { set_error("fvg_residual_host: null argument"); return FVG_ERR_INVALID; }
@@ -457,6 +521,48 @@ int fvg_residual_host(fvg_flow *f, const double *h_u, double *h_res, int accumul
 	if((rc = ensure(f, &f->d_hu, 4*n)) != 0) return rc;
 	if((rc = ensure(f, &f->d_hr, 4*n)) != 0) return rc;
 	if((rc = ensure(f, &f->d_hdt, n)) != 0) return rc;
+	if(!f->pipe.planned) plan_host_pipe(f);
+	const fvg_flow::HostPipe &P = f->pipe;
+	if(P.K >= 2 && !accumulate && f->plan.recon != FVG_RECON_WENO && !f->timing) {
+		// chunked pipeline: uploads in sweep order on one stream, the two passes per chunk on a second one as soon
+		// as their inputs are complete, downloads of finished chunks on a third (PCIe is full duplex)
+		const std::vector<int> &tc0 = f->mesh->h_tcell0;
+		std::vector<int> pos(P.K);
+		for(int j = 0; j < P.K; j++) pos[P.order[j]] = j;
+		unsigned long long uploaded = 0, cells_done = 0, faces_done = 0;
+		for(int j = 0; j < P.K; j++) {
+			const int c = P.order[j];
+			const size_t i0 = (size_t)tc0[P.tile0[c]], i1 = (size_t)tc0[P.tile0[c+1]];
+			FVG_CUDA(cudaMemcpyAsync(f->d_hu + 4*i0, h_u + 4*i0, 4*(i1 - i0)*sizeof(double), cudaMemcpyHostToDevice, P.s_in));
+			FVG_CUDA(cudaEventRecord(P.ev_up[j], P.s_in));
+			uploaded |= 1ull << c;
+			bool waited = false;
+			// gradient passes whose inputs are now complete (in upload order), then the face passes they release
+			for(int q = 0; q < P.K; q++) {
+				const int d = P.order[q];
+				if((cells_done >> d) & 1ull || (P.deps[d] & ~uploaded) != 0) continue;
+				if(!waited) { FVG_CUDA(cudaStreamWaitEvent(P.s_run, P.ev_up[j], 0)); waited = true; }
+				if((rc = run_gradient_pass(f, f->d_hu, P.s_run, P.tile0[d], P.tile0[d+1])) != 0) return rc;
+				cells_done |= 1ull << d;
+			}
+			for(int q = 0; q < P.K; q++) {
+				const int d = P.order[q];
+				if((faces_done >> d) & 1ull || (P.deps[d] & ~cells_done) != 0) continue;
+				if((rc = run_face_pass(f, f->d_hu, EP_RESIDUAL, 0, gettimesteps, f->d_hr, f->d_hdt, 0.0, nullptr, P.s_run,
+				                       P.tile0[d], P.tile0[d+1])) != 0) return rc;
+				faces_done |= 1ull << d;
+				FVG_CUDA(cudaEventRecord(P.ev_face[d], P.s_run));
+				FVG_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_face[d], 0));
+				const size_t a0 = (size_t)tc0[P.tile0[d]], a1 = (size_t)tc0[P.tile0[d+1]];
+				FVG_CUDA(cudaMemcpyAsync(h_res + 4*a0, f->d_hr + 4*a0, 4*(a1 - a0)*sizeof(double), cudaMemcpyDeviceToHost, P.s_out));
+				if(gettimesteps) FVG_CUDA(cudaMemcpyAsync(h_dtm + a0, f->d_hdt + a0, (a1 - a0)*sizeof(double), cudaMemcpyDeviceToHost, P.s_out));
+			}
+		}
+		FVG_CUDA(cudaStreamSynchronize(P.s_out));
+		FVG_CUDA(cudaStreamSynchronize(P.s_run));
+		if(faces_done != (P.K == 64 ? ~0ull : (1ull << P.K) - 1)) { set_error("fvg_residual_host: internal error, chunk schedule incomplete"); return FVG_ERR_INVALID; }
+		return 0;
+	}
 	cudaStream_t s = nullptr;
 	FVG_CUDA(cudaMemcpyAsync(f->d_hu, h_u, 4*n*sizeof(double), cudaMemcpyHostToDevice, s));
 	// the reference adds into the caller's residual: upload it and accumulate on the device

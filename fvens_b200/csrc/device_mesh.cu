@@ -614,7 +614,9 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	if(m->identity_perm) { D.new2old = nullptr; D.old2new = nullptr; }
 	else { UP(d2g, new2old) D.old2new = nullptr; }
 #undef UP
-	m->h_tcell0 = tcell0;
+	m->h_tcell0 = tcell0; m->h_thoff = thoff; m->h_thalo = thalo;
+	m->h_rc.resize(2*(size_t)nown);
+	for(int i = 0; i < nown; i++) { m->h_rc[2*(size_t)i] = drc[i].x; m->h_rc[2*(size_t)i+1] = drc[i].y; }
 	return 0;
 }
 

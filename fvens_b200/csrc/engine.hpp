@@ -104,7 +104,8 @@ struct fvg_mesh {
 	std::vector<unsigned> h_fLR;               ///< kept so that flow creation can patch in the BC indices
 	std::vector<int> h_bentry;
 	std::vector<int> h_markers;                ///< sorted distinct boundary markers = slots of the BC table
-	std::vector<int> h_tcell0;
+	std::vector<int> h_tcell0, h_thoff, h_thalo;
+	std::vector<double> h_rc;                  ///< cell centres, device order (own cells)
 	int nghost = 0, rank = 0, nranks = 1;
 	std::vector<int> send_counts, recv_counts, h_send_idx;
 };
@@ -135,6 +136,16 @@ struct fvg_flow {
 	double *d_norm = nullptr;      ///< [1]
 	double *h_norm = nullptr;      ///< pinned [1]
 	double *d_hu = nullptr, *d_hr = nullptr, *d_hdt = nullptr;   ///< staging for the host-buffer entry point
+	// chunked host-buffer pipeline (fvg_residual_host): tile ranges, their upload order and dependencies
+	struct HostPipe {
+		bool planned = false;
+		int K = 0;
+		std::vector<int> tile0;                 ///< [K+1] chunk -> first tile
+		std::vector<int> order;                 ///< upload order of the chunks
+		std::vector<unsigned long long> deps;   ///< chunk -> chunks owning its tiles' cells and halo cells (bit mask)
+		cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+		std::vector<cudaEvent_t> ev_up, ev_face;
+	} pipe;
 	std::vector<void*> allocs;
 	long long launches = 0;
 	int prefetch_distance = 0;
@@ -156,6 +167,7 @@ struct CellArgs {
 	double *gu;            ///< out: unlimited gradients (may be null)
 	int bnd_policy;
 	int prefetch_distance; ///< tiles ahead whose operands are pulled into L2 (0 = off)
+	int tile0 = 0, tile1 = -1;   ///< tile range of this launch (tile1 < 0: all tiles)
 };
 int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaStream_t s);
 int launch_weno_kernel(const DMesh &m, double lambda, const double *gu, double *lg, cudaStream_t s);
@@ -215,6 +227,7 @@ struct FaceArgs {
 	// "thread k reads row k" is free of shared-memory bank conflicts (32-byte rows: SWIZZLE_32B, 64-byte: SWIZZLE_64B)
 	CUtensorMap tm_u;      ///< u as [ncell][4]
 	CUtensorMap tm_g;      ///< lg as [ncell][8] (linear reconstruction only)
+	int tile0 = 0, tile1 = -1;   ///< tile range of this launch (tile1 < 0: all tiles)
 };
 /// Rows per TMA box of the per-cell row arrays (a box has at most 256 rows and must tile TC exactly)
 __host__ __device__ inline int tile_box_rows(int TC) {

@@ -217,31 +217,32 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		cp_async_commit();
 	};
 
-	int t = blockIdx.x;
-	if(t >= M.ntile) return;
+	const int tend = A.tile1;                 // this launch covers tiles [tile0, tile1)
+	int t = A.tile0 + (int)blockIdx.x;
+	if(t >= tend) return;
 	if(tid == 0 && (smem_u32(smraw) & 1023u) != 0) __trap();      // the swizzle formulas assume this alignment
 	TileDesc D = load_tile_desc(M, t);
 	// descriptors run two tiles ahead of the computation and the next tile's halo index one tile ahead, so that
 	// neither global load is waited for where it is consumed
 	TileDesc Dn = D;
-	if(t + (int)gridDim.x < M.ntile) Dn = load_tile_desc(M, t + (int)gridDim.x);
+	if(t + (int)gridDim.x < tend) Dn = load_tile_desc(M, t + (int)gridDim.x);
 	if(tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
 	__syncthreads();
 	if(tid == 0) { issue_AC(D, 0); issue_B(D); }
 	issue_halo(D.nh, tid < D.nh ? M.thalo[D.h0 + tid] : 0);
 
-	for(int it = 0; t < M.ntile; it++) {
+	for(int it = 0; t < tend; it++) {
 		const unsigned par = (unsigned)(it & 1);
 		const uint4 *const scl = reinterpret_cast<const uint4*>(smraw + S.scl + (int)par*S.cbuf);
 		const double *const sar = reinterpret_cast<const double*>(smraw + S.sar + (int)par*S.cbuf);
 		const int aoff = D.c0 & 1;
 		// the next tile's descriptor and this thread's halo index for it are in flight during phase A
 		const int tn = t + (int)gridDim.x;
-		const bool have_next = tn < M.ntile;
+		const bool have_next = tn < tend;
 		int gnext = 0;
 		if(have_next && tid < Dn.nh) gnext = M.thalo[Dn.h0 + tid];
 		TileDesc Dnn = Dn;
-		if(tn + (int)gridDim.x < M.ntile) Dnn = load_tile_desc(M, tn + (int)gridDim.x);
+		if(tn + (int)gridDim.x < tend) Dnn = load_tile_desc(M, tn + (int)gridDim.x);
 
 		// ---- phase A: face states of the own cells
 		mbar_wait(bar, par);
@@ -501,7 +502,11 @@ static int launch_one(const FaceArgs &a, cudaStream_t s)
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, face_kernel<FLUX,RECON,VISC>, FACE_BLOCK, smem);
 		ctas = sms*(per > 0 ? per : 1);
 	}
-	face_kernel<FLUX,RECON,VISC><<<a.m.ntile < ctas ? a.m.ntile : ctas, FACE_BLOCK, smem, s>>>(a);
+	FaceArgs b = a;
+	if(b.tile1 < 0) b.tile1 = b.m.ntile;
+	const int nt = b.tile1 - b.tile0;
+	if(nt <= 0) return 0;
+	face_kernel<FLUX,RECON,VISC><<<nt < ctas ? nt : ctas, FACE_BLOCK, smem, s>>>(b);
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "face_kernel launch", __FILE__, __LINE__);
 	return 0;

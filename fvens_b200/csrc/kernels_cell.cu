@@ -65,7 +65,7 @@ cell_kernel(const CellArgs A)
 	const double *const sclen = reinterpret_cast<const double*>(smraw + S.sclen);
 	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);
 
-	const int t = blockIdx.x, tid = threadIdx.x;
+	const int t = blockIdx.x + A.tile0, tid = threadIdx.x;
 	const int c0 = M.tcell0[t], nc = M.tcell0[t+1] - c0;
 	const int h0 = M.thoff[t], nh = M.thoff[t+1] - h0;
 	const int e0 = M.fsoff[t], ne = M.fsoff[t+1] - e0;
@@ -302,7 +302,9 @@ static int launch_cell(const CellArgs &a, cudaStream_t s)
 			cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
 		if(ea != cudaSuccess) return cuda_fail(ea, "cell_kernel smem attribute", __FILE__, __LINE__);
 	}
-	cell_kernel<GRAD,LIM,PRIM_IN><<<a.m.ntile, CELL_BLOCK, S.total, s>>>(a);
+	const int t1 = a.tile1 < 0 ? a.m.ntile : a.tile1;
+	if(t1 <= a.tile0) return 0;
+	cell_kernel<GRAD,LIM,PRIM_IN><<<t1 - a.tile0, CELL_BLOCK, S.total, s>>>(a);
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "cell_kernel launch", __FILE__, __LINE__);
 	return 0;

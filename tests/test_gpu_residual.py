@@ -118,6 +118,21 @@ def test_host_buffer_entry_point():
     assert rel_err_by_component(res, r0) < TOL and np.abs(dt/dt0-1).max() < TOL
 
 
+@pytest.mark.parametrize("kw", [dict(recon="VENKATAKRISHNAN"), dict(recon="VANALBADA", viscous=True),
+                                dict(order2=False), dict(recon="BARTHJESPERSEN", gradient="GREENGAUSS", flux="HLLC")])
+def test_host_buffer_pipeline_matches_the_device_resident_path(kw):
+    # device-ordered mesh with many tiles: fvg_residual_host runs its chunked upload / compute / download pipeline
+    # (tile ranges launched as soon as the chunks they depend on have arrived); same bits as one full launch
+    fl, of, u, _ = make_case("bump:96:36", reorder="none", tile=32, **kw)
+    assert fl.dmesh.info.ntile >= 64
+    r1, d1 = gpu_residual(fl, u)
+    res = np.full_like(u, 7.0); dt = np.zeros(len(u))
+    fl.compute_residual_host(u, res, True, dt, accumulate=False)
+    assert np.array_equal(res, r1) and np.array_equal(dt, d1)
+    r0, dt0, _, _ = of.residual(u)
+    assert rel_err_by_component(res, r0) < TOL and np.abs(dt/dt0-1).max() < TOL
+
+
 @pytest.mark.parametrize("reorder", ["none", "hilbert", "rcm"])
 def test_results_do_not_depend_on_renumbering(reorder):
     fl, of, u, _ = make_case("naca0012luo.msh", flux="HLLC", recon="BARTHJESPERSEN", gradient="GREENGAUSS",
