@@ -70,6 +70,17 @@ static int limiter_mode(int recon)
 	return 0;
 }
 
+/// Tile range (and list) of a split pass: explicit range if given, else the flow's selected part
+static void resolve_tiles(const fvg_flow *f, int &tile0, int &tile1, const int *&tlist)
+{
+	tlist = nullptr;
+	const DMesh &D = f->mesh->d;
+	if(tile1 >= 0 || f->part == 0 || !D.tile_order) return;
+	tlist = D.tile_order;
+	if(f->part == 1) { tile0 = 0; tile1 = D.ntile_interior; }
+	else { tile0 = D.ntile_interior; tile1 = D.ntile; }
+}
+
 /// Pass A on a device-ordered conserved state: fills f->d_lg and/or f->d_gu
 static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s, int tile0 = 0, int tile1 = -1)
 {
@@ -79,6 +90,7 @@ static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s, int t
 	a.m = f->mesh->d; a.gas = f->gas; a.u = u; a.ug = nullptr; a.gin = nullptr;
 	a.bnd_policy = P.bnd_policy;
 	a.prefetch_distance = f->prefetch_distance;
+	resolve_tiles(f, tile0, tile1, a.tlist);
 	a.tile0 = tile0; a.tile1 = tile1;
 	int rc;
 	if(P.recon == FVG_RECON_WENO) {
@@ -153,6 +165,7 @@ static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumul
 	a.epilogue = epilogue; a.accumulate = accumulate; a.gettimesteps = gettimesteps;
 	a.res = res; a.dtm = dtm; a.cfl = cfl; a.unew = unew; a.partial = f->d_partial;
 	a.prefetch_distance = f->prefetch_distance;
+	resolve_tiles(f, tile0, tile1, a.tlist);
 	a.tile0 = tile0; a.tile1 = tile1;
 	const int recon = !P.order2 ? FR_FIRST : (P.recon == FVG_RECON_VANALBADA ? FR_MUSCL : FR_LINEAR);
 	int rt = make_row_tensor_map(&a.tm_u, u, (size_t)a.m.ncell, 4, tile_box_rows(a.m.TC));
@@ -786,9 +799,17 @@ int fvg_euler_face_pass(fvg_flow *f, const double *d_u, double *d_unew, double c
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	int rc;
 	if((rc = run_face_pass(f, d_u, EP_STEP, 0, 1, nullptr, nullptr, cfl, d_unew, s)) != 0) return rc;
+	if(f->part == 1 && f->mesh->d.tile_order) return 0;      // the norm is summed once all tiles have their partial sums
 	if((rc = launch_final_norm(f->d_partial, f->mesh->d.ntile, f->d_norm, s)) != 0) return rc;
 	f->launches++;
 	if(d_resnorm2) FVG_CUDA(cudaMemcpyAsync(d_resnorm2, f->d_norm, sizeof(double), cudaMemcpyDeviceToDevice, s));
+	return 0;
+}
+
+int fvg_flow_select_tiles(fvg_flow *f, int part)
+{
+	if(!f || part < 0 || part > 2) { set_error("fvg_flow_select_tiles: bad argument"); return FVG_ERR_INVALID; }
+	f->part = part;
 	return 0;
 }
 

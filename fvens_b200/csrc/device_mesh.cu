@@ -260,6 +260,18 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 		}
 	}
 	const int ntile = (int)tcell0.size() - 1;
+	std::vector<int> tile_order;
+	int ntile_interior = ntile;
+	if(nranks > 1) {
+		std::vector<int> bnd;
+		for(int t = 0; t < ntile; t++) {
+			bool ghost = false;
+			for(int h = thoff[t]; h < thoff[t+1] && !ghost; h++) ghost = thalo[h] >= nown;
+			(ghost ? bnd : tile_order).push_back(t);
+		}
+		ntile_interior = (int)tile_order.size();
+		tile_order.insert(tile_order.end(), bnd.begin(), bnd.end());
+	}
 	std::vector<int> tile_of((size_t)ntot, -1);
 	for(int t = 0; t < ntile; t++) for(int i = tcell0[t]; i < tcell0[t+1]; i++) tile_of[i] = t;
 
@@ -611,6 +623,8 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	UP(fsoff, fsoff) UP(tbnd, tbnd) UP(fLR, fLR) UP(fn, fn) UP(flen, flen) UP(fgr, fgr)
 	UP(ford, ford) UP(m->h_fref, fref) UP(bcell, bcell) UP(m->h_bentry, bentry) UP(bslot, bslot) UP(rcbp, rcbp)
 	UP(m->h_send_idx, send_idx)
+	D.ntile_interior = ntile_interior;
+	if(tile_order.empty()) D.tile_order = nullptr; else { UP(tile_order, tile_order) }
 	if(m->identity_perm) { D.new2old = nullptr; D.old2new = nullptr; }
 	else { UP(d2g, new2old) D.old2new = nullptr; }
 #undef UP

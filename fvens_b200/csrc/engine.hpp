@@ -76,6 +76,10 @@ struct DMesh {
 	const int *new2old;
 	const int *old2new;
 	const int *send_idx;    ///< [nsend] own cells packed for the peers, grouped by peer rank
+	// tiles that see no ghost cell first, then the tiles on the partition boundary (null on an unpartitioned mesh):
+	// the first group can run while the ghost rows are still being exchanged
+	const int *tile_order;
+	int ntile_interior;
 };
 
 constexpr unsigned NB_NONE = 0xFFFFu;   ///< no such local face (4th slot of a triangle)
@@ -149,6 +153,7 @@ struct fvg_flow {
 	std::vector<void*> allocs;
 	long long launches = 0;
 	int prefetch_distance = 0;
+	int part = 0;                  ///< tiles the split passes cover: 0 all, 1 interior, 2 partition boundary
 	// optional per-pass timing (CUDA events on the launching stream)
 	bool timing = false;
 	std::vector<cudaEvent_t> ev;   ///< triples: before pass A, between A and B, after B
@@ -168,6 +173,7 @@ struct CellArgs {
 	int bnd_policy;
 	int prefetch_distance; ///< tiles ahead whose operands are pulled into L2 (0 = off)
 	int tile0 = 0, tile1 = -1;   ///< tile range of this launch (tile1 < 0: all tiles)
+	const int *tlist = nullptr;  ///< when set, the range indexes this list of tiles
 };
 int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaStream_t s);
 int launch_weno_kernel(const DMesh &m, double lambda, const double *gu, double *lg, cudaStream_t s);
@@ -228,6 +234,7 @@ struct FaceArgs {
 	CUtensorMap tm_u;      ///< u as [ncell][4]
 	CUtensorMap tm_g;      ///< lg as [ncell][8] (linear reconstruction only)
 	int tile0 = 0, tile1 = -1;   ///< tile range of this launch (tile1 < 0: all tiles)
+	const int *tlist = nullptr;  ///< when set, the range indexes this list of tiles
 };
 /// Rows per TMA box of the per-cell row arrays (a box has at most 256 rows and must tile TC exactly)
 __host__ __device__ inline int tile_box_rows(int TC) {

@@ -217,32 +217,37 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		cp_async_commit();
 	};
 
-	const int tend = A.tile1;                 // this launch covers tiles [tile0, tile1)
-	int t = A.tile0 + (int)blockIdx.x;
-	if(t >= tend) return;
+	// this launch covers positions [tile0, tile1) of the tile list (or the tiles themselves when there is no list)
+	const int tend = A.tile1, G = (int)gridDim.x;
+	int ti = A.tile0 + (int)blockIdx.x;
+	if(ti >= tend) return;
+	auto tile_at = [&](int i) { return A.tlist ? A.tlist[i] : i; };
+	int t = tile_at(ti);
 	if(tid == 0 && (smem_u32(smraw) & 1023u) != 0) __trap();      // the swizzle formulas assume this alignment
 	TileDesc D = load_tile_desc(M, t);
 	// descriptors run two tiles ahead of the computation and the next tile's halo index one tile ahead, so that
 	// neither global load is waited for where it is consumed
 	TileDesc Dn = D;
-	if(t + (int)gridDim.x < tend) Dn = load_tile_desc(M, t + (int)gridDim.x);
+	int tnx = ti + G < tend ? tile_at(ti + G) : 0;
+	if(ti + G < tend) Dn = load_tile_desc(M, tnx);
 	if(tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
 	__syncthreads();
 	if(tid == 0) { issue_AC(D, 0); issue_B(D); }
 	issue_halo(D.nh, tid < D.nh ? M.thalo[D.h0 + tid] : 0);
 
-	for(int it = 0; t < tend; it++) {
+	for(int it = 0; ti < tend; it++) {
 		const unsigned par = (unsigned)(it & 1);
 		const uint4 *const scl = reinterpret_cast<const uint4*>(smraw + S.scl + (int)par*S.cbuf);
 		const double *const sar = reinterpret_cast<const double*>(smraw + S.sar + (int)par*S.cbuf);
 		const int aoff = D.c0 & 1;
 		// the next tile's descriptor and this thread's halo index for it are in flight during phase A
-		const int tn = t + (int)gridDim.x;
-		const bool have_next = tn < tend;
+		const int tin = ti + G;
+		const bool have_next = tin < tend;
 		int gnext = 0;
 		if(have_next && tid < Dn.nh) gnext = M.thalo[Dn.h0 + tid];
 		TileDesc Dnn = Dn;
-		if(tn + (int)gridDim.x < tend) Dnn = load_tile_desc(M, tn + (int)gridDim.x);
+		int tnn = 0;
+		if(tin + G < tend) { tnn = tile_at(tin + G); Dnn = load_tile_desc(M, tnn); }
 
 		// ---- phase A: face states of the own cells
 		mbar_wait(bar, par);
@@ -479,7 +484,7 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		}
 		// phase C reads the flux slots that the next tile's phase A overwrites
 		__syncthreads();
-		t = tn; D = Dn; Dn = Dnn;
+		ti = tin; t = tnx; tnx = tnn; D = Dn; Dn = Dnn;
 	}
 }
 

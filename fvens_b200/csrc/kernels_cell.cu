@@ -65,7 +65,7 @@ cell_kernel(const CellArgs A)
 	const double *const sclen = reinterpret_cast<const double*>(smraw + S.sclen);
 	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);
 
-	const int t = blockIdx.x + A.tile0, tid = threadIdx.x;
+	const int t = A.tlist ? A.tlist[blockIdx.x + A.tile0] : (int)blockIdx.x + A.tile0, tid = threadIdx.x;
 	const int c0 = M.tcell0[t], nc = M.tcell0[t+1] - c0;
 	const int h0 = M.thoff[t], nh = M.thoff[t+1] - h0;
 	const int e0 = M.fsoff[t], ne = M.fsoff[t+1] - e0;

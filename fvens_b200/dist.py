@@ -132,6 +132,13 @@ class DistFlow:
         if self.order2:
             self.flow.use_buffers(self.lg, self.gu)
         self.global_ids = self.dmesh.permutation()
+        # exchanges overlapped with the tiles that see no ghost cell (FVG_OVERLAP=0: the plain sequence); WENO keeps the
+        # plain sequence (its second stage needs every neighbour's unlimited gradient first)
+        self.overlap = (torch.device(device).type == "cuda" and nranks > 1 and not self.weno
+                        and os.environ.get("FVG_OVERLAP", "1") != "0")
+        if self.overlap:
+            self._halo_stream = torch.cuda.Stream(device=device, priority=-1)
+            self._ev_u, self._ev_g, self._ev_l = (torch.cuda.Event() for _ in range(3))
 
     def _stream(self):
         return torch.cuda.current_stream().cuda_stream
@@ -149,8 +156,52 @@ class DistFlow:
         if self.need_lg:
             self.halo.exchange(self.lg)
 
+    def _overlapped(self, u, exchange_state, face):
+        """Both exchanges hidden behind the tiles that need no ghost row:
+             halo stream:    exchange(u) .......................... exchange(gradients) ..........
+             compute stream: gradients, interior tiles | boundary tiles | face pass, interior | boundary
+        The exchange kernels are enqueued on a high-priority stream BEFORE the compute kernel they overlap with (the
+        face kernel is persistent and would otherwise hold every SM until it ends)."""
+        cur = torch.cuda.current_stream()
+        hs = self._halo_stream
+        fl = self.flow
+        if exchange_state:
+            hs.wait_stream(cur)                 # u is final (and the previous evaluation has consumed the ghost rows)
+            with torch.cuda.stream(hs):
+                self.halo.exchange(u)
+                self._ev_u.record(hs)
+        if self.order2:
+            fl.select_tiles(1)
+            fl.gradient_pass(u, 0, stream=cur.cuda_stream)
+            if exchange_state:
+                cur.wait_event(self._ev_u)
+            fl.select_tiles(2)
+            fl.gradient_pass(u, 0, stream=cur.cuda_stream)
+            self._ev_g.record(cur)
+            hs.wait_event(self._ev_g)
+            with torch.cuda.stream(hs):
+                if self.need_gu:
+                    self.halo.exchange(self.gu)
+                if self.need_lg:
+                    self.halo.exchange(self.lg)
+                self._ev_l.record(hs)
+            fl.select_tiles(1)
+            face(cur.cuda_stream)
+            cur.wait_event(self._ev_l)
+        else:
+            fl.select_tiles(1)
+            face(cur.cuda_stream)
+            if exchange_state:
+                cur.wait_event(self._ev_u)
+        fl.select_tiles(2)
+        face(cur.cuda_stream)
+        fl.select_tiles(0)
+
     def residual(self, u, res, dtm, gettimesteps=True, exchange_state=True):
         """u [ncell+nghost,4]; res [ncell,4] (overwritten); dtm [ncell]."""
+        if self.overlap:
+            return self._overlapped(u, exchange_state,
+                                    lambda s: self.flow.face_pass(u, res, gettimesteps, dtm, accumulate=False, stream=s))
         if exchange_state:
             self.halo.exchange(u)
         self._gradients(u)
@@ -158,6 +209,9 @@ class DistFlow:
 
     def euler_step(self, u, unew, cfl, norm2, exchange_state=True):
         """One forward-Euler step: unew (own rows) from u; norm2 = this rank's sum of r_E^2*area (device scalar)."""
+        if self.overlap:
+            return self._overlapped(u, exchange_state,
+                                    lambda s: self.flow.euler_face_pass(u, unew, cfl, norm2, stream=s))
         if exchange_state:
             self.halo.exchange(u)
         self._gradients(u)

@@ -359,6 +359,10 @@ class FlowFV:
         check(load().fvg_euler_face_pass(self._h, _ptr(u), _ptr(unew), C.c_double(cfl), _ptr(resnorm2),
                                          C.c_void_p(stream or 0)))
 
+    def select_tiles(self, part):
+        """Tiles covered by the split passes: 0 all, 1 interior (no ghost cell in sight), 2 partition boundary."""
+        check(load().fvg_flow_select_tiles(self._h, int(part)))
+
     def launch_count(self):
         c = C.c_longlong(0)
         check(load().fvg_flow_launch_count(self._h, C.byref(c)))

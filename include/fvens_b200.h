@@ -229,6 +229,12 @@ int fvg_face_pass(fvg_flow *f, const double *d_u, double *d_res, int accumulate,
                   double *d_dtm, void *stream);
 int fvg_euler_face_pass(fvg_flow *f, const double *d_u, double *d_unew, double cfl, double *d_resnorm2,
                         void *stream);
+/* Which tiles the split passes above cover from now on: 0 = all (default), 1 = tiles that see no ghost cell,
+ * 2 = tiles on the partition boundary. A multi-GPU driver runs part 1 while the ghost rows are in flight and
+ * part 2 once they have arrived (the reference overlaps its trace exchange with the interior faces the same way,
+ * spatial/flow_spatial.cpp:738-782). On an unpartitioned mesh every tile is in part 1 and part 2 is empty;
+ * fvg_euler_face_pass sums the norm after part 2 (or 0). WENO's stage-1 pass always covers all tiles. */
+int fvg_flow_select_tiles(fvg_flow *f, int part);
 int fvg_flow_buffers(fvg_flow *f, double **d_lg, double **d_gu);
 /* Makes the flow use caller-owned gradient buffers ([ncell+nghost][8] doubles each, device memory that must
  * outlive the flow's use of them), e.g. tensors that a communication library can address. */
