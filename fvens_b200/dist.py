@@ -132,10 +132,12 @@ class DistFlow:
         if self.order2:
             self.flow.use_buffers(self.lg, self.gu)
         self.global_ids = self.dmesh.permutation()
-        # exchanges overlapped with the tiles that see no ghost cell (FVG_OVERLAP=0: the plain sequence); WENO keeps the
-        # plain sequence (its second stage needs every neighbour's unlimited gradient first)
+        # FVG_OVERLAP=1: exchanges overlapped with the tiles that see no ghost cell. Off by default: on B200 boxes the
+        # two extra launches per pass cost what the hidden exchanges save (10M cells: 0.600 vs 0.586 ms at 2 GPUs, 0.193
+        # vs 0.189 ms at 8; profiles/r01_bench_v9_*). WENO always uses the plain sequence (its second stage needs every
+        # neighbour's unlimited gradient first).
         self.overlap = (torch.device(device).type == "cuda" and nranks > 1 and not self.weno
-                        and os.environ.get("FVG_OVERLAP", "1") != "0")
+                        and os.environ.get("FVG_OVERLAP", "0") == "1")
         if self.overlap:
             self._halo_stream = torch.cuda.Stream(device=device, priority=-1)
             self._ev_u, self._ev_g, self._ev_l = (torch.cuda.Event() for _ in range(3))

@@ -1,0 +1,17 @@
+#!/bin/bash
+# Multi-GPU pass on an N-GPU box: gpurun --gpus N --timeout 1500 -- 'bash tools/gpu_scale.sh <tag> N'
+tag=${1:-rXX}; n=${2:-2}
+out=gpurun_out; mkdir -p $out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1"
+timeout 300 $TR --master-port 29511 tests/mgpu_check.py > $out/${tag}_mgpu_check_n$n.log 2>&1; tail -3 $out/${tag}_mgpu_check_n$n.log
+timeout 600 $TR --master-port 29512 bench.py --gpus $n --steps 100 --warmup 5 > $out/${tag}_bench_n$n.json 2> $out/${tag}_bench_n$n.err
+FVG_OVERLAP=0 timeout 600 $TR --master-port 29513 bench.py --gpus $n --steps 100 --warmup 5 > $out/${tag}_bench_n${n}_nooverlap.json 2> $out/${tag}_bench_n${n}_nooverlap.err
+for f in $out/${tag}_bench_n$n.json $out/${tag}_bench_n${n}_nooverlap.json; do python - "$f" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], 'ms/step', d['ms_per_step'], 'Gfaces/s', d['value'], 'euler ms', d['euler_step']['ms_per_step'], 'e2e', d['e2e']['value'], d['config']['parallelism'][:60])
+except Exception as e: print(sys.argv[1], 'FAILED', e)
+PY
+done
+tail -5 $out/${tag}_bench_n$n.err
