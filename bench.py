@@ -381,7 +381,7 @@ def main():
         "e2e": {"value": nf_glob/t_e2e.item()/1e9, "unit": "Gfaces/s", "ms_per_step": t_e2e.item()*1e3,
                 "h2d_bytes_per_step": 32*nc, "d2h_bytes_per_step": 40*nc,
                 "note": "pinned host buffers: H2D u, kernels" + (" + halos" if world > 1 else "") + ", D2H residual + dt"
-                        + (" (bytes are per rank)" if world > 1 else " (fvg_residual_host)")},
+                        + (" (bytes are per rank)" if world > 1 else " (fvg_residual_host: chunked upload / compute / download pipeline)")},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

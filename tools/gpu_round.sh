@@ -8,6 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $o
 ( time timeout 600 python -m pytest tests -m gpu -x -q ) > $out/${tag}_pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> $out/${tag}_pytest_gpu.log
 timeout 600 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
+timeout 300 python bench.py --numerics hllc-gg-bj --no-cpu-baseline > $out/${tag}_bench_n1_hllc_gg_bj.json 2> $out/${tag}_bench_n1_hllc_gg_bj.err
 timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $out/${tag}_launches_bench.log 2>&1
