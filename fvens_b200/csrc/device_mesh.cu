@@ -502,6 +502,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	fLR.assign((size_t)ns, LR_PAD);
 	std::vector<double2> fn((size_t)ns, make_double2(1.0, 0.0)), fgr((size_t)ns, make_double2(0.0, 0.0));
 	std::vector<double> flen((size_t)ns, 0.0);
+	std::vector<double2> fgw((size_t)ns, make_double2(0.5, 0.5)), fgln((size_t)ns, make_double2(0.0, 0.0));
 	std::vector<int> own_entry((size_t)nf, -1), dup_entry((size_t)nf, -1);
 	m->h_fref.assign(ns, PAD); m->h_fcolour = scolour; m->h_ftile.resize(ns);
 	auto local_of = [&](int t, int g) -> unsigned {
@@ -530,6 +531,16 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 				g[d] = sum/2;
 			}
 			fgr[e] = make_double2(g[0], g[1]);
+			{
+				// Green-Gauss: u_face = (u_L/d_L + u_R/d_R)/(1/d_L + 1/d_R), d = distance of the midpoint to the cell centre
+				// (boundary: to the mirrored ghost centre, aspatial.cpp:98-119)
+				const double lx = rc[2*(size_t)d2g[L]], ly = rc[2*(size_t)d2g[L]+1];
+				const double rx = R >= 0 ? rc[2*(size_t)d2g[R]] : 2.0*g[0] - lx, ry = R >= 0 ? rc[2*(size_t)d2g[R]+1] : 2.0*g[1] - ly;
+				const double di = 1.0/std::sqrt((g[0]-lx)*(g[0]-lx) + (g[1]-ly)*(g[1]-ly));
+				const double dj = 1.0/std::sqrt((g[0]-rx)*(g[0]-rx) + (g[1]-ry)*(g[1]-ry));
+				fgw[e] = make_double2(di/(di + dj), dj/(di + dj));
+				fgln[e] = make_double2(flen[e]*fn[e].x, flen[e]*fn[e].y);
+			}
 			if(sface[e] >= 0) own_entry[f] = e; else dup_entry[f] = e;
 			m->h_fref[e] = sface[e];
 		}
@@ -620,7 +631,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 #define UP(vec, field) if((rcode = upload(m, vec, &D.field)) != 0) return rcode;
 	UP(cloc, cloc) UP(drc, rc) UP(area, area) UP(V, wlsV) UP(clength, clength)
 	UP(tcell0, tcell0) UP(thoff, thoff) UP(thalo, thalo)
-	UP(fsoff, fsoff) UP(tbnd, tbnd) UP(fLR, fLR) UP(fn, fn) UP(flen, flen) UP(fgr, fgr)
+	UP(fsoff, fsoff) UP(tbnd, tbnd) UP(fLR, fLR) UP(fn, fn) UP(flen, flen) UP(fgr, fgr) UP(fgw, fgw) UP(fgln, fgln)
 	UP(ford, ford) UP(m->h_fref, fref) UP(bcell, bcell) UP(m->h_bentry, bentry) UP(bslot, bslot) UP(rcbp, rcbp)
 	UP(m->h_send_idx, send_idx)
 	D.ntile_interior = ntile_interior;

@@ -64,6 +64,8 @@ struct DMesh {
 	const double2 *fn;      ///< unit normal, left -> right
 	const double *flen;
 	const double2 *fgr;     ///< face midpoint
+	const double2 *fgw;     ///< Green-Gauss face data: inverse-distance weights of the left and right cell (they add up to 1)
+	const double2 *fgln;    ///< ... and len*n_x, len*n_y (agradientschemes.cpp:62-214 with the geometry folded in once)
 	const unsigned short *ford; ///< per tile: tile-local positions of its real (non-padding) entries, ascending; length = stream
 	                        ///< segment, the first (segment - tbnd.w) values are meaningful
 	const int *fref;        ///< reference face id (intfac index); duplicate copy of a cut face: -1-id; padding: INT_MIN

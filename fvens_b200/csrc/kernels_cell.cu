@@ -24,15 +24,14 @@ __device__ __forceinline__ void lds4h(const double *p, int o0, int o1, double v[
 
 /// Shared-memory carve-up of the cell kernel
 struct CellSmem {
-	int sp, src, sgr, sn, slen, scl, sV, sclen, bar, total;
+	int sp, src, sgr, sW, scl, sV, sclen, bar, total;
 	__host__ __device__ CellSmem(int TC, int HMAX, int EMAX, bool mids, bool metrics, bool wls, bool venkat) {
 		const int CAPC = TC + HMAX;
 		int o = 0;
 		sp = o; o += CAPC*32;
 		src = o; o += CAPC*16;
 		sgr = o; o += mids ? EMAX*16 : 0;
-		sn = o; o += metrics ? EMAX*16 : 0;
-		slen = o; o += metrics ? EMAX*8 : 0;
+		sW = o; o += metrics ? EMAX*32 : 0;
 		scl = o; o += TC*16;
 		sV = o; o += wls ? TC*32 : 0;
 		sclen = o; o += venkat ? (TC + 2)*8 : 0;
@@ -58,8 +57,7 @@ cell_kernel(const CellArgs A)
 	double *const sp = reinterpret_cast<double*>(smraw + S.sp);
 	double2 *const src = reinterpret_cast<double2*>(smraw + S.src);
 	double2 *const sgr = reinterpret_cast<double2*>(smraw + S.sgr);
-	double2 *const sn = reinterpret_cast<double2*>(smraw + S.sn);
-	double *const slen = reinterpret_cast<double*>(smraw + S.slen);
+	const double2 *const sW = reinterpret_cast<const double2*>(smraw + S.sW);     // two 16-byte planes: weights, len*normal
 	const uint4 *const scl = reinterpret_cast<const uint4*>(smraw + S.scl);
 	const double4 *const sV = reinterpret_cast<const double4*>(smraw + S.sV);
 	const double *const sclen = reinterpret_cast<const double*>(smraw + S.sclen);
@@ -76,7 +74,7 @@ cell_kernel(const CellArgs A)
 	if(tid == 0) {
 		unsigned bytes = (unsigned)nc*(32u + 16u + 16u + (GRAD == GM_WLS ? 32u : 0u)) + (LIM == LM_VENKAT ? (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u : 0u);
 		if(MIDS) bytes += (unsigned)ne*16u;
-		if(METRICS) bytes += (unsigned)ne*(16u + 8u);
+		if(METRICS) bytes += (unsigned)ne*32u;
 		mbar_expect_tx(bar, bytes);
 		bulk_g2s(sp, A.u + 4*(size_t)c0, (unsigned)nc*32u, bar);
 		bulk_g2s(src, M.rc + c0, (unsigned)nc*16u, bar);
@@ -86,7 +84,7 @@ cell_kernel(const CellArgs A)
 		// 8-byte rows: copy whole 16-byte granules starting at the even cell below c0 (the array is padded by one entry)
 		if(LIM == LM_VENKAT) bulk_g2s(smraw + S.sclen, M.clength + (c0 & ~1), (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u, bar);
 		if(MIDS) bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
-		if(METRICS) { bulk_g2s(sn, M.fn + e0, (unsigned)ne*16u, bar); bulk_g2s(slen, M.flen + e0, (unsigned)ne*8u, bar); }
+		if(METRICS) { bulk_g2s(smraw + S.sW, M.fgw + e0, (unsigned)ne*16u, bar); bulk_g2s(smraw + S.sW + M.EMAX*16, M.fgln + e0, (unsigned)ne*16u, bar); }
 	}
 	if(tid == 32 && A.prefetch_distance > 0 && t + A.prefetch_distance < M.ntile) {
 		const int tp = t + A.prefetch_distance;
@@ -98,7 +96,7 @@ cell_kernel(const CellArgs A)
 		{ const int ph0 = M.thoff[tp] & ~3, ph1 = (M.thoff[tp+1] + 3) & ~3; if(ph1 > ph0) bulk_prefetch_l2(M.thalo + ph0, (unsigned)(ph1 - ph0)*4u); }
 		if(GRAD == GM_WLS) bulk_prefetch_l2(M.wlsV + pc0, (unsigned)pnc*32u);
 		if(MIDS) bulk_prefetch_l2(M.fgr + pe0, (unsigned)pne*16u);
-		if(METRICS) { bulk_prefetch_l2(M.fn + pe0, (unsigned)pne*16u); bulk_prefetch_l2(M.flen + pe0, (unsigned)pne*8u); }
+		if(METRICS) { bulk_prefetch_l2(M.fgw + pe0, (unsigned)pne*16u); bulk_prefetch_l2(M.fgln + pe0, (unsigned)pne*16u); }
 	}
 	if(NEED_NBRS) {
 		for(int k = tid; k < nh*3; k += CELL_BLOCK) {
@@ -200,20 +198,17 @@ cell_kernel(const CellArgs A)
 					}
 				}
 				if(GRAD == GM_GG) {
+					// face value = own state * own weight + neighbour state * its weight; the face's len*normal points from the
+					// entry's left to its right cell
 					const bool isR = (cf[j] & 0x8000u) != 0;
-					const double2 mid = sgr[le];
-					const double2 n = sn[le];
-					const double len = slen[le];
-					// inverse distances of the face midpoint to the two centres
-					const double di = frsqrt((mid.x-rci.x)*(mid.x-rci.x) + (mid.y-rci.y)*(mid.y-rci.y));
-					const double dj = frsqrt((mid.x-rj.x)*(mid.x-rj.x) + (mid.y-rj.y)*(mid.y-rj.y));
-					const double sgn = isR ? -1.0 : 1.0;
-					const double isum = frcp(di + dj);
+					const double2 w = sW[le], ln = sW[M.EMAX + le];
+					const double wi = isR ? w.y : w.x, wj = isR ? w.x : w.y;
+					const double sx = isR ? -ln.x : ln.x, sy = isR ? -ln.y : ln.y;
 					#pragma unroll
 					for(int v = 0; v < 4; v++) {
-						const double ut = (pi[v]*di + pj[v]*dj)*isum*len;
-						acc[2*v] += sgn*(ut*n.x)*ainv;
-						acc[2*v+1] += sgn*(ut*n.y)*ainv;
+						const double ut = pi[v]*wi + pj[v]*wj;
+						acc[2*v] += ut*sx;
+						acc[2*v+1] += ut*sy;
 					}
 				}
 				if(LIM != LM_NONE && !(bndj && A.bnd_policy != 0)) {
@@ -237,7 +232,7 @@ cell_kernel(const CellArgs A)
 				g[2*v+1] = V.z*acc[2*v] + V.w*acc[2*v+1];
 			}
 		}
-		else if(GRAD == GM_GG) { for(int q = 0; q < 8; q++) g[q] = acc[q]; }
+		else if(GRAD == GM_GG) { for(int q = 0; q < 8; q++) g[q] = acc[q]*ainv; }
 		else if(GRAD == GM_GIVEN) { ld4(A.gin + 8*(size_t)i + 2*o0, g); ld4(A.gin + 8*(size_t)i + 2*o1, g+4); }
 		else { for(int q = 0; q < 8; q++) g[q] = 0.0; }
 
