@@ -78,7 +78,8 @@ static void resolve_tiles(const fvg_flow *f, int &tile0, int &tile1, const int *
 	if(tile1 >= 0 || f->part == 0 || !D.tile_order) return;
 	tlist = D.tile_order;
 	if(f->part == 1) { tile0 = 0; tile1 = D.ntile_interior; }
-	else { tile0 = D.ntile_interior; tile1 = D.ntile; }
+	else if(f->part == 2) { tile0 = D.ntile_interior; tile1 = D.ntile; }
+	else { tile0 = 0; tile1 = D.ntile; }
 }
 
 /// Pass A on a device-ordered conserved state: fills f->d_lg and/or f->d_gu
@@ -92,6 +93,7 @@ static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s, int t
 	a.prefetch_distance = f->prefetch_distance;
 	resolve_tiles(f, tile0, tile1, a.tlist);
 	a.tile0 = tile0; a.tile1 = tile1;
+	if(a.tlist && f->part == 3) a.gs_u = f->gs_u;
 	int rc;
 	if(P.recon == FVG_RECON_WENO) {
 		a.lg = nullptr; a.gu = f->d_gu;
@@ -167,6 +169,7 @@ static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumul
 	a.prefetch_distance = f->prefetch_distance;
 	resolve_tiles(f, tile0, tile1, a.tlist);
 	a.tile0 = tile0; a.tile1 = tile1;
+	if(a.tlist && f->part == 3) { a.gs_u = f->gs_u; a.gs_g = f->gs_g; }
 	const int recon = !P.order2 ? FR_FIRST : (P.recon == FVG_RECON_VANALBADA ? FR_MUSCL : FR_LINEAR);
 	int rt = make_row_tensor_map(&a.tm_u, u, (size_t)a.m.ncell, 4, tile_box_rows(a.m.TC));
 	if(rt == 0 && recon == FR_LINEAR) rt = make_row_tensor_map(&a.tm_g, a.lg, (size_t)a.m.ncell, 8, tile_box_rows(a.m.TC));
@@ -806,9 +809,21 @@ int fvg_euler_face_pass(fvg_flow *f, const double *d_u, double *d_unew, double c
 	return 0;
 }
 
+int fvg_flow_ghost_source(fvg_flow *f, int which, fvg_halo *h, unsigned long long token)
+{
+	if(!f || which < 0 || which > 1) { set_error("fvg_flow_ghost_source: bad argument"); return FVG_ERR_INVALID; }
+	GhostSrc &g = which == 0 ? f->gs_u : f->gs_g;
+	if(!h || token == 0) { g = GhostSrc(); return 0; }
+	if(which == 1 && (f->plan.visc != VISC_NONE || f->plan.recon == FVG_RECON_VANALBADA || f->plan.recon == FVG_RECON_WENO)) {
+		set_error("fvg_flow_ghost_source: viscous, MUSCL and WENO passes read ghost rows from the arrays; use fvg_halo_exchange");
+		return FVG_ERR_UNSUPPORTED;
+	}
+	return fvg_halo_ghost_source(h, token, &g);
+}
+
 int fvg_flow_select_tiles(fvg_flow *f, int part)
 {
-	if(!f || part < 0 || part > 2) { set_error("fvg_flow_select_tiles: bad argument"); return FVG_ERR_INVALID; }
+	if(!f || part < 0 || part > 3) { set_error("fvg_flow_select_tiles: bad argument"); return FVG_ERR_INVALID; }
 	f->part = part;
 	return 0;
 }

@@ -84,6 +84,16 @@ struct DMesh {
 	int ntile_interior;
 };
 
+/// Where a pass finds the ghost rows of an array when they are NOT copied into the array: in the halo window of
+/// exchange `seq`, valid once every sending neighbour's flag has reached `seq` (rows == nullptr: in the array itself)
+struct GhostSrc {
+	const double *rows = nullptr;              ///< window buffer of that exchange: [nghost][width]
+	const unsigned long long *flags = nullptr; ///< [nranks] arrival flags, then the error word
+	const int *recv_off = nullptr;             ///< [nranks+1] ghost-row offsets per source rank
+	unsigned long long seq = 0;
+	int nranks = 0;
+};
+
 constexpr unsigned NB_NONE = 0xFFFFu;   ///< no such local face (4th slot of a triangle)
 constexpr unsigned NB_BND = 0xFFFEu;    ///< neighbour is a physical boundary ghost
 constexpr unsigned LR_BND = 0xFFE0u;    ///< right field of a boundary entry = LR_BND | bc index
@@ -155,7 +165,8 @@ struct fvg_flow {
 	std::vector<void*> allocs;
 	long long launches = 0;
 	int prefetch_distance = 0;
-	int part = 0;                  ///< tiles the split passes cover: 0 all, 1 interior, 2 partition boundary
+	int part = 0;                  ///< tiles the split passes cover: 0 all, 1 interior, 2 partition boundary, 3 all, interior first
+	fvg::GhostSrc gs_u, gs_g;      ///< set by fvg_flow_ghost_source
 	// optional per-pass timing (CUDA events on the launching stream)
 	bool timing = false;
 	std::vector<cudaEvent_t> ev;   ///< triples: before pass A, between A and B, after B
@@ -176,6 +187,7 @@ struct CellArgs {
 	int prefetch_distance; ///< tiles ahead whose operands are pulled into L2 (0 = off)
 	int tile0 = 0, tile1 = -1;   ///< tile range of this launch (tile1 < 0: all tiles)
 	const int *tlist = nullptr;  ///< when set, the range indexes this list of tiles
+	GhostSrc gs_u;               ///< ghost rows of u (partition-boundary tiles wait for them inside the kernel)
 };
 int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaStream_t s);
 int launch_weno_kernel(const DMesh &m, double lambda, const double *gu, double *lg, cudaStream_t s);
@@ -237,6 +249,7 @@ struct FaceArgs {
 	CUtensorMap tm_g;      ///< lg as [ncell][8] (linear reconstruction only)
 	int tile0 = 0, tile1 = -1;   ///< tile range of this launch (tile1 < 0: all tiles)
 	const int *tlist = nullptr;  ///< when set, the range indexes this list of tiles
+	GhostSrc gs_u, gs_g;         ///< ghost rows of u and of the reconstruction gradients, see GhostSrc
 };
 /// Rows per TMA box of the per-cell row arrays (a box has at most 256 rows and must tile TC exactly)
 __host__ __device__ inline int tile_box_rows(int TC) {
@@ -254,5 +267,9 @@ int launch_face_hll(int recon, int visc, const FaceArgs &a, cudaStream_t s);
 int launch_face_hllc(int recon, int visc, const FaceArgs &a, cudaStream_t s);
 
 GasParams make_gas(const fvg_physics &p, double limiter_param);
+} // namespace fvg
+struct fvg_halo;
+extern "C" int fvg_halo_ghost_source(fvg_halo *h, unsigned long long token, fvg::GhostSrc *out);   // halo.cu (internal)
+namespace fvg {
 
 } // namespace fvg

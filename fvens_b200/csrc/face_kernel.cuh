@@ -119,6 +119,24 @@ __device__ __forceinline__ void halo_side_state(const FaceArgs &A, const double 
 	extrapolate_prim(pc, ga, gb, gr.x, gr.y, rc.x, rc.y, pf);
 }
 
+/// Called by a whole CTA before it touches ghost rows that arrive through a halo window: thread r waits until the
+/// neighbour rank r has published exchange `seq` (bounded spin: on a timeout the window's error word is set and the
+/// kernel goes on, the caller reads fvg_halo_status). The barrier makes the acquired rows visible to all threads.
+__device__ __forceinline__ void ghost_wait(const GhostSrc &g, unsigned long long seq)
+{
+	if((int)threadIdx.x < g.nranks) {
+		const int r = threadIdx.x;
+		if(g.recv_off[r+1] > g.recv_off[r]) {
+			long long spins = 0;
+			while(ld_acquire_sys_u64(g.flags + r) < seq) {
+				__nanosleep(64);
+				if(++spins > 30000000ll) { atomicExch(const_cast<unsigned long long*>(g.flags) + g.nranks, seq); break; }
+			}
+		}
+	}
+	__syncthreads();
+}
+
 /// Descriptor of one tile (all uniform across the CTA)
 struct TileDesc { int c0, nc, h0, nh, e0, ne, nreal; };
 __device__ __forceinline__ TileDesc load_tile_desc(const DMesh &M, int t) {
@@ -206,11 +224,15 @@ face_kernel(const __grid_constant__ FaceArgs A)
 	// halo rows of a tile: thread h gathers halo cell h (device index g), FACE_BLOCK >= HMAX
 	auto issue_halo = [&](int nh, int g) {
 		if(tid < nh) {
-			cp_async16(hu + 4*tid, A.u + 4*(size_t)g);
-			cp_async16(hu + 4*tid + 2, A.u + 4*(size_t)g + 2);
+			// a ghost cell's rows may live in a halo window instead of the arrays (in-kernel receive)
+			const bool gh = g >= M.ncell;
+			const double *const urow = (gh && A.gs_u.rows) ? A.gs_u.rows + 4*(size_t)(g - M.ncell) : A.u + 4*(size_t)g;
+			cp_async16(hu + 4*tid, urow);
+			cp_async16(hu + 4*tid + 2, urow + 2);
 			if(MIDS) {
+				const double *const grow = (gh && A.gs_g.rows) ? A.gs_g.rows + 8*(size_t)(g - M.ncell) : gsrc + 8*(size_t)g;
 				#pragma unroll
-				for(int q = 0; q < 4; q++) cp_async16(hg + 8*tid + 2*q, gsrc + 8*(size_t)g + 2*q);
+				for(int q = 0; q < 4; q++) cp_async16(hg + 8*tid + 2*q, grow + 2*q);
 				cp_async16(hrc + tid, M.rc + g);
 			}
 		}
@@ -233,6 +255,13 @@ face_kernel(const __grid_constant__ FaceArgs A)
 	if(tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
 	__syncthreads();
 	if(tid == 0) { issue_AC(D, 0); issue_B(D); }
+	// in-kernel receive: the tile list has the partition-boundary tiles last; a CTA waits for the neighbours' rows
+	// once, right before it gathers the halo of its first boundary tile (by then they have usually arrived)
+	const bool recv_here = A.tlist != nullptr && (A.gs_u.rows != nullptr || A.gs_g.rows != nullptr);
+	const GhostSrc &gsw = A.gs_g.rows ? A.gs_g : A.gs_u;
+	const unsigned long long wseq = A.gs_g.rows ? (A.gs_g.seq > A.gs_u.seq ? A.gs_g.seq : A.gs_u.seq) : A.gs_u.seq;
+	bool waited = !recv_here;
+	if(!waited && ti >= M.ntile_interior) { ghost_wait(gsw, wseq); waited = true; }
 	issue_halo(D.nh, tid < D.nh ? M.thalo[D.h0 + tid] : 0);
 
 	for(int it = 0; ti < tend; it++) {
@@ -422,6 +451,7 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		// group B buffers are free: the next tile's entry metadata and halo rows
 		if(have_next) {
 			if(tid == 0) { fence_proxy_async(); issue_B(Dn); }
+			if(!waited && tin >= M.ntile_interior) { ghost_wait(gsw, wseq); waited = true; }
 			issue_halo(Dn.nh, gnext);
 		}
 

@@ -7,9 +7,12 @@
  *         caller's array.
  * Replaces the reference's L2TraceVector::updateSharedFacesBegin/End (src/linalg/tracevector.cpp:214-325, MPI
  * Isend/Irecv of packed face states) and its VecGhostUpdateBegin/End calls (src/ode/aodesolver.cpp:212,247;
- * src/spatial/flow_spatial.cpp:711-729). Receive areas are double-buffered by sequence parity, so a rank may run
- * one exchange ahead of a neighbour without overwriting rows the neighbour has not consumed yet (a rank cannot
- * get two ahead: its next receive needs the neighbour's next send).
+ * src/spatial/flow_spatial.cpp:711-729). A window has three receive areas used round robin by sequence number: a
+ * rank may run one exchange ahead of a neighbour without overwriting rows the neighbour has not consumed yet (it
+ * cannot get two ahead: its next receive needs the neighbour's next send), and with the IN-KERNEL RECEIVE
+ * (fvg_halo_post + fvg_flow_ghost_source: no recv kernel, the consuming pass waits on the flags itself and reads the
+ * window directly) the two most recent exchanges - state and gradients of one evaluation - stay readable while the
+ * next state exchange is already arriving.
  */
 #include "engine.hpp"
 #include <cstring>
@@ -20,7 +23,7 @@ struct fvg_halo {
 	fvg_mesh *mesh = nullptr;
 	int nranks = 1, rank = 0, max_width = 0;
 	size_t area_doubles = 0;                 ///< doubles per parity buffer (nghost * max_width)
-	unsigned char *window = nullptr;         ///< local window: header (nranks flags + 1 error word, uint64, padded to 256 B), then [2][area] doubles
+	unsigned char *window = nullptr;         ///< local window: header (nranks flags + 1 error word, uint64, padded to 256 B), then [3][area] doubles
 	size_t hdr = 0;                          ///< header bytes (the same on every rank)
 	std::vector<unsigned long long> peer_area;   ///< area_doubles of each peer's window (its parity-buffer stride)
 	unsigned long long *d_peer_area = nullptr;
@@ -38,6 +41,7 @@ struct fvg_halo {
 namespace fvg {
 
 constexpr int HALO_CTAS_PER_PEER = 4;
+constexpr unsigned long long HALO_NBUF = 3;   ///< receive areas per window, used round robin by sequence number
 constexpr int HALO_THREADS = 512;
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -61,7 +65,7 @@ halo_send_block(const int block, const double *__restrict__ src, const int *__re
 	const int r = block/HALO_CTAS_PER_PEER, sub = block - r*HALO_CTAS_PER_PEER;
 	const int k0 = send_off[r], nrow = send_off[r+1] - k0;
 	if(nrow == 0 || peer[r] == nullptr) return;
-	double *const dst = reinterpret_cast<double*>(peer[r] + hdr) + (seq & 1ull)*peer_area[r] + (size_t)peer_row0[r]*width;
+	double *const dst = reinterpret_cast<double*>(peer[r] + hdr) + (seq % HALO_NBUF)*peer_area[r] + (size_t)peer_row0[r]*width;
 	const int w2 = width/2;                   // widths are even (4 or 8): rows move as 16-byte pieces
 	const long long tot = (long long)nrow*w2;
 	for(long long q = (long long)sub*HALO_THREADS + threadIdx.x; q < tot; q += (long long)HALO_CTAS_PER_PEER*HALO_THREADS) {
@@ -102,7 +106,7 @@ halo_recv_block(const int block, const int nblocks, double *__restrict__ dst, co
 		}
 	}
 	__syncthreads();
-	const double *const srcw = reinterpret_cast<const double*>(window + hdr) + (seq & 1ull)*area_doubles;
+	const double *const srcw = reinterpret_cast<const double*>(window + hdr) + (seq % HALO_NBUF)*area_doubles;
 	const long long tot = (long long)nghost*width/2;
 	double2 *const out = reinterpret_cast<double2*>(dst + (size_t)ncell*width);
 	const double2 *const in = reinterpret_cast<const double2*>(srcw);
@@ -149,7 +153,7 @@ int fvg_halo_create(fvg_mesh *mesh, int max_width, fvg_halo **out)
 	h->mesh = mesh; h->nranks = mesh->nranks; h->rank = mesh->rank; h->max_width = max_width;
 	h->area_doubles = (size_t)std::max(mesh->d.nghost, 1)*max_width;
 	h->hdr = (((size_t)h->nranks + 1)*sizeof(unsigned long long) + 255)/256*256;
-	const size_t bytes = h->hdr + 2*h->area_doubles*sizeof(double);
+	const size_t bytes = h->hdr + HALO_NBUF*h->area_doubles*sizeof(double);
 	FVG_CUDA(cudaMalloc((void**)&h->window, bytes));
 	FVG_CUDA(cudaMemset(h->window, 0, bytes));
 	h->send_off.assign(h->nranks + 1, 0); h->recv_off.assign(h->nranks + 1, 0);
@@ -238,6 +242,27 @@ static int halo_launch(fvg_halo *h, const double *src, double *dst, int width, b
 int fvg_halo_send(fvg_halo *h, const double *d_arr, int width, void *stream)
 {
 	return halo_launch(h, d_arr, nullptr, width, true, false, stream, "fvg_halo_send");
+}
+
+int fvg_halo_post(fvg_halo *h, const double *d_arr, int width, void *stream, unsigned long long *token)
+{
+	if(!token) { set_error("fvg_halo_post: null argument"); return FVG_ERR_INVALID; }
+	const int rc = halo_launch(h, d_arr, nullptr, width, true, false, stream, "fvg_halo_post");
+	if(rc == 0) *token = h->seq;
+	return rc;
+}
+
+int fvg_halo_ghost_source(fvg_halo *h, unsigned long long token, fvg::GhostSrc *out)
+{
+	if(!h || !out || !h->connected || token == 0 || token > h->seq || token + HALO_NBUF <= h->seq + 1) {
+		set_error("fvg_halo_ghost_source: no such exchange in the window any more"); return FVG_ERR_INVALID;
+	}
+	out->rows = reinterpret_cast<const double*>(h->window + h->hdr) + (token % HALO_NBUF)*h->area_doubles;
+	out->flags = reinterpret_cast<const unsigned long long*>(h->window);
+	out->recv_off = h->d_recv_off;
+	out->seq = token;
+	out->nranks = h->nranks;
+	return 0;
 }
 
 int fvg_halo_recv(fvg_halo *h, double *d_arr, int width, void *stream)

@@ -70,6 +70,10 @@ cell_kernel(const CellArgs A)
 	constexpr bool NEED_NBRS = GRAD == GM_GG || GRAD == GM_WLS || LIM != LM_NONE;
 
 	if(tid == 0) mbar_init(bar, 1);
+	// in-kernel receive of the state's ghost rows: the CTAs of partition-boundary tiles (last in the tile list) wait
+	// for the neighbours here; interior tiles never do
+	const bool ghost_win = A.gs_u.rows != nullptr;
+	if(ghost_win && A.tlist && (int)blockIdx.x + A.tile0 >= M.ntile_interior) ghost_wait(A.gs_u, A.gs_u.seq);
 	__syncthreads();
 	if(tid == 0) {
 		unsigned bytes = (unsigned)nc*(32u + 16u + 16u + (GRAD == GM_WLS ? 32u : 0u)) + (LIM == LM_VENKAT ? (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u : 0u);
@@ -103,7 +107,8 @@ cell_kernel(const CellArgs A)
 			const int h = k/3, piece = k - 3*h;
 			const size_t g = (size_t)M.thalo[h0 + h];
 			const int row = nc + h;
-			if(piece < 2) cp_async16(sp + 4*row + 2*piece, A.u + 4*g + 2*piece);
+			const double *const urow = (ghost_win && g >= (size_t)M.ncell) ? A.gs_u.rows + 4*(g - (size_t)M.ncell) : A.u + 4*g;
+			if(piece < 2) cp_async16(sp + 4*row + 2*piece, urow + 2*piece);
 			else cp_async16(src + row, M.rc + g);
 		}
 		cp_async_commit();

@@ -138,6 +138,10 @@ class DistFlow:
         # neighbour's unlimited gradient first).
         self.overlap = (torch.device(device).type == "cuda" and nranks > 1 and not self.weno
                         and os.environ.get("FVG_OVERLAP", "0") == "1")
+        # in-kernel receive (default with the peer windows; FVG_FUSED_RECV=0 turns it off): inviscid flows with linear
+        # reconstruction or first order - the other passes read ghost rows straight from the arrays
+        self.fused_recv = (use_peer and not self.overlap and not self.need_gu and not self.weno and not phys.viscous_sim
+                           and os.environ.get("FVG_FUSED_RECV", "1") != "0")
         if self.overlap:
             self._halo_stream = torch.cuda.Stream(device=device, priority=-1)
             self._ev_u, self._ev_g, self._ev_l = (torch.cuda.Event() for _ in range(3))
@@ -199,8 +203,24 @@ class DistFlow:
         face(cur.cuda_stream)
         fl.select_tiles(0)
 
+    def _in_kernel_receive(self, u, face):
+        """Two sends and two passes, no receive kernel: each pass waits for the neighbours' rows itself, in the CTAs that
+        reach a partition-boundary tile and after their interior tiles, and reads the ghost rows from the halo window."""
+        s = self._stream()
+        fl, win = self.flow, self.halo.win
+        fl.ghost_source(0, win, win.post(u, 4, stream=s))
+        fl.select_tiles(3)
+        if self.order2:
+            fl.gradient_pass(u, 0, stream=s)
+            fl.ghost_source(1, win, win.post(self.lg, 8, stream=s))
+        face(s)
+        fl.select_tiles(0)
+        fl.ghost_source(0); fl.ghost_source(1)
+
     def residual(self, u, res, dtm, gettimesteps=True, exchange_state=True):
         """u [ncell+nghost,4]; res [ncell,4] (overwritten); dtm [ncell]."""
+        if self.fused_recv and exchange_state:
+            return self._in_kernel_receive(u, lambda s: self.flow.face_pass(u, res, gettimesteps, dtm, accumulate=False, stream=s))
         if self.overlap:
             return self._overlapped(u, exchange_state,
                                     lambda s: self.flow.face_pass(u, res, gettimesteps, dtm, accumulate=False, stream=s))
@@ -211,6 +231,8 @@ class DistFlow:
 
     def euler_step(self, u, unew, cfl, norm2, exchange_state=True):
         """One forward-Euler step: unew (own rows) from u; norm2 = this rank's sum of r_E^2*area (device scalar)."""
+        if self.fused_recv and exchange_state:
+            return self._in_kernel_receive(u, lambda s: self.flow.euler_face_pass(u, unew, cfl, norm2, stream=s))
         if self.overlap:
             return self._overlapped(u, exchange_state,
                                     lambda s: self.flow.euler_face_pass(u, unew, cfl, norm2, stream=s))

@@ -359,6 +359,12 @@ class FlowFV:
         check(load().fvg_euler_face_pass(self._h, _ptr(u), _ptr(unew), C.c_double(cfl), _ptr(resnorm2),
                                          C.c_void_p(stream or 0)))
 
+    def ghost_source(self, which, window=None, token=0):
+        """Ghost rows of the state (which=0) / the reconstruction gradients (which=1) come from the halo window of
+        exchange `token` (PeerHaloWindow.post) instead of the array; None/0 switches back."""
+        check(load().fvg_flow_ghost_source(self._h, int(which), window._h if window is not None else None,
+                                           C.c_ulonglong(token)))
+
     def select_tiles(self, part):
         """Tiles covered by the split passes: 0 all, 1 interior (no ghost cell in sight), 2 partition boundary."""
         check(load().fvg_flow_select_tiles(self._h, int(part)))
@@ -433,6 +439,12 @@ class PeerHaloWindow:
 
     def send(self, arr, width, stream=None):
         check(load().fvg_halo_send(self._h, _ptr(arr), int(width), C.c_void_p(stream or 0)))
+
+    def post(self, arr, width, stream=None):
+        """Send only; returns the token of this exchange for FlowFV.ghost_source."""
+        tok = C.c_ulonglong(0)
+        check(load().fvg_halo_post(self._h, _ptr(arr), int(width), C.c_void_p(stream or 0), C.byref(tok)))
+        return int(tok.value)
 
     def recv(self, arr, width, stream=None):
         check(load().fvg_halo_recv(self._h, _ptr(arr), int(width), C.c_void_p(stream or 0)))

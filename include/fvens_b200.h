@@ -153,6 +153,15 @@ int fvg_halo_send(fvg_halo *h, const double *d_arr, int width, void *stream);
 int fvg_halo_recv(fvg_halo *h, double *d_arr, int width, void *stream);
 /* send + recv in one launch (the pushing and the waiting CTAs are co-resident) */
 int fvg_halo_exchange(fvg_halo *h, double *d_arr, int width, void *stream);
+/* In-kernel receive: fvg_halo_post only sends (this rank's rows into the neighbours' windows, flag released) and
+ * returns a token; fvg_flow_ghost_source(flow, which, halo, token) tells the flow that the ghost rows of the state
+ * (which = 0) or of the reconstruction gradients (which = 1) are NOT in the array but in the halo window of that
+ * exchange. The next split passes, run with fvg_flow_select_tiles(flow, 3), then wait for the neighbours' flags
+ * inside the kernel - only the CTAs that reach a partition-boundary tile, only once, and after all their interior
+ * tiles - and gather the ghost rows straight from the window: no receive kernel, no copy, and the wait hides behind
+ * the interior work. Valid for the two most recent exchanges of a window. token 0 / halo NULL switches back to the
+ * array. Inviscid linear-reconstruction or first-order flows only (other passes read ghost rows from the arrays). */
+int fvg_halo_post(fvg_halo *h, const double *d_arr, int width, void *stream, unsigned long long *token);
 /* 0 if every receive so far saw its neighbours arrive; else the sequence number of a receive that gave up waiting */
 int fvg_halo_status(fvg_halo *h, unsigned long long *h_timed_out_seq);
 void fvg_halo_destroy(fvg_halo *h);
@@ -233,8 +242,11 @@ int fvg_euler_face_pass(fvg_flow *f, const double *d_u, double *d_unew, double c
  * 2 = tiles on the partition boundary. A multi-GPU driver runs part 1 while the ghost rows are in flight and
  * part 2 once they have arrived (the reference overlaps its trace exchange with the interior faces the same way,
  * spatial/flow_spatial.cpp:738-782). On an unpartitioned mesh every tile is in part 1 and part 2 is empty;
- * fvg_euler_face_pass sums the norm after part 2 (or 0). WENO's stage-1 pass always covers all tiles. */
+ * fvg_euler_face_pass sums the norm after part 2 (or 0). WENO's stage-1 pass always covers all tiles.
+ * 3 = all tiles in ONE launch, interior tiles first: the order the in-kernel receive below relies on. */
 int fvg_flow_select_tiles(fvg_flow *f, int part);
+/* see fvg_halo_post */
+int fvg_flow_ghost_source(fvg_flow *f, int which, fvg_halo *h, unsigned long long token);
 int fvg_flow_buffers(fvg_flow *f, double **d_lg, double **d_gu);
 /* Makes the flow use caller-owned gradient buffers ([ncell+nghost][8] doubles each, device memory that must
  * outlive the flow's use of them), e.g. tensors that a communication library can address. */
