@@ -93,7 +93,7 @@ static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s, int t
 	a.prefetch_distance = f->prefetch_distance;
 	resolve_tiles(f, tile0, tile1, a.tlist);
 	a.tile0 = tile0; a.tile1 = tile1;
-	if(a.tlist && f->part == 3) a.gs_u = f->gs_u;
+	a.gs_u = f->gs_u;
 	int rc;
 	if(P.recon == FVG_RECON_WENO) {
 		a.lg = nullptr; a.gu = f->d_gu;
@@ -169,7 +169,7 @@ static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumul
 	a.prefetch_distance = f->prefetch_distance;
 	resolve_tiles(f, tile0, tile1, a.tlist);
 	a.tile0 = tile0; a.tile1 = tile1;
-	if(a.tlist && f->part == 3) { a.gs_u = f->gs_u; a.gs_g = f->gs_g; }
+	a.gs_u = f->gs_u; a.gs_g = f->gs_g;
 	const int recon = !P.order2 ? FR_FIRST : (P.recon == FVG_RECON_VANALBADA ? FR_MUSCL : FR_LINEAR);
 	int rt = make_row_tensor_map(&a.tm_u, u, (size_t)a.m.ncell, 4, tile_box_rows(a.m.TC));
 	if(rt == 0 && recon == FR_LINEAR) rt = make_row_tensor_map(&a.tm_g, a.lg, (size_t)a.m.ncell, 8, tile_box_rows(a.m.TC));

@@ -477,7 +477,10 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 				for(int c = 0; c < 8; c++) { members += gcnt[g*8+c]; distinct += gcnt[g*8+c] > 0; }
 				if(members > 0) { ngroups++; if(distinct < members) nconfl++; }
 			}
-			tbnd[t] = make_int4(seg[0], seg[0] + seg[1], cnt[2], len - nr);
+			// w: padding entries of the segment; bit 16: the tile's halo contains a ghost cell of another rank (the halo
+			// list is ascending, ghosts are numbered after the own cells)
+			const bool ghost_tile = thoff[t+1] > thoff[t] && thalo[thoff[t+1]-1] >= nown;
+			tbnd[t] = make_int4(seg[0], seg[0] + seg[1], cnt[2], (len - nr) | (ghost_tile ? 0x10000 : 0));
 			fsoff[t+1] = fsoff[t] + len;
 			emax_seen = std::max(emax_seen, len);
 		}

@@ -58,6 +58,7 @@ struct DMesh {
 	const int *fsoff;       ///< [ntile+1] stream segment of each tile (multiples of 4)
 	const int4 *tbnd;       ///< [ntile] x: tile-local index of the first cut entry (one side in the halo), y: of the first
 	                        ///< physical-boundary entry, z: number of boundary entries (halo + these <= HMAX), w: padding entries
+	                        ///< (low 16 bits) | 0x10000 if the tile's halo contains a ghost cell of another rank
 	// per stream entry
 	const unsigned *fLR;    ///< local left | local right << 16; right >= LR_BND: boundary face with BC table index (right & 15);
 	                        ///< LR_PAD: padding entry

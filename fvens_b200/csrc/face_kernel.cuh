@@ -138,13 +138,14 @@ __device__ __forceinline__ void ghost_wait(const GhostSrc &g, unsigned long long
 }
 
 /// Descriptor of one tile (all uniform across the CTA)
-struct TileDesc { int c0, nc, h0, nh, e0, ne, nreal; };
+struct TileDesc { int c0, nc, h0, nh, e0, ne, nreal, ghost; };
 __device__ __forceinline__ TileDesc load_tile_desc(const DMesh &M, int t) {
 	TileDesc D;
 	D.c0 = M.tcell0[t]; D.nc = M.tcell0[t+1] - D.c0;
 	D.h0 = M.thoff[t]; D.nh = M.thoff[t+1] - D.h0;
 	D.e0 = M.fsoff[t]; D.ne = M.fsoff[t+1] - D.e0;
-	D.nreal = D.ne - M.tbnd[t].w;
+	const int w = M.tbnd[t].w;
+	D.nreal = D.ne - (w & 0xFFFF); D.ghost = w >> 16;
 	return D;
 }
 
@@ -255,13 +256,13 @@ face_kernel(const __grid_constant__ FaceArgs A)
 	if(tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
 	__syncthreads();
 	if(tid == 0) { issue_AC(D, 0); issue_B(D); }
-	// in-kernel receive: the tile list has the partition-boundary tiles last; a CTA waits for the neighbours' rows
-	// once, right before it gathers the halo of its first boundary tile (by then they have usually arrived)
-	const bool recv_here = A.tlist != nullptr && (A.gs_u.rows != nullptr || A.gs_g.rows != nullptr);
+	// in-kernel receive: a CTA waits for the neighbours' rows once, right before it gathers the halo of its first
+	// tile that sees a ghost cell (a few percent of the tiles, so for most CTAs the rows have long arrived by then)
+	const bool recv_here = A.gs_u.rows != nullptr || A.gs_g.rows != nullptr;
 	const GhostSrc &gsw = A.gs_g.rows ? A.gs_g : A.gs_u;
 	const unsigned long long wseq = A.gs_g.rows ? (A.gs_g.seq > A.gs_u.seq ? A.gs_g.seq : A.gs_u.seq) : A.gs_u.seq;
 	bool waited = !recv_here;
-	if(!waited && ti >= M.ntile_interior) { ghost_wait(gsw, wseq); waited = true; }
+	if(!waited && D.ghost) { ghost_wait(gsw, wseq); waited = true; }
 	issue_halo(D.nh, tid < D.nh ? M.thalo[D.h0 + tid] : 0);
 
 	for(int it = 0; ti < tend; it++) {
@@ -451,7 +452,7 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		// group B buffers are free: the next tile's entry metadata and halo rows
 		if(have_next) {
 			if(tid == 0) { fence_proxy_async(); issue_B(Dn); }
-			if(!waited && tin >= M.ntile_interior) { ghost_wait(gsw, wseq); waited = true; }
+			if(!waited && Dn.ghost) { ghost_wait(gsw, wseq); waited = true; }
 			issue_halo(Dn.nh, gnext);
 		}
 

@@ -70,10 +70,6 @@ cell_kernel(const CellArgs A)
 	constexpr bool NEED_NBRS = GRAD == GM_GG || GRAD == GM_WLS || LIM != LM_NONE;
 
 	if(tid == 0) mbar_init(bar, 1);
-	// in-kernel receive of the state's ghost rows: the CTAs of partition-boundary tiles (last in the tile list) wait
-	// for the neighbours here; interior tiles never do
-	const bool ghost_win = A.gs_u.rows != nullptr;
-	if(ghost_win && A.tlist && (int)blockIdx.x + A.tile0 >= M.ntile_interior) ghost_wait(A.gs_u, A.gs_u.seq);
 	__syncthreads();
 	if(tid == 0) {
 		unsigned bytes = (unsigned)nc*(32u + 16u + 16u + (GRAD == GM_WLS ? 32u : 0u)) + (LIM == LM_VENKAT ? (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u : 0u);
@@ -102,18 +98,28 @@ cell_kernel(const CellArgs A)
 		if(MIDS) bulk_prefetch_l2(M.fgr + pe0, (unsigned)pne*16u);
 		if(METRICS) { bulk_prefetch_l2(M.fgw + pe0, (unsigned)pne*16u); bulk_prefetch_l2(M.fgln + pe0, (unsigned)pne*16u); }
 	}
+	const int4 tbq = M.tbnd[t];
+	// in-kernel receive of the state's ghost rows: a tile that sees ghost cells waits for the neighbours' rows (its
+	// other copies are already in flight), then gathers those rows from the halo window
+	const bool ghost_win = A.gs_u.rows != nullptr && (tbq.w >> 16) != 0;
 	if(NEED_NBRS) {
 		for(int k = tid; k < nh*3; k += CELL_BLOCK) {
 			const int h = k/3, piece = k - 3*h;
 			const size_t g = (size_t)M.thalo[h0 + h];
 			const int row = nc + h;
-			const double *const urow = (ghost_win && g >= (size_t)M.ncell) ? A.gs_u.rows + 4*(g - (size_t)M.ncell) : A.u + 4*g;
-			if(piece < 2) cp_async16(sp + 4*row + 2*piece, urow + 2*piece);
-			else cp_async16(src + row, M.rc + g);
+			if(piece == 2) cp_async16(src + row, M.rc + g);
+			else if(!(ghost_win && g >= (size_t)M.ncell)) cp_async16(sp + 4*row + 2*piece, A.u + 4*g + 2*piece);
+		}
+		if(ghost_win) {
+			ghost_wait(A.gs_u, A.gs_u.seq);
+			for(int k = tid; k < nh*2; k += CELL_BLOCK) {
+				const int h = k >> 1, piece = k & 1;
+				const size_t g = (size_t)M.thalo[h0 + h];
+				if(g >= (size_t)M.ncell) cp_async16(sp + 4*(nc + h) + 2*piece, A.gs_u.rows + 4*(g - (size_t)M.ncell) + 2*piece);
+			}
 		}
 		cp_async_commit();
 	}
-	const int4 tbq = M.tbnd[t];
 	const int2 tb = make_int2(tbq.y, tbq.z);   // boundary entries of the tile: first (tile-local) and count
 	const int grow0 = nc + nh;                 // their ghost cells are staged as rows grow0 .. grow0 + tb.y - 1
 	cp_async_wait_all();

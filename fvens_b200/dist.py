@@ -204,17 +204,15 @@ class DistFlow:
         fl.select_tiles(0)
 
     def _in_kernel_receive(self, u, face):
-        """Two sends and two passes, no receive kernel: each pass waits for the neighbours' rows itself, in the CTAs that
-        reach a partition-boundary tile and after their interior tiles, and reads the ghost rows from the halo window."""
+        """Two sends and two passes, no receive kernel: each pass waits for the neighbours' rows itself, only in the CTAs
+        that reach a tile with ghost cells in its halo, and reads the ghost rows from the halo window."""
         s = self._stream()
         fl, win = self.flow, self.halo.win
         fl.ghost_source(0, win, win.post(u, 4, stream=s))
-        fl.select_tiles(3)
         if self.order2:
             fl.gradient_pass(u, 0, stream=s)
             fl.ghost_source(1, win, win.post(self.lg, 8, stream=s))
         face(s)
-        fl.select_tiles(0)
         fl.ghost_source(0); fl.ghost_source(1)
 
     def residual(self, u, res, dtm, gettimesteps=True, exchange_state=True):

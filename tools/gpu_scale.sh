@@ -5,8 +5,8 @@ out=gpurun_out; mkdir -p $out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1"
 timeout 300 $TR --master-port 29511 tests/mgpu_check.py > $out/${tag}_mgpu_check_n$n.log 2>&1; tail -3 $out/${tag}_mgpu_check_n$n.log
 timeout 600 $TR --master-port 29512 bench.py --gpus $n --steps 100 --warmup 5 > $out/${tag}_bench_n$n.json 2> $out/${tag}_bench_n$n.err
-FVG_OVERLAP=0 timeout 600 $TR --master-port 29513 bench.py --gpus $n --steps 100 --warmup 5 > $out/${tag}_bench_n${n}_nooverlap.json 2> $out/${tag}_bench_n${n}_nooverlap.err
-for f in $out/${tag}_bench_n$n.json $out/${tag}_bench_n${n}_nooverlap.json; do python - "$f" <<'PY'
+FVG_FUSED_RECV=0 timeout 600 $TR --master-port 29513 bench.py --gpus $n --steps 100 --warmup 5 > $out/${tag}_bench_n${n}_recvkernel.json 2> $out/${tag}_bench_n${n}_recvkernel.err
+for f in $out/${tag}_bench_n$n.json $out/${tag}_bench_n${n}_recvkernel.json; do python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
