@@ -373,7 +373,7 @@ int fvg_flow_create(fvg_mesh *mesh, const fvg_physics *phys, const fvg_numerics 
 	int rc;
 	if(P.need_lg && (rc = dev_alloc(f.get(), &f->d_lg, 8*(size_t)n)) != 0) return rc;
 	if(P.need_gu && (rc = dev_alloc(f.get(), &f->d_gu, 8*(size_t)n)) != 0) return rc;
-	if((rc = dev_alloc(f.get(), &f->d_partial, mesh->d.ntile)) != 0) return rc;
+	if((rc = dev_alloc(f.get(), &f->d_partial, (size_t)mesh->d.ntile*(FACE_BLOCK/32))) != 0) return rc;
 	if((rc = dev_alloc(f.get(), &f->d_norm, 1)) != 0) return rc;
 	FVG_CUDA(cudaMallocHost((void**)&f->h_norm, sizeof(double)));
 	{
@@ -803,7 +803,7 @@ int fvg_euler_face_pass(fvg_flow *f, const double *d_u, double *d_unew, double c
 	int rc;
 	if((rc = run_face_pass(f, d_u, EP_STEP, 0, 1, nullptr, nullptr, cfl, d_unew, s)) != 0) return rc;
 	if(f->part == 1 && f->mesh->d.tile_order) return 0;      // the norm is summed once all tiles have their partial sums
-	if((rc = launch_final_norm(f->d_partial, f->mesh->d.ntile, f->d_norm, s)) != 0) return rc;
+	if((rc = launch_final_norm(f->d_partial, f->mesh->d.ntile*(FACE_BLOCK/32), f->d_norm, s)) != 0) return rc;
 	f->launches++;
 	if(d_resnorm2) FVG_CUDA(cudaMemcpyAsync(d_resnorm2, f->d_norm, sizeof(double), cudaMemcpyDeviceToDevice, s));
 	return 0;
@@ -839,7 +839,7 @@ static int step_device_order(fvg_flow *f, const double *uin, double *uout, doubl
 	if((rc = mark(f, s)) != 0) return rc;
 	if((rc = run_face_pass(f, uin, EP_STEP, 0, 1, nullptr, nullptr, cfl, uout, s)) != 0) return rc;
 	if((rc = mark(f, s)) != 0) return rc;
-	if((rc = launch_final_norm(f->d_partial, f->mesh->d.ntile, f->d_norm, s)) != 0) return rc;
+	if((rc = launch_final_norm(f->d_partial, f->mesh->d.ntile*(FACE_BLOCK/32), f->d_norm, s)) != 0) return rc;
 	f->launches++;
 	return 0;
 }

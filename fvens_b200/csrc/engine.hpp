@@ -149,7 +149,7 @@ struct fvg_flow {
 	double *d_rperm = nullptr;     ///< [ncell][4] scratch residual in device order
 	double *d_dtperm = nullptr;    ///< [ncell]
 	double *d_u2 = nullptr;        ///< [ncell][4] second state buffer for the fused step
-	double *d_partial = nullptr;   ///< [ntile] per-tile partial norms
+	double *d_partial = nullptr;   ///< [ntile][FACE_BLOCK/32] partial norms per tile and warp
 	double *d_norm = nullptr;      ///< [1]
 	double *h_norm = nullptr;      ///< pinned [1]
 	double *d_hu = nullptr, *d_hr = nullptr, *d_hdt = nullptr;   ///< staging for the host-buffer entry point
@@ -242,7 +242,7 @@ struct FaceArgs {
 	double *dtm;           ///< [ncell]
 	double cfl;            ///< EP_STEP
 	double *unew;          ///< EP_STEP: [ncell][4]
-	double *partial;       ///< EP_STEP: [ntile] sum of r_E^2*area
+	double *partial;       ///< EP_STEP: [ntile][FACE_BLOCK/32] sums of r_E^2*area per tile and warp
 	int prefetch_distance; ///< tiles ahead whose operands are pulled into L2 (0 = off)
 	// TMA descriptors of the per-cell row arrays staged per tile: box = TC rows, hardware-swizzled so that
 	// "thread k reads row k" is free of shared-memory bank conflicts (32-byte rows: SWIZZLE_32B, 64-byte: SWIZZLE_64B)

@@ -192,7 +192,6 @@ face_kernel(const __grid_constant__ FaceArgs A)
 	double *const sg = reinterpret_cast<double*>(smraw + S.sg);
 	double2 *const src = reinterpret_cast<double2*>(smraw + S.src);
 	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);       // [0]: groups A + C, [1]: group B
-	double *const red_s = reinterpret_cast<double*>(smraw + S.red);
 
 	const int tid = threadIdx.x;
 	const double *const gsrc = RECON == FR_MUSCL ? A.gu : A.lg;     // gradients used by the reconstruction
@@ -503,15 +502,10 @@ face_kernel(const __grid_constant__ FaceArgs A)
 			}
 		}
 		if(A.epilogue == EP_STEP) {
-			// fixed-order block reduction: warp shuffle tree, then thread 0 sums the warp partials in order
+			// fixed-order reduction: warp shuffle tree here, one partial per (tile, warp); the norm kernel sums them in
+			// index order (no CTA barrier and no atomics: bitwise reproducible)
 			for(int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-			if((tid & 31) == 0) red_s[tid >> 5] = part;
-			__syncthreads();
-			if(tid == 0) {
-				double s = 0.0;
-				for(int w = 0; w < FACE_BLOCK/32; w++) s += red_s[w];
-				A.partial[t] = s;
-			}
+			if((tid & 31) == 0) A.partial[(size_t)t*(FACE_BLOCK/32) + (tid >> 5)] = part;
 		}
 		// phase C reads the flux slots that the next tile's phase A overwrites
 		__syncthreads();
