@@ -192,8 +192,14 @@ struct Flow {
 				const double areainv1 = 1.0/m->area[ie];
 				for(int iv = 0; iv < 4; iv++) {
 					const double ut = (u[4*ie+iv]*dL + ug[4*f+iv]*dR)/(dL+dR) * m->facemetric[3*f+2];
-					for(int d = 0; d < 2; d++)
+					// The reference updates grad[ielem] WITHOUT `omp atomic` in this loop (agradientschemes.cpp:109-110):
+					// a cell with two boundary faces (domain corners) races when the faces fall to different threads,
+					// and its gradient - then the residual of the cells around it - comes out wrong now and then. The
+					// oracle states the intended (sequential) arithmetic, so the update is atomic here.
+					for(int d = 0; d < 2; d++) {
+#pragma omp atomic update
 						grad[8*ie+d+2*iv] += (ut * m->facemetric[3*f+d])*areainv1;
+					}
 				}
 			}
 
