@@ -1,0 +1,134 @@
+"""Control-file front end and case driver (fvens_b200/host/controlparser.hpp, casesolvers.hpp, fvens_steady.cpp)
+against the reference's own control files (tests/golden/ctrl, copied from testcases/naca0012, tests/flow-general,
+tests/inv-2dcyl): what parse_flow_controlfile (reference src/utilities/controlparser.cpp:60-290) must extract,
+including Boost.PropertyTree INFO corner cases the reference's files rely on (#include, quoted and unquoted values,
+`key` and `{` on different lines, a second word after a value starting a new key).
+The GPU test runs the fvens_steady executable end to end and compares it with the same run driven through the
+Python mirror of the class surface."""
+import json
+import math
+import os
+import re
+import subprocess
+import xml.dom.minidom
+
+import numpy as np
+import pytest
+
+from common import ROOT, MESHDIR
+
+CTRL = os.path.join(ROOT, "tests", "golden", "ctrl")
+PROBE = os.path.join(ROOT, "tests", "cpp", "test_controlparser")
+STEADY = os.path.join(ROOT, "tests", "cpp", "fvens_steady")
+BC = dict(slipwall=0, farfield=1, inflowoutflow=2, subsonic_inflow=3, extrapolation=4, periodic=5, isothermalwall=6, adiabaticwall=7)
+
+
+def parse(name, *cmd):
+    r = subprocess.run([PROBE, os.path.join(CTRL, name), *cmd], capture_output=True, text=True, timeout=60)
+    return json.loads(r.stdout.strip().splitlines()[-1])       # the parser announces command-line overrides on stdout, as the reference
+
+
+def test_naca0012_explicit_control_file():
+    o = parse("naca0012-transonic-explicit.ctrl")
+    assert o["meshfile"] == "testcases/naca0012/grids/NACA0012_inv.su2" and o["vtu"] == "naca.vtu" and o["logfile"] == "naca-log"
+    assert o["lognres"] == 0 and o["flowtype"] == "EULER" and o["viscsim"] == 0 and o["sim_type"] == "STEADY"
+    assert o["gamma"] == 1.4 and o["Minf"] == 0.8 and o["alpha"] == math.pi/180.0*1.25
+    assert o["Tinf"] == 298.0 and o["Reinf"] is None and o["Pr"] is None          # the reference's 1/0 and 0/0 for Euler runs
+    assert (o["invflux"], o["gradient"], o["limiter"], o["order2"]) == ("HLLC", "LEASTSQUARES", "WENO", 1)
+    assert o["limiter_param"] == 20.0                                               # read here, lost in the reference
+    assert o["pseudotimetype"] == "EXPLICIT" and (o["initcfl"], o["endcfl"], o["tolerance"], o["maxiter"]) == (0.2, 0.2, 1e-5, 200000)
+    assert o["usestarter"] == 1 and (o["firstinitcfl"], o["firsttolerance"], o["firstmaxiter"]) == (0.8, 0.1, 10000)
+    assert o["lwalls"] == [2] and o["surfnameprefix"] == "inv-naca" and o["vol_output_reqd"] == "NO"
+    assert o["bcs"] == [dict(tag=2, type=BC["slipwall"], vals=[]), dict(tag=4, type=BC["farfield"], vals=[])]
+    # firstorder_spatial_numerics_config / extract_spatial_numerics_config
+    assert o["first_order"] == dict(gradient="NONE", limiter="NONE", order2=0, flux="HLLC") and o["main"] == dict(gradient="LEASTSQUARES", order2=1)
+    assert o["phys_nbc"] == 2
+
+
+def test_viscous_control_file_and_info_corner_cases():
+    o = parse("flow-general-test.ctrl")
+    assert o["flowtype"] == "NAVIERSTOKES" and o["viscsim"] == 1 and o["useconstvisc"] == 0
+    assert (o["Minf"], o["Tinf"], o["Reinf"], o["Pr"]) == (0.5, 288.15, 5000.0, 0.72)
+    assert (o["invflux"], o["gradient"], o["limiter"]) == ("ROE", "LEASTSQUARES", "NONE")
+    bcs = {b["tag"]: b for b in o["bcs"]}
+    assert bcs[4]["type"] == BC["farfield"] and bcs[2]["type"] == BC["adiabaticwall"] and bcs[3]["type"] == BC["isothermalwall"]
+    assert bcs[2]["vals"] == [0.0]                      # quoted "0.0"
+    # `boundary_values 0.0  290.0` is unquoted: Boost's INFO parser takes "0.0" as the value and starts a new key with
+    # "290.0" - so does this parser (the reference's Isothermalwall2D then reads past the end of bc_vals)
+    assert bcs[3]["vals"] == [0.0]
+
+
+def test_include_directive_and_command_line_overrides():
+    o = parse("expl-cyl-ls-hllc.ctrl", "source_dir", CTRL, "mesh_file", "some/mesh.msh", "log_file_prefix", "/tmp/x")
+    assert o["meshfile"] == "some/mesh.msh" and o["logfile"] == "/tmp/x" and o["lognres"] == 1
+    assert o["Minf"] == 0.38 and o["lwalls"] == [2] and o["surfnameprefix"] == "2dcyl"
+    assert (o["invflux"], o["gradient"], o["limiter"], o["limiter_param"]) == ("HLLC", "LEASTSQUARES", "NONE", 1.0)
+    assert (o["initcfl"], o["tolerance"], o["maxiter"], o["firstmaxiter"]) == (0.25, 1e-4, 10000, 1000)
+    # without the source directory the include cannot be resolved: an error, not a silent default
+    assert "cannot open control file" in parse("expl-cyl-ls-hllc.ctrl", "source_dir", "/nonexistent")["error"]
+
+
+def test_implicit_options_are_parsed_but_missing_keys_are_errors(tmp_path):
+    o = parse("naca0012-transonic-implicit.ctrl")
+    assert o["pseudotimetype"] == "IMPLICIT" and o["invfluxjac"] == o["invflux"]       # "consistent"
+    bad = tmp_path / "bad.ctrl"
+    bad.write_text(open(os.path.join(CTRL, "naca0012-transonic-explicit.ctrl")).read().replace("freestream_Mach_number  0.8", ""))
+    assert "No such node (flow_conditions.freestream_Mach_number)" in parse(str(bad))["error"]
+    bad.write_text("io {\n mesh_file \"x\"\n")
+    assert "unmatched" in parse(str(bad))["error"]
+
+
+@pytest.mark.gpu
+def test_fvens_steady_end_to_end(tmp_path):
+    import torch
+    from fvens_b200 import lib
+    nsteps = 40
+    mesh = os.path.join(MESHDIR, "2dcylinder1.msh")
+    prefix = str(tmp_path / "cyl")
+    # the control file's output names are relative: run in the temporary directory
+    r = subprocess.run([STEADY, os.path.join(CTRL, "expl-cyl-ls-hllc.ctrl"), "--source_dir", CTRL, "--mesh_file", mesh,
+                        "--log_file_prefix", prefix, "--max_timesteps", str(nsteps)], capture_output=True, text=True, timeout=600,
+                       cwd=str(tmp_path))
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "--------------- End" in r.stdout
+    m = re.search(r"Functionals: h (\S+) entropy (\S+) CL (\S+) CDp (\S+) CDf (\S+)", r.stdout)
+    h, entropy, cl, cdp, cdf = (float(x) for x in m.groups())
+
+    # the same case through the Python mirror: first-order starter, then the main solve, both capped at nsteps
+    um = lib.UMesh.read(mesh)
+    phys = lib.make_physics(1.4, 0.38, 298.0, float("inf"), float("nan"), 0.0)
+    bcs = [(2, "slipwall", (0, 0)), (4, "farfield", (0, 0))]
+    dm = lib.DeviceMesh(um, reorder="hilbert", tile_cells=256)
+    u = torch.from_numpy(np.tile(lib.freestream(phys), (um.nelem, 1))).cuda()
+    f1 = lib.FlowFV(dm, phys, "HLLC", "NONE", "NONE", 1.0, False, 0, bcs)
+    f1.solve_forward_euler(u, 0.5, 1e-1, nsteps)
+    f2 = lib.FlowFV(dm, phys, "HLLC", "LEASTSQUARES", "NONE", 1.0, True, 0, bcs)
+    code, steps, hist = f2.solve_forward_euler(u, 0.25, 1e-4, nsteps)
+    g = torch.zeros(um.nelem, 8, dtype=torch.float64, device="cuda")
+    f2.getGradients(u, g)
+    cl0, cdp0, cdf0 = f2.computeSurfaceData(u, g, 2)
+    assert abs(cl - cl0) < 1e-12 + 1e-10*abs(cl0) and abs(cdp - cdp0) < 1e-12 + 1e-10*abs(cdp0) and cdf == 0.0 == cdf0
+    assert abs(entropy/f2.entropy_error(u) - 1) < 1e-10 and abs(h - 1.0/math.sqrt(um.nelem)) < 1e-12
+
+    # residual history in the reference's format (spatial/aoutput.cpp:617-636): header, rule, one line per step
+    lines = open(prefix + "-residual_history.log").read().splitlines()
+    assert lines[0].split() == ["#", "NStep", "Log", "rel", "resi", "Log", "abs", "resi", "Tot.Wtime", "Lin.Wtime", "Lin.iters", "CFL"]
+    assert lines[1].startswith("#---") and len(lines) == 2 + steps
+    rows = np.array([[float(x) for x in ln.split()] for ln in lines[2:]])
+    assert (rows[:, 0] == np.arange(1, steps+1)).all() and rows[0, 1] == 0.0 and (rows[:, 6] == 0.25).all()
+    assert np.abs(rows[:, 2] - np.log10(hist)).max() < 1e-5          # printed with 6 significant digits, norm stored as float
+    # surface file: one line per wall face + the coefficient line; VTU: well-formed, one value per point
+    surf = open(os.path.join(str(tmp_path), "2dcyl-surf_w2.out")).read().splitlines()
+    a = um.arrays()
+    nwall = int((a["btags"][:, 0] == 2).sum())
+    assert surf[0].startswith("#  x") and len(surf) == nwall + 3 and surf[-2].startswith("# Cl")
+    assert abs(float(surf[-1].split()[1]) - cl) < 1e-5*max(abs(cl), 1e-3)
+    pts = np.array([[float(x) for x in ln.split()] for ln in surf[1:1+nwall]])
+    assert np.abs(np.hypot(pts[:, 0], pts[:, 1]) - 0.5).max() < 0.02      # face midpoints of the cylinder of radius 0.5
+    doc = xml.dom.minidom.parse(os.path.join(str(tmp_path), "2dcyl.vtu"))
+    piece = doc.getElementsByTagName("Piece")[0]
+    assert int(piece.getAttribute("NumberOfPoints")) == a["coords"].shape[0] and int(piece.getAttribute("NumberOfCells")) == um.nelem
+    names = [d.getAttribute("Name") for d in doc.getElementsByTagName("PointData")[0].getElementsByTagName("DataArray")]
+    assert names == ["density", "mach-number", "pressure", "temperature", "velocity"]
+    dens = np.array(doc.getElementsByTagName("PointData")[0].getElementsByTagName("DataArray")[0].firstChild.data.split(), dtype=float)
+    assert len(dens) == a["coords"].shape[0] and (dens > 0.5).all() and (dens < 1.5).all()
