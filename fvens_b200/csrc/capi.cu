@@ -666,6 +666,28 @@ int fvg_boundary_states(fvg_flow *f, const double *d_ins, double *d_gs, void *st
 	return rc;
 }
 
+int fvg_jacobian_vector_product(fvg_flow *f, const double *d_u, const double *d_res, const double *d_mdt, const double *d_x,
+                                double eps, double *d_y, void *stream)
+{
+	if(!f || !d_u || !d_res || !d_mdt || !d_x || !d_y || !(eps > 0.0)) { set_error("fvg_jacobian_vector_product: bad argument"); return FVG_ERR_INVALID; }
+	if(f->mesh->nranks > 1) { set_error("fvg_jacobian_vector_product: single-GPU entry point"); return FVG_ERR_UNSUPPORTED; }
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	const int n = f->mesh->d.ncell;
+	const int nblk = 1024;
+	int rc;
+	if((rc = ensure(f, &f->d_jaux, 4*(size_t)n)) != 0) return rc;
+	if((rc = ensure(f, &f->d_jyg, 4*(size_t)n)) != 0) return rc;
+	if((rc = ensure(f, &f->d_jpart, nblk)) != 0) return rc;
+	if((rc = ensure(f, &f->d_jnorm, 1)) != 0) return rc;
+	// |x|^2 stays on the device; aux = u + eps/|x| x; yg = -r(aux); y = mdt x + (res - yg)/(eps/|x|)
+	if((rc = launch_sumsq(d_x, 4ll*n, f->d_jpart, nblk, f->d_jnorm, s)) != 0) return rc;
+	if((rc = launch_perturb(d_u, d_x, f->d_jnorm, eps, 4ll*n, f->d_jaux, s)) != 0) return rc;
+	if((rc = fvg_residual(f, f->d_jaux, f->d_jyg, 0, 0, nullptr, s)) != 0) return rc;
+	if((rc = launch_jvp_combine(d_x, d_res, f->d_jyg, d_mdt, f->d_jnorm, eps, n, 4, d_y, s)) != 0) return rc;
+	f->launches += 4;
+	return 0;
+}
+
 int fvg_get_gradients(fvg_flow *f, const double *d_u, double *d_grads, void *stream)
 {
 	if(!f || !d_u || !d_grads) { set_error("fvg_get_gradients: null argument"); return FVG_ERR_INVALID; }

@@ -153,6 +153,7 @@ struct fvg_flow {
 	double *d_norm = nullptr;      ///< [1]
 	double *h_norm = nullptr;      ///< pinned [1]
 	double *d_hu = nullptr, *d_hr = nullptr, *d_hdt = nullptr;   ///< staging for the host-buffer entry point
+	double *d_jaux = nullptr, *d_jyg = nullptr, *d_jpart = nullptr, *d_jnorm = nullptr;   ///< scratch of fvg_jacobian_vector_product
 	// chunked host-buffer pipeline (fvg_residual_host): tile ranges, their upload order and dependencies
 	struct HostPipe {
 		bool planned = false;
@@ -212,6 +213,10 @@ int launch_boundary_prim_ghosts(const DMesh &m, const GasParams &g, const double
                                 double *ug, bool prim_out, cudaStream_t s);
 int launch_halo_pack(const DMesh &m, const double *src, int width, double *dst, cudaStream_t s);
 int launch_final_norm(const double *partial, int n, double *out, cudaStream_t s);
+int launch_sumsq(const double *x, long long n, double *partial, int nblk, double *out, cudaStream_t s);
+int launch_perturb(const double *u, const double *x, const double *xnorm2, double eps, long long n, double *aux, cudaStream_t s);
+int launch_jvp_combine(const double *x, const double *res, const double *yg, const double *mdt, const double *xnorm2,
+                       double eps, int ncell, int nvars, double *y, cudaStream_t s);
 int launch_surface_data(const DMesh &m, const GasParams &g, double aoa, const double *u, const double *grads,
                         int slot, double *out4, cudaStream_t s);
 int launch_entropy(const DMesh &m, const GasParams &g, const double *u, double *out, cudaStream_t s);

@@ -679,6 +679,73 @@ int launch_entropy(const DMesh &m, const GasParams &g, const double *u, double *
 }
 
 // ------------------------------------------------------------------------------------------------
+// vector kernels of the matrix-free Jacobian-vector product (linalg/alinalg.cpp:143-230)
+
+/// per-block partial sums of x_i^2 (fixed order inside the block; summed by final_norm_kernel)
+__global__ void sumsq_kernel(const double *__restrict__ x, long long n, double *__restrict__ partial)
+{
+	__shared__ double s[256];
+	double acc = 0.0;
+	for(long long i = (long long)blockIdx.x*256 + threadIdx.x; i < n; i += (long long)gridDim.x*256) acc += x[i]*x[i];
+	s[threadIdx.x] = acc;
+	__syncthreads();
+	for(int o = 128; o > 0; o >>= 1) {
+		if(threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+		__syncthreads();
+	}
+	if(threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+
+/// aux = u + (eps/|x|) x; |x|^2 is read from device memory (no host round trip)
+__global__ void perturb_kernel(const double *__restrict__ u, const double *__restrict__ x, const double *__restrict__ xnorm2,
+                               double eps, long long n, double *__restrict__ aux)
+{
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	const double pertmag = eps/sqrt(xnorm2[0]);
+	aux[i] = u[i] + pertmag*x[i];
+}
+
+/// y = mdt x + (res - yg)/(eps/|x|): res and yg hold -r(u) and -r(u + pert) as compute_residual leaves them
+__global__ void jvp_combine_kernel(const double *__restrict__ x, const double *__restrict__ res, const double *__restrict__ yg,
+                                   const double *__restrict__ mdt, const double *__restrict__ xnorm2, double eps,
+                                   int ncell, int nvars, double *__restrict__ y)
+{
+	const long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+	if(i >= (long long)ncell*nvars) return;
+	const double pertmag = eps/sqrt(xnorm2[0]);
+	y[i] = mdt[i/nvars]*x[i] + (-yg[i] + res[i])/pertmag;
+}
+
+int launch_sumsq(const double *x, long long n, double *partial, int nblk, double *out, cudaStream_t s)
+{
+	sumsq_kernel<<<nblk, 256, 0, s>>>(x, n, partial);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "sumsq_kernel launch", __FILE__, __LINE__);
+	return launch_final_norm(partial, nblk, out, s);
+}
+
+int launch_perturb(const double *u, const double *x, const double *xnorm2, double eps, long long n, double *aux, cudaStream_t s)
+{
+	if(n == 0) return 0;
+	perturb_kernel<<<(unsigned)((n + 255)/256), 256, 0, s>>>(u, x, xnorm2, eps, n, aux);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "perturb_kernel launch", __FILE__, __LINE__);
+	return 0;
+}
+
+int launch_jvp_combine(const double *x, const double *res, const double *yg, const double *mdt, const double *xnorm2,
+                       double eps, int ncell, int nvars, double *y, cudaStream_t s)
+{
+	const long long n = (long long)ncell*nvars;
+	if(n == 0) return 0;
+	jvp_combine_kernel<<<(unsigned)((n + 255)/256), 256, 0, s>>>(x, res, yg, mdt, xnorm2, eps, ncell, nvars, y);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "jvp_combine_kernel launch", __FILE__, __LINE__);
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // pointwise test hooks
 
 template <int FLUX>

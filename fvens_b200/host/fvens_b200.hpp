@@ -836,6 +836,37 @@ private:
 	}
 };
 
+/// Reference: MatrixFreeSpatialJacobian (linalg/alinalg.hpp:60-110, alinalg.cpp:122-230): the action of the
+/// pseudo-time-shifted residual Jacobian on a vector by a finite difference of two residuals. set_state stores
+/// (non-owning) the state, the residual compute_residual left for it and the diagonal shift; apply(x, y) costs one
+/// residual evaluation on the device. Device Vecs are used in place, host Vecs are staged.
+template <int nvars>
+class MatrixFreeSpatialJacobian {
+public:
+	explicit MatrixFreeSpatialJacobian(const Spatial<freal,nvars> *const s, const freal difference_step = 1e-7)
+		: spatial(s), eps(difference_step), u(nullptr), res(nullptr), mdt(nullptr) {}
+
+	int set_state(const Vec u_state, const Vec r_state, const Vec dtms) { u = u_state; res = r_state; mdt = dtms; return 0; }
+
+	StatusCode apply(const Vec x, Vec y) const {
+		const FlowFV_base<freal> *const eng = dynamic_cast<const FlowFV_base<freal>*>(spatial);
+		if(!eng || !u || !res || !mdt || !x || !y) return FVG_ERR_INVALID;
+		const size_t n = (size_t)spatial->mesh()->gnelem();
+		if(u->place == VEC_DEVICE && x->place == VEC_DEVICE && y->place == VEC_DEVICE && res->place == VEC_DEVICE && mdt->place == VEC_DEVICE)
+			return fvg_jacobian_vector_product(eng->engine_flow(), u->dev, res->dev, mdt->dev, x->dev, eps, y->dev, nullptr);
+		if(u->place != VEC_HOST || x->place != VEC_HOST || y->place != VEC_HOST || res->place != VEC_HOST || mdt->place != VEC_HOST)
+			return FVG_ERR_INVALID;
+		DeviceScratch du(n*nvars, u->host.data()), dr(n*nvars, res->host.data()), dm(n, mdt->host.data()), dx(n*nvars, x->host.data()), dy(n*nvars);
+		const int rc = fvg_jacobian_vector_product(eng->engine_flow(), du.p, dr.p, dm.p, dx.p, eps, dy.p, nullptr);
+		if(rc == 0) dy.download(y->host.data());
+		return rc;
+	}
+private:
+	const Spatial<freal,nvars> *const spatial;
+	const freal eps;
+	Vec u, res, mdt;
+};
+
 /// Reference: initializeSystemVector (utilities/casesolvers.cpp:52-69): u := free stream everywhere
 inline StatusCode initializeSystemVector(const FlowPhysicsConfig& pconf, const UMesh<freal,NDIM>& m, Vec u)
 {

@@ -317,6 +317,11 @@ class FlowFV:
     def compute_boundary_states(self, ins, gs, stream=None):
         check(load().fvg_boundary_states(self._h, _ptr(ins), _ptr(gs), C.c_void_p(stream or 0)))
 
+    def jacobian_vector_product(self, u, res, mdt, x, y, eps=1e-7, stream=None):
+        """MatrixFreeSpatialJacobian::apply: y = mdt*x + (r(u + h x) - r(u))/h, h = eps/|x|; res = compute_residual(u)."""
+        check(load().fvg_jacobian_vector_product(self._h, _ptr(u), _ptr(res), _ptr(mdt), _ptr(x), C.c_double(eps), _ptr(y),
+                                                 C.c_void_p(stream or 0)))
+
     def getGradients(self, u, grads, stream=None):
         check(load().fvg_get_gradients(self._h, _ptr(u), _ptr(grads), C.c_void_p(stream or 0)))
 

@@ -259,6 +259,14 @@ int fvg_face_values(fvg_flow *f, const double *d_uprim, const double *d_ug, cons
                     double *d_ufl, double *d_ufr, void *stream);
 /* FlowFV_base::compute_boundary_states (spatial/flow_spatial.cpp:74-93): ins, gs [nbface][4] conserved */
 int fvg_boundary_states(fvg_flow *f, const double *d_ins, double *d_gs, void *stream);
+/* MatrixFreeSpatialJacobian::apply (linalg/alinalg.cpp:143-230): y = mdt x + (r(u + h x) - r(u))/h with h = eps/|x|_2,
+ * the product of the pseudo-time-shifted residual Jacobian with x by one extra residual evaluation (a Krylov solver
+ * can sit on top of the GPU residual without any matrix). d_res is what fvg_residual left for the state d_u
+ * (accumulate = 0), d_mdt the diagonal shift per cell (the reference passes area/dt), all device arrays in the
+ * caller's cell order; the reference's default eps is 1e-7. Asynchronous on `stream`, no host synchronisation
+ * (|x| is reduced and consumed on the device). */
+int fvg_jacobian_vector_product(fvg_flow *f, const double *d_u, const double *d_res, const double *d_mdt, const double *d_x,
+                                double eps, double *d_y, void *stream);
 /* FlowFV_base::getGradients (spatial/flow_spatial.cpp:96-112): gradients of the CONSERVED variables */
 int fvg_get_gradients(fvg_flow *f, const double *d_u, double *d_grads, void *stream);
 /* FlowFV_base::computeSurfaceData (spatial/flow_spatial.cpp:131-310): out3 = Cl, Cdp, Cdf over the

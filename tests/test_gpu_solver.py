@@ -84,3 +84,38 @@ def test_lift_and_drag_after_identical_steps():
     cl, cdp, cdf = fl.computeSurfaceData(du, g, 2)
     cl0, cdp0, cdf0 = of.surface_data(u0, of.get_gradients(u0), 2)
     assert abs(cl-cl0) < 1e-10 and abs(cdp-cdp0) < 1e-10 and abs(cdf-cdf0) < 1e-10
+
+
+@pytest.mark.parametrize("cfg", [dict(recon="VENKATAKRISHNAN"), dict(order2=False, flux="HLLC"),
+                                 dict(mesh="2dcylinderhybrid.msh", recon="NONE", viscous=True, Reinf=100.0)])
+def test_matrix_free_jacobian_vector_product(cfg):
+    """fvg_jacobian_vector_product against MatrixFreeSpatialJacobian::apply (reference src/linalg/alinalg.cpp:143-230)
+    restated with the oracle's residual: y = mdt x + (R(u) - R(u + h x))/h, h = eps/|x|_2, R = what compute_residual
+    leaves. The difference quotient divides round-off of size 1e-16 |R| by h ~ 1e-7/|x|, so two correct residual
+    implementations agree on y only to about 1e-7 relative: the tolerance below is 5e-6 of max|y|."""
+    mesh = cfg.pop("mesh", "bump:40:15")
+    fl, of, u, um = make_case(mesh, tile=64, **cfg)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(u.shape)*np.abs(u).mean(axis=0)*0.1
+    eps = 1e-7
+    res0, dt0, _, _ = of.residual(u)
+    mdt = um.arrays()["area"]/dt0
+    h = eps/np.linalg.norm(x.ravel())
+    yg0, _, _, _ = of.residual(u + h*x, False)
+    y0 = mdt[:, None]*x + (res0 - yg0)/h
+    du, dx = torch.from_numpy(u).cuda(), torch.from_numpy(x).cuda()
+    dres = torch.zeros_like(du); ddt = torch.zeros(len(u), dtype=torch.float64, device="cuda")
+    fl.compute_residual(du, dres, True, ddt, accumulate=False)
+    dmdt = torch.from_numpy(um.arrays()["area"]).cuda()/ddt
+    dy = torch.zeros_like(du)
+    fl.jacobian_vector_product(du, dres, dmdt, dx, dy, eps)
+    torch.cuda.synchronize()
+    y = dy.cpu().numpy()
+    assert np.abs(y - y0).max() < 5e-6*np.abs(y0).max()
+    # it IS the directional derivative: halving x halves the Jacobian part (linearity up to the difference error)
+    dy2 = torch.zeros_like(du)
+    fl.jacobian_vector_product(du, dres, dmdt, 0.5*dx, dy2, eps)
+    torch.cuda.synchronize()
+    jx = y - mdt[:, None]*x
+    jx2 = dy2.cpu().numpy() - mdt[:, None]*0.5*x
+    assert np.abs(jx2 - 0.5*jx).max() < 1e-5*np.abs(jx).max()
