@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 #include <memory>
 
 struct fvg_umesh { fvens::UMesh<double,2> m; };
@@ -300,6 +301,67 @@ int fvg_umesh_rcm_ordering(const fvg_umesh *m, int *perm)
 	rcm_order(m->m.gnelem(), m->m.gmaxnfael(), m->m.esuelData(), m->m.nnodeData(), p);
 	std::memcpy(perm, p.data(), sizeof(int)*p.size());
 	return 0;
+}
+
+int fvg_umesh_cell_adjacency(const fvg_umesh *m, int *ptrs, int *store)
+{
+	if(!m || !ptrs) { set_error("fvg_umesh_cell_adjacency: null argument"); return FVG_ERR_INVALID; }
+	const auto &M = m->m;
+	const int n = M.gnelem(), mw = M.gmaxnfael();
+	const int *const esuel = M.esuelData();
+	ptrs[0] = 0;
+	for(int i = 0; i < n; i++) {
+		int k = 0;
+		for(int j = 0; j < M.gnfael(i); j++) { const int e = esuel[(size_t)i*mw+j]; if(e >= 0 && e < n) k++; }
+		ptrs[i+1] = ptrs[i] + k;
+	}
+	if(store)
+		for(int i = 0; i < n; i++) {
+			int p = ptrs[i];
+			for(int j = 0; j < M.gnfael(i); j++) { const int e = esuel[(size_t)i*mw+j]; if(e >= 0 && e < n) store[p++] = e; }
+		}
+	return 0;
+}
+
+int fvg_umesh_write_scotch_graph(const fvg_umesh *m, const char *path)
+{
+	if(!m || !path) { set_error("fvg_umesh_write_scotch_graph: null argument"); return FVG_ERR_INVALID; }
+	const int n = m->m.gnelem();
+	std::vector<int> ptrs((size_t)n + 1);
+	fvg_umesh_cell_adjacency(m, ptrs.data(), nullptr);
+	std::vector<int> store((size_t)std::max(ptrs[n], 1));
+	fvg_umesh_cell_adjacency(m, ptrs.data(), store.data());
+	FILE *f = std::fopen(path, "w");
+	if(!f) { set_error(std::string("fvg_umesh_write_scotch_graph: cannot open ") + path); return FVG_ERR_IO; }
+	// Scotch source graph (.grf): version, vertex and arc counts, base value and flags (no weights, no labels),
+	// then per vertex its degree and neighbours
+	std::fprintf(f, "0\n%d %d\n0 000\n", n, ptrs[n]);
+	for(int i = 0; i < n; i++) {
+		std::fprintf(f, "%d", ptrs[i+1] - ptrs[i]);
+		for(int p = ptrs[i]; p < ptrs[i+1]; p++) std::fprintf(f, " %d", store[p]);
+		std::fprintf(f, "\n");
+	}
+	std::fclose(f);
+	return 0;
+}
+
+int fvg_partition_read_scotch_map(const fvg_umesh *m, const char *path, int *cell_rank, int *nparts)
+{
+	if(!m || !path || !cell_rank) { set_error("fvg_partition_read_scotch_map: null argument"); return FVG_ERR_INVALID; }
+	FILE *f = std::fopen(path, "r");
+	if(!f) { set_error(std::string("fvg_partition_read_scotch_map: cannot open ") + path); return FVG_ERR_IO; }
+	const int n = m->m.gnelem();
+	int cnt = 0, rc = 0, maxp = -1;
+	if(std::fscanf(f, "%d", &cnt) != 1 || cnt != n) { set_error("fvg_partition_read_scotch_map: the mapping does not have one line per cell"); rc = FVG_ERR_INVALID; }
+	std::vector<char> seen((size_t)n, 0);
+	for(int k = 0; k < n && rc == 0; k++) {
+		int v = -1, p = -1;
+		if(std::fscanf(f, "%d %d", &v, &p) != 2 || v < 0 || v >= n || p < 0 || seen[v]) { set_error("fvg_partition_read_scotch_map: bad or repeated entry"); rc = FVG_ERR_INVALID; break; }
+		seen[v] = 1; cell_rank[v] = p; maxp = std::max(maxp, p);
+	}
+	std::fclose(f);
+	if(rc == 0 && nparts) *nparts = maxp + 1;
+	return rc;
 }
 
 int fvg_umesh_hilbert_ordering(const fvg_umesh *m, int *perm)

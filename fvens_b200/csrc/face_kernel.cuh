@@ -524,13 +524,15 @@ static int launch_one(const FaceArgs &a, cudaStream_t s)
 		if(ea != cudaSuccess) return cuda_fail(ea, "face_kernel smem attribute", __FILE__, __LINE__);
 	}
 	if(a.m.HMAX > FACE_BLOCK) { set_error("face kernel: halo capacity exceeds the CTA size"); return FVG_ERR_INVALID; }
-	static int ctas = 0;                      // persistent CTAs: as many as are resident at once
-	if(ctas == 0) {
+	static int ctas = 0;                      // persistent CTAs: as many as are resident at once (depends on the mesh's
+	static size_t ctas_smem = 0;              // staging capacities through the shared-memory size)
+	if(ctas == 0 || ctas_smem != smem) {
 		int dev = 0, sms = 0, per = 0;
 		cudaGetDevice(&dev);
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, face_kernel<FLUX,RECON,VISC>, FACE_BLOCK, smem);
 		ctas = sms*(per > 0 ? per : 1);
+		ctas_smem = smem;
 	}
 	FaceArgs b = a;
 	if(b.tile1 < 0) b.tile1 = b.m.ntile;

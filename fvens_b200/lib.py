@@ -184,6 +184,24 @@ class UMesh:
         check(load().fvg_umesh_reorder_cells(self._h, _ip(perm)))
         self.__init__(self._h)
 
+    def cell_adjacency(self):
+        """CSR adjacency of the cells across interior faces (the reference's getCellAdjLists)."""
+        ptrs = np.zeros(self.nelem + 1, dtype=np.int32)
+        check(load().fvg_umesh_cell_adjacency(self._h, _ip(ptrs), None))
+        store = np.zeros(max(int(ptrs[-1]), 1), dtype=np.int32)
+        check(load().fvg_umesh_cell_adjacency(self._h, _ip(ptrs), _ip(store)))
+        return ptrs, store[:ptrs[-1]]
+
+    def write_scotch_graph(self, path):
+        check(load().fvg_umesh_write_scotch_graph(self._h, str(path).encode()))
+
+    def read_scotch_map(self, path):
+        """cell -> part from a Scotch mapping file; returns (cell_rank, nparts)."""
+        cr = np.zeros(self.nelem, dtype=np.int32)
+        npart = C.c_int(0)
+        check(load().fvg_partition_read_scotch_map(self._h, str(path).encode(), _ip(cr), C.byref(npart)))
+        return cr, npart.value
+
     def rcm_ordering(self):
         perm = np.zeros(self.nelem, dtype=np.int32)
         check(load().fvg_umesh_rcm_ordering(self._h, _ip(perm)))

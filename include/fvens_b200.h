@@ -67,6 +67,14 @@ int fvg_umesh_reorder_cells(fvg_umesh *m, const int *perm);
 /* Reverse Cuthill-McKee ordering of the cell adjacency graph, the stand-in for `-mesh_reorder rcm`
  * (mesh/ameshutils.cpp:246-288, which calls PETSc MatGetOrdering). perm[new] = old. */
 int fvg_umesh_rcm_ordering(const fvg_umesh *m, int *perm);
+/* getCellAdjLists (mesh/meshpartitioning.cpp:376-430): CSR adjacency of the cells across interior faces, the graph
+ * the reference hands to Scotch (ptrs [nelem+1]; store [ptrs[nelem]], may be NULL to get the sizes only). */
+int fvg_umesh_cell_adjacency(const fvg_umesh *m, int *ptrs, int *store);
+/* The same graph as a Scotch source-graph file (.grf), and the reader of a Scotch mapping file (.map: number of
+ * vertices, then "vertex part" lines) into a cell->rank map for fvg_mesh_create_part: where Scotch is available
+ * (`gpart N mesh.grf mesh.map`) its partition replaces fvg_partition_sfc without touching anything else. */
+int fvg_umesh_write_scotch_graph(const fvg_umesh *m, const char *path);
+int fvg_partition_read_scotch_map(const fvg_umesh *m, const char *path, int *cell_rank, int *nparts);
 /* Hilbert space-filling-curve ordering of the cell centres (the locality order the device mesh uses;
  * contiguous index ranges are compact patches, which is what both the tiles and the multi-GPU
  * partitions want). perm[new] = old. */

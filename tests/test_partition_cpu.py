@@ -107,3 +107,41 @@ def test_halo_exchange_over_gloo(world):
     results = dict(q.get(timeout=5) for _ in range(world))
     assert all(p.exitcode == 0 for p in procs)
     assert results == {r: True for r in range(world)}
+
+
+def test_scotch_graph_export_and_mapping_import(tmp_path):
+    """The cell adjacency graph the reference hands to Scotch (getCellAdjLists, mesh/meshpartitioning.cpp:376-430)
+    as a Scotch source-graph file, and a Scotch mapping file read back as the cell -> rank map of
+    fvg_mesh_create_part (the drop-in point for a real Scotch partition)."""
+    um = lib.UMesh.read(mesh_path("2dcylinderhybrid.msh"))
+    a = um.arrays()
+    ptrs, store = um.cell_adjacency()
+    n = um.nelem
+    interior = a["intfac"][um.nbface:]
+    assert ptrs[-1] == 2*len(interior)                       # every interior face is an arc in both directions
+    adj = [set(store[ptrs[i]:ptrs[i+1]].tolist()) for i in range(n)]
+    assert all(len(adj[i]) == ptrs[i+1] - ptrs[i] for i in range(n))
+    for L, R in interior[:, :2]:
+        assert R in adj[L] and L in adj[R]
+    # neighbours come in local-face order, as the reference's list does
+    for i in (0, n//2, n-1):
+        want = [e for e in a["esuel"][i, :a["nnode"][i]] if 0 <= e < n]
+        assert store[ptrs[i]:ptrs[i+1]].tolist() == want
+    g = tmp_path / "mesh.grf"
+    um.write_scotch_graph(g)
+    lines = g.read_text().split("\n")
+    assert lines[0] == "0" and lines[1].split() == [str(n), str(ptrs[-1])] and lines[2] == "0 000"
+    for i in (0, 17, n-1):
+        row = [int(x) for x in lines[3+i].split()]
+        assert row[0] == len(row) - 1 and row[1:] == store[ptrs[i]:ptrs[i+1]].tolist()
+    assert len([ln for ln in lines if ln]) == 3 + n
+    # a mapping file (here: the SFC partition written in Scotch's format, lines in shuffled order)
+    part = lib.partition_sfc(um, 3)
+    order = np.random.default_rng(0).permutation(n)
+    mp = tmp_path / "mesh.map"
+    mp.write_text(f"{n}\n" + "".join(f"{v}\t{part[v]}\n" for v in order))
+    cr, nparts = um.read_scotch_map(mp)
+    assert nparts == 3 and np.array_equal(cr, part)
+    mp.write_text(f"{n-1}\n")
+    with pytest.raises(lib.FvgError):
+        um.read_scotch_map(mp)
