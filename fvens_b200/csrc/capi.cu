@@ -457,6 +457,7 @@ void fvg_flow_destroy(fvg_flow *f)
 	if(f->h_norm) cudaFreeHost(f->h_norm);
 	for(cudaEvent_t e : f->pipe.ev_up) cudaEventDestroy(e);
 	for(cudaEvent_t e : f->pipe.ev_face) cudaEventDestroy(e);
+	if(f->pipe.ev_start) cudaEventDestroy(f->pipe.ev_start);
 	if(f->pipe.s_in) cudaStreamDestroy(f->pipe.s_in);
 	if(f->pipe.s_run) cudaStreamDestroy(f->pipe.s_run);
 	if(f->pipe.s_out) cudaStreamDestroy(f->pipe.s_out);
@@ -586,6 +587,7 @@ static void plan_host_pipe(fvg_flow *f)
 	for(int c = 0; c < K && ok; c++)
 		ok = cudaEventCreateWithFlags(&P.ev_up[c], cudaEventDisableTiming) == cudaSuccess
 		  && cudaEventCreateWithFlags(&P.ev_face[c], cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&P.ev_start, cudaEventDisableTiming) == cudaSuccess;
 	if(!ok) { cudaGetLastError(); return; }
 	P.K = K;
 }
@@ -608,6 +610,10 @@ int fvg_residual_host(fvg_flow *f, const double *h_u, double *h_res, int accumul
 		std::vector<int> pos(P.K);
 		for(int j = 0; j < P.K; j++) pos[P.order[j]] = j;
 		unsigned long long uploaded = 0, cells_done = 0, faces_done = 0;
+		// earlier calls on the default stream may still be using the flow's gradient buffers
+		FVG_CUDA(cudaEventRecord(P.ev_start, nullptr));
+		FVG_CUDA(cudaStreamWaitEvent(P.s_in, P.ev_start, 0));
+		FVG_CUDA(cudaStreamWaitEvent(P.s_run, P.ev_start, 0));
 		for(int j = 0; j < P.K; j++) {
 			const int c = P.order[j];
 			const size_t i0 = (size_t)tc0[P.tile0[c]], i1 = (size_t)tc0[P.tile0[c+1]];

@@ -163,6 +163,7 @@ struct fvg_flow {
 		std::vector<unsigned long long> deps;   ///< chunk -> chunks owning its tiles' cells and halo cells (bit mask)
 		cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
 		std::vector<cudaEvent_t> ev_up, ev_face;
+		cudaEvent_t ev_start = nullptr;         ///< orders the pipeline after earlier work on the default stream
 	} pipe;
 	std::vector<void*> allocs;
 	long long launches = 0;
