@@ -371,7 +371,9 @@ def main():
                    "tile_cells": info.tile_cells, "cut_face_duplicates_rank0": info.ncut_dup,
                    "parallelism": "single GPU" if world == 1 else
                    f"{world} GPUs, Hilbert-curve partition, one ghost layer; per evaluation: state halo, gradient pass, "
-                   f"gradient halo, face pass; halo transport: " + ("peer-mapped windows over NVLink (CUDA IPC, direct stores + flags)" if df.halo_kind == "peer" else "NCCL all-to-all with row splits"),
+                   f"gradient halo, face pass; halo transport: " + (("peer-mapped windows over NVLink (CUDA IPC, direct stores + flags)"
+                                                  + (", received inside the consuming kernels" if df.fused_recv else ", one send+receive kernel per exchange"))
+                                                 if df.halo_kind == "peer" else "NCCL all-to-all with row splits"),
                    "l2": "inputs (320 MB state + 640 MB gradients + 3 GB mesh) exceed the 126 MB L2; no explicit flush"},
         "residual_evals_per_s": 1e3/ms_step,
         "residual_roofline_frac": (bA + bB)/(ms_step*1e-3)/1e9/(peak*world),
