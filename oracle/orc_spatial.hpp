@@ -6,11 +6,16 @@
  * (separate passes P1..P11, face loops with `omp atomic`, per-call scratch allocation) because
  * this code is also the CPU baseline timed by bench.py.
  *
- * Deliberate deviations from the reference, both documented in SURVEY.md section 0:
+ * PINNED: tests/test_oracle_ref_b.py and tests/test_oracle_ref_c.py hold this restatement against the reference's
+ * own object code for the same loops (oracle/ref_tier_b.cpp, ref_tier_c.cpp: the reference's sources compiled in
+ * place) to 1e-12; tests/test_oracle_kat.py against the reference's known-answer tests.
+ *
+ * Deliberate deviations from the reference, documented in SURVEY.md section 0 and DESIGN.md section 2:
  *  H1: Barth-Jespersen / Venkatakrishnan index the cell-state array with boundary ghost ids
  *      (out of bounds in the reference). Here bnd_policy 0 uses the boundary ghost state `ug`,
  *      bnd_policy 1 skips boundary neighbours (as the reference's WENO does).
  *  H2: limiter_param is an explicit input.
+ *  The Green-Gauss boundary-face update is atomic (the reference's races under OpenMP).
  */
 #ifndef ORC_SPATIAL_HPP
 #define ORC_SPATIAL_HPP

@@ -1,5 +1,6 @@
-"""ctypes wrapper of the CPU oracle (oracle/liborc.so) and of the tier-A reference build
-(oracle/_ref/libfvens_ref_a.so). TEST INFRASTRUCTURE ONLY - never imported by fvens_b200/."""
+"""ctypes wrapper of the CPU oracle (oracle/liborc.so) and of the reference builds (oracle/_ref/libfvens_ref_a.so:
+the reference's gas-dynamics sources; libfvens_ref_b.so: its gradient and reconstruction sources).
+TEST INFRASTRUCTURE ONLY - never imported by fvens_b200/."""
 import ctypes as C
 import os
 import numpy as np
@@ -7,6 +8,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORC_PATH = os.path.join(ROOT, "oracle", "liborc.so")
 REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libfvens_ref_a.so")
+REFB_PATH = os.path.join(ROOT, "oracle", "_ref", "libfvens_ref_b.so")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 _orc = None
@@ -41,6 +43,126 @@ def ref():
     if _ref is None:
         _ref = C.CDLL(REF_PATH)
     return _ref
+
+
+_refb = None
+
+
+def have_ref_b():
+    return os.path.exists(REFB_PATH)
+
+
+def ref_b():
+    global _refb
+    if _refb is None:
+        _refb = C.CDLL(REFB_PATH)
+    return _refb
+
+
+def _ref_mesh_args(a):
+    """Mesh arrays (Mesh.arrays()) in the argument order of oracle/ref_tier_b.cpp; keeps the converted arrays alive."""
+    sizes = np.array([a["coords"].shape[0], len(a["nnode"]), len(a["btags"]), a["intfac"].shape[0], 4], dtype=np.int32)
+    keep = [sizes, np.ascontiguousarray(a["coords"]), np.ascontiguousarray(a["nnode"], dtype=np.int32),
+            np.ascontiguousarray(a["inpoel"], dtype=np.int32), np.ascontiguousarray(a["esuel"], dtype=np.int32),
+            np.ascontiguousarray(a["elemface"], dtype=np.int32), np.ascontiguousarray(a["intfac"], dtype=np.int32),
+            np.ascontiguousarray(a["facemetric"]), np.ascontiguousarray(a["area"])]
+    args = [_ip(keep[0]), _dp(keep[1]), _ip(keep[2]), _ip(keep[3]), _ip(keep[4]), _ip(keep[5]), _ip(keep[6]), _dp(keep[7]), _dp(keep[8])]
+    return args, keep
+
+
+def ref_gradients(a, gradient, rc, rcbp, u, ug):
+    """The reference's own GradientScheme classes (spatial/agradientschemes.cpp compiled in place): [nelem][8]."""
+    args, keep = _ref_mesh_args(a)
+    rc, rcbp, u, ug = (np.ascontiguousarray(x, dtype=np.float64) for x in (rc, rcbp, u, ug))
+    grad = np.zeros((len(a["nnode"]), 8))
+    ref_b().ref_gradients(int(gradient), *args, _dp(rc), _dp(rcbp), _dp(u), _dp(ug), _dp(grad))
+    return grad
+
+
+def ref_face_values(a, recon, param, rc, rcbp, gr, u, ug, grad, fill=np.nan):
+    """The reference's own SolutionReconstruction classes (areconstruction.cpp, limitedlinearreconstruction.cpp,
+    musclreconstruction.cpp compiled in place): ufl, ufr [naface][4]; entries a class does not write keep `fill`."""
+    args, keep = _ref_mesh_args(a)
+    rc, rcbp, gr, u, ug, grad = (np.ascontiguousarray(x, dtype=np.float64) for x in (rc, rcbp, gr, u, ug, grad))
+    nf = a["intfac"].shape[0]
+    ufl = np.full((nf, 4), fill); ufr = np.full((nf, 4), fill)
+    ref_b().ref_face_values(int(recon), C.c_double(param), *args, _dp(rc), _dp(rcbp), _dp(gr), _dp(u), _dp(ug), _dp(grad),
+                            _dp(ufl), _dp(ufr))
+    return ufl, ufr
+
+
+REFC_PATH = os.path.join(ROOT, "oracle", "_ref", "libfvens_ref_c.so")
+_refc = None
+
+
+def have_ref_c():
+    return os.path.exists(REFC_PATH)
+
+
+def ref_residual(a, p, flux, gradient, recon, limiter_param, order2, bcs, u, gettimesteps=True):
+    """The reference's own FlowFV::compute_residual (oracle/ref_tier_c.cpp). flux / gradient / recon: the control
+    file keys (upper case); bcs: (tag, type id, (v0, v1)). Returns (residual [nelem][4], dt [nelem])."""
+    global _refc
+    if _refc is None:
+        _refc = C.CDLL(REFC_PATH)
+    args, keep = _ref_mesh_args(a)
+    btags = np.ascontiguousarray(a["btags"], dtype=np.int32).reshape(-1)
+    ph = np.array([p.gamma, p.Minf, p.Tinf, p.Reinf, p.Pr, p.aoa], dtype=np.float64)
+    tt = np.array([[t, ty] for (t, ty, v) in bcs], dtype=np.int32).reshape(-1)
+    vv = np.array([[v[0], v[1]] for (t, ty, v) in bcs], dtype=np.float64).reshape(-1)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    n = len(a["nnode"])
+    res = np.zeros((n, 4)); dtm = np.zeros(n)
+    rc = _refc.ref_residual(*args, _ip(btags), _dp(ph), flux.encode(), gradient.encode(), recon.encode(), C.c_double(limiter_param),
+                            int(order2), int(p.viscous_sim), int(p.const_visc), len(bcs), _ip(tt), _dp(vv), _dp(u),
+                            int(gettimesteps), _dp(res), _dp(dtm))
+    if rc != 0:
+        raise RuntimeError(f"reference compute_residual returned {rc}")
+    return res, dtm
+
+
+REFC_OMP_PATH = os.path.join(ROOT, "oracle", "_ref", "libfvens_ref_c_omp.so")
+
+
+class RefFlow:
+    """The reference's own FlowFV object (oracle/ref_tier_c.cpp), kept alive for repeated evaluations: the CPU arm of
+    bench.py. omp=True loads the build with the reference's OpenMP pragmas enabled."""
+
+    def __init__(self, a, p, flux, gradient, recon, limiter_param, order2, bcs, omp=True):
+        path = REFC_OMP_PATH if omp else REFC_PATH
+        self.lib = C.CDLL(path)
+        self.lib.ref_flow_create.restype = C.c_void_p
+        args, keep = _ref_mesh_args(a)
+        btags = np.ascontiguousarray(a["btags"], dtype=np.int32).reshape(-1)
+        ph = np.array([p.gamma, p.Minf, p.Tinf, p.Reinf, p.Pr, p.aoa], dtype=np.float64)
+        tt = np.array([[t, ty] for (t, ty, v) in bcs], dtype=np.int32).reshape(-1)
+        vv = np.array([[v[0], v[1]] for (t, ty, v) in bcs], dtype=np.float64).reshape(-1)
+        self.n = len(a["nnode"])
+        self.h = C.c_void_p(self.lib.ref_flow_create(*args, _ip(btags), _dp(ph), flux.encode(), gradient.encode(), recon.encode(),
+                                                     C.c_double(limiter_param), int(order2), int(p.viscous_sim), int(p.const_visc),
+                                                     len(bcs), _ip(tt), _dp(vv)))
+
+    def threads(self):
+        return int(self.lib.ref_num_threads())
+
+    def residual(self, u, gettimesteps=True, want=True):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        res = np.zeros((self.n, 4)) if want else None
+        dtm = np.zeros(self.n) if want else None
+        rc = self.lib.ref_flow_residual(self.h, _dp(u), int(gettimesteps), _dp(res) if want else None, _dp(dtm) if want else None)
+        if rc != 0:
+            raise RuntimeError(f"reference compute_residual returned {rc}")
+        return res, dtm
+
+    def __del__(self):
+        try:
+            self.lib.ref_flow_destroy(self.h)
+        except Exception:
+            pass
+
+
+def have_ref_c_omp():
+    return os.path.exists(REFC_OMP_PATH)
 
 
 def set_threads(n):
