@@ -41,5 +41,10 @@ static inline PetscErrorCode VecGhostUpdateEnd(Vec, InsertMode, ScatterMode) { r
 static inline PetscErrorCode VecDestroy(Vec *v) { delete *v; *v = NULL; return 0; }
 static inline PetscErrorCode VecDuplicate(Vec v, Vec *w) { *w = new _p_Vec(*v); return 0; }
 static inline PetscErrorCode VecSet(Vec v, PetscScalar s) { for(auto& x : v->a) x = s; return 0; }
+typedef struct _p_PetscViewer* PetscViewer;
+typedef enum { FILE_MODE_READ = 0, FILE_MODE_WRITE = 1 } PetscFileMode;
+static inline PetscErrorCode PetscViewerBinaryOpen(MPI_Comm, const char*, PetscFileMode, PetscViewer *v) { *v = NULL; return PETSC_ERR_SUP; }
+static inline PetscErrorCode PetscViewerDestroy(PetscViewer *v) { *v = NULL; return 0; }
+static inline PetscErrorCode VecView(Vec, PetscViewer) { return PETSC_ERR_SUP; }
 static inline PetscErrorCode PetscObjectGetComm(PetscObject, MPI_Comm *c) { *c = MPI_COMM_WORLD; return 0; }
 #endif

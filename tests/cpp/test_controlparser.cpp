@@ -1,6 +1,6 @@
 /* CPU-only: parses a control file with the host front end (fvens_b200/host/controlparser.hpp) and prints the
  * FlowParserOptions as JSON for tests/test_controlfile.py. usage: test_controlparser <ctrl> [key value]... */
-#include "../../fvens_b200/host/controlparser.hpp"
+#include "../../fvens_b200/host/casesolvers.hpp"
 #include <cstdio>
 using namespace fvens;
 
@@ -9,6 +9,16 @@ static std::string q(const std::string& s) { return "\"" + s + "\""; }
 int main(int argc, char *argv[])
 {
 	if(argc < 2) return 2;
+	if(std::string(argv[1]) == "--history") {
+		// the residual-history writer of casesolvers.hpp on monitors given as: step rel abs wtime cfl ...
+		writeConvergenceHistoryHeader(std::cout);
+		for(int i = 2; i + 4 < argc; i += 5) {
+			SteadyStepMonitor s; s.step = std::atoi(argv[i]); s.rmsres = (float)std::atof(argv[i+1]); s.absrmsres = (float)std::atof(argv[i+2]);
+			s.odewalltime = (float)std::atof(argv[i+3]); s.linwalltime = 0; s.linits = 0; s.cfl = (float)std::atof(argv[i+4]);
+			writeStepToConvergenceHistory(s, std::cout);
+		}
+		return 0;
+	}
 	std::map<std::string,std::string> cmd;
 	for(int i = 2; i + 1 < argc; i += 2) cmd[argv[i]] = argv[i+1];
 	try {

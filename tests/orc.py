@@ -128,8 +128,8 @@ class RefFlow:
     """The reference's own FlowFV object (oracle/ref_tier_c.cpp), kept alive for repeated evaluations: the CPU arm of
     bench.py. omp=True loads the build with the reference's OpenMP pragmas enabled."""
 
-    def __init__(self, a, p, flux, gradient, recon, limiter_param, order2, bcs, omp=True):
-        path = REFC_OMP_PATH if omp else REFC_PATH
+    def __init__(self, a, p, flux, gradient, recon, limiter_param, order2, bcs, omp=True, path=None):
+        path = path or (REFC_OMP_PATH if omp else REFC_PATH)
         self.lib = C.CDLL(path)
         self.lib.ref_flow_create.restype = C.c_void_p
         args, keep = _ref_mesh_args(a)
@@ -159,6 +159,40 @@ class RefFlow:
             self.lib.ref_flow_destroy(self.h)
         except Exception:
             pass
+
+
+REFD_PATH = os.path.join(ROOT, "oracle", "_ref", "libfvens_ref_d.so")
+
+
+def have_ref_d():
+    return os.path.exists(REFD_PATH)
+
+
+class RefSolver(RefFlow):
+    """Tier D: the reference's own SteadyForwardEulerSolver::solve on the reference's own FlowFV (oracle/ref_tier_d.cpp)."""
+
+    def __init__(self, a, p, flux, gradient, recon, limiter_param, order2, bcs):
+        # the handle functions are the same symbols in the tier-D library
+        RefFlow.__init__(self, a, p, flux, gradient, recon, limiter_param, order2, bcs, omp=False, path=REFD_PATH)
+
+    def forward_euler(self, u, cfl, tol, maxiter):
+        """Returns (code, steps, relative history, absolute history, final state); code 0 converged, 1 max iterations."""
+        u = np.array(u, dtype=np.float64, copy=True)
+        steps = C.c_int(0)
+        hrel = np.zeros(max(maxiter, 1)); habs = np.zeros(max(maxiter, 1))
+        code = self.lib.ref_flow_forward_euler(self.h, C.c_double(cfl), C.c_double(tol), int(maxiter), _dp(u), C.byref(steps),
+                                               _dp(hrel), _dp(habs))
+        return code, steps.value, hrel[:steps.value], habs[:steps.value], u
+
+    def history_text(self, steps, rel, abs_, wtime, cfl):
+        f32 = lambda x: np.ascontiguousarray(x, dtype=np.float32)
+        st = np.ascontiguousarray(steps, dtype=np.int32)
+        rel, abs_, wtime, cfl = f32(rel), f32(abs_), f32(wtime), f32(cfl)
+        buf = C.create_string_buffer(200*(len(st) + 3))
+        fp = lambda x: x.ctypes.data_as(C.POINTER(C.c_float))
+        n = self.lib.ref_convergence_history_text(len(st), _ip(st), fp(rel), fp(abs_), fp(wtime), fp(cfl), buf, len(buf))
+        assert n >= 0
+        return buf.value.decode()
 
 
 def have_ref_c_omp():

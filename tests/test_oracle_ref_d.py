@@ -1,0 +1,66 @@
+"""Tier D: the explicit pseudo-time driver. The oracle's restatement of SteadyForwardEulerSolver::solve
+(oracle/orc_spatial.hpp, the checker of the GPU solver tests) against the REFERENCE'S OWN solver object code
+(ode/aodesolver.cpp compiled unmodified on top of its own FlowFV, oracle/ref_tier_d.cpp), and the residual-history
+writer of fvens_b200/host/casesolvers.hpp against the reference's writer (spatial/aoutput.cpp:617-636) character by
+character."""
+import os
+import subprocess
+import numpy as np
+import pytest
+
+import orc
+from common import ROOT, mesh_path, rel_err_by_component, INVISCID_BCS, VISCOUS_BCS
+from fvens_b200 import lib, synth
+
+pytestmark = pytest.mark.skipif(not orc.have_ref_d(), reason="oracle/_ref/libfvens_ref_d.so not built (needs /root/reference)")
+
+
+def setup(mesh, flux, gradient, recon, order2=True, viscous=False, lp=1.0):
+    om = orc.Mesh.read(mesh_path(mesh))
+    a = om.arrays()
+    phys = lib.make_physics(1.4, 0.5, 288.15, 100.0, 0.72, 0.02, viscous, False)
+    tags = set(a["btags"].tolist())
+    bcs = [(t, lib.BC[ty], v) for (t, ty, v) in (VISCOUS_BCS if viscous else INVISCID_BCS) if t in tags]
+    of = orc.Flow(om, phys, lib.FLUX[flux], lib.GRAD[gradient], lib.RECON[recon], lp, order2, 0, bcs)
+    rs = orc.RefSolver(a, phys, flux, gradient if order2 else "NONE", recon if order2 else "NONE", lp, order2, bcs)
+    rc, _, _ = of.geometry()
+    u = synth.perturbed_state(rc, 1.4, 0.5, 0.02, amp=0.05)
+    return of, rs, u
+
+
+@pytest.mark.parametrize("cfg", [("2dcylinderhybrid.msh", "ROE", "LEASTSQUARES", "VANALBADA", True, False),
+                                 ("naca0012luo.msh", "HLLC", "GREENGAUSS", "NONE", True, False),
+                                 ("2dcylinderhybrid.msh", "HLL", "NONE", "NONE", False, False),
+                                 ("2dcylinderhybrid.msh", "ROE", "LEASTSQUARES", "NONE", True, True)])
+def test_forward_euler_loop_against_reference_solver(cfg):
+    mesh, flux, gradient, recon, order2, viscous = cfg
+    of, rs, u = setup(mesh, flux, gradient, recon, order2, viscous)
+    nsteps = 60
+    code0, steps0, hist0, u0 = of.forward_euler(u, 0.4, 1e-30, nsteps)
+    code1, steps1, rel1, abs1, u1 = rs.forward_euler(u, 0.4, 1e-30, nsteps)
+    assert (code0, steps0) == (1, nsteps) and (code1, steps1) == (1, nsteps)         # both: Tolerance_error at max iterations
+    # the state in double precision; round-off grows through 60 non-linear steps
+    assert rel_err_by_component(u0, u1) < 1e-10
+    # the reference keeps its history in single precision
+    assert np.abs(hist0/abs1 - 1).max() < 3e-7 and np.abs(hist0/hist0[0]/rel1 - 1).max() < 3e-7
+
+
+def test_converged_exit_and_tolerance():
+    of, rs, u = setup("2dcylinderhybrid.msh", "ROE", "NONE", "NONE", False)
+    code0, steps0, hist0, u0 = of.forward_euler(u, 0.5, 0.5, 2000)        # stop once the residual has halved
+    code1, steps1, rel1, abs1, u1 = rs.forward_euler(u, 0.5, 0.5, 2000)
+    assert code0 == 0 and code1 == 0 and steps0 == steps1 and 1 < steps0 < 2000
+    assert rel_err_by_component(u0, u1) < 1e-10 and rel1[-1] <= 0.5 < rel1[-2]
+
+
+def test_residual_history_writer_matches_the_reference_writer():
+    of, rs, u = setup("2dcylinderhybrid.msh", "ROE", "NONE", "NONE", False)
+    steps = [1, 2, 50, 51, 1234, 200000]
+    rel = [1.0, 0.731234, 3.4e-3, 1.0e-5, 9.87654321e-9, 1.2e-12]
+    abs_ = [0.0123, 0.0091, 4.2e-5, 1.2e-7, 1.1e-10, 1.5e-14]
+    wt = [0.001, 0.0025, 1.25, 1.3, 321.5, 98765.4]
+    cfl = [0.25, 0.25, 0.5, 0.5, 1.0, 1000.0]
+    want = rs.history_text(steps, rel, abs_, wt, cfl)
+    args = [str(x) for row in zip(steps, rel, abs_, wt, cfl) for x in row]
+    got = subprocess.run([os.path.join(ROOT, "tests", "cpp", "test_controlparser"), "--history", *args], capture_output=True, text=True).stdout
+    assert got == want and want.count("\n") == 2 + len(steps)
