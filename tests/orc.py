@@ -195,6 +195,105 @@ class RefSolver(RefFlow):
         return buf.value.decode()
 
 
+REFE_PATH = os.path.join(ROOT, "oracle", "_ref", "libfvens_ref_e.so")
+_refe = None
+
+
+def have_ref_e():
+    return os.path.exists(REFE_PATH)
+
+
+class RefCase:
+    """Tier E: the reference's own UMesh (readers, topology, metrics), FlowFV, explicit solver and output unit, all
+    compiled from its unmodified sources (oracle/ref_tier_e.cpp). No stand-in for the mesh."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise RuntimeError("reference mesh construction failed")
+        self.h = C.c_void_p(handle)
+        s = np.zeros(5, dtype=np.int32)
+        self.lib.ref_e_mesh_sizes(self.h, _ip(s))
+        self.npoin, self.nelem, self.nbface, self.naface, self.maxnnode = (int(x) for x in s)
+
+    @staticmethod
+    def _lib():
+        global _refe
+        if _refe is None:
+            _refe = C.CDLL(REFE_PATH)
+            _refe.ref_e_mesh_read.restype = C.c_void_p
+            _refe.ref_e_mesh_from_arrays.restype = C.c_void_p
+        return _refe
+
+    lib = property(lambda self: RefCase._lib())
+
+    @classmethod
+    def read(cls, path):
+        return cls(cls._lib().ref_e_mesh_read(str(path).encode()))
+
+    @classmethod
+    def from_arrays(cls, coords, nnode, inpoel, bface):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        nnode = np.ascontiguousarray(nnode, dtype=np.int32)
+        inpoel = np.ascontiguousarray(inpoel, dtype=np.int32)
+        bface = np.ascontiguousarray(bface, dtype=np.int32)
+        return cls(cls._lib().ref_e_mesh_from_arrays(len(coords), _dp(coords), len(nnode), inpoel.shape[1], _ip(nnode), _ip(inpoel),
+                                                     len(bface), _ip(bface)))
+
+    def arrays(self):
+        d = dict(coords=np.zeros((self.npoin, 2)), inpoel=np.zeros((self.nelem, 4), dtype=np.int32),
+                 nnode=np.zeros(self.nelem, dtype=np.int32), bface=np.zeros((self.nbface, 3), dtype=np.int32),
+                 esuel=np.zeros((self.nelem, 4), dtype=np.int32), elemface=np.zeros((self.nelem, 4), dtype=np.int32),
+                 intfac=np.zeros((self.naface, 4), dtype=np.int32), btags=np.zeros(self.nbface, dtype=np.int32),
+                 facemetric=np.zeros((self.naface, 3)), area=np.zeros(self.nelem))
+        self.lib.ref_e_mesh_get(self.h, _dp(d["coords"]), _ip(d["inpoel"]), _ip(d["nnode"]), _ip(d["bface"]), _ip(d["esuel"]),
+                                _ip(d["elemface"]), _ip(d["intfac"]), _ip(d["btags"]), _dp(d["facemetric"]), _dp(d["area"]))
+        return d
+
+    def flow(self, p, flux, gradient, recon, limiter_param, order2, bcs):
+        ph = np.array([p.gamma, p.Minf, p.Tinf, p.Reinf, p.Pr, p.aoa], dtype=np.float64)
+        tt = np.array([[t, ty] for (t, ty, v) in bcs], dtype=np.int32).reshape(-1)
+        vv = np.array([[v[0], v[1]] for (t, ty, v) in bcs], dtype=np.float64).reshape(-1)
+        rc = self.lib.ref_e_flow_create(self.h, _dp(ph), flux.encode(), gradient.encode(), recon.encode(), C.c_double(limiter_param),
+                                        int(order2), int(p.viscous_sim), int(p.const_visc), len(bcs), _ip(tt), _dp(vv))
+        if rc != 0:
+            raise RuntimeError("reference FlowFV construction failed")
+        self.phys = p
+        return self
+
+    def residual(self, u, gettimesteps=True):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        res = np.zeros((self.nelem, 4)); dtm = np.zeros(self.nelem)
+        rc = self.lib.ref_e_flow_residual(self.h, _dp(u), int(gettimesteps), _dp(res), _dp(dtm))
+        if rc != 0:
+            raise RuntimeError(f"reference compute_residual returned {rc}")
+        return res, dtm
+
+    def forward_euler(self, u, cfl, tol, maxiter):
+        u = np.array(u, dtype=np.float64, copy=True)
+        steps = C.c_int(0)
+        hrel = np.zeros(max(maxiter, 1)); habs = np.zeros(max(maxiter, 1))
+        code = self.lib.ref_e_flow_forward_euler(self.h, C.c_double(cfl), C.c_double(tol), int(maxiter), _dp(u), C.byref(steps),
+                                                 _dp(hrel), _dp(habs))
+        return code, steps.value, hrel[:steps.value], habs[:steps.value], u
+
+    def surface_and_entropy(self, u, marker):
+        """(Cl, Cdp, Cdf, entropy norm) from the reference's computeSurfaceData / getGradients / FlowOutput."""
+        p = self.phys
+        ph = np.array([p.gamma, p.Minf, p.Tinf, p.Reinf, p.Pr], dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        out = np.zeros(4)
+        rc = self.lib.ref_e_surface_and_entropy(self.h, _dp(u), int(marker), C.c_double(p.aoa), _dp(ph), _dp(out))
+        if rc != 0:
+            raise RuntimeError("reference surface data failed")
+        return tuple(out)
+
+    def __del__(self):
+        try:
+            self.lib.ref_e_destroy(self.h)
+        except Exception:
+            pass
+
+
 def have_ref_c_omp():
     return os.path.exists(REFC_OMP_PATH)
 

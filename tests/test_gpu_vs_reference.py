@@ -1,6 +1,7 @@
-"""The CUDA path held DIRECTLY against the reference's own object code: FlowFV::compute_residual of the reference,
-compiled from its unmodified sources (oracle/ref_tier_c.cpp -> oracle/_ref/libfvens_ref_c.so, built where
-/root/reference exists and shipped with the tree), on the same mesh and state as fvg_residual - no oracle in between.
+"""The CUDA path held DIRECTLY against the reference's own object code: the reference's mesh reader and UMesh, its
+FlowFV::compute_residual and everything under it, compiled from its unmodified sources (oracle/ref_tier_e.cpp ->
+oracle/_ref/libfvens_ref_e.so, built where /root/reference exists and shipped with the tree), given the same mesh FILE
+and state as fvg_residual - no oracle and no stand-in for the mesh in between.
 Tolerance 1e-12 relative per component (BASELINE.json north_star). Barth-Jespersen / Venkatakrishnan: cells at a
 physical boundary and their neighbours are excluded, the reference reads undefined memory there."""
 import numpy as np
@@ -12,7 +13,7 @@ from common import mesh_path, rel_err_by_component, INVISCID_BCS, VISCOUS_BCS
 from fvens_b200 import lib, synth
 from test_oracle_ref_c import cells_untouched_by_h1
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not orc.have_ref_c(), reason="oracle/_ref/libfvens_ref_c.so not shipped")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not orc.have_ref_e(), reason="oracle/_ref/libfvens_ref_e.so not shipped")]
 TOL = 1e-12
 
 
@@ -36,8 +37,9 @@ def test_cuda_residual_against_reference_object_code(cfg):
     named = [b for b in (VISCOUS_BCS if viscous else INVISCID_BCS) if b[0] in tags]
     rc = synth.cell_centres(a["coords"], a["nnode"], np.where(np.arange(4)[None, :] < a["nnode"][:, None], a["inpoel"], -1))
     u = synth.perturbed_state(rc, 1.4, 0.6, 0.03, amp=0.08, shock=cfg.get("shock", False))
-    r1, dt1 = orc.ref_residual(a, phys, flux, gradient if order2 else "NONE", recon if order2 else "NONE", lp, order2,
-                               [(t, lib.BC[ty], v) for (t, ty, v) in named], u)
+    rf = orc.RefCase.read(mesh_path(mesh)).flow(phys, flux, gradient if order2 else "NONE", recon if order2 else "NONE", lp, order2,
+                                                [(t, lib.BC[ty], v) for (t, ty, v) in named])
+    r1, dt1 = rf.residual(u)
     dm = lib.DeviceMesh(um, reorder="hilbert", tile_cells=128)
     fl = lib.FlowFV(dm, phys, flux, gradient, recon, lp, order2, 0, named)
     du = torch.from_numpy(u).cuda()

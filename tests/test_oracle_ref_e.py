@@ -1,0 +1,75 @@
+"""Tier E: the whole chain in the reference's own object code - its mesh readers and UMesh (topology, orientation,
+areas, face metrics), its FlowFV::compute_residual, its explicit solver, its surface functionals and entropy norm,
+compiled from its unmodified sources without any stand-in for the mesh (oracle/ref_tier_e.cpp). Held against the
+oracle (oracle/orc_mesh.hpp, orc_spatial.hpp), the checker of every GPU parity test:
+  mesh arrays: integers bit for bit, metrics to round-off, for every fixture mesh (Gmsh 2 and SU2) and a synthetic one;
+  residual + time steps from the mesh FILE: 1e-12; 40 forward-Euler steps: 1e-10; Cl / Cd / entropy norm: 1e-10."""
+import numpy as np
+import pytest
+
+import orc
+from common import mesh_path, rel_err_by_component, INVISCID_BCS, VISCOUS_BCS
+from fvens_b200 import lib, synth
+
+pytestmark = pytest.mark.skipif(not orc.have_ref_e(), reason="oracle/_ref/libfvens_ref_e.so not built (needs /root/reference)")
+MESHES = ["2dcylinder0.msh", "2dcylinder1.msh", "2dcylinder2.msh", "2dcylinderhybrid.msh", "naca0012luo.msh", "NACA0012_inv.su2",
+          "NACA0012_lam_hybrid_1.msh", "squarecoarse.msh", "squareunsquad0.msh", "testhybrid.msh", "testperiodic.msh"]
+
+
+def same_mesh(a, b):
+    for k in ("inpoel", "nnode", "bface", "esuel", "elemface", "intfac", "btags"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["coords"], b["coords"])
+    assert np.abs(a["area"]/b["area"] - 1).max() < 1e-14
+    assert np.abs(a["facemetric"] - b["facemetric"]).max() < 1e-14*np.abs(b["facemetric"]).max()
+
+
+@pytest.mark.parametrize("mesh", MESHES)
+def test_mesh_topology_and_metrics_against_the_reference_mesh_class(mesh):
+    om = orc.Mesh.read(mesh_path(mesh))
+    rm = orc.RefCase.read(mesh_path(mesh))
+    assert (om.npoin, om.nelem, om.nbface, om.naface) == (rm.npoin, rm.nelem, rm.nbface, rm.naface)
+    same_mesh(om.arrays(), rm.arrays())
+
+
+def test_mesh_from_arrays():
+    arrs = synth.bump_channel(30, 12)
+    same_mesh(orc.Mesh.from_arrays(*arrs).arrays(), orc.RefCase.from_arrays(*arrs).arrays())
+    arrs = synth.ogrid_cylinder(24, 10, tri_fraction=0.3)
+    same_mesh(orc.Mesh.from_arrays(*arrs).arrays(), orc.RefCase.from_arrays(*arrs).arrays())
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(mesh="NACA0012_inv.su2", flux="ROE", gradient="LEASTSQUARES", recon="VANALBADA"),
+    dict(mesh="naca0012luo.msh", flux="HLLC", gradient="GREENGAUSS", recon="WENO", lp=20.0),
+    dict(mesh="2dcylinderhybrid.msh", flux="AUSMPLUS", order2=False),
+    dict(mesh="NACA0012_lam_hybrid_1.msh", flux="ROE", gradient="LEASTSQUARES", recon="NONE", viscous=True),
+])
+def test_whole_chain_from_the_mesh_file(cfg):
+    mesh = cfg["mesh"]; flux = cfg["flux"]; gradient = cfg.get("gradient", "NONE"); recon = cfg.get("recon", "NONE")
+    lp = cfg.get("lp", 1.0); order2 = cfg.get("order2", True); viscous = cfg.get("viscous", False)
+    om = orc.Mesh.read(mesh_path(mesh))
+    a = om.arrays()
+    phys = lib.make_physics(1.4, 0.5, 288.15, 200.0, 0.72, 0.03, viscous, False)
+    tags = set(a["btags"].tolist())
+    bcs = [(t, lib.BC[ty], v) for (t, ty, v) in (VISCOUS_BCS if viscous else INVISCID_BCS) if t in tags]
+    of = orc.Flow(om, phys, lib.FLUX[flux], lib.GRAD[gradient], lib.RECON[recon], lp, order2, 0, bcs)
+    rf = orc.RefCase.read(mesh_path(mesh)).flow(phys, flux, gradient, recon, lp, order2, bcs)
+    rc, _, _ = of.geometry()
+    u = synth.perturbed_state(rc, 1.4, 0.5, 0.03, amp=0.06)
+    r0, dt0, _, _ = of.residual(u)
+    r1, dt1 = rf.residual(u)
+    assert rel_err_by_component(r0, r1) < 1e-12 and np.abs(dt0/dt1 - 1).max() < 1e-12
+    # forward Euler from this state
+    code0, steps0, hist0, u0 = of.forward_euler(u, 0.3, 1e-30, 40)
+    code1, steps1, rel1, abs1, u1 = rf.forward_euler(u, 0.3, 1e-30, 40)
+    assert (code0, steps0, code1, steps1) == (1, 40, 1, 40) and rel_err_by_component(u0, u1) < 1e-10
+    assert np.abs(hist0/abs1 - 1).max() < 3e-7
+    # functionals on the wall marker of the advanced state
+    wall = 2
+    cl1, cdp1, cdf1, ent1 = rf.surface_and_entropy(u1, wall)
+    cl0, cdp0, cdf0 = of.surface_data(u0, of.get_gradients(u0), wall)
+    ent0 = of.entropy_error(u0)
+    scale = max(abs(cl1), abs(cdp1), 1e-3)
+    assert abs(cl0 - cl1) < 1e-9*scale and abs(cdp0 - cdp1) < 1e-9*scale and abs(cdf0 - cdf1) < 1e-9*max(abs(cdf1), 1e-3)
+    assert abs(ent0/ent1 - 1) < 1e-9
