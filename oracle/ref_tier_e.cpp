@@ -112,6 +112,19 @@ void* ref_e_mesh_from_arrays(int npoin, const double *coords, int nelem, int max
 	return h;
 }
 
+/// UMesh::reorder_cells (new cell i = old cell perm[i], mesh/mesh.cpp:85-99) followed by the preprocessing again
+void ref_e_mesh_reorder(void *hv, const int *perm)
+{
+	RefCase *h = static_cast<RefCase*>(hv);
+	std::stringstream sink;
+	std::streambuf *const old = std::cout.rdbuf(sink.rdbuf());
+	h->m->reorder_cells(perm);
+	h->m->compute_topological();
+	h->m->compute_areas();
+	h->m->compute_face_data();
+	std::cout.rdbuf(old);
+}
+
 void ref_e_destroy(void *hv) { delete static_cast<RefCase*>(hv); }
 
 /// sizes = {npoin, nelem, nbface, naface, maxnnode}

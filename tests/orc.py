@@ -249,6 +249,11 @@ class RefCase:
                                 _ip(d["elemface"]), _ip(d["intfac"]), _ip(d["btags"]), _dp(d["facemetric"]), _dp(d["area"]))
         return d
 
+    def reorder_cells(self, perm):
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
+        assert len(perm) == self.nelem
+        self.lib.ref_e_mesh_reorder(self.h, _ip(perm))
+
     def flow(self, p, flux, gradient, recon, limiter_param, order2, bcs):
         ph = np.array([p.gamma, p.Minf, p.Tinf, p.Reinf, p.Pr, p.aoa], dtype=np.float64)
         tt = np.array([[t, ty] for (t, ty, v) in bcs], dtype=np.int32).reshape(-1)

@@ -73,3 +73,25 @@ def test_whole_chain_from_the_mesh_file(cfg):
     scale = max(abs(cl1), abs(cdp1), 1e-3)
     assert abs(cl0 - cl1) < 1e-9*scale and abs(cdp0 - cdp1) < 1e-9*scale and abs(cdf0 - cdf1) < 1e-9*max(abs(cdf1), 1e-3)
     assert abs(ent0/ent1 - 1) < 1e-9
+
+
+@pytest.mark.parametrize("mesh", ["2dcylinderhybrid.msh", "NACA0012_inv.su2", "testhybrid.msh"])
+def test_product_host_mesh_against_the_reference_mesh_class(mesh):
+    """The PRODUCT's host mesh (fvens_b200/host/mesh.hpp + csrc/umesh.cpp, what the device mesh is built from) against
+    the reference's UMesh object code directly, also after UMesh::reorder_cells with the same permutation."""
+    um = lib.UMesh.read(mesh_path(mesh))
+    rm = orc.RefCase.read(mesh_path(mesh))
+
+    def same(a, b):
+        mw = a["inpoel"].shape[1]
+        for k in ("inpoel", "esuel", "elemface"):
+            assert np.array_equal(a[k], b[k][:, :mw]), k
+        assert np.array_equal(a["nnode"], b["nnode"]) and np.array_equal(a["intfac"], b["intfac"])
+        assert np.array_equal(a["btags"][:, 0], b["btags"]) and np.array_equal(a["coords"], b["coords"])
+        assert np.abs(a["area"]/b["area"] - 1).max() < 1e-14
+        assert np.abs(a["facemetric"] - b["facemetric"]).max() < 1e-14*np.abs(b["facemetric"]).max()
+    same(um.arrays(), rm.arrays())
+    perm = np.random.default_rng(11).permutation(um.nelem).astype(np.int32)
+    um.reorder_cells(perm)
+    rm.reorder_cells(perm)
+    same(um.arrays(), rm.arrays())
