@@ -9,6 +9,7 @@
  */
 #include "engine.hpp"
 #include <algorithm>
+#include <array>
 #include <numeric>
 #include <cmath>
 #include <cstring>
@@ -643,6 +644,23 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	else { UP(d2g, new2old) D.old2new = nullptr; }
 #undef UP
 	m->h_tcell0 = tcell0; m->h_thoff = thoff; m->h_thalo = thalo;
+	// per-tile send lists: the rows a tile's cells contribute to the neighbours' ghost blocks, as (tile-local cell,
+	// peer rank, row inside this rank's block of the peer's ghost range). A producing kernel can push these rows to the
+	// peers as soon as the tile is done (the per-rank list send_idx is the same set, grouped by peer).
+	m->h_tsoff.assign((size_t)ntile + 1, 0);
+	m->h_tsend.clear();
+	if(nranks > 1) {
+		std::vector<std::array<int,4>> items;     // tile, local cell, peer, row
+		int k = 0;
+		for(int r = 0; r < nranks; r++)
+			for(int q = 0; q < m->send_counts[r]; q++, k++) {
+				const int c = m->h_send_idx[k];
+				items.push_back({tile_of[c], c - tcell0[tile_of[c]], r, q});
+			}
+		std::sort(items.begin(), items.end());
+		for(const auto &it : items) { m->h_tsoff[it[0]+1]++; m->h_tsend.push_back(it[1]); m->h_tsend.push_back(it[2]); m->h_tsend.push_back(it[3]); }
+		for(int t = 0; t < ntile; t++) m->h_tsoff[t+1] += m->h_tsoff[t];
+	}
 	m->h_rc.resize(2*(size_t)nown);
 	for(int i = 0; i < nown; i++) { m->h_rc[2*(size_t)i] = drc[i].x; m->h_rc[2*(size_t)i+1] = drc[i].y; }
 	return 0;
@@ -723,6 +741,14 @@ int fvg_mesh_halo_lists(const fvg_mesh *m, int *send_counts, int *recv_counts, i
 	if(send_counts) std::memcpy(send_counts, m->send_counts.data(), sizeof(int)*m->send_counts.size());
 	if(recv_counts) std::memcpy(recv_counts, m->recv_counts.data(), sizeof(int)*m->recv_counts.size());
 	if(send_idx && !m->h_send_idx.empty()) std::memcpy(send_idx, m->h_send_idx.data(), sizeof(int)*m->h_send_idx.size());
+	return 0;
+}
+
+int fvg_mesh_tile_send_lists(const fvg_mesh *m, int *tile_off, int *cell_peer_row)
+{
+	if(!m || !tile_off) { set_error("fvg_mesh_tile_send_lists: null argument"); return FVG_ERR_INVALID; }
+	std::memcpy(tile_off, m->h_tsoff.data(), sizeof(int)*m->h_tsoff.size());
+	if(cell_peer_row && !m->h_tsend.empty()) std::memcpy(cell_peer_row, m->h_tsend.data(), sizeof(int)*m->h_tsend.size());
 	return 0;
 }
 

@@ -122,6 +122,7 @@ struct fvg_mesh {
 	std::vector<int> h_bentry;
 	std::vector<int> h_markers;                ///< sorted distinct boundary markers = slots of the BC table
 	std::vector<int> h_tcell0, h_thoff, h_thalo;
+	std::vector<int> h_tsoff, h_tsend;         ///< per-tile send lists: offsets [ntile+1]; triples (tile-local cell, peer, row in my block)
 	std::vector<double> h_rc;                  ///< cell centres, device order (own cells)
 	int nghost = 0, rank = 0, nranks = 1;
 	std::vector<int> send_counts, recv_counts, h_send_idx;

@@ -260,6 +260,14 @@ class DeviceMesh:
     def halo_pack(self, src, width, sendbuf, stream=None):
         check(load().fvg_halo_pack(self._h, _ptr(src), int(width), _ptr(sendbuf), C.c_void_p(stream or 0)))
 
+    def tile_send_lists(self):
+        """(tile_off [ntile+1], triples [n][3] = tile-local cell, peer, row in my block of the peer's ghost range)."""
+        off = np.zeros(self.info.ntile + 1, dtype=np.int32)
+        check(load().fvg_mesh_tile_send_lists(self._h, _ip(off), None))
+        tr = np.zeros((max(int(off[-1]), 1), 3), dtype=np.int32)
+        check(load().fvg_mesh_tile_send_lists(self._h, _ip(off), _ip(tr)))
+        return off, tr[:off[-1]]
+
     def tile_offsets(self):
         t = np.zeros(self.info.ntile+1, dtype=np.int32)
         check(load().fvg_mesh_tile_offsets(self._h, _ip(t)))

@@ -140,6 +140,10 @@ void fvg_mesh_destroy(fvg_mesh *m);
 int fvg_mesh_halo_lists(const fvg_mesh *m, int *send_counts, int *recv_counts, int *send_idx);
 /* Packs rows of a device-ordered array for the peers: sendbuf[k][:] = src[send_idx[k]][:] (width doubles). */
 int fvg_halo_pack(const fvg_mesh *m, const double *d_src, int width, double *d_sendbuf, void *stream);
+/* The same send pattern per tile: tile_off [ntile+1]; cell_peer_row (may be NULL) holds, for the entries of tile t,
+ * triples {tile-local cell, peer rank, row inside this rank's block of the peer's ghost range}, i.e. where a kernel
+ * that has just produced the row of that cell would store it in the peer's ghost block. */
+int fvg_mesh_tile_send_lists(const fvg_mesh *m, int *tile_off, int *cell_peer_row);
 int fvg_mesh_get_info(const fvg_mesh *m, fvg_mesh_info *info);
 
 /* Peer-memory halo exchange (one process per GPU, all GPUs in one NVLink/NVSwitch box). Each rank owns a window

@@ -145,3 +145,29 @@ def test_scotch_graph_export_and_mapping_import(tmp_path):
     mp.write_text(f"{n-1}\n")
     with pytest.raises(lib.FvgError):
         um.read_scotch_map(mp)
+
+
+@pytest.mark.parametrize("nranks", [2, 5])
+def test_tile_send_lists_are_the_halo_send_lists_grouped_by_tile(nranks):
+    """fvg_mesh_tile_send_lists: the rows a tile's cells contribute to the neighbours' ghost blocks (for kernels that push
+    their output to the peers as they produce it) are exactly the per-rank send lists, regrouped by tile."""
+    um = lib.UMesh.from_arrays(*synth.bump_channel(60, 24))
+    part, meshes = build_parts(um, nranks, tile=64)
+    for r, dm in enumerate(meshes):
+        sc, rc, idx = dm.halo_lists()
+        off, tr = dm.tile_send_lists()
+        t0 = dm.tile_offsets()
+        assert off[0] == 0 and off[-1] == len(idx) == len(tr) and (np.diff(off) >= 0).all()
+        tile = np.repeat(np.arange(dm.info.ntile), np.diff(off))
+        cell = t0[tile] + tr[:, 0]
+        assert (tr[:, 0] >= 0).all() and (cell < t0[tile + 1]).all()
+        so = np.concatenate(([0], np.cumsum(sc)))
+        want = {(int(idx[k]), p, k - int(so[p])) for p in range(nranks) for k in range(so[p], so[p+1])}
+        got = {(int(c), int(p), int(q)) for c, (_, p, q) in zip(cell, tr)}
+        assert got == want and len(got) == len(tr)
+        # rows of one peer are visited in ascending order inside a tile (ascending cells)
+        for t in range(dm.info.ntile):
+            seg = tr[off[t]:off[t+1]]
+            for p in set(seg[:, 1].tolist()):
+                rows = seg[seg[:, 1] == p, 2]
+                assert (np.diff(rows) > 0).all()
