@@ -299,7 +299,9 @@ public:
 		return time.getTimingData();
 	}
 
-	/// Starter + main solve; writes <log_file_prefix>-residual_history.log when asked (casesolvers.cpp:386-420)
+	/// Starter + main solve; writes <log_file_prefix>-residual_history.log when asked (casesolvers.cpp:386-420).
+	/// One deliberate difference: the reference loses the history when the main solve stops at max_timesteps (the
+	/// solver's Tolerance_error passes through execute() before the file is written); here the file is written first.
 	int execute(const Spatial<freal,NVARS> *const prob, const bool outhist, Vec u) const {
 		fvens_throw(execute_starter(prob, u), "Startup solve failed!");
 		const TimingData td = execute_main(prob, u);
