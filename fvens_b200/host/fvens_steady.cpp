@@ -30,11 +30,11 @@ int main(int argc, char *argv[])
 	try {
 		FlowParserOptions opts = parse_flow_controlfile(argv[1], cmdvars);
 		if(cap >= 0) { opts.maxiter = std::min(opts.maxiter, cap); opts.firstmaxiter = std::min(opts.firstmaxiter, cap); }
+		SteadyFlowCase case1(opts);              // rejects what this build cannot run (implicit, unsteady) before any work
 		const UMesh<freal,NDIM> m = constructMeshFlow(opts, "");
 		std::cout << "Mesh: " << m.gnelem() << " cells, " << m.gnaface() << " faces, " << m.gnbface() << " boundary faces\n";
 		Vec u = nullptr;
 		fvens_throw(initializeSystemVector(opts, m, &u, host_vec ? VEC_HOST : VEC_DEVICE), "could not create the state vector");
-		SteadyFlowCase case1(opts);
 		const FlowSolutionFunctionals fnls = case1.run_output(true, true, m, u);
 		std::cout << std::setprecision(12) << "Functionals: h " << fnls.meshSizeParameter << " entropy " << fnls.entropy
 		          << " CL " << fnls.cl << " CDp " << fnls.cdp << " CDf " << fnls.cdf << "\n";

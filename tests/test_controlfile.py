@@ -78,6 +78,18 @@ def test_implicit_options_are_parsed_but_missing_keys_are_errors(tmp_path):
     assert "unmatched" in parse(str(bad))["error"]
 
 
+def test_fvens_steady_rejects_what_it_cannot_run(tmp_path):
+    """No GPU needed: the driver validates the case before it touches the mesh or the device."""
+    r = subprocess.run([STEADY, os.path.join(CTRL, "naca0012-transonic-implicit.ctrl")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "pseudotime_stepping_type implicit" in r.stderr
+    r = subprocess.run([STEADY, str(tmp_path / "missing.ctrl")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "cannot open control file" in r.stderr
+    r = subprocess.run([STEADY], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "control file" in r.stderr
+    r = subprocess.run([STEADY, os.path.join(CTRL, "naca0012-transonic-explicit.ctrl"), "--bogus"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2
+
+
 @pytest.mark.gpu
 def test_fvens_steady_end_to_end(tmp_path):
     import torch
