@@ -89,7 +89,7 @@ inline void writeScalarsVectorToVtu_PointData(const std::string& fname, const UM
 			for(fint i = 0; i < m.gnpoin(); i++) {
 				out << "\t\t\t\t";
 				for(int idim = 0; idim < NDIM; idim++) out << y(i,idim) << " ";
-				out << "0.0\n";
+				out << "0.0 " << '\n';
 			}
 			out << "\t\t\t</DataArray>\n";
 		}
@@ -100,7 +100,7 @@ inline void writeScalarsVectorToVtu_PointData(const std::string& fname, const UM
 	for(fint i = 0; i < m.gnpoin(); i++) {
 		out << "\t\t\t";
 		for(int idim = 0; idim < NDIM; idim++) out << m.gcoords(i,idim) << " ";
-		out << "0.0\n";
+		out << "0.0 " << '\n';
 	}
 	out << "\t\t</DataArray>\n\t\t</Points>\n";
 	out << "\t\t<Cells>\n";
@@ -115,13 +115,136 @@ inline void writeScalarsVectorToVtu_PointData(const std::string& fname, const UM
 	fint totalcells = 0;
 	for(fint i = 0; i < m.gnelem(); i++) { totalcells += m.gnnode(i); out << "\t\t\t\t" << totalcells << '\n'; }
 	out << "\t\t\t</DataArray>\n";
-	out << "\t\t\t<DataArray type=\"UInt32\" Name=\"types\" Format=\"ascii\">\n";
+	out << "\t\t\t<DataArray type=\"Int32\" Name=\"types\" Format=\"ascii\">\n";
 	for(fint i = 0; i < m.gnelem(); i++) out << "\t\t\t\t" << (m.gnnode(i) == 3 ? 5 : 9) << '\n';      // VTK_TRIANGLE, VTK_QUAD
 	out << "\t\t\t</DataArray>\n";
 	out << "\t\t</Cells>\n";
 	out << "\t</Piece>\n</UnstructuredGrid>\n</VTKFile>";
 	out.close();
 	std::cout << "Vtu file written.\n";
+}
+
+// ---------------------------------------------------------------------------------------- output on host arrays
+
+/// Area-weighted cell->point averaging, then density, Mach number, pressure, temperature and velocity
+/// (FlowOutput::postprocess_point, aoutput.cpp:97-148); u [nelem][NVARS] conserved
+inline void postprocess_point(const UMesh<freal,NDIM>& m, const FlowPhysicsConfig& pconf, const freal *const u,
+                              amat::Array2d<freal>& scalars, amat::Array2d<freal>& velocities)
+{
+	scalars.resize(m.gnpoin(), 4); velocities.resize(m.gnpoin(), NDIM);
+	std::vector<freal> up((size_t)m.gnpoin()*NVARS, 0.0), areasum(m.gnpoin(), 0.0);
+	// The reference adds the cell area to the point's area sum inside its loop over the variables
+	// (aoutput.cpp:115-123), i.e. NVARS times per node, so its point values of the CONSERVED variables - and with them
+	// the density and pressure it writes - are 1/NVARS of the area-weighted averages (velocity, Mach number and
+	// temperature are ratios and come out right). Here the area is added once per node: true averages.
+	for(fint ielem = 0; ielem < m.gnelem(); ielem++)
+		for(int inode = 0; inode < m.gnnode(ielem); inode++) {
+			const fint p = m.ginpoel(ielem,inode);
+			for(int ivar = 0; ivar < NVARS; ivar++) up[(size_t)p*NVARS+ivar] += u[(size_t)ielem*NVARS+ivar]*m.garea(ielem);
+			areasum[p] += m.garea(ielem);
+		}
+	for(fint ip = 0; ip < m.gnpoin(); ip++) {
+		freal *const q = &up[(size_t)ip*NVARS];
+		for(int ivar = 0; ivar < NVARS; ivar++) q[ivar] /= areasum[ip];
+	}
+	for(fint ip = 0; ip < m.gnpoin(); ip++) {
+		const freal *const q = &up[(size_t)ip*NVARS];
+		scalars(ip,0) = q[0];
+		for(int idim = 0; idim < NDIM; idim++) velocities(ip,idim) = q[idim+1]/q[0];
+		const freal vmag2 = velocities(ip,0)*velocities(ip,0) + velocities(ip,1)*velocities(ip,1);
+		scalars(ip,2) = hostgas::pressure(pconf.gamma, q);
+		scalars(ip,1) = std::sqrt(vmag2)/hostgas::soundspeed(pconf.gamma, q);
+		scalars(ip,3) = hostgas::temperature(pconf.gamma, pconf.Minf, q);
+	}
+}
+
+/// x y rho u v p T M per cell (FlowOutput::exportVolumeData, aoutput.cpp:150-176)
+inline void exportVolumeData(const UMesh<freal,NDIM>& m, const FlowPhysicsConfig& pconf, const freal *const u, const std::string& volfile)
+{
+	std::ofstream fout(volfile + "-vol.out");
+	if(!fout) throw std::runtime_error("cannot open " + volfile + "-vol.out");
+	fout << "#   x    y    rho     u      v      p      T      M \n";
+	for(fint iel = 0; iel < m.gnelem(); iel++) {
+		const freal *const q = &u[(size_t)iel*NVARS];
+		const freal T = hostgas::temperature(pconf.gamma, pconf.Minf, q), c = hostgas::soundspeed(pconf.gamma, q), p = hostgas::pressure(pconf.gamma, q);
+		const freal vmag = std::sqrt(q[1]/q[0]*q[1]/q[0] + q[2]/q[0]*q[2]/q[0]);
+		freal rc[NDIM] = {0.0, 0.0};
+		for(int ino = 0; ino < m.gnnode(iel); ino++) for(int j = 0; j < NDIM; j++) rc[j] += m.gcoords(m.ginpoel(iel,ino),j);
+		for(int j = 0; j < NDIM; j++) rc[j] /= m.gnnode(iel);
+		fout << rc[0] << " " << rc[1] << " " << q[0] << " " << q[1]/q[0] << " " << q[2]/q[0] << " " << p << " " << T << " " << vmag/c << '\n';
+	}
+}
+
+/// The per-face table of computeSurfaceData (flow_spatial.cpp:131-310) for the faces with marker iwbcm: x, y, Cp, Cf per
+/// face, from the cell state and the conserved-variable gradients; also the integrated Cl, Cdp, Cdf the reference derives
+/// from the same rows (the product takes those from the device, fvg_surface_data; here they serve the host-only checks).
+inline std::tuple<freal,freal,freal> surfaceFaceTable(const UMesh<freal,NDIM>& m, const FlowPhysicsConfig& pconf, const freal *const u,
+                                                      const GradBlock_t<freal,NDIM,NVARS> *const grad, const int iwbcm,
+                                                      std::vector<std::array<freal,4>>& rows)
+{
+	rows.clear();
+	const freal pinf = 1.0/(pconf.gamma*pconf.Minf*pconf.Minf);
+	const freal wind[NDIM] = {std::cos(pconf.aoa), std::sin(pconf.aoa)}, flownormal[NDIM] = {-wind[1], wind[0]};
+	freal totalarea = 0, Cl = 0, Cdp = 0, Cdf = 0;
+	for(fint iface = m.gPhyBFaceStart(); iface < m.gPhyBFaceEnd(); iface++) {
+		if(m.gbtags(iface,0) != iwbcm) continue;
+		const fint lelem = m.gintfac(iface,0);
+		const std::array<freal,NDIM> n = m.gnormal(iface);
+		const freal area = m.gfacemetric(iface,NDIM);
+		const freal tangf[NDIM] = {n[1], -n[0]};
+		freal fcen[NDIM];
+		for(int j = 0; j < NDIM; j++) {
+			fcen[j] = 0;
+			for(int inofa = 0; inofa < m.gnnofa(iface); inofa++) fcen[j] += m.gcoords(m.gintfac(iface,2+inofa),j);
+			fcen[j] /= m.gnnofa(iface);
+		}
+		const freal *const q = &u[(size_t)lelem*NVARS];
+		const freal cp = (hostgas::pressure(pconf.gamma, q) - pinf)*2.0;
+		const freal muhat = hostgas::viscosity(pconf, q);
+		freal gradu[NDIM][NDIM];
+		for(int i = 0; i < NDIM; i++) for(int j = 0; j < NDIM; j++)
+			gradu[i][j] = (grad[lelem](j,i+1)*q[0] - q[i+1]*grad[lelem](j,0))/(q[0]*q[0]);
+		freal force[NDIM];
+		for(int i = 0; i < NDIM; i++) { force[i] = 0; for(int j = 0; j < NDIM; j++) force[i] += (gradu[i][j] + gradu[j][i])*n[j]; }
+		const freal tauw = muhat*(force[0]*tangf[0] + force[1]*tangf[1]);
+		rows.push_back({fcen[0], fcen[1], cp, 2*tauw});
+		totalarea += area;
+		Cl += cp*(n[0]*flownormal[0] + n[1]*flownormal[1])*area;
+		Cdp += cp*(n[0]*wind[0] + n[1]*wind[1])*area;
+		Cdf += 2*tauw*(tangf[0]*wind[0] + tangf[1]*wind[1])*area;
+	}
+	return std::make_tuple(Cl/totalarea, Cdp/totalarea, Cdf/totalarea);
+}
+
+/// <basename>-surf_w<marker>.out in the reference's format (FlowOutput::exportSurfaceData, aoutput.cpp:209-241)
+inline void writeWallSurfaceFile(const std::string& fname, const std::vector<std::array<freal,4>>& rows, const freal Cl, const freal Cdp, const freal Cdf)
+{
+	std::ofstream fout(fname);
+	if(!fout) throw std::runtime_error("cannot open " + fname);
+	fout << "#  x \t y \t Cp  \t Cf \n";
+	for(const auto& r : rows) { for(int j = 0; j < 4; j++) fout << "  " << r[j]; fout << '\n'; }
+	fout << "# Cl      Cdp      Cdf\n";
+	fout << "# " << Cl << "  " << Cdp << "  " << Cdf << '\n';
+}
+
+/// <basename>-surf_o<marker>.out: face centre and cell velocity per face of an "other" boundary (aoutput.cpp:243-290)
+inline void writeOtherSurfaceFile(const std::string& fname, const UMesh<freal,NDIM>& m, const freal *const u, const int marker)
+{
+	std::ofstream fout(fname);
+	if(!fout) throw std::runtime_error("cannot open " + fname);
+	fout << "#   x         y          u           v\n";
+	for(fint iface = m.gPhyBFaceStart(); iface < m.gPhyBFaceEnd(); iface++) {
+		if(m.gbtags(iface,0) != marker) continue;
+		const fint lelem = m.gintfac(iface,0);
+		const freal *const q = &u[(size_t)lelem*NVARS];
+		freal coord[NDIM];
+		for(int j = 0; j < NDIM; j++) {
+			coord[j] = 0;
+			for(int inofa = 0; inofa < m.gnnofa(iface); inofa++) coord[j] += m.gcoords(m.gintfac(iface,2+inofa),j);
+			coord[j] /= m.gnnofa(iface);
+		}
+		fout << "  " << coord[0] << "  " << coord[1] << "  " << q[1]/q[0] << "  " << q[2]/q[0] << '\n';
+	}
 }
 
 // ---------------------------------------------------------------------------------------- FlowOutput
@@ -140,48 +263,16 @@ public:
 		return e;
 	}
 
-	/// Area-weighted cell->point averaging, then density, Mach number, pressure, temperature and velocity (aoutput.cpp:97-148)
 	StatusCode postprocess_point(const std::vector<freal>& u, amat::Array2d<freal>& scalars, amat::Array2d<freal>& velocities) const {
-		scalars.resize(m->gnpoin(), 4); velocities.resize(m->gnpoin(), NDIM);
-		std::vector<freal> up((size_t)m->gnpoin()*NVARS, 0.0), areasum(m->gnpoin(), 0.0);
-		for(fint ielem = 0; ielem < m->gnelem(); ielem++)
-			for(int inode = 0; inode < m->gnnode(ielem); inode++) {
-				const fint p = m->ginpoel(ielem,inode);
-				for(int ivar = 0; ivar < NVARS; ivar++) up[(size_t)p*NVARS+ivar] += u[(size_t)ielem*NVARS+ivar]*m->garea(ielem);
-				areasum[p] += m->garea(ielem);
-			}
-		for(fint ip = 0; ip < m->gnpoin(); ip++) {
-			freal *const q = &up[(size_t)ip*NVARS];
-			for(int ivar = 0; ivar < NVARS; ivar++) q[ivar] /= areasum[ip];
-			scalars(ip,0) = q[0];
-			for(int idim = 0; idim < NDIM; idim++) velocities(ip,idim) = q[idim+1]/q[0];
-			const freal vmag2 = velocities(ip,0)*velocities(ip,0) + velocities(ip,1)*velocities(ip,1);
-			scalars(ip,2) = hostgas::pressure(pconf.gamma, q);
-			scalars(ip,1) = std::sqrt(vmag2)/hostgas::soundspeed(pconf.gamma, q);
-			scalars(ip,3) = hostgas::temperature(pconf.gamma, pconf.Minf, q);
-		}
+		fvens::postprocess_point(*m, pconf, u.data(), scalars, velocities);
 		return 0;
 	}
 
-	/// x y rho u v p T M per cell (aoutput.cpp:150-176)
-	void exportVolumeData(const std::vector<freal>& u, const std::string& volfile) const {
-		std::ofstream fout(volfile + "-vol.out");
-		if(!fout) throw std::runtime_error("cannot open " + volfile + "-vol.out");
-		fout << "#   x    y    rho     u      v      p      T      M \n";
-		for(fint iel = 0; iel < m->gnelem(); iel++) {
-			const freal *const q = &u[(size_t)iel*NVARS];
-			const freal T = hostgas::temperature(pconf.gamma, pconf.Minf, q), c = hostgas::soundspeed(pconf.gamma, q), p = hostgas::pressure(pconf.gamma, q);
-			const freal vmag = std::sqrt(q[1]/q[0]*q[1]/q[0] + q[2]/q[0]*q[2]/q[0]);
-			freal rc[NDIM] = {0.0, 0.0};
-			for(int ino = 0; ino < m->gnnode(iel); ino++) for(int j = 0; j < NDIM; j++) rc[j] += m->gcoords(m->ginpoel(iel,ino),j);
-			for(int j = 0; j < NDIM; j++) rc[j] /= m->gnnode(iel);
-			fout << rc[0] << " " << rc[1] << " " << q[0] << " " << q[1]/q[0] << " " << q[2]/q[0] << " " << p << " " << T << " " << vmag/c << '\n';
-		}
-	}
+	void exportVolumeData(const std::vector<freal>& u, const std::string& volfile) const { fvens::exportVolumeData(*m, pconf, u.data(), volfile); }
 
 	/// Per wall marker: x, y, Cp, Cf of every face with that marker and the integrated Cl, Cdp, Cdf; per other marker:
 	/// x, y and the velocity (aoutput.cpp:181-290). The integrals are the device's (fvg_surface_data); the per-face table
-	/// restates flow_spatial.cpp:131-310 on the host from the same cell state and conserved-variable gradients.
+	/// is computed on the host from the same cell state and conserved-variable gradients (surfaceFaceTable).
 	void exportSurfaceData(const Vec u, const std::vector<int>& wbcm, const std::vector<int>& obcm, const std::string& basename) const {
 		const fint ne = m->gnelem();
 		std::vector<freal> uh((size_t)ne*NVARS);
@@ -189,51 +280,17 @@ public:
 		std::vector<GradBlock_t<freal,NDIM,NVARS>> grad(ne);
 		space->getGradients(u, &grad[0]);
 		const amat::Array2dView<freal> ua(uh.data(), ne, NVARS);
-		const freal pinf = 1.0/(pconf.gamma*pconf.Minf*pconf.Minf);
 		for(size_t im = 0; im < wbcm.size(); im++) {
-			const std::string fname = basename + "-surf_w" + std::to_string(wbcm[im]) + ".out";
-			std::ofstream fout(fname);
-			if(!fout) throw std::runtime_error("cannot open " + fname);
-			fout << "#  x \t y \t Cp  \t Cf \n";
 			MVector<freal> dummy;
 			freal Cl, Cdp, Cdf;
 			std::tie(Cl, Cdp, Cdf) = space->computeSurfaceData(ua, &grad[0], wbcm[im], dummy);
-			for(fint iface = m->gPhyBFaceStart(); iface < m->gPhyBFaceEnd(); iface++) {
-				if(m->gbtags(iface,0) != wbcm[im]) continue;
-				const fint lelem = m->gintfac(iface,0);
-				const std::array<freal,NDIM> n = m->gnormal(iface);
-				const freal tangf[NDIM] = {n[1], -n[0]};
-				freal fcen[NDIM];
-				for(int j = 0; j < NDIM; j++) fcen[j] = 0.5*(m->gcoords(m->gintfac(iface,2),j) + m->gcoords(m->gintfac(iface,3),j));
-				const freal *const q = &uh[(size_t)lelem*NVARS];
-				const freal cp = (hostgas::pressure(pconf.gamma, q) - pinf)*2.0;
-				const freal muhat = hostgas::viscosity(pconf, q);
-				freal gradu[NDIM][NDIM];
-				for(int i = 0; i < NDIM; i++) for(int j = 0; j < NDIM; j++)
-					gradu[i][j] = (grad[lelem](j,i+1)*q[0] - q[i+1]*grad[lelem](j,0))/(q[0]*q[0]);
-				freal force[NDIM];
-				for(int i = 0; i < NDIM; i++) { force[i] = 0; for(int j = 0; j < NDIM; j++) force[i] += (gradu[i][j] + gradu[j][i])*n[j]; }
-				const freal tauw = muhat*(force[0]*tangf[0] + force[1]*tangf[1]);
-				fout << "  " << fcen[0] << "  " << fcen[1] << "  " << cp << "  " << 2*tauw << '\n';
-			}
-			fout << "# Cl      Cdp      Cdf\n";
-			fout << "# " << Cl << "  " << Cdp << "  " << Cdf << '\n';
+			std::vector<std::array<freal,4>> rows;
+			surfaceFaceTable(*m, pconf, uh.data(), &grad[0], wbcm[im], rows);
+			writeWallSurfaceFile(basename + "-surf_w" + std::to_string(wbcm[im]) + ".out", rows, Cl, Cdp, Cdf);
 			std::cout << "FlowOutput: CL = " << Cl << "   CDp = " << Cdp << "    CDf = " << Cdf << std::endl;
 		}
-		for(size_t im = 0; im < obcm.size(); im++) {
-			const std::string fname = basename + "-surf_o" + std::to_string(obcm[im]) + ".out";
-			std::ofstream fout(fname);
-			if(!fout) throw std::runtime_error("cannot open " + fname);
-			fout << "#   x         y          u           v\n";
-			for(fint iface = m->gPhyBFaceStart(); iface < m->gPhyBFaceEnd(); iface++) {
-				if(m->gbtags(iface,0) != obcm[im]) continue;
-				const fint lelem = m->gintfac(iface,0);
-				const freal *const q = &uh[(size_t)lelem*NVARS];
-				fout << "  " << 0.5*(m->gcoords(m->gintfac(iface,2),0) + m->gcoords(m->gintfac(iface,3),0))
-				     << "  " << 0.5*(m->gcoords(m->gintfac(iface,2),1) + m->gcoords(m->gintfac(iface,3),1))
-				     << "  " << q[1]/q[0] << "  " << q[2]/q[0] << '\n';
-			}
-		}
+		for(size_t im = 0; im < obcm.size(); im++)
+			writeOtherSurfaceFile(basename + "-surf_o" + std::to_string(obcm[im]) + ".out", *m, uh.data(), obcm[im]);
 	}
 
 private:

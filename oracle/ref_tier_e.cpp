@@ -204,6 +204,35 @@ int ref_e_flow_forward_euler(void *hv, double cfl, double tol, int maxiter, doub
 	return code;
 }
 
+/// The reference's output artefacts for the state u: <basename>-surf_w<m>.out / -surf_o<m>.out (FlowOutput::exportSurfaceData),
+/// the VTU file (postprocess_point + writeScalarsVectorToVtu_PointData) and <volprefix>-vol.out (exportVolumeData)
+int ref_e_write_outputs(void *hv, const double *u, double aoa, const double *phys, int nwall, const int *walls, int nother,
+                        const int *others, const char *basename, const char *vtufile, const char *volprefix)
+{
+	RefCase *h = static_cast<RefCase*>(hv);
+	const FlowFV_base<freal> *const fv = dynamic_cast<const FlowFV_base<freal>*>(h->prob.get());
+	if(!fv) return 1;
+	std::copy(u, u + h->uv.a.size(), h->uv.a.begin());
+	const IdealGasPhysics<freal> phy(phys[0], phys[1], phys[2], phys[3], phys[4]);
+	std::stringstream sink;
+	std::streambuf *const old = std::cout.rdbuf(sink.rdbuf());
+	int rc = 0;
+	try {
+		FlowOutput out(fv, &phy, aoa);
+		out.exportSurfaceData(&h->uv, std::vector<int>(walls, walls + nwall), std::vector<int>(others, others + nother), basename);
+		amat::Array2d<freal> scalars, velocities;
+		out.postprocess_point(&h->uv, scalars, velocities);
+		std::string scalarnames[] = {"density", "mach-number", "pressure", "temperature"};
+		writeScalarsVectorToVtu_PointData(vtufile, *h->m, scalars, scalarnames, velocities, "velocity");
+		const fint ne = h->m->gnelem();
+		MVector<freal> umat(ne, NVARS);
+		for(fint i = 0; i < ne; i++) for(int j = 0; j < NVARS; j++) umat(i,j) = u[(size_t)i*NVARS+j];
+		out.exportVolumeData(umat, volprefix);
+	} catch(std::exception&) { rc = 2; }
+	std::cout.rdbuf(old);
+	return rc;
+}
+
 /// Cl, Cdp, Cdf of the reference's computeSurfaceData on gradients from its getGradients; entropy norm from FlowOutput
 int ref_e_surface_and_entropy(void *hv, const double *u, int marker, double aoa, const double *phys, double *out4)
 {

@@ -19,6 +19,32 @@ int main(int argc, char *argv[])
 		}
 		return 0;
 	}
+	if(std::string(argv[1]) == "--outputs") {
+		// the host-side writers of casesolvers.hpp on given arrays (no GPU): --outputs mesh ufile gradfile gamma Minf Tinf Reinf Pr
+		// aoa viscous constvisc wallmarker othermarker prefix
+		if(argc < 16) return 2;
+		const UMesh<freal,NDIM> m = constructMesh(argv[2]);
+		const size_t ne = m.gnelem();
+		std::vector<double> u(ne*NVARS);
+		std::vector<GradBlock_t<freal,NDIM,NVARS>> grad(ne);
+		{ std::ifstream f(argv[3], std::ios::binary); f.read(reinterpret_cast<char*>(u.data()), u.size()*sizeof(double)); if(!f) return 3; }
+		{ std::ifstream f(argv[4], std::ios::binary); f.read(reinterpret_cast<char*>(grad.data()), ne*sizeof(grad[0])); if(!f) return 3; }
+		FlowPhysicsConfig pc { std::atof(argv[5]), std::atof(argv[6]), std::atof(argv[7]), std::atof(argv[8]), std::atof(argv[9]),
+		                       std::atof(argv[10]), std::atoi(argv[11]) != 0, std::atoi(argv[12]) != 0, {} };
+		const int wall = std::atoi(argv[13]), other = std::atoi(argv[14]);
+		const std::string prefix = argv[15];
+		std::vector<std::array<freal,4>> rows;
+		freal Cl, Cdp, Cdf;
+		std::tie(Cl, Cdp, Cdf) = surfaceFaceTable(m, pc, u.data(), grad.data(), wall, rows);
+		writeWallSurfaceFile(prefix + "-surf_w" + std::to_string(wall) + ".out", rows, Cl, Cdp, Cdf);
+		writeOtherSurfaceFile(prefix + "-surf_o" + std::to_string(other) + ".out", m, u.data(), other);
+		amat::Array2d<freal> scalars, velocities;
+		postprocess_point(m, pc, u.data(), scalars, velocities);
+		const std::string names[] = {"density", "mach-number", "pressure", "temperature"};
+		writeScalarsVectorToVtu_PointData(prefix + ".vtu", m, scalars, names, velocities, "velocity");
+		exportVolumeData(m, pc, u.data(), prefix);
+		return 0;
+	}
 	std::map<std::string,std::string> cmd;
 	for(int i = 2; i + 1 < argc; i += 2) cmd[argv[i]] = argv[i+1];
 	try {

@@ -281,6 +281,17 @@ class RefCase:
                                                  _dp(hrel), _dp(habs))
         return code, steps.value, hrel[:steps.value], habs[:steps.value], u
 
+    def write_outputs(self, u, walls, others, basename, vtufile, volprefix):
+        """The reference's own surface / VTU / volume files for the state u."""
+        p = self.phys
+        ph = np.array([p.gamma, p.Minf, p.Tinf, p.Reinf, p.Pr], dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        w = np.ascontiguousarray(walls, dtype=np.int32); ot = np.ascontiguousarray(others, dtype=np.int32)
+        rc = self.lib.ref_e_write_outputs(self.h, _dp(u), C.c_double(p.aoa), _dp(ph), len(w), _ip(w), len(ot), _ip(ot),
+                                          str(basename).encode(), str(vtufile).encode(), str(volprefix).encode())
+        if rc != 0:
+            raise RuntimeError(f"reference output failed ({rc})")
+
     def surface_and_entropy(self, u, marker):
         """(Cl, Cdp, Cdf, entropy norm) from the reference's computeSurfaceData / getGradients / FlowOutput."""
         p = self.phys

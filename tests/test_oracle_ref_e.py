@@ -95,3 +95,63 @@ def test_product_host_mesh_against_the_reference_mesh_class(mesh):
     um.reorder_cells(perm)
     rm.reorder_cells(perm)
     same(um.arrays(), rm.arrays())
+
+
+def _vtu_arrays(path):
+    import xml.dom.minidom
+    doc = xml.dom.minidom.parse(str(path))
+    out = {}
+    for d in doc.getElementsByTagName("DataArray"):
+        name = d.getAttribute("Name") or "points"
+        out[name] = (d.getAttribute("type"), d.firstChild.data)
+    piece = doc.getElementsByTagName("Piece")[0]
+    return out, int(piece.getAttribute("NumberOfPoints")), int(piece.getAttribute("NumberOfCells"))
+
+
+def test_output_files_of_the_host_layer_against_the_reference_writers(tmp_path):
+    """The artefacts fvens_steady leaves behind - surface files, volume file, VTU - written by the host layer
+    (fvens_b200/host/casesolvers.hpp, free functions on host arrays: no GPU) and by the reference's own FlowOutput /
+    VTU writer (spatial/aoutput.cpp, tier E) for the same viscous state. Text files: identical, or equal to the printed
+    precision where the gradients come from different (1e-13-equal) sources. VTU: identical blocks, except density and
+    pressure - the reference divides its point sums of the conserved variables by NVARS times the area sum
+    (aoutput.cpp:115-127), the host layer writes the true area-weighted averages."""
+    import os
+    import subprocess
+    from common import ROOT
+    mesh = mesh_path("2dcylinderhybrid.msh")
+    om = orc.Mesh.read(mesh)
+    a = om.arrays()
+    phys = lib.make_physics(1.4, 0.5, 288.15, 150.0, 0.72, 0.05, True, False)
+    bcs = [(2, lib.BC["adiabaticwall"], (0.0, 0.0)), (4, lib.BC["farfield"], (0.0, 0.0))]
+    of = orc.Flow(om, phys, lib.FLUX["ROE"], lib.GRAD["LEASTSQUARES"], lib.RECON["NONE"], 1.0, True, 0, bcs)
+    rc, _, _ = of.geometry()
+    u = synth.perturbed_state(rc, 1.4, 0.5, 0.05, amp=0.07)
+    grads = of.get_gradients(u)
+    rf = orc.RefCase.read(mesh).flow(phys, "ROE", "LEASTSQUARES", "NONE", 1.0, True, bcs)
+    rdir = tmp_path / "ref"; hdir = tmp_path / "host"
+    rdir.mkdir(); hdir.mkdir()
+    rf.write_outputs(u, [2], [4], rdir / "case", rdir / "case.vtu", rdir / "case")
+    (tmp_path / "u.bin").write_bytes(np.ascontiguousarray(u).tobytes())
+    (tmp_path / "g.bin").write_bytes(np.ascontiguousarray(grads).tobytes())
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "test_controlparser"), "--outputs", mesh, str(tmp_path / "u.bin"),
+                        str(tmp_path / "g.bin"), "1.4", "0.5", "288.15", "150.0", "0.72", "0.05", "1", "0", "2", "4", str(hdir / "case")],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    # volume file and the "other boundary" surface file: pure functions of mesh and state -> the same text
+    assert (hdir / "case-vol.out").read_text() == (rdir / "case-vol.out").read_text()
+    assert (hdir / "case-surf_o4.out").read_text() == (rdir / "case-surf_o4.out").read_text()
+    # wall surface file: same layout; numbers equal to the 6 printed digits (gradients from the oracle vs the reference)
+    hw = (hdir / "case-surf_w2.out").read_text().splitlines(); rw = (rdir / "case-surf_w2.out").read_text().splitlines()
+    assert len(hw) == len(rw) and hw[0] == rw[0] and hw[-2] == rw[-2] and len(hw) > 10
+    for x, y in zip(hw[1:-2] + [hw[-1][1:]], rw[1:-2] + [rw[-1][1:]]):
+        p, q = np.array(x.split(), dtype=float), np.array(y.split(), dtype=float)
+        assert np.abs(p - q).max() <= 2e-5*max(np.abs(q).max(), 1e-3)
+    assert abs(float(hw[-1].split()[3])) > 1e-4          # a viscous case: the skin-friction drag is there
+    # VTU
+    hv, hnp, hnc = _vtu_arrays(hdir / "case.vtu"); rv, rnp, rnc = _vtu_arrays(rdir / "case.vtu")
+    assert (hnp, hnc) == (rnp, rnc) == (a["coords"].shape[0], om.nelem) and list(hv) == list(rv)
+    for name in ("mach-number", "temperature", "velocity", "points", "connectivity", "offsets", "types"):
+        assert hv[name] == rv[name], name
+    for name in ("density", "pressure"):
+        h = np.array(hv[name][1].split(), dtype=float); rr = np.array(rv[name][1].split(), dtype=float)
+        assert hv[name][0] == rv[name][0] and np.abs(h/(4.0*rr) - 1).max() < 1e-9
