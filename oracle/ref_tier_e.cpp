@@ -4,6 +4,8 @@
  * metrics), its FlowFV::compute_residual with everything under it (the tier-C sources), its explicit pseudo-time
  * solver and output unit (ode/aodesolver.cpp, spatial/aoutput.cpp) - compiled UNMODIFIED, in place from
  * /root/reference/src against ref_shim_b/ (Eigen-lite, serial PETSc Vec, single-process MPI, boost::split, boost::bimap).
+ * Also its mesh partitioner (mesh/meshpartitioning.cpp: restrictMeshToPartitions, the subdomain + connectivity-face
+ * construction every rank of an MPI run performs), driven rank by rank through a settable rank/size in the MPI stand-in.
  * No mesh stand-in here: from the mesh file to the residual every instruction is the reference's. This file adds the
  * mesh construction sequence of the reference's constructMesh / preprocessMesh for one rank without reordering
  * (mesh/ameshutils.cpp:97-153, 39-96), createSystemVector, and a C interface; it contains no reference code.
@@ -11,6 +13,7 @@
  */
 #include "mesh/mesh.cpp"
 #include "mesh/meshreaders.cpp"
+#include "mesh/meshpartitioning.cpp"
 #include "ref_sources_spatial.hpp"
 #include "spatial/aoutput.cpp"
 #include "ode/aodesolver.cpp"
@@ -110,6 +113,60 @@ void* ref_e_mesh_from_arrays(int npoin, const double *coords, int nelem, int max
 	} catch(std::exception&) { delete h; h = nullptr; }
 	std::cout.rdbuf(old);
 	return h;
+}
+
+namespace {
+/// restrictMeshToPartitions with a given cell -> rank map (the reference's partitioners only differ in how they fill it)
+struct GivenPartitioner : public ReplicatedGlobalMeshPartitioner {
+	GivenPartitioner(const UMesh<freal,NDIM>& gm, const int *dist) : ReplicatedGlobalMeshPartitioner(gm) { elemdist.assign(dist, dist + gm.gnelem()); }
+	void compute_partition() {}
+};
+struct TrivialProbe : public TrivialReplicatedGlobalMeshPartitioner {
+	using TrivialReplicatedGlobalMeshPartitioner::TrivialReplicatedGlobalMeshPartitioner;
+	const std::vector<int>& dist() const { return elemdist; }
+};
+}
+
+/// TrivialReplicatedGlobalMeshPartitioner::compute_partition for `nranks` ranks: cell -> rank into dist [nelem]
+void ref_e_trivial_partition(void *hv, int nranks, int *dist)
+{
+	RefCase *h = static_cast<RefCase*>(hv);
+	mpi_lite_size = nranks; mpi_lite_rank = 0;
+	TrivialProbe p(*h->m);
+	p.compute_partition();
+	std::copy(p.dist().begin(), p.dist().end(), dist);
+	mpi_lite_size = 1;
+}
+
+/// The subdomain mesh of `rank` as the reference builds it: restrictMeshToPartitions on the global mesh of hv (which
+/// must have its topology), then the preprocessing. Returns a new handle (mesh only) or NULL.
+void* ref_e_restrict_to_rank(void *hv, const int *dist, int nranks, int rank)
+{
+	RefCase *g = static_cast<RefCase*>(hv);
+	std::stringstream sink;
+	std::streambuf *const old = std::cout.rdbuf(sink.rdbuf());
+	RefCase *h = nullptr;
+	mpi_lite_size = nranks; mpi_lite_rank = rank;
+	try {
+		GivenPartitioner p(*g->m, dist);
+		h = new RefCase;
+		h->m.reset(new UMesh<freal,NDIM>(p.restrictMeshToPartitions()));
+		h->m->compute_topological();
+		h->m->compute_areas();
+		h->m->compute_face_data();
+	} catch(std::exception&) { delete h; h = nullptr; }
+	mpi_lite_size = 1; mpi_lite_rank = 0;
+	std::cout.rdbuf(old);
+	return h;
+}
+
+/// number of connectivity faces; glob [nelem] global cell ids; conn [nconn][5] = gconnface(i, 0..4)
+int ref_e_connectivity(void *hv, int *glob, int *conn)
+{
+	const UMesh<freal,NDIM>& m = *static_cast<RefCase*>(hv)->m;
+	if(glob) for(fint i = 0; i < m.gnelem(); i++) glob[i] = m.gglobalElemIndex(i);
+	if(conn) for(fint i = 0; i < m.gnConnFace(); i++) for(int j = 0; j < 5; j++) conn[(size_t)i*5+j] = m.gconnface(i,j);
+	return m.gnConnFace();
 }
 
 /// UMesh::reorder_cells (new cell i = old cell perm[i], mesh/mesh.cpp:85-99) followed by the preprocessing again

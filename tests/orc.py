@@ -249,6 +249,26 @@ class RefCase:
                                 _ip(d["elemface"]), _ip(d["intfac"]), _ip(d["btags"]), _dp(d["facemetric"]), _dp(d["area"]))
         return d
 
+    def trivial_partition(self, nranks):
+        """cell -> rank of the reference's TrivialReplicatedGlobalMeshPartitioner."""
+        dist = np.zeros(self.nelem, dtype=np.int32)
+        self.lib.ref_e_trivial_partition(self.h, int(nranks), _ip(dist))
+        return dist
+
+    def restrict_to_rank(self, dist, nranks, rank):
+        """The subdomain mesh the reference's restrictMeshToPartitions builds for `rank` (a new RefCase, mesh only)."""
+        dist = np.ascontiguousarray(dist, dtype=np.int32)
+        self.lib.ref_e_restrict_to_rank.restype = C.c_void_p
+        return RefCase(self.lib.ref_e_restrict_to_rank(self.h, _ip(dist), int(nranks), int(rank)))
+
+    def connectivity(self):
+        """(global cell ids [nelem], connectivity faces [nconn][5]: local cell, local face, neighbour rank, neighbour's global
+        cell, global face id)."""
+        n = self.lib.ref_e_connectivity(self.h, None, None)
+        glob = np.zeros(self.nelem, dtype=np.int32); conn = np.zeros((max(n, 1), 5), dtype=np.int32)
+        self.lib.ref_e_connectivity(self.h, _ip(glob), _ip(conn))
+        return glob, conn[:n]
+
     def reorder_cells(self, perm):
         perm = np.ascontiguousarray(perm, dtype=np.int32)
         assert len(perm) == self.nelem

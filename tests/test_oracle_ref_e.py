@@ -155,3 +155,59 @@ def test_output_files_of_the_host_layer_against_the_reference_writers(tmp_path):
     for name in ("density", "pressure"):
         h = np.array(hv[name][1].split(), dtype=float); rr = np.array(rv[name][1].split(), dtype=float)
         assert hv[name][0] == rv[name][0] and np.abs(h/(4.0*rr) - 1).max() < 1e-9
+
+
+def _read_dist_golden(path):
+    lines = open(path).read().split("\n")
+    i = [l.strip().lower() for l in lines].index("#connfaces")
+    elems = np.array([int(x) for x in lines[1:i] if x.strip()], dtype=np.int32)
+    conn = np.array([[int(y) for y in x.split()] for x in lines[i+1:] if x.strip()], dtype=np.int32).reshape(-1, 4)
+    return elems, conn
+
+
+def test_reference_partitioner_reproduces_its_goldens_and_the_product_agrees():
+    """tests/mesh/distributedmesh.cpp of the reference, replayed on its own object code (mesh/meshpartitioning.cpp in
+    tier E, one process playing the three ranks): the trivial 3-way partition of testhybrid.msh gives the golden
+    subdomain meshes (testhybrid_part*.msh), global cell indices and connectivity faces (testhybrid-distb_part*.dat).
+    Then the PRODUCT's subdomain construction (fvg_mesh_create_part, host-only build) for the same cell -> rank map: the
+    same own cells in the same order, and ghost cells = the neighbours behind the reference's connectivity faces, owned
+    by the ranks the reference names."""
+    gm = orc.RefCase.read(mesh_path("testhybrid.msh"))
+    dist = gm.trivial_partition(3)
+    um = lib.UMesh.read(mesh_path("testhybrid.msh"))
+    assert sorted(set(dist.tolist())) == [0, 1, 2]
+    for r in range(3):
+        lm = gm.restrict_to_rank(dist, 3, r)
+        gold = orc.RefCase.read(mesh_path(f"testhybrid_part{r+1}.msh"))
+        la, ga = lm.arrays(), gold.arrays()
+        assert (lm.npoin, lm.nelem, lm.nbface) == (gold.npoin, gold.nelem, gold.nbface)
+        assert np.array_equal(la["nnode"], ga["nnode"]) and np.array_equal(la["inpoel"], ga["inpoel"])
+        assert np.abs(la["coords"] - ga["coords"]).max() < 1e-12
+        elems, conn4 = _read_dist_golden(mesh_path(f"testhybrid-distb_part{r+1}.dat"))
+        glob, conn = lm.connectivity()
+        assert np.array_equal(glob, elems) and np.array_equal(conn[:, :4], conn4)
+        assert (dist[glob] == r).all()
+        # the product, for the same distribution
+        dm = lib.DeviceMesh(um, reorder="none", tile_cells=32, device=-2, cell_rank=dist, rank=r, nranks=3)
+        ids = dm.permutation()
+        assert np.array_equal(ids[:dm.ncell], glob)
+        assert set(ids[dm.ncell:].tolist()) == set(conn[:, 3].tolist())
+        owner = {int(c): int(rk) for rk, c in zip(conn[:, 2], conn[:, 3])}
+        assert all(dist[g] == owner[int(g)] for g in ids[dm.ncell:])
+
+
+@pytest.mark.parametrize("nranks", [2, 5])
+def test_product_subdomains_against_the_reference_partitioner_on_a_hilbert_partition(nranks):
+    """The space-filling-curve partition bench.py uses, restricted to each rank by the reference's own
+    restrictMeshToPartitions and by the product: own cells (ascending global index), ghost sets, owners."""
+    arrs = synth.bump_channel(40, 16)
+    um = lib.UMesh.from_arrays(*arrs)
+    part = lib.partition_sfc(um, nranks)
+    gm = orc.RefCase.from_arrays(*arrs)
+    for r in range(nranks):
+        glob, conn = gm.restrict_to_rank(part, nranks, r).connectivity()
+        dm = lib.DeviceMesh(um, reorder="none", tile_cells=64, device=-2, cell_rank=part, rank=r, nranks=nranks)
+        ids = dm.permutation()
+        assert np.array_equal(ids[:dm.ncell], glob) and (part[glob] == r).all()
+        assert set(ids[dm.ncell:].tolist()) == set(conn[:, 3].tolist()) and len(conn) >= dm.nghost > 0
+        assert all(part[c] == rk for rk, c in zip(conn[:, 2], conn[:, 3]))
