@@ -27,6 +27,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <ctime>
+#include <fstream>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -832,6 +834,117 @@ private:
 		}
 		if(code == FVG_OK && step == config.maxiter && resi/initres > config.tol) code = FVG_ERR_TOLERANCE;
 		VecDestroy(&r); VecDestroy(&dt);
+		return code;
+	}
+};
+
+/// Reference: UnsteadySolver (ode/aodesolver.hpp:195-226)
+template <int nvars>
+class UnsteadySolver {
+public:
+	UnsteadySolver(const Spatial<freal,nvars> *const spatial, Vec soln, const int temporal_order, const std::string log_file)
+		: space(spatial), uvec(soln), order(temporal_order), cputime(0.0), walltime(0.0), logfile(log_file) {}
+	virtual ~UnsteadySolver() {}
+	std::tuple<double,double> getRunTimes() const { return std::make_tuple(walltime, cputime); }
+	virtual StatusCode solve(const freal time) = 0;
+protected:
+	const Spatial<freal,nvars> *space;
+	Vec uvec;
+	const int order;
+	double cputime, walltime;
+	const std::string logfile;
+};
+
+/// Reference: TVDRKSolver (ode/aodesolver.hpp:229-258, aodesolver.cpp:647-785), total-variation-diminishing
+/// Runge-Kutta up to order 3 with the reference's coefficient table and global time step cfl * min(dtm). The stages
+/// are evaluated at the stage state and the update has the sign of the forward-Euler loop - the reference's loop does
+/// neither (see fvg_tvdrk_solve in include/fvens_b200.h). With the engine's FlowFV the loop runs on the device; with
+/// any other Spatial the generic loop below drives compute_residual on host Vecs.
+template <int nvars>
+class TVDRKSolver : public UnsteadySolver<nvars> {
+public:
+	TVDRKSolver(const Spatial<freal,nvars> *const spatial, Vec soln, const int temporal_order, const std::string log_file,
+	            const double cfl_num)
+		: UnsteadySolver<nvars>(spatial, soln, temporal_order, log_file), cfl(cfl_num), tvdcoeffs(3*std::max(temporal_order,1), 0.0),
+		  nsteps(0), phytime(0.0)
+	{
+		if(temporal_order < 1 || temporal_order > 3) std::cout << "! Temporal order " << temporal_order << " not available!\n";
+		else fvg_tvdrk_coefficients(temporal_order, tvdcoeffs.data());
+		std::cout << " TVDRKSolver: Initialized TVD RK solver of order " << temporal_order << ", CFL = " << cfl << std::endl;
+	}
+
+	StatusCode solve(const freal finaltime) {
+		if(this->order < 1 || this->order > 3) throw UnsupportedOptionError("TVDRKSolver: temporal order not available");
+		Vec u = this->uvec;
+		const auto t0 = std::chrono::steady_clock::now();
+		const double c0 = (double)clock()/(double)CLOCKS_PER_SEC;
+		int code;
+		const FlowFV_base<freal> *const eng = dynamic_cast<const FlowFV_base<freal>*>(this->space);
+		if(eng) {
+			if(u->place == VEC_DEVICE) code = fvg_tvdrk_solve(eng->engine_flow(), u->dev, this->order, cfl, finaltime, 0, &nsteps, &phytime);
+			else {
+				DeviceScratch du(u->size(), u->host.data());
+				code = fvg_tvdrk_solve(eng->engine_flow(), du.p, this->order, cfl, finaltime, 0, &nsteps, &phytime);
+				if(code == FVG_OK || code == FVG_ERR_NUMERICAL) du.download(u->host.data());
+			}
+		}
+		else code = generic_loop(u, finaltime);
+		this->walltime += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		this->cputime += (double)clock()/(double)CLOCKS_PER_SEC - c0;
+		if(code == FVG_ERR_NUMERICAL) throw Numerical_error("TVDRK solver diverged - dtmin is Nan or inf!");
+		fvg_throw(code, "TVDRKSolver::solve");
+		std::cout << " TVDRKSolver: solve(): Done, steps = " << nsteps << ", phy time = " << phytime << "\n\n";
+		std::cout << " TVDRKSolver: solve(): Time taken by ODE solver:\n";
+		std::cout << "                                   CPU time = " << this->cputime << ", wall time = " << this->walltime << std::endl << std::endl;
+		if(!this->logfile.empty()) {
+			// the reference appends threads, wall and CPU time to the log file (aodesolver.cpp:769-771); 0 threads = no OpenMP
+			std::ofstream outf(this->logfile, std::ofstream::app);
+			outf << "\t" << 0 << "\t" << this->walltime << "\t" << this->cputime << "\n";
+		}
+		return 0;
+	}
+
+	int numSteps() const { return nsteps; }
+	double physicalTime() const { return phytime; }
+protected:
+	const double cfl;
+	std::vector<double> tvdcoeffs;       ///< [order][3]
+private:
+	int nsteps; double phytime;
+
+	int generic_loop(Vec u, const freal finaltime) {
+		const UMesh<freal,NDIM> *const m = this->space->mesh();
+		if(u->place != VEC_HOST) return FVG_ERR_UNSUPPORTED;
+		const fint n = m->gnelem();
+		Vec us = nullptr, r = nullptr, dt = nullptr;
+		VecDuplicate(u, &us); VecDuplicate(u, &r); VecCreateBlocked(n, 0, 1, VEC_HOST, &dt);
+		us->host = u->host;
+		int code = FVG_OK;
+		nsteps = 0; phytime = 0.0;
+		while(phytime <= finaltime - 1e-12 && code == FVG_OK) {
+			double dtmin = 0.0;
+			for(int istage = 0; istage < this->order && code == FVG_OK; istage++) {
+				VecSet(r, 0.0);
+				const int ierr = this->space->compute_residual(us, r, true, dt);
+				if(ierr) { code = ierr; break; }
+				if(istage == 0) {
+					dtmin = n > 0 ? dt->host[0] : 0.0;
+					for(fint i = 0; i < n; i++) { if(!(dt->host[i] == dt->host[i])) dtmin = dt->host[i]; else if(dt->host[i] < dtmin) dtmin = dt->host[i]; }
+				}
+				if(!std::isfinite(dtmin)) { code = FVG_ERR_NUMERICAL; break; }
+				const double a = tvdcoeffs[3*istage], b = tvdcoeffs[3*istage+1], c = tvdcoeffs[3*istage+2];
+				for(fint i = 0; i < n; i++)
+					for(int k = 0; k < nvars; k++) {
+						const size_t j = (size_t)i*nvars + k;
+						us->host[j] = a*u->host[j] + b*us->host[j] + c*dtmin*cfl/m->garea(i)*r->host[j];
+					}
+			}
+			if(code != FVG_OK) break;
+			u->host = us->host;
+			nsteps++;
+			phytime += dtmin*cfl;
+		}
+		VecDestroy(&us); VecDestroy(&r); VecDestroy(&dt);
 		return code;
 	}
 };

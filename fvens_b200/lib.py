@@ -374,6 +374,15 @@ class FlowFV:
             check(code)
         return code, steps.value, hist[:steps.value].copy()
 
+    def solve_tvdrk(self, u, order, cfl, finaltime, maxsteps=0):
+        """TVDRKSolver::solve as an SSP Runge-Kutta scheme (fvg_tvdrk_solve). Returns (status code, steps, time)."""
+        steps = C.c_int(0); time = C.c_double(0)
+        code = load().fvg_tvdrk_solve(self._h, _ptr(u), int(order), C.c_double(cfl), C.c_double(finaltime), int(maxsteps),
+                                      C.byref(steps), C.byref(time))
+        if code not in (0, 6):
+            check(code)
+        return code, steps.value, time.value
+
     # split passes for multi-GPU drivers
     def use_buffers(self, lg, gu):
         self._bufs = (lg, gu)      # keep the tensors alive
@@ -511,3 +520,10 @@ def device_count():
     c = C.c_int(0)
     check(load().fvg_device_count(C.byref(c)))
     return c.value
+
+
+def tvdrk_coefficients(order):
+    """initialize_TVDRK_Coeffs (ode/aodesolver.cpp:45-67): [order][3] weights of u^n, the stage state and the update."""
+    c = np.zeros((int(order), 3))
+    check(load().fvg_tvdrk_coefficients(int(order), _dp(c)))
+    return c

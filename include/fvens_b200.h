@@ -298,6 +298,21 @@ int fvg_euler_step(fvg_flow *f, double *d_u, double cfl, double *d_resnorm2, voi
 int fvg_forward_euler_solve(fvg_flow *f, double *d_u, double cfl, double tol, int maxiter,
                             int check_every, int *h_steps, double *h_hist);
 
+/* TVDRKSolver (ode/aodesolver.hpp:229-258; solve: ode/aodesolver.cpp:672-785), the explicit time-accurate driver,
+ * as a strong-stability-preserving Runge-Kutta scheme of order 1, 2 or 3 in Shu-Osher form with the reference's
+ * coefficient table (initialize_TVDRK_Coeffs, ode/aodesolver.cpp:45-67):
+ *     u(0) = u;  u(i+1) = a_i u + b_i u(i) + c_i dt/area * (-r(u(i)));  u <- u(order);  time += dt
+ * dt = cfl * min over cells of the local time step at u (first stage), as the reference. Unlike the reference's loop
+ * the residual is evaluated at the STAGE state and enters with the sign the forward-Euler loop uses (the reference
+ * evaluates every stage at u and subtracts -r). Loop: while time <= finaltime - 1e-12 (the last step
+ * is not clipped, as the reference) and, if maxsteps > 0, step < maxsteps. Returns FVG_ERR_NUMERICAL when dt is not
+ * finite ("TVDRK solver diverged - dtmin is Nan or inf!"); d_u then holds the last completed step. Synchronous;
+ * d_u [ncell][4] in the caller's cell order. */
+int fvg_tvdrk_solve(fvg_flow *f, double *d_u, int order, double cfl, double finaltime, int maxsteps,
+                    int *h_steps, double *h_time);
+/* the coefficient table: h_coeffs [order][3] = (a_i, b_i, c_i) */
+int fvg_tvdrk_coefficients(int order, double *h_coeffs);
+
 /* Pointwise test hooks (host buffers; each launches a kernel - there is no CPU path):
  * InviscidFlux::get_flux (spatial/anumericalflux.hpp:32-34), FlowBC::computeGhostState
  * (spatial/abc.hpp:72-73), FlowFV::compute_viscous_flux (spatial/flow_spatial.cpp:349-395). */
