@@ -48,6 +48,27 @@ int ref_flow_forward_euler(void *hv, double cfl, double tol, int maxiter, double
 	return code;
 }
 
+/** TVDRKSolver<NVARS>(space, u, order, logfile, cfl).solve(finaltime) of the reference (ode/aodesolver.cpp:647-785), as
+ * it is: used to document what that loop computes (every stage evaluated at the step's initial state, update
+ * subtracted) next to the scheme the product implements. u [nelem][4] in/out. Returns 0, 2 on Numerical_error. */
+int ref_flow_tvdrk(void *hv, int order, double cfl, double finaltime, const char *logfile, double *u)
+{
+	RefFlow *h = static_cast<RefFlow*>(hv);
+	_p_Vec uv;
+	uv.a.assign(u, u + h->uv.a.size()); uv.nlocal = h->uv.nlocal; uv.nghost = 0;
+	int code = 0;
+	std::stringstream sink;
+	std::streambuf *const old = std::cout.rdbuf(sink.rdbuf());
+	try {
+		TVDRKSolver<NVARS> solver(h->prob.get(), &uv, order, logfile, cfl);
+		code = solver.solve(finaltime);
+	}
+	catch(Numerical_error&) { code = 2; }
+	std::cout.rdbuf(old);
+	std::copy(uv.a.begin(), uv.a.end(), u);
+	return code;
+}
+
 /// The reference's convergence-history writer (spatial/aoutput.cpp:617-636) into a string buffer
 int ref_convergence_history_text(int nsteps, const int *step, const float *rel, const float *abs_, const float *wtime,
                                  const float *cfl, char *out, int outlen)

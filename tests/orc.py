@@ -184,6 +184,12 @@ class RefSolver(RefFlow):
                                                _dp(hrel), _dp(habs))
         return code, steps.value, hrel[:steps.value], habs[:steps.value], u
 
+    def tvdrk(self, u, order, cfl, finaltime, logfile=os.devnull):
+        """The reference's TVDRKSolver::solve as it is. Returns (code, final state)."""
+        u = np.array(u, dtype=np.float64, copy=True)
+        code = self.lib.ref_flow_tvdrk(self.h, int(order), C.c_double(cfl), C.c_double(finaltime), logfile.encode(), _dp(u))
+        return code, u
+
     def history_text(self, steps, rel, abs_, wtime, cfl):
         f32 = lambda x: np.ascontiguousarray(x, dtype=np.float32)
         st = np.ascontiguousarray(steps, dtype=np.int32)

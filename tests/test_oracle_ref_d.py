@@ -64,3 +64,49 @@ def test_residual_history_writer_matches_the_reference_writer():
     args = [str(x) for row in zip(steps, rel, abs_, wt, cfl) for x in row]
     got = subprocess.run([os.path.join(ROOT, "tests", "cpp", "test_controlparser"), "--history", *args], capture_output=True, text=True).stdout
     assert got == want and want.count("\n") == 2 + len(steps)
+
+
+def _stage_table(order):
+    return lib.tvdrk_coefficients(order)
+
+
+def test_reference_tvdrk_loop_as_it_is_and_what_the_product_does_instead():
+    """TVDRKSolver::solve of the reference (ode/aodesolver.cpp:672-785), run from its own object code, equals its loop
+    restated literally: every stage takes compute_residual at the step's INITIAL state (`uvec`, :711) and the update is
+    SUBTRACTED (:734) although compute_residual leaves -r(u) (the forward-Euler loop adds it, :207). So one order-1 step
+    of the reference is exactly the mirror image of a forward-Euler step with the global time step - it integrates
+    backwards in time. The product's fvg_tvdrk_solve / TVDRKSolver keep the coefficient table, the time step
+    (cfl * min dtm of the first stage) and the loop condition, evaluate at the stage state and add the update; that
+    scheme's order of accuracy is shown in tests/cpp/test_ode_host.cpp. Here: the shared pieces (table, dt) are pinned
+    by the reference's object code."""
+    of, rs, u = setup("2dcylinderhybrid.msh", "ROE", "LEASTSQUARES", "VANALBADA")     # (no H1 hazard with MUSCL)
+    area = orc.Mesh.read(mesh_path("2dcylinderhybrid.msh")).arrays()["area"]
+    cfl = 0.4
+    r, dtm, _, _ = of.residual(u)                       # what compute_residual leaves: -r(u), local time steps
+    dt = cfl*dtm.min()
+    # order 1, one step (finaltime tiny: the loop runs once, the step is not clipped)
+    code, u1 = rs.tvdrk(u, 1, cfl, 1e-9)
+    assert code == 0
+    assert rel_err_by_component(u1, u - (dt/area)[:, None]*r) < 1e-12          # the reference: minus
+    forward = u + (dt/area)[:, None]*r                                         # the product's order-1 step: plus
+    assert rel_err_by_component(2*u - u1, forward) < 1e-12
+    # order 3, two steps: the literal loop in numpy on the oracle's residual
+    c = _stage_table(3)
+    lit = u.copy()
+    time = 0.0
+    for _ in range(2):
+        rr, dd, _, _ = of.residual(lit)
+        dts = cfl*dd.min()
+        us = lit.copy()
+        for i in range(3):
+            us = c[i, 0]*lit + c[i, 1]*us - (c[i, 2]*dts/area)[:, None]*rr     # rr: always at the step's initial state
+        lit = us
+        time += dts
+    code, u3 = rs.tvdrk(u, 3, cfl, time - 0.25*dts)
+    assert code == 0 and rel_err_by_component(u3, lit) < 1e-11
+    # ... which is not a third-order scheme: with the residual frozen, the three stages collapse to ONE Euler-like step
+    # of weight sum_i (prod of later b's) c_i = 1 in the wrong direction
+    rr, dd, _, _ = of.residual(u)
+    one = u - (cfl*dd.min()/area)[:, None]*rr
+    code, u3_1 = rs.tvdrk(u, 3, cfl, 1e-9)
+    assert rel_err_by_component(u3_1, one) < 1e-12
