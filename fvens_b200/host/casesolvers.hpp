@@ -417,5 +417,19 @@ protected:
 	const FlowParserOptions opts;
 };
 
+/// Reference: UnsteadyFlowCase (utilities/casesolvers.hpp:212-220, casesolvers.cpp:422-445): only TVDRK exists
+class UnsteadyFlowCase {
+public:
+	explicit UnsteadyFlowCase(const FlowParserOptions& options) : opts(options) {}
+
+	int execute(const Spatial<freal,NVARS> *const prob, Vec u) const {
+		if(opts.time_integrator != "TVDRK") throw UnsupportedOptionError("Nothing but TVDRK is implemented yet!");
+		TVDRKSolver<NVARS> time(prob, u, opts.time_order, opts.logfile, opts.phy_cfl);
+		return time.solve(opts.final_time);
+	}
+protected:
+	const FlowParserOptions opts;
+};
+
 }
 #endif

@@ -9,6 +9,8 @@
  * Run by tests/test_ode_host.py.
  */
 #include "../../fvens_b200/host/fvens_b200.hpp"
+#include "../../fvens_b200/host/controlparser.hpp"
+#include "../../fvens_b200/host/casesolvers.hpp"
 #include <cstdio>
 
 using namespace fvens;
@@ -115,6 +117,19 @@ int main(int argc, char **argv)
 		CHECK(line.compare(0, 5, "case\t") == 0 && tabs == 3, "log line: <tab>threads<tab>wall<tab>cpu appended");
 		const std::tuple<double,double> rt = time.getRunTimes();
 		CHECK(std::get<0>(rt) >= 0 && std::get<1>(rt) >= 0, "run times");
+		VecDestroy(&u);
+	}
+	// UnsteadyFlowCase::execute (utilities/casesolvers.cpp:429-445): TVDRK with the control file's order, CFL and final time
+	{
+		DecaySpatial sp(&m, 0.02);
+		Vec u = nullptr; createSystemVector(&m, NVARS, &u); VecSet(u, 1.0);
+		FlowParserOptions o;
+		o.time_integrator = "TVDRK"; o.time_order = 2; o.phy_cfl = 0.5; o.final_time = 0.1; o.logfile = "";
+		CHECK(UnsteadyFlowCase(o).execute(&sp, u) == 0 && sp.nevals == 20 && u->host[0] < 1.0, "UnsteadyFlowCase: 10 steps of order 2");
+		o.time_integrator = "BDF";
+		bool threw = false;
+		try { UnsteadyFlowCase(o).execute(&sp, u); } catch(UnsupportedOptionError&) { threw = true; }
+		CHECK(threw, "only TVDRK exists");
 		VecDestroy(&u);
 	}
 	std::printf(nfail ? "FAILED (%d)\n" : "ALL PASSED\n", nfail);
