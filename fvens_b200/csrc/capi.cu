@@ -243,6 +243,14 @@ int fvg_umesh_read(const char *path, fvg_umesh **out)
 	} catch(std::exception &e) { set_error(e.what()); return FVG_ERR_IO; }
 }
 
+int fvg_umesh_write_gmsh2(const fvg_umesh *m, const char *path)
+{
+	if(!m || !path) { set_error("fvg_umesh_write_gmsh2: null argument"); return FVG_ERR_INVALID; }
+	try { m->m.writeGmsh2(path); }
+	catch(std::exception &e) { set_error(e.what()); return FVG_ERR_IO; }
+	return 0;
+}
+
 int fvg_umesh_from_arrays(int npoin, const double *coords, int nelem, const int *nnode,
                           const int *inpoel, int nbface, const int *bface, fvg_umesh **out)
 {

@@ -430,6 +430,41 @@ void UMesh<scalar,ndim>::compute_periodic_map(const int bcm, const int axis)
 		}
 }
 
+/// Gmsh 2.2 ASCII: nodes with a zero z coordinate; boundary faces first (line = type 1), then cells (triangle = 2,
+/// quadrangle = 3). Gmsh wants at least two tags per element: a missing second tag is 1 + the last physical tag
+/// (1 when there is no tag at all), so that different physical groups keep different elementary ids.
+template <typename scalar, int ndim>
+void UMesh<scalar,ndim>::writeGmsh2(const std::string mfile) const
+{
+	std::ofstream out(mfile);
+	if(!out) throw std::runtime_error("UMesh: writeGmsh2(): cannot open " + mfile + " for writing");
+	out.precision(20);
+	out << "$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n" << npoin << '\n';
+	for(fint p = 0; p < npoin; p++)
+		out << p+1 << ' ' << coords[(size_t)p*ndim] << ' ' << coords[(size_t)p*ndim+1] << ' ' << 0.0 << '\n';
+	out << "$EndNodes\n$Elements\n" << nelem + nbface << '\n';
+
+	const auto tags = [&out](const int *const t, const int nt) {
+		out << ' ' << std::max(nt, 2);
+		for(int k = 0; k < nt; k++) out << ' ' << t[k];
+		for(int k = nt; k < 2; k++) out << ' ' << (nt == 0 ? 1 : 1 + t[nt-1]);
+	};
+	const int bw = nnofa + nbtag;
+	for(fint f = 0; f < nbface; f++) {
+		out << f+1 << ' ' << (nnofa == 3 ? 8 : 1);
+		tags(&bface[(size_t)f*bw] + nnofa, nbtag);
+		for(int k = 0; k < nnofa; k++) out << ' ' << bface[(size_t)f*bw+k] + 1;
+		out << '\n';
+	}
+	for(fint e = 0; e < nelem; e++) {
+		out << nbface+e+1 << ' ' << (nnode[e] == 3 ? 2 : 3);
+		tags(ndtag ? &vol_regions[(size_t)e*ndtag] : nullptr, ndtag);
+		for(int k = 0; k < nnode[e]; k++) out << ' ' << inpoel[(size_t)e*maxnnode+k] + 1;
+		out << '\n';
+	}
+	out << "$EndElements\n";
+}
+
 template class UMesh<freal,NDIM>;
 
 UMesh<freal,NDIM> constructMesh(const std::string mesh_path)

@@ -124,6 +124,36 @@ inline void writeScalarsVectorToVtu_PointData(const std::string& fname, const UM
 	std::cout << "Vtu file written.\n";
 }
 
+/// Reference: writeMeshToVtu (spatial/aoutput.cpp:557-615): the grid alone. The reference writes the cell offsets as
+/// nnode(i)*(i+1), which is the running node count only when all cells have the same type; the running count is
+/// written here (same file for all-triangle and all-quadrangle meshes, a readable one for hybrid meshes).
+inline void writeMeshToVtu(const std::string& fname, const UMesh<freal,NDIM>& m)
+{
+	std::cout << "Writing vtu output...\n";
+	std::ofstream out(fname);
+	if(!out) throw std::runtime_error("cannot open " + fname + " for writing");
+	out << std::setprecision(10);
+	out << "<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n";
+	out << "\t<Piece NumberOfPoints=\"" << m.gnpoin() << "\" NumberOfCells=\"" << m.gnelem() << "\">\n";
+	out << "\t\t<Points>\n\t\t<DataArray type=\"Float64\" NumberOfComponents=\"3\" Format=\"ascii\">\n";
+	for(fint i = 0; i < m.gnpoin(); i++) out << "\t\t\t" << m.gcoords(i,0) << " " << m.gcoords(i,1) << " " << 0.0 << '\n';
+	out << "\t\t</DataArray>\n\t\t</Points>\n\t\t<Cells>\n";
+	out << "\t\t\t<DataArray type=\"UInt32\" Name=\"connectivity\" Format=\"ascii\">\n";
+	for(fint i = 0; i < m.gnelem(); i++) {
+		out << "\t\t\t\t";
+		for(int j = 0; j < m.gnnode(i); j++) out << m.ginpoel(i,j) << " ";
+		out << '\n';
+	}
+	out << "\t\t\t</DataArray>\n\t\t\t<DataArray type=\"UInt32\" Name=\"offsets\" Format=\"ascii\">\n";
+	fint nodes = 0;
+	for(fint i = 0; i < m.gnelem(); i++) { nodes += m.gnnode(i); out << "\t\t\t\t" << nodes << '\n'; }
+	out << "\t\t\t</DataArray>\n\t\t\t<DataArray type=\"Int32\" Name=\"types\" Format=\"ascii\">\n";
+	for(fint i = 0; i < m.gnelem(); i++) out << "\t\t\t\t" << (m.gnnode(i) == 3 ? 5 : 9) << '\n';
+	out << "\t\t\t</DataArray>\n\t\t</Cells>\n\t</Piece>\n</UnstructuredGrid>\n</VTKFile>";
+	out.close();
+	std::cout << "Vtu file written.\n";
+}
+
 // ---------------------------------------------------------------------------------------- output on host arrays
 
 /// Area-weighted cell->point averaging, then density, Mach number, pressure, temperature and velocity

@@ -98,6 +98,8 @@ public:
 	fint gmaxnfael() const { return maxnfael; }
 	std::vector<fint> getConnectivityGlobalIndices() const;
 
+	/// Writes the mesh as Gmsh 2.2 ASCII (reference: mesh.cpp:205-286; the job of utilities/convertformat.cpp)
+	void writeGmsh2(const std::string mfile) const;
 	void correctBoundaryFaceOrientation();
 	void scoords(const fint pointno, const int dim, const scalar value) {
 		assert(pointno < npoin); assert(dim < ndim);

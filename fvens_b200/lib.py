@@ -146,6 +146,10 @@ class UMesh:
         check(load().fvg_umesh_read(str(path).encode(), C.byref(h)))
         return cls(h)
 
+    def write_gmsh2(self, path):
+        """UMesh::writeGmsh2: Gmsh 2.2 ASCII (the conversion utilities/convertformat.cpp does)."""
+        check(load().fvg_umesh_write_gmsh2(self._h, str(path).encode()))
+
     @classmethod
     def from_arrays(cls, coords, nnode, inpoel, bface):
         coords = np.ascontiguousarray(coords, dtype=np.float64)

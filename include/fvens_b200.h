@@ -60,6 +60,9 @@ int fvg_umesh_read(const char *path, fvg_umesh **out);
  * bface [nbface][3] = node0, node1, marker. */
 int fvg_umesh_from_arrays(int npoin, const double *coords, int nelem, const int *nnode,
                           const int *inpoel, int nbface, const int *bface, fvg_umesh **out);
+/* UMesh::writeGmsh2 (mesh/mesh.cpp:205-286): Gmsh 2.2 ASCII, what utilities/convertformat.cpp produces from any
+ * readable format (e.g. SU2 -> msh). */
+int fvg_umesh_write_gmsh2(const fvg_umesh *m, const char *path);
 void fvg_umesh_destroy(fvg_umesh *m);
 /* UMesh::reorder_cells (mesh/mesh.cpp:85-99) followed by the topology/metric rebuild of
  * preprocessMesh (mesh/ameshutils.cpp:60-100): new cell i = old cell perm[i]. */

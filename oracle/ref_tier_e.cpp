@@ -160,6 +160,46 @@ void* ref_e_restrict_to_rank(void *hv, const int *dist, int nranks, int rank)
 	return h;
 }
 
+/// The body of the reference's utilities/convertformat.cpp main (the file itself is a program, so its three statements
+/// are restated): readMesh -> UMesh(md) -> writeGmsh2 | writeMeshToVtu, no preprocessing in between
+int ref_e_convertformat(const char *inmesh, const char *outmesh, const char *outformat)
+{
+	std::stringstream sink;
+	std::streambuf *const old = std::cout.rdbuf(sink.rdbuf());
+	int rc = 0;
+	try {
+		const MeshData md = readMesh(inmesh);
+		const UMesh<freal,NDIM> m(md);
+		if(std::string(outformat) == "msh") m.writeGmsh2(outmesh);
+		else if(std::string(outformat) == "vtu") writeMeshToVtu(outmesh, m);
+		else rc = -1;
+	} catch(std::exception&) { rc = 1; }
+	std::cout.rdbuf(old);
+	return rc;
+}
+
+/// writeMeshToVtu of the reference (spatial/aoutput.cpp:557-615)
+int ref_e_write_mesh_vtu(void *hv, const char *path)
+{
+	RefCase *h = static_cast<RefCase*>(hv);
+	std::stringstream sink;
+	std::streambuf *const old = std::cout.rdbuf(sink.rdbuf());
+	writeMeshToVtu(path, *h->m);
+	std::cout.rdbuf(old);
+	return 0;
+}
+
+/// UMesh::writeGmsh2 of the reference (mesh/mesh.cpp:205-286)
+int ref_e_write_gmsh2(void *hv, const char *path)
+{
+	RefCase *h = static_cast<RefCase*>(hv);
+	std::stringstream sink;
+	std::streambuf *const old = std::cout.rdbuf(sink.rdbuf());
+	h->m->writeGmsh2(path);
+	std::cout.rdbuf(old);
+	return 0;
+}
+
 /// number of connectivity faces; glob [nelem] global cell ids; conn [nconn][5] = gconnface(i, 0..4)
 int ref_e_connectivity(void *hv, int *glob, int *conn)
 {

@@ -209,6 +209,21 @@ def have_ref_e():
     return os.path.exists(REFE_PATH)
 
 
+def _load_ref_e():
+    global _refe
+    if _refe is None:
+        _refe = C.CDLL(REFE_PATH)
+        _refe.ref_e_mesh_read.restype = C.c_void_p
+        _refe.ref_e_mesh_from_arrays.restype = C.c_void_p
+        _refe.ref_e_restrict_to_rank.restype = C.c_void_p
+    return _refe
+
+
+def ref_convertformat(inmesh, outmesh, fmt):
+    """The reference's utilities/convertformat.cpp (tier E)."""
+    return _load_ref_e().ref_e_convertformat(str(inmesh).encode(), str(outmesh).encode(), fmt.encode())
+
+
 class RefCase:
     """Tier E: the reference's own UMesh (readers, topology, metrics), FlowFV, explicit solver and output unit, all
     compiled from its unmodified sources (oracle/ref_tier_e.cpp). No stand-in for the mesh."""
@@ -223,12 +238,7 @@ class RefCase:
 
     @staticmethod
     def _lib():
-        global _refe
-        if _refe is None:
-            _refe = C.CDLL(REFE_PATH)
-            _refe.ref_e_mesh_read.restype = C.c_void_p
-            _refe.ref_e_mesh_from_arrays.restype = C.c_void_p
-        return _refe
+        return _load_ref_e()
 
     lib = property(lambda self: RefCase._lib())
 
@@ -254,6 +264,12 @@ class RefCase:
         self.lib.ref_e_mesh_get(self.h, _dp(d["coords"]), _ip(d["inpoel"]), _ip(d["nnode"]), _ip(d["bface"]), _ip(d["esuel"]),
                                 _ip(d["elemface"]), _ip(d["intfac"]), _ip(d["btags"]), _dp(d["facemetric"]), _dp(d["area"]))
         return d
+
+    def write_gmsh2(self, path):
+        self.lib.ref_e_write_gmsh2(self.h, str(path).encode())
+
+    def write_mesh_vtu(self, path):
+        self.lib.ref_e_write_mesh_vtu(self.h, str(path).encode())
 
     def trivial_partition(self, nranks):
         """cell -> rank of the reference's TrivialReplicatedGlobalMeshPartitioner."""

@@ -4,11 +4,14 @@ compiled from its unmodified sources without any stand-in for the mesh (oracle/r
 oracle (oracle/orc_mesh.hpp, orc_spatial.hpp), the checker of every GPU parity test:
   mesh arrays: integers bit for bit, metrics to round-off, for every fixture mesh (Gmsh 2 and SU2) and a synthetic one;
   residual + time steps from the mesh FILE: 1e-12; 40 forward-Euler steps: 1e-10; Cl / Cd / entropy norm: 1e-10."""
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
 import orc
-from common import mesh_path, rel_err_by_component, INVISCID_BCS, VISCOUS_BCS
+from common import ROOT, mesh_path, rel_err_by_component, INVISCID_BCS, VISCOUS_BCS
 from fvens_b200 import lib, synth
 
 pytestmark = pytest.mark.skipif(not orc.have_ref_e(), reason="oracle/_ref/libfvens_ref_e.so not built (needs /root/reference)")
@@ -211,3 +214,54 @@ def test_product_subdomains_against_the_reference_partitioner_on_a_hilbert_parti
         assert np.array_equal(ids[:dm.ncell], glob) and (part[glob] == r).all()
         assert set(ids[dm.ncell:].tolist()) == set(conn[:, 3].tolist()) and len(conn) >= dm.nghost > 0
         assert all(part[c] == rk for rk, c in zip(conn[:, 2], conn[:, 3]))
+
+
+@pytest.mark.parametrize("mesh", ["testhybrid.msh", "2dcylinderhybrid.msh", "NACA0012_inv.su2", "NACA0012_lam_hybrid_1.msh", "squarecoarse.msh"])
+def test_gmsh_writer_against_the_reference_writer(mesh, tmp_path):
+    """UMesh::writeGmsh2 (mesh/mesh.cpp:205-286; what utilities/convertformat.cpp produces, e.g. SU2 -> msh): the host
+    layer's file equals the reference's byte for byte, and reading it back gives the same mesh."""
+    a, b = str(tmp_path / "ref.msh"), str(tmp_path / "own.msh")
+    orc.RefCase.read(mesh_path(mesh)).write_gmsh2(a)
+    um = lib.UMesh.read(mesh_path(mesh))
+    um.write_gmsh2(b)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    back = lib.UMesh.read(b).arrays()
+    orig = um.arrays()
+    for k in ("nnode", "inpoel", "esuel", "intfac"):
+        assert np.array_equal(back[k], orig[k]), k
+    # an SU2 mesh has one tag per boundary face; the file carries the second one Gmsh requires
+    assert np.array_equal(back["btags"][:, 0], orig["btags"][:, 0])
+    assert np.array_equal(back["coords"], orig["coords"])           # 20 significant digits: exact round trip
+    with pytest.raises(lib.FvgError):
+        um.write_gmsh2(str(tmp_path / "no" / "such" / "dir.msh"))
+
+
+CONVERT = os.path.join(ROOT, "tests", "cpp", "convertformat")
+
+
+@pytest.mark.parametrize("mesh", ["NACA0012_inv.su2", "squarecoarse.msh", "2dcylinderhybrid.msh"])
+def test_convertformat_program(mesh, tmp_path):
+    """utilities/convertformat.cpp: <in> <out> msh|vtu. msh: the reference writer's bytes. vtu (writeMeshToVtu,
+    spatial/aoutput.cpp:557-615): the reference's bytes on single-cell-type meshes; on a hybrid mesh the reference's
+    `offsets` array is nnode(i)*(i+1) instead of the running node count, every other line is the same."""
+    a, b = str(tmp_path / "ref"), str(tmp_path / "own")
+    r = subprocess.run([CONVERT, mesh_path(mesh), b + ".msh", "msh"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert orc.ref_convertformat(mesh_path(mesh), a + ".msh", "msh") == 0
+    assert open(a + ".msh", "rb").read() == open(b + ".msh", "rb").read()
+    r = subprocess.run([CONVERT, mesh_path(mesh), b + ".vtu", "vtu"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert orc.ref_convertformat(mesh_path(mesh), a + ".vtu", "vtu") == 0
+    la, lb = open(a + ".vtu").read().split("\n"), open(b + ".vtu").read().split("\n")
+    nnode = lib.UMesh.read(mesh_path(mesh)).arrays()["nnode"]
+    if len(set(nnode.tolist())) == 1:
+        assert la == lb
+    else:
+        assert len(la) == len(lb)
+        i0 = lb.index('\t\t\t<DataArray type="UInt32" Name="offsets" Format="ascii">') + 1
+        assert la[:i0] == lb[:i0] and la[i0+len(nnode):] == lb[i0+len(nnode):]
+        assert [int(x) for x in lb[i0:i0+len(nnode)]] == np.cumsum(nnode).tolist()
+        assert [int(x) for x in la[i0:i0+len(nnode)]] == (nnode*np.arange(1, len(nnode)+1)).tolist()
+    # usage / bad format
+    assert subprocess.run([CONVERT, mesh_path(mesh)], capture_output=True).returncode == 2
+    assert subprocess.run([CONVERT, mesh_path(mesh), b + ".x", "stl"], capture_output=True).returncode != 0
