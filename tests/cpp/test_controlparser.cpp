@@ -58,10 +58,10 @@ int main(int argc, char *argv[])
 		            std::isfinite(o.Pr) ? std::to_string(o.Pr).c_str() : "null", (int)o.useconstvisc);
 		std::printf("\"invflux\": %s, \"invfluxjac\": %s, \"gradient\": %s, \"limiter\": %s, \"limiter_param\": %.17g, \"order2\": %d, "
 		            "\"pseudotimetype\": %s, \"initcfl\": %.17g, \"endcfl\": %.17g, \"tolerance\": %.17g, \"maxiter\": %d, \"usestarter\": %d, "
-		            "\"firstinitcfl\": %.17g, \"firsttolerance\": %.17g, \"firstmaxiter\": %d, \"sim_type\": %s, \"surfnameprefix\": %s, "
+		            "\"firstinitcfl\": %.17g, \"firstendcfl\": %.17g, \"firsttolerance\": %.17g, \"firstmaxiter\": %d, \"sim_type\": %s, \"surfnameprefix\": %s, "
 		            "\"vol_output_reqd\": %s, ",
 		            q(o.invflux).c_str(), q(o.invfluxjac).c_str(), q(o.gradientmethod).c_str(), q(o.limiter).c_str(), o.limiter_param, (int)o.order2,
-		            q(o.pseudotimetype).c_str(), o.initcfl, o.endcfl, o.tolerance, o.maxiter, (int)o.usestarter, o.firstinitcfl, o.firsttolerance,
+		            q(o.pseudotimetype).c_str(), o.initcfl, o.endcfl, o.tolerance, o.maxiter, (int)o.usestarter, o.firstinitcfl, o.firstendcfl, o.firsttolerance,
 		            o.firstmaxiter, q(o.sim_type).c_str(), q(o.surfnameprefix).c_str(), q(o.vol_output_reqd).c_str());
 		std::printf("\"lwalls\": [");
 		for(size_t i = 0; i < o.lwalls.size(); i++) std::printf("%s%d", i ? ", " : "", o.lwalls[i]);

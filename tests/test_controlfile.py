@@ -87,3 +87,22 @@ def test_fvens_steady_rejects_what_it_cannot_run(tmp_path):
     assert r.returncode == 2 and "control file" in r.stderr
     r = subprocess.run([STEADY, os.path.join(CTRL, "naca0012-transonic-explicit.ctrl"), "--bogus"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 2
+
+
+def test_reference_parse_test_against_its_testdata():
+    """tests/utils/testparse.cpp (Utils_ParseControlInfo): inv-explicit.ctrl parsed and compared, field by field and
+    in the order of parse_solution_file, with inv-explicit.testdata (both files are the reference's fixtures)."""
+    o = parse("inv-explicit.ctrl")
+    t = open(os.path.join(CTRL, "inv-explicit.testdata")).read().split()
+    it = iter(t)
+    assert o["meshfile"] == next(it) and o["vtu"] == next(it) and o["logfile"] == next(it) and o["lognres"] == int(next(it))
+    assert o["flowtype"] == next(it) and o["gamma"] == float(next(it))
+    assert o["alpha"] == float(next(it))*math.pi/180.0 and o["Minf"] == float(next(it))
+    assert o["bcs"][0] == dict(tag=int(next(it)), type=BC["slipwall"], vals=[])
+    assert o["bcs"][1] == dict(tag=int(next(it)), type=BC["farfield"], vals=[])
+    assert len(o["lwalls"]) == int(next(it)) and o["surfnameprefix"] == next(it) and o["vol_output_reqd"] == next(it)
+    assert o["sim_type"] == next(it) and o["invflux"] == next(it) and o["gradient"] == next(it) and o["limiter"] == next(it)
+    assert o["pseudotimetype"] == next(it)
+    assert (o["initcfl"], o["endcfl"], o["tolerance"], o["maxiter"]) == (float(next(it)), float(next(it)), float(next(it)), int(next(it)))
+    assert (o["firstinitcfl"], o["firstendcfl"], o["firsttolerance"], o["firstmaxiter"]) == (float(next(it)), float(next(it)), float(next(it)), int(next(it)))
+    assert next(it, None) is None
