@@ -5,6 +5,10 @@ tag=${1:-rXX}
 out=gpurun_out
 mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/${tag}_smi.txt 2>&1
+# tests written after round 1's GPU minutes were spent run first and on their own, so that a failure there is seen
+# without hiding the rest of the suite
+( time timeout 600 python -m pytest tests/test_unsteady_gpu.py tests/test_order_of_accuracy_gpu.py -m gpu -q ) > $out/${tag}_pytest_gpu_new.log 2>&1
+echo "pytest rc=$?" >> $out/${tag}_pytest_gpu_new.log
 ( time timeout 600 python -m pytest tests -m gpu -x -q ) > $out/${tag}_pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> $out/${tag}_pytest_gpu.log
 timeout 600 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
@@ -15,4 +19,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'cell_kernel|face_kernel' -s 6 -c 2 \
    -f -o $out/${tag}_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $out/${tag}_full.log 2>&1
 python tools/ncu_summary.py $out/${tag}_full.ncu-rep > $out/${tag}_ncu_summary.txt 2>&1
-tail -3 $out/${tag}_pytest_gpu.log; cat $out/${tag}_bench_n1.json; tail -2 $out/${tag}_bench_n1.err
+tail -3 $out/${tag}_pytest_gpu_new.log; tail -3 $out/${tag}_pytest_gpu.log; cat $out/${tag}_bench_n1.json; tail -2 $out/${tag}_bench_n1.err
