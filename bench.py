@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--cpu-cells", type=float, default=1.0e6, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--partition", default="sfc", choices=["sfc", "rcb"],
+                    help="N > 1: Hilbert-curve chunks (default, the measured configuration) or recursive coordinate bisection")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -228,7 +230,7 @@ def main():
             fl.compute_residual(du, res, True, dtm, accumulate=False, stream=stream)
     else:
         from fvens_b200.dist import DistFlow
-        part = lib.partition_sfc(um, world)
+        part = (lib.partition_rcb if args.partition == "rcb" else lib.partition_sfc)(um, world)
         df = DistFlow(um, part, rank, world, phys, dev, reorder="none", tile_cells=args.tile, bcs=BCS, **num)
         dm, fl = df.dmesh, df.flow
         nc = df.ncell
@@ -386,7 +388,7 @@ def main():
                    "cells_on_rank0": nc, "ghost_cells_on_rank0": int(info.nghost),
                    "tile_cells": info.tile_cells, "cut_face_duplicates_rank0": info.ncut_dup,
                    "parallelism": "single GPU" if world == 1 else
-                   f"{world} GPUs, Hilbert-curve partition, one ghost layer; per evaluation: state halo, gradient pass, "
+                   f"{world} GPUs, {'coordinate-bisection' if args.partition == 'rcb' else 'Hilbert-curve'} partition, one ghost layer; per evaluation: state halo, gradient pass, "
                    f"gradient halo, face pass; halo transport: " + (("peer-mapped windows over NVLink (CUDA IPC, direct stores + flags)"
                                                   + (", received inside the consuming kernels" if df.fused_recv else ", one send+receive kernel per exchange"))
                                                  if df.halo_kind == "peer" else "NCCL all-to-all with row splits"),

@@ -844,6 +844,43 @@ int fvg_partition_sfc(const fvg_umesh *m, int nranks, int *cell_rank)
 	return 0;
 }
 
+namespace {
+/// Recursive coordinate bisection of the cells idx[lo, hi) into ranks [r0, r0 + nparts): split along the longer side
+/// of the bounding box of the cell centres, cell counts in proportion to the number of ranks on either side
+void rcb_split(const double *rc, std::vector<int> &idx, int lo, int hi, int r0, int nparts, int *cell_rank)
+{
+	if(nparts == 1) { for(int k = lo; k < hi; k++) cell_rank[idx[k]] = r0; return; }
+	double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
+	for(int k = lo; k < hi; k++)
+		for(int d = 0; d < 2; d++) {
+			const double x = rc[2*(size_t)idx[k]+d];
+			mn[d] = std::min(mn[d], x); mx[d] = std::max(mx[d], x);
+		}
+	const int ax = (mx[1] - mn[1] > mx[0] - mn[0]) ? 1 : 0;
+	const int nleft = nparts/2;
+	const int mid = lo + (int)(((long long)(hi - lo)*nleft)/nparts);
+	// ties in the coordinate are broken by the cell index, so the result does not depend on the library's nth_element
+	std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [rc, ax](const int a, const int b) {
+		const double xa = rc[2*(size_t)a+ax], xb = rc[2*(size_t)b+ax];
+		return xa < xb || (xa == xb && a < b);
+	});
+	rcb_split(rc, idx, lo, mid, r0, nleft, cell_rank);
+	rcb_split(rc, idx, mid, hi, r0 + nleft, nparts - nleft, cell_rank);
+}
+}
+
+int fvg_partition_rcb(const fvg_umesh *m, int nranks, int *cell_rank)
+{
+	if(!m || !cell_rank || nranks < 1) { set_error("fvg_partition_rcb: bad argument"); return FVG_ERR_INVALID; }
+	const int n = m->m.gnelem();
+	std::vector<double> rc(2*(size_t)n);
+	m->m.compute_cell_centres(rc.data());
+	std::vector<int> idx(n);
+	for(int i = 0; i < n; i++) idx[i] = i;
+	rcb_split(rc.data(), idx, 0, n, 0, nranks, cell_rank);
+	return 0;
+}
+
 int fvg_halo_pack(const fvg_mesh *m, const double *d_src, int width, double *d_sendbuf, void *stream)
 {
 	if(!m || !d_src || (m->d.nsend > 0 && !d_sendbuf) || width < 1) { set_error("fvg_halo_pack: bad argument"); return FVG_ERR_INVALID; }

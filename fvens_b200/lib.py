@@ -520,6 +520,13 @@ def partition_sfc(umesh, nranks):
     return part
 
 
+def partition_rcb(umesh, nranks):
+    """cell -> rank map by recursive coordinate bisection of the cell centres (balanced to one cell for any nranks)."""
+    part = np.zeros(umesh.nelem, dtype=np.int32)
+    check(load().fvg_partition_rcb(umesh._h, int(nranks), _ip(part)))
+    return part
+
+
 def device_count():
     c = C.c_int(0)
     check(load().fvg_device_count(C.byref(c)))

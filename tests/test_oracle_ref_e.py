@@ -199,13 +199,14 @@ def test_reference_partitioner_reproduces_its_goldens_and_the_product_agrees():
         assert all(dist[g] == owner[int(g)] for g in ids[dm.ncell:])
 
 
+@pytest.mark.parametrize("partition", [lib.partition_sfc, lib.partition_rcb])
 @pytest.mark.parametrize("nranks", [2, 5])
-def test_product_subdomains_against_the_reference_partitioner_on_a_hilbert_partition(nranks):
-    """The space-filling-curve partition bench.py uses, restricted to each rank by the reference's own
+def test_product_subdomains_against_the_reference_partitioner_on_a_hilbert_partition(nranks, partition):
+    """The space-filling-curve partition bench.py uses and the coordinate-bisection one, restricted to each rank by the reference's own
     restrictMeshToPartitions and by the product: own cells (ascending global index), ghost sets, owners."""
     arrs = synth.bump_channel(40, 16)
     um = lib.UMesh.from_arrays(*arrs)
-    part = lib.partition_sfc(um, nranks)
+    part = partition(um, nranks)
     gm = orc.RefCase.from_arrays(*arrs)
     for r in range(nranks):
         glob, conn = gm.restrict_to_rank(part, nranks, r).connectivity()

@@ -14,19 +14,21 @@ from common import mesh_path
 from fvens_b200 import lib, synth
 
 
-def build_parts(um, nranks, reorder="hilbert", tile=64):
-    part = lib.partition_sfc(um, nranks)
+def build_parts(um, nranks, reorder="hilbert", tile=64, partitioner="sfc"):
+    part = (lib.partition_rcb if partitioner == "rcb" else lib.partition_sfc)(um, nranks)
     return part, [lib.DeviceMesh(um, reorder=reorder, tile_cells=tile, device=-2, cell_rank=part, rank=r, nranks=nranks)
                   for r in range(nranks)]
 
 
+@pytest.mark.parametrize("partitioner", ["sfc", "rcb"])
 @pytest.mark.parametrize("nranks", [2, 3, 8])
 @pytest.mark.parametrize("mesh", ["2dcylinderhybrid.msh", "bump"])
-def test_subdomains_are_consistent(mesh, nranks):
+def test_subdomains_are_consistent(mesh, nranks, partitioner):
     um = lib.UMesh.from_arrays(*synth.bump_channel(40, 15)) if mesh == "bump" else lib.UMesh.read(mesh_path(mesh))
     a = um.arrays()
-    part, dms = build_parts(um, nranks)
-    assert np.bincount(part, minlength=nranks).min() >= um.nelem//nranks - 1      # balanced
+    part, dms = build_parts(um, nranks, partitioner=partitioner)
+    counts = np.bincount(part, minlength=nranks)
+    assert counts.min() >= um.nelem//nranks - 1 and counts.max() <= um.nelem//nranks + 1      # balanced
     owned = np.concatenate([dm.permutation()[:dm.ncell] for dm in dms])
     assert sorted(owned.tolist()) == list(range(um.nelem))                        # every cell owned exactly once
     nb = um.nbface
@@ -171,3 +173,28 @@ def test_tile_send_lists_are_the_halo_send_lists_grouped_by_tile(nranks):
             for p in set(seg[:, 1].tolist()):
                 rows = seg[seg[:, 1] == p, 2]
                 assert (np.diff(rows) > 0).all()
+
+
+def edge_cut(um, part):
+    a = um.arrays()
+    f = a["intfac"][um.nbface:, :2]
+    return int((part[f[:, 0]] != part[f[:, 1]]).sum())
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 5, 8])
+def test_partition_quality_edge_cut_and_balance(nranks):
+    """the in-tree partitioners are judged by edge cut and balance. On the benchmark geometry (bump
+    channel, aspect 2.67) both are balanced to one cell; recursive coordinate bisection cuts fewer faces than the
+    Hilbert-curve partition (except where the curve's own cut happens to be straight), and both stay within a small factor of the straight-cut estimate
+    (nranks - 1 cuts across the short side for strips)."""
+    nx, ny = 400, 150
+    um = lib.UMesh.from_arrays(*synth.bump_channel(nx, ny))
+    sfc, rcb = lib.partition_sfc(um, nranks), lib.partition_rcb(um, nranks)
+    for part in (sfc, rcb):
+        c = np.bincount(part, minlength=nranks)
+        assert c.max() - c.min() <= 1 and part.min() == 0 and part.max() == nranks - 1
+    cs, cr = edge_cut(um, sfc), edge_cut(um, rcb)
+    strips = (nranks - 1)*ny*4/3            # a straight cut crosses ny lattice rows; a split quad adds a diagonal
+    assert cr <= 1.15*cs and cr < 1.6*strips and cs < 3.0*strips
+    # deterministic
+    assert np.array_equal(rcb, lib.partition_rcb(um, nranks))
