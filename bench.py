@@ -187,7 +187,7 @@ def main():
         gf, ms, info = cpu_reference(args.cpu_cells, args.numerics, max(1, min(args.steps, 20)), max(1, min(args.warmup, 3)))
         line = {"impl": "reference", "metric": "Gfaces/s", "value": gf, "unit": "Gfaces/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "timed_on": info["sample"]},
                 "residual_evals_per_s": 1e3/ms,
                 "cpu_baseline": {"value": gf, "unit": "Gfaces/s", "cores": info["cores"], "kind": info["kind"],
