@@ -177,3 +177,22 @@ def perturbed_state(rc, gamma, Minf, aoa=0.0, amp=0.05, shock=False):
         vx = np.where(right, vx/rr, vx)
     E = p/(gamma-1.0) + 0.5*rho*(vx*vx + vy*vy)
     return np.ascontiguousarray(np.stack([rho, rho*vx, rho*vy, E], axis=1))
+
+
+def isentropic_vortex(rc, gamma, Minf, t=0.0, strength=0.6, sigma=0.8, clength=1.0, centre=(0.0, 0.0)):
+    """Isentropic vortex convected by the unit free stream along x, evaluated at the points rc at time t (conserved
+    variables, the reference's non-dimensionalisation: rho_inf = |v_inf| = 1, p_inf = 1/(gamma M^2)).
+    omega = strength * exp(-r^2 / (2 sigma^2 clength^2)), v = v_inf + (-y, x)/clength * omega, T/T_inf = 1 -
+    (gamma-1)/2 (M sigma)^2 omega^2, rho = T^(1/(gamma-1)), p = p_inf T^(gamma/(gamma-1)) - an exact solution of the
+    Euler equations (radial balance dp/dr = rho v_theta^2 / r). The reference's own vortex test
+    (tests/isentropic-vortex/isentropicvortex.cpp:18-43, disabled in tests/CMakeLists.txt:46, written for units with
+    c_inf = 1) has the same form without the (M sigma)^2 factor; BASELINE configs[4] / SURVEY 8d config 5."""
+    x = rc[:, 0] - centre[0] - t
+    y = rc[:, 1] - centre[1]
+    om = strength*np.exp(-(x*x + y*y)/(2.0*sigma*sigma*clength*clength))
+    th = 1.0 - 0.5*(gamma - 1.0)*(Minf*sigma)**2*om*om
+    rho = th**(1.0/(gamma - 1.0))
+    p = th**(gamma/(gamma - 1.0))/(gamma*Minf*Minf)
+    vx = 1.0 - y/clength*om
+    vy = x/clength*om
+    return np.stack([rho, rho*vx, rho*vy, p/(gamma - 1.0) + 0.5*rho*(vx*vx + vy*vy)], axis=1)

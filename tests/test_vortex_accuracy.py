@@ -1,0 +1,105 @@
+"""Order of accuracy in space and time on the convected isentropic vortex (BASELINE configs[4]):
+[-5,5]^2, n x n cells, Roe + weighted least squares + linear reconstruction, SSP Runge-Kutta (fvg_tvdrk_solve) to
+t = 1, density error against the exact solution in the area-weighted L2 norm. The reference's own vortex test is
+disabled and has no control file and its FlowBC family has no periodic member, so the boundaries are
+far-field states (the vortex is 1e-6 of its strength there). The oracle run (CPU) gives orders 2.26 / 2.20 on 32, 64,
+128 quads and 2.21 / 2.14 on jittered hybrid meshes; the GPU run must reproduce the oracle's states and orders.
+The GPU cases were written after the round's GPU minutes were spent (the file sorts last among the GPU tests)."""
+import os
+
+import numpy as np
+import pytest
+
+import orc
+from common import rel_err_by_component
+from fvens_b200 import lib, synth
+
+G, M, CFL, TFINAL = 1.4, 0.5, 0.4, 1.0
+BCS = [(t, "farfield", ()) for t in (1, 2, 3, 4)]
+
+
+def oracle_tvdrk(of, u, area, order, cfl, finaltime):
+    c = lib.tvdrk_coefficients(order)
+    u = u.copy()
+    time, step = 0.0, 0
+    while time <= finaltime - 1e-12:
+        us = u.copy()
+        for i in range(order):
+            r, dtm, _, _ = of.residual(us)
+            if i == 0:
+                dtmin = dtm.min()
+            us = c[i, 0]*u + c[i, 1]*us + (c[i, 2]*cfl*dtmin/area)[:, None]*r
+        u = us
+        step += 1
+        time += dtmin*cfl
+    return u, step, time
+
+
+def setup(n, hybrid):
+    arrs = synth.square(n, jitter=0.15 if hybrid else 0.0, tri_fraction=0.3 if hybrid else 0.0)
+    om = orc.Mesh.from_arrays(*arrs)
+    phys = lib.make_physics(G, M, 288.15, 5000.0, 0.72, 0.0, False, False)
+    of = orc.Flow(om, phys, lib.FLUX["ROE"], lib.GRAD["LEASTSQUARES"], lib.RECON["NONE"], 1.0, True, 0,
+                  [(t, lib.BC[ty], v) for (t, ty, v) in BCS])
+    rc, _, _ = of.geometry()
+    return arrs, om, phys, of, rc, om.arrays()["area"]
+
+
+def density_error(u, rc, area, t):
+    ex = synth.isentropic_vortex(rc, G, M, t)
+    return float(np.sqrt(((u[:, 0] - ex[:, 0])**2*area).sum()))
+
+
+def order(e, ncell):
+    return [np.log(e[k+1]/e[k])/np.log(np.sqrt(ncell[k]/ncell[k+1])) for k in range(len(e)-1)]
+
+
+def test_vortex_is_a_steady_solution_in_its_own_frame():
+    # residual of the exact field is the truncation error only: it falls with h^2 (interior cells)
+    norms = []
+    for n in (32, 64):
+        arrs, om, phys, of, rc, area = setup(n, False)
+        r, _, _, _ = of.residual(synth.isentropic_vortex(rc, G, M, 0.0))
+        # d(rho)/dt + div = 0 with pure convection: compare with the convective derivative -d(rho)/dx of the exact field
+        eps = 1e-6
+        drho = (synth.isentropic_vortex(rc + [eps, 0], G, M)[:, 0] - synth.isentropic_vortex(rc - [eps, 0], G, M)[:, 0])/(2*eps)
+        inner = (np.abs(rc) < 4.0).all(axis=1)
+        norms.append(np.sqrt((((r[:, 0]/area + drho)**2*area)[inner]).sum()))
+    assert norms[1] < 0.3*norms[0]
+
+
+@pytest.mark.parametrize("hybrid", [False, True])
+def test_oracle_order_of_accuracy(hybrid):
+    orc.set_threads(os.cpu_count() or 1)
+    errs, ncell = [], []
+    for n in (32, 64):
+        arrs, om, phys, of, rc, area = setup(n, hybrid)
+        u, steps, time = oracle_tvdrk(of, synth.isentropic_vortex(rc, G, M, 0.0), area, 2, CFL, TFINAL)
+        errs.append(density_error(u, rc, area, time)); ncell.append(len(area))
+        assert TFINAL <= time < TFINAL + 0.05
+    p = order(errs, ncell)[0]
+    assert abs(p - (2.21 if hybrid else 2.26)) < 0.03 and errs[1] < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hybrid,rk", [(False, 2), (True, 3)])
+def test_gpu_vortex_states_and_order(hybrid, rk):
+    import torch
+    errs, ncell = [], []
+    for n in (32, 64, 128):
+        arrs, om, phys, of, rc, area = setup(n, hybrid)
+        um = lib.UMesh.from_arrays(*arrs)
+        dm = lib.DeviceMesh(um, reorder="hilbert", tile_cells=256)
+        fl = lib.FlowFV(dm, phys, "ROE", "LEASTSQUARES", "NONE", 1.0, True, 0, BCS)
+        u0 = synth.isentropic_vortex(rc, G, M, 0.0)
+        du = torch.from_numpy(u0).cuda()
+        code, steps, time = fl.solve_tvdrk(du, rk, CFL, TFINAL)
+        u = du.cpu().numpy()
+        assert code == 0 and TFINAL <= time < TFINAL + 0.05
+        if n <= 64:
+            uo, so, to = oracle_tvdrk(of, u0, area, rk, CFL, TFINAL)
+            assert steps == so and abs(time/to - 1) < 1e-11
+            assert rel_err_by_component(u, uo) < 1e-9        # ~1500 residual evaluations of round-off
+        errs.append(density_error(u, rc, area, time)); ncell.append(len(area))
+    p = order(errs, ncell)
+    assert 1.9 < p[0] < 2.5 and 1.9 < p[1] < 2.5 and errs[2] < 3e-4
