@@ -253,6 +253,9 @@ face_kernel(const __grid_constant__ FaceArgs A)
 	int tnx = ti + G < tend ? tile_at(ti + G) : 0;
 	if(ti + G < tend) Dn = load_tile_desc(M, tnx);
 	if(tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+	pdl_launch_dependents();
+	// (PDL variant) everything above reads only the mesh; the state and gradient rows below are the previous kernels'
+	pdl_wait();
 	__syncthreads();
 	if(tid == 0) { issue_AC(D, 0); issue_B(D); }
 	// in-kernel receive: a CTA waits for the neighbours' rows once, right before it gathers the halo of its first
@@ -538,7 +541,18 @@ static int launch_one(const FaceArgs &a, cudaStream_t s)
 	if(b.tile1 < 0) b.tile1 = b.m.ntile;
 	const int nt = b.tile1 - b.tile0;
 	if(nt <= 0) return 0;
+#ifdef FVG_PDL
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3((unsigned)(nt < ctas ? nt : ctas)); cfg.blockDim = dim3(FACE_BLOCK); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	const cudaError_t el = cudaLaunchKernelEx(&cfg, face_kernel<FLUX,RECON,VISC>, b);
+	if(el != cudaSuccess) return cuda_fail(el, "face_kernel launch (PDL)", __FILE__, __LINE__);
+#else
 	face_kernel<FLUX,RECON,VISC><<<nt < ctas ? nt : ctas, FACE_BLOCK, smem, s>>>(b);
+#endif
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "face_kernel launch", __FILE__, __LINE__);
 	return 0;

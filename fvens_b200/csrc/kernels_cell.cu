@@ -70,6 +70,10 @@ cell_kernel(const CellArgs A)
 	constexpr bool NEED_NBRS = GRAD == GM_GG || GRAD == GM_WLS || LIM != LM_NONE;
 
 	if(tid == 0) mbar_init(bar, 1);
+	pdl_launch_dependents();
+	// (PDL variant) the tile descriptors above are mesh data; the state read below may be the previous kernel's output
+	// and the gradient rows written at the end are still being read by the previous face pass until it completes
+	pdl_wait();
 	__syncthreads();
 	if(tid == 0) {
 		unsigned bytes = (unsigned)nc*(32u + 16u + 16u + (GRAD == GM_WLS ? 32u : 0u)) + (LIM == LM_VENKAT ? (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u : 0u);
@@ -310,7 +314,18 @@ static int launch_cell(const CellArgs &a, cudaStream_t s)
 	}
 	const int t1 = a.tile1 < 0 ? a.m.ntile : a.tile1;
 	if(t1 <= a.tile0) return 0;
+#ifdef FVG_PDL
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3((unsigned)(t1 - a.tile0)); cfg.blockDim = dim3(CELL_BLOCK); cfg.dynamicSmemBytes = (size_t)S.total; cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	const cudaError_t el = cudaLaunchKernelEx(&cfg, cell_kernel<GRAD,LIM,PRIM_IN>, a);
+	if(el != cudaSuccess) return cuda_fail(el, "cell_kernel launch (PDL)", __FILE__, __LINE__);
+#else
 	cell_kernel<GRAD,LIM,PRIM_IN><<<t1 - a.tile0, CELL_BLOCK, S.total, s>>>(a);
+#endif
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "cell_kernel launch", __FILE__, __LINE__);
 	return 0;

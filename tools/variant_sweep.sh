@@ -1,6 +1,11 @@
 #!/bin/bash
 # Times the residual with differently-built copies of the library (launch bounds / block sizes), tile sizes and
 # environment knobs. usage: tools/variant_sweep.sh "<lib:tile[:ENV=val]> ..."   (lib = path of a .so or "default")
+# Variants are built next to the default library, e.g. the programmatic-dependent-launch build (pass B's prologue under
+# pass A's tail and the next pass A's under pass B's; compiles, PREEXIT/ACQBULK in the SASS, never run yet):
+#   make -C fvens_b200/csrc -j8 EXTRA=-DFVG_PDL OBJDIR=build_pdl TARGET=../variants_pdl.so
+#   tools/variant_sweep.sh "default:256 fvens_b200/variants_pdl.so:256"
+# and for N GPUs: FVENS_B200_LIB=$PWD/fvens_b200/variants_pdl.so torchrun ... bench.py --gpus N
 for spec in $1; do
   IFS=: read lib tile envs <<< "$spec"
   if [ "$lib" != "default" ]; then export FVENS_B200_LIB=$lib; else unset FVENS_B200_LIB; fi
