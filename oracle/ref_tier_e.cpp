@@ -160,6 +160,17 @@ void* ref_e_restrict_to_rank(void *hv, const int *dist, int nranks, int rank)
 	return h;
 }
 
+/// getCellAdjLists of the reference (mesh/meshpartitioning.cpp:376-430): the CSR graph it would hand to Scotch.
+/// Returns the number of adjacency entries; ptrs [nelem+1], store [that number] (either may be NULL).
+int ref_e_cell_adjacency(void *hv, int *ptrs, int *store)
+{
+	RefCase *h = static_cast<RefCase*>(hv);
+	const ListOfArrays<fint> loa = getCellAdjLists(*h->m);
+	if(ptrs) std::copy(loa.ptrs.begin(), loa.ptrs.end(), ptrs);
+	if(store) std::copy(loa.store.begin(), loa.store.end(), store);
+	return (int)loa.store.size();
+}
+
 /// The body of the reference's utilities/convertformat.cpp main (the file itself is a program, so its three statements
 /// are restated): readMesh -> UMesh(md) -> writeGmsh2 | writeMeshToVtu, no preprocessing in between
 int ref_e_convertformat(const char *inmesh, const char *outmesh, const char *outformat)

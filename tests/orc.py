@@ -271,6 +271,13 @@ class RefCase:
     def write_mesh_vtu(self, path):
         self.lib.ref_e_write_mesh_vtu(self.h, str(path).encode())
 
+    def cell_adjacency(self):
+        """getCellAdjLists of the reference: (ptrs [nelem+1], store)."""
+        n = self.lib.ref_e_cell_adjacency(self.h, None, None)
+        ptrs = np.zeros(self.nelem + 1, dtype=np.int32); store = np.zeros(max(n, 1), dtype=np.int32)
+        self.lib.ref_e_cell_adjacency(self.h, _ip(ptrs), _ip(store))
+        return ptrs, store[:n]
+
     def trivial_partition(self, nranks):
         """cell -> rank of the reference's TrivialReplicatedGlobalMeshPartitioner."""
         dist = np.zeros(self.nelem, dtype=np.int32)

@@ -266,3 +266,12 @@ def test_convertformat_program(mesh, tmp_path):
     # usage / bad format
     assert subprocess.run([CONVERT, mesh_path(mesh)], capture_output=True).returncode == 2
     assert subprocess.run([CONVERT, mesh_path(mesh), b + ".x", "stl"], capture_output=True).returncode != 0
+
+
+@pytest.mark.parametrize("mesh", ["testhybrid.msh", "2dcylinderhybrid.msh", "NACA0012_inv.su2"])
+def test_cell_adjacency_graph_against_the_reference(mesh):
+    """fvg_umesh_cell_adjacency = getCellAdjLists (mesh/meshpartitioning.cpp:376-430), the graph the reference would
+    hand to SCOTCH_graphBuild: same CSR, entry for entry."""
+    p0, s0 = orc.RefCase.read(mesh_path(mesh)).cell_adjacency()
+    p1, s1 = lib.UMesh.read(mesh_path(mesh)).cell_adjacency()
+    assert np.array_equal(p0, p1) and np.array_equal(s0, s1)
