@@ -1,0 +1,45 @@
+/* ORACLE - TEST INFRASTRUCTURE ONLY.
+ * Compile-and-run check of the reference-side binding (fvens_b200/host/reference_binding/flow_spatial_b200.hpp): the
+ * binding is built here against the reference's own, unmodified headers and sources (everything of tier E) and linked
+ * with libfvens_b200.so, which proves that the class in INTEGRATION.md is real code for the real FVENS. On a GPU box the
+ * reference's own SteadyForwardEulerSolver then drives the CUDA residual through it (tests/test_reference_binding.py).
+ * Built into oracle/_ref/libfvens_ref_binding.so (needs /root/reference and the product library).
+ */
+#include "ref_tier_e.cpp"
+#include "../fvens_b200/host/reference_binding/flow_spatial_b200.hpp"
+
+extern "C" {
+
+/// As ref_e_flow_create, but the Spatial object is the binding: FlowFV_B200 on the mesh of the case.
+/// Returns 0, or 1 with the message in ref_binding_error().
+static std::string binding_error;
+const char* ref_binding_error() { return binding_error.c_str(); }
+
+int ref_e_flow_create_b200(void *hv, const double *phys, const char *flux, const char *gradient, const char *recon, double limiter_param,
+                           int order2, int viscous, int const_visc, int nbc, const int *bc_tag_type, const double *bc_vals)
+{
+	RefCase *h = static_cast<RefCase*>(hv);
+	std::stringstream sink;
+	std::streambuf *const old = std::cout.rdbuf(sink.rdbuf());
+	int rc = 0;
+	try {
+		std::vector<FlowBCConfig> bcs;
+		for(int i = 0; i < nbc; i++) {
+			FlowBCConfig c;
+			c.bc_tag = bc_tag_type[2*i]; c.bc_type = static_cast<BCType>(bc_tag_type[2*i+1]);
+			c.bc_vals = {bc_vals[2*i], bc_vals[2*i+1]};
+			bcs.push_back(c);
+		}
+		const FlowPhysicsConfig pconf { phys[0], phys[1], phys[2], phys[3], phys[4], phys[5], viscous != 0, const_visc != 0, bcs };
+		const FlowNumericsConfig nconf { flux, flux, gradient, recon, limiter_param, order2 != 0 };
+		h->prob.reset(create_flowSpatialDiscretization_b200(h->m.get(), pconf, nconf));
+		const size_t ne = h->m->gnelem();
+		h->uv.a.assign(ne*NVARS, 0.0); h->uv.nlocal = (PetscInt)(ne*NVARS); h->uv.nghost = 0;
+		h->rv = h->uv;
+		h->dv.a.assign(ne, 0.0); h->dv.nlocal = (PetscInt)ne; h->dv.nghost = 0;
+	} catch(std::exception& e) { binding_error = e.what(); rc = 1; }
+	std::cout.rdbuf(old);
+	return rc;
+}
+
+}

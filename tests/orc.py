@@ -240,7 +240,7 @@ class RefCase:
     def _lib():
         return _load_ref_e()
 
-    lib = property(lambda self: RefCase._lib())
+    lib = property(lambda self: type(self)._lib())
 
     @classmethod
     def read(cls, path):
@@ -311,6 +311,21 @@ class RefCase:
                                         int(order2), int(p.viscous_sim), int(p.const_visc), len(bcs), _ip(tt), _dp(vv))
         if rc != 0:
             raise RuntimeError("reference FlowFV construction failed")
+        self.phys = p
+        return self
+
+    def flow_b200(self, p, flux, gradient, recon, limiter_param, order2, bcs):
+        """The Spatial object becomes the reference-side binding FlowFV_B200 (RefBindingCase only): compute_residual goes
+        to the GPU through libfvens_b200, everything else stays the reference's."""
+        ph = np.array([p.gamma, p.Minf, p.Tinf, p.Reinf, p.Pr, p.aoa], dtype=np.float64)
+        tt = np.array([[t, ty] for (t, ty, v) in bcs], dtype=np.int32).reshape(-1)
+        vv = np.array([[v[0], v[1]] for (t, ty, v) in bcs], dtype=np.float64).reshape(-1)
+        rc = self.lib.ref_e_flow_create_b200(self.h, _dp(ph), flux.encode(), gradient.encode(), recon.encode(),
+                                             C.c_double(limiter_param), int(order2), int(p.viscous_sim), int(p.const_visc),
+                                             len(bcs), _ip(tt), _dp(vv))
+        if rc != 0:
+            self.lib.ref_binding_error.restype = C.c_char_p
+            raise RuntimeError("FlowFV_B200: " + self.lib.ref_binding_error().decode())
         self.phys = p
         return self
 
@@ -550,3 +565,26 @@ class Flow:
             orc().orc_flow_free(self.h)
         except Exception:
             pass
+
+
+REFBIND_PATH = os.path.join(ROOT, "oracle", "_ref", "libfvens_ref_binding.so")
+_refbind = None
+
+
+def have_ref_binding():
+    return os.path.exists(REFBIND_PATH)
+
+
+class RefBindingCase(RefCase):
+    """Tier E plus the reference-side binding (oracle/ref_binding.cpp): the reference's mesh, solver and output code with
+    FlowFV_B200 (fvens_b200/host/reference_binding/flow_spatial_b200.hpp) as the Spatial object."""
+
+    @staticmethod
+    def _lib():
+        global _refbind
+        if _refbind is None:
+            _refbind = C.CDLL(REFBIND_PATH)
+            _refbind.ref_e_mesh_read.restype = C.c_void_p
+            _refbind.ref_e_mesh_from_arrays.restype = C.c_void_p
+            _refbind.ref_e_restrict_to_rank.restype = C.c_void_p
+        return _refbind
