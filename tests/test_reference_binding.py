@@ -33,7 +33,8 @@ def case(cls, mesh, viscous=False):
     tags = set(np.asarray(rc.arrays()["btags"]).reshape(rc.nbface, -1)[:, 0].tolist())
     bcs = [(t, lib.BC[ty], v) for (t, ty, v) in (VISCOUS_BCS if viscous else INVISCID_BCS) if t in tags]
     a = rc.arrays()
-    cen = synth.cell_centres(a["coords"], a["nnode"], a["inpoel"])
+    inpoel = np.asarray(a["inpoel"]).reshape(rc.nelem, -1)
+    cen = synth.cell_centres(a["coords"], a["nnode"], np.where(np.arange(inpoel.shape[1])[None, :] < a["nnode"][:, None], inpoel, -1))
     u = synth.perturbed_state(cen, 1.4, 0.5, 0.02, amp=0.05)
     return rc, phys, bcs, u
 
