@@ -25,3 +25,14 @@ def test_coefficient_table_is_the_reference_s():
     c3 = lib.tvdrk_coefficients(3)
     assert np.array_equal(c3, [[1.0, 0.0, 1.0], [0.75, 0.25, 0.25], [0.3333333333333333, 0.6666666666666667, 0.6666666666666667]])
     assert np.abs(c3[:, 0] + c3[:, 1] - 1).max() < 1e-15
+
+
+def test_argument_validation_needs_no_gpu():
+    import ctypes as C
+    L = lib.load()
+    steps, time = C.c_int(7), C.c_double(7.0)
+    assert L.fvg_tvdrk_solve(None, None, 2, C.c_double(0.5), C.c_double(1.0), 0, C.byref(steps), C.byref(time)) != 0
+    assert "fvg_tvdrk_solve: bad argument" in L.fvg_last_error().decode()
+    c = (C.c_double*9)()
+    assert L.fvg_tvdrk_coefficients(0, c) != 0 and "temporal order 0 not available" in L.fvg_last_error().decode()
+    assert L.fvg_tvdrk_coefficients(3, None) != 0
