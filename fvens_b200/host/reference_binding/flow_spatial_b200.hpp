@@ -20,8 +20,11 @@
 
 namespace fvens {
 
+/// How the device-resident driver (ode_b200.hpp) finds the engine behind a Spatial pointer
+struct B200Engine { virtual fvg_flow* engine_flow() const = 0; virtual ~B200Engine() {} };
+
 template <bool secondOrderRequested, bool constVisc>
-class FlowFV_B200 : public FlowFV<freal,secondOrderRequested,constVisc>
+class FlowFV_B200 : public FlowFV<freal,secondOrderRequested,constVisc>, public B200Engine
 {
 public:
 	FlowFV_B200(const UMesh<freal,NDIM> *const mesh, const FlowPhysicsConfig& pc, const FlowNumericsConfig& nc,
@@ -94,6 +97,8 @@ public:
 		}
 		return fvg_residual_host(flow, uh.getArray(), rh.getArray(), 1, 0, nullptr);     // 0 = success, as CHKERRQ expects
 	}
+
+	fvg_flow* engine_flow() const { return flow; }
 
 private:
 	fvg_mesh *dmesh;

@@ -7,6 +7,7 @@
  */
 #include "ref_tier_e.cpp"
 #include "../fvens_b200/host/reference_binding/flow_spatial_b200.hpp"
+#include "../fvens_b200/host/reference_binding/ode_b200.hpp"
 
 extern "C" {
 
@@ -40,6 +41,33 @@ int ref_e_flow_create_b200(void *hv, const double *phys, const char *flux, const
 	} catch(std::exception& e) { binding_error = e.what(); rc = 1; }
 	std::cout.rdbuf(old);
 	return rc;
+}
+
+/// As ref_e_flow_forward_euler, with the device-resident driver of the binding (ode_b200.hpp) in place of the
+/// reference's SteadyForwardEulerSolver; the Spatial object must be the binding's (ref_e_flow_create_b200).
+/// Returns 0 converged, 1 Tolerance_error, 2 Numerical_error, 3 other failure (message in ref_binding_error()).
+int ref_e_flow_forward_euler_b200(void *hv, double cfl, double tol, int maxiter, double *u, int *steps, double *hist_rel, double *hist_abs)
+{
+	RefCase *h = static_cast<RefCase*>(hv);
+	_p_Vec uv;
+	uv.a.assign(u, u + h->uv.a.size()); uv.nlocal = h->uv.nlocal; uv.nghost = 0;
+	const SteadySolverConfig conf { true, "ref-binding", false, cfl, cfl, 0, 0, tol, maxiter, 0, 0 };
+	int code = 0;
+	*steps = 0;
+	std::stringstream sink;
+	std::streambuf *const old = std::cout.rdbuf(sink.rdbuf());
+	try {
+		SteadyForwardEulerSolver_B200 solver(h->prob.get(), &uv, conf);
+		try { code = solver.solve(&uv); }
+		catch(Tolerance_error&) { code = 1; }
+		catch(Numerical_error&) { code = 2; }
+		const TimingData td = solver.getTimingData();
+		*steps = td.num_timesteps;
+		for(size_t i = 0; i < td.convhis.size() && (int)i < maxiter; i++) { hist_rel[i] = td.convhis[i].rmsres; hist_abs[i] = td.convhis[i].absrmsres; }
+	} catch(std::exception& e) { binding_error = e.what(); code = 3; }
+	std::cout.rdbuf(old);
+	std::copy(uv.a.begin(), uv.a.end(), u);
+	return code;
 }
 
 }

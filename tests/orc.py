@@ -345,6 +345,18 @@ class RefCase:
                                                  _dp(hrel), _dp(habs))
         return code, steps.value, hrel[:steps.value], habs[:steps.value], u
 
+    def forward_euler_b200(self, u, cfl, tol, maxiter):
+        """The binding's device-resident driver SteadyForwardEulerSolver_B200 (RefBindingCase after flow_b200)."""
+        u = np.array(u, dtype=np.float64, copy=True)
+        steps = C.c_int(0)
+        hrel = np.zeros(max(maxiter, 1)); habs = np.zeros(max(maxiter, 1))
+        code = self.lib.ref_e_flow_forward_euler_b200(self.h, C.c_double(cfl), C.c_double(tol), int(maxiter), _dp(u), C.byref(steps),
+                                                      _dp(hrel), _dp(habs))
+        if code == 3:
+            self.lib.ref_binding_error.restype = C.c_char_p
+            raise RuntimeError(self.lib.ref_binding_error().decode())
+        return code, steps.value, hrel[:steps.value], habs[:steps.value], u
+
     def write_outputs(self, u, walls, others, basename, vtufile, volprefix):
         """The reference's own surface / VTU / volume files for the state u."""
         p = self.phys

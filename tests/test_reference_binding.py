@@ -7,7 +7,8 @@ CPU: the library builds, needs exactly six ABI symbols, and constructing the bin
 the library's error (no silent fallback to the reference's CPU residual).
 GPU (written after the round's GPU minutes were spent, never run): the reference's mesh reader + the binding give the
 reference's own residual to 1e-12, and the reference's own SteadyForwardEulerSolver object code, driving the CUDA
-residual through the binding, reproduces its CPU run."""
+residual through the binding, reproduces its CPU run; so does the binding's device-resident driver
+(ode_b200.hpp: SteadyForwardEulerSolver_B200, a SteadySolver of the reference around fvg_forward_euler_solve)."""
 import subprocess
 
 import numpy as np
@@ -42,8 +43,9 @@ def case(cls, mesh, viscous=False):
 def test_binding_library_needs_only_the_residual_entry_points():
     out = subprocess.run(["nm", "-D", "--undefined-only", orc.REFBIND_PATH], capture_output=True, text=True).stdout
     used = sorted(ln.split()[-1] for ln in out.splitlines() if " fvg_" in ln)
-    assert used == ["fvg_flow_create", "fvg_flow_destroy", "fvg_last_error", "fvg_mesh_create", "fvg_mesh_destroy",
-                    "fvg_residual_host"]
+    # flow_spatial_b200.hpp: create/destroy + fvg_residual_host; ode_b200.hpp: device buffer + fvg_forward_euler_solve
+    assert used == ["fvg_flow_create", "fvg_flow_destroy", "fvg_forward_euler_solve", "fvg_free", "fvg_last_error", "fvg_malloc",
+                    "fvg_memcpy", "fvg_mesh_create", "fvg_mesh_destroy", "fvg_residual_host"]
 
 
 @pytest.mark.skipif(_gpus() > 0, reason="needs a machine WITHOUT a GPU")
@@ -54,6 +56,9 @@ def test_binding_fails_loudly_without_a_gpu():
     # the same case with the reference's own Spatial object still works in this library
     r, dt = rc.flow(phys, "ROE", "LEASTSQUARES", "VANALBADA", 1.0, True, bcs).residual(u)
     assert np.isfinite(r).all() and (dt > 0).all()
+    # the device-resident driver refuses a Spatial that is not the binding's (it could only run it on the CPU)
+    with pytest.raises(RuntimeError, match="needs a FlowFV_B200"):
+        rc.forward_euler_b200(u, 0.4, 1e-30, 5)
 
 
 @pytest.mark.gpu
@@ -79,3 +84,8 @@ def test_reference_code_on_top_of_the_cuda_residual(cfg):
     assert (c0, s0) == (c1, s1) == (1, nsteps)
     assert np.abs(abs1/abs0 - 1).max() < 1e-6          # the reference stores its history in single precision
     assert rel_err_by_component(u1, u0) < 1e-10
+    # the binding's device-resident driver (one upload, fused steps on the GPU, one download): same contract
+    c2, s2, rel2, abs2, u2 = gpu.forward_euler_b200(u, 0.4, 1e-30, nsteps)
+    assert (c2, s2) == (1, nsteps)
+    assert np.abs(abs2/abs0 - 1).max() < 1e-6 and np.abs(rel2/rel0 - 1).max() < 1e-6
+    assert rel_err_by_component(u2, u0) < 1e-10
