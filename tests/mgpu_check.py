@@ -40,7 +40,7 @@ def main():
     phys = lib.make_physics(1.4, 0.5, 288.15, 5000.0, 0.72, 0.0)
     bcs = [(2, "slipwall", (0, 0)), (3, "inflowoutflow", (0, 0)), (4, "inflowoutflow", (0, 0))]
     u0 = synth.perturbed_state(rc, 1.4, 0.5)
-    part = lib.partition_sfc(um, world)
+    part = (lib.partition_rcb if os.environ.get("MGPU_PARTITION", "sfc") == "rcb" else lib.partition_sfc)(um, world)
     ok = True
     for numerics in (dict(flux="ROE", gradient="LEASTSQUARES", reconstruction="VENKATAKRISHNAN", limiter_param=2.0),
                      dict(flux="HLLC", gradient="GREENGAUSS", reconstruction="WENO", limiter_param=2.0)):

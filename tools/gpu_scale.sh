@@ -6,6 +6,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr
 timeout 300 $TR --master-port 29511 tests/mgpu_check.py > $out/${tag}_mgpu_check_n$n.log 2>&1; tail -3 $out/${tag}_mgpu_check_n$n.log
 timeout 600 $TR --master-port 29512 bench.py --gpus $n --steps 100 --warmup 5 > $out/${tag}_bench_n$n.json 2> $out/${tag}_bench_n$n.err
 FVG_FUSED_RECV=0 timeout 600 $TR --master-port 29513 bench.py --gpus $n --steps 100 --warmup 5 > $out/${tag}_bench_n${n}_recvkernel.json 2> $out/${tag}_bench_n${n}_recvkernel.err
+MGPU_PARTITION=rcb timeout 300 $TR --master-port 29515 tests/mgpu_check.py > $out/${tag}_mgpu_check_rcb_n$n.log 2>&1; tail -2 $out/${tag}_mgpu_check_rcb_n$n.log
 # coordinate-bisection partition (fewer ghost rows and neighbours; first timed in round 2)
 timeout 600 $TR --master-port 29514 bench.py --gpus $n --steps 100 --warmup 5 --partition rcb > $out/${tag}_bench_n${n}_rcb.json 2> $out/${tag}_bench_n${n}_rcb.err
 for f in $out/${tag}_bench_n$n.json $out/${tag}_bench_n${n}_recvkernel.json $out/${tag}_bench_n${n}_rcb.json; do python - "$f" <<'PY'
