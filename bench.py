@@ -126,9 +126,26 @@ def cpu_reference(cells, numerics, steps, warmup):
     flux, grad, recon, lp = NUMERICS[numerics][:4]
     phys = lib.make_physics(1.4, MINF, 288.15, 5000.0, 0.72, 0.0)
     bcs = [(t, lib.BC[ty], v) for (t, ty, v) in BCS]
+    build = "-O3 -msse4.2 (its default release flags)"
     if orc.have_ref_c_omp():
         rf = orc.RefFlow(om.arrays(), phys, flux, grad, recon, lp, True, bcs, omp=True)
         kind, cores = "reference", rf.threads()
+        if os.path.exists(orc.REFC_OMP_AVX2_PATH) and orc.host_has_avx2_fma():
+            # the reference's -DAVX_2 build option: keep whichever build is faster on this host (two evaluations each)
+            # (best of three single evaluations each, interleaved, after one untimed evaluation each)
+            def once(flow):
+                t = time.perf_counter()
+                flow.residual(u, True, want=False)
+                return time.perf_counter() - t
+            rf2 = orc.RefFlow(om.arrays(), phys, flux, grad, recon, lp, True, bcs, omp=True, path=orc.REFC_OMP_AVX2_PATH)
+            once(rf); once(rf2)
+            ta, tb = [], []
+            for _ in range(3):
+                ta.append(once(rf)); tb.append(once(rf2))
+            if min(tb) < min(ta):
+                rf, build = rf2, "-O3 -mavx2 -mfma (its AVX_2 build option)"
+            else:
+                del rf2
 
         def evaluate():
             rf.residual(u, True, want=False)
@@ -145,7 +162,7 @@ def cpu_reference(cells, numerics, steps, warmup):
     for _ in range(steps):
         evaluate()
     dt = (time.perf_counter() - t0)/steps
-    what = ("the reference's own FlowFV::compute_residual (flow_spatial.cpp and its callees compiled unmodified, OpenMP)"
+    what = ("the reference's own FlowFV::compute_residual (flow_spatial.cpp and its callees compiled unmodified, OpenMP, " + build + ")"
             if kind == "reference" else "the oracle's restatement of the reference's loops (OpenMP)")
     info = {"cells": om.nelem, "faces": om.naface, "cores": cores, "kind": kind,
             "sample": f"{what} on a bump channel {nx}x{ny} base lattice = {om.nelem} cells / {om.naface} faces "

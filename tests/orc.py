@@ -122,6 +122,15 @@ def ref_residual(a, p, flux, gradient, recon, limiter_param, order2, bcs, u, get
 
 
 REFC_OMP_PATH = os.path.join(ROOT, "oracle", "_ref", "libfvens_ref_c_omp.so")
+REFC_OMP_AVX2_PATH = os.path.join(ROOT, "oracle", "_ref", "libfvens_ref_c_omp_avx2.so")
+
+
+def host_has_avx2_fma():
+    try:
+        flags = next(ln for ln in open("/proc/cpuinfo") if ln.startswith("flags")).split()
+    except (OSError, StopIteration):
+        return False
+    return "avx2" in flags and "fma" in flags
 
 
 class RefFlow:
