@@ -64,3 +64,14 @@ def test_flow_conv_program_passes_the_reference_s_acceptance_window(tmp_path):
         assert abs(10**float(le)/e - 1) < 1e-3            # same converged state as the oracle's run
     orders = [float(x) for x in re.findall(r"^\s+(\S+)\s*$", r.stdout.split(">> Spatial orders =")[1].split("---")[0], re.M)]
     assert len(orders) == 2 and abs(orders[0] - 1.748) < 5e-3 and 1.65 <= orders[1] <= 2.1
+
+
+def test_flow_conv_rejects_what_it_cannot_run():
+    """No GPU needed: usage errors and an implicit control file are refused before any device work."""
+    assert subprocess.run([FLOW_CONV], capture_output=True).returncode == 2
+    r = subprocess.run([FLOW_CONV, os.path.join(CTRL, "expl-inv-cyl-gg-roe_tri.ctrl"), "--source_dir", CTRL, "--number_of_meshes", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "at least 2" in r.stderr
+    r = subprocess.run([FLOW_CONV, os.path.join(CTRL, "naca0012-transonic-implicit.ctrl"), "--number_of_meshes", "3"],
+                       capture_output=True, text=True)
+    assert r.returncode == 3 and "implicit" in r.stderr
