@@ -2,7 +2,7 @@
  * Compile-and-run check of the reference-side binding (fvens_b200/host/reference_binding/flow_spatial_b200.hpp): the
  * binding is built here against the reference's own, unmodified headers and sources (everything of tier E) and linked
  * with libfvens_b200.so, which proves that the class in INTEGRATION.md is real code for the real FVENS. On a GPU box the
- * reference's own SteadyForwardEulerSolver then drives the CUDA residual through it (tests/test_reference_binding.py).
+ * reference's own SteadyForwardEulerSolver then drives the CUDA residual through it (tests/test_post_r1_c_reference_binding.py).
  * Built into oracle/_ref/libfvens_ref_binding.so (needs /root/reference and the product library).
  */
 #include "ref_tier_e.cpp"

@@ -4,7 +4,7 @@
  * error and the mesh size parameter, and pass iff the observed order between the two finest meshes lies in [1.65, 2.1].
  * The reference registers it for the explicit solver as Flow_Explicit_Euler_Cylinder_GreenGauss_Roe_Tri_
  * EntropyConvergence (tests/inv-2dcyl/CMakeLists.txt, 3 meshes of testcases/2dcylinder/grids). Needs a B200.
- * Run by tests/test_order_of_accuracy_gpu.py.
+ * Run by tests/test_post_r1_b_flow_conv.py.
  */
 #include "../../fvens_b200/host/casesolvers.hpp"
 

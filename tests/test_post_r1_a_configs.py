@@ -5,7 +5,7 @@ squares + Venkatakrishnan, explicit forward-Euler pseudo-time from the free stre
 lift/drag after 1000 identical steps against the oracle. The oracle run with 1 and with 8 threads (different summation
 orders) differs by 1.5e-14 in the history after 1000 steps: round-off does not grow on this case, so the bounds of the
 60- and 200-step tests in test_gpu_solver.py hold here as well.
-Added after the round's GPU minutes were spent (hence a file of its own that sorts after the verified GPU tests); it
+Added after the round's GPU minutes were spent (hence a file of its own; the test_post_r1_* files sort after the verified GPU tests); it
 uses only entry points those tests already exercise."""
 import numpy as np
 import pytest

@@ -6,8 +6,8 @@ entropy error must fall with an observed order in [1.65, 2.1] between the two fi
 
 The same procedure is run on the oracle (CPU; the two coarser meshes in the CPU suite, all three once by hand:
 entropy errors 0.0655314050, 0.0195118119, 0.00496115021, orders 1.748, 1.976) and by the flow_conv program on the
-GPU (tests/cpp/flow_conv.cpp). The GPU case was written after the round's GPU minutes were spent (it sorts after
-the other GPU tests on purpose)."""
+GPU (tests/cpp/flow_conv.cpp). The GPU case was written after the round's GPU minutes were spent (the test_post_r1_* files sort after
+the verified GPU tests on purpose)."""
 import os
 import re
 import subprocess

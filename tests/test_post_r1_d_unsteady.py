@@ -4,7 +4,7 @@ oracle's residual: state after a few steps, step count, physical time, the loop 
 The scheme itself (coefficients, observed order 1/2/3, dt = cfl*min(dtm) from the first stage) is tested without a
 GPU through the host class's generic loop (tests/test_ode_host.py).
 
-This file was written after the round's GPU minutes were spent; it sorts last among the GPU tests on purpose."""
+This file was written after the round's GPU minutes were spent; the test_post_r1_* files sort after the verified GPU tests on purpose."""
 import numpy as np
 import pytest
 import torch

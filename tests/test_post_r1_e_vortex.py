@@ -4,7 +4,7 @@ t = 1, density error against the exact solution in the area-weighted L2 norm. Th
 disabled and has no control file and its FlowBC family has no periodic member, so the boundaries are
 far-field states (the vortex is 1e-6 of its strength there). The oracle run (CPU) gives orders 2.26 / 2.20 on 32, 64,
 128 quads and 2.21 / 2.14 on jittered hybrid meshes; the GPU run must reproduce the oracle's states and orders.
-The GPU cases were written after the round's GPU minutes were spent (the file sorts last among the GPU tests)."""
+The GPU cases were written after the round's GPU minutes were spent (the test_post_r1_* files sort after the verified GPU tests)."""
 import os
 
 import numpy as np
