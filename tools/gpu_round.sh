@@ -7,7 +7,7 @@ mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/${tag}_smi.txt 2>&1
 # tests written after round 1's GPU minutes were spent run first and on their own, so that a failure there is seen
 # without hiding the rest of the suite
-( time timeout 600 python -m pytest tests/test_post_r1_d_unsteady.py tests/test_post_r1_b_flow_conv.py tests/test_post_r1_e_vortex.py tests/test_post_r1_a_configs.py tests/test_post_r1_c_reference_binding.py -m gpu -q ) > $out/${tag}_pytest_gpu_new.log 2>&1
+( time timeout 600 python -m pytest tests/test_post_r1_a_configs.py tests/test_post_r1_b_flow_conv.py tests/test_post_r1_c_reference_binding.py tests/test_post_r1_d_unsteady.py tests/test_post_r1_e_vortex.py -m gpu -q ) > $out/${tag}_pytest_gpu_new.log 2>&1
 echo "pytest rc=$?" >> $out/${tag}_pytest_gpu_new.log
 ( time timeout 600 python -m pytest tests -m gpu -x -q ) > $out/${tag}_pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> $out/${tag}_pytest_gpu.log
