@@ -119,6 +119,12 @@ def cpu_reference(cells, numerics, steps, warmup):
     flow_spatial.cpp and everything it calls, compiled unmodified with its OpenMP pragmas on - oracle/ref_tier_c.cpp) that
     is what is timed (kind "reference"); otherwise the oracle's restatement of the same loops (kind "port").
     Returns (Gfaces/s, ms/step, info)."""
+    # all host cores for the CPU arm, also under torchrun (which sets OMP_NUM_THREADS=1 for its workers unless the caller
+    # has set it): the OpenMP runtime of the oracle libraries reads the variable when it is first loaded, i.e. below
+    if os.environ.get("OMP_NUM_THREADS", "1") == "1" and "FVG_CPU_THREADS" not in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    elif "FVG_CPU_THREADS" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = os.environ["FVG_CPU_THREADS"]
     import orc
     from fvens_b200 import lib
     um, arrs, u, (nx, ny) = build_case(cells, numerics, 512)
