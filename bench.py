@@ -225,6 +225,9 @@ def main():
     from fvens_b200 import lib
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
+    if args.gpus != world:
+        sys.exit(f"bench.py: --gpus {args.gpus} needs one rank per GPU but WORLD_SIZE is {world}; launch it as "
+                 f"python -m torch.distributed.run --nnodes=1 --nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
