@@ -20,3 +20,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'cel
    -f -o $out/${tag}_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $out/${tag}_full.log 2>&1
 python tools/ncu_summary.py $out/${tag}_full.ncu-rep > $out/${tag}_ncu_summary.txt 2>&1
 tail -3 $out/${tag}_pytest_gpu_new.log; tail -3 $out/${tag}_pytest_gpu.log; cat $out/${tag}_bench_n1.json; tail -2 $out/${tag}_bench_n1.err
+# programmatic-dependent-launch build variant (never run in round 1): parity on a subset of the residual tests, then A/B timing
+( timeout 900 make -C fvens_b200/csrc -j16 EXTRA=-DFVG_PDL OBJDIR=build_pdl TARGET=../variants_pdl.so > $out/${tag}_pdl_build.log 2>&1 \
+  && FVENS_B200_LIB=$PWD/fvens_b200/variants_pdl.so timeout 600 python -m pytest tests/test_gpu_residual.py tests/test_gpu_solver.py -m gpu -x -q > $out/${tag}_pdl_pytest.log 2>&1; \
+  tail -2 $out/${tag}_pdl_pytest.log; \
+  timeout 600 bash tools/variant_sweep.sh "default:256 $PWD/fvens_b200/variants_pdl.so:256 default:256 $PWD/fvens_b200/variants_pdl.so:256" > $out/${tag}_pdl_sweep.txt 2>&1; cat $out/${tag}_pdl_sweep.txt )
