@@ -3,7 +3,7 @@
  * The reference's TVDRKSolver::solve (ode/aodesolver.cpp:672-785) carries the Shu-Osher coefficient table
  * (initialize_TVDRK_Coeffs, :45-67) but (1) evaluates the residual at the step's initial state in every stage and
  * (2) subtracts dt/area * residual although compute_residual leaves -r(u) there (the forward-Euler loop adds it,
- * :207). SURVEY 8f-4 asks for the scheme as it is meant:
+ * :208). SURVEY 8f-4 asks for the scheme as it is meant:
  *     u^(0) = u^n;  u^(i+1) = a_i u^n + b_i u^(i) + c_i dt/area * (-r(u^(i)));  u^(n+1) = u^(order)
  * with the reference's table (a, b, c), its global time step dt = cfl * min_cells dtm(u^n) taken in the first stage,
  * its loop condition (time <= finaltime - 1e-12, last step not clipped) and its divergence check on dt.

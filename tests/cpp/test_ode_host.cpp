@@ -4,7 +4,7 @@
  * The model problem is du/dt = -lambda_i u per cell (residual = area * lambda_i * u, local time steps given), whose
  * exact solution is known: the observed order of accuracy of orders 1, 2, 3 must be 1, 2, 3 - which it is only if the
  * stages are evaluated at the stage state and the update has the right sign (the reference's loop, ode/aodesolver.cpp:
- * 708-741, does neither). Also: dt = cfl * min(dtm) from the first stage, the loop condition and step count, the
+ * 708-742, does neither). Also: dt = cfl * min(dtm) from the first stage, the loop condition and step count, the
  * divergence check, the log-file line, the coefficient table of initialize_TVDRK_Coeffs (:45-67).
  * Run by tests/test_ode_host.py.
  */

@@ -72,8 +72,8 @@ def _stage_table(order):
 
 def test_reference_tvdrk_loop_as_it_is_and_what_the_product_does_instead():
     """TVDRKSolver::solve of the reference (ode/aodesolver.cpp:672-785), run from its own object code, equals its loop
-    restated literally: every stage takes compute_residual at the step's INITIAL state (`uvec`, :711) and the update is
-    SUBTRACTED (:734) although compute_residual leaves -r(u) (the forward-Euler loop adds it, :207). So one order-1 step
+    restated literally: every stage takes compute_residual at the step's INITIAL state (`uvec`, :719) and the update is
+    SUBTRACTED (:740) although compute_residual leaves -r(u) (the forward-Euler loop adds it, :208). So one order-1 step
     of the reference is exactly the mirror image of a forward-Euler step with the global time step - it integrates
     backwards in time. The product's fvg_tvdrk_solve / TVDRKSolver keep the coefficient table, the time step
     (cfl * min dtm of the first stage) and the loop condition, evaluate at the stage state and add the update; that
