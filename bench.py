@@ -437,14 +437,14 @@ def main():
         ach_face = bB/t_face/1e9
         line["kernels_ms"] = {"gradient_limiter_pass": t_cell*1e3, "face_pass": t_face*1e3, "timed_evals": ntimed}
         line["roofline"] = {"bound": "hbm", "kernel": "face_kernel (reconstruct + flux + spectral radius + accumulate)",
-                            "achieved": ach_face, "peak": peak, "unit": "GB/s", "frac": ach_face/peak, "traffic": traffic,
+                            "achieved": ach_face, "peak": peak, "unit": "GB/s", "frac": ach_face/peak, "frac_of_nominal_8000_GBs": ach_face/8000.0, "traffic": traffic,
                             "algorithmic_bytes_per_launch": bB, "peak_source": peak_src,
                             "cell_pass": {"achieved": bA/t_cell/1e9, "frac": bA/t_cell/1e9/peak,
                                           "algorithmic_bytes_per_launch": bA}}
     else:
         ach = (bA + bB)/world/(ms_step*1e-3)/1e9
         line["roofline"] = {"bound": "hbm", "kernel": "whole evaluation per GPU (cell pass + face pass + halos)",
-                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach/peak, "traffic": None,
+                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach/peak, "frac_of_nominal_8000_GBs": ach/8000.0, "traffic": None,
                             "algorithmic_bytes_per_launch": (bA + bB)/world, "peak_source": peak_src}
     if not args.no_cpu_baseline and world == 1:
         gf, ms, ci = cpu_reference(args.cpu_cells, args.numerics, 6, 2)
