@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 import orc
-from common import mesh_path, rel_err_by_component, INVISCID_BCS, VISCOUS_BCS
+from common import mesh_path, rel_err_by_component, INVISCID_BCS, VISCOUS_BCS, not_yet_run_on_a_gpu
 from fvens_b200 import lib, synth
 
 def _gpus():
@@ -62,6 +62,7 @@ def test_binding_fails_loudly_without_a_gpu():
 
 
 @pytest.mark.gpu
+@not_yet_run_on_a_gpu
 @pytest.mark.parametrize("cfg", [("2dcylinderhybrid.msh", "ROE", "LEASTSQUARES", "VANALBADA", True, False),
                                  ("naca0012luo.msh", "HLLC", "GREENGAUSS", "NONE", True, False),
                                  ("NACA0012_inv.su2", "AUSM", "LEASTSQUARES", "WENO", True, False),

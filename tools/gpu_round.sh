@@ -5,9 +5,9 @@ tag=${1:-rXX}
 out=gpurun_out
 mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/${tag}_smi.txt 2>&1
-# tests written after round 1's GPU minutes were spent run first and on their own, so that a failure there is seen
-# without hiding the rest of the suite
-( time timeout 600 python -m pytest tests/test_post_r1_a_configs.py tests/test_post_r1_b_flow_conv.py tests/test_post_r1_c_reference_binding.py tests/test_post_r1_d_unsteady.py tests/test_post_r1_e_vortex.py -m gpu -q ) > $out/${tag}_pytest_gpu_new.log 2>&1
+# tests written after round 1's GPU minutes were spent are opt-in (FVG_RUN_UNVERIFIED=1, tests/common.py) until they have
+# passed once; they run first and on their own here, without -x, so that every one of them reports
+( time FVG_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/test_post_r1_a_configs.py tests/test_post_r1_b_flow_conv.py tests/test_post_r1_c_reference_binding.py tests/test_post_r1_d_unsteady.py tests/test_post_r1_e_vortex.py -m gpu -q ) > $out/${tag}_pytest_gpu_new.log 2>&1
 echo "pytest rc=$?" >> $out/${tag}_pytest_gpu_new.log
 ( time timeout 600 python -m pytest tests -m gpu -x -q ) > $out/${tag}_pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> $out/${tag}_pytest_gpu.log
