@@ -36,14 +36,3 @@ INVISCID_BCS = [(2, "slipwall", (0.0, 0.0)), (3, "inflowoutflow", (0.0, 0.0)), (
                 (1, "extrapolation", (0.0, 0.0))]
 VISCOUS_BCS = [(2, "adiabaticwall", (0.0, 0.0)), (3, "isothermalwall", (0.1, 1.02)), (4, "farfield", (0.0, 0.0)),
                (1, "slipwall", (0.0, 0.0))]
-
-
-import pytest as _pytest
-
-# GPU tests written after round 1's GPU minutes were spent have never run on a GPU. Until they have, they are opt-in,
-# so that an error in a test that could not be tried does not hide the verified suite behind it:
-#   FVG_RUN_UNVERIFIED=1 python -m pytest tests -m gpu        (tools/gpu_round.sh runs them first, on their own)
-# Remove the marker from a test once it has passed on a B200.
-not_yet_run_on_a_gpu = _pytest.mark.skipif(
-    os.environ.get("FVG_RUN_UNVERIFIED") != "1",
-    reason="written after round 1's GPU minutes were spent and never run on a GPU yet; FVG_RUN_UNVERIFIED=1 enables it")

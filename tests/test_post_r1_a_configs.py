@@ -11,10 +11,10 @@ import numpy as np
 import pytest
 import torch
 
-from common import rel_err_by_component, not_yet_run_on_a_gpu
+from common import rel_err_by_component
 from gpu_common import make_case, gpu_residual
 
-pytestmark = [pytest.mark.gpu, not_yet_run_on_a_gpu]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_config0_naca0012_thousand_step_convergence_check():

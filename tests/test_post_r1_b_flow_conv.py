@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 import orc
-from common import ROOT, MESHDIR, mesh_path, not_yet_run_on_a_gpu
+from common import ROOT, MESHDIR, mesh_path
 from fvens_b200 import lib
 
 CTRL = os.path.join(ROOT, "tests", "golden", "ctrl")
@@ -50,7 +50,6 @@ def test_oracle_entropy_convergence_on_the_two_coarser_meshes():
 
 
 @pytest.mark.gpu
-@not_yet_run_on_a_gpu
 def test_flow_conv_program_passes_the_reference_s_acceptance_window(tmp_path):
     r = subprocess.run([FLOW_CONV, os.path.join(CTRL, "expl-inv-cyl-gg-roe_tri.ctrl"), "--source_dir", CTRL,
                         "--number_of_meshes", "3", "--mesh_file", os.path.join(MESHDIR, "2dcylinder"),

@@ -5,7 +5,7 @@ libfvens_ref_binding.so) and linked with libfvens_b200.so.
 
 CPU: the library builds, needs exactly six ABI symbols, and constructing the binding without a GPU fails loudly with
 the library's error (no silent fallback to the reference's CPU residual).
-GPU (written after the round's GPU minutes were spent, never run): the reference's mesh reader + the binding give the
+GPU (first run and green on a B200 in round 2, profiles/r02_pytest_gpu_formerly_unrun.log): the reference's mesh reader + the binding give the
 reference's own residual to 1e-12, and the reference's own SteadyForwardEulerSolver object code, driving the CUDA
 residual through the binding, reproduces its CPU run; so does the binding's device-resident driver
 (ode_b200.hpp: SteadyForwardEulerSolver_B200, a SteadySolver of the reference around fvg_forward_euler_solve)."""
@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 import orc
-from common import mesh_path, rel_err_by_component, INVISCID_BCS, VISCOUS_BCS, not_yet_run_on_a_gpu
+from common import mesh_path, rel_err_by_component, INVISCID_BCS, VISCOUS_BCS
 from fvens_b200 import lib, synth
 
 def _gpus():
@@ -62,7 +62,6 @@ def test_binding_fails_loudly_without_a_gpu():
 
 
 @pytest.mark.gpu
-@not_yet_run_on_a_gpu
 @pytest.mark.parametrize("cfg", [("2dcylinderhybrid.msh", "ROE", "LEASTSQUARES", "VANALBADA", True, False),
                                  ("naca0012luo.msh", "HLLC", "GREENGAUSS", "NONE", True, False),
                                  ("NACA0012_inv.su2", "AUSM", "LEASTSQUARES", "WENO", True, False),

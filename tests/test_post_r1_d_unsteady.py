@@ -8,11 +8,11 @@ This file was written after the round's GPU minutes were spent; the test_post_r1
 import numpy as np
 import pytest
 import torch
-from common import rel_err_by_component, not_yet_run_on_a_gpu
+from common import rel_err_by_component
 from gpu_common import make_case
 from fvens_b200 import lib
 
-pytestmark = [pytest.mark.gpu, not_yet_run_on_a_gpu]
+pytestmark = [pytest.mark.gpu]
 
 
 def oracle_tvdrk(of, u, area, order, cfl, finaltime, maxsteps=0):

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import orc
-from common import rel_err_by_component, not_yet_run_on_a_gpu
+from common import rel_err_by_component
 from fvens_b200 import lib, synth
 
 G, M, CFL, TFINAL = 1.4, 0.5, 0.4, 1.0
@@ -82,7 +82,6 @@ def test_oracle_order_of_accuracy(hybrid):
 
 
 @pytest.mark.gpu
-@not_yet_run_on_a_gpu
 @pytest.mark.parametrize("hybrid,rk", [(False, 2), (True, 3)])
 def test_gpu_vortex_states_and_order(hybrid, rk):
     import torch
