@@ -99,25 +99,46 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_case(cells, numerics, tile):
-    """Host mesh (Hilbert-ordered, so the device numbering is the identity), its arrays and the state."""
-    from fvens_b200 import lib, synth
+def build_arrays(cells):
+    """The benchmark mesh and state as plain numpy arrays (no library): bump-channel generator, cells renumbered along a
+    Hilbert curve (the reference's `-mesh_reorder` step with a locality order; synth.hilbert_order is the numpy twin of
+    fvg_umesh_hilbert_ordering), perturbed free stream. Both arms - and the cpu_baseline leg - are built from this, so
+    they time the same mesh in the same numbering; the reference arm never maps libfvens_b200.so."""
+    from fvens_b200 import synth
     nx, ny = lattice_for(cells)
-    arrs = synth.bump_channel(nx, ny, seed=12345)
-    um = lib.UMesh.from_arrays(*arrs)
-    perm = um.hilbert_ordering()          # the reference's `-mesh_reorder` step, with a locality order
-    um.reorder_cells(perm)
-    coords, nnode, inpoel, bface = arrs
-    nnode, inpoel = nnode[perm], inpoel[perm]
+    coords, nnode, inpoel, bface = synth.bump_channel(nx, ny, seed=12345)
     rc = synth.cell_centres(coords, nnode, inpoel)
+    perm = synth.hilbert_order(rc)
+    nnode, inpoel, rc = np.ascontiguousarray(nnode[perm]), np.ascontiguousarray(inpoel[perm]), rc[perm]
     u = synth.perturbed_state(rc, 1.4, MINF)
-    return um, (coords, nnode, inpoel, bface), u, (nx, ny)
+    return (coords, nnode, inpoel, bface), u, (nx, ny)
 
 
-def cpu_reference(cells, numerics, steps, warmup):
-    """The reference's CPU path on the host cores. When oracle/_ref/libfvens_ref_c_omp.so exists (the reference's own
-    flow_spatial.cpp and everything it calls, compiled unmodified with its OpenMP pragmas on - oracle/ref_tier_c.cpp) that
-    is what is timed (kind "reference"); otherwise the oracle's restatement of the same loops (kind "port").
+def build_case(cells, numerics, tile):
+    """Host mesh of the CUDA arm from the same arrays (already Hilbert-ordered: the device numbering is the identity)."""
+    from fvens_b200 import lib
+    arrs, u, lat = build_arrays(cells)
+    um = lib.UMesh.from_arrays(*arrs)
+    return um, arrs, u, lat
+
+
+def workload_config(args, nc, nf, lat):
+    """`config` of the JSON line: the workload only, identical in both arms (the GPU arm's layout details go under
+    `layout`)."""
+    flux, grad, recon, lp = NUMERICS[args.numerics][:4]
+    return {"workload": f"synthetic hybrid tri/quad Gaussian-bump channel, {args.cells/1e6:g}M cells, "
+                        f"{flux}+{grad}+{recon} second-order residual with local time steps (BASELINE configs[2] mesh, "
+                        f"north-star headline numerics)",
+            "cells": int(nc), "faces": int(nf), "lattice": [int(lat[0]), int(lat[1])], "numerics": args.numerics,
+            "cell_order": "Hilbert curve (host renumbering, identical in both arms)",
+            "l2": "inputs (320 MB state + 640 MB gradients + 3 GB mesh at 10M cells) exceed the 126 MB L2; no explicit flush"}
+
+
+def cpu_reference(cells, numerics, steps, warmup, extras=False, prebuilt=None):
+    """The reference's CPU path on the host cores, on the SAME mesh as the CUDA arm. When
+    oracle/_ref/libfvens_ref_c_omp.so exists (the reference's own flow_spatial.cpp and everything it calls, compiled
+    unmodified with its OpenMP pragmas on - oracle/ref_tier_c.cpp) that is what is timed (kind "reference"); otherwise
+    the oracle's restatement of the same loops (kind "port"). Only numpy, tests/orc.py and oracle/ are used here.
     Returns (Gfaces/s, ms/step, info)."""
     # all host cores for the CPU arm, also under torchrun (which sets OMP_NUM_THREADS=1 for its workers unless the caller
     # has set it): the OpenMP runtime of the oracle libraries reads the variable when it is first loaded, i.e. below
@@ -125,33 +146,43 @@ def cpu_reference(cells, numerics, steps, warmup):
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     elif "FVG_CPU_THREADS" in os.environ:
         os.environ["OMP_NUM_THREADS"] = os.environ["FVG_CPU_THREADS"]
+    os.environ.setdefault("OMP_PROC_BIND", "close")
     import orc
-    from fvens_b200 import lib
-    um, arrs, u, (nx, ny) = build_case(cells, numerics, 512)
+    from fvens_b200 import lib      # constants only (name tables, the physics struct); the shared library is not loaded
+    arrs, u, (nx, ny) = prebuilt if prebuilt is not None else build_arrays(cells)
     om = orc.Mesh.from_arrays(*arrs)
     flux, grad, recon, lp = NUMERICS[numerics][:4]
     phys = lib.make_physics(1.4, MINF, 288.15, 5000.0, 0.72, 0.0)
     bcs = [(t, lib.BC[ty], v) for (t, ty, v) in BCS]
     build = "-O3 -msse4.2 (its default release flags)"
+    extra = {}
+
+    def once(flow):
+        t = time.perf_counter()
+        flow.residual(u, True, want=False)
+        return time.perf_counter() - t
     if orc.have_ref_c_omp():
         rf = orc.RefFlow(om.arrays(), phys, flux, grad, recon, lp, True, bcs, omp=True)
         kind, cores = "reference", rf.threads()
+        once(rf)
+        ta = [once(rf) for _ in range(2)]
+        extra["ms_per_eval_sse42_build"] = min(ta)*1e3
         if os.path.exists(orc.REFC_OMP_AVX2_PATH) and orc.host_has_avx2_fma():
-            # the reference's -DAVX_2 build option: keep whichever build is faster on this host (two evaluations each)
-            # (best of three single evaluations each, interleaved, after one untimed evaluation each)
-            def once(flow):
-                t = time.perf_counter()
-                flow.residual(u, True, want=False)
-                return time.perf_counter() - t
+            # the reference's -DAVX_2 build option: keep whichever build is faster on this host (best of two single
+            # evaluations each after one untimed evaluation)
             rf2 = orc.RefFlow(om.arrays(), phys, flux, grad, recon, lp, True, bcs, omp=True, path=orc.REFC_OMP_AVX2_PATH)
-            once(rf); once(rf2)
-            ta, tb = [], []
-            for _ in range(3):
-                ta.append(once(rf)); tb.append(once(rf2))
+            once(rf2)
+            tb = [once(rf2) for _ in range(2)]
+            extra["ms_per_eval_avx2_build"] = min(tb)*1e3
             if min(tb) < min(ta):
                 rf, build = rf2, "-O3 -mavx2 -mfma (its AVX_2 build option)"
             else:
                 del rf2
+        if extras:
+            # one evaluation on a single thread (the libraries share one OpenMP runtime; orc_set_num_threads sets its ICV)
+            orc.set_threads(1)
+            extra["ms_per_eval_1_thread"] = once(rf)*1e3
+            orc.set_threads(cores)
 
         def evaluate():
             rf.residual(u, True, want=False)
@@ -170,9 +201,10 @@ def cpu_reference(cells, numerics, steps, warmup):
     dt = (time.perf_counter() - t0)/steps
     what = ("the reference's own FlowFV::compute_residual (flow_spatial.cpp and its callees compiled unmodified, OpenMP, " + build + ")"
             if kind == "reference" else "the oracle's restatement of the reference's loops (OpenMP)")
-    info = {"cells": om.nelem, "faces": om.naface, "cores": cores, "kind": kind,
-            "sample": f"{what} on a bump channel {nx}x{ny} base lattice = {om.nelem} cells / {om.naface} faces "
-                      f"(same generator and numerics as the GPU workload, {steps} evaluations after {warmup} warm-up)"}
+    info = {"cells": om.nelem, "faces": om.naface, "cores": cores, "kind": kind, "lattice": (nx, ny), "extra": extra,
+            "sample": f"{what} on the whole workload mesh: bump channel {nx}x{ny} base lattice = {om.nelem} cells / {om.naface} "
+                      f"faces, Hilbert-ordered (same arrays, numbering, state and numerics as the CUDA arm), {steps} evaluations "
+                      f"after {warmup} warm-up, {cores} threads"}
     return om.naface/dt/1e9, dt*1e3, info
 
 
@@ -185,7 +217,8 @@ def main():
     ap.add_argument("--cells", type=float, default=10.0e6)
     ap.add_argument("--numerics", default="roe-wls-venkat", choices=list(NUMERICS))
     ap.add_argument("--tile", type=int, default=256)
-    ap.add_argument("--cpu-cells", type=float, default=1.0e6, help="size of the bounded CPU sample")
+    ap.add_argument("--cpu-cells", type=float, default=0.0,
+                    help="cells of the CPU arms' mesh; 0 (default) = the workload's own mesh (same config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--partition", default="sfc", choices=["sfc", "rcb"],
@@ -198,24 +231,29 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     flux, grad, recon, lp = NUMERICS[args.numerics][:4]
-    workload = (f"synthetic hybrid tri/quad Gaussian-bump channel, {args.cells/1e6:g}M cells, "
-                f"{flux}+{grad}+{recon} second-order residual with local time steps (BASELINE configs[2] mesh, "
-                f"north-star headline numerics)")
-
     if args.impl == "reference":
         if rank != 0:
             return
         import __graft_entry__ as g
-        g.build(quiet=True)
-        gf, ms, info = cpu_reference(args.cpu_cells, args.numerics, max(1, min(args.steps, 20)), max(1, min(args.warmup, 3)))
+        g.build_oracle(quiet=True)        # the checker libraries only: this process never maps libfvens_b200.so
+        # same mesh, same --steps / --warmup as the CUDA arm (a 10M-cell evaluation takes a few tenths of a second on a
+        # 16-thread host; --cpu-cells bounds the sample if a host is too slow for that)
+        cells = args.cpu_cells if args.cpu_cells else args.cells
+        gf, ms, info = cpu_reference(cells, args.numerics, max(1, args.steps), max(1, args.warmup), extras=True)
         line = {"impl": "reference", "metric": "Gfaces/s", "value": gf, "unit": "Gfaces/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "timed_on": info["sample"]},
+                "config": workload_config(args, info["cells"], info["faces"], info["lattice"]),
                 "residual_evals_per_s": 1e3/ms,
                 "cpu_baseline": {"value": gf, "unit": "Gfaces/s", "cores": info["cores"], "kind": info["kind"],
-                                 "sample": info["sample"]},
+                                 "sample": info["sample"], **info["extra"]},
                 "e2e": {"value": gf, "unit": "Gfaces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        try:    # evidence that this arm is process-clean: the shared objects of this repo mapped by this process
+            maps = sorted({ln.split()[-1][len(ROOT)+1:] for ln in open("/proc/self/maps") if ROOT in ln and ".so" in ln})
+            line["repo_libraries_mapped"] = maps
+            assert not any("libfvens_b200" in m for m in maps), "the reference arm must not load the product library"
+        except OSError:
+            pass
         print(json.dumps(line))
         return
 
@@ -401,24 +439,27 @@ def main():
     bA, bB = algorithmic_bytes(args.numerics, nc_glob, nf_glob)
     gfaces = nf_glob/(ms_step*1e-3)/1e9
     info = dm.info
-    traffic = None
+    traffic, traffic_src = None, None
     try:        # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"face_kernel:{args.numerics}:{args.tile}:{int(args.cells)}")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(f"face_kernel:{args.numerics}:{args.tile}:{int(args.cells)}")
+        if traffic is not None:
+            traffic_src = ("not measured by this run: dram__bytes_read.sum + dram__bytes_write.sum of one face_kernel launch from the "
+                           "committed `ncu --set full` capture of this command, " + str(tj.get("source", "profiles/")))
     except Exception:
         pass
     line = {
         "metric": "Gfaces/s", "value": gfaces, "unit": "Gfaces/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "cells": nc_glob, "faces": nf_glob, "lattice": [nx, ny],
-                   "cells_on_rank0": nc, "ghost_cells_on_rank0": int(info.nghost),
+        "config": workload_config(args, nc_glob, nf_glob, (nx, ny)),
+        "layout": {"cells_on_rank0": nc, "ghost_cells_on_rank0": int(info.nghost),
                    "tile_cells": info.tile_cells, "cut_face_duplicates_rank0": info.ncut_dup,
                    "parallelism": "single GPU" if world == 1 else
                    f"{world} GPUs, {'coordinate-bisection' if args.partition == 'rcb' else 'Hilbert-curve'} partition, one ghost layer; per evaluation: state halo, gradient pass, "
                    f"gradient halo, face pass; halo transport: " + (("peer-mapped windows over NVLink (CUDA IPC, direct stores + flags)"
                                                   + (", received inside the consuming kernels" if df.fused_recv else ", one send+receive kernel per exchange"))
-                                                 if df.halo_kind == "peer" else "NCCL all-to-all with row splits"),
-                   "l2": "inputs (320 MB state + 640 MB gradients + 3 GB mesh) exceed the 126 MB L2; no explicit flush"},
+                                                 if df.halo_kind == "peer" else "NCCL all-to-all with row splits")},
         "residual_evals_per_s": 1e3/ms_step,
         "residual_roofline_frac": (bA + bB)/(ms_step*1e-3)/1e9/(peak*world),
         "euler_step": {"ms_per_step": ms_euler, "Gfaces/s": nf_glob/(ms_euler*1e-3)/1e9,
@@ -437,7 +478,7 @@ def main():
         ach_face = bB/t_face/1e9
         line["kernels_ms"] = {"gradient_limiter_pass": t_cell*1e3, "face_pass": t_face*1e3, "timed_evals": ntimed}
         line["roofline"] = {"bound": "hbm", "kernel": "face_kernel (reconstruct + flux + spectral radius + accumulate)",
-                            "achieved": ach_face, "peak": peak, "unit": "GB/s", "frac": ach_face/peak, "frac_of_nominal_8000_GBs": ach_face/8000.0, "traffic": traffic,
+                            "achieved": ach_face, "peak": peak, "unit": "GB/s", "frac": ach_face/peak, "frac_of_nominal_8000_GBs": ach_face/8000.0, "traffic": traffic, "traffic_source": traffic_src,
                             "algorithmic_bytes_per_launch": bB, "peak_source": peak_src,
                             "cell_pass": {"achieved": bA/t_cell/1e9, "frac": bA/t_cell/1e9/peak,
                                           "algorithmic_bytes_per_launch": bA}}
@@ -447,9 +488,10 @@ def main():
                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach/peak, "frac_of_nominal_8000_GBs": ach/8000.0, "traffic": None,
                             "algorithmic_bytes_per_launch": (bA + bB)/world, "peak_source": peak_src}
     if not args.no_cpu_baseline and world == 1:
-        gf, ms, ci = cpu_reference(args.cpu_cells, args.numerics, 6, 2)
+        gf, ms, ci = cpu_reference(args.cpu_cells if args.cpu_cells else args.cells, args.numerics, 6, 2,
+                                   prebuilt=None if args.cpu_cells else (arrs, u, (nx, ny)))
         line["cpu_baseline"] = {"value": gf, "unit": "Gfaces/s", "cores": ci["cores"], "kind": ci["kind"],
-                                "sample": ci["sample"], "ms_per_eval": ms}
+                                "sample": ci["sample"], "ms_per_eval": ms, **ci["extra"]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -151,6 +151,33 @@ def cell_centres(coords, nnode, inpoel):
     return np.stack([cx, cy], axis=1)
 
 
+def hilbert_order(rc, order=20):
+    """new2old permutation of the points rc along a Hilbert curve on a 2^order grid over their bounding box: the numpy
+    twin of fvg_umesh_hilbert_ordering (csrc/device_mesh.cu hilbert_order / hilbert_d), ties broken by index. Lets a
+    process build the Hilbert-ordered benchmark mesh without loading libfvens_b200.so (bench.py --impl reference)."""
+    rc = np.asarray(rc, dtype=np.float64)
+    lo = rc.min(axis=0); hi = rc.max(axis=0)
+    span = max(hi[0] - lo[0], hi[1] - lo[1], 1e-300)
+    scale = float((1 << order) - 1)/span
+    x = ((rc[:, 0] - lo[0])*scale).astype(np.uint32)
+    y = ((rc[:, 1] - lo[1])*scale).astype(np.uint32)
+    n = np.uint32(1 << order)
+    d = np.zeros(len(rc), dtype=np.uint64)
+    s = 1 << (order - 1)
+    while s > 0:
+        s32 = np.uint32(s)
+        rx = (x & s32) != 0
+        ry = (y & s32) != 0
+        d += np.uint64(s*s)*((3*rx.astype(np.uint64)) ^ ry.astype(np.uint64))
+        flip = ~ry & rx
+        x = np.where(flip, n - np.uint32(1) - x, x)
+        y = np.where(flip, n - np.uint32(1) - y, y)
+        swap = ~ry
+        x, y = np.where(swap, y, x), np.where(swap, x, y)
+        s >>= 1
+    return np.argsort(d, kind="stable").astype(np.int32)
+
+
 def freestream_state(gamma, Minf, aoa):
     """IdealGasPhysics::compute_freestream_state (src/physics/aphysics.cpp:44-58)"""
     pinf = 1.0/(gamma*Minf*Minf)
