@@ -268,6 +268,9 @@ def main():
                  f"python -m torch.distributed.run --nnodes=1 --nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # everything runs on one non-default stream (CUDA graphs of the multi-GPU evaluation cannot be captured on the legacy
+    # default stream; torch.cuda.Event and the library's timing events are recorded on this same stream)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -301,7 +304,7 @@ def main():
         ids = torch.from_numpy(df.global_ids.astype(np.int64))
         du = torch.zeros((df.ncell + df.nghost, 4), dtype=torch.float64, device=dev)
         du[:nc] = torch.from_numpy(u[ids[:nc].numpy()]).to(dev)
-        halo_launches = 2          # pack kernels per evaluation (state rows, gradient rows)
+        halo_launches = 0 if df.engine is not None else 2      # split schedule: send kernels per evaluation (state rows, gradient rows)
 
         def evaluate():
             df.residual(du, res, dtm, gettimesteps=True, exchange_state=True)
@@ -408,7 +411,8 @@ def main():
 
         def step():
             df.euler_step(cur[0], cur[1], 0.5, n2)
-            dist.all_reduce(n2)
+            if not df.norm_is_global:
+                dist.all_reduce(n2)
             cur.reverse()
     for _ in range(3):
         step()
@@ -456,15 +460,20 @@ def main():
         "layout": {"cells_on_rank0": nc, "ghost_cells_on_rank0": int(info.nghost),
                    "tile_cells": info.tile_cells, "cut_face_duplicates_rank0": info.ncut_dup,
                    "parallelism": "single GPU" if world == 1 else
-                   f"{world} GPUs, {'coordinate-bisection' if args.partition == 'rcb' else 'Hilbert-curve'} partition, one ghost layer; per evaluation: state halo, gradient pass, "
-                   f"gradient halo, face pass; halo transport: " + (("peer-mapped windows over NVLink (CUDA IPC, direct stores + flags)"
-                                                  + (", received inside the consuming kernels" if df.fused_recv else ", one send+receive kernel per exchange"))
-                                                 if df.halo_kind == "peer" else "NCCL all-to-all with row splits")},
+                   f"{world} GPUs, {'coordinate-bisection' if args.partition == 'rcb' else 'Hilbert-curve'} partition, one ghost layer; "
+                   + ("per evaluation: gradient pass + face pass, one C call replayed from a CUDA graph; the producing kernels store the "
+                      "neighbours' state / gradient rows into their peer-mapped windows over NVLink (CUDA IPC), the consuming kernels wait "
+                      "on arrival flags in the partition-boundary tiles, which run last (fvg_dist_residual)" if df.halo_kind == "fused" else
+                      "per evaluation: state halo, gradient pass, gradient halo, face pass; halo transport: "
+                      + (("peer-mapped windows over NVLink (CUDA IPC, direct stores + flags)"
+                          + (", received inside the consuming kernels" if df.fused_recv else ", one send+receive kernel per exchange"))
+                         if df.halo_kind == "peer" else "NCCL all-to-all with row splits"))},
         "residual_evals_per_s": 1e3/ms_step,
         "residual_roofline_frac": (bA + bB)/(ms_step*1e-3)/1e9/(peak*world),
         "euler_step": {"ms_per_step": ms_euler, "Gfaces/s": nf_glob/(ms_euler*1e-3)/1e9,
                        "note": "fused residual + local dt + forward-Euler update + energy-residual norm"
-                               + (" + all-reduce of the norm" if world > 1 else "")},
+                               + ((" + norm reduced over the ranks through the peer windows (no NCCL call)" if df.norm_is_global
+                                   else " + all-reduce of the norm") if world > 1 else "")},
         "e2e": {"value": nf_glob/t_e2e.item()/1e9, "unit": "Gfaces/s", "ms_per_step": t_e2e.item()*1e3,
                 "h2d_bytes_per_step": 32*nc, "d2h_bytes_per_step": 40*nc,
                 "note": "pinned host buffers: H2D u, kernels" + (" + halos" if world > 1 else "") + ", D2H residual + dt"

@@ -76,22 +76,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 }
 
 
-// Programmatic dependent launch (build variant -DFVG_PDL, see tools/variant_sweep.sh): a kernel launched with the
-// programmatic-stream-serialization attribute may start while its predecessor in the stream is still running; it must
-// not touch what the predecessor writes (or overwrite what it reads) before pdl_wait(), which returns once the
-// predecessor has completed and its writes are visible. pdl_launch_dependents() lets the successor's CTAs be scheduled
-// as soon as every CTA of this grid has started. Both are no-ops in the default build.
-__device__ __forceinline__ void pdl_wait()
-{
-#ifdef FVG_PDL
-	asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void pdl_launch_dependents()
-{
-#ifdef FVG_PDL
-	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while
+// its predecessor in the stream is still running; it must not touch what the predecessor writes (or overwrite what it
+// reads) before pdl_wait(), which returns once the predecessor has completed and its writes are visible.
+// pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as every CTA of this grid has started. Without
+// the launch attribute (FVG_PDL=0) both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 } // namespace fvg

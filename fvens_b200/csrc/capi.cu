@@ -55,14 +55,7 @@ static FaceLauncher face_launcher(int flux)
 }
 
 template <typename T>
-static int dev_alloc(fvg_flow *f, T **p, size_t count)
-{
-	void *q = nullptr;
-	FVG_CUDA(cudaMalloc(&q, std::max<size_t>(count, 1)*sizeof(T)));
-	f->allocs.push_back(q);
-	*p = static_cast<T*>(q);
-	return 0;
-}
+static int dev_alloc(fvg_flow *f, T **p, size_t count) { return flow_dev_alloc(f, p, count); }
 
 static int limiter_mode(int recon)
 {
@@ -71,20 +64,22 @@ static int limiter_mode(int recon)
 	return 0;
 }
 
-/// Tile range (and list) of a split pass: explicit range if given, else the flow's selected part
-static void resolve_tiles(const fvg_flow *f, int &tile0, int &tile1, const int *&tlist)
+/// Tile range and order of a pass: explicit range (natural order) if given, else the flow's selected part; the fused
+/// multi-GPU evaluation walks all tiles, interior tiles first
+static void resolve_tiles(const fvg_flow *f, int &tile0, int &tile1, bool &ordered)
 {
-	tlist = nullptr;
+	ordered = false;
 	const DMesh &D = f->mesh->d;
+	if(f->roles.active && D.tile_order && tile1 < 0) { ordered = true; tile0 = 0; tile1 = D.ntile; return; }
 	if(tile1 >= 0 || f->part == 0 || !D.tile_order) return;
-	tlist = D.tile_order;
+	ordered = true;
 	if(f->part == 1) { tile0 = 0; tile1 = D.ntile_interior; }
 	else if(f->part == 2) { tile0 = D.ntile_interior; tile1 = D.ntile; }
 	else { tile0 = 0; tile1 = D.ntile; }
 }
 
-/// Pass A on a device-ordered conserved state: fills f->d_lg and/or f->d_gu
-static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s, int tile0 = 0, int tile1 = -1)
+/// Pass A on a conserved state (device order, or caller order with src_idx / ucopy): fills f->d_lg and/or f->d_gu
+int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s, int tile0, int tile1, const int *src_idx, double *ucopy)
 {
 	const FlowPlan &P = f->plan;
 	if(!P.order2) return 0;
@@ -92,15 +87,20 @@ static int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s, int t
 	a.m = f->mesh->d; a.gas = f->gas; a.u = u; a.ug = nullptr; a.gin = nullptr;
 	a.bnd_policy = P.bnd_policy;
 	a.prefetch_distance = f->prefetch_distance;
-	resolve_tiles(f, tile0, tile1, a.tlist);
+	resolve_tiles(f, tile0, tile1, a.ordered);
 	a.tile0 = tile0; a.tile1 = tile1;
 	a.gs_u = f->gs_u;
+	a.src_idx = src_idx; a.halo_src = src_idx ? f->mesh->d.halo_src : nullptr; a.ucopy = ucopy;
+	if(f->roles.active) a.dist = f->roles.cell;
 	int rc;
 	if(P.recon == FVG_RECON_WENO) {
 		a.lg = nullptr; a.gu = f->d_gu;
 		if((rc = launch_cell_kernel(P.gradient, 0, false, a, s)) != 0) return rc;
 		f->launches++;
-		if((rc = launch_weno_kernel(f->mesh->d, f->gas.limiter_param, f->d_gu, f->d_lg, s)) != 0) return rc;
+		WenoArgs w;
+		w.m = f->mesh->d; w.lambda = f->gas.limiter_param; w.gu = f->d_gu; w.lg = f->d_lg; w.ordered = a.ordered;
+		if(f->roles.active) w.dist = f->roles.weno;
+		if((rc = launch_weno_kernel(w, s)) != 0) return rc;
 		f->launches++;
 	}
 	else if(P.recon == FVG_RECON_VANALBADA) {
@@ -158,8 +158,8 @@ int make_row_tensor_map(CUtensorMap *tm, const double *base, size_t nrows, int w
 	return 0;
 }
 
-static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumulate, int gettimesteps,
-                         double *res, double *dtm, double cfl, double *unew, cudaStream_t s, int tile0 = 0, int tile1 = -1)
+int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumulate, int gettimesteps,
+                  double *res, double *dtm, double cfl, double *unew, cudaStream_t s, int tile0, int tile1, const int *dst_idx)
 {
 	const FlowPlan &P = f->plan;
 	FaceArgs a;
@@ -168,9 +168,11 @@ static int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumul
 	a.epilogue = epilogue; a.accumulate = accumulate; a.gettimesteps = gettimesteps;
 	a.res = res; a.dtm = dtm; a.cfl = cfl; a.unew = unew; a.partial = f->d_partial;
 	a.prefetch_distance = f->prefetch_distance;
-	resolve_tiles(f, tile0, tile1, a.tlist);
+	resolve_tiles(f, tile0, tile1, a.ordered);
 	a.tile0 = tile0; a.tile1 = tile1;
 	a.gs_u = f->gs_u; a.gs_g = f->gs_g;
+	a.dst_idx = dst_idx;
+	if(f->roles.active) a.dist = f->roles.face;
 	const int recon = !P.order2 ? FR_FIRST : (P.recon == FVG_RECON_VANALBADA ? FR_MUSCL : FR_LINEAR);
 	int rt = make_row_tensor_map(&a.tm_u, u, (size_t)a.m.ncell, 4, tile_box_rows(a.m.TC));
 	if(rt == 0 && recon == FR_LINEAR) rt = make_row_tensor_map(&a.tm_g, a.lg, (size_t)a.m.ncell, 8, tile_box_rows(a.m.TC));
@@ -531,17 +533,18 @@ int fvg_residual(fvg_flow *f, const double *d_u, double *d_res, int accumulate, 
 		if((rc = run_face_pass(f, d_u, EP_RESIDUAL, accumulate, gettimesteps, d_res, d_dtm, 0.0, nullptr, s)) != 0) return rc;
 		return mark(f, s);
 	}
-	// renumbered mesh: gather the state into device order, scatter the results back
+	// renumbered mesh, caller-ordered arrays. Second order: the permutation is fused into the passes - the gradient
+	// pass gathers the state rows through new2old and leaves a device-ordered copy for the face pass, whose residual /
+	// time-step stores go straight to the caller's rows (no permutation kernels, SURVEY 8b drop-in path)
 	if((rc = ensure(f, &f->d_uperm, 4*(size_t)n)) != 0) return rc;
-	if((rc = ensure(f, &f->d_rperm, 4*(size_t)n)) != 0) return rc;
-	if((rc = ensure(f, &f->d_dtperm, n)) != 0) return rc;
+	if(f->plan.order2) {
+		if((rc = run_gradient_pass(f, d_u, s, 0, -1, D.new2old, f->d_uperm)) != 0) return rc;
+		return run_face_pass(f, f->d_uperm, EP_RESIDUAL, accumulate, gettimesteps, d_res, d_dtm, 0.0, nullptr, s, 0, -1, D.new2old);
+	}
+	// first order (no gradient pass to gather in): one gather kernel, then the face pass scatters its stores
 	if((rc = launch_permute_rows(d_u, f->d_uperm, D.new2old, n, 4, true, false, s)) != 0) return rc;
-	if((rc = run_gradient_pass(f, f->d_uperm, s)) != 0) return rc;
-	if((rc = run_face_pass(f, f->d_uperm, EP_RESIDUAL, 0, gettimesteps, f->d_rperm, f->d_dtperm, 0.0, nullptr, s)) != 0) return rc;
-	if((rc = launch_permute_rows(f->d_rperm, d_res, D.new2old, n, 4, false, accumulate != 0, s)) != 0) return rc;
-	if(gettimesteps && (rc = launch_permute_rows(f->d_dtperm, d_dtm, D.new2old, n, 1, false, false, s)) != 0) return rc;
-	f->launches += gettimesteps ? 3 : 2;
-	return 0;
+	f->launches++;
+	return run_face_pass(f, f->d_uperm, EP_RESIDUAL, accumulate, gettimesteps, d_res, d_dtm, 0.0, nullptr, s, 0, -1, D.new2old);
 }
 
 /** Plan of the chunked host-buffer pipeline. The tiles are cut into K ranges of consecutive tiles (compact patches
@@ -717,7 +720,11 @@ int fvg_face_values(fvg_flow *f, const double *d_uprim, const double *d_ug, cons
 	if(rc == 0 && P.recon != FVG_RECON_NONE && P.recon != FVG_RECON_VANALBADA) {
 		const cudaError_t e = cudaMallocAsync((void**)&slg, sizeof(double)*8*(size_t)D.ncell, s);
 		if(e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
-		if(rc == 0 && P.recon == FVG_RECON_WENO) { rc = launch_weno_kernel(D, f->gas.limiter_param, g, slg, s); f->launches++; }
+		if(rc == 0 && P.recon == FVG_RECON_WENO) {
+			WenoArgs w;
+			w.m = D; w.lambda = f->gas.limiter_param; w.gu = g; w.lg = slg;
+			rc = launch_weno_kernel(w, s); f->launches++;
+		}
 		else if(rc == 0) {
 			CellArgs a;
 			a.m = D; a.gas = f->gas; a.u = u; a.ug = d_ug; a.gin = g; a.lg = slg; a.gu = nullptr;
@@ -918,7 +925,11 @@ int fvg_gradient_pass(fvg_flow *f, const double *d_u, int stage, void *stream)
 	a.prefetch_distance = f->prefetch_distance;
 	int rc;
 	if(stage == 0) { a.lg = nullptr; a.gu = f->d_gu; rc = launch_cell_kernel(P.gradient, 0, false, a, s); }
-	else rc = launch_weno_kernel(f->mesh->d, f->gas.limiter_param, f->d_gu, f->d_lg, s);
+	else {
+		WenoArgs w;
+		w.m = f->mesh->d; w.lambda = f->gas.limiter_param; w.gu = f->d_gu; w.lg = f->d_lg;
+		rc = launch_weno_kernel(w, s);
+	}
 	if(rc == 0) f->launches++;
 	return rc;
 }
@@ -988,7 +999,18 @@ int fvg_euler_step(fvg_flow *f, double *d_u, double cfl, double *d_resnorm2, voi
 	const size_t n = D.ncell;
 	int rc;
 	if((rc = ensure(f, &f->d_u2, 4*n)) != 0) return rc;
-	if(f->mesh->identity_perm) {
+	if(f->plan.order2) {
+		// the gradient pass leaves a device-ordered copy of the state (gathered through the permutation when the mesh is
+		// renumbered); the face pass reads only that copy, so it can store the new state straight into the caller's rows
+		const int *perm = f->mesh->identity_perm ? nullptr : D.new2old;
+		if((rc = mark(f, s)) != 0) return rc;
+		if((rc = run_gradient_pass(f, d_u, s, 0, -1, perm, f->d_u2)) != 0) return rc;
+		if((rc = mark(f, s)) != 0) return rc;
+		if((rc = run_face_pass(f, f->d_u2, EP_STEP, 0, 1, nullptr, nullptr, cfl, d_u, s, 0, -1, perm)) != 0) return rc;
+		if((rc = mark(f, s)) != 0) return rc;
+		if((rc = launch_final_norm(f->d_partial, f->mesh->d.ntile*(FACE_BLOCK/32), f->d_norm, s)) != 0) return rc;
+		f->launches++;
+	} else if(f->mesh->identity_perm) {
 		if((rc = step_device_order(f, d_u, f->d_u2, cfl, s)) != 0) return rc;
 		FVG_CUDA(cudaMemcpyAsync(d_u, f->d_u2, 4*n*sizeof(double), cudaMemcpyDeviceToDevice, s));
 	} else {

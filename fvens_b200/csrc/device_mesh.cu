@@ -640,8 +640,31 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	UP(m->h_send_idx, send_idx)
 	D.ntile_interior = ntile_interior;
 	if(tile_order.empty()) D.tile_order = nullptr; else { UP(tile_order, tile_order) }
+	{
+		// one 48-byte record per tile with everything a kernel needs to start on it (three 16-byte pieces, fetched into
+		// shared memory by cp.async ahead of time): in natural tile order and, on a partitioned mesh, interior tiles first
+		std::vector<int4> tdesc(3*(size_t)ntile), tdesc_ord;
+		for(int t = 0; t < ntile; t++) {
+			tdesc[3*(size_t)t] = make_int4(t, tcell0[t], tcell0[t+1] - tcell0[t], thoff[t]);
+			tdesc[3*(size_t)t+1] = make_int4(thoff[t+1] - thoff[t], fsoff[t], fsoff[t+1] - fsoff[t], tbnd[t].w);
+			tdesc[3*(size_t)t+2] = make_int4(tbnd[t].x, tbnd[t].y, tbnd[t].z, 0);
+		}
+		UP(tdesc, tdesc)
+		D.tdesc_ord = nullptr;
+		if(!tile_order.empty()) {
+			tdesc_ord.resize(3*(size_t)ntile);
+			for(int i = 0; i < ntile; i++) for(int q = 0; q < 3; q++) tdesc_ord[3*(size_t)i+q] = tdesc[3*(size_t)tile_order[i]+q];
+			UP(tdesc_ord, tdesc_ord)
+		}
+	}
+	D.halo_src = nullptr;
 	if(m->identity_perm) { D.new2old = nullptr; D.old2new = nullptr; }
-	else { UP(d2g, new2old) D.old2new = nullptr; }
+	else {
+		UP(d2g, new2old) D.old2new = nullptr;
+		std::vector<int> halo_src(thalo.size());
+		for(size_t q = 0; q < thalo.size(); q++) halo_src[q] = d2g[thalo[q]];
+		UP(halo_src, halo_src)
+	}
 #undef UP
 	m->h_tcell0 = tcell0; m->h_thoff = thoff; m->h_thalo = thalo;
 	// per-tile send lists: the rows a tile's cells contribute to the neighbours' ghost blocks, as (tile-local cell,

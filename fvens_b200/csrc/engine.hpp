@@ -6,6 +6,7 @@
 #include <vector>
 #include <cstdint>
 #include "gas.cuh"
+#include "dist_dev.cuh"
 #include "../../include/fvens_b200.h"
 
 namespace fvg {
@@ -78,11 +79,15 @@ struct DMesh {
 	// permutation (null when identity)
 	const int *new2old;
 	const int *old2new;
+	const int *halo_src;    ///< new2old of every entry of thalo (null when identity): caller-ordered halo gathers without a dependent load
 	const int *send_idx;    ///< [nsend] own cells packed for the peers, grouped by peer rank
 	// tiles that see no ghost cell first, then the tiles on the partition boundary (null on an unpartitioned mesh):
 	// the first group can run while the ghost rows are still being exchanged
 	const int *tile_order;
 	int ntile_interior;
+	/// one record of three int4 per tile: {tile, c0, nc, h0} {nh, e0, ne, tbnd.w} {tbnd.x, tbnd.y, tbnd.z, 0}; tdesc in
+	/// natural tile order, tdesc_ord in the order of tile_order (null when there is none)
+	const int4 *tdesc, *tdesc_ord;
 };
 
 /// Where a pass finds the ghost rows of an array when they are NOT copied into the array: in the halo window of
@@ -93,6 +98,17 @@ struct GhostSrc {
 	const int *recv_off = nullptr;             ///< [nranks+1] ghost-row offsets per source rank
 	unsigned long long seq = 0;
 	int nranks = 0;
+};
+
+/// Role of one kernel launch in the fused multi-GPU evaluation (see dist_dev.cuh). d == nullptr: not part of one.
+struct DistRole {
+	const DistDev *d = nullptr;
+	unsigned wait = 0;         ///< bit mask of row types whose ghost rows this kernel reads from the window
+	unsigned push = 0;         ///< bit mask of row types this kernel produces and pushes per tile (X_U: the step epilogue)
+	int first = 0;             ///< first kernel of the evaluation: its prologue pushes the state rows
+	int last = 0;              ///< last kernel of the evaluation: its last CTA advances the evaluation counter
+	int force_push = 0;        ///< push the state rows in the prologue even if a step epilogue is on record as having done so
+	int visc_type = X_LG;      ///< row type of the gradients the viscous flux reads (X_LG when no limiter alters them)
 };
 
 constexpr unsigned NB_NONE = 0xFFFFu;   ///< no such local face (4th slot of a triangle)
@@ -171,6 +187,8 @@ struct fvg_flow {
 	int prefetch_distance = 0;
 	int part = 0;                  ///< tiles the split passes cover: 0 all, 1 interior, 2 partition boundary, 3 all, interior first
 	fvg::GhostSrc gs_u, gs_g;      ///< set by fvg_flow_ghost_source
+	/// fused multi-GPU evaluation (dist.cu): while `active`, the passes run over all tiles, interior tiles first, with these roles
+	struct DistRoles { bool active = false; fvg::DistRole cell, weno, face; } roles;
 	// optional per-pass timing (CUDA events on the launching stream)
 	bool timing = false;
 	std::vector<cudaEvent_t> ev;   ///< triples: before pass A, between A and B, after B
@@ -190,11 +208,30 @@ struct CellArgs {
 	int bnd_policy;
 	int prefetch_distance; ///< tiles ahead whose operands are pulled into L2 (0 = off)
 	int tile0 = 0, tile1 = -1;   ///< tile range of this launch (tile1 < 0: all tiles)
-	const int *tlist = nullptr;  ///< when set, the range indexes this list of tiles
+	const int4 *tdesc = nullptr; ///< tile sequence the range indexes (DMesh::tdesc or tdesc_ord; set by the launcher from `ordered`)
+	bool ordered = false;        ///< walk the tiles in the order of DMesh::tile_order (interior tiles first)
 	GhostSrc gs_u;               ///< ghost rows of u (partition-boundary tiles wait for them inside the kernel)
+	DistRole dist;               ///< fused multi-GPU evaluation (dist.cu): what this launch pushes and waits for
+	const int *src_idx = nullptr;    ///< caller-ordered state: row of `u` holding device cell i (null: u is in device order)
+	const int *halo_src = nullptr;   ///< ... and the same for the entries of thalo (precomputed: no dependent index load)
+	double *ucopy = nullptr;         ///< ... the own rows are also written here in device order (read by the face pass)
 };
 int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaStream_t s);
-int launch_weno_kernel(const DMesh &m, double lambda, const double *gu, double *lg, cudaStream_t s);
+struct WenoArgs {
+	DMesh m;
+	double lambda;
+	const double *gu;      ///< [ncell(+nghost)][8] unlimited gradients
+	double *lg;            ///< out: [ncell][8]
+	const int4 *tdesc = nullptr;
+	bool ordered = false;
+	GhostSrc gs_gu;        ///< ghost rows of gu
+	DistRole dist;
+};
+int launch_weno_kernel(const WenoArgs &a, cudaStream_t s);
+/// persistent-grid size for a kernel: SMs x resident CTAs, cached per (device, kernel, shared-memory size)
+int resident_ctas(const void *kernel, int block, size_t smem);
+/// launches with the programmatic-dependent-launch attribute when FVG_PDL is not "0"
+bool pdl_enabled();
 
 struct FaceValArgs {
 	DMesh m;
@@ -256,8 +293,12 @@ struct FaceArgs {
 	CUtensorMap tm_u;      ///< u as [ncell][4]
 	CUtensorMap tm_g;      ///< lg as [ncell][8] (linear reconstruction only)
 	int tile0 = 0, tile1 = -1;   ///< tile range of this launch (tile1 < 0: all tiles)
-	const int *tlist = nullptr;  ///< when set, the range indexes this list of tiles
+	const int4 *tdesc = nullptr; ///< tile sequence the range indexes (DMesh::tdesc or tdesc_ord; set by the launcher from `ordered`)
+	bool ordered = false;        ///< walk the tiles in the order of DMesh::tile_order (interior tiles first)
 	GhostSrc gs_u, gs_g;         ///< ghost rows of u and of the reconstruction gradients, see GhostSrc
+	GhostSrc gs_v;               ///< ghost rows of the viscous flux's gradients (fused multi-GPU evaluation only)
+	DistRole dist;               ///< fused multi-GPU evaluation (dist.cu)
+	const int *dst_idx = nullptr;    ///< caller-ordered outputs: row of res / dtm / unew that receives device cell i (null: device order)
 };
 /// Rows per TMA box of the per-cell row arrays (a box has at most 256 rows and must tile TC exactly)
 __host__ __device__ inline int tile_box_rows(int TC) {
@@ -275,6 +316,19 @@ int launch_face_hll(int recon, int visc, const FaceArgs &a, cudaStream_t s);
 int launch_face_hllc(int recon, int visc, const FaceArgs &a, cudaStream_t s);
 
 GasParams make_gas(const fvg_physics &p, double limiter_param);
+/// Pass A / pass B on a device-ordered conserved state (capi.cu); used by the C ABI entry points and by dist.cu
+int run_gradient_pass(fvg_flow *f, const double *u, cudaStream_t s, int tile0 = 0, int tile1 = -1,
+                      const int *src_idx = nullptr, double *ucopy = nullptr);
+int run_face_pass(fvg_flow *f, const double *u, int epilogue, int accumulate, int gettimesteps,
+                  double *res, double *dtm, double cfl, double *unew, cudaStream_t s, int tile0 = 0, int tile1 = -1,
+                  const int *dst_idx = nullptr);
+template <typename T> int flow_dev_alloc(fvg_flow *f, T **p, size_t count) {
+	void *q = nullptr;
+	FVG_CUDA(cudaMalloc(&q, (count > 0 ? count : 1)*sizeof(T)));
+	f->allocs.push_back(q);
+	*p = static_cast<T*>(q);
+	return 0;
+}
 } // namespace fvg
 struct fvg_halo;
 extern "C" int fvg_halo_ghost_source(fvg_halo *h, unsigned long long token, fvg::GhostSrc *out);   // halo.cu (internal)

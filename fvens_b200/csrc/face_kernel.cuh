@@ -52,6 +52,11 @@ __device__ __forceinline__ int tile_global(const DMesh &M, int t, int c0, int nc
 	return loc < (unsigned)nc ? c0 + (int)loc : M.thalo[M.thoff[t] + (int)loc - nc];
 }
 
+/// ... with the tile's halo offset at hand
+__device__ __forceinline__ int tile_global_h(const DMesh &M, int h0, int c0, int nc, unsigned loc) {
+	return loc < (unsigned)nc ? c0 + (int)loc : M.thalo[h0 + (int)loc - nc];
+}
+
 /// u_face = u_cell + g . (gr - rc) for the four primitive variables (reconstruction_utils.hpp:17-32);
 /// g = 8 gradients in GradBlock order, in shared memory
 __device__ __forceinline__ void extrapolate4(const double pc[4], const double *g, double dx, double dy, double pf[4]) {
@@ -78,7 +83,7 @@ __device__ __forceinline__ double muscl_term(double delta, double dlr) {
 /// planes): entry e then sits in bank group e mod 8, consecutive entries (phase B) are conflict-free, and the
 /// per-cell scatters / gathers of phases A and C are conflict-free by the placement of the entries (device_mesh.cu).
 struct FaceSmem {
-	int fsL, fsR, sgr, sn, slen, sLR, sord, hu, hg, hrc, su, sg, src, scl, sar, cbuf, bar, red, total;   // byte offsets
+	int fsL, fsR, sgr, sn, slen, sLR, sord, hu, hg, hrc, su, sg, src, scl, sar, cbuf, bar, red, ring, gptr, total;   // byte offsets
 	__host__ __device__ FaceSmem(int TC, int EMAX, int HMAX, bool mids, bool linear) {
 		int o = 0;
 		su = o; o += TC*32;                    // own cells: state, reconstruction gradient (both hardware-swizzled: keep them
@@ -98,6 +103,8 @@ struct FaceSmem {
 		scl = o; sar = o + TC*16; o += 2*cbuf;
 		bar = o; o += 16;                      // two mbarriers
 		red = o; o += 8*(FACE_BLOCK/32);       // warp partials of the norm
+		ring = o; o += 3*48;                   // descriptor records of the current and the next two tiles
+		gptr = o; o += 32;                     // fused multi-GPU evaluation: evaluation number, window areas of the ghost rows
 		total = o;
 	}
 };
@@ -137,16 +144,27 @@ __device__ __forceinline__ void ghost_wait(const GhostSrc &g, unsigned long long
 	__syncthreads();
 }
 
-/// Descriptor of one tile (all uniform across the CTA)
-struct TileDesc { int c0, nc, h0, nh, e0, ne, nreal, ghost; };
-__device__ __forceinline__ TileDesc load_tile_desc(const DMesh &M, int t) {
+/// Row `g` of a device-ordered [.][width] array whose ghost rows (g >= ncell) may live in a halo window instead
+__device__ __forceinline__ const double *ghost_aware_row(const double *arr, const double *win_rows, int ncell, int g, int width) {
+	return (g >= ncell && win_rows) ? win_rows + (size_t)width*(size_t)(g - ncell) : arr + (size_t)width*(size_t)g;
+}
+
+/// Descriptor of one tile (all uniform across the CTA), unpacked from the tile's 48-byte record (DMesh::tdesc): the
+/// records of the next two tiles of a CTA travel into a small shared-memory ring by cp.async while the current tile
+/// computes, so no descriptor is held in registers across a tile and none is waited for
+struct TileDesc { int t, c0, nc, h0, nh, e0, ne, nreal, ghost, cut0, bnd0; };
+__device__ __forceinline__ TileDesc unpack_tile_desc(const int4 *rec) {
+	const int4 a = rec[0], b = rec[1], c = rec[2];
 	TileDesc D;
-	D.c0 = M.tcell0[t]; D.nc = M.tcell0[t+1] - D.c0;
-	D.h0 = M.thoff[t]; D.nh = M.thoff[t+1] - D.h0;
-	D.e0 = M.fsoff[t]; D.ne = M.fsoff[t+1] - D.e0;
-	const int w = M.tbnd[t].w;
-	D.nreal = D.ne - (w & 0xFFFF); D.ghost = w >> 16;
+	D.t = a.x; D.c0 = a.y; D.nc = a.z; D.h0 = a.w;
+	D.nh = b.x; D.e0 = b.y; D.ne = b.z;
+	D.nreal = D.ne - (b.w & 0xFFFF); D.ghost = b.w >> 16;
+	D.cut0 = c.x; D.bnd0 = c.y;
 	return D;
+}
+/// threads 0..2 of a CTA: asynchronous copy of the record at position `pos` of the launch's tile sequence into `slot`
+__device__ __forceinline__ void fetch_tile_desc(int4 *slot, const int4 *tdesc, int pos) {
+	if(threadIdx.x < 3) cp_async16(slot + threadIdx.x, tdesc + 3*(size_t)pos + threadIdx.x);
 }
 
 /** Persistent CTAs (two per SM), each walking over tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -195,6 +213,12 @@ face_kernel(const __grid_constant__ FaceArgs A)
 
 	const int tid = threadIdx.x;
 	const double *const gsrc = RECON == FR_MUSCL ? A.gu : A.lg;     // gradients used by the reconstruction
+	// where the ghost rows are: in the arrays, in the window of a posted exchange (legacy split passes: A.gs_*), or in
+	// this evaluation's areas of the fused multi-GPU evaluation (set below, once the evaluation number is known)
+	// (kept in shared memory, not in registers: they are read once per tile)
+	int4 *const ring = reinterpret_cast<int4*>(smraw + S.ring);
+	struct GhostPtrs { unsigned long long dk; const double *u, *g, *v; };
+	GhostPtrs *const gp = reinterpret_cast<GhostPtrs*>(smraw + S.gptr);
 
 	// issue helpers (thread 0 only for the bulk copies). 8-byte rows (area) are copied from the even cell below c0.
 	auto issue_AC = [&](const TileDesc &D, int buf) {
@@ -226,11 +250,11 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		if(tid < nh) {
 			// a ghost cell's rows may live in a halo window instead of the arrays (in-kernel receive)
 			const bool gh = g >= M.ncell;
-			const double *const urow = (gh && A.gs_u.rows) ? A.gs_u.rows + 4*(size_t)(g - M.ncell) : A.u + 4*(size_t)g;
+			const double *const urow = (gh && gp->u) ? gp->u + 4*(size_t)(g - M.ncell) : A.u + 4*(size_t)g;
 			cp_async16(hu + 4*tid, urow);
 			cp_async16(hu + 4*tid + 2, urow + 2);
 			if(MIDS) {
-				const double *const grow = (gh && A.gs_g.rows) ? A.gs_g.rows + 8*(size_t)(g - M.ncell) : gsrc + 8*(size_t)g;
+				const double *const grow = (gh && gp->g) ? gp->g + 8*(size_t)(g - M.ncell) : gsrc + 8*(size_t)g;
 				#pragma unroll
 				for(int q = 0; q < 4; q++) cp_async16(hg + 8*tid + 2*q, grow + 2*q);
 				cp_async16(hrc + tid, M.rc + g);
@@ -239,32 +263,53 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		cp_async_commit();
 	};
 
-	// this launch covers positions [tile0, tile1) of the tile list (or the tiles themselves when there is no list)
+	// this launch covers positions [tile0, tile1) of the tile sequence A.tdesc (natural order, or interior tiles first)
 	const int tend = A.tile1, G = (int)gridDim.x;
 	int ti = A.tile0 + (int)blockIdx.x;
-	if(ti >= tend) return;
-	auto tile_at = [&](int i) { return A.tlist ? A.tlist[i] : i; };
-	int t = tile_at(ti);
 	if(tid == 0 && (smem_u32(smraw) & 1023u) != 0) __trap();      // the swizzle formulas assume this alignment
-	TileDesc D = load_tile_desc(M, t);
-	// descriptors run two tiles ahead of the computation and the next tile's halo index one tile ahead, so that
-	// neither global load is waited for where it is consumed
-	TileDesc Dn = D;
-	int tnx = ti + G < tend ? tile_at(ti + G) : 0;
-	if(ti + G < tend) Dn = load_tile_desc(M, tnx);
-	if(tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+	// descriptor records run two tiles ahead of the computation (shared-memory ring) and the next tile's halo index one
+	// tile ahead (a register), so that neither global load is waited for where it is consumed
+	fetch_tile_desc(ring, A.tdesc, ti);
+	if(ti + G < tend) fetch_tile_desc(ring + 3, A.tdesc, ti + G);
+	cp_async_commit();
+	if(tid == 0) {
+		mbar_init(bar, 1); mbar_init(bar + 1, 1);
+		gp->dk = 0; gp->u = A.gs_u.rows; gp->g = A.gs_g.rows; gp->v = A.gs_v.rows;
+	}
 	pdl_launch_dependents();
-	// (PDL variant) everything above reads only the mesh; the state and gradient rows below are the previous kernels'
+	// (programmatic dependent launch) everything above reads only the mesh; the state and gradient rows below are the
+	// previous kernels' output
 	pdl_wait();
+	cp_async_wait_all();
 	__syncthreads();
+	TileDesc D = unpack_tile_desc(ring);
+	int t = D.t;
 	if(tid == 0) { issue_AC(D, 0); issue_B(D); }
+	if(A.dist.d) {
+		const DistDev *const dd = A.dist.d;
+		const unsigned long long dk = dd->ctl->k;
+		if(tid == 0) {
+			gp->dk = dk;
+			if(A.dist.wait & (1u << X_U)) gp->u = dist_ghost_rows(dd, X_U, dk);
+			if(MIDS && (A.dist.wait & (1u << (RECON == FR_MUSCL ? X_GU : X_LG)))) gp->g = dist_ghost_rows(dd, RECON == FR_MUSCL ? X_GU : X_LG, dk);
+			if(VISC != VISC_NONE && (A.dist.wait & (1u << A.dist.visc_type))) gp->v = dist_ghost_rows(dd, A.dist.visc_type, dk);
+		}
+		if(A.dist.first) dist_push_state_prologue(dd, dk, A.u, A.dist.force_push);
+		__syncthreads();
+	}
 	// in-kernel receive: a CTA waits for the neighbours' rows once, right before it gathers the halo of its first
-	// tile that sees a ghost cell (a few percent of the tiles, so for most CTAs the rows have long arrived by then)
-	const bool recv_here = A.gs_u.rows != nullptr || A.gs_g.rows != nullptr;
-	const GhostSrc &gsw = A.gs_g.rows ? A.gs_g : A.gs_u;
-	const unsigned long long wseq = A.gs_g.rows ? (A.gs_g.seq > A.gs_u.seq ? A.gs_g.seq : A.gs_u.seq) : A.gs_u.seq;
+	// tile that sees a ghost cell (interior tiles come first, so for most CTAs the rows have long arrived by then)
+	const bool recv_here = A.dist.d ? A.dist.wait != 0 : (A.gs_u.rows != nullptr || A.gs_g.rows != nullptr);
+	auto wait_for_ghost_rows = [&]() {
+		if(A.dist.d) dist_wait(A.dist.d, A.dist.wait, gp->dk);
+		else {
+			const GhostSrc &gsw = A.gs_g.rows ? A.gs_g : A.gs_u;
+			const unsigned long long wseq = A.gs_g.rows ? (A.gs_g.seq > A.gs_u.seq ? A.gs_g.seq : A.gs_u.seq) : A.gs_u.seq;
+			ghost_wait(gsw, wseq);
+		}
+	};
 	bool waited = !recv_here;
-	if(!waited && D.ghost) { ghost_wait(gsw, wseq); waited = true; }
+	if(!waited && D.ghost) { wait_for_ghost_rows(); waited = true; }
 	issue_halo(D.nh, tid < D.nh ? M.thalo[D.h0 + tid] : 0);
 
 	for(int it = 0; ti < tend; it++) {
@@ -272,14 +317,13 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		const uint4 *const scl = reinterpret_cast<const uint4*>(smraw + S.scl + (int)par*S.cbuf);
 		const double *const sar = reinterpret_cast<const double*>(smraw + S.sar + (int)par*S.cbuf);
 		const int aoff = D.c0 & 1;
-		// the next tile's descriptor and this thread's halo index for it are in flight during phase A
+		// the record of the tile after next and this thread's halo index for the next tile are in flight during phase A
 		const int tin = ti + G;
 		const bool have_next = tin < tend;
+		const int4 *const rnext = ring + 3*((it + 1) % 3);
 		int gnext = 0;
-		if(have_next && tid < Dn.nh) gnext = M.thalo[Dn.h0 + tid];
-		TileDesc Dnn = Dn;
-		int tnn = 0;
-		if(tin + G < tend) { tnn = tile_at(tin + G); Dnn = load_tile_desc(M, tnn); }
+		if(have_next) { const int nh_n = rnext[1].x, h0_n = rnext[0].w; if(tid < nh_n) gnext = M.thalo[h0_n + tid]; }
+		if(tin + G < tend) fetch_tile_desc(ring + 3*((it + 2) % 3), A.tdesc, tin + G);      // joins this tile's halo group
 
 		// ---- phase A: face states of the own cells
 		mbar_wait(bar, par);
@@ -319,16 +363,20 @@ face_kernel(const __grid_constant__ FaceArgs A)
 				double pf[4];
 				if(RECON == FR_LINEAR) extrapolate_prim(pc, ga, gb, grj[j].x, grj[j].y, rc.x, rc.y, pf);
 				else { for(int q = 0; q < 4; q++) pf[q] = pc[q]; }
-				double2 *const dst = ((cf[j] & 0x8000u) ? fsR : fsL) + e;
+				const bool right = (cf[j] & 0x8000u) != 0;
+				double2 *const dst = (right ? fsR : fsL) + e;
 				dst[0] = make_double2(pf[0], pf[1]);
 				dst[EP] = make_double2(pf[2], pf[3]);
+				// a face cut by the tile boundary: its other side is a halo cell, reconstructed in phase B, which then
+				// finds the face midpoint in that side's (otherwise unused) slot instead of fetching it from global memory
+				if(RECON == FR_LINEAR && e >= D.cut0 && e < D.bnd0) (right ? fsL : fsR)[e] = grj[j];
 			}
 		}
 		mbar_wait(bar + 1, par);
 		cp_async_wait_all();        // this tile's halo rows: gathered since the previous tile's phase B ended
 		__syncthreads();
 		// group A buffers are free: the next tile's phase-A inputs (and its stencil/area into the other C buffer)
-		if(tid == 0 && have_next) { fence_proxy_async(); issue_AC(Dn, (int)(par ^ 1u)); }
+		if(tid == 0 && have_next) { fence_proxy_async(); issue_AC(unpack_tile_desc(rnext), (int)(par ^ 1u)); }
 
 		// ---- phase B: fluxes, one real stream entry per thread and round (the list `sord` skips the padding entries, so
 		// the rounds are full: consecutive threads still take nearly consecutive entries)
@@ -345,13 +393,13 @@ face_kernel(const __grid_constant__ FaceArgs A)
 			const BCEntry &bc = A.gas.bc[Rf & 15u];
 			double sl[4], sr[4];       // face states: conserved (first order) / primitive; MUSCL: cell states
 			if(L < (unsigned)D.nc) ldp4(fsL + e, EP, sl);
-			else halo_side_state<RECON>(A, hu, hg, hrc, (int)L - D.nc, MIDS ? M.fgr[D.e0 + e] : make_double2(0,0), sl);
+			else halo_side_state<RECON>(A, hu, hg, hrc, (int)L - D.nc, RECON == FR_LINEAR ? fsL[e] : make_double2(0,0), sl);
 			if(!bnd) {
 				if(Rf < (unsigned)D.nc) ldp4(fsR + e, EP, sr);
-				else halo_side_state<RECON>(A, hu, hg, hrc, (int)Rf - D.nc, MIDS ? M.fgr[D.e0 + e] : make_double2(0,0), sr);
+				else halo_side_state<RECON>(A, hu, hg, hrc, (int)Rf - D.nc, RECON == FR_LINEAR ? fsR[e] : make_double2(0,0), sr);
 			}
-			const int gidL = (VISC != VISC_NONE || RECON == FR_MUSCL) ? tile_global(M, t, D.c0, D.nc, L) : 0;
-			const int gidR = (VISC != VISC_NONE || RECON == FR_MUSCL) ? (bnd ? gidL : tile_global(M, t, D.c0, D.nc, Rf)) : 0;
+			const int gidL = (VISC != VISC_NONE || RECON == FR_MUSCL) ? tile_global_h(M, D.h0, D.c0, D.nc, L) : 0;
+			const int gidR = (VISC != VISC_NONE || RECON == FR_MUSCL) ? (bnd ? gidL : tile_global_h(M, D.h0, D.c0, D.nc, Rf)) : 0;
 
 			Side a, bs;
 			double ucl[4], ucr[4];      // conserved cell states for the viscous flux (right = ghost of the cell state)
@@ -370,9 +418,9 @@ face_kernel(const __grid_constant__ FaceArgs A)
 					bs = load_side<true>(A.gas, ur, nx, ny);
 				} else bs = side_from_prim<true>(A.gas, sr, nx, ny);
 				if(VISC != VISC_NONE) {
-					ld4(A.u + 4*(size_t)gidL, ucl);
+					ld4(ghost_aware_row(A.u, gp->u, M.ncell, gidL, 4), ucl);
 					if(bnd) ghost_state(A.gas, bc, ucl, nx, ny, ucr);
-					else ld4(A.u + 4*(size_t)gidR, ucr);
+					else ld4(ghost_aware_row(A.u, gp->u, M.ncell, gidR, 4), ucr);
 				}
 			}
 			else { // MUSCL with Van Albada limiter: sl, sr are the primitive CELL states
@@ -390,7 +438,7 @@ face_kernel(const __grid_constant__ FaceArgs A)
 				}
 				const double dx = rr.x - rl.x, dy = rr.y - rl.y;
 				double ga[4], gb[4], pfl[4], pfr[4];
-				ld4(gsrc + 8*(size_t)gidL, ga); ld4(gsrc + 8*(size_t)gidL + 4, gb);
+				{ const double *const gl_ = ghost_aware_row(gsrc, gp->g, M.ncell, gidL, 8); ld4(gl_, ga); ld4(gl_ + 4, gb); }
 				{
 					const double gx[4] = {ga[0], ga[2], gb[0], gb[2]}, gy[4] = {ga[1], ga[3], gb[1], gb[3]};
 					for(int q = 0; q < 4; q++) {
@@ -405,7 +453,7 @@ face_kernel(const __grid_constant__ FaceArgs A)
 					ghost_state(A.gas, bc, ul, nx, ny, ur);
 					bs = load_side<true>(A.gas, ur, nx, ny);
 				} else {
-					ld4(gsrc + 8*(size_t)gidR, ga); ld4(gsrc + 8*(size_t)gidR + 4, gb);
+					{ const double *const gr_ = ghost_aware_row(gsrc, gp->g, M.ncell, gidR, 8); ld4(gr_, ga); ld4(gr_ + 4, gb); }
 					const double gx[4] = {ga[0], ga[2], gb[0], gb[2]}, gy[4] = {ga[1], ga[3], gb[1], gb[3]};
 					for(int q = 0; q < 4; q++) {
 						const double dlr = sr[q] - sl[q];
@@ -431,9 +479,9 @@ face_kernel(const __grid_constant__ FaceArgs A)
 				} else rr = M.rc[gidR];
 				double gl[8], grr[8], vf[4];
 				if(RECON != FR_FIRST) {
-					ld4(A.gu + 8*(size_t)gidL, gl); ld4(A.gu + 8*(size_t)gidL + 4, gl+4);
+					{ const double *const gl_ = ghost_aware_row(A.gu, gp->v, M.ncell, gidL, 8); ld4(gl_, gl); ld4(gl_ + 4, gl+4); }
 					if(bnd) for(int q = 0; q < 8; q++) grr[q] = gl[q];
-					else { ld4(A.gu + 8*(size_t)gidR, grr); ld4(A.gu + 8*(size_t)gidR + 4, grr+4); }
+					else { const double *const gr_ = ghost_aware_row(A.gu, gp->v, M.ncell, gidR, 8); ld4(gr_, grr); ld4(gr_ + 4, grr+4); }
 				}
 				viscous_face_flux<RECON != FR_FIRST, VISC == VISC_CONST>(A.gas, nx, ny, rl.x, rl.y, rr.x, rr.y,
 					ucl, ucr, gl, grr, ul, ur, vf);
@@ -453,15 +501,17 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		__syncthreads();
 		// group B buffers are free: the next tile's entry metadata and halo rows
 		if(have_next) {
-			if(tid == 0) { fence_proxy_async(); issue_B(Dn); }
-			if(!waited && Dn.ghost) { ghost_wait(gsw, wseq); waited = true; }
-			issue_halo(Dn.nh, gnext);
+			if(tid == 0) { fence_proxy_async(); issue_B(unpack_tile_desc(rnext)); }
+			if(!waited && (rnext[1].w >> 16)) { wait_for_ghost_rows(); waited = true; }
+			issue_halo(rnext[1].x, gnext);
 		}
 
 		// ---- phase C: per-cell sums in local-face order, then the epilogue
 		double part = 0.0;
 		for(int k = tid; k < D.nc; k += FACE_BLOCK) {
 			const size_t c = (size_t)(D.c0 + k);
+			// caller-ordered outputs: the row of res / dtm / unew that belongs to device cell c
+			const size_t co = A.dst_idx ? (size_t)A.dst_idx[c] : c;
 			const uint4 cl = scl[k];
 			const double ar = sar[k + aoff];
 			const unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
@@ -489,18 +539,18 @@ face_kernel(const __grid_constant__ FaceArgs A)
 			if(A.epilogue == EP_RESIDUAL) {
 				if(A.accumulate) {
 					double o[4];
-					ld4c(A.res + 4*c, o);
+					ld4c(A.res + 4*co, o);
 					for(int v = 0; v < 4; v++) r[v] += o[v];
 				}
-				st4(A.res + 4*c, r);
-				if(A.gettimesteps) A.dtm[c] = ar/integ;
+				st4(A.res + 4*co, r);
+				if(A.gettimesteps) A.dtm[co] = ar/integ;
 			} else {
 				const double dt = ar/integ;
 				const double fac = A.cfl*dt/ar;
 				double uo[4];
 				if(k == tid) { for(int q = 0; q < 4; q++) uo[q] = uc0[q]; } else ld4(A.u + 4*c, uo);
 				uo[0] += fac*r[0]; uo[1] += fac*r[1]; uo[2] += fac*r[2]; uo[3] += fac*r[3];
-				st4(A.unew + 4*c, uo);
+				st4(A.unew + 4*co, uo);
 				part += r[3]*r[3]*ar;
 			}
 		}
@@ -512,8 +562,13 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		}
 		// phase C reads the flux slots that the next tile's phase A overwrites
 		__syncthreads();
-		ti = tin; t = tnx; tnx = tnn; D = Dn; Dn = Dnn;
+		// fused multi-GPU pseudo-time step: the tile's updated state rows go to the neighbours as the state of the next
+		// evaluation (the barrier above ordered the stores before the read-back)
+		if(A.epilogue == EP_STEP && A.dist.d && (A.dist.push & (1u << X_U))) dist_push_tile(A.dist.d, X_U, gp->dk + 1, t, D.c0, A.unew);
+		ti = tin;
+		if(have_next) { D = unpack_tile_desc(rnext); t = D.t; }
 	}
+	if(A.dist.d && A.dist.last) dist_finish_evaluation(A.dist.d, gp->dk, A.epilogue == EP_STEP && (A.dist.push & (1u << X_U)) != 0);
 }
 
 template <int FLUX, int RECON, int VISC>
@@ -527,32 +582,24 @@ static int launch_one(const FaceArgs &a, cudaStream_t s)
 		if(ea != cudaSuccess) return cuda_fail(ea, "face_kernel smem attribute", __FILE__, __LINE__);
 	}
 	if(a.m.HMAX > FACE_BLOCK) { set_error("face kernel: halo capacity exceeds the CTA size"); return FVG_ERR_INVALID; }
-	static int ctas = 0;                      // persistent CTAs: as many as are resident at once (depends on the mesh's
-	static size_t ctas_smem = 0;              // staging capacities through the shared-memory size)
-	if(ctas == 0 || ctas_smem != smem) {
-		int dev = 0, sms = 0, per = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, face_kernel<FLUX,RECON,VISC>, FACE_BLOCK, smem);
-		ctas = sms*(per > 0 ? per : 1);
-		ctas_smem = smem;
-	}
+	// persistent CTAs: as many as are resident at once (depends on the device and, through the shared-memory size, on
+	// the mesh's staging capacities)
+	const int ctas = resident_ctas((const void*)face_kernel<FLUX,RECON,VISC>, FACE_BLOCK, smem);
 	FaceArgs b = a;
 	if(b.tile1 < 0) b.tile1 = b.m.ntile;
+	b.tdesc = (b.ordered && b.m.tdesc_ord) ? b.m.tdesc_ord : b.m.tdesc;
 	const int nt = b.tile1 - b.tile0;
 	if(nt <= 0) return 0;
-#ifdef FVG_PDL
-	cudaLaunchConfig_t cfg{};
-	cfg.gridDim = dim3((unsigned)(nt < ctas ? nt : ctas)); cfg.blockDim = dim3(FACE_BLOCK); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	attr[0].val.programmaticStreamSerializationAllowed = 1;
-	cfg.attrs = attr; cfg.numAttrs = 1;
-	const cudaError_t el = cudaLaunchKernelEx(&cfg, face_kernel<FLUX,RECON,VISC>, b);
-	if(el != cudaSuccess) return cuda_fail(el, "face_kernel launch (PDL)", __FILE__, __LINE__);
-#else
-	face_kernel<FLUX,RECON,VISC><<<nt < ctas ? nt : ctas, FACE_BLOCK, smem, s>>>(b);
-#endif
+	{
+		cudaLaunchConfig_t cfg{};
+		cfg.gridDim = dim3((unsigned)(nt < ctas ? nt : ctas)); cfg.blockDim = dim3(FACE_BLOCK); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+		cfg.attrs = attr; cfg.numAttrs = 1;
+		const cudaError_t el = cudaLaunchKernelEx(&cfg, face_kernel<FLUX,RECON,VISC>, b);
+		if(el != cudaSuccess) return cuda_fail(el, "face_kernel launch", __FILE__, __LINE__);
+	}
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "face_kernel launch", __FILE__, __LINE__);
 	return 0;

@@ -106,8 +106,27 @@ class PeerHaloExchange:
         self.win.recv(arr, arr.shape[1], stream=torch.cuda.current_stream().cuda_stream)
 
 
+def _allgather_handles(handle, recv_counts, device, group):
+    """All-gather of the 64-byte IPC handles and the receive-count rows (set-up only)."""
+    world = dist.get_world_size(group)
+    mine = torch.zeros(64 + 4*world, dtype=torch.uint8)
+    mine[:64] = torch.frombuffer(bytearray(handle), dtype=torch.uint8)
+    mine[64:] = torch.from_numpy(np.ascontiguousarray(recv_counts, dtype=np.int32).view(np.uint8))
+    if dist.get_backend(group) == "nccl":      # NCCL moves device tensors; gloo (single-GPU tests) host tensors
+        mine = mine.to(device)
+    every = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine, group=group)
+    every = [e.cpu().numpy() for e in every]
+    return [e[:64].tobytes() for e in every], np.stack([e[64:].view(np.int32) for e in every])
+
+
 class DistFlow:
-    """FlowFV on one rank's subdomain + the halo exchanges. Arrays are device-ordered [ncell+nghost, .]."""
+    """FlowFV on one rank's subdomain + the halo exchanges. Arrays are device-ordered [ncell+nghost, .].
+
+    Default on GPUs (FVG_DIST=fused): the fused evaluation of libfvens_b200.so (fvg_dist_*, csrc/dist.cu) - two kernels per
+    residual, rows pushed to the neighbours by the producing kernels, one C call per evaluation replayed from a CUDA
+    graph. FVG_DIST=split selects the round-1 schedule driven from here (send kernels + split passes), kept for A/B
+    comparisons and for the CPU (gloo) tests of the exchange pattern."""
 
     def __init__(self, umesh, cell_rank, rank, nranks, phys, device, reorder="hilbert", tile_cells=256, group=None,
                  **numerics):
@@ -115,7 +134,9 @@ class DistFlow:
                                     cell_rank=cell_rank, rank=rank, nranks=nranks)
         self.flow = lib.FlowFV(self.dmesh, phys, **numerics)
         # transport: peer-mapped windows over NVLink on GPUs (FVG_HALO=nccl selects the all-to-all), gloo on the CPU
-        use_peer = torch.device(device).type == "cuda" and nranks > 1 and os.environ.get("FVG_HALO", "peer") == "peer"
+        fused = torch.device(device).type == "cuda" and nranks > 1 and os.environ.get("FVG_DIST", "fused") == "fused"
+        use_peer = (torch.device(device).type == "cuda" and nranks > 1 and os.environ.get("FVG_HALO", "peer") == "peer"
+                    and not fused)
         self.halo = PeerHaloExchange(self.dmesh, device, group) if use_peer else HaloExchange(self.dmesh, device, group)
         self.halo_kind = "peer" if use_peer else "collective"
         self.ncell, self.nghost = self.dmesh.ncell, self.dmesh.nghost
@@ -142,12 +163,42 @@ class DistFlow:
         # reconstruction or first order - the other passes read ghost rows straight from the arrays
         self.fused_recv = (use_peer and not self.overlap and not self.need_gu and not self.weno and not phys.viscous_sim
                            and os.environ.get("FVG_FUSED_RECV", "1") != "0")
+        # the fused C-level evaluation
+        self.engine = None
+        if torch.device(device).type == "cuda" and nranks > 1 and os.environ.get("FVG_DIST", "fused") == "fused":
+            self.engine = lib.DistEngine(self.flow)
+            _, rc, _ = self.dmesh.halo_lists()
+            handles, counts = _allgather_handles(self.engine.handle(), rc, device, group)
+            self.engine.connect(handles, counts)
+            dist.barrier(group=group)
+            self.halo_kind = "fused"
         if self.overlap:
             self._halo_stream = torch.cuda.Stream(device=device, priority=-1)
             self._ev_u, self._ev_g, self._ev_l = (torch.cuda.Event() for _ in range(3))
 
     def _stream(self):
         return torch.cuda.current_stream().cuda_stream
+
+    @property
+    def norm_is_global(self):
+        """True if euler_step's norm2 is already reduced over the ranks (fused engine)."""
+        return self.engine is not None
+
+    def solve_forward_euler(self, u, cfl, tol, maxiter, check_every=1):
+        """SteadyForwardEulerSolver::solve on the partitioned mesh (fvg_dist_forward_euler_solve): u [>= ncell, 4], own rows
+        updated in place. Returns (status, steps, global history)."""
+        if self.engine is None:
+            raise RuntimeError("the multi-GPU solver needs the fused engine (FVG_DIST=fused on CUDA devices)")
+        return self.engine.solve_forward_euler(u, cfl, tol, maxiter, check_every)
+
+    def check(self):
+        """Raises FvgError(COMM) if a neighbour stopped delivering rows (call at the caller's own sync points)."""
+        if self.engine is not None:
+            self.engine.status()
+        elif self.halo_kind == "peer":
+            seq = self.halo.win.status()
+            if seq:
+                raise lib.FvgError(7, f"a halo receive timed out waiting for exchange {seq}")
 
     def _gradients(self, u):
         if not self.order2:
@@ -217,6 +268,10 @@ class DistFlow:
 
     def residual(self, u, res, dtm, gettimesteps=True, exchange_state=True):
         """u [ncell+nghost,4]; res [ncell,4] (overwritten); dtm [ncell]."""
+        if self.engine is not None:
+            if not exchange_state:
+                raise ValueError("the fused evaluation always brings the neighbours' state rows")
+            return self.engine.residual(u, res, gettimesteps, dtm, accumulate=False, stream=self._stream())
         if self.fused_recv and exchange_state:
             return self._in_kernel_receive(u, lambda s: self.flow.face_pass(u, res, gettimesteps, dtm, accumulate=False, stream=s))
         if self.overlap:
@@ -228,7 +283,10 @@ class DistFlow:
         self.flow.face_pass(u, res, gettimesteps, dtm, accumulate=False, stream=self._stream())
 
     def euler_step(self, u, unew, cfl, norm2, exchange_state=True):
-        """One forward-Euler step: unew (own rows) from u; norm2 = this rank's sum of r_E^2*area (device scalar)."""
+        """One forward-Euler step: unew (own rows) from u; norm2 (device scalar) = this rank's sum of r_E^2*area - or, with
+        the fused engine, already the sum over ALL ranks (see `norm_is_global`)."""
+        if self.engine is not None:
+            return self.engine.euler_step(u, unew, cfl, norm2, stream=self._stream())
         if self.fused_recv and exchange_state:
             return self._in_kernel_receive(u, lambda s: self.flow.euler_face_pass(u, unew, cfl, norm2, stream=s))
         if self.overlap:

@@ -513,6 +513,70 @@ class PeerHaloWindow:
             pass
 
 
+class DistEngine:
+    """fvg_dist: the fused multi-GPU evaluation of one rank (include/fvens_b200.h). The caller all-gathers the handles and
+    receive counts (any transport) and passes them to connect()."""
+
+    def __init__(self, flow):
+        self.flow = flow
+        h = C.c_void_p()
+        check(load().fvg_dist_create(flow._h, C.byref(h)))
+        self._h = h
+
+    def handle(self):
+        buf = (C.c_ubyte*64)()
+        check(load().fvg_dist_ipc_handle(self._h, buf))
+        return bytes(buf)
+
+    def connect(self, handles, all_recv_counts):
+        hb = b"".join(handles)
+        arc = np.ascontiguousarray(all_recv_counts, dtype=np.int32)
+        check(load().fvg_dist_connect(self._h, C.c_char_p(hb), _ip(arc)))
+
+    def residual(self, u, res, gettimesteps=True, dtm=None, accumulate=False, stream=None):
+        check(load().fvg_dist_residual(self._h, _ptr(u), _ptr(res), int(accumulate), int(gettimesteps), _ptr(dtm),
+                                       C.c_void_p(stream or 0)))
+
+    def euler_step(self, u, unew, cfl, resnorm2=None, stream=None):
+        check(load().fvg_dist_euler_step(self._h, _ptr(u), _ptr(unew), C.c_double(cfl), _ptr(resnorm2),
+                                         C.c_void_p(stream or 0)))
+
+    def invalidate_state(self):
+        check(load().fvg_dist_invalidate_state(self._h))
+
+    def solve_forward_euler(self, u, cfl, tol, maxiter, check_every=1):
+        """Returns (status code, steps, global history); raises on hard errors (FVG_ERR_COMM included)."""
+        steps = C.c_int(0)
+        hist = np.zeros(max(maxiter, 1))
+        code = load().fvg_dist_forward_euler_solve(self._h, _ptr(u), C.c_double(cfl), C.c_double(tol), int(maxiter),
+                                                   int(check_every), C.byref(steps), _dp(hist))
+        if code not in (0, 5, 6):
+            check(code)
+        return code, steps.value, hist[:steps.value].copy()
+
+    def status(self):
+        """Raises FvgError (code 7, COMM) if a wait for a neighbour's rows has timed out."""
+        v = C.c_ulonglong(0)
+        check(load().fvg_dist_status(self._h, C.byref(v)))
+        return int(v.value)
+
+    def counters(self):
+        ev = C.c_longlong(0); gr = C.c_longlong(0); dk = C.c_ulonglong(0)
+        check(load().fvg_dist_counters(self._h, C.byref(ev), C.byref(gr), C.byref(dk)))
+        return ev.value, gr.value, int(dk.value)
+
+    def close(self):
+        if self._h:
+            load().fvg_dist_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def partition_sfc(umesh, nranks):
     """cell -> rank map: the Hilbert order of the cells cut into nranks equal chunks."""
     part = np.zeros(umesh.nelem, dtype=np.int32)

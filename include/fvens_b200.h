@@ -185,6 +185,47 @@ int fvg_halo_post(fvg_halo *h, const double *d_arr, int width, void *stream, uns
 /* 0 if every receive so far saw its neighbours arrive; else the sequence number of a receive that gave up waiting */
 int fvg_halo_status(fvg_halo *h, unsigned long long *h_timed_out_seq);
 void fvg_halo_destroy(fvg_halo *h);
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-GPU evaluation (one process per GPU of one NVLink/NVSwitch box): the product form of the split passes
+ * above. FlowFV::compute_residual on a partitioned mesh (spatial/flow_spatial.cpp:637-816 with its ghost updates and
+ * trace exchanges, :711-788; linalg/tracevector.cpp:214-325) is the SAME two kernels as on one GPU (three with WENO):
+ * the kernel that produces a row a neighbour needs - the gradient pass for gradient rows, the step epilogue (or the
+ * first wave of the evaluation's first kernel) for state rows - stores it straight into the neighbour's peer-mapped
+ * window over NVLink, and the consuming kernel waits for the neighbours' rows only in the CTAs that reach a
+ * partition-boundary tile, after the interior tiles. The evaluation number lives on the device, so an evaluation is
+ * captured once into a CUDA graph and replayed (any stream but the legacy default stream; FVG_GRAPH=0 disables).
+ * Set-up as for fvg_halo: create, all-gather the 64-byte handles and the recv_counts rows, connect.
+ * Arrays are device-ordered: [ncell + nghost][.] for the state (the ghost rows of the ARRAY are never read: they
+ * live in the window), [ncell][.] for residual / time steps. Every rank must issue the same sequence of calls. */
+typedef struct fvg_dist fvg_dist;
+typedef struct fvg_flow fvg_flow;    /* declared below */
+int fvg_dist_create(fvg_flow *flow, fvg_dist **out);
+int fvg_dist_ipc_handle(fvg_dist *d, void *handle64);
+int fvg_dist_connect(fvg_dist *d, const void *handles, const int *all_recv_counts);
+/* FlowFV::compute_residual on this rank's subdomain; accumulate as for fvg_residual */
+int fvg_dist_residual(fvg_dist *d, const double *d_u, double *d_res, int accumulate, int gettimesteps, double *d_dtm,
+                      void *stream);
+/* One forward-Euler pseudo-time step (ode/aodesolver.cpp:189-247): d_unew's own rows from d_u (two distinct arrays);
+ * the step epilogue pushes the new state rows to the neighbours, so the next evaluation of d_unew needs no state
+ * exchange (pass another array, or call fvg_dist_invalidate_state after modifying it, and the rows are pushed again).
+ * d_resnorm2 (device, may be NULL on ALL ranks): the sum over ALL ranks of r_E^2 * area for this step (:218-229), reduced
+ * through the windows in rank order - bitwise the same on every rank. */
+int fvg_dist_euler_step(fvg_dist *d, const double *d_u, double *d_unew, double cfl, double *d_resnorm2, void *stream);
+int fvg_dist_invalidate_state(fvg_dist *d);
+/* SteadyForwardEulerSolver::solve (ode/aodesolver.cpp:136-282) on the partitioned mesh: same contract as
+ * fvg_forward_euler_solve; d_u holds this rank's own rows [ncell][4] (ghost rows, if present, are ignored), h_hist the
+ * GLOBAL residual norms (identical on all ranks). FVG_ERR_COMM if a neighbour stopped delivering rows. */
+int fvg_dist_forward_euler_solve(fvg_dist *d, double *d_u, double cfl, double tol, int maxiter, int check_every,
+                                 int *h_steps, double *h_hist);
+/* FVG_OK, or FVG_ERR_COMM once a wait for a neighbour's rows has timed out (FVG_HALO_TIMEOUT_MS, default 20 s); the
+ * flag value that never arrived is returned. Synchronises the device. */
+int fvg_dist_status(fvg_dist *d, unsigned long long *h_timed_out);
+int fvg_dist_counters(fvg_dist *d, long long *evaluations, long long *graph_replays, unsigned long long *device_evaluation);
+/* test hook: the receive area of (row type 0 state / 1 unlimited gradients / 2 reconstruction gradients, evaluation parity)
+ * as [nghost][4 or 8] doubles, and the 3 x 16 arrival flags */
+int fvg_dist_debug_window(fvg_dist *d, int type, int parity, double *h_rows, unsigned long long *h_flags);
+void fvg_dist_destroy(fvg_dist *d);
+
 /* cell_new2old[ncell + nghost]: device cell i holds reference (global) cell cell_new2old[i]. */
 int fvg_mesh_permutation(const fvg_mesh *m, int *cell_new2old);
 /* tile_cell0[ntile+1]: device cells [tile_cell0[t], tile_cell0[t+1]) are tile t's own cells. */
