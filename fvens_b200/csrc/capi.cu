@@ -394,6 +394,17 @@ int fvg_umesh_view(const fvg_umesh *h, fvg_host_mesh *v)
 	v->coords = m.coordsData(); v->inpoel = m.inpoelData(); v->nnode = m.nnodeData();
 	v->esuel = m.esuelData(); v->elemface = m.elemfaceData(); v->intfac = m.intfacData();
 	v->btags = m.btagsData(); v->facemetric = m.facemetricData(); v->area = m.areaData();
+	v->bpartner = m.periodicmapData();
+	return 0;
+}
+
+int fvg_umesh_compute_periodic_map(fvg_umesh *h, int marker, int axis, int *npairs)
+{
+	if(!h || axis < 0 || axis > 1) { set_error("fvg_umesh_compute_periodic_map: bad argument"); return FVG_ERR_INVALID; }
+	h->m.compute_periodic_map(marker, axis);
+	int np = 0;
+	for(int b = 0; b < h->m.gnbface(); b++) if(h->m.gbtags(b,0) == marker && h->m.gperiodicmap(b) >= 0) np++;
+	if(npairs) *npairs = np/2;
 	return 0;
 }
 
@@ -417,7 +428,7 @@ int fvg_flow_create(fvg_mesh *mesh, const fvg_physics *phys, const fvg_numerics 
 	f->phys = *phys;
 	f->gas = make_gas(*phys, num->limiter_param);
 	for(int i = 0; i < nbc; i++)
-		if(bcs[i].type < 0 || bcs[i].type > 7 || bcs[i].type == PERIODIC_BC) {
+		if(bcs[i].type < 0 || bcs[i].type > 7) {
 			// reference: create_const_flowBCs throws for types without a FlowBC class (abc.cpp:493-494)
 			set_error("fvg_flow_create: boundary condition type " + std::to_string(bcs[i].type) + " is not available");
 			return FVG_ERR_UNSUPPORTED;
@@ -429,6 +440,14 @@ int fvg_flow_create(fvg_mesh *mesh, const fvg_physics *phys, const fvg_numerics 
 		int k = -1;
 		for(int i = 0; i < nbc; i++) if(bcs[i].tag == mesh->h_markers[sl]) k = i;
 		if(k < 0) { set_error("fvg_flow_create: no boundary condition for marker " + std::to_string(mesh->h_markers[sl])); return FVG_ERR_INVALID; }
+		// a periodic marker is one whose faces the mesh has paired (fvg_host_mesh::bpartner): no ghost state exists for it.
+		// The reference has no periodic FlowBC (abc.cpp:493-494 throws); here the pairing IS the boundary condition.
+		const bool paired = sl < mesh->h_marker_periodic.size() && mesh->h_marker_periodic[sl] != 0;
+		if((bcs[k].type == PERIODIC_BC) != paired) {
+			set_error("fvg_flow_create: marker " + std::to_string(mesh->h_markers[sl]) + (paired ? " is paired as periodic in the mesh but its boundary condition is not 'periodic'"
+			          : " has the periodic boundary condition but the mesh holds no pairing for it (UMesh::compute_periodic_map)"));
+			return FVG_ERR_UNSUPPORTED;
+		}
 		f->gas.bc[sl].tag = bcs[k].tag; f->gas.bc[sl].type = bcs[k].type;
 		f->gas.bc[sl].v0 = bcs[k].vals[0]; f->gas.bc[sl].v1 = bcs[k].vals[1];
 	}
@@ -460,9 +479,37 @@ int fvg_flow_create(fvg_mesh *mesh, const fvg_physics *phys, const fvg_numerics 
 	return 0;
 }
 
+/// Single-rank mesh with periodic ghost cells: the exchange engine (dist.cu) with this rank as its own peer, created
+/// on first use. The periodic rows travel exactly like the rows of a partition - pushed by the producing kernels into
+/// the (own) window, waited for in the tiles that see a ghost cell.
+static int self_exchange(fvg_flow *f, fvg_dist **out)
+{
+	if(!f->self_dist) {
+		fvg_dist *d = nullptr;
+		int rc = fvg_dist_create(f, &d);
+		if(rc != 0) return rc;
+		const int rcv = f->mesh->recv_counts.empty() ? 0 : f->mesh->recv_counts[0];
+		unsigned char handle[64] = {0};
+		if((rc = fvg_dist_connect(d, handle, &rcv)) != 0) { fvg_dist_destroy(d); return rc; }
+		f->self_dist = d;
+	}
+	*out = f->self_dist;
+	return 0;
+}
+static bool has_periodic_ghosts(const fvg_flow *f) { return f->mesh->nranks == 1 && f->mesh->d.nghost > 0; }
+static int reject_periodic(const fvg_flow *f, const char *who)
+{
+	if(f->mesh->d.nghost > 0 && f->mesh->nranks == 1) {
+		set_error(std::string(who) + ": not available on a mesh with periodic boundaries (use fvg_residual and the drivers built on it)");
+		return FVG_ERR_UNSUPPORTED;
+	}
+	return 0;
+}
+
 void fvg_flow_destroy(fvg_flow *f)
 {
 	if(!f) return;
+	if(f->self_dist) fvg_dist_destroy(f->self_dist);
 	for(void *p : f->allocs) cudaFree(p);
 	if(f->h_norm) cudaFreeHost(f->h_norm);
 	for(cudaEvent_t e : f->pipe.ev_up) cudaEventDestroy(e);
@@ -521,7 +568,12 @@ int fvg_residual(fvg_flow *f, const double *d_u, double *d_res, int accumulate, 
                  double *d_dtm, void *stream)
 {
 	if(!f || !d_u || !d_res || (gettimesteps && !d_dtm)) { set_error("fvg_residual: null argument"); return FVG_ERR_INVALID; }
-	if(f->mesh->nranks > 1) { set_error("fvg_residual: a subdomain mesh needs the ghost gradients exchanged between the passes; use fvg_gradient_pass / fvg_face_pass"); return FVG_ERR_UNSUPPORTED; }
+	if(f->mesh->nranks > 1) { set_error("fvg_residual: a subdomain mesh needs its neighbours' rows; use fvg_dist_residual"); return FVG_ERR_UNSUPPORTED; }
+	if(has_periodic_ghosts(f)) {
+		fvg_dist *sd = nullptr;
+		const int rcd = self_exchange(f, &sd);
+		return rcd != 0 ? rcd : fvg_dist_residual(sd, d_u, d_res, accumulate, gettimesteps, d_dtm, stream);
+	}
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	const DMesh &D = f->mesh->d;
 	const int n = D.ncell;
@@ -562,7 +614,7 @@ static void plan_host_pipe(fvg_flow *f)
 	int K = 48;
 	if(const char *ev = getenv("FVG_HOST_CHUNKS")) K = atoi(ev);
 	K = std::min(std::min(K, 64), ntile/8);
-	if(K < 2 || !m->identity_perm || m->nranks > 1 || m->h_thoff.empty()) return;
+	if(K < 2 || !m->identity_perm || m->nranks > 1 || m->d.nghost > 0 || m->h_thoff.empty()) return;
 	P.tile0.resize(K+1);
 	for(int c = 0; c <= K; c++) P.tile0[c] = (int)((long long)ntile*c/K);
 	std::vector<int> chunk_of_tile(ntile);
@@ -684,6 +736,7 @@ static int to_device_order(fvg_flow *f, const double *src, int width, double **s
 int fvg_gradients(fvg_flow *f, const double *d_uprim, const double *d_ug, double *d_grad, void *stream)
 {
 	if(!f || !d_uprim || !d_grad || (f->mesh->d.nbface > 0 && !d_ug)) { set_error("fvg_gradients: null argument"); return FVG_ERR_INVALID; }
+	{ const int rp = reject_periodic(f, "fvg_gradients"); if(rp != 0) return rp; }
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	const DMesh &D = f->mesh->d;
 	double *su = nullptr, *sg = nullptr;
@@ -708,6 +761,7 @@ int fvg_face_values(fvg_flow *f, const double *d_uprim, const double *d_ug, cons
                     double *d_ufl, double *d_ufr, void *stream)
 {
 	if(!f || !d_uprim || !d_grad || !d_ufl || !d_ufr || (f->mesh->d.nbface > 0 && !d_ug)) { set_error("fvg_face_values: null argument"); return FVG_ERR_INVALID; }
+	{ const int rp = reject_periodic(f, "fvg_face_values"); if(rp != 0) return rp; }
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	const DMesh &D = f->mesh->d;
 	const FlowPlan &P = f->plan;
@@ -774,6 +828,7 @@ int fvg_jacobian_vector_product(fvg_flow *f, const double *d_u, const double *d_
 int fvg_get_gradients(fvg_flow *f, const double *d_u, double *d_grads, void *stream)
 {
 	if(!f || !d_u || !d_grads) { set_error("fvg_get_gradients: null argument"); return FVG_ERR_INVALID; }
+	{ const int rp = reject_periodic(f, "fvg_get_gradients"); if(rp != 0) return rp; }
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	const DMesh &D = f->mesh->d;
 	double *su = nullptr, *sug = nullptr, *sg = nullptr;
@@ -993,11 +1048,26 @@ static int step_device_order(fvg_flow *f, const double *uin, double *uout, doubl
 int fvg_euler_step(fvg_flow *f, double *d_u, double cfl, double *d_resnorm2, void *stream)
 {
 	if(!f || !d_u) { set_error("fvg_euler_step: null argument"); return FVG_ERR_INVALID; }
-	if(f->mesh->nranks > 1) { set_error("fvg_euler_step: use the split passes on a subdomain mesh"); return FVG_ERR_UNSUPPORTED; }
+	if(f->mesh->nranks > 1) { set_error("fvg_euler_step: use fvg_dist_euler_step on a subdomain mesh"); return FVG_ERR_UNSUPPORTED; }
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	const DMesh &D = f->mesh->d;
 	const size_t n = D.ncell;
 	int rc;
+	if(has_periodic_ghosts(f)) {
+		// periodic mesh: the exchange engine steps device-ordered ping-pong buffers
+		fvg_dist *sd = nullptr;
+		if((rc = self_exchange(f, &sd)) != 0) return rc;
+		if((rc = ensure(f, &f->d_u2, 4*n)) != 0) return rc;
+		if((rc = ensure(f, &f->d_uperm, 4*n)) != 0) return rc;
+		if(f->mesh->identity_perm) FVG_CUDA(cudaMemcpyAsync(f->d_uperm, d_u, 4*n*sizeof(double), cudaMemcpyDeviceToDevice, s));
+		else { if((rc = launch_permute_rows(d_u, f->d_uperm, D.new2old, (int)n, 4, true, false, s)) != 0) return rc; f->launches++; }
+		if((rc = fvg_dist_invalidate_state(sd)) != 0) return rc;
+		if((rc = fvg_dist_euler_step(sd, f->d_uperm, f->d_u2, cfl, f->d_norm, stream)) != 0) return rc;
+		if(f->mesh->identity_perm) FVG_CUDA(cudaMemcpyAsync(d_u, f->d_u2, 4*n*sizeof(double), cudaMemcpyDeviceToDevice, s));
+		else { if((rc = launch_permute_rows(f->d_u2, d_u, D.new2old, (int)n, 4, false, false, s)) != 0) return rc; f->launches++; }
+		if(d_resnorm2) FVG_CUDA(cudaMemcpyAsync(d_resnorm2, f->d_norm, sizeof(double), cudaMemcpyDeviceToDevice, s));
+		return 0;
+	}
 	if((rc = ensure(f, &f->d_u2, 4*n)) != 0) return rc;
 	if(f->plan.order2) {
 		// the gradient pass leaves a device-ordered copy of the state (gathered through the permutation when the mesh is
@@ -1028,7 +1098,12 @@ int fvg_forward_euler_solve(fvg_flow *f, double *d_u, double cfl, double tol, in
                             int check_every, int *h_steps, double *h_hist)
 {
 	if(!f || !d_u || !h_steps) { set_error("fvg_forward_euler_solve: null argument"); return FVG_ERR_INVALID; }
-	if(f->mesh->nranks > 1) { set_error("fvg_forward_euler_solve: single-process driver; use the split passes on a subdomain mesh"); return FVG_ERR_UNSUPPORTED; }
+	if(f->mesh->nranks > 1) { set_error("fvg_forward_euler_solve: use fvg_dist_forward_euler_solve on a subdomain mesh"); return FVG_ERR_UNSUPPORTED; }
+	if(has_periodic_ghosts(f)) {
+		fvg_dist *sd = nullptr;
+		const int rcd = self_exchange(f, &sd);
+		return rcd != 0 ? rcd : fvg_dist_forward_euler_solve(sd, d_u, cfl, tol, maxiter, check_every, h_steps, h_hist);
+	}
 	if(check_every < 1) check_every = 1;
 	*h_steps = 0;
 	if(maxiter <= 0) return 0;

@@ -161,6 +161,19 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	std::vector<int> bslot(nb);
 	for(int b = 0; b < nb; b++)
 		bslot[b] = (int)(std::lower_bound(m->h_markers.begin(), m->h_markers.end(), m->h_btag[b]) - m->h_markers.begin());
+	// a marker is periodic when every one of its faces has a partner (then no boundary condition is ever evaluated for it)
+	m->h_marker_periodic.assign(m->h_markers.size(), hm->bpartner ? 1 : 0);
+	{
+		std::vector<int> any(m->h_markers.size(), 0);
+		for(int b = 0; b < nb; b++) {
+			const bool paired = hm->bpartner && hm->bpartner[b] >= 0;
+			if(!paired) m->h_marker_periodic[bslot[b]] = 0; else any[bslot[b]] = 1;
+		}
+		for(size_t k = 0; k < any.size(); k++) {
+			if(any[k] && !m->h_marker_periodic[k]) { set_error("fvg_mesh_create: marker " + std::to_string(m->h_markers[k]) + " has periodic and non-periodic faces"); return FVG_ERR_INVALID; }
+			if(!any[k]) m->h_marker_periodic[k] = 0;
+		}
+	}
 
 	// ---- global locality order, then the rank's own cells and ghosts
 	std::vector<int> gorder;
@@ -181,25 +194,65 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	const int nown = (int)d2g.size();
 	if(nown == 0) { set_error("fvg_mesh_create: this rank owns no cells"); return FVG_ERR_INVALID; }
 	m->send_counts.assign(nranks, 0); m->recv_counts.assign(nranks, 0);
+	// Periodic boundaries (hm->bpartner, UMesh::compute_periodic_map): a boundary face f with partner fp becomes an
+	// interior face whose right cell is a GHOST copy of the partner's cell b, displaced by the period (centre rc_b +
+	// mid_f - mid_fp). Such ghosts are rows like the ghosts of a partition - filled by the same exchange, possibly from
+	// this very rank - so everything downstream (tiles, halos, streams, kernels) sees an ordinary interior face.
+	// Each of the two partner faces is evaluated once, by the tile of its own left cell.
+	const int *const bpart = hm->bpartner;
+	auto face_mid = [&](int f, int d) { return 0.5*(hm->coords[2*(size_t)hm->intfac[4*(size_t)f+2]+d] + hm->coords[2*(size_t)hm->intfac[4*(size_t)f+3]+d]); };
+	if(bpart)
+		for(int b = 0; b < nb; b++) {
+			const int q = bpart[b];
+			if(q < 0) continue;
+			if(q >= nb || q == b || bpart[q] != b || m->h_btag[q] != m->h_btag[b]) { set_error("fvg_mesh_create: inconsistent periodic pairing of the boundary faces"); return FVG_ERR_INVALID; }
+		}
+	auto partner_of = [&](int f) { return (bpart && f >= 0 && f < nb) ? bpart[f] : -1; };
+	std::vector<int> pg_dev((size_t)std::max(nb, 1), -1);      // boundary face -> device index of its periodic ghost cell
+	std::vector<double2> gshift;                                // displacement of every ghost cell's centre (zero for partition ghosts)
+	m->h_periodic_faces = 0;
 	{
-		std::vector<std::pair<long long,int>> ghosts;      // (owner*2^32 + owner's index, old id)
-		std::vector<std::pair<int,int>> sends;             // (peer, my device index)
+		struct GhostRec { long long key; int pface; int cell; };      // pface: the partner's boundary face (owned by `cell`), -1 for a partition ghost
+		struct SendRec { int peer, idx, pface; };
+		std::vector<GhostRec> ghosts;
+		std::vector<SendRec> sends;
 		for(int i = 0; i < nown; i++) {
 			const int o = d2g[i];
 			for(int j = 0; j < hm->nnode[o]; j++) {
 				const int e = hm->esuel[(size_t)o*mw+j];
-				if(e < 0 || e >= n || rank_of(e) == rank) continue;
-				ghosts.push_back(std::make_pair(((long long)rank_of(e) << 32) + rankidx[e], e));
-				sends.push_back(std::make_pair(rank_of(e), i));
+				if(e >= n) {
+					const int f = e - n, fp = partner_of(f);
+					if(fp < 0) continue;
+					const int b = hm->intfac[4*(size_t)fp];
+					ghosts.push_back({((long long)rank_of(b) << 32) + rankidx[b], fp, b});
+					sends.push_back({rank_of(b), i, f});      // the cell behind fp sees this cell through its face fp, whose partner is f
+					m->h_periodic_faces++;
+					continue;
+				}
+				if(e < 0 || rank_of(e) == rank) continue;
+				ghosts.push_back({((long long)rank_of(e) << 32) + rankidx[e], -1, e});
+				sends.push_back({rank_of(e), i, -1});
 			}
 		}
-		std::sort(ghosts.begin(), ghosts.end());
-		ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
-		for(const auto &gst : ghosts) { g2d[gst.second] = (int)d2g.size(); d2g.push_back(gst.second); m->recv_counts[rank_of(gst.second)]++; }
-		std::sort(sends.begin(), sends.end());
-		sends.erase(std::unique(sends.begin(), sends.end()), sends.end());
+		auto gless = [](const GhostRec &a, const GhostRec &b) { return a.key < b.key || (a.key == b.key && a.pface < b.pface); };
+		std::sort(ghosts.begin(), ghosts.end(), gless);
+		ghosts.erase(std::unique(ghosts.begin(), ghosts.end(), [](const GhostRec &a, const GhostRec &b) { return a.key == b.key && a.pface == b.pface; }), ghosts.end());
+		for(const GhostRec &gst : ghosts) {
+			const int dev = (int)d2g.size();
+			d2g.push_back(gst.cell);
+			m->recv_counts[rank_of(gst.cell)]++;
+			if(gst.pface < 0) { g2d[gst.cell] = dev; gshift.push_back(make_double2(0.0, 0.0)); }
+			else {
+				const int f = bpart[gst.pface];      // this rank's face
+				pg_dev[f] = dev;
+				gshift.push_back(make_double2(face_mid(f, 0) - face_mid(gst.pface, 0), face_mid(f, 1) - face_mid(gst.pface, 1)));
+			}
+		}
+		auto sless = [](const SendRec &a, const SendRec &b) { return a.peer != b.peer ? a.peer < b.peer : (a.idx != b.idx ? a.idx < b.idx : a.pface < b.pface); };
+		std::sort(sends.begin(), sends.end(), sless);
+		sends.erase(std::unique(sends.begin(), sends.end(), [](const SendRec &a, const SendRec &b) { return a.peer == b.peer && a.idx == b.idx && a.pface == b.pface; }), sends.end());
 		m->h_send_idx.clear();
-		for(const auto &sd : sends) { m->h_send_idx.push_back(sd.second); m->send_counts[sd.first]++; }
+		for(const SendRec &sd : sends) { m->h_send_idx.push_back(sd.idx); m->send_counts[sd.peer]++; }
 	}
 	const int ntot = (int)d2g.size();
 	m->nghost = ntot - nown;
@@ -211,7 +264,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	// faces that touch an own cell, ascending global id
 	auto is_own = [&](int dev) { return dev >= 0 && dev < nown; };
 	auto faceL = [&](int f) { return g2d[hm->intfac[4*(size_t)f]]; };
-	auto faceR = [&](int f) { return f < nb ? -1 : g2d[hm->intfac[4*(size_t)f+1]]; };
+	auto faceR = [&](int f) { return f < nb ? pg_dev[f] : g2d[hm->intfac[4*(size_t)f+1]]; };
 	std::vector<int> rfaces;
 	for(int f = 0; f < nf; f++) {
 		const int L = faceL(f), R = faceR(f);
@@ -221,7 +274,14 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	// neighbour (device numbering) of own device cell i across local face j: >= 0 cell (own or ghost), -1 boundary
 	auto nbr_of = [&](int i, int j) {
 		const int e = hm->esuel[(size_t)d2g[i]*mw+j];
-		return e < n ? g2d[e] : -1;
+		return e < n ? g2d[e] : pg_dev[e - n];
+	};
+	// centre of a device cell (periodic ghosts: the partner's centre displaced by the period)
+	auto centre = [&](int dev, int d) {
+		const double c = rc[2*(size_t)d2g[dev]+d];
+		if(dev < nown) return c;
+		const double2 sh = gshift[(size_t)(dev - nown)];
+		return c + (d == 0 ? sh.x : sh.y);
 	};
 
 	// ---- tiles: greedy ranges of consecutive own cells within the capacities
@@ -263,7 +323,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	const int ntile = (int)tcell0.size() - 1;
 	std::vector<int> tile_order;
 	int ntile_interior = ntile;
-	if(nranks > 1) {
+	if(ntot > nown) {
 		std::vector<int> bnd;
 		for(int t = 0; t < ntile; t++) {
 			bool ghost = false;
@@ -538,8 +598,8 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 			{
 				// Green-Gauss: u_face = (u_L/d_L + u_R/d_R)/(1/d_L + 1/d_R), d = distance of the midpoint to the cell centre
 				// (boundary: to the mirrored ghost centre, aspatial.cpp:98-119)
-				const double lx = rc[2*(size_t)d2g[L]], ly = rc[2*(size_t)d2g[L]+1];
-				const double rx = R >= 0 ? rc[2*(size_t)d2g[R]] : 2.0*g[0] - lx, ry = R >= 0 ? rc[2*(size_t)d2g[R]+1] : 2.0*g[1] - ly;
+				const double lx = centre(L, 0), ly = centre(L, 1);
+				const double rx = R >= 0 ? centre(R, 0) : 2.0*g[0] - lx, ry = R >= 0 ? centre(R, 1) : 2.0*g[1] - ly;
 				const double di = 1.0/std::sqrt((g[0]-lx)*(g[0]-lx) + (g[1]-ly)*(g[1]-ly));
 				const double dj = 1.0/std::sqrt((g[0]-rx)*(g[0]-rx) + (g[1]-ry)*(g[1]-ry));
 				fgw[e] = make_double2(di/(di + dj), dj/(di + dj));
@@ -552,8 +612,9 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	// ---- per-cell arrays in device order (centres also for the ghosts)
 	std::vector<uint4> cloc((size_t)nown);
 	std::vector<double2> drc((size_t)ntot);
-	std::vector<double> area((size_t)nown + 1, 1.0), clength((size_t)nown + 1, 1.0);     // one pad entry: tiles copy 16-byte granules
-	for(int i = 0; i < ntot; i++) drc[i] = make_double2(rc[2*(size_t)d2g[i]], rc[2*(size_t)d2g[i]+1]);
+	std::vector<double> area((size_t)ntot + 1, 1.0), clength((size_t)nown + 1, 1.0);     // one pad entry: tiles copy 16-byte granules
+	for(int i = nown; i < ntot; i++) area[i] = hm->area[d2g[i]];                          // (ghost areas: the viscous spectral radius of a cut face's far side)
+	for(int i = 0; i < ntot; i++) drc[i] = make_double2(centre(i, 0), centre(i, 1));
 	for(int i = 0; i < nown; i++) {
 		const int o = d2g[i], t = tile_of[i];
 		unsigned a[4] = {NB_NONE, NB_NONE, NB_NONE, NB_NONE}, c[4] = {0,0,0,0};
@@ -562,7 +623,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 			const int f = hm->elemface[(size_t)o*mw+j];
 			if(e < 0 || f < 0 || f >= nf) { set_error("fvg_mesh_create: inconsistent esuel/elemface"); return FVG_ERR_INVALID; }
 			if(e >= n && (e-n != f || f >= nb)) { set_error("fvg_mesh_create: boundary ghost index does not match its face"); return FVG_ERR_INVALID; }
-			a[j] = e < n ? local_of(t, g2d[e]) : NB_BND;
+			a[j] = e < n ? local_of(t, g2d[e]) : (pg_dev[e - n] >= 0 ? local_of(t, pg_dev[e - n]) : NB_BND);
 			const bool isL = hm->intfac[4*(size_t)f] == o;
 			if(!isL && (f < nb || hm->intfac[4*(size_t)f+1] != o)) { set_error("fvg_mesh_create: elemface/intfac mismatch"); return FVG_ERR_INVALID; }
 			// the copy of the face that lives in this cell's tile
@@ -609,7 +670,12 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 		for(int f = 0; f < nf; f++) {
 			const int ie = hm->intfac[4*(size_t)f];
 			double dr[2];
-			if(f < nb) { dr[0] = rc[2*(size_t)ie] - rcbp[f].x; dr[1] = rc[2*(size_t)ie+1] - rcbp[f].y; }
+			if(f < nb && partner_of(f) >= 0) {
+				// periodic face: the neighbour is the partner's cell displaced by the period
+				const int fp = partner_of(f), je = hm->intfac[4*(size_t)fp];
+				for(int d = 0; d < 2; d++) dr[d] = rc[2*(size_t)ie+d] - (rc[2*(size_t)je+d] + face_mid(f, d) - face_mid(fp, d));
+			}
+			else if(f < nb) { dr[0] = rc[2*(size_t)ie] - rcbp[f].x; dr[1] = rc[2*(size_t)ie+1] - rcbp[f].y; }
 			else { const int je = hm->intfac[4*(size_t)f+1]; dr[0] = rc[2*(size_t)ie] - rc[2*(size_t)je]; dr[1] = rc[2*(size_t)ie+1] - rc[2*(size_t)je+1]; }
 			double w2 = 0;
 			for(int d = 0; d < 2; d++) w2 += dr[d]*dr[d];
@@ -672,7 +738,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	// peers as soon as the tile is done (the per-rank list send_idx is the same set, grouped by peer).
 	m->h_tsoff.assign((size_t)ntile + 1, 0);
 	m->h_tsend.clear();
-	if(nranks > 1) {
+	if(!m->h_send_idx.empty()) {
 		std::vector<std::array<int,4>> items;     // tile, local cell, peer, row
 		int k = 0;
 		for(int r = 0; r < nranks; r++)

@@ -148,10 +148,21 @@ static int enqueue_evaluation(fvg_dist *D, const double *u, double *res, int acc
                               double cfl, double *unew, bool force_push, cudaStream_t s)
 {
 	fvg_flow *f = D->flow;
+	// single-rank periodic mesh renumbered by the engine: caller-ordered arrays, permutation fused into the passes
+	// (the fused step always runs on device-ordered ping-pong buffers)
+	const int *perm = (D->mesh->identity_perm || unew) ? nullptr : D->mesh->d.new2old;
+	if(perm && !f->d_uperm) { const int ra = flow_dev_alloc(f, &f->d_uperm, 4*(size_t)D->mesh->d.ncell); if(ra != 0) return ra; }
 	set_roles(D, unew != nullptr, force_push);
-	int rc = run_gradient_pass(f, u, s);
-	if(rc == 0) rc = unew ? run_face_pass(f, u, EP_STEP, 0, 1, nullptr, nullptr, cfl, unew, s)
-	                      : run_face_pass(f, u, EP_RESIDUAL, accumulate, gettimesteps, res, dtm, 0.0, nullptr, s);
+	int rc = 0;
+	const double *uface = u;
+	if(perm) {
+		if(f->plan.order2) rc = run_gradient_pass(f, u, s, 0, -1, perm, f->d_uperm);
+		else { rc = launch_permute_rows(u, f->d_uperm, perm, D->mesh->d.ncell, 4, true, false, s); f->launches++; }
+		uface = f->d_uperm;
+	}
+	else rc = run_gradient_pass(f, u, s);
+	if(rc == 0) rc = unew ? run_face_pass(f, uface, EP_STEP, 0, 1, nullptr, nullptr, cfl, unew, s)
+	                      : run_face_pass(f, uface, EP_RESIDUAL, accumulate, gettimesteps, res, dtm, 0.0, nullptr, s, 0, -1, perm);
 	f->roles = fvg_flow::DistRoles();
 	return rc;
 }
@@ -207,7 +218,7 @@ int fvg_dist_create(fvg_flow *flow, fvg_dist **out)
 	fvg_mesh *m = flow->mesh;
 	if(m->device < 0) return dist_fail("fvg_dist_create: host-only mesh", FVG_ERR_INVALID);
 	if(m->nranks > MAXRANKS) return dist_fail("fvg_dist_create: at most 16 ranks per box", FVG_ERR_UNSUPPORTED);
-	if(!m->identity_perm) return dist_fail("fvg_dist_create: subdomain meshes are device-ordered", FVG_ERR_INVALID);
+	if(!m->identity_perm && m->nranks > 1) return dist_fail("fvg_dist_create: subdomain meshes are device-ordered", FVG_ERR_INVALID);
 	FVG_CUDA(cudaSetDevice(m->device));
 	std::unique_ptr<fvg_dist> D(new fvg_dist);
 	D->flow = flow; D->mesh = m; D->nranks = m->nranks; D->rank = m->rank;
@@ -254,7 +265,7 @@ int fvg_dist_connect(fvg_dist *D, const void *handles, const int *all_recv_count
 		H.peer_row0[r] = off;
 		H.send_off[r+1] = H.send_off[r] + m->send_counts[r];
 		H.recv_off[r+1] = H.recv_off[r] + m->recv_counts[r];
-		if(r == D->rank) continue;
+		if(r == D->rank) { H.peer[r] = D->window; continue; }       // (periodic rows of this rank's own cells)
 		if(all_recv_counts[(size_t)r*n + D->rank] != m->send_counts[r])
 			return dist_fail("fvg_dist_connect: send/receive counts of two ranks disagree", FVG_ERR_COMM);
 		// every rank is mapped (not only the halo neighbours): the norm reduction stores into all windows
@@ -389,8 +400,13 @@ int fvg_dist_forward_euler_solve(fvg_dist *D, double *d_u, double cfl, double to
 		FVG_CUDA(cudaDeviceSynchronize());       // earlier work of the caller on other streams
 	}
 	double *cur = D->d_u1, *nxt = D->d_u2;
-	cudaError_t e = cudaMemcpyAsync(cur, d_u, 4*nown*sizeof(double), cudaMemcpyDeviceToDevice, s);
-	if(e != cudaSuccess) rc = cuda_fail(e, "state copy", __FILE__, __LINE__);
+	const int *perm = D->mesh->identity_perm ? nullptr : D->mesh->d.new2old;
+	cudaError_t e = cudaSuccess;
+	if(perm) { rc = launch_permute_rows(d_u, cur, perm, (int)nown, 4, true, false, s); f->launches++; }
+	else {
+		e = cudaMemcpyAsync(cur, d_u, 4*nown*sizeof(double), cudaMemcpyDeviceToDevice, s);
+		if(e != cudaSuccess) rc = cuda_fail(e, "state copy", __FILE__, __LINE__);
+	}
 	D->pushed_ptr = nullptr;
 	std::vector<double> hist((size_t)maxiter);
 	int step = 0, status = FVG_OK;
@@ -443,9 +459,10 @@ int fvg_dist_forward_euler_solve(fvg_dist *D, double *d_u, double cfl, double to
 	if(rc == 0) {
 		*h_steps = step;
 		if(h_hist) std::memcpy(h_hist, hist.data(), sizeof(double)*step);
-		e = cudaMemcpyAsync(d_u, cur, 4*nown*sizeof(double), cudaMemcpyDeviceToDevice, s);
+		if(perm) { rc = launch_permute_rows(cur, d_u, perm, (int)nown, 4, false, false, s); f->launches++; }
+		else e = cudaMemcpyAsync(d_u, cur, 4*nown*sizeof(double), cudaMemcpyDeviceToDevice, s);
 		if(e == cudaSuccess) e = cudaStreamSynchronize(s);
-		if(e != cudaSuccess) rc = cuda_fail(e, "state copy", __FILE__, __LINE__);
+		if(rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "state copy", __FILE__, __LINE__);
 	}
 	D->pushed_ptr = nullptr;     // the caller's array is not the one whose rows the neighbours hold
 	if(rc != 0) return rc;

@@ -156,8 +156,10 @@ __device__ __forceinline__ void dist_push_tile(const DistDev *d, int type, unsig
 }
 
 /// Prologue push of the state rows of evaluation k (first DIST_PROLOGUE_CTAS CTAs of the evaluation's first kernel; the
-/// others return at once). Skipped when a step epilogue has already pushed them. `u` is [ncell+.][4], device order.
-__device__ __forceinline__ void dist_push_state_prologue(const DistDev *d, unsigned long long k, const double *u, int force)
+/// others return at once). Skipped when a step epilogue has already pushed them. `u` is [ncell+.][4], device order (or
+/// caller order with the row map src_idx: single-rank periodic meshes renumbered by the engine).
+__device__ __forceinline__ void dist_push_state_prologue(const DistDev *d, unsigned long long k, const double *u, int force,
+                                                         const int *src_idx = nullptr)
 {
 	const int np = (int)gridDim.x < DIST_PROLOGUE_CTAS ? (int)gridDim.x : DIST_PROLOGUE_CTAS;
 	if((int)blockIdx.x >= np) return;
@@ -167,7 +169,8 @@ __device__ __forceinline__ void dist_push_state_prologue(const DistDev *d, unsig
 		const int i = (int)(q >> 1), c = (int)(q & 1);
 		int r = 0;
 		while(i >= d->send_off[r+1]) r++;
-		const double2 v = *reinterpret_cast<const double2*>(u + 4*(size_t)d->send_idx[i] + 2*c);
+		const int cell = d->send_idx[i];
+		const double2 v = *reinterpret_cast<const double2*>(u + 4*(size_t)(src_idx ? src_idx[cell] : cell) + 2*c);
 		*reinterpret_cast<double2*>(dist_peer_row(d, r, X_U, k, i - d->send_off[r]) + 2*c) = v;
 	}
 	__threadfence_system();

@@ -137,10 +137,12 @@ struct fvg_mesh {
 	std::vector<unsigned> h_fLR;               ///< kept so that flow creation can patch in the BC indices
 	std::vector<int> h_bentry;
 	std::vector<int> h_markers;                ///< sorted distinct boundary markers = slots of the BC table
+	std::vector<int> h_marker_periodic;        ///< per slot: 1 if the marker's faces are periodic pairs (interior faces on the device)
 	std::vector<int> h_tcell0, h_thoff, h_thalo;
 	std::vector<int> h_tsoff, h_tsend;         ///< per-tile send lists: offsets [ntile+1]; triples (tile-local cell, peer, row in my block)
 	std::vector<double> h_rc;                  ///< cell centres, device order (own cells)
 	int nghost = 0, rank = 0, nranks = 1;
+	int h_periodic_faces = 0;                  ///< own boundary faces that a periodic pairing turned into interior faces
 	std::vector<int> send_counts, recv_counts, h_send_idx;
 };
 
@@ -189,6 +191,7 @@ struct fvg_flow {
 	fvg::GhostSrc gs_u, gs_g;      ///< set by fvg_flow_ghost_source
 	/// fused multi-GPU evaluation (dist.cu): while `active`, the passes run over all tiles, interior tiles first, with these roles
 	struct DistRoles { bool active = false; fvg::DistRole cell, weno, face; } roles;
+	struct fvg_dist *self_dist = nullptr;      ///< single-rank mesh with periodic ghost cells: the exchange engine with this rank as its own peer
 	// optional per-pass timing (CUDA events on the launching stream)
 	bool timing = false;
 	std::vector<cudaEvent_t> ev;   ///< triples: before pass A, between A and B, after B

@@ -53,12 +53,18 @@ struct CellSmem {
  * rows on its send list as soon as it has stored them (dist_dev.cuh).
  * Caller-ordered state (A.src_idx): own and halo rows are gathered through the permutation and the own rows are also
  * written in device order to A.ucopy, which is what the face pass reads - no separate permutation kernel.
- * LOOP = false is the one-tile-per-CTA form (grid = number of tiles): nothing is carried from tile to tile, which keeps
- * the stencil loop within 80 registers. */
-template <int GRAD, int LIM, bool PRIM_IN, bool LOOP>
+ * MODE: CM_PLAIN one tile per CTA (grid = number of tiles), no multi-GPU code; CM_DIST the same with it; CM_LOOP a
+ * resident-size grid walking the tiles. In the first two nothing is carried from tile to tile, which keeps the stencil
+ * loop within the 80 registers of three CTAs per SM. */
+enum { CM_PLAIN = 0, CM_DIST = 1, CM_LOOP = 2 };
+template <int GRAD, int LIM, bool PRIM_IN, int MODE>
 __global__ void __launch_bounds__(CELL_BLOCK, FVG_CELL_MINB)
 cell_kernel(const __grid_constant__ CellArgs A)
 {
+	constexpr bool LOOP = MODE == CM_LOOP;
+	// the plain form is compiled without the multi-GPU code: measured faster on one GPU than the same kernel with the
+	// (never taken) push / wait branches in it
+	const DistDev *const distd = MODE != CM_PLAIN ? A.dist.d : nullptr;
 	extern __shared__ __align__(1024) unsigned char smraw[];
 	const DMesh &M = A.m;
 	constexpr bool MIDS = LIM != LM_NONE || GRAD == GM_GG;
@@ -92,10 +98,10 @@ cell_kernel(const __grid_constant__ CellArgs A)
 	// (both kept in shared memory: they are needed once per partition-boundary tile only)
 	unsigned long long *const sdk = reinterpret_cast<unsigned long long*>(smraw + S.ring + 96);
 	const double **const sghost = reinterpret_cast<const double**>(smraw + S.ring + 104);
-	if(A.dist.d) {
-		const unsigned long long dk = A.dist.d->ctl->k;
-		if(tid == 0) { *sdk = dk; *sghost = (A.dist.wait & (1u << X_U)) ? dist_ghost_rows(A.dist.d, X_U, dk) : nullptr; }
-		if(A.dist.first) dist_push_state_prologue(A.dist.d, dk, A.u, A.dist.force_push);
+	if(distd) {
+		const unsigned long long dk = distd->ctl->k;
+		if(tid == 0) { *sdk = dk; *sghost = (A.dist.wait & (1u << X_U)) ? dist_ghost_rows(distd, X_U, dk) : nullptr; }
+		if(A.dist.first) dist_push_state_prologue(distd, dk, A.u, A.dist.force_push, A.src_idx);
 	}
 	else if(tid == 0) { *sdk = 0; *sghost = A.gs_u.rows; }
 	__syncthreads();
@@ -157,7 +163,7 @@ cell_kernel(const __grid_constant__ CellArgs A)
 				}
 			}
 			if(ghost_win) {
-				if(A.dist.d) dist_wait(A.dist.d, 1u << X_U, *sdk);
+				if(distd) dist_wait(distd, 1u << X_U, *sdk);
 				else ghost_wait(A.gs_u, A.gs_u.seq);
 				const double *const ghost_rows_u = *sghost;
 				for(int k = tid; k < nh*2; k += CELL_BLOCK) {
@@ -348,17 +354,17 @@ cell_kernel(const __grid_constant__ CellArgs A)
 		}
 		// the staging buffers are free for the next tile once every thread is past the stencil loop; the same barrier
 		// orders this tile's gradient stores before the push below reads them back
-		const bool pushes = A.dist.d != nullptr && A.dist.push != 0;
+		const bool pushes = distd != nullptr && A.dist.push != 0;
 		if(have_next || pushes) __syncthreads();
 		if(pushes) {
 			const int4 rp = A.tdesc[3*(size_t)ti];      // (this tile's record again: nothing of it is held across the stencil loop)
-			if((A.dist.push & (1u << X_GU)) && A.gu) dist_push_tile(A.dist.d, X_GU, *sdk, rp.x, rp.y, A.gu);
-			if((A.dist.push & (1u << X_LG)) && A.lg) dist_push_tile(A.dist.d, X_LG, *sdk, rp.x, rp.y, A.lg);
+			if((A.dist.push & (1u << X_GU)) && A.gu) dist_push_tile(distd, X_GU, *sdk, rp.x, rp.y, A.gu);
+			if((A.dist.push & (1u << X_LG)) && A.lg) dist_push_tile(distd, X_LG, *sdk, rp.x, rp.y, A.lg);
 		}
 		if(!LOOP) break;
 		if(have_next) { const int4 *const rec = ring + 3*((it + 1) & 1); r0 = rec[0]; r1 = rec[1]; r2 = rec[2]; }
 	}
-	if(A.dist.d && A.dist.last) dist_finish_evaluation(A.dist.d, *sdk, false);
+	if(distd && A.dist.last) dist_finish_evaluation(distd, *sdk, false);
 }
 
 bool pdl_enabled()
@@ -397,12 +403,12 @@ static cudaError_t launch_pdl(Kern kernel, int grid, int block, size_t smem, cud
 	return cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
-template <int GRAD, int LIM, bool PRIM_IN, bool LOOP>
+template <int GRAD, int LIM, bool PRIM_IN, int MODE>
 static int launch_cell_grid(const CellArgs &b, int grid, cudaStream_t s)
 {
 	const CellSmem S(b.m.TC, b.m.HMAX, b.m.EMAX, LIM != LM_NONE || GRAD == GM_GG, GRAD == GM_GG, GRAD == GM_WLS, LIM == LM_VENKAT);
 	if(S.total > 48*1024) {
-		const cudaError_t ea = cudaFuncSetAttribute(cell_kernel<GRAD,LIM,PRIM_IN,LOOP>,
+		const cudaError_t ea = cudaFuncSetAttribute(cell_kernel<GRAD,LIM,PRIM_IN,MODE>,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
 		if(ea != cudaSuccess) return cuda_fail(ea, "cell_kernel smem attribute", __FILE__, __LINE__);
 	}
@@ -410,10 +416,10 @@ static int launch_cell_grid(const CellArgs &b, int grid, cudaStream_t s)
 		static int waves = -1;
 		if(waves < 0) { const char *e = getenv("FVG_CELL_PERSIST"); waves = e ? atoi(e) : 1; if(waves < 1) waves = 1; }
 		const int nt = b.tile1 - b.tile0;
-		const int ctas = waves*resident_ctas((const void*)cell_kernel<GRAD,LIM,PRIM_IN,LOOP>, CELL_BLOCK, (size_t)S.total);
+		const int ctas = waves*resident_ctas((const void*)cell_kernel<GRAD,LIM,PRIM_IN,MODE>, CELL_BLOCK, (size_t)S.total);
 		grid = nt < ctas ? nt : ctas;
 	}
-	const cudaError_t el = launch_pdl(cell_kernel<GRAD,LIM,PRIM_IN,LOOP>, grid, CELL_BLOCK, (size_t)S.total, s, b);
+	const cudaError_t el = launch_pdl(cell_kernel<GRAD,LIM,PRIM_IN,MODE>, grid, CELL_BLOCK, (size_t)S.total, s, b);
 	if(el != cudaSuccess) return cuda_fail(el, "cell_kernel launch", __FILE__, __LINE__);
 	return 0;
 }
@@ -432,8 +438,11 @@ static int launch_cell(const CellArgs &a, cudaStream_t s)
 	// FVG_CELL_PERSIST=<waves> selects the looping form on a grid of waves x resident CTAs (residual path only).
 	static int persist = -1;
 	if(persist < 0) { const char *e = getenv("FVG_CELL_PERSIST"); persist = e ? atoi(e) : 0; }
-	if(persist > 0 && !PRIM_IN) return launch_cell_grid<GRAD,LIM,PRIM_IN,!PRIM_IN>(b, 0, s);
-	return launch_cell_grid<GRAD,LIM,PRIM_IN,false>(b, nt, s);
+	if(!PRIM_IN) {      // (the plug-in entry points with primitive input are single-GPU, one tile per CTA)
+		if(persist > 0) return launch_cell_grid<GRAD,LIM,PRIM_IN,PRIM_IN ? CM_PLAIN : CM_LOOP>(b, 0, s);
+		if(b.dist.d) return launch_cell_grid<GRAD,LIM,PRIM_IN,PRIM_IN ? CM_PLAIN : CM_DIST>(b, nt, s);
+	}
+	return launch_cell_grid<GRAD,LIM,PRIM_IN,CM_PLAIN>(b, nt, s);
 }
 
 int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaStream_t s)

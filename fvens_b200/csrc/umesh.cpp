@@ -412,8 +412,9 @@ void UMesh<scalar,ndim>::compute_face_data()
 template <typename scalar, int ndim>
 void UMesh<scalar,ndim>::compute_periodic_map(const int bcm, const int axis)
 {
-	if(bcm < 0) return;
-	periodicmap.assign(nbface, -1);
+	if(bcm < 0 || axis < 0 || axis > 1) return;
+	// one call per periodic direction (each with its own marker): earlier pairings are kept
+	if((fint)periodicmap.size() != nbface) periodicmap.assign(nbface, -1);
 	const int ax = 1-axis;
 	struct Key { scalar c; fint f; };
 	std::vector<Key> keys;

@@ -134,6 +134,8 @@ public:
 	const scalar* facemetricData() const { return facemetric.data(); }
 	const scalar* areaData() const { return area.data(); }
 	const fint* bfaceData() const { return bface.data(); }
+	/// partner boundary face of every boundary face (-1: none); null before any compute_periodic_map
+	const fint* periodicmapData() const { return periodicmap.empty() ? nullptr : periodicmap.data(); }
 	int gmaxnnode() const { return maxnnode; }
 
 private:

@@ -43,7 +43,7 @@ class HostMeshView(C.Structure):
                 ("nnode", C.POINTER(C.c_int)), ("esuel", C.POINTER(C.c_int)),
                 ("elemface", C.POINTER(C.c_int)), ("intfac", C.POINTER(C.c_int)),
                 ("btags", C.POINTER(C.c_int)), ("facemetric", C.POINTER(C.c_double)),
-                ("area", C.POINTER(C.c_double))]
+                ("area", C.POINTER(C.c_double)), ("bpartner", C.POINTER(C.c_int))]
 
 
 class MeshOpts(C.Structure):
@@ -182,6 +182,20 @@ class UMesh:
             btags=self._arr(v.btags, (v.nbface, v.nbtag), np.int32),
             facemetric=self._arr(v.facemetric, (v.naface, 3), np.float64),
             area=self._arr(v.area, (v.nelem,), np.float64))
+
+    def compute_periodic_map(self, marker, axis):
+        """UMesh::compute_periodic_map: pairs the boundary faces with this marker along `axis` (0: x-periodic, 1: y-periodic);
+        returns the number of pairs. Device meshes built afterwards treat the pairs as interior faces."""
+        n = C.c_int(0)
+        check(load().fvg_umesh_compute_periodic_map(self._h, int(marker), int(axis), C.byref(n)))
+        self.__init__(self._h)
+        return n.value
+
+    def periodic_partners(self):
+        v = self.view
+        if not v.bpartner:
+            return np.full(v.nbface, -1, dtype=np.int32)
+        return self._arr(v.bpartner, (v.nbface,), np.int32)
 
     def reorder_cells(self, perm):
         perm = np.ascontiguousarray(perm, dtype=np.int32)

@@ -143,6 +143,56 @@ def square(n, lo=-5.0, hi=5.0, tri_fraction=0.0, seed=12345, jitter=0.0):
     return coords, nnode, inpoel, bface
 
 
+def periodic_square(n, lo=-5.0, hi=5.0, tri_fraction=0.0, seed=12345, jitter=0.0):
+    """The doubly periodic box of the isentropic-vortex series (tests/isentropic-vortex/grids/dom.geo: [-5,5]^2): as
+    square(), with marker 3 on the left and right sides (periodic in x) and 4 on the bottom and top (periodic in y).
+    Jitter moves interior nodes only, so that partner faces keep matching midpoints."""
+    coords, nnode, inpoel, bface = square(n, lo, hi, tri_fraction, seed, jitter)
+    bface = bface.copy()
+    m = bface[:, 2]
+    bface[:, 2] = np.where((m == 2) | (m == 4), 3, 4)
+    return coords, nnode, inpoel, bface
+
+
+def boundary_edges(nnode, inpoel):
+    """(node0, node1) of every edge that belongs to exactly one cell, oriented as in that cell (counter-clockwise)."""
+    n = len(nnode)
+    j = np.arange(4)[None, :]
+    a = inpoel
+    b = np.take_along_axis(inpoel, (j + 1) % nnode[:, None], axis=1)
+    valid = j < nnode[:, None]
+    a = a[valid]; b = b[valid]
+    lo = np.minimum(a, b).astype(np.int64); hi = np.maximum(a, b).astype(np.int64)
+    key = lo*(int(inpoel.max()) + 1) + hi
+    _, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
+    once = cnt[inv] == 1
+    return np.stack([a[once], b[once]], axis=1).astype(np.int32)
+
+
+def unfold_periodic(coords, nnode, inpoel, period, marker=9):
+    """3 x 3 copies of a doubly periodic mesh laid side by side (the centre copy first, so that its cells keep their
+    indices), nodes on the seams merged, every outer edge a boundary face with `marker`. On this mesh an ordinary
+    (non-periodic) evaluation gives, in the centre copy, exactly what a periodic evaluation gives on the original mesh:
+    the oracle for the periodic pairing, which the reference cannot run."""
+    shifts = [(0, 0)] + [(i, j) for j in (-1, 0, 1) for i in (-1, 0, 1) if (i, j) != (0, 0)]
+    npo = len(coords)
+    allc = np.concatenate([coords + np.array([i*period, j*period]) for (i, j) in shifts])
+    h = np.sqrt(period*period/len(nnode))
+    keyxy = np.round(allc/(1e-6*h)).astype(np.int64)
+    _, first, inv = np.unique(keyxy, axis=0, return_index=True, return_inverse=True)
+    inv = inv.reshape(-1)
+    newcoords = allc[first]
+    cells = []
+    for k in range(len(shifts)):
+        ip = np.where(inpoel >= 0, inv[np.where(inpoel >= 0, inpoel, 0) + k*npo], -1)
+        cells.append(ip)
+    ip = np.concatenate(cells).astype(np.int32)
+    nn = np.tile(nnode, len(shifts)).astype(np.int32)
+    be = boundary_edges(nn, ip)
+    bface = np.concatenate([be, np.full((len(be), 1), marker, dtype=np.int32)], axis=1).astype(np.int32)
+    return newcoords, nn, ip, bface
+
+
 def cell_centres(coords, nnode, inpoel):
     idx = np.where(inpoel < 0, 0, inpoel)
     w = (inpoel >= 0).astype(np.float64)

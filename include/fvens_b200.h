@@ -96,8 +96,17 @@ typedef struct {
 	const int *btags;           /* [nbface][nbtag]         gbtags    */
 	const double *facemetric;   /* [naface][3] nx,ny,len   gfacemetric */
 	const double *area;         /* [nelem]                 garea     */
+	const int *bpartner;        /* [nbface] partner boundary face of a periodic face, -1 otherwise; may be NULL
+	                               (UMesh::compute_periodic_map, mesh.cpp:369-424). The device mesh turns a periodic
+	                               pair into interior faces: each of the two boundary faces gets the partner's cell,
+	                               displaced by the period, as its right cell (one flux per geometric edge
+	                               and cell, unlike the reference's dead periodic path, which would count it twice) */
 } fvg_host_mesh;
 int fvg_umesh_view(const fvg_umesh *m, fvg_host_mesh *view);
+/* UMesh::compute_periodic_map(bcm, axis) (mesh/mesh.cpp:369-424): pairs the boundary faces with marker `marker` whose
+ * midpoints agree in the coordinate other than `axis` (0: periodic in x, 1: periodic in y). One call per periodic
+ * direction, each with its own marker; take the view (fvg_umesh_view) afterwards. Returns the number of pairs. */
+int fvg_umesh_compute_periodic_map(fvg_umesh *m, int marker, int axis, int *npairs);
 
 /* ------------------------------------------------------------------------------------------------
  * Device mesh: SoA copy of the arrays above, cells renumbered for locality, faces regrouped into
@@ -265,7 +274,8 @@ typedef struct {
 
 /* FlowBCConfig (spatial/abc.hpp:34-40); type = BCType of spatial/abctypes.hpp:13-22:
  * 0 slip wall, 1 far field, 2 inflow-outflow, 3 subsonic inflow (vals = p0, T0), 4 extrapolation,
- * 5 periodic (rejected), 6 isothermal wall (vals = tangential velocity, T), 7 adiabatic wall (vals[0] = v_t) */
+ * 5 periodic (accepted for a marker whose faces the mesh has all paired, see fvg_host_mesh::bpartner; no ghost state is
+ * ever computed for it), 6 isothermal wall (vals = tangential velocity, T), 7 adiabatic wall (vals[0] = v_t) */
 typedef struct {
 	int tag, type;
 	double vals[2];

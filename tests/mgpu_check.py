@@ -23,6 +23,8 @@ CASES = [
     ("inviscid", dict(flux="LLF", gradient="NONE", reconstruction="NONE", order2=False)),
     ("viscous", dict(flux="ROE", gradient="LEASTSQUARES", reconstruction="NONE")),
     ("viscous", dict(flux="HLL", gradient="GREENGAUSS", reconstruction="BARTHJESPERSEN")),
+    # doubly periodic box: periodic rows travel with the partition's rows (some of them from a rank to itself)
+    ("periodic", dict(flux="ROE", gradient="LEASTSQUARES", reconstruction="VENKATAKRISHNAN", limiter_param=2.0)),
 ]
 
 
@@ -58,7 +60,16 @@ def main():
     bcs_i = [(2, "slipwall", (0, 0)), (3, "inflowoutflow", (0, 0)), (4, "inflowoutflow", (0, 0))]
     bcs_v = [(2, "adiabaticwall", (0, 0)), (3, "farfield", (0, 0)), (4, "farfield", (0, 0))]
     u0 = synth.perturbed_state(rc, 1.4, 0.5)
-    part = (lib.partition_rcb if os.environ.get("MGPU_PARTITION", "sfc") == "rcb" else lib.partition_sfc)(um, world)
+    partition = lib.partition_rcb if os.environ.get("MGPU_PARTITION", "sfc") == "rcb" else lib.partition_sfc
+    part = partition(um, world)
+    base = (um, u0, part)
+    parrs = synth.periodic_square(40, tri_fraction=0.3, jitter=0.15)
+    pum = lib.UMesh.from_arrays(*parrs)
+    pum.compute_periodic_map(3, 0); pum.compute_periodic_map(4, 1)
+    prc = synth.cell_centres(parrs[0], parrs[1], parrs[2])
+    pu0 = synth.perturbed_state(prc/5.0, 1.4, 0.5)          # sin(2 pi x/5) cos(3 pi y/5): periodic on [-5,5]^2
+    periodic = (pum, pu0, partition(pum, world))
+    bcs_p = [(3, "periodic", (0, 0)), (4, "periodic", (0, 0))]
     stream = torch.cuda.Stream(device=dev)          # graphs cannot be captured on the legacy default stream
     ok = True
 
@@ -91,7 +102,10 @@ def main():
         os._exit(0 if good else 1)       # the windows of a broken exchange are not worth an orderly teardown
 
     for kind, numerics in CASES:
-        phys, bcs = (inviscid, bcs_i) if kind == "inviscid" else (viscous, bcs_v)
+        phys, bcs = (viscous, bcs_v) if kind == "viscous" else ((inviscid, bcs_p) if kind == "periodic" else (inviscid, bcs_i))
+        if kind == "periodic" and os.environ.get("FVG_DIST", "fused") != "fused":
+            continue          # only the fused engine delivers a rank's periodic rows to itself
+        um, u0, part = periodic if kind == "periodic" else base
         df = DistFlow(um, part, rank, world, phys, dev, tile_cells=128, bcs=bcs, **numerics)
         ids = torch.from_numpy(df.global_ids.astype(np.int64)).to(dev)
         n = df.ncell + df.nghost
