@@ -31,22 +31,127 @@ NUMERICS = {
     "roe-wls-venkat": ("ROE", "LEASTSQUARES", "VENKATAKRISHNAN", 2.0, 144 + 32 + 8, 160),
     "hllc-gg-bj": ("HLLC", "GREENGAUSS", "BARTHJESPERSEN", 0.0, 144 + 8, 160),
 }
-BCS = [(2, "slipwall", (0.0, 0.0)), (3, "inflowoutflow", (0.0, 0.0)), (4, "inflowoutflow", (0.0, 0.0))]
+FLUXES = ["LLF", "VANLEER", "AUSM", "HLL", "HLLC", "ROE"]
+# the default workload's free-stream Mach number and boundary conditions (also used by tests/test_gpu_scale.py and tools/)
 MINF = 0.2
+BCS = [(2, "slipwall", (0.0, 0.0)), (3, "inflowoutflow", (0.0, 0.0)), (4, "inflowoutflow", (0.0, 0.0))]
 
 
-def lattice_for(cells):
-    """Base lattice of the bump channel (aspect 2.67) whose hybrid mesh has ~`cells` cells (x 4/3 from splitting)."""
-    nbase = cells/(1.0 + 1.0/3.0)
-    ny = int(round((nbase/2.6667)**0.5))
-    nx = int(round(2.6667*ny))
+def lattice_for(cells, aspect=2.6667, split=1.0/3.0):
+    """Base lattice nx x ny (nx/ny = aspect) whose mesh has ~`cells` cells when a fraction `split` of the quads is cut in two."""
+    nbase = cells/(1.0 + split)
+    ny = int(round((nbase/aspect)**0.5))
+    nx = int(round(aspect*ny))
     return nx, ny
 
 
-def algorithmic_bytes(numerics, nc, nf):
-    """pass A = c_A*N_c + 16*N_f (face midpoints), pass B = 160*N_c + 48*N_f."""
-    cA, cB = NUMERICS[numerics][4], NUMERICS[numerics][5]
-    return cA*nc + 16*nf, cB*nc + 48*nf
+class Workload:
+    """One benchmark configuration: mesh arrays (numpy only, Hilbert-ordered), state, physics, boundary conditions,
+    numerics and the algorithmic bytes of SURVEY 8(d). Shared by both arms and by the cpu_baseline leg."""
+
+    def __init__(self, args, world=1):
+        self.name = args.workload
+        self.args = args
+        w = args.workload
+        self.periodic = []
+        self.viscous = False
+        self.reference_can_run = True
+        if w == "bump":          # BASELINE configs[2] mesh with the north-star headline numerics (or --numerics hllc-gg-bj)
+            flux, grad, recon, lp, cA, cB = NUMERICS[args.numerics]
+            self.minf, self.bcs = MINF, BCS
+            self.num = dict(flux=flux, gradient=grad, reconstruction=recon, limiter_param=lp, order2=True)
+            self.cA, self.cB, self.cX = cA, cB, 0
+            self.what = (f"synthetic hybrid tri/quad Gaussian-bump channel, {args.cells/1e6:g}M cells, {flux}+{grad}+{recon} second-order "
+                         f"residual with local time steps (BASELINE configs[2] mesh, north-star headline numerics)")
+            self.tag = args.numerics
+        elif w == "viscous":     # BASELINE configs[1] numerics at benchmark size: laminar Navier-Stokes, Roe + WLS + MAG viscous flux
+            self.minf, self.viscous = 0.5, True
+            self.bcs = [(2, "adiabaticwall", (0.0, 0.0)), (3, "farfield", (0.0, 0.0)), (4, "farfield", (0.0, 0.0))]
+            self.num = dict(flux="ROE", gradient="LEASTSQUARES", reconstruction="NONE", limiter_param=1.0, order2=True)
+            self.cA, self.cB, self.cX = 144 + 32, 160, 0
+            self.what = (f"synthetic hybrid tri/quad bump channel with no-slip adiabatic walls, {args.cells/1e6:g}M cells, laminar "
+                         f"Navier-Stokes (Re 5000, Sutherland), ROE + LEASTSQUARES + modified-average-gradient viscous flux, second order "
+                         f"(BASELINE configs[1] numerics at benchmark size)")
+            self.tag = "roe-wls-none-viscous"
+        elif w == "ogrid-weno":  # BASELINE configs[3]: O-grid around a cylinder, quads, WLS + WENO, one of the six fluxes
+            self.minf = 0.38
+            self.bcs = [(2, "slipwall", (0.0, 0.0)), (4, "farfield", (0.0, 0.0))]
+            self.num = dict(flux=args.flux.upper(), gradient="LEASTSQUARES", reconstruction="WENO", limiter_param=args.weno_lambda, order2=True)
+            self.cA, self.cB, self.cX = 144 + 32 + 0, 160, 192
+            self.what = (f"synthetic O-grid around a cylinder (2dcylstruct.geo scaled up), quads, {args.cells/1e6:g}M cells, "
+                         f"{args.flux.upper()} + LEASTSQUARES + WENO (lambda = {args.weno_lambda:g}) second-order residual with local time steps "
+                         f"(BASELINE configs[3]; 50M cells at 8 GPUs is {50/8:g}M per GPU)")
+            self.tag = f"{args.flux.lower()}-wls-weno"
+        elif w == "vortex":      # BASELINE configs[4]: doubly periodic box of the isentropic vortex, n x n quads
+            self.minf = 0.5
+            self.bcs = [(3, "periodic", (0.0, 0.0)), (4, "periodic", (0.0, 0.0))]
+            self.periodic = [(3, 0), (4, 1)]
+            self.num = dict(flux="ROE", gradient="LEASTSQUARES", reconstruction="NONE", limiter_param=1.0, order2=True)
+            self.cA, self.cB, self.cX = 144 + 32, 160, 0
+            self.n = int(args.n if args.n else round(args.cells**0.5))
+            if args.scaling == "weak":
+                self.n = int(round(self.n*world**0.5))
+            self.what = (f"isentropic-vortex box [-5,5]^2, {self.n} x {self.n} quads, periodic in x and y, ROE + LEASTSQUARES + linear "
+                         f"reconstruction, second-order residual with local time steps (BASELINE configs[4]; "
+                         f"{'weak' if args.scaling == 'weak' else 'strong'} scaling of the halo exchange)")
+            self.tag = "roe-wls-none-periodic"
+            self.reference_can_run = False       # no periodic FlowBC in the reference (SURVEY H8)
+        else:
+            raise SystemExit(f"unknown workload {w}")
+
+    def physics(self):
+        from fvens_b200 import lib
+        return lib.make_physics(1.4, self.minf, 288.15, 5000.0, 0.72, 0.0, self.viscous, False)
+
+    def arrays(self):
+        """(coords, nnode, inpoel, bface), state, lattice - plain numpy, cells renumbered along a Hilbert curve (the
+        reference's `-mesh_reorder` step with a locality order; synth.hilbert_order is the numpy twin of
+        fvg_umesh_hilbert_ordering). Both arms are built from this, so they time the same mesh in the same numbering."""
+        from fvens_b200 import synth
+        a = self.args
+        if self.name in ("bump", "viscous"):
+            lat = lattice_for(a.cells)
+            coords, nnode, inpoel, bface = synth.bump_channel(lat[0], lat[1], seed=12345)
+        elif self.name == "ogrid-weno":
+            lat = lattice_for(a.cells, aspect=12500.0/4000.0, split=0.0)
+            coords, nnode, inpoel, bface = synth.ogrid_cylinder(lat[0], lat[1])
+        else:
+            lat = (self.n, self.n)
+            coords, nnode, inpoel, bface = synth.periodic_square(self.n)
+        rc = synth.cell_centres(coords, nnode, inpoel)
+        perm = synth.hilbert_order(rc)
+        nnode, inpoel, rc = np.ascontiguousarray(nnode[perm]), np.ascontiguousarray(inpoel[perm]), rc[perm]
+        if self.name == "vortex":
+            u = synth.isentropic_vortex(rc, 1.4, self.minf, 0.0)
+        else:
+            u = synth.perturbed_state(rc, 1.4, self.minf)
+        return (coords, nnode, inpoel, bface), np.ascontiguousarray(u), lat
+
+    def host_mesh(self, arrs):
+        from fvens_b200 import lib
+        um = lib.UMesh.from_arrays(*arrs)
+        for marker, axis in self.periodic:
+            um.compute_periodic_map(marker, axis)
+        return um
+
+    def algorithmic_bytes(self, nc, nf):
+        """pass A = c_A*N_c + 16*N_f (face midpoints), pass B = 160*N_c + 48*N_f, WENO pass 192*N_c."""
+        return self.cA*nc + 16*nf + self.cX*nc, self.cB*nc + 48*nf
+
+    def config(self, nc, nf, lat):
+        """`config` of the JSON line: the workload only, identical in both arms (the GPU arm's layout goes under `layout`)."""
+        return {"workload": self.what, "cells": int(nc), "faces": int(nf), "lattice": [int(lat[0]), int(lat[1])],
+                "numerics": self.tag, "cell_order": "Hilbert curve (host renumbering, identical in both arms)",
+                "l2": "inputs (32 B state + 64 B gradients + ~300 B mesh per cell: 4 GB at 10M cells) exceed the 126 MB L2 from "
+                      "0.4M cells per GPU up; no explicit flush"}
+
+
+def build_case(cells, numerics, tile):
+    """Host mesh of the CUDA arm for the default workload (used by tests/test_gpu_scale.py and tools/)."""
+    ns = argparse.Namespace(workload="bump", numerics=numerics, cells=cells)
+    wl = Workload(ns)
+    arrs, u, lat = wl.arrays()
+    return wl.host_mesh(arrs), arrs, u, lat
 
 
 class ClockSampler:
@@ -99,42 +204,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_arrays(cells):
-    """The benchmark mesh and state as plain numpy arrays (no library): bump-channel generator, cells renumbered along a
-    Hilbert curve (the reference's `-mesh_reorder` step with a locality order; synth.hilbert_order is the numpy twin of
-    fvg_umesh_hilbert_ordering), perturbed free stream. Both arms - and the cpu_baseline leg - are built from this, so
-    they time the same mesh in the same numbering; the reference arm never maps libfvens_b200.so."""
-    from fvens_b200 import synth
-    nx, ny = lattice_for(cells)
-    coords, nnode, inpoel, bface = synth.bump_channel(nx, ny, seed=12345)
-    rc = synth.cell_centres(coords, nnode, inpoel)
-    perm = synth.hilbert_order(rc)
-    nnode, inpoel, rc = np.ascontiguousarray(nnode[perm]), np.ascontiguousarray(inpoel[perm]), rc[perm]
-    u = synth.perturbed_state(rc, 1.4, MINF)
-    return (coords, nnode, inpoel, bface), u, (nx, ny)
-
-
-def build_case(cells, numerics, tile):
-    """Host mesh of the CUDA arm from the same arrays (already Hilbert-ordered: the device numbering is the identity)."""
-    from fvens_b200 import lib
-    arrs, u, lat = build_arrays(cells)
-    um = lib.UMesh.from_arrays(*arrs)
-    return um, arrs, u, lat
-
-
-def workload_config(args, nc, nf, lat):
-    """`config` of the JSON line: the workload only, identical in both arms (the GPU arm's layout details go under
-    `layout`)."""
-    flux, grad, recon, lp = NUMERICS[args.numerics][:4]
-    return {"workload": f"synthetic hybrid tri/quad Gaussian-bump channel, {args.cells/1e6:g}M cells, "
-                        f"{flux}+{grad}+{recon} second-order residual with local time steps (BASELINE configs[2] mesh, "
-                        f"north-star headline numerics)",
-            "cells": int(nc), "faces": int(nf), "lattice": [int(lat[0]), int(lat[1])], "numerics": args.numerics,
-            "cell_order": "Hilbert curve (host renumbering, identical in both arms)",
-            "l2": "inputs (320 MB state + 640 MB gradients + 3 GB mesh at 10M cells) exceed the 126 MB L2; no explicit flush"}
-
-
-def cpu_reference(cells, numerics, steps, warmup, extras=False, prebuilt=None):
+def cpu_reference(wl, steps, warmup, extras=False, prebuilt=None):
     """The reference's CPU path on the host cores, on the SAME mesh as the CUDA arm. When
     oracle/_ref/libfvens_ref_c_omp.so exists (the reference's own flow_spatial.cpp and everything it calls, compiled
     unmodified with its OpenMP pragmas on - oracle/ref_tier_c.cpp) that is what is timed (kind "reference"); otherwise
@@ -149,11 +219,11 @@ def cpu_reference(cells, numerics, steps, warmup, extras=False, prebuilt=None):
     os.environ.setdefault("OMP_PROC_BIND", "close")
     import orc
     from fvens_b200 import lib      # constants only (name tables, the physics struct); the shared library is not loaded
-    arrs, u, (nx, ny) = prebuilt if prebuilt is not None else build_arrays(cells)
+    arrs, u, (nx, ny) = prebuilt if prebuilt is not None else wl.arrays()
     om = orc.Mesh.from_arrays(*arrs)
-    flux, grad, recon, lp = NUMERICS[numerics][:4]
-    phys = lib.make_physics(1.4, MINF, 288.15, 5000.0, 0.72, 0.0)
-    bcs = [(t, lib.BC[ty], v) for (t, ty, v) in BCS]
+    flux, grad, recon, lp = wl.num["flux"], wl.num["gradient"], wl.num["reconstruction"], wl.num["limiter_param"]
+    phys = wl.physics()
+    bcs = [(t, lib.BC[ty], v) for (t, ty, v) in wl.bcs]
     build = "-O3 -msse4.2 (its default release flags)"
     extra = {}
 
@@ -202,7 +272,7 @@ def cpu_reference(cells, numerics, steps, warmup, extras=False, prebuilt=None):
     what = ("the reference's own FlowFV::compute_residual (flow_spatial.cpp and its callees compiled unmodified, OpenMP, " + build + ")"
             if kind == "reference" else "the oracle's restatement of the reference's loops (OpenMP)")
     info = {"cells": om.nelem, "faces": om.naface, "cores": cores, "kind": kind, "lattice": (nx, ny), "extra": extra,
-            "sample": f"{what} on the whole workload mesh: bump channel {nx}x{ny} base lattice = {om.nelem} cells / {om.naface} "
+            "sample": f"{what} on the whole workload mesh: {nx}x{ny} base lattice = {om.nelem} cells / {om.naface} "
                       f"faces, Hilbert-ordered (same arrays, numbering, state and numerics as the CUDA arm), {steps} evaluations "
                       f"after {warmup} warm-up, {cores} threads"}
     return om.naface/dt/1e9, dt*1e3, info
@@ -215,7 +285,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=float, default=10.0e6)
-    ap.add_argument("--numerics", default="roe-wls-venkat", choices=list(NUMERICS))
+    ap.add_argument("--workload", default="bump", choices=["bump", "viscous", "ogrid-weno", "vortex"],
+                    help="bump: the headline (BASELINE configs[2] mesh, north-star numerics); viscous: configs[1] numerics at size; "
+                         "ogrid-weno: configs[3]; vortex: configs[4] periodic box")
+    ap.add_argument("--numerics", default="roe-wls-venkat", choices=list(NUMERICS), help="bump workload only")
+    ap.add_argument("--flux", default="roe", choices=[f.lower() for f in FLUXES], help="ogrid-weno workload: the inviscid flux")
+    ap.add_argument("--weno-lambda", type=float, default=1.0, help="ogrid-weno workload: central weight of the WENO average (1 or 20)")
+    ap.add_argument("--n", type=int, default=0, help="vortex workload: cells per side (default sqrt(--cells))")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="vortex workload with N > 1: fixed mesh, or n*sqrt(N)")
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--cpu-cells", type=float, default=0.0,
                     help="cells of the CPU arms' mesh; 0 (default) = the workload's own mesh (same config)")
@@ -230,20 +307,26 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    flux, grad, recon, lp = NUMERICS[args.numerics][:4]
+    wl = Workload(args, world)
     if args.impl == "reference":
         if rank != 0:
+            return
+        if not wl.reference_can_run:
+            print(json.dumps({"impl": "reference", "unavailable": "the reference has no periodic FlowBC (abc.cpp:493-494 throws) and its "
+                              "face loop would count periodic edges twice (SURVEY H8/H8b): it cannot evaluate this workload"}))
             return
         import __graft_entry__ as g
         g.build_oracle(quiet=True)        # the checker libraries only: this process never maps libfvens_b200.so
         # same mesh, same --steps / --warmup as the CUDA arm (a 10M-cell evaluation takes a few tenths of a second on a
         # 16-thread host; --cpu-cells bounds the sample if a host is too slow for that)
-        cells = args.cpu_cells if args.cpu_cells else args.cells
-        gf, ms, info = cpu_reference(cells, args.numerics, max(1, args.steps), max(1, args.warmup), extras=True)
+        if args.cpu_cells:
+            args.cells = args.cpu_cells
+            wl = Workload(args, world)
+        gf, ms, info = cpu_reference(wl, max(1, args.steps), max(1, args.warmup), extras=True)
         line = {"impl": "reference", "metric": "Gfaces/s", "value": gf, "unit": "Gfaces/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(args, info["cells"], info["faces"], info["lattice"]),
+                "scaling": args.scaling if args.workload == "vortex" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": wl.config(info["cells"], info["faces"], info["lattice"]),
                 "residual_evals_per_s": 1e3/ms,
                 "cpu_baseline": {"value": gf, "unit": "Gfaces/s", "cores": info["cores"], "kind": info["kind"],
                                  "sample": info["sample"], **info["extra"]},
@@ -281,11 +364,13 @@ def main():
     lib.load()
 
     # every rank builds the same global mesh; with N > 1 it is partitioned (strong scaling of the 10M-cell case)
-    um, arrs, u, (nx, ny) = build_case(args.cells, args.numerics, args.tile)
-    phys = lib.make_physics(1.4, MINF, 288.15, 5000.0, 0.72, 0.0)
+    arrs, u, (nx, ny) = wl.arrays()
+    um = wl.host_mesh(arrs)
+    phys = wl.physics()
+    BCS = wl.bcs
     nc_glob, nf_glob = um.nelem, um.naface
     stream = torch.cuda.current_stream().cuda_stream
-    num = dict(flux=flux, gradient=grad, reconstruction=recon, limiter_param=lp, order2=True)
+    num = wl.num
     if world == 1:
         dm = lib.DeviceMesh(um, reorder="none", tile_cells=args.tile, device=local_rank)
         fl = lib.FlowFV(dm, phys, bcs=BCS, **num)
@@ -440,13 +525,13 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    bA, bB = algorithmic_bytes(args.numerics, nc_glob, nf_glob)
+    bA, bB = wl.algorithmic_bytes(nc_glob, nf_glob)
     gfaces = nf_glob/(ms_step*1e-3)/1e9
     info = dm.info
     traffic, traffic_src = None, None
     try:        # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get(f"face_kernel:{args.numerics}:{args.tile}:{int(args.cells)}")
+        traffic = tj.get(f"face_kernel:{wl.tag}:{args.tile}:{int(args.cells)}") if args.workload == "bump" else None
         if traffic is not None:
             traffic_src = ("not measured by this run: dram__bytes_read.sum + dram__bytes_write.sum of one face_kernel launch from the "
                            "committed `ncu --set full` capture of this command, " + str(tj.get("source", "profiles/")))
@@ -454,9 +539,10 @@ def main():
         pass
     line = {
         "metric": "Gfaces/s", "value": gfaces, "unit": "Gfaces/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": args.scaling if args.workload == "vortex" else "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, nc_glob, nf_glob, (nx, ny)),
+        "config": wl.config(nc_glob, nf_glob, (nx, ny)),
         "layout": {"cells_on_rank0": nc, "ghost_cells_on_rank0": int(info.nghost),
                    "tile_cells": info.tile_cells, "cut_face_duplicates_rank0": info.ncut_dup,
                    "parallelism": "single GPU" if world == 1 else
@@ -496,9 +582,12 @@ def main():
         line["roofline"] = {"bound": "hbm", "kernel": "whole evaluation per GPU (cell pass + face pass + halos)",
                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach/peak, "frac_of_nominal_8000_GBs": ach/8000.0, "traffic": None,
                             "algorithmic_bytes_per_launch": (bA + bB)/world, "peak_source": peak_src}
-    if not args.no_cpu_baseline and world == 1:
-        gf, ms, ci = cpu_reference(args.cpu_cells if args.cpu_cells else args.cells, args.numerics, 6, 2,
-                                   prebuilt=None if args.cpu_cells else (arrs, u, (nx, ny)))
+    if not args.no_cpu_baseline and world == 1 and wl.reference_can_run:
+        wlc = wl
+        if args.cpu_cells:
+            args.cells = args.cpu_cells
+            wlc = Workload(args, world)
+        gf, ms, ci = cpu_reference(wlc, 6, 2, prebuilt=None if args.cpu_cells else (arrs, u, (nx, ny)))
         line["cpu_baseline"] = {"value": gf, "unit": "Gfaces/s", "cores": ci["cores"], "kind": ci["kind"],
                                 "sample": ci["sample"], "ms_per_eval": ms, **ci["extra"]}
     print(json.dumps(line))

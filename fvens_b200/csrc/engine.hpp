@@ -168,6 +168,7 @@ struct fvg_flow {
 	double *d_rperm = nullptr;     ///< [ncell][4] scratch residual in device order
 	double *d_dtperm = nullptr;    ///< [ncell]
 	double *d_u2 = nullptr;        ///< [ncell][4] second state buffer for the fused step
+	double *d_rk = nullptr;        ///< scratch of fvg_tvdrk_solve: stage state, residual, local steps, areas, reduction blocks
 	double *d_partial = nullptr;   ///< [ntile][FACE_BLOCK/32] partial norms per tile and warp
 	double *d_norm = nullptr;      ///< [1]
 	double *h_norm = nullptr;      ///< pinned [1]
@@ -215,6 +216,7 @@ struct CellArgs {
 	bool ordered = false;        ///< walk the tiles in the order of DMesh::tile_order (interior tiles first)
 	GhostSrc gs_u;               ///< ghost rows of u (partition-boundary tiles wait for them inside the kernel)
 	DistRole dist;               ///< fused multi-GPU evaluation (dist.cu): what this launch pushes and waits for
+	int pdl = 0;                     ///< launched with the programmatic-dependent-launch attribute: griddepcontrol.wait before the first read
 	const int *src_idx = nullptr;    ///< caller-ordered state: row of `u` holding device cell i (null: u is in device order)
 	const int *halo_src = nullptr;   ///< ... and the same for the entries of thalo (precomputed: no dependent index load)
 	double *ucopy = nullptr;         ///< ... the own rows are also written here in device order (read by the face pass)

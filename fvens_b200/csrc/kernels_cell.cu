@@ -8,364 +8,9 @@
  * The gradient + limiter pass is a cell-gather: one thread per cell walks its <= 4 faces, so there
  * is no scatter at all (the reference scatters from faces with omp atomics).
  */
-#include "engine.hpp"
-#include "face_kernel.cuh"   // ld4 / st4 / extrapolation helpers
+#include "cell_kernel.cuh"
 
 namespace fvg {
-
-enum { GM_ZERO = 0, GM_GG = 1, GM_WLS = 2, GM_GIVEN = 3 };
-enum { LM_NONE = 0, LM_BJ = 1, LM_VENKAT = 2 };
-
-/// 32-byte row from shared memory, halves at double offsets o0 and o1 (0 and 2 in either order)
-__device__ __forceinline__ void lds4h(const double *p, int o0, int o1, double v[4]) {
-	const double2 a = *reinterpret_cast<const double2*>(p + o0), b = *reinterpret_cast<const double2*>(p + o1);
-	v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-
-/// Shared-memory carve-up of the cell kernel
-struct CellSmem {
-	int sp, src, sgr, sW, scl, sV, sclen, bar, ring, total;
-	__host__ __device__ CellSmem(int TC, int HMAX, int EMAX, bool mids, bool metrics, bool wls, bool venkat) {
-		const int CAPC = TC + HMAX;
-		int o = 0;
-		sp = o; o += CAPC*32;
-		src = o; o += CAPC*16;
-		sgr = o; o += mids ? EMAX*16 : 0;
-		sW = o; o += metrics ? EMAX*32 : 0;
-		scl = o; o += TC*16;
-		sV = o; o += wls ? TC*32 : 0;
-		sclen = o; o += venkat ? (TC + 2)*8 : 0;
-		bar = o; o += 16;
-		ring = o; o += 2*48 + 16;             // descriptor records of the current and the next tile; evaluation number + ghost-row area
-		total = o;
-	}
-};
-
-/** Gradient + limiter pass: persistent CTAs (three per SM) walking over tiles ti = tile0 + blockIdx.x, + gridDim.x, ...
- * The tile's cell states and centres (own cells by TMA bulk copy, halo cells by cp.async gathers) and the face
- * midpoints of its stream are staged in shared memory; conserved states are converted to primitive ONCE per staged
- * cell (the reference converts the whole field in a separate pass, flow_spatial.cpp:697-699). Then one thread per own
- * cell gathers its <= 4 neighbours from shared memory: no scatter, no atomics. The staging buffers are single
- * (three CTAs per SM overlap each other's copies); the next tile's descriptor is fetched while the current tile
- * computes, so the only exposed latency per tile is that of its own copies.
- * Multi-GPU (A.dist): the first wave's prologue pushes the state rows the neighbours need, a tile that sees ghost
- * cells waits for the neighbours' state rows and reads them from the halo window, and every tile pushes the gradient
- * rows on its send list as soon as it has stored them (dist_dev.cuh).
- * Caller-ordered state (A.src_idx): own and halo rows are gathered through the permutation and the own rows are also
- * written in device order to A.ucopy, which is what the face pass reads - no separate permutation kernel.
- * MODE: CM_PLAIN one tile per CTA (grid = number of tiles), no multi-GPU code; CM_DIST the same with it; CM_LOOP a
- * resident-size grid walking the tiles. In the first two nothing is carried from tile to tile, which keeps the stencil
- * loop within the 80 registers of three CTAs per SM. */
-enum { CM_PLAIN = 0, CM_DIST = 1, CM_LOOP = 2 };
-template <int GRAD, int LIM, bool PRIM_IN, int MODE>
-__global__ void __launch_bounds__(CELL_BLOCK, FVG_CELL_MINB)
-cell_kernel(const __grid_constant__ CellArgs A)
-{
-	constexpr bool LOOP = MODE == CM_LOOP;
-	// the plain form is compiled without the multi-GPU code: measured faster on one GPU than the same kernel with the
-	// (never taken) push / wait branches in it
-	const DistDev *const distd = MODE != CM_PLAIN ? A.dist.d : nullptr;
-	extern __shared__ __align__(1024) unsigned char smraw[];
-	const DMesh &M = A.m;
-	constexpr bool MIDS = LIM != LM_NONE || GRAD == GM_GG;
-	constexpr bool METRICS = GRAD == GM_GG;
-	const CellSmem S(M.TC, M.HMAX, M.EMAX, MIDS, METRICS, GRAD == GM_WLS, LIM == LM_VENKAT);
-	double *const sp = reinterpret_cast<double*>(smraw + S.sp);
-	double2 *const src = reinterpret_cast<double2*>(smraw + S.src);
-	double2 *const sgr = reinterpret_cast<double2*>(smraw + S.sgr);
-	const double2 *const sW = reinterpret_cast<const double2*>(smraw + S.sW);     // two 16-byte planes: weights, len*normal
-	const uint4 *const scl = reinterpret_cast<const uint4*>(smraw + S.scl);
-	const double4 *const sV = reinterpret_cast<const double4*>(smraw + S.sV);
-	const double *const sclen = reinterpret_cast<const double*>(smraw + S.sclen);
-	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);
-	constexpr bool NEED_NBRS = GRAD == GM_GG || GRAD == GM_WLS || LIM != LM_NONE;
-
-	const int tid = threadIdx.x, G = (int)gridDim.x;
-	const int tend = A.tile1;
-	int ti = A.tile0 + (int)blockIdx.x;
-	// the tile's 48-byte descriptor record (DMesh::tdesc): the first one is loaded directly, those of a CTA's further
-	// tiles (grids smaller than the tile count) travel into a two-slot shared-memory ring one tile ahead
-	int4 *const ring = reinterpret_cast<int4*>(smraw + S.ring);
-	if(tid == 0) mbar_init(bar, 1);
-	pdl_launch_dependents();
-	// (programmatic dependent launch) the tile descriptors are mesh data; the state read below may be the previous
-	// kernel's output and the gradient rows written at the end are still being read by the previous face pass until it
-	// completes
-	pdl_wait();
-	int4 r0 = make_int4(0, 0, 0, 0), r1 = r0, r2 = r0;
-	if(ti < tend) { r0 = A.tdesc[3*(size_t)ti]; r1 = A.tdesc[3*(size_t)ti + 1]; r2 = A.tdesc[3*(size_t)ti + 2]; }
-	// fused multi-GPU evaluation: the evaluation number, the window area of this evaluation's state rows, the prologue
-	// (both kept in shared memory: they are needed once per partition-boundary tile only)
-	unsigned long long *const sdk = reinterpret_cast<unsigned long long*>(smraw + S.ring + 96);
-	const double **const sghost = reinterpret_cast<const double**>(smraw + S.ring + 104);
-	if(distd) {
-		const unsigned long long dk = distd->ctl->k;
-		if(tid == 0) { *sdk = dk; *sghost = (A.dist.wait & (1u << X_U)) ? dist_ghost_rows(distd, X_U, dk) : nullptr; }
-		if(A.dist.first) dist_push_state_prologue(distd, dk, A.u, A.dist.force_push, A.src_idx);
-	}
-	else if(tid == 0) { *sdk = 0; *sghost = A.gs_u.rows; }
-	__syncthreads();
-
-	for(int it = 0; ti < tend; it++, ti += G) {
-		const int t = r0.x, c0 = r0.y, nc = r0.z, h0 = r0.w, nh = r1.x, e0 = r1.y, ne = r1.z;
-		const int4 tbq = make_int4(r2.x, r2.y, r2.z, r1.w);
-		// the next tile's record travels while this tile is staged (it joins this tile's cp.async group)
-		const bool have_next = LOOP && ti + G < tend;
-		if(have_next) fetch_tile_desc(ring + 3*((it + 1) & 1), A.tdesc, ti + G);
-		if(tid == 0) {
-			if(it > 0) fence_proxy_async();       // the buffers were read through the generic proxy by the previous tile
-			unsigned bytes = (unsigned)nc*((A.src_idx ? 0u : 32u) + 16u + 16u + (GRAD == GM_WLS ? 32u : 0u))
-			               + (LIM == LM_VENKAT ? (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u : 0u);
-			if(MIDS) bytes += (unsigned)ne*16u;
-			if(METRICS) bytes += (unsigned)ne*32u;
-			mbar_expect_tx(bar, bytes);
-			if(!A.src_idx) bulk_g2s(sp, A.u + 4*(size_t)c0, (unsigned)nc*32u, bar);
-			bulk_g2s(src, M.rc + c0, (unsigned)nc*16u, bar);
-			// the cells' stencil metadata rides along (consumed from shared memory: no registers held across the staging)
-			bulk_g2s(smraw + S.scl, M.cloc + c0, (unsigned)nc*16u, bar);
-			if(GRAD == GM_WLS) bulk_g2s(smraw + S.sV, M.wlsV + c0, (unsigned)nc*32u, bar);
-			// 8-byte rows: copy whole 16-byte granules starting at the even cell below c0 (the array is padded by one entry)
-			if(LIM == LM_VENKAT) bulk_g2s(smraw + S.sclen, M.clength + (c0 & ~1), (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u, bar);
-			if(MIDS) bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
-			if(METRICS) { bulk_g2s(smraw + S.sW, M.fgw + e0, (unsigned)ne*16u, bar); bulk_g2s(smraw + S.sW + M.EMAX*16, M.fgln + e0, (unsigned)ne*16u, bar); }
-		}
-		if(tid == 32 && A.prefetch_distance > 0 && !A.ordered && t + A.prefetch_distance < M.ntile) {
-			const int tp = t + A.prefetch_distance;
-			const int pc0 = M.tcell0[tp], pnc = M.tcell0[tp+1] - pc0;
-			const int pe0 = M.fsoff[tp], pne = M.fsoff[tp+1] - pe0;
-			if(!A.src_idx) bulk_prefetch_l2(A.u + 4*(size_t)pc0, (unsigned)pnc*32u);
-			bulk_prefetch_l2(M.rc + pc0, (unsigned)pnc*16u);
-			bulk_prefetch_l2(M.cloc + pc0, (unsigned)pnc*16u);
-			{ const int ph0 = M.thoff[tp] & ~3, ph1 = (M.thoff[tp+1] + 3) & ~3; if(ph1 > ph0) bulk_prefetch_l2(M.thalo + ph0, (unsigned)(ph1 - ph0)*4u); }
-			if(GRAD == GM_WLS) bulk_prefetch_l2(M.wlsV + pc0, (unsigned)pnc*32u);
-			if(MIDS) bulk_prefetch_l2(M.fgr + pe0, (unsigned)pne*16u);
-			if(METRICS) { bulk_prefetch_l2(M.fgw + pe0, (unsigned)pne*16u); bulk_prefetch_l2(M.fgln + pe0, (unsigned)pne*16u); }
-		}
-		// caller-ordered state: the own rows are gathered through the permutation (16-byte pieces)
-		if(A.src_idx) {
-			for(int k = tid; k < nc*2; k += CELL_BLOCK) {
-				const int row = k >> 1, piece = k & 1;
-				cp_async16(sp + 4*row + 2*piece, A.u + 4*(size_t)A.src_idx[c0 + row] + 2*piece);
-			}
-		}
-		// in-kernel receive of the state's ghost rows: a tile that sees ghost cells waits for the neighbours' rows (its
-		// other copies are already in flight), then gathers those rows from the halo window
-		const bool ghost_win = (tbq.w >> 16) != 0 && *sghost != nullptr;
-		if(NEED_NBRS) {
-			for(int k = tid; k < nh*3; k += CELL_BLOCK) {
-				const int h = k/3, piece = k - 3*h;
-				const size_t g = (size_t)M.thalo[h0 + h];
-				const int row = nc + h;
-				if(piece == 2) cp_async16(src + row, M.rc + g);
-				else if(!(ghost_win && g >= (size_t)M.ncell)) {
-					const size_t gs = A.halo_src ? (size_t)A.halo_src[h0 + h] : g;
-					cp_async16(sp + 4*row + 2*piece, A.u + 4*gs + 2*piece);
-				}
-			}
-			if(ghost_win) {
-				if(distd) dist_wait(distd, 1u << X_U, *sdk);
-				else ghost_wait(A.gs_u, A.gs_u.seq);
-				const double *const ghost_rows_u = *sghost;
-				for(int k = tid; k < nh*2; k += CELL_BLOCK) {
-					const int h = k >> 1, piece = k & 1;
-					const size_t g = (size_t)M.thalo[h0 + h];
-					if(g >= (size_t)M.ncell) cp_async16(sp + 4*(nc + h) + 2*piece, ghost_rows_u + 4*(g - (size_t)M.ncell) + 2*piece);
-				}
-			}
-		}
-		cp_async_commit();
-		const int2 tb = make_int2(tbq.y, tbq.z);   // boundary entries of the tile: first (tile-local) and count
-		const int grow0 = nc + nh;                 // their ghost cells are staged as rows grow0 .. grow0 + tb.y - 1
-		cp_async_wait_all();
-		mbar_wait(bar, (unsigned)(it & 1));
-		__syncthreads();
-		{
-			// one pass over the staged rows: cell and halo states become primitive in place; the ghost cell of every
-			// physical-boundary face gets its own row (state from the boundary condition applied to the conserved
-			// state of the adjacent cell, flow_spatial.cpp:659-695; centre mirrored about the face midpoint,
-			// aspatial.cpp:98-119), so that the stencil loop below needs no boundary branch at all
-			const int nrows = NEED_NBRS ? grow0 + tb.y : nc;
-			for(int k = tid; k < nrows; k += CELL_BLOCK) {
-				if(k < grow0) {
-					if(PRIM_IN) continue;
-					// 32-byte rows, one per thread: threads 4..7 of every 8 take the halves in the opposite order, which
-					// spreads a quarter warp over all 32 banks (plain row-order access is a 2-way conflict)
-					const int hb = (tid >> 2) & 1;
-					const double2 h0_ = *reinterpret_cast<const double2*>(sp + 4*k + 2*hb);
-					const double2 h1_ = *reinterpret_cast<const double2*>(sp + 4*k + 2*(1 - hb));
-					const double uc[4] = {hb ? h1_.x : h0_.x, hb ? h1_.y : h0_.y, hb ? h0_.x : h1_.x, hb ? h0_.y : h1_.y};
-					if(A.ucopy && k < nc) st4(A.ucopy + 4*(size_t)(c0 + k), uc);
-					double up[4];
-					cons2prim(A.gas, uc, up);
-					*reinterpret_cast<double2*>(sp + 4*k + 2*hb) = hb ? make_double2(up[2], up[3]) : make_double2(up[0], up[1]);
-					*reinterpret_cast<double2*>(sp + 4*k + 2*(1 - hb)) = hb ? make_double2(up[0], up[1]) : make_double2(up[2], up[3]);
-				} else {
-					const int ge = e0 + tb.x + (k - grow0);
-					const unsigned LR = M.fLR[ge];
-					const int L = (int)(LR & 0xFFFFu);
-					double pj[4];
-					if(PRIM_IN) ld4(A.ug + 4*(size_t)M.fref[ge], pj);
-					else {
-						const double2 n = M.fn[ge];
-						double ui[4], gs[4];
-						ld4(A.u + 4*(size_t)(A.src_idx ? A.src_idx[c0 + L] : c0 + L), ui);
-						ghost_state(A.gas, A.gas.bc[(LR >> 16) & 15u], ui, n.x, n.y, gs);
-						cons2prim(A.gas, gs, pj);
-					}
-					const double2 mid = M.fgr[ge];
-					const double2 rl = M.rc[c0 + L];
-					*reinterpret_cast<double2*>(sp + 4*k) = make_double2(pj[0], pj[1]);
-					*reinterpret_cast<double2*>(sp + 4*k + 2) = make_double2(pj[2], pj[3]);
-					src[k] = make_double2(2.0*mid.x - rl.x, 2.0*mid.y - rl.y);
-				}
-			}
-			__syncthreads();
-		}
-
-		for(int k = tid; k < nc; k += CELL_BLOCK) {
-			const int i = c0 + k;
-			const uint4 cl = scl[k];
-			unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
-			const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
-			const bool quad = nb[3] != NB_NONE;       // only the fourth slot can be empty (triangles)
-			const double2 rci = src[k];
-			// Threads 4..7 of every 8 work on the variables in the order (2,3,0,1): they read the second half of every
-			// 32-byte state row first. Nothing below depends on which variable is which (gradient, limiter and their
-			// inputs are per variable), so the permutation costs nothing and is undone by the store addresses; it makes
-			// the own-row access conflict-free and spreads the neighbour gathers over all 8 bank groups instead of 4.
-			const int hb = (tid >> 2) & 1;
-			const int o0 = 2*hb, o1 = 2 - 2*hb;
-			double pi[4];
-			lds4h(sp + 4*k, o0, o1, pi);
-
-			double acc[8] = {0,0,0,0,0,0,0,0};   // GG: gradient sums; WLS: right-hand side. Index d + 2*v
-			double dmin[4] = {0,0,0,0}, dmax[4] = {0,0,0,0};
-			const double ainv = GRAD == GM_GG ? frcp(M.area[i]) : 0.0;
-
-			if(NEED_NBRS) {
-				#pragma unroll
-				for(int j = 0; j < 4; j++) {
-					if(j == 3 && !quad) break;
-					const int le = (int)(cf[j] & 0x7FFFu);
-					const bool bndj = nb[j] == NB_BND;
-					const unsigned nj = bndj ? (unsigned)(grow0 + le - tb.x) : nb[j];
-					double pj[4];
-					lds4h(sp + 4*nj, o0, o1, pj);
-					const double2 rj = src[nj];
-					if(GRAD == GM_WLS) {
-						const double dx = rci.x - rj.x, dy = rci.y - rj.y;
-						const double w = frcp(dx*dx + dy*dy);
-						const double wx = w*dx, wy = w*dy;
-						#pragma unroll
-						for(int v = 0; v < 4; v++) {
-							const double du = pi[v] - pj[v];
-							acc[2*v] += wx*du;
-							acc[2*v+1] += wy*du;
-						}
-					}
-					if(GRAD == GM_GG) {
-						// face value = own state * own weight + neighbour state * its weight; the face's len*normal points from the
-						// entry's left to its right cell
-						const bool isR = (cf[j] & 0x8000u) != 0;
-						const double2 w = sW[le], ln = sW[M.EMAX + le];
-						const double wi = isR ? w.y : w.x, wj = isR ? w.x : w.y;
-						const double sx = isR ? -ln.x : ln.x, sy = isR ? -ln.y : ln.y;
-						#pragma unroll
-						for(int v = 0; v < 4; v++) {
-							const double ut = pi[v]*wi + pj[v]*wj;
-							acc[2*v] += ut*sx;
-							acc[2*v+1] += ut*sy;
-						}
-					}
-					if(LIM != LM_NONE && !(bndj && A.bnd_policy != 0)) {
-						#pragma unroll
-						for(int v = 0; v < 4; v++) {
-							// plain selects: fmax/fmin on doubles cost three times as much for their NaN rules
-							const double du = pj[v] - pi[v];
-							dmax[v] = du > dmax[v] ? du : dmax[v];
-							dmin[v] = du < dmin[v] ? du : dmin[v];
-						}
-					}
-				}
-			}
-
-			double g[8];
-			if(GRAD == GM_WLS) {
-				const double4 V = sV[k];
-				#pragma unroll
-				for(int v = 0; v < 4; v++) {
-					g[2*v]   = V.x*acc[2*v] + V.y*acc[2*v+1];
-					g[2*v+1] = V.z*acc[2*v] + V.w*acc[2*v+1];
-				}
-			}
-			else if(GRAD == GM_GG) { for(int q = 0; q < 8; q++) g[q] = acc[q]*ainv; }
-			else if(GRAD == GM_GIVEN) { ld4(A.gin + 8*(size_t)i + 2*o0, g); ld4(A.gin + 8*(size_t)i + 2*o1, g+4); }
-			else { for(int q = 0; q < 8; q++) g[q] = 0.0; }
-
-			// GradBlock rows hold (d/dx, d/dy) of variables 0..3 in order: this thread's first two variables are 0,1 or 2,3
-			if(A.gu) { st4(A.gu + 8*(size_t)i + 2*o0, g); st4(A.gu + 8*(size_t)i + 2*o1, g+4); }
-			if(!A.lg) continue;
-
-			if(LIM != LM_NONE) {
-				// The limiter is the minimum over the faces of a ratio N/D with D > 0 (and of 1). The faces are
-				// compared by cross-multiplication and only the winning ratio is divided: one reciprocal per
-				// variable instead of one per face and variable. The reference divides per face and takes fmin
-				// (limitedlinearreconstruction.cpp:150-170, 244-262); the selected face is the same up to ties.
-				// Variable-outer order keeps the live state small (one variable's running minimum at a time).
-				double eps2 = 0.0;
-				if(LIM == LM_VENKAT) {
-					const double kh = A.gas.limiter_param*sclen[k + (c0 & 1)];
-					eps2 = kh*kh*kh;
-				}
-				double ddx[4], ddy[4];
-				#pragma unroll
-				for(int j = 0; j < 4; j++) {
-					const double2 mid = sgr[(j == 3 && !quad) ? 0 : (cf[j] & 0x7FFFu)];
-					ddx[j] = mid.x - rci.x; ddy[j] = mid.y - rci.y;
-				}
-				#pragma unroll
-				for(int v = 0; v < 4; v++) {
-					double bn = 1.0, bd = 1.0;
-					#pragma unroll
-					for(int j = 0; j < 4; j++) {
-						if(j == 3 && !quad) break;
-						const double uface = pi[v] + g[2*v]*ddx[j] + g[2*v+1]*ddy[j];
-						const double dm = uface - pi[v];
-						double n_, d_;
-						if(LIM == LM_VENKAT) {
-							const double dp = dm < 0.0 ? dmin[v] : dmax[v];
-							const double dp2e = dp*dp + eps2, dpm = dp*dm;
-							n_ = dp2e + 2.0*dpm;
-							d_ = dp2e + dpm + 2.0*dm*dm;
-						} else {
-							// Barth-Jespersen: dmax/dm for dm > 0, dmin/dm for dm < 0 (ratios of like signs), else 1
-							const bool pos = dm > 0.0;
-							n_ = pos ? dmax[v] : -dmin[v];
-							d_ = pos ? dm : -dm;
-							if(dm == 0.0) { n_ = 1.0; d_ = 1.0; }
-						}
-						if(n_*bd < bn*d_) { bn = n_; bd = d_; }
-					}
-					const double lim = bn*frcp(bd);
-					g[2*v] *= lim; g[2*v+1] *= lim;
-				}
-			}
-			st4(A.lg + 8*(size_t)i + 2*o0, g); st4(A.lg + 8*(size_t)i + 2*o1, g+4);
-		}
-		// the staging buffers are free for the next tile once every thread is past the stencil loop; the same barrier
-		// orders this tile's gradient stores before the push below reads them back
-		const bool pushes = distd != nullptr && A.dist.push != 0;
-		if(have_next || pushes) __syncthreads();
-		if(pushes) {
-			const int4 rp = A.tdesc[3*(size_t)ti];      // (this tile's record again: nothing of it is held across the stencil loop)
-			if((A.dist.push & (1u << X_GU)) && A.gu) dist_push_tile(distd, X_GU, *sdk, rp.x, rp.y, A.gu);
-			if((A.dist.push & (1u << X_LG)) && A.lg) dist_push_tile(distd, X_LG, *sdk, rp.x, rp.y, A.lg);
-		}
-		if(!LOOP) break;
-		if(have_next) { const int4 *const rec = ring + 3*((it + 1) & 1); r0 = rec[0]; r1 = rec[1]; r2 = rec[2]; }
-	}
-	if(distd && A.dist.last) dist_finish_evaluation(distd, *sdk, false);
-}
 
 bool pdl_enabled()
 {
@@ -389,65 +34,299 @@ int resident_ctas(const void *kernel, int block, size_t smem)
 	return ctas;
 }
 
-/// kernel launch with the programmatic-stream-serialization attribute (the kernel may start while its predecessor in
-/// the stream drains; it calls griddepcontrol.wait before touching the predecessor's output)
-template <typename Kern, typename Args>
-static cudaError_t launch_pdl(Kern kernel, int grid, int block, size_t smem, cudaStream_t s, const Args &a)
-{
-	cudaLaunchConfig_t cfg{};
-	cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-	cfg.attrs = attr; cfg.numAttrs = 1;
-	return cudaLaunchKernelEx(&cfg, kernel, a);
-}
 
-template <int GRAD, int LIM, bool PRIM_IN, int MODE>
-static int launch_cell_grid(const CellArgs &b, int grid, cudaStream_t s)
+/** Gradient + limiter pass, one CTA per tile: the single-GPU, device-ordered form, kept as a kernel of its own.
+ * It is the same algorithm as cell_kernel<.., CM_PLAIN> (cell_kernel.cuh) in the shape it had before that template grew its
+ * multi-GPU / caller-order / looping features; on the 10M-cell benchmark this text runs in 0.490 ms and the template's
+ * plain instantiation in 0.548 ms (same instruction mix, different code generation: A/B runs in profiles/r02_cell_kernel_ab.txt),
+ * so the headline path keeps it. The tile's cell states and centres (own cells by TMA bulk
+ * copy, halo cells by cp.async gathers) and the face midpoints of its stream are staged in shared
+ * memory; conserved states are converted to primitive ONCE per staged cell (the reference converts the
+ * whole field in a separate pass, flow_spatial.cpp:697-699). Then one thread per own cell gathers its
+ * <= 4 neighbours from shared memory: no scatter, no atomics. */
+template <int GRAD, int LIM, bool PRIM_IN>
+__global__ void __launch_bounds__(CELL_BLOCK, FVG_CELL_MINB)
+cell_kernel_plain(const CellArgs A)
 {
-	const CellSmem S(b.m.TC, b.m.HMAX, b.m.EMAX, LIM != LM_NONE || GRAD == GM_GG, GRAD == GM_GG, GRAD == GM_WLS, LIM == LM_VENKAT);
-	if(S.total > 48*1024) {
-		const cudaError_t ea = cudaFuncSetAttribute(cell_kernel<GRAD,LIM,PRIM_IN,MODE>,
-			cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
-		if(ea != cudaSuccess) return cuda_fail(ea, "cell_kernel smem attribute", __FILE__, __LINE__);
+	extern __shared__ __align__(1024) unsigned char smraw[];
+	const DMesh &M = A.m;
+	constexpr bool MIDS = LIM != LM_NONE || GRAD == GM_GG;
+	constexpr bool METRICS = GRAD == GM_GG;
+	const CellSmem S(M.TC, M.HMAX, M.EMAX, MIDS, METRICS, GRAD == GM_WLS, LIM == LM_VENKAT);
+	double *const sp = reinterpret_cast<double*>(smraw + S.sp);
+	double2 *const src = reinterpret_cast<double2*>(smraw + S.src);
+	double2 *const sgr = reinterpret_cast<double2*>(smraw + S.sgr);
+	const double2 *const sW = reinterpret_cast<const double2*>(smraw + S.sW);     // two 16-byte planes: weights, len*normal
+	const uint4 *const scl = reinterpret_cast<const uint4*>(smraw + S.scl);
+	const double4 *const sV = reinterpret_cast<const double4*>(smraw + S.sV);
+	const double *const sclen = reinterpret_cast<const double*>(smraw + S.sclen);
+	uint64_t *const bar = reinterpret_cast<uint64_t*>(smraw + S.bar);
+
+	const int t = (int)blockIdx.x + A.tile0, tid = threadIdx.x;
+	const int c0 = M.tcell0[t], nc = M.tcell0[t+1] - c0;
+	const int h0 = M.thoff[t], nh = M.thoff[t+1] - h0;
+	const int e0 = M.fsoff[t], ne = M.fsoff[t+1] - e0;
+	constexpr bool NEED_NBRS = GRAD == GM_GG || GRAD == GM_WLS || LIM != LM_NONE;
+
+	if(tid == 0) mbar_init(bar, 1);
+	pdl_launch_dependents();
+	// (PDL variant) the tile descriptors above are mesh data; the state read below may be the previous kernel's output
+	// and the gradient rows written at the end are still being read by the previous face pass until it completes
+	pdl_wait();
+	__syncthreads();
+	if(tid == 0) {
+		unsigned bytes = (unsigned)nc*(32u + 16u + 16u + (GRAD == GM_WLS ? 32u : 0u)) + (LIM == LM_VENKAT ? (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u : 0u);
+		if(MIDS) bytes += (unsigned)ne*16u;
+		if(METRICS) bytes += (unsigned)ne*32u;
+		mbar_expect_tx(bar, bytes);
+		bulk_g2s(sp, A.u + 4*(size_t)c0, (unsigned)nc*32u, bar);
+		bulk_g2s(src, M.rc + c0, (unsigned)nc*16u, bar);
+		// the cells' stencil metadata rides along (consumed from shared memory: no registers held across the staging)
+		bulk_g2s(smraw + S.scl, M.cloc + c0, (unsigned)nc*16u, bar);
+		if(GRAD == GM_WLS) bulk_g2s(smraw + S.sV, M.wlsV + c0, (unsigned)nc*32u, bar);
+		// 8-byte rows: copy whole 16-byte granules starting at the even cell below c0 (the array is padded by one entry)
+		if(LIM == LM_VENKAT) bulk_g2s(smraw + S.sclen, M.clength + (c0 & ~1), (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u, bar);
+		if(MIDS) bulk_g2s(sgr, M.fgr + e0, (unsigned)ne*16u, bar);
+		if(METRICS) { bulk_g2s(smraw + S.sW, M.fgw + e0, (unsigned)ne*16u, bar); bulk_g2s(smraw + S.sW + M.EMAX*16, M.fgln + e0, (unsigned)ne*16u, bar); }
 	}
-	if(grid <= 0) {      // resident-size grid
-		static int waves = -1;
-		if(waves < 0) { const char *e = getenv("FVG_CELL_PERSIST"); waves = e ? atoi(e) : 1; if(waves < 1) waves = 1; }
-		const int nt = b.tile1 - b.tile0;
-		const int ctas = waves*resident_ctas((const void*)cell_kernel<GRAD,LIM,PRIM_IN,MODE>, CELL_BLOCK, (size_t)S.total);
-		grid = nt < ctas ? nt : ctas;
+	if(tid == 32 && A.prefetch_distance > 0 && t + A.prefetch_distance < M.ntile) {
+		const int tp = t + A.prefetch_distance;
+		const int pc0 = M.tcell0[tp], pnc = M.tcell0[tp+1] - pc0;
+		const int pe0 = M.fsoff[tp], pne = M.fsoff[tp+1] - pe0;
+		bulk_prefetch_l2(A.u + 4*(size_t)pc0, (unsigned)pnc*32u);
+		bulk_prefetch_l2(M.rc + pc0, (unsigned)pnc*16u);
+		bulk_prefetch_l2(M.cloc + pc0, (unsigned)pnc*16u);
+		{ const int ph0 = M.thoff[tp] & ~3, ph1 = (M.thoff[tp+1] + 3) & ~3; if(ph1 > ph0) bulk_prefetch_l2(M.thalo + ph0, (unsigned)(ph1 - ph0)*4u); }
+		if(GRAD == GM_WLS) bulk_prefetch_l2(M.wlsV + pc0, (unsigned)pnc*32u);
+		if(MIDS) bulk_prefetch_l2(M.fgr + pe0, (unsigned)pne*16u);
+		if(METRICS) { bulk_prefetch_l2(M.fgw + pe0, (unsigned)pne*16u); bulk_prefetch_l2(M.fgln + pe0, (unsigned)pne*16u); }
 	}
-	const cudaError_t el = launch_pdl(cell_kernel<GRAD,LIM,PRIM_IN,MODE>, grid, CELL_BLOCK, (size_t)S.total, s, b);
-	if(el != cudaSuccess) return cuda_fail(el, "cell_kernel launch", __FILE__, __LINE__);
-	return 0;
+	const int4 tbq = M.tbnd[t];
+	// in-kernel receive of the state's ghost rows: a tile that sees ghost cells waits for the neighbours' rows (its
+	// other copies are already in flight), then gathers those rows from the halo window
+	const bool ghost_win = A.gs_u.rows != nullptr && (tbq.w >> 16) != 0;
+	if(NEED_NBRS) {
+		for(int k = tid; k < nh*3; k += CELL_BLOCK) {
+			const int h = k/3, piece = k - 3*h;
+			const size_t g = (size_t)M.thalo[h0 + h];
+			const int row = nc + h;
+			if(piece == 2) cp_async16(src + row, M.rc + g);
+			else if(!(ghost_win && g >= (size_t)M.ncell)) cp_async16(sp + 4*row + 2*piece, A.u + 4*g + 2*piece);
+		}
+		if(ghost_win) {
+			ghost_wait(A.gs_u, A.gs_u.seq);
+			for(int k = tid; k < nh*2; k += CELL_BLOCK) {
+				const int h = k >> 1, piece = k & 1;
+				const size_t g = (size_t)M.thalo[h0 + h];
+				if(g >= (size_t)M.ncell) cp_async16(sp + 4*(nc + h) + 2*piece, A.gs_u.rows + 4*(g - (size_t)M.ncell) + 2*piece);
+			}
+		}
+		cp_async_commit();
+	}
+	const int2 tb = make_int2(tbq.y, tbq.z);   // boundary entries of the tile: first (tile-local) and count
+	const int grow0 = nc + nh;                 // their ghost cells are staged as rows grow0 .. grow0 + tb.y - 1
+	cp_async_wait_all();
+	mbar_wait(bar, 0);
+	__syncthreads();
+	{
+		// one pass over the staged rows: cell and halo states become primitive in place; the ghost cell of every
+		// physical-boundary face gets its own row (state from the boundary condition applied to the conserved
+		// state of the adjacent cell, flow_spatial.cpp:659-695; centre mirrored about the face midpoint,
+		// aspatial.cpp:98-119), so that the stencil loop below needs no boundary branch at all
+		const int nrows = NEED_NBRS ? grow0 + tb.y : nc;
+		for(int k = tid; k < nrows; k += CELL_BLOCK) {
+			if(k < grow0) {
+				if(PRIM_IN) continue;
+				// 32-byte rows, one per thread: threads 4..7 of every 8 take the halves in the opposite order, which
+				// spreads a quarter warp over all 32 banks (plain row-order access is a 2-way conflict)
+				const int hb = (tid >> 2) & 1;
+				const double2 h0 = *reinterpret_cast<const double2*>(sp + 4*k + 2*hb);
+				const double2 h1 = *reinterpret_cast<const double2*>(sp + 4*k + 2*(1 - hb));
+				const double uc[4] = {hb ? h1.x : h0.x, hb ? h1.y : h0.y, hb ? h0.x : h1.x, hb ? h0.y : h1.y};
+				double up[4];
+				cons2prim(A.gas, uc, up);
+				*reinterpret_cast<double2*>(sp + 4*k + 2*hb) = hb ? make_double2(up[2], up[3]) : make_double2(up[0], up[1]);
+				*reinterpret_cast<double2*>(sp + 4*k + 2*(1 - hb)) = hb ? make_double2(up[0], up[1]) : make_double2(up[2], up[3]);
+			} else {
+				const int ge = e0 + tb.x + (k - grow0);
+				const unsigned LR = M.fLR[ge];
+				const int L = (int)(LR & 0xFFFFu);
+				double pj[4];
+				if(PRIM_IN) ld4(A.ug + 4*(size_t)M.fref[ge], pj);
+				else {
+					const double2 n = M.fn[ge];
+					double ui[4], gs[4];
+					ld4(A.u + 4*(size_t)(c0 + L), ui);
+					ghost_state(A.gas, A.gas.bc[(LR >> 16) & 15u], ui, n.x, n.y, gs);
+					cons2prim(A.gas, gs, pj);
+				}
+				const double2 mid = M.fgr[ge];
+				const double2 rl = M.rc[c0 + L];
+				*reinterpret_cast<double2*>(sp + 4*k) = make_double2(pj[0], pj[1]);
+				*reinterpret_cast<double2*>(sp + 4*k + 2) = make_double2(pj[2], pj[3]);
+				src[k] = make_double2(2.0*mid.x - rl.x, 2.0*mid.y - rl.y);
+			}
+		}
+		__syncthreads();
+	}
+
+	for(int k = tid; k < nc; k += CELL_BLOCK) {
+		const int i = c0 + k;
+		const uint4 cl = scl[k];
+		unsigned nb[4] = {cl.x & 0xFFFFu, cl.x >> 16, cl.y & 0xFFFFu, cl.y >> 16};
+		const unsigned cf[4] = {cl.z & 0xFFFFu, cl.z >> 16, cl.w & 0xFFFFu, cl.w >> 16};
+		const bool quad = nb[3] != NB_NONE;       // only the fourth slot can be empty (triangles)
+		const double2 rci = src[k];
+		// Threads 4..7 of every 8 work on the variables in the order (2,3,0,1): they read the second half of every
+		// 32-byte state row first. Nothing below depends on which variable is which (gradient, limiter and their
+		// inputs are per variable), so the permutation costs nothing and is undone by the store addresses; it makes
+		// the own-row access conflict-free and spreads the neighbour gathers over all 8 bank groups instead of 4.
+		const int hb = (tid >> 2) & 1;
+		const int o0 = 2*hb, o1 = 2 - 2*hb;
+		double pi[4];
+		lds4h(sp + 4*k, o0, o1, pi);
+
+		double acc[8] = {0,0,0,0,0,0,0,0};   // GG: gradient sums; WLS: right-hand side. Index d + 2*v
+		double dmin[4] = {0,0,0,0}, dmax[4] = {0,0,0,0};
+		const double ainv = GRAD == GM_GG ? frcp(M.area[i]) : 0.0;
+
+		if(NEED_NBRS) {
+			#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				if(j == 3 && !quad) break;
+				const int le = (int)(cf[j] & 0x7FFFu);
+				const bool bndj = nb[j] == NB_BND;
+				const unsigned nj = bndj ? (unsigned)(grow0 + le - tb.x) : nb[j];
+				double pj[4];
+				lds4h(sp + 4*nj, o0, o1, pj);
+				const double2 rj = src[nj];
+				if(GRAD == GM_WLS) {
+					const double dx = rci.x - rj.x, dy = rci.y - rj.y;
+					const double w = frcp(dx*dx + dy*dy);
+					const double wx = w*dx, wy = w*dy;
+					#pragma unroll
+					for(int v = 0; v < 4; v++) {
+						const double du = pi[v] - pj[v];
+						acc[2*v] += wx*du;
+						acc[2*v+1] += wy*du;
+					}
+				}
+				if(GRAD == GM_GG) {
+					// face value = own state * own weight + neighbour state * its weight; the face's len*normal points from the
+					// entry's left to its right cell
+					const bool isR = (cf[j] & 0x8000u) != 0;
+					const double2 w = sW[le], ln = sW[M.EMAX + le];
+					const double wi = isR ? w.y : w.x, wj = isR ? w.x : w.y;
+					const double sx = isR ? -ln.x : ln.x, sy = isR ? -ln.y : ln.y;
+					#pragma unroll
+					for(int v = 0; v < 4; v++) {
+						const double ut = pi[v]*wi + pj[v]*wj;
+						acc[2*v] += ut*sx;
+						acc[2*v+1] += ut*sy;
+					}
+				}
+				if(LIM != LM_NONE && !(bndj && A.bnd_policy != 0)) {
+					#pragma unroll
+					for(int v = 0; v < 4; v++) {
+						// plain selects: fmax/fmin on doubles cost three times as much for their NaN rules
+						const double du = pj[v] - pi[v];
+						dmax[v] = du > dmax[v] ? du : dmax[v];
+						dmin[v] = du < dmin[v] ? du : dmin[v];
+					}
+				}
+			}
+		}
+
+		double g[8];
+		if(GRAD == GM_WLS) {
+			const double4 V = sV[k];
+			#pragma unroll
+			for(int v = 0; v < 4; v++) {
+				g[2*v]   = V.x*acc[2*v] + V.y*acc[2*v+1];
+				g[2*v+1] = V.z*acc[2*v] + V.w*acc[2*v+1];
+			}
+		}
+		else if(GRAD == GM_GG) { for(int q = 0; q < 8; q++) g[q] = acc[q]*ainv; }
+		else if(GRAD == GM_GIVEN) { ld4(A.gin + 8*(size_t)i + 2*o0, g); ld4(A.gin + 8*(size_t)i + 2*o1, g+4); }
+		else { for(int q = 0; q < 8; q++) g[q] = 0.0; }
+
+		// GradBlock rows hold (d/dx, d/dy) of variables 0..3 in order: this thread's first two variables are 0,1 or 2,3
+		if(A.gu) { st4(A.gu + 8*(size_t)i + 2*o0, g); st4(A.gu + 8*(size_t)i + 2*o1, g+4); }
+		if(!A.lg) continue;
+
+		if(LIM != LM_NONE) {
+			// The limiter is the minimum over the faces of a ratio N/D with D > 0 (and of 1). The faces are
+			// compared by cross-multiplication and only the winning ratio is divided: one reciprocal per
+			// variable instead of one per face and variable. The reference divides per face and takes fmin
+			// (limitedlinearreconstruction.cpp:150-170, 244-262); the selected face is the same up to ties.
+			// Variable-outer order keeps the live state small (one variable's running minimum at a time).
+			double eps2 = 0.0;
+			if(LIM == LM_VENKAT) {
+				const double kh = A.gas.limiter_param*sclen[k + (c0 & 1)];
+				eps2 = kh*kh*kh;
+			}
+			double ddx[4], ddy[4];
+			#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				const double2 mid = sgr[(j == 3 && !quad) ? 0 : (cf[j] & 0x7FFFu)];
+				ddx[j] = mid.x - rci.x; ddy[j] = mid.y - rci.y;
+			}
+			#pragma unroll
+			for(int v = 0; v < 4; v++) {
+				double bn = 1.0, bd = 1.0;
+				#pragma unroll
+				for(int j = 0; j < 4; j++) {
+					if(j == 3 && !quad) break;
+					const double uface = pi[v] + g[2*v]*ddx[j] + g[2*v+1]*ddy[j];
+					const double dm = uface - pi[v];
+					double n_, d_;
+					if(LIM == LM_VENKAT) {
+						const double dp = dm < 0.0 ? dmin[v] : dmax[v];
+						const double dp2e = dp*dp + eps2, dpm = dp*dm;
+						n_ = dp2e + 2.0*dpm;
+						d_ = dp2e + dpm + 2.0*dm*dm;
+					} else {
+						// Barth-Jespersen: dmax/dm for dm > 0, dmin/dm for dm < 0 (ratios of like signs), else 1
+						const bool pos = dm > 0.0;
+						n_ = pos ? dmax[v] : -dmin[v];
+						d_ = pos ? dm : -dm;
+						if(dm == 0.0) { n_ = 1.0; d_ = 1.0; }
+					}
+					if(n_*bd < bn*d_) { bn = n_; bd = d_; }
+				}
+				const double lim = bn*frcp(bd);
+				g[2*v] *= lim; g[2*v+1] *= lim;
+			}
+		}
+		st4(A.lg + 8*(size_t)i + 2*o0, g); st4(A.lg + 8*(size_t)i + 2*o1, g+4);
+	}
 }
 
 template <int GRAD, int LIM, bool PRIM_IN>
-static int launch_cell(const CellArgs &a, cudaStream_t s)
+static int launch_cell_plain(const CellArgs &b, int nt, cudaStream_t s)
+{
+	const CellSmem S(b.m.TC, b.m.HMAX, b.m.EMAX, LIM != LM_NONE || GRAD == GM_GG, GRAD == GM_GG, GRAD == GM_WLS, LIM == LM_VENKAT);
+	if(S.total > 48*1024) {
+		const cudaError_t ea = cudaFuncSetAttribute(cell_kernel_plain<GRAD,LIM,PRIM_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
+		if(ea != cudaSuccess) return cuda_fail(ea, "cell_kernel smem attribute", __FILE__, __LINE__);
+	}
+	cell_kernel_plain<GRAD,LIM,PRIM_IN><<<nt, CELL_BLOCK, S.total, s>>>(b);
+	const cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess) return cuda_fail(e, "cell_kernel launch", __FILE__, __LINE__);
+	return 0;
+}
+
+int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaStream_t s)
 {
 	CellArgs b = a;
 	if(b.tile1 < 0) b.tile1 = b.m.ntile;
 	b.tdesc = (b.ordered && b.m.tdesc_ord) ? b.m.tdesc_ord : b.m.tdesc;
 	const int nt = b.tile1 - b.tile0;
 	if(nt <= 0) return 0;
-	// One CTA per tile by default: measured faster than a resident-size grid walking the tiles (0.49 vs 0.56 ms on the
-	// 10M-cell benchmark): the hardware's CTA scheduler balances uneven tiles over the SMs, and a kernel that carries
-	// nothing from tile to tile keeps its stencil loop within the 80 registers of three CTAs per SM.
-	// FVG_CELL_PERSIST=<waves> selects the looping form on a grid of waves x resident CTAs (residual path only).
-	static int persist = -1;
-	if(persist < 0) { const char *e = getenv("FVG_CELL_PERSIST"); persist = e ? atoi(e) : 0; }
-	if(!PRIM_IN) {      // (the plug-in entry points with primitive input are single-GPU, one tile per CTA)
-		if(persist > 0) return launch_cell_grid<GRAD,LIM,PRIM_IN,PRIM_IN ? CM_PLAIN : CM_LOOP>(b, 0, s);
-		if(b.dist.d) return launch_cell_grid<GRAD,LIM,PRIM_IN,PRIM_IN ? CM_PLAIN : CM_DIST>(b, nt, s);
-	}
-	return launch_cell_grid<GRAD,LIM,PRIM_IN,CM_PLAIN>(b, nt, s);
-}
-
-int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaStream_t s)
-{
-#define C(G,L,P) if(grad == G && lim == L && prim_in == P) return launch_cell<G,L,P>(a, s);
+	int mode = cell_mode_of(b, prim_in);
+	if(mode == CM_PLAIN && b.ordered) mode = CM_DIST;       // (a tile sequence other than the natural one: the general kernel)
+	if(mode != CM_PLAIN) return launch_cell_kernel_modes(grad, lim, mode, b, s);
+#define C(G,L,P) if(grad == G && lim == L && prim_in == P) return launch_cell_plain<G,L,P>(b, nt, s);
 	C(GM_ZERO,LM_NONE,false) C(GM_ZERO,LM_BJ,false) C(GM_ZERO,LM_VENKAT,false)
 	C(GM_GG,LM_NONE,false) C(GM_GG,LM_BJ,false) C(GM_GG,LM_VENKAT,false)
 	C(GM_WLS,LM_NONE,false) C(GM_WLS,LM_BJ,false) C(GM_WLS,LM_VENKAT,false)

@@ -69,19 +69,6 @@ static int launch_rk_stage(const double *u0, const double *us, const double *res
 	return 0;
 }
 
-/// device scratch of one solve
-struct Scratch {
-	std::vector<void*> p;
-	~Scratch() { for(void *q : p) cudaFree(q); }
-	int get(double **out, size_t count) {
-		void *q = nullptr;
-		FVG_CUDA(cudaMalloc(&q, (count ? count : 1)*sizeof(double)));
-		p.push_back(q);
-		*out = static_cast<double*>(q);
-		return 0;
-	}
-};
-
 } // namespace fvg
 
 using namespace fvg;
@@ -112,14 +99,14 @@ extern "C" int fvg_tvdrk_solve(fvg_flow *f, double *d_u, int order, double cfl, 
 	const DMesh &D = f->mesh->d;
 	const int n = D.ncell;
 	const int nblk = 1024;
-	Scratch mem;
-	double *us = nullptr, *res = nullptr, *dtm = nullptr, *part = nullptr, *dtmin = nullptr, *area_own = nullptr;
-	if((rc = mem.get(&us, 4*(size_t)n)) != 0 || (rc = mem.get(&res, 4*(size_t)n)) != 0 || (rc = mem.get(&dtm, n)) != 0
-	   || (rc = mem.get(&part, nblk)) != 0 || (rc = mem.get(&dtmin, 1)) != 0) return rc;
+	// scratch arrays are owned by the flow (allocated on first use, freed with it), as for the other drivers:
+	// stage state [4n], residual [4n], local steps [n], caller-ordered areas [n], reduction blocks, the global step
+	if(!f->d_rk && (rc = flow_dev_alloc(f, &f->d_rk, 10*(size_t)n + (size_t)nblk + 1)) != 0) return rc;
+	double *const us = f->d_rk, *const res = us + 4*(size_t)n, *const dtm = res + 4*(size_t)n, *const area_own = dtm + n,
+	       *const part = area_own + n, *const dtmin = part + nblk;
 	// cell areas in the caller's cell order
 	const double *area = D.area;
 	if(!f->mesh->identity_perm) {
-		if((rc = mem.get(&area_own, n)) != 0) return rc;
 		if((rc = launch_permute_rows(D.area, area_own, D.new2old, n, 1, false, false, s)) != 0) return rc;
 		f->launches++;
 		area = area_own;
@@ -138,9 +125,11 @@ extern "C" int fvg_tvdrk_solve(fvg_flow *f, double *d_u, int order, double cfl, 
 			if((rc = launch_rk_stage(d_u, us, res, area, dtmin, coef[3*istage], coef[3*istage+1], coef[3*istage+2]*cfl, n, 4, us, s)) != 0) return rc;
 			f->launches++;
 		}
-		double h_dtmin = 0.0;
-		FVG_CUDA(cudaMemcpyAsync(&h_dtmin, dtmin, sizeof(double), cudaMemcpyDeviceToHost, s));
+		// the host needs the step for the time and the stopping rule, as in the reference (aodesolver.cpp:719-726): one read
+		// per step through the flow's pinned scalar
+		FVG_CUDA(cudaMemcpyAsync(f->h_norm, dtmin, sizeof(double), cudaMemcpyDeviceToHost, s));
 		FVG_CUDA(cudaStreamSynchronize(s));
+		const double h_dtmin = *f->h_norm;
 		if(!std::isfinite(h_dtmin)) { status = FVG_ERR_NUMERICAL; break; }      // the state of the last good step is kept
 		FVG_CUDA(cudaMemcpyAsync(d_u, us, 4*(size_t)n*sizeof(double), cudaMemcpyDeviceToDevice, s));
 		step++;

@@ -31,6 +31,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -322,6 +323,18 @@ public:
 		: FlowBC<scalar,j_real>(ISOTHERMAL_WALL_BC, bc_tag, gp, wall_tangential_velocity, wall_temperature) {}
 };
 
+/// Periodic marker. NOT in the reference (its factory throws for PERIODIC_BC, abc.cpp:493-494, and its face loop would
+/// count a periodic edge twice): here the faces of the marker are paired by UMesh::compute_periodic_map
+/// and the device mesh makes interior faces of them, so no ghost state is ever asked of this object.
+template <typename scalar, typename j_real = freal>
+class PeriodicBC : public FlowBC<scalar,j_real> {
+public:
+	PeriodicBC(const int bc_tag, const IdealGasPhysics<scalar>& gp) : FlowBC<scalar,j_real>(PERIODIC_BC, bc_tag, gp) {}
+	void computeGhostState(const scalar *const, const scalar *const, scalar *const) const {
+		throw UnsupportedOptionError("PeriodicBC has no ghost state: its faces are interior faces of the device mesh");
+	}
+};
+
 /// Reference: create_const_flowBCs (spatial/abc.cpp:461-500); unknown types throw std::runtime_error
 template <typename scalar>
 std::map<int,const FlowBC<scalar>*> create_const_flowBCs(const std::vector<FlowBCConfig>& conf,
@@ -339,6 +352,7 @@ std::map<int,const FlowBC<scalar>*> create_const_flowBCs(const std::vector<FlowB
 		case EXTRAPOLATION_BC: bc = new Extrapolation<scalar>(it->bc_tag, physics); break;
 		case ADIABATIC_WALL_BC: bc = new Adiabaticwall2D<scalar>(it->bc_tag, physics, it->bc_vals.at(0)); break;
 		case ISOTHERMAL_WALL_BC: bc = new Isothermalwall2D<scalar>(it->bc_tag, physics, it->bc_vals.at(0), it->bc_vals.at(1)); break;
+		case PERIODIC_BC: bc = new PeriodicBC<scalar>(it->bc_tag, physics); break;      // (the reference throws here)
 		default: throw std::runtime_error("BC type not implemented yet!");
 		}
 		bcmap[it->bc_tag] = bc;
@@ -402,20 +416,30 @@ const InviscidFlux<scalar>* create_const_inviscidflux(const std::string& type, c
 
 // ---------------------------------------------------------------------------------------- engine handle
 
+/// View of a host UMesh in the layout of the C ABI (non-owning)
+inline fvg_host_mesh host_mesh_view(const UMesh<freal,NDIM> *const m) {
+	fvg_host_mesh v;
+	v.npoin = m->gnpoin(); v.nelem = m->gnelem(); v.nbface = m->gnbface(); v.naface = m->gnaface();
+	v.ninface = m->gninface(); v.nconnface = m->gnConnFace(); v.maxnnode = m->gmaxnnode(); v.nbtag = m->gnbtag();
+	v.coords = m->coordsData(); v.inpoel = m->inpoelData(); v.nnode = m->nnodeData(); v.esuel = m->esuelData();
+	v.elemface = m->elemfaceData(); v.intfac = m->intfacData(); v.btags = m->btagsData();
+	v.facemetric = m->facemetricData(); v.area = m->areaData();
+	v.bpartner = m->periodicmapData();       // periodic pairs (UMesh::compute_periodic_map), or null
+	return v;
+}
+
 /// Device mesh + flow context shared by the plug-in classes and FlowFV. Owns its ABI handles.
+/// With a cell -> rank map it is one rank's subdomain of a mesh distributed over the GPUs of a box (the job of the
+/// reference's ReplicatedGlobalMeshPartitioner::restrictMeshToPartitions, mesh/meshpartitioning.cpp:24-159).
 class EngineContext {
 public:
 	EngineContext(const UMesh<freal,NDIM> *const m, const fvg_physics& phys, const fvg_numerics& num,
-	              const std::vector<fvg_bc>& bcs, const int reorder = FVG_REORDER_HILBERT, const int tile_cells = 256)
+	              const std::vector<fvg_bc>& bcs, const int reorder = FVG_REORDER_HILBERT, const int tile_cells = 256,
+	              const int *const cell_rank = nullptr, const int rank = 0, const int nranks = 1, const int device = -1)
 	{
-		fvg_host_mesh v;
-		v.npoin = m->gnpoin(); v.nelem = m->gnelem(); v.nbface = m->gnbface(); v.naface = m->gnaface();
-		v.ninface = m->gninface(); v.nconnface = m->gnConnFace(); v.maxnnode = m->gmaxnnode(); v.nbtag = m->gnbtag();
-		v.coords = m->coordsData(); v.inpoel = m->inpoelData(); v.nnode = m->nnodeData(); v.esuel = m->esuelData();
-		v.elemface = m->elemfaceData(); v.intfac = m->intfacData(); v.btags = m->btagsData();
-		v.facemetric = m->facemetricData(); v.area = m->areaData();
-		fvg_mesh_opts o; o.reorder = reorder; o.tile_cells = tile_cells; o.device = -1;
-		fvg_throw(fvg_mesh_create(&v, &o, &mesh), "fvg_mesh_create");
+		const fvg_host_mesh v = host_mesh_view(m);
+		fvg_mesh_opts o; o.reorder = reorder; o.tile_cells = tile_cells; o.device = device;
+		fvg_throw(cell_rank ? fvg_mesh_create_part(&v, &o, cell_rank, rank, nranks, &mesh) : fvg_mesh_create(&v, &o, &mesh), "fvg_mesh_create");
 		const int rc = fvg_flow_create(mesh, &phys, &num, bcs.data(), (int)bcs.size(), &flow);
 		if(rc) { fvg_mesh_destroy(mesh); mesh = nullptr; fvg_throw(rc, "fvg_flow_create"); }
 	}
@@ -614,7 +638,8 @@ class FlowFV_base : public Spatial<scalar,NVARS> {
 public:
 	/// tile_cells / reorder are engine knobs with no reference counterpart; the defaults are the tuned ones
 	FlowFV_base(const UMesh<scalar,NDIM> *const mesh, const FlowPhysicsConfig& pconf, const FlowNumericsConfig& nconf,
-	            const int bnd_policy = FVG_BND_GHOST, const int reorder = FVG_REORDER_HILBERT, const int tile_cells = 256)
+	            const int bnd_policy = FVG_BND_GHOST, const int reorder = FVG_REORDER_HILBERT, const int tile_cells = 256,
+	            const int *const cell_rank = nullptr, const int rank = 0, const int nranks = 1, const int device = -1)
 		: Spatial<scalar,NVARS>(mesh), pconfig(pconf), nconfig(nconf),
 		  physics(pconf.gamma, pconf.Minf, pconf.Tinf, pconf.Reinf, pconf.Pr),
 		  uinf(physics.compute_freestream_state(pconf.aoa)),
@@ -628,7 +653,8 @@ public:
 		n.limiter_param = nconf.limiter_param; n.order2 = nconf.order2; n.bnd_policy = bnd_policy;
 		std::vector<fvg_bc> b;
 		for(auto it = bcs.begin(); it != bcs.end(); ++it) b.push_back(it->second->abi());
-		ctx.reset(new EngineContext(mesh, physics.abi(pconf.aoa, pconf.viscous_sim, pconf.const_visc), n, b, reorder, tile_cells));
+		ctx.reset(new EngineContext(mesh, physics.abi(pconf.aoa, pconf.viscous_sim, pconf.const_visc), n, b, reorder, tile_cells,
+		                            cell_rank, rank, nranks, device));
 	}
 	virtual ~FlowFV_base() {
 		delete inviflux;
@@ -693,8 +719,9 @@ template <typename scalar, bool secondOrderRequested, bool constVisc>
 class FlowFV : public FlowFV_base<scalar> {
 public:
 	FlowFV(const UMesh<scalar,NDIM> *const mesh, const FlowPhysicsConfig& pconf, const FlowNumericsConfig& nconf,
-	       const int bnd_policy = FVG_BND_GHOST, const int reorder = FVG_REORDER_HILBERT, const int tile_cells = 256)
-		: FlowFV_base<scalar>(mesh, fix_p(pconf), fix_n(nconf), bnd_policy, reorder, tile_cells) {}
+	       const int bnd_policy = FVG_BND_GHOST, const int reorder = FVG_REORDER_HILBERT, const int tile_cells = 256,
+	       const int *const cell_rank = nullptr, const int rank = 0, const int nranks = 1, const int device = -1)
+		: FlowFV_base<scalar>(mesh, fix_p(pconf), fix_n(nconf), bnd_policy, reorder, tile_cells, cell_rank, rank, nranks, device) {}
 
 	/// spatial/flow_spatial.cpp:637-816. Host Vecs: upload u (and the residual it adds into), kernels,
 	/// download residual and time steps. Device Vecs: kernels only, asynchronous on the default stream.
@@ -731,6 +758,80 @@ const FlowFV_base<scalar>* create_const_flowSpatialDiscretization(const UMesh<sc
 	if(pconf.const_visc) return new FlowFV<scalar,false,true>(m, pconf, nconf);
 	return new FlowFV<scalar,false,false>(m, pconf, nconf);
 }
+
+// ---------------------------------------------------------------------------------------- multi-GPU
+
+/// All-gather used once at set-up: every rank contributes `bytes` bytes at `mine`, `all` receives nranks*bytes in rank
+/// order. The transport is the caller's (MPI_Allgather in an MPI program - exactly what the reference's drivers have at
+/// hand - a socket, shared files ...); nothing else of the data path goes through it.
+typedef std::function<void(const void *mine, void *all, size_t bytes)> AllGather;
+
+/// FlowFV on one rank's subdomain of a mesh distributed over the GPUs of one NVLink/NVSwitch box: the reference's
+/// FlowFV over a ReplicatedGlobalMeshPartitioner subdomain (mesh/meshpartitioning.cpp:24-159) with its L2TraceVector
+/// exchange (linalg/tracevector.cpp:214-325) and ghost updates (spatial/flow_spatial.cpp:711-788), here the fused
+/// evaluation fvg_dist_*. Every rank passes the same GLOBAL mesh and cell -> rank map (fvg_partition_sfc / _rcb, a Scotch
+/// map read by fvg_partition_read_scotch_map, or the reference's trivial partition). Device Vecs in device order:
+/// [ncell() own rows (+ ghost rows, ignored)]; global_cell(i) says which cell of the global mesh row i is.
+template <typename scalar, bool secondOrderRequested, bool constVisc>
+class DistributedFlowFV : public FlowFV<scalar,secondOrderRequested,constVisc> {
+public:
+	DistributedFlowFV(const UMesh<scalar,NDIM> *const globalmesh, const FlowPhysicsConfig& pconf, const FlowNumericsConfig& nconf,
+	                  const std::vector<int>& cell_rank, const int rank, const int nranks, const int device, const AllGather& allgather,
+	                  const int bnd_policy = FVG_BND_GHOST, const int tile_cells = 256)
+		: FlowFV<scalar,secondOrderRequested,constVisc>(globalmesh, pconf, nconf, bnd_policy, FVG_REORDER_HILBERT, tile_cells,
+		                                                cell_rank.data(), rank, nranks, device), nr(nranks)
+	{
+		if((fint)cell_rank.size() != globalmesh->gnelem()) throw std::runtime_error("DistributedFlowFV: cell_rank needs one entry per cell of the global mesh");
+		fvg_throw(fvg_dist_create(this->ctx->flow, &dist), "fvg_dist_create");
+		fvg_mesh_info info;
+		fvg_throw(fvg_mesh_get_info(this->ctx->mesh, &info), "fvg_mesh_get_info");
+		nown = info.ncell; nghost = info.nghost;
+		// set-up exchange: 64-byte window handle + this rank's receive counts
+		std::vector<int> sc((size_t)nranks), rc((size_t)nranks);
+		fvg_throw(fvg_mesh_halo_lists(this->ctx->mesh, sc.data(), rc.data(), nullptr), "fvg_mesh_halo_lists");
+		const size_t rec = 64 + sizeof(int)*(size_t)nranks;
+		std::vector<unsigned char> mine(rec), all(rec*(size_t)nranks);
+		fvg_throw(fvg_dist_ipc_handle(dist, mine.data()), "fvg_dist_ipc_handle");
+		std::memcpy(mine.data() + 64, rc.data(), sizeof(int)*(size_t)nranks);
+		allgather(mine.data(), all.data(), rec);
+		std::vector<unsigned char> handles(64*(size_t)nranks);
+		std::vector<int> counts((size_t)nranks*(size_t)nranks);
+		for(int r = 0; r < nranks; r++) {
+			std::memcpy(handles.data() + 64*(size_t)r, all.data() + rec*(size_t)r, 64);
+			std::memcpy(counts.data() + (size_t)r*(size_t)nranks, all.data() + rec*(size_t)r + 64, sizeof(int)*(size_t)nranks);
+		}
+		fvg_throw(fvg_dist_connect(dist, handles.data(), counts.data()), "fvg_dist_connect");
+		perm.resize((size_t)nown + (size_t)nghost);
+		fvg_throw(fvg_mesh_permutation(this->ctx->mesh, perm.data()), "fvg_mesh_permutation");
+	}
+	~DistributedFlowFV() { if(dist) fvg_dist_destroy(dist); }
+
+	fint ncell() const { return nown; }
+	fint nghostcell() const { return nghost; }
+	fint global_cell(const fint i) const { return perm[(size_t)i]; }
+	/// This rank's rows of a global cell array (host), `width` doubles per cell
+	std::vector<scalar> restrict_to_rank(const scalar *const global, const int width) const {
+		std::vector<scalar> loc((size_t)nown*(size_t)width);
+		for(fint i = 0; i < nown; i++) for(int k = 0; k < width; k++) loc[(size_t)i*width+k] = global[(size_t)perm[(size_t)i]*width+k];
+		return loc;
+	}
+
+	/// spatial/flow_spatial.cpp:637-816 on the subdomain; device Vecs ([ncell()] own rows at least), adds into `residual`
+	StatusCode compute_residual(const Vec u, Vec residual, const bool gettimesteps, Vec timesteps) const {
+		if(!u || !residual || (gettimesteps && !timesteps)) return FVG_ERR_INVALID;
+		if(u->place != VEC_DEVICE || residual->place != VEC_DEVICE || (gettimesteps && timesteps->place != VEC_DEVICE)) return FVG_ERR_INVALID;
+		return fvg_dist_residual(dist, u->dev, residual->dev, 1, gettimesteps, gettimesteps ? timesteps->dev : nullptr, nullptr);
+	}
+	/// FVG_ERR_COMM (as Engine_error) once a neighbour rank has stopped delivering rows
+	void check_neighbours() const { unsigned long long t = 0; fvg_throw(fvg_dist_status(dist, &t), "DistributedFlowFV"); }
+	fvg_dist* engine_dist() const { return dist; }
+	int nranks() const { return nr; }
+private:
+	fvg_dist *dist = nullptr;
+	fint nown = 0, nghost = 0;
+	int nr = 1;
+	std::vector<int> perm;
+};
 
 // ---------------------------------------------------------------------------------------- pseudo-time
 
@@ -782,7 +883,14 @@ public:
 		std::vector<double> hist((size_t)config.maxiter, 0.0);
 		int code;
 		const FlowFV_base<freal> *const eng = dynamic_cast<const FlowFV_base<freal>*>(this->space);
-		if(eng) {
+		fvg_dist *const dist = distributed_engine(this->space);
+		if(dist) {
+			// partitioned mesh: the loop of aodesolver.cpp:177-251 with its ghost update (:212) and MPI_Allreduce (:227)
+			// folded into the kernels and the peer windows (fvg_dist_forward_euler_solve); device Vec of own rows
+			if(u->place != VEC_DEVICE) throw UnsupportedOptionError("SteadyForwardEulerSolver on a distributed FlowFV takes a device Vec");
+			code = fvg_dist_forward_euler_solve(dist, u->dev, config.cflinit, config.tol, config.maxiter, 1, &steps, hist.data());
+		}
+		else if(eng) {
 			// note H4 of SURVEY.md: the reference applies cflinit on every step
 			if(u->place == VEC_DEVICE)
 				code = fvg_forward_euler_solve(eng->engine_flow(), u->dev, config.cflinit, config.tol, config.maxiter, 1, &steps, hist.data());
@@ -809,6 +917,14 @@ public:
 		return 0;
 	}
 private:
+	/// the exchange engine behind a DistributedFlowFV of any template flavour (null otherwise)
+	static fvg_dist* distributed_engine(const Spatial<freal,nvars> *const sp) {
+		if(auto p = dynamic_cast<const DistributedFlowFV<freal,true,true>*>(sp)) return p->engine_dist();
+		if(auto p = dynamic_cast<const DistributedFlowFV<freal,true,false>*>(sp)) return p->engine_dist();
+		if(auto p = dynamic_cast<const DistributedFlowFV<freal,false,true>*>(sp)) return p->engine_dist();
+		if(auto p = dynamic_cast<const DistributedFlowFV<freal,false,false>*>(sp)) return p->engine_dist();
+		return nullptr;
+	}
 	/// aodesolver.cpp:177-251 for a Spatial that is not the engine's: orchestration only, host Vecs
 	int generic_loop(Vec u, int& step, std::vector<double>& hist) {
 		const SteadySolverConfig& config = this->config;

@@ -62,6 +62,7 @@ public:
 		v.coords = coords.data(); v.inpoel = inpoel.data(); v.nnode = nnode.data(); v.esuel = esuel.data();
 		v.elemface = elemface.data(); v.intfac = intfac.data(); v.btags = btags.data();
 		v.facemetric = facemetric.data(); v.area = area.data();
+		v.bpartner = nullptr;      // the reference cannot run periodic boundaries: none to forward
 		const fvg_mesh_opts mo = { reorder, tile_cells, -1 };
 		if(fvg_mesh_create(&v, &mo, &dmesh)) throw std::runtime_error(fvg_last_error());
 

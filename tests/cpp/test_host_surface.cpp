@@ -69,9 +69,19 @@ static void test_wall_bcs(const std::string& dir)
 		}
 		for(auto& kv : bcs) delete kv.second;
 	}
+	// abc.cpp:493-494: a type without a FlowBC class throws std::runtime_error. PERIODIC_BC is such a type in the reference;
+	// here it has a class (its faces become interior faces of the device mesh) whose ghost state must never be asked for
 	bool threw = false;
-	try { create_const_flowBCs<freal>({{7, PERIODIC_BC, {}, {}}}, phy, uinf); } catch(std::runtime_error&) { threw = true; }
+	try { create_const_flowBCs<freal>({{7, (BCType)99, {}, {}}}, phy, uinf); } catch(std::runtime_error&) { threw = true; }
 	CHECK(threw, "a BC type without a class must throw std::runtime_error");
+	{
+		auto pb = create_const_flowBCs<freal>({{7, PERIODIC_BC, {}, {}}}, phy, uinf);
+		bool refused = false;
+		double g[4]; const double nn[2] = {1.0, 0.0};
+		try { pb.at(7)->computeGhostState(u, nn, g); } catch(UnsupportedOptionError&) { refused = true; }
+		CHECK(refused, "the periodic marker has no ghost state");
+		for(auto& kv : pb) delete kv.second;
+	}
 }
 
 struct GeomProbe : public Spatial<freal,NVARS> {
