@@ -298,6 +298,7 @@ def main():
                     help="cells of the CPU arms' mesh; 0 (default) = the workload's own mesh (same config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--time-passes", action="store_true", help="N > 1: time the two passes on every rank (turns graph replay off)")
     ap.add_argument("--partition", default="sfc", choices=["sfc", "rcb"],
                     help="N > 1: Hilbert-curve chunks (default, the measured configuration) or recursive coordinate bisection")
     args = ap.parse_args()
@@ -380,6 +381,13 @@ def main():
 
         def evaluate():
             fl.compute_residual(du, res, True, dtm, accumulate=False, stream=stream)
+        if os.environ.get("FVG_SELF_DIST") == "1":
+            # diagnostic: the multi-GPU kernels (exchange engine with no neighbour) on one GPU, to price their extra code
+            eng = lib.DistEngine(fl)
+            eng.connect([eng.handle()], np.zeros((1, 1), dtype=np.int32))
+
+            def evaluate():
+                eng.residual(du, res, True, dtm, accumulate=False, stream=stream)
     else:
         from fvens_b200.dist import DistFlow
         part = (lib.partition_rcb if args.partition == "rcb" else lib.partition_sfc)(um, world)
@@ -413,6 +421,9 @@ def main():
     barrier()
     if world == 1:
         fl.timing(True)
+    elif df.engine is not None and args.time_passes:
+        # per-pass times on every rank (events between the kernels: no graph replay, no launch overlap while this is on)
+        fl.timing(True)
     launches0 = fl.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -425,7 +436,15 @@ def main():
     windows = [(w0, time.perf_counter())]
     ms_total = e0.elapsed_time(e1)
     launches = fl.launch_count() - launches0 + halo_launches*args.steps
-    ms_cell, ms_face, ntimed = fl.timing(False) if world == 1 else (0.0, 0.0, 0)
+    ms_cell, ms_face, ntimed = fl.timing(False) if (world == 1 or (df.engine is not None and args.time_passes)) else (0.0, 0.0, 0)
+    if world > 1 and ntimed:
+        tk = torch.tensor([ms_cell/ntimed, ms_face/ntimed], dtype=torch.float64, device=dev)
+        tmin = tk.clone(); dist.all_reduce(tk, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        pass_times = {"gradient_limiter_pass_max": tk[0].item(), "face_pass_max": tk[1].item(),
+                      "gradient_limiter_pass_min": tmin[0].item(), "face_pass_min": tmin[1].item(), "timed_evals": ntimed,
+                      "note": "per-rank CUDA events between the two kernels (direct launches, no graph replay): max / min over the ranks"}
+    else:
+        pass_times = None
     # a short timed region can end between two nvidia-smi rows (100 ms apart): keep the same kernels running,
     # untimed, until at least three rows have been taken under this load
     probe = torch.tensor([0], dtype=torch.int32, device=dev)
@@ -578,6 +597,8 @@ def main():
                             "cell_pass": {"achieved": bA/t_cell/1e9, "frac": bA/t_cell/1e9/peak,
                                           "algorithmic_bytes_per_launch": bA}}
     else:
+        if pass_times:
+            line["kernels_ms"] = pass_times
         ach = (bA + bB)/world/(ms_step*1e-3)/1e9
         line["roofline"] = {"bound": "hbm", "kernel": "whole evaluation per GPU (cell pass + face pass + halos)",
                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach/peak, "frac_of_nominal_8000_GBs": ach/8000.0, "traffic": None,

@@ -70,7 +70,9 @@ static void resolve_tiles(const fvg_flow *f, int &tile0, int &tile1, bool &order
 {
 	ordered = false;
 	const DMesh &D = f->mesh->d;
-	if(f->roles.active && D.tile_order && tile1 < 0) { ordered = true; tile0 = 0; tile1 = D.ntile; return; }
+	// (subdomain meshes are numbered interior tiles first; a single-rank periodic mesh keeps the caller's numbering and
+	// walks the tile list instead)
+	if(f->roles.active && D.tile_order && tile1 < 0) { ordered = f->mesh->nranks == 1; tile0 = 0; tile1 = D.ntile; return; }
 	if(tile1 >= 0 || f->part == 0 || !D.tile_order) return;
 	ordered = true;
 	if(f->part == 1) { tile0 = 0; tile1 = D.ntile_interior; }

@@ -102,14 +102,15 @@ cell_kernel(const __grid_constant__ CellArgs A)
 	}
 	// fused multi-GPU evaluation: the evaluation number, the window area of this evaluation's state rows, the prologue
 	// (both kept in shared memory: they are needed once per partition-boundary tile only)
-	unsigned long long *const sdk = reinterpret_cast<unsigned long long*>(smraw + S.ring + 96);
+	// The evaluation number lives in device memory (DistCtl::k). Only the few CTAs that need it read it - those of the
+	// first wave that push the state rows, and later the tiles that see a ghost cell (they wait and push): a load on
+	// every CTA's critical path costs 0.13 ms per launch on the 39 000 one-tile CTAs of the benchmark.
 	const double **const sghost = reinterpret_cast<const double**>(smraw + S.ring + 104);
 	if(distd) {
-		const unsigned long long dk = distd->ctl->k;
-		if(tid == 0) { *sdk = dk; *sghost = (A.dist.wait & (1u << X_U)) ? dist_ghost_rows(distd, X_U, dk) : nullptr; }
-		if(A.dist.first) dist_push_state_prologue(distd, dk, A.u, A.dist.force_push, src_idx);
+		if(A.dist.first && (int)blockIdx.x < DIST_PROLOGUE_CTAS)
+			dist_push_state_prologue(distd, A.dist.ctl->k, A.u, A.dist.force_push, src_idx);
 	}
-	else if(tid == 0) { *sdk = 0; *sghost = A.gs_u.rows; }
+	else if(tid == 0) *sghost = A.gs_u.rows;
 	__syncthreads();
 
 	for(int it = 0; ti < tend; it++, ti += G) {
@@ -156,7 +157,8 @@ cell_kernel(const __grid_constant__ CellArgs A)
 		}
 		// in-kernel receive of the state's ghost rows: a tile that sees ghost cells waits for the neighbours' rows (its
 		// other copies are already in flight), then gathers those rows from the halo window
-		const bool ghost_win = (tbq.w >> 16) != 0 && *sghost != nullptr;
+		const bool ghost_tile = (tbq.w >> 16) != 0;
+		const bool ghost_win = ghost_tile && (distd ? (A.dist.wait & (1u << X_U)) != 0 : *sghost != nullptr);
 		if(NEED_NBRS) {
 			for(int k = tid; k < nh*3; k += CELL_BLOCK) {
 				const int h = k/3, piece = k - 3*h;
@@ -169,9 +171,13 @@ cell_kernel(const __grid_constant__ CellArgs A)
 				}
 			}
 			if(ghost_win) {
-				if(distd) dist_wait(distd, 1u << X_U, *sdk);
-				else ghost_wait(A.gs_u, A.gs_u.seq);
-				const double *const ghost_rows_u = *sghost;
+				const double *ghost_rows_u;
+				if(distd) {
+					const unsigned long long dk = A.dist.ctl->k;
+					dist_wait(distd, 1u << X_U, dk);
+					ghost_rows_u = A.dist.ghost[X_U][dk & 1ull];
+				}
+				else { ghost_wait(A.gs_u, A.gs_u.seq); ghost_rows_u = *sghost; }
 				for(int k = tid; k < nh*2; k += CELL_BLOCK) {
 					const int h = k >> 1, piece = k & 1;
 					const size_t g = (size_t)M.thalo[h0 + h];
@@ -360,17 +366,19 @@ cell_kernel(const __grid_constant__ CellArgs A)
 		}
 		// the staging buffers are free for the next tile once every thread is past the stencil loop; the same barrier
 		// orders this tile's gradient stores before the push below reads them back
-		const bool pushes = distd != nullptr && A.dist.push != 0;
+		// (a tile pushes rows exactly when it sees a ghost cell: the cells next to a cut face are the ones the neighbour needs)
+		const bool pushes = distd != nullptr && A.dist.push != 0 && (LOOP || ghost_tile);
 		if(have_next || pushes) __syncthreads();
 		if(pushes) {
 			const int4 rp = A.tdesc[3*(size_t)ti];      // (this tile's record again: nothing of it is held across the stencil loop)
-			if((A.dist.push & (1u << X_GU)) && A.gu) dist_push_tile(distd, X_GU, *sdk, rp.x, rp.y, A.gu);
-			if((A.dist.push & (1u << X_LG)) && A.lg) dist_push_tile(distd, X_LG, *sdk, rp.x, rp.y, A.lg);
+			const unsigned long long dk = A.dist.ctl->k;
+			if((A.dist.push & (1u << X_GU)) && A.gu) dist_push_tile(distd, X_GU, dk, rp.x, rp.y, A.gu);
+			if((A.dist.push & (1u << X_LG)) && A.lg) dist_push_tile(distd, X_LG, dk, rp.x, rp.y, A.lg);
 		}
 		if(!LOOP) break;
 		if(have_next) { const int4 *const rec = ring + 3*((it + 1) & 1); r0 = rec[0]; r1 = rec[1]; r2 = rec[2]; }
 	}
-	if(distd && A.dist.last) dist_finish_evaluation(distd, *sdk, false);
+	if(distd && A.dist.last) dist_finish_evaluation(distd, A.dist.ctl->k, false);
 }
 
 /// kernel launch with the programmatic-stream-serialization attribute (the kernel may start while its predecessor in

@@ -321,6 +321,37 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 		}
 	}
 	const int ntile = (int)tcell0.size() - 1;
+	// Subdomain of a partitioned mesh: renumber the own cells so that the tiles which see a ghost cell come LATE. The
+	// kernels then meet them last in their natural tile order - no tile list, no indirection on any CTA's critical path -
+	// and the rows the neighbours push have had the whole interior to arrive (the same tiles are the ones that push).
+	// Tiles stay what they are (the same cells, in the same relative order); halo lists are re-sorted. Ghost rows and
+	// send lists are ordered by the owner's position in the GLOBAL locality order (rankidx), which no rank's tiling changes.
+	if(nranks > 1 && ntot > nown) {
+		std::vector<char> is_bnd((size_t)ntile, 0);
+		for(int t = 0; t < ntile; t++) is_bnd[t] = thoff[t+1] > thoff[t] && thalo[thoff[t+1]-1] >= nown;
+		// ... last but for about two waves of interior tiles, behind which the latency of their pushes (a system-scope
+		// fence over NVLink per tile) hides instead of sitting in the kernel's tail
+		std::vector<int> torder, inner;
+		for(int t = 0; t < ntile; t++) if(!is_bnd[t]) inner.push_back(t);
+		const size_t after = std::min<size_t>(inner.size()/3, 1024);
+		torder.assign(inner.begin(), inner.end() - (long)after);
+		for(int t = 0; t < ntile; t++) if(is_bnd[t]) torder.push_back(t);
+		torder.insert(torder.end(), inner.end() - (long)after, inner.end());
+		std::vector<int> newpos((size_t)nown), d2g_new(d2g), tcell0_new(1, 0), thoff_new(1, 0), thalo_new;
+		for(int t : torder) {
+			for(int i = tcell0[t]; i < tcell0[t+1]; i++) { newpos[i] = tcell0_new.back() + (i - tcell0[t]); d2g_new[(size_t)newpos[i]] = d2g[i]; }
+			tcell0_new.push_back(tcell0_new.back() + tcell0[t+1] - tcell0[t]);
+		}
+		for(int t : torder) {
+			const size_t b0 = thalo_new.size();
+			for(int h = thoff[t]; h < thoff[t+1]; h++) thalo_new.push_back(thalo[h] < nown ? newpos[thalo[h]] : thalo[h]);
+			std::sort(thalo_new.begin() + (long)b0, thalo_new.end());
+			thoff_new.push_back((int)thalo_new.size());
+		}
+		d2g.swap(d2g_new); tcell0.swap(tcell0_new); thoff.swap(thoff_new); thalo.swap(thalo_new);
+		for(int i = 0; i < nown; i++) g2d[d2g[i]] = i;
+		for(int &c : m->h_send_idx) c = newpos[c];
+	}
 	std::vector<int> tile_order;
 	int ntile_interior = ntile;
 	if(ntot > nown) {

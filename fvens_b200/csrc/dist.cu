@@ -120,6 +120,12 @@ static void set_roles(fvg_dist *D, bool step, bool force_push)
 	const bool limited = P.recon == FVG_RECON_BARTHJESPERSEN || P.recon == FVG_RECON_VENKATAKRISHNAN;
 	const bool visc = P.visc != VISC_NONE;
 	R.cell.d = R.weno.d = R.face.d = dev;
+	R.cell.ctl = R.weno.ctl = R.face.ctl = D->d_ctl;
+	for(int t = 0; t < X_COUNT; t++)
+		for(int par = 0; par < 2; par++) {
+			const double *area = reinterpret_cast<const double*>(D->window + sizeof(WinHdr)) + xarea_off(t, par, (size_t)D->mesh->d.nghost);
+			R.cell.ghost[t][par] = R.weno.ghost[t][par] = R.face.ghost[t][par] = area;
+		}
 	R.face.wait = U; R.face.last = 1; R.face.push = step ? U : 0u; R.face.force_push = force_push ? 1 : 0;
 	R.face.visc_type = X_LG;
 	if(!P.order2) R.face.first = 1;
@@ -155,14 +161,22 @@ static int enqueue_evaluation(fvg_dist *D, const double *u, double *res, int acc
 	set_roles(D, unew != nullptr, force_push);
 	int rc = 0;
 	const double *uface = u;
+	// per-pass timing (fvg_flow_timing): events on the launching stream, direct launches only (not inside a captured graph)
+	cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+	cudaStreamIsCapturing(s, &cap);
+	const bool timed = f->timing && cap == cudaStreamCaptureStatusNone;
+	auto mark = [&]() { if(timed) { cudaEvent_t e; if(cudaEventCreate(&e) == cudaSuccess) { f->ev.push_back(e); cudaEventRecord(e, s); } } };
+	mark();
 	if(perm) {
 		if(f->plan.order2) rc = run_gradient_pass(f, u, s, 0, -1, perm, f->d_uperm);
 		else { rc = launch_permute_rows(u, f->d_uperm, perm, D->mesh->d.ncell, 4, true, false, s); f->launches++; }
 		uface = f->d_uperm;
 	}
 	else rc = run_gradient_pass(f, u, s);
+	mark();
 	if(rc == 0) rc = unew ? run_face_pass(f, uface, EP_STEP, 0, 1, nullptr, nullptr, cfl, unew, s)
 	                      : run_face_pass(f, uface, EP_RESIDUAL, accumulate, gettimesteps, res, dtm, 0.0, nullptr, s, 0, -1, perm);
+	mark();
 	f->roles = fvg_flow::DistRoles();
 	return rc;
 }
@@ -182,7 +196,7 @@ static int enqueue_norm(fvg_dist *D, int push, int lag, double *out, double *his
 template <typename Body>
 static int run_graphed(fvg_dist *D, const fvg_dist::Graph &key, cudaStream_t s, Body body)
 {
-	if(!D->use_graph || s == nullptr || s == cudaStreamLegacy) return body();
+	if(!D->use_graph || D->flow->timing || s == nullptr || s == cudaStreamLegacy) return body();
 	for(const fvg_dist::Graph &g : D->graphs)
 		if(g.kind == key.kind && g.a == key.a && g.b == key.b && g.c == key.c && g.f0 == key.f0 && g.f1 == key.f1 && g.f2 == key.f2 &&
 		   g.x == key.x && g.s == key.s) {

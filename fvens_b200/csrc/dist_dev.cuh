@@ -138,9 +138,11 @@ __device__ __forceinline__ void dist_push_tile(const DistDev *d, int type, unsig
 		const double2 v = ld_cg_f64x2(arr + (size_t)(c0 + lc)*width + 2*c);
 		*reinterpret_cast<double2*>(dist_peer_row(d, r, type, k, row) + 2*c) = v;
 	}
-	__threadfence_system();
+	// One system-scope fence per CTA, by the thread that signals: the CTA barrier orders every thread's stores before
+	// it (fences are cumulative), and 255 fewer fences per tile travel over NVLink.
 	__syncthreads();
 	if(threadIdx.x == 0) {
+		__threadfence_system();
 		unsigned mask = d->tpeers[t];
 		while(mask) {
 			const int r = __ffs((int)mask) - 1;
@@ -148,7 +150,7 @@ __device__ __forceinline__ void dist_push_tile(const DistDev *d, int type, unsig
 			const unsigned prev = atomicAdd(&d->ctl->arrive[type][r], 1u);
 			if(prev == (unsigned)d->ntile_send[r] - 1u) {
 				d->ctl->arrive[type][r] = 0;
-				__threadfence_system();
+				__threadfence_system();      // (acquire side: the other tiles' fenced stores, seen through the counter)
 				st_release_sys_u64(&reinterpret_cast<WinHdr*>(d->peer[r])->flag[type][d->rank], k + 1);
 			}
 		}
@@ -173,9 +175,9 @@ __device__ __forceinline__ void dist_push_state_prologue(const DistDev *d, unsig
 		const double2 v = *reinterpret_cast<const double2*>(u + 4*(size_t)(src_idx ? src_idx[cell] : cell) + 2*c);
 		*reinterpret_cast<double2*>(dist_peer_row(d, r, X_U, k, i - d->send_off[r]) + 2*c) = v;
 	}
-	__threadfence_system();
 	__syncthreads();
 	if(threadIdx.x == 0) {
+		__threadfence_system();
 		const unsigned prev = atomicAdd(&d->ctl->pro_arrive, 1u);
 		if(prev == (unsigned)np - 1u) {
 			d->ctl->pro_arrive = 0;

@@ -103,6 +103,8 @@ struct GhostSrc {
 /// Role of one kernel launch in the fused multi-GPU evaluation (see dist_dev.cuh). d == nullptr: not part of one.
 struct DistRole {
 	const DistDev *d = nullptr;
+	const DistCtl *ctl = nullptr;                 ///< d->ctl (spares the kernels a dependent load)
+	const double *ghost[X_COUNT][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   ///< local receive areas by type and evaluation parity
 	unsigned wait = 0;         ///< bit mask of row types whose ghost rows this kernel reads from the window
 	unsigned push = 0;         ///< bit mask of row types this kernel produces and pushes per tile (X_U: the step epilogue)
 	int first = 0;             ///< first kernel of the evaluation: its prologue pushes the state rows

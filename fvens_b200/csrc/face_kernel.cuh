@@ -287,12 +287,13 @@ face_kernel(const __grid_constant__ FaceArgs A)
 	if(tid == 0) { issue_AC(D, 0); issue_B(D); }
 	if(A.dist.d) {
 		const DistDev *const dd = A.dist.d;
-		const unsigned long long dk = dd->ctl->k;
+		const unsigned long long dk = A.dist.ctl->k;
 		if(tid == 0) {
+			const int par = (int)(dk & 1ull);
 			gp->dk = dk;
-			if(A.dist.wait & (1u << X_U)) gp->u = dist_ghost_rows(dd, X_U, dk);
-			if(MIDS && (A.dist.wait & (1u << (RECON == FR_MUSCL ? X_GU : X_LG)))) gp->g = dist_ghost_rows(dd, RECON == FR_MUSCL ? X_GU : X_LG, dk);
-			if(VISC != VISC_NONE && (A.dist.wait & (1u << A.dist.visc_type))) gp->v = dist_ghost_rows(dd, A.dist.visc_type, dk);
+			if(A.dist.wait & (1u << X_U)) gp->u = A.dist.ghost[X_U][par];
+			if(MIDS && (A.dist.wait & (1u << (RECON == FR_MUSCL ? X_GU : X_LG)))) gp->g = A.dist.ghost[RECON == FR_MUSCL ? X_GU : X_LG][par];
+			if(VISC != VISC_NONE && (A.dist.wait & (1u << A.dist.visc_type))) gp->v = A.dist.ghost[A.dist.visc_type][par];
 		}
 		if(A.dist.first) dist_push_state_prologue(dd, dk, A.u, A.dist.force_push);
 		__syncthreads();

@@ -44,7 +44,7 @@ int resident_ctas(const void *kernel, int block, size_t smem)
  * memory; conserved states are converted to primitive ONCE per staged cell (the reference converts the
  * whole field in a separate pass, flow_spatial.cpp:697-699). Then one thread per own cell gathers its
  * <= 4 neighbours from shared memory: no scatter, no atomics. */
-template <int GRAD, int LIM, bool PRIM_IN>
+template <int GRAD, int LIM, bool PRIM_IN, bool DIST>
 __global__ void __launch_bounds__(CELL_BLOCK, FVG_CELL_MINB)
 cell_kernel_plain(const CellArgs A)
 {
@@ -74,6 +74,8 @@ cell_kernel_plain(const CellArgs A)
 	// and the gradient rows written at the end are still being read by the previous face pass until it completes
 	pdl_wait();
 	__syncthreads();
+	// fused multi-GPU evaluation (DIST): a few CTAs of the first wave push the state rows the neighbours need
+	if(DIST && A.dist.first && (int)blockIdx.x < DIST_PROLOGUE_CTAS) dist_push_state_prologue(A.dist.d, A.dist.ctl->k, A.u, A.dist.force_push);
 	if(tid == 0) {
 		unsigned bytes = (unsigned)nc*(32u + 16u + 16u + (GRAD == GM_WLS ? 32u : 0u)) + (LIM == LM_VENKAT ? (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u : 0u);
 		if(MIDS) bytes += (unsigned)ne*16u;
@@ -104,7 +106,7 @@ cell_kernel_plain(const CellArgs A)
 	const int4 tbq = M.tbnd[t];
 	// in-kernel receive of the state's ghost rows: a tile that sees ghost cells waits for the neighbours' rows (its
 	// other copies are already in flight), then gathers those rows from the halo window
-	const bool ghost_win = A.gs_u.rows != nullptr && (tbq.w >> 16) != 0;
+	const bool ghost_win = (tbq.w >> 16) != 0 && (DIST ? (A.dist.wait & (1u << X_U)) != 0 : A.gs_u.rows != nullptr);
 	if(NEED_NBRS) {
 		for(int k = tid; k < nh*3; k += CELL_BLOCK) {
 			const int h = k/3, piece = k - 3*h;
@@ -114,11 +116,14 @@ cell_kernel_plain(const CellArgs A)
 			else if(!(ghost_win && g >= (size_t)M.ncell)) cp_async16(sp + 4*row + 2*piece, A.u + 4*g + 2*piece);
 		}
 		if(ghost_win) {
-			ghost_wait(A.gs_u, A.gs_u.seq);
+			// (the evaluation number is read only here and where rows are pushed: a handful of tiles)
+			const double *rows;
+			if(DIST) { const unsigned long long dk = A.dist.ctl->k; dist_wait(A.dist.d, 1u << X_U, dk); rows = A.dist.ghost[X_U][dk & 1ull]; }
+			else { ghost_wait(A.gs_u, A.gs_u.seq); rows = A.gs_u.rows; }
 			for(int k = tid; k < nh*2; k += CELL_BLOCK) {
 				const int h = k >> 1, piece = k & 1;
 				const size_t g = (size_t)M.thalo[h0 + h];
-				if(g >= (size_t)M.ncell) cp_async16(sp + 4*(nc + h) + 2*piece, A.gs_u.rows + 4*(g - (size_t)M.ncell) + 2*piece);
+				if(g >= (size_t)M.ncell) cp_async16(sp + 4*(nc + h) + 2*piece, rows + 4*(g - (size_t)M.ncell) + 2*piece);
 			}
 		}
 		cp_async_commit();
@@ -300,17 +305,25 @@ cell_kernel_plain(const CellArgs A)
 		}
 		st4(A.lg + 8*(size_t)i + 2*o0, g); st4(A.lg + 8*(size_t)i + 2*o1, g+4);
 	}
+	// a tile that sees a ghost cell has cells the neighbours need: its gradient rows go to their windows now
+	if(DIST && A.dist.push != 0 && (M.tbnd[t].w >> 16) != 0) {
+		__syncthreads();
+		const unsigned long long dk = A.dist.ctl->k;
+		if((A.dist.push & (1u << X_GU)) && A.gu) dist_push_tile(A.dist.d, X_GU, dk, t, M.tcell0[t], A.gu);
+		if((A.dist.push & (1u << X_LG)) && A.lg) dist_push_tile(A.dist.d, X_LG, dk, t, M.tcell0[t], A.lg);
+	}
 }
 
-template <int GRAD, int LIM, bool PRIM_IN>
+
+template <int GRAD, int LIM, bool PRIM_IN, bool DIST>
 static int launch_cell_plain(const CellArgs &b, int nt, cudaStream_t s)
 {
 	const CellSmem S(b.m.TC, b.m.HMAX, b.m.EMAX, LIM != LM_NONE || GRAD == GM_GG, GRAD == GM_GG, GRAD == GM_WLS, LIM == LM_VENKAT);
 	if(S.total > 48*1024) {
-		const cudaError_t ea = cudaFuncSetAttribute(cell_kernel_plain<GRAD,LIM,PRIM_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
+		const cudaError_t ea = cudaFuncSetAttribute(cell_kernel_plain<GRAD,LIM,PRIM_IN,DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
 		if(ea != cudaSuccess) return cuda_fail(ea, "cell_kernel smem attribute", __FILE__, __LINE__);
 	}
-	cell_kernel_plain<GRAD,LIM,PRIM_IN><<<nt, CELL_BLOCK, S.total, s>>>(b);
+	cell_kernel_plain<GRAD,LIM,PRIM_IN,DIST><<<nt, CELL_BLOCK, S.total, s>>>(b);
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "cell_kernel launch", __FILE__, __LINE__);
 	return 0;
@@ -325,8 +338,18 @@ int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaS
 	if(nt <= 0) return 0;
 	int mode = cell_mode_of(b, prim_in);
 	if(mode == CM_PLAIN && b.ordered) mode = CM_DIST;       // (a tile sequence other than the natural one: the general kernel)
+	static int fast_dist = -1;
+	if(fast_dist < 0) { const char *e = getenv("FVG_CELL_FASTDIST"); fast_dist = e ? atoi(e) : 1; }
+	if(mode == CM_DIST && b.dist.d && fast_dist && b.tile0 == 0 && nt == b.m.ntile) {
+		// multi-GPU, device order: the one-tile-per-CTA kernel in its natural tile order (the partition-boundary tiles are
+		// spread over the grid: their pushes travel while the rest computes; the face pass runs them last)
+#define D(G,L) if(grad == G && lim == L) return launch_cell_plain<G,L,false,true>(b, nt, s);
+		D(GM_ZERO,LM_NONE) D(GM_ZERO,LM_BJ) D(GM_ZERO,LM_VENKAT) D(GM_GG,LM_NONE) D(GM_GG,LM_BJ) D(GM_GG,LM_VENKAT)
+		D(GM_WLS,LM_NONE) D(GM_WLS,LM_BJ) D(GM_WLS,LM_VENKAT)
+#undef D
+	}
 	if(mode != CM_PLAIN) return launch_cell_kernel_modes(grad, lim, mode, b, s);
-#define C(G,L,P) if(grad == G && lim == L && prim_in == P) return launch_cell_plain<G,L,P>(b, nt, s);
+#define C(G,L,P) if(grad == G && lim == L && prim_in == P) return launch_cell_plain<G,L,P,false>(b, nt, s);
 	C(GM_ZERO,LM_NONE,false) C(GM_ZERO,LM_BJ,false) C(GM_ZERO,LM_VENKAT,false)
 	C(GM_GG,LM_NONE,false) C(GM_GG,LM_BJ,false) C(GM_GG,LM_VENKAT,false)
 	C(GM_WLS,LM_NONE,false) C(GM_WLS,LM_BJ,false) C(GM_WLS,LM_VENKAT,false)
@@ -362,8 +385,8 @@ weno_kernel(const __grid_constant__ WenoArgs A)
 	GhostSrc gsg = A.gs_gu;
 	unsigned long long dk = 0;
 	if(A.dist.d) {
-		dk = A.dist.d->ctl->k;
-		if(A.dist.wait & (1u << X_GU)) gsg.rows = dist_ghost_rows(A.dist.d, X_GU, dk);
+		dk = A.dist.ctl->k;
+		if(A.dist.wait & (1u << X_GU)) gsg.rows = A.dist.ghost[X_GU][dk & 1ull];
 	}
 	int it = 0;
 	for(int ti = blockIdx.x; ti < M.ntile; ti += G, it++) {

@@ -193,7 +193,8 @@ def test_reference_partitioner_reproduces_its_goldens_and_the_product_agrees():
         # the product, for the same distribution
         dm = lib.DeviceMesh(um, reorder="none", tile_cells=32, device=-2, cell_rank=dist, rank=r, nranks=3)
         ids = dm.permutation()
-        assert np.array_equal(ids[:dm.ncell], glob)
+        # same own cells (the device numbers the tiles that see a ghost cell last, so the order is its own)
+        assert np.array_equal(np.sort(ids[:dm.ncell]), glob)
         assert set(ids[dm.ncell:].tolist()) == set(conn[:, 3].tolist())
         owner = {int(c): int(rk) for rk, c in zip(conn[:, 2], conn[:, 3])}
         assert all(dist[g] == owner[int(g)] for g in ids[dm.ncell:])
@@ -212,7 +213,13 @@ def test_product_subdomains_against_the_reference_partitioner_on_a_hilbert_parti
         glob, conn = gm.restrict_to_rank(part, nranks, r).connectivity()
         dm = lib.DeviceMesh(um, reorder="none", tile_cells=64, device=-2, cell_rank=part, rank=r, nranks=nranks)
         ids = dm.permutation()
-        assert np.array_equal(ids[:dm.ncell], glob) and (part[glob] == r).all()
+        assert np.array_equal(np.sort(ids[:dm.ncell]), glob) and (part[glob] == r).all()
+        # tiles that send rows to a neighbour (= tiles that see a ghost cell) are one block late in the device numbering,
+        # followed only by the interior tiles that hide the latency of their pushes
+        toff, _ = dm.tile_send_lists()
+        sends = np.diff(toff) > 0
+        first, last = np.argmax(sends), len(sends) - 1 - np.argmax(sends[::-1])
+        assert sends.any() and sends[first:last+1].all() and (len(sends) < 4 or first >= (len(sends) - sends.sum())//2)
         assert set(ids[dm.ncell:].tolist()) == set(conn[:, 3].tolist()) and len(conn) >= dm.nghost > 0
         assert all(part[c] == rk for rk, c in zip(conn[:, 2], conn[:, 3]))
 
