@@ -119,8 +119,9 @@ class Workload:
             lat = (self.n, self.n)
             coords, nnode, inpoel, bface = synth.periodic_square(self.n)
         rc = synth.cell_centres(coords, nnode, inpoel)
-        perm = synth.hilbert_order(rc)
-        nnode, inpoel, rc = np.ascontiguousarray(nnode[perm]), np.ascontiguousarray(inpoel[perm]), rc[perm]
+        if getattr(a, "cell_order", "hilbert") == "hilbert":
+            perm = synth.hilbert_order(rc)
+            nnode, inpoel, rc = np.ascontiguousarray(nnode[perm]), np.ascontiguousarray(inpoel[perm]), rc[perm]
         if self.name == "vortex":
             u = synth.isentropic_vortex(rc, 1.4, self.minf, 0.0)
         else:
@@ -141,7 +142,10 @@ class Workload:
     def config(self, nc, nf, lat):
         """`config` of the JSON line: the workload only, identical in both arms (the GPU arm's layout goes under `layout`)."""
         return {"workload": self.what, "cells": int(nc), "faces": int(nf), "lattice": [int(lat[0]), int(lat[1])],
-                "numerics": self.tag, "cell_order": "Hilbert curve (host renumbering, identical in both arms)",
+                "numerics": self.tag,
+                "cell_order": "Hilbert curve (host renumbering, identical in both arms)" if getattr(self.args, "cell_order", "hilbert") == "hilbert"
+                else "the generator's row-major numbering as the caller's; the engine renumbers internally (reorder = hilbert) and "
+                     "gathers / scatters through the permutation inside its two kernels (the drop-in path of FlowFV_B200)",
                 "l2": "inputs (32 B state + 64 B gradients + ~300 B mesh per cell: 4 GB at 10M cells) exceed the 126 MB L2 from "
                       "0.4M cells per GPU up; no explicit flush"}
 
@@ -297,6 +301,9 @@ def main():
     ap.add_argument("--cpu-cells", type=float, default=0.0,
                     help="cells of the CPU arms' mesh; 0 (default) = the workload's own mesh (same config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cell-order", default="hilbert", choices=["hilbert", "caller"],
+                    help="hilbert: the host mesh is renumbered along a Hilbert curve first (default, both arms); caller: arrays stay in "
+                         "the generator's row-major order and the engine renumbers internally (single GPU)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--time-passes", action="store_true", help="N > 1: time the two passes on every rank (turns graph replay off)")
     ap.add_argument("--partition", default="sfc", choices=["sfc", "rcb"],
@@ -373,7 +380,7 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     num = wl.num
     if world == 1:
-        dm = lib.DeviceMesh(um, reorder="none", tile_cells=args.tile, device=local_rank)
+        dm = lib.DeviceMesh(um, reorder="none" if args.cell_order == "hilbert" else "hilbert", tile_cells=args.tile, device=local_rank)
         fl = lib.FlowFV(dm, phys, bcs=BCS, **num)
         nc = nc_glob
         du = torch.from_numpy(u).cuda()

@@ -592,8 +592,11 @@ int fvg_residual(fvg_flow *f, const double *d_u, double *d_res, int accumulate, 
 	// time-step stores go straight to the caller's rows (no permutation kernels, SURVEY 8b drop-in path)
 	if((rc = ensure(f, &f->d_uperm, 4*(size_t)n)) != 0) return rc;
 	if(f->plan.order2) {
+		if((rc = mark(f, s)) != 0) return rc;
 		if((rc = run_gradient_pass(f, d_u, s, 0, -1, D.new2old, f->d_uperm)) != 0) return rc;
-		return run_face_pass(f, f->d_uperm, EP_RESIDUAL, accumulate, gettimesteps, d_res, d_dtm, 0.0, nullptr, s, 0, -1, D.new2old);
+		if((rc = mark(f, s)) != 0) return rc;
+		if((rc = run_face_pass(f, f->d_uperm, EP_RESIDUAL, accumulate, gettimesteps, d_res, d_dtm, 0.0, nullptr, s, 0, -1, D.new2old)) != 0) return rc;
+		return mark(f, s);
 	}
 	// first order (no gradient pass to gather in): one gather kernel, then the face pass scatters its stores
 	if((rc = launch_permute_rows(d_u, f->d_uperm, D.new2old, n, 4, true, false, s)) != 0) return rc;
@@ -668,7 +671,7 @@ int fvg_residual_host(fvg_flow *f, const double *h_u, double *h_res, int accumul
 	if((rc = ensure(f, &f->d_hdt, n)) != 0) return rc;
 	if(!f->pipe.planned) plan_host_pipe(f);
 	const fvg_flow::HostPipe &P = f->pipe;
-	if(P.K >= 2 && !accumulate && f->plan.recon != FVG_RECON_WENO && !f->timing) {
+	if(P.K >= 2 && f->plan.recon != FVG_RECON_WENO && !f->timing) {
 		// chunked pipeline: uploads in sweep order on one stream, the two passes per chunk on a second one as soon
 		// as their inputs are complete, downloads of finished chunks on a third (PCIe is full duplex)
 		const std::vector<int> &tc0 = f->mesh->h_tcell0;
@@ -683,6 +686,9 @@ int fvg_residual_host(fvg_flow *f, const double *h_u, double *h_res, int accumul
 			const int c = P.order[j];
 			const size_t i0 = (size_t)tc0[P.tile0[c]], i1 = (size_t)tc0[P.tile0[c+1]];
 			FVG_CUDA(cudaMemcpyAsync(f->d_hu + 4*i0, h_u + 4*i0, 4*(i1 - i0)*sizeof(double), cudaMemcpyHostToDevice, P.s_in));
+			// the reference adds into the caller's residual: its rows ride up with the state rows and the face
+			// pass of the chunk accumulates on the device
+			if(accumulate) FVG_CUDA(cudaMemcpyAsync(f->d_hr + 4*i0, h_res + 4*i0, 4*(i1 - i0)*sizeof(double), cudaMemcpyHostToDevice, P.s_in));
 			FVG_CUDA(cudaEventRecord(P.ev_up[j], P.s_in));
 			uploaded |= 1ull << c;
 			bool waited = false;
@@ -697,7 +703,7 @@ int fvg_residual_host(fvg_flow *f, const double *h_u, double *h_res, int accumul
 			for(int q = 0; q < P.K; q++) {
 				const int d = P.order[q];
 				if((faces_done >> d) & 1ull || (P.deps[d] & ~cells_done) != 0) continue;
-				if((rc = run_face_pass(f, f->d_hu, EP_RESIDUAL, 0, gettimesteps, f->d_hr, f->d_hdt, 0.0, nullptr, P.s_run,
+				if((rc = run_face_pass(f, f->d_hu, EP_RESIDUAL, accumulate, gettimesteps, f->d_hr, f->d_hdt, 0.0, nullptr, P.s_run,
 				                       P.tile0[d], P.tile0[d+1])) != 0) return rc;
 				faces_done |= 1ull << d;
 				FVG_CUDA(cudaEventRecord(P.ev_face[d], P.s_run));

@@ -948,7 +948,8 @@ private:
 			hist[step++] = resi;
 			if(!std::isfinite(resi)) { code = FVG_ERR_NUMERICAL; break; }
 		}
-		if(code == FVG_OK && step == config.maxiter && resi/initres > config.tol) code = FVG_ERR_TOLERANCE;
+		// aodesolver.cpp:253-256: reaching maxiter is an error whatever the last residual (as fvg_forward_euler_solve)
+		if(code == FVG_OK && step == config.maxiter) code = FVG_ERR_TOLERANCE;
 		VecDestroy(&r); VecDestroy(&dt);
 		return code;
 	}

@@ -131,6 +131,15 @@ def test_host_buffer_pipeline_matches_the_device_resident_path(kw):
     assert np.array_equal(res, r1) and np.array_equal(dt, d1)
     r0, dt0, _, _ = of.residual(u)
     assert rel_err_by_component(res, r0) < TOL and np.abs(dt/dt0-1).max() < TOL
+    # the class surface always accumulates (the reference adds -r(u) into the caller's vector): the pipeline
+    # uploads the residual rows with the state rows and accumulates on the device - same bits as the device-resident call
+    import torch
+    base = np.random.default_rng(3).standard_normal(u.shape)
+    acc = base.copy(); dt2 = np.zeros(len(u))
+    fl.compute_residual_host(u, acc, True, dt2, accumulate=True)
+    dacc = torch.from_numpy(base).cuda(); ddt = torch.zeros(len(u), dtype=torch.float64, device="cuda")
+    fl.compute_residual(torch.from_numpy(u).cuda(), dacc, True, ddt, accumulate=True)
+    assert np.array_equal(acc, dacc.cpu().numpy()) and np.array_equal(dt2, d1)
 
 
 @pytest.mark.parametrize("reorder", ["none", "hilbert", "rcm"])
