@@ -295,7 +295,7 @@ def main():
     ap.add_argument("--numerics", default="roe-wls-venkat", choices=list(NUMERICS), help="bump workload only")
     ap.add_argument("--flux", default="roe", choices=[f.lower() for f in FLUXES], help="ogrid-weno workload: the inviscid flux")
     ap.add_argument("--weno-lambda", type=float, default=1.0, help="ogrid-weno workload: central weight of the WENO average (1 or 20)")
-    ap.add_argument("--n", type=int, default=0, help="vortex workload: cells per side (default sqrt(--cells))")
+    ap.add_argument("--vortex-n", dest="n", type=int, default=0, help="vortex workload: cells per side (default sqrt(--cells))")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="vortex workload with N > 1: fixed mesh, or n*sqrt(N)")
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--cpu-cells", type=float, default=0.0,

@@ -213,6 +213,11 @@ face_kernel(const __grid_constant__ FaceArgs A)
 
 	const int tid = threadIdx.x;
 	const double *const gsrc = RECON == FR_MUSCL ? A.gu : A.lg;     // gradients used by the reconstruction
+	// Viscous flux with linear reconstruction and no limiter (the laminar cases of the reference: the gradients of the
+	// viscous flux ARE the reconstruction gradients): phase B takes the cell states, gradients, centres and areas of both
+	// sides from the staged rows instead of gathering 230 bytes per entry from global memory; the own-cell rows (group
+	// A buffers) are then refilled for the next tile after phase B instead of after phase A.
+	const bool keepA = VISC != VISC_NONE && RECON == FR_LINEAR && A.gu == A.lg;
 	// where the ghost rows are: in the arrays, in the window of a posted exchange (legacy split passes: A.gs_*), or in
 	// this evaluation's areas of the fused multi-GPU evaluation (set below, once the evaluation number is known)
 	// (kept in shared memory, not in registers: they are read once per tile)
@@ -377,7 +382,7 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		cp_async_wait_all();        // this tile's halo rows: gathered since the previous tile's phase B ended
 		__syncthreads();
 		// group A buffers are free: the next tile's phase-A inputs (and its stencil/area into the other C buffer)
-		if(tid == 0 && have_next) { fence_proxy_async(); issue_AC(unpack_tile_desc(rnext), (int)(par ^ 1u)); }
+		if(tid == 0 && have_next && !keepA) { fence_proxy_async(); issue_AC(unpack_tile_desc(rnext), (int)(par ^ 1u)); }
 
 		// ---- phase B: fluxes, one real stream entry per thread and round (the list `sord` skips the padding entries, so
 		// the rounds are full: consecutive threads still take nearly consecutive entries)
@@ -399,8 +404,9 @@ face_kernel(const __grid_constant__ FaceArgs A)
 				if(Rf < (unsigned)D.nc) ldp4(fsR + e, EP, sr);
 				else halo_side_state<RECON>(A, hu, hg, hrc, (int)Rf - D.nc, RECON == FR_LINEAR ? fsR[e] : make_double2(0,0), sr);
 			}
-			const int gidL = (VISC != VISC_NONE || RECON == FR_MUSCL) ? tile_global_h(M, D.h0, D.c0, D.nc, L) : 0;
-			const int gidR = (VISC != VISC_NONE || RECON == FR_MUSCL) ? (bnd ? gidL : tile_global_h(M, D.h0, D.c0, D.nc, Rf)) : 0;
+			const bool need_gid = ((VISC != VISC_NONE) && !keepA) || RECON == FR_MUSCL;
+			const int gidL = need_gid ? tile_global_h(M, D.h0, D.c0, D.nc, L) : 0;
+			const int gidR = need_gid ? (bnd ? gidL : tile_global_h(M, D.h0, D.c0, D.nc, Rf)) : 0;
 
 			Side a, bs;
 			double ucl[4], ucr[4];      // conserved cell states for the viscous flux (right = ghost of the cell state)
@@ -419,9 +425,17 @@ face_kernel(const __grid_constant__ FaceArgs A)
 					bs = load_side<true>(A.gas, ur, nx, ny);
 				} else bs = side_from_prim<true>(A.gas, sr, nx, ny);
 				if(VISC != VISC_NONE) {
-					ld4(ghost_aware_row(A.u, gp->u, M.ncell, gidL, 4), ucl);
-					if(bnd) ghost_state(A.gas, bc, ucl, nx, ny, ucr);
-					else ld4(ghost_aware_row(A.u, gp->u, M.ncell, gidR, 4), ucr);
+					if(keepA) {
+						if(L < (unsigned)D.nc) { const double2 c0_ = *reinterpret_cast<const double2*>(su + rows32_chunk((int)L, 0)), c1_ = *reinterpret_cast<const double2*>(su + rows32_chunk((int)L, 1)); ucl[0] = c0_.x; ucl[1] = c0_.y; ucl[2] = c1_.x; ucl[3] = c1_.y; }
+						else lds4(hu + 4*((int)L - D.nc), ucl);
+						if(bnd) ghost_state(A.gas, bc, ucl, nx, ny, ucr);
+						else if(Rf < (unsigned)D.nc) { const double2 c0_ = *reinterpret_cast<const double2*>(su + rows32_chunk((int)Rf, 0)), c1_ = *reinterpret_cast<const double2*>(su + rows32_chunk((int)Rf, 1)); ucr[0] = c0_.x; ucr[1] = c0_.y; ucr[2] = c1_.x; ucr[3] = c1_.y; }
+						else lds4(hu + 4*((int)Rf - D.nc), ucr);
+					} else {
+						ld4(ghost_aware_row(A.u, gp->u, M.ncell, gidL, 4), ucl);
+						if(bnd) ghost_state(A.gas, bc, ucl, nx, ny, ucr);
+						else ld4(ghost_aware_row(A.u, gp->u, M.ncell, gidR, 4), ucr);
+					}
 				}
 			}
 			else { // MUSCL with Van Albada limiter: sl, sr are the primitive CELL states
@@ -471,28 +485,57 @@ face_kernel(const __grid_constant__ FaceArgs A)
 			double srj = (fabs(bs.vn) + bs.c)*len;
 
 			if(VISC != VISC_NONE) {
-				const double ul[4] = {a.r, a.mx, a.my, a.E}, ur[4] = {bs.r, bs.mx, bs.my, bs.E};
-				const double2 rl = M.rc[gidL];
-				double2 rr;
-				if(bnd) {
-					const double2 gr = M.fgr[D.e0 + e];
-					rr = make_double2(2.0*gr.x - rl.x, 2.0*gr.y - rl.y);
-				} else rr = M.rc[gidR];
+				const bool ownL = L < (unsigned)D.nc, ownR = !bnd && Rf < (unsigned)D.nc;
+				double2 rl, rr;
 				double gl[8], grr[8], vf[4];
-				if(RECON != FR_FIRST) {
-					{ const double *const gl_ = ghost_aware_row(A.gu, gp->v, M.ncell, gidL, 8); ld4(gl_, gl); ld4(gl_ + 4, gl+4); }
-					if(bnd) for(int q = 0; q < 8; q++) grr[q] = gl[q];
-					else { const double *const gr_ = ghost_aware_row(A.gu, gp->v, M.ncell, gidR, 8); ld4(gr_, grr); ld4(gr_ + 4, grr+4); }
+				if(RECON == FR_LINEAR && keepA) {
+					// centres and gradient rows of both cells out of shared memory (own cells: the swizzled TMA rows)
+					auto rows = [&](bool own, unsigned loc, double2 &rc_, double g_[8]) {
+						if(own) {
+							rc_ = src[loc];
+							#pragma unroll
+							for(int c = 0; c < 4; c++) { const double2 v = *reinterpret_cast<const double2*>(sg + rows64_chunk((int)loc, c)); g_[2*c] = v.x; g_[2*c+1] = v.y; }
+						} else {
+							const int h = (int)loc - D.nc;
+							rc_ = hrc[h];
+							lds4(hg + 8*h, g_); lds4(hg + 8*h + 4, g_ + 4);
+						}
+					};
+					rows(ownL, L, rl, gl);
+					if(bnd) {
+						const double2 gr = sgr[e];
+						rr = make_double2(2.0*gr.x - rl.x, 2.0*gr.y - rl.y);
+						for(int q = 0; q < 8; q++) grr[q] = gl[q];
+					} else rows(ownR, Rf, rr, grr);
+				} else {
+					rl = M.rc[gidL];
+					if(bnd) {
+						const double2 gr = M.fgr[D.e0 + e];
+						rr = make_double2(2.0*gr.x - rl.x, 2.0*gr.y - rl.y);
+					} else rr = M.rc[gidR];
+					if(RECON != FR_FIRST) {
+						{ const double *const gl_ = ghost_aware_row(A.gu, gp->v, M.ncell, gidL, 8); ld4(gl_, gl); ld4(gl_ + 4, gl+4); }
+						if(bnd) for(int q = 0; q < 8; q++) grr[q] = gl[q];
+						else { const double *const gr_ = ghost_aware_row(A.gu, gp->v, M.ncell, gidR, 8); ld4(gr_, grr); ld4(gr_ + 4, grr+4); }
+					}
 				}
-				viscous_face_flux<RECON != FR_FIRST, VISC == VISC_CONST>(A.gas, nx, ny, rl.x, rl.y, rr.x, rr.y,
-					ucl, ucr, gl, grr, ul, ur, vf);
+				// viscosities of the two face states (needed by the flux and by the spectral radius); a.ir, a.p etc. are at hand
+				const double iRe = frcp(A.gas.Reinf);
+				const double mui = VISC == VISC_CONST ? iRe : sutherland_fast(A.gas, a.p, a.ir);
+				const double muj = VISC == VISC_CONST ? iRe : sutherland_fast(A.gas, bs.p, bs.ir);
+				viscous_face_flux_fast<RECON != FR_FIRST>(A.gas, nx, ny, rl.x, rl.y, rr.x, rr.y, ucl, ucr, gl, grr,
+					a.vx, a.vy, bs.vx, bs.vy, mui, muj, vf);
 				for(int q = 0; q < 4; q++) f[q] += vf[q]*len;
-				const double mui = VISC == VISC_CONST ? 1.0/A.gas.Reinf : viscosity_cons(A.gas, ul);
-				const double muj = VISC == VISC_CONST ? 1.0/A.gas.Reinf : viscosity_cons(A.gas, ur);
-				const double coi = fmax(4.0/(3.0*ul[0]), A.gas.g/ul[0]);
-				const double coj = fmax(4.0/(3.0*ur[0]), A.gas.g/ur[0]);
-				sri += coi*mui/A.gas.Pr*len*len/M.area[gidL];
-				if(!bnd) srj += coj*muj/A.gas.Pr*len*len/M.area[gidR];
+				// max(4/(3 rho), gamma/rho) mu/Pr len^2/area (flow_spatial.cpp:600-617); both terms of the max scale with 1/rho
+				const double cmax = fmax(4.0/3.0, A.gas.g)*frcp(A.gas.Pr)*len*len;
+				if(RECON == FR_LINEAR && keepA) {
+					// (the spectral radius of a side is consumed only by a cell of this tile: a halo side needs none)
+					if(ownL) sri += cmax*a.ir*mui*frcp(sar[(int)L + aoff]);
+					if(ownR) srj += cmax*bs.ir*muj*frcp(sar[(int)Rf + aoff]);
+				} else {
+					sri += cmax*a.ir*mui*frcp(M.area[gidL]);
+					if(!bnd) srj += cmax*bs.ir*muj*frcp(M.area[gidR]);
+				}
 			}
 			// the entry's slots now carry its flux and the two spectral radii
 			fsL[e] = make_double2(f[0], f[1]);
@@ -502,7 +545,7 @@ face_kernel(const __grid_constant__ FaceArgs A)
 		__syncthreads();
 		// group B buffers are free: the next tile's entry metadata and halo rows
 		if(have_next) {
-			if(tid == 0) { fence_proxy_async(); issue_B(unpack_tile_desc(rnext)); }
+			if(tid == 0) { fence_proxy_async(); if(keepA) issue_AC(unpack_tile_desc(rnext), (int)(par ^ 1u)); issue_B(unpack_tile_desc(rnext)); }
 			if(!waited && (rnext[1].w >> 16)) { wait_for_ghost_rows(); waited = true; }
 			issue_halo(rnext[1].x, gnext);
 		}

@@ -16,7 +16,7 @@ timeout 300 python bench.py --workload viscous --no-cpu-baseline > $out/${tag}_b
 timeout 300 python bench.py --workload ogrid-weno --cells 6.25e6 --flux roe --no-cpu-baseline > $out/${tag}_bench_n1_ogrid_weno_roe.json 2> /dev/null
 for fl in llf vanleer ausm hll hllc; do timeout 300 python bench.py --workload ogrid-weno --cells 6.25e6 --flux $fl --no-cpu-baseline --e2e-steps 1 --steps 30 > $out/${tag}_bench_n1_ogrid_weno_$fl.json 2> /dev/null; done
 timeout 300 python bench.py --workload ogrid-weno --cells 6.25e6 --flux roe --weno-lambda 20 --no-cpu-baseline --e2e-steps 1 --steps 30 > $out/${tag}_bench_n1_ogrid_weno_roe_l20.json 2> /dev/null
-for n in 512 2048 4096; do timeout 300 python bench.py --workload vortex --n $n --no-cpu-baseline --e2e-steps 1 --steps 30 > $out/${tag}_bench_n1_vortex_$n.json 2> /dev/null; done
+for n in 512 2048 4096; do timeout 300 python bench.py --workload vortex --vortex-n $n --no-cpu-baseline --e2e-steps 1 --steps 30 > $out/${tag}_bench_n1_vortex_$n.json 2> /dev/null; done
 for f in $out/${tag}_bench_n1*.json $out/${tag}_bench_ref.json; do tail -1 $f | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$f'.split('/')[-1], d.get('ms_per_step'), d.get('value'), (d.get('roofline') or {}).get('frac'), d.get('residual_roofline_frac'), (d.get('kernels_ms') or ''))" 2>/dev/null; done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $out/${tag}_launches_bench.log 2>&1
