@@ -1,11 +1,10 @@
 #!/bin/bash
 # Times the residual with differently-built copies of the library (launch bounds / block sizes), tile sizes and
 # environment knobs. usage: tools/variant_sweep.sh "<lib:tile[:ENV=val]> ..."   (lib = path of a .so or "default")
-# Variants are built next to the default library, e.g. the programmatic-dependent-launch build (pass B's prologue under
-# pass A's tail and the next pass A's under pass B's; compiles, PREEXIT/ACQBULK in the SASS, never run yet):
-#   make -C fvens_b200/csrc -j8 EXTRA=-DFVG_PDL OBJDIR=build_pdl TARGET=../variants_pdl.so
-#   tools/variant_sweep.sh "default:256 fvens_b200/variants_pdl.so:256"
-# and for N GPUs: FVENS_B200_LIB=$PWD/fvens_b200/variants_pdl.so torchrun ... bench.py --gpus N
+# Variants are built next to the default library (FVENS_B200_LIB selects one), e.g. other launch bounds:
+#   make -C fvens_b200/csrc -j8 EXTRA="-DFVG_FACE_BLOCK=320" OBJDIR=build_320 TARGET=../variants_320.so
+#   tools/variant_sweep.sh "default:256 fvens_b200/variants_320.so:256 default:256:FVG_PREFETCH_WAVES=0"
+# This is how the A/B runs of profiles/r02_cell_kernel_ab.txt were made (round-1 library against the round-2 one on one box).
 for spec in $1; do
   IFS=: read lib tile envs <<< "$spec"
   if [ "$lib" != "default" ]; then export FVENS_B200_LIB=$lib; else unset FVENS_B200_LIB; fi
