@@ -16,7 +16,15 @@ namespace fvens {
 
 /// Reference: constructMeshFlow (mesh/ameshutils.cpp:39-153). Cell reordering (-mesh_reorder) is the engine's job.
 inline UMesh<freal,NDIM> constructMeshFlow(const FlowParserOptions& opts, const std::string& mesh_suffix) {
-	return constructMesh(opts.meshfile + mesh_suffix);
+	UMesh<freal,NDIM> m = constructMesh(opts.meshfile + mesh_suffix);
+	// utilities/casesolvers.cpp:31-35: a `periodic` boundary condition carries (marker, axis) in its `options`; the
+	// pairs become interior faces of the device mesh (the reference pairs them too but has no FlowBC to run them with)
+	for(auto it = opts.bcconf.begin(); it != opts.bcconf.end(); it++)
+		if(it->bc_type == PERIODIC_BC) {
+			if(it->bc_opts.size() < 2) throw std::runtime_error("periodic boundary condition needs `options marker axis`");
+			m.compute_periodic_map(it->bc_opts[0], it->bc_opts[1]);
+		}
+	return m;
 }
 
 /// Reference: initializeSystemVector (utilities/casesolvers.cpp:52-69)

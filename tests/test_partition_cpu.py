@@ -198,3 +198,43 @@ def test_partition_quality_edge_cut_and_balance(nranks):
     assert cr <= 1.15*cs and cr < 1.6*strips and cs < 3.0*strips
     # deterministic
     assert np.array_equal(rcb, lib.partition_rcb(um, nranks))
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+@pytest.mark.parametrize("nranks,partition", [(2, "sfc"), (3, "rcb"), (5, "sfc")])
+def test_send_lists_and_ghost_blocks_of_all_ranks_agree(nranks, partition, periodic):
+    """The exchange pattern of the fused evaluation, checked on the CPU with host-only device meshes of EVERY rank: the
+    rows rank q sends to rank r - in q's send order - are exactly the cells of r's ghost block from q, in r's ghost
+    order. Holds with the late numbering of the partition-boundary tiles (ghost order is keyed on the global locality
+    order, not on the owner's device numbering) and with periodic pairs, whose ghost copies may come from the rank
+    itself; every own cell appears once, every tile that sends is in one late block."""
+    if periodic:
+        arrs = synth.periodic_square(36, tri_fraction=0.3, jitter=0.1)
+        um = lib.UMesh.from_arrays(*arrs)
+        um.compute_periodic_map(3, 0); um.compute_periodic_map(4, 1)
+    else:
+        arrs = synth.bump_channel(60, 24)
+        um = lib.UMesh.from_arrays(*arrs)
+    part = (lib.partition_sfc if partition == "sfc" else lib.partition_rcb)(um, nranks)
+    meshes = [lib.DeviceMesh(um, reorder="hilbert", tile_cells=64, device=-2, cell_rank=part, rank=r, nranks=nranks) for r in range(nranks)]
+    perms = [m.permutation() for m in meshes]
+    lists = [m.halo_lists() for m in meshes]
+    owned = np.concatenate([p[:m.ncell] for p, m in zip(perms, meshes)])
+    assert np.array_equal(np.sort(owned), np.arange(um.nelem))
+    for r in range(nranks):
+        sc, rc, idx = lists[r]
+        assert rc.sum() == meshes[r].nghost and sc.sum() == len(idx)
+        goff = np.concatenate(([0], np.cumsum(rc)))
+        for q in range(nranks):
+            scq, _, idxq = lists[q]
+            soff = np.concatenate(([0], np.cumsum(scq)))
+            sent = perms[q][idxq[soff[r]:soff[r+1]]]                     # global cells q pushes to r, in q's order
+            ghosts = perms[r][meshes[r].ncell + goff[q]: meshes[r].ncell + goff[q+1]]
+            assert np.array_equal(sent, ghosts), (r, q)
+            assert (part[ghosts] == q).all()
+            if q == r and not periodic:
+                assert len(ghosts) == 0
+        toff, _ = meshes[r].tile_send_lists()
+        sends = np.diff(toff) > 0
+        first, last = np.argmax(sends), len(sends) - 1 - np.argmax(sends[::-1])
+        assert sends[first:last+1].all()
