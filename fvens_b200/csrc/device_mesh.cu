@@ -138,6 +138,12 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 	const int HMAX = std::max(32, (3*TC/8 + 31)/32*32);
 	const int EMAX = (2*TC + TC/8 + 31)/32*32;
 	const int LCAP = (2*TC + TC/4 + 31)/32*32;    // cap on a tile's stream segment including bank padding
+	// The face kernel takes a tile's entries FACE_BLOCK at a time: a tile just over a multiple of that size pays a whole
+	// round for a handful of entries (all-quad meshes: 2 entries per cell + half the perimeter = 544 for a 16 x 16 tile,
+	// which used to fall back to 204 cells). Tiles are cut at the largest multiple within the capacity instead
+	// (FVG_TILE_ENTRY_CAP=0: the capacity itself, the cut of the earlier rounds).
+	int ECAP = EMAX >= FACE_BLOCK ? EMAX/FACE_BLOCK*FACE_BLOCK : EMAX;
+	if(const char *ev = getenv("FVG_TILE_ENTRY_CAP")) { const int v = atoi(ev); ECAP = v > 0 ? std::min(v, EMAX) : EMAX; }
 	const int reorder = opts ? opts->reorder : FVG_REORDER_NONE;
 	auto rank_of = [&](int o) { return cell_rank ? cell_rank[o] : 0; };
 	if(cell_rank) for(int o = 0; o < n; o++) if(cell_rank[o] < 0 || cell_rank[o] >= nranks) { set_error("fvg_mesh_create: cell_rank entry out of range"); return FVG_ERR_INVALID; }
@@ -294,6 +300,19 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 		while(s < nown) {
 			int nc = std::min(TC, nown - s);
 			const int t = (int)tcell0.size() - 1;
+			if(ECAP < EMAX) {
+				// entries of the first k cells of the run, k = 1..nc, in one sweep: a cell adds its faces but those it
+				// shares with an earlier cell of the run (counted when that cell came in). The run ends at the entry cap.
+				int E = 0, k = 0;
+				for(; k < nc; k++) {
+					const int i = s + k, nn = hm->nnode[d2g[i]];
+					int add = 0;
+					for(int j = 0; j < nn; j++) { const int q = nbr_of(i, j); if(!(q >= s && q < i)) add++; }
+					if(E + add > ECAP && k > 0) break;
+					E += add;
+				}
+				nc = k;
+			}
 			for(int attempt = 0; ; attempt++) {
 				halo.clear();
 				int E = 0, nbnd = 0;
@@ -310,7 +329,7 @@ static int build(const fvg_host_mesh *hm, const fvg_mesh_opts *opts, const int *
 				}
 				// boundary ghost cells are staged like halo cells, so they share the row capacity
 				if(((int)halo.size() + nbnd <= HMAX && E <= EMAX) || nc == 1) break;
-				nc = std::max(1, std::min(nc - 1, (int)(nc*0.8)));
+				nc = std::max(1, std::min(nc - 1, ECAP < EMAX ? nc - nc/16 : (int)(nc*0.8)));
 			}
 			if((int)halo.size() > HMAX) { set_error("fvg_mesh_create: a single cell exceeds the halo capacity"); return FVG_ERR_INVALID; }
 			std::sort(halo.begin(), halo.end());

@@ -210,3 +210,27 @@ def test_hilbert_order_makes_compact_tiles():
     hil = lib.DeviceMesh(um, reorder="hilbert", tile_cells=128, device=-2).info
     # row-major strips cut far more faces than Hilbert patches
     assert hil.ncut_dup < 0.5*none.ncut_dup
+
+
+def test_tiles_of_a_quad_mesh_are_cut_at_whole_rounds_of_the_face_kernel(monkeypatch):
+    """All-quad meshes: a 256-cell tile has 2 entries per cell plus half its perimeter, just over two rounds of the face
+    kernel's 256 threads (and over the staging capacity unless it is a perfect square, which made the earlier cut fall
+    back to 204 cells). The cut ends a tile at 512 entries instead: more cells per tile, both rounds full."""
+    from fvens_b200 import synth
+    n = 160
+    coords, nnode, inpoel, bface = synth.periodic_square(n)
+    rc = synth.cell_centres(coords, nnode, inpoel)
+    perm = synth.hilbert_order(rc)
+    um = lib.UMesh.from_arrays(coords, np.ascontiguousarray(nnode[perm]), np.ascontiguousarray(inpoel[perm]), bface)
+
+    def stats():
+        dm = lib.DeviceMesh(um, reorder="none", device=-2)
+        face, _, tile_of = dm.stream()
+        real = np.bincount(tile_of[face >= 0], minlength=dm.info.ntile)
+        return np.diff(dm.tile_offsets()), real
+    cells, real = stats()
+    assert real.max() <= 512 and np.median(real) >= 500
+    assert cells.mean() > 225
+    monkeypatch.setenv("FVG_TILE_ENTRY_CAP", "0")            # the capacity alone: the earlier rounds' cut
+    cells_old, real_old = stats()
+    assert cells_old.mean() < cells.mean() - 15 and real_old.max() <= 544
