@@ -44,7 +44,7 @@ int resident_ctas(const void *kernel, int block, size_t smem)
  * memory; conserved states are converted to primitive ONCE per staged cell (the reference converts the
  * whole field in a separate pass, flow_spatial.cpp:697-699). Then one thread per own cell gathers its
  * <= 4 neighbours from shared memory: no scatter, no atomics. */
-template <int GRAD, int LIM, bool PRIM_IN, bool DIST>
+template <int GRAD, int LIM, bool PRIM_IN, bool DIST, bool PERM = false>
 __global__ void __launch_bounds__(CELL_BLOCK, FVG_CELL_MINB)
 cell_kernel_plain(const CellArgs A)
 {
@@ -77,11 +77,11 @@ cell_kernel_plain(const CellArgs A)
 	// fused multi-GPU evaluation (DIST): a few CTAs of the first wave push the state rows the neighbours need
 	if(DIST && A.dist.first && (int)blockIdx.x < DIST_PROLOGUE_CTAS) dist_push_state_prologue(A.dist.d, A.dist.ctl->k, A.u, A.dist.force_push);
 	if(tid == 0) {
-		unsigned bytes = (unsigned)nc*(32u + 16u + 16u + (GRAD == GM_WLS ? 32u : 0u)) + (LIM == LM_VENKAT ? (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u : 0u);
+		unsigned bytes = (unsigned)nc*((PERM ? 0u : 32u) + 16u + 16u + (GRAD == GM_WLS ? 32u : 0u)) + (LIM == LM_VENKAT ? (unsigned)((nc + (c0 & 1) + 1) & ~1)*8u : 0u);
 		if(MIDS) bytes += (unsigned)ne*16u;
 		if(METRICS) bytes += (unsigned)ne*32u;
 		mbar_expect_tx(bar, bytes);
-		bulk_g2s(sp, A.u + 4*(size_t)c0, (unsigned)nc*32u, bar);
+		if(!PERM) bulk_g2s(sp, A.u + 4*(size_t)c0, (unsigned)nc*32u, bar);
 		bulk_g2s(src, M.rc + c0, (unsigned)nc*16u, bar);
 		// the cells' stencil metadata rides along (consumed from shared memory: no registers held across the staging)
 		bulk_g2s(smraw + S.scl, M.cloc + c0, (unsigned)nc*16u, bar);
@@ -95,13 +95,29 @@ cell_kernel_plain(const CellArgs A)
 		const int tp = t + A.prefetch_distance;
 		const int pc0 = M.tcell0[tp], pnc = M.tcell0[tp+1] - pc0;
 		const int pe0 = M.fsoff[tp], pne = M.fsoff[tp+1] - pe0;
-		bulk_prefetch_l2(A.u + 4*(size_t)pc0, (unsigned)pnc*32u);
+		if(!PERM) bulk_prefetch_l2(A.u + 4*(size_t)pc0, (unsigned)pnc*32u);
+		else {
+			// caller-ordered state: the rows themselves are scattered, their indices are not
+			const int q0 = pc0 & ~3, q1 = min((pc0 + pnc + 3) & ~3, M.ncell & ~3);
+			if(q1 > q0) bulk_prefetch_l2(A.src_idx + q0, (unsigned)(q1 - q0)*4u);
+			const int ph0 = M.thoff[tp] & ~3, ph1 = (M.thoff[tp+1] + 3) & ~3;
+			if(ph1 > ph0) bulk_prefetch_l2(A.halo_src + ph0, (unsigned)(ph1 - ph0)*4u);
+		}
 		bulk_prefetch_l2(M.rc + pc0, (unsigned)pnc*16u);
 		bulk_prefetch_l2(M.cloc + pc0, (unsigned)pnc*16u);
 		{ const int ph0 = M.thoff[tp] & ~3, ph1 = (M.thoff[tp+1] + 3) & ~3; if(ph1 > ph0) bulk_prefetch_l2(M.thalo + ph0, (unsigned)(ph1 - ph0)*4u); }
 		if(GRAD == GM_WLS) bulk_prefetch_l2(M.wlsV + pc0, (unsigned)pnc*32u);
 		if(MIDS) bulk_prefetch_l2(M.fgr + pe0, (unsigned)pne*16u);
 		if(METRICS) { bulk_prefetch_l2(M.fgw + pe0, (unsigned)pne*16u); bulk_prefetch_l2(M.fgln + pe0, (unsigned)pne*16u); }
+	}
+	// caller-ordered state (A.src_idx: caller's row of every device cell): the own rows are gathered in 16-byte pieces
+	// instead of one bulk copy, the halo rows through A.halo_src, and the conversion loop below leaves the own rows in
+	// device order in A.ucopy for the face pass - no permutation kernel on either side of the evaluation
+	if(PERM) {
+		for(int k = tid; k < nc*2; k += CELL_BLOCK) {
+			const int row = k >> 1, piece = k & 1;
+			cp_async16(sp + 4*row + 2*piece, A.u + 4*(size_t)A.src_idx[c0 + row] + 2*piece);
+		}
 	}
 	const int4 tbq = M.tbnd[t];
 	// in-kernel receive of the state's ghost rows: a tile that sees ghost cells waits for the neighbours' rows (its
@@ -113,7 +129,7 @@ cell_kernel_plain(const CellArgs A)
 			const size_t g = (size_t)M.thalo[h0 + h];
 			const int row = nc + h;
 			if(piece == 2) cp_async16(src + row, M.rc + g);
-			else if(!(ghost_win && g >= (size_t)M.ncell)) cp_async16(sp + 4*row + 2*piece, A.u + 4*g + 2*piece);
+			else if(!(ghost_win && g >= (size_t)M.ncell)) cp_async16(sp + 4*row + 2*piece, A.u + 4*(PERM ? (size_t)A.halo_src[h0 + h] : g) + 2*piece);
 		}
 		if(ghost_win) {
 			// (the evaluation number is read only here and where rows are pushed: a handful of tiles)
@@ -148,6 +164,7 @@ cell_kernel_plain(const CellArgs A)
 				const double2 h0 = *reinterpret_cast<const double2*>(sp + 4*k + 2*hb);
 				const double2 h1 = *reinterpret_cast<const double2*>(sp + 4*k + 2*(1 - hb));
 				const double uc[4] = {hb ? h1.x : h0.x, hb ? h1.y : h0.y, hb ? h0.x : h1.x, hb ? h0.y : h1.y};
+				if(PERM && k < nc) st4(A.ucopy + 4*(size_t)(c0 + k), uc);
 				double up[4];
 				cons2prim(A.gas, uc, up);
 				*reinterpret_cast<double2*>(sp + 4*k + 2*hb) = hb ? make_double2(up[2], up[3]) : make_double2(up[0], up[1]);
@@ -161,7 +178,7 @@ cell_kernel_plain(const CellArgs A)
 				else {
 					const double2 n = M.fn[ge];
 					double ui[4], gs[4];
-					ld4(A.u + 4*(size_t)(c0 + L), ui);
+					ld4(A.u + 4*(size_t)(PERM ? A.src_idx[c0 + L] : c0 + L), ui);
 					ghost_state(A.gas, A.gas.bc[(LR >> 16) & 15u], ui, n.x, n.y, gs);
 					cons2prim(A.gas, gs, pj);
 				}
@@ -315,15 +332,15 @@ cell_kernel_plain(const CellArgs A)
 }
 
 
-template <int GRAD, int LIM, bool PRIM_IN, bool DIST>
+template <int GRAD, int LIM, bool PRIM_IN, bool DIST, bool PERM = false>
 static int launch_cell_plain(const CellArgs &b, int nt, cudaStream_t s)
 {
 	const CellSmem S(b.m.TC, b.m.HMAX, b.m.EMAX, LIM != LM_NONE || GRAD == GM_GG, GRAD == GM_GG, GRAD == GM_WLS, LIM == LM_VENKAT);
 	if(S.total > 48*1024) {
-		const cudaError_t ea = cudaFuncSetAttribute(cell_kernel_plain<GRAD,LIM,PRIM_IN,DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
+		const cudaError_t ea = cudaFuncSetAttribute(cell_kernel_plain<GRAD,LIM,PRIM_IN,DIST,PERM>, cudaFuncAttributeMaxDynamicSharedMemorySize, S.total);
 		if(ea != cudaSuccess) return cuda_fail(ea, "cell_kernel smem attribute", __FILE__, __LINE__);
 	}
-	cell_kernel_plain<GRAD,LIM,PRIM_IN,DIST><<<nt, CELL_BLOCK, S.total, s>>>(b);
+	cell_kernel_plain<GRAD,LIM,PRIM_IN,DIST,PERM><<<nt, CELL_BLOCK, S.total, s>>>(b);
 	const cudaError_t e = cudaGetLastError();
 	if(e != cudaSuccess) return cuda_fail(e, "cell_kernel launch", __FILE__, __LINE__);
 	return 0;
@@ -344,6 +361,15 @@ int launch_cell_kernel(int grad, int lim, bool prim_in, const CellArgs &a, cudaS
 		// multi-GPU, device order: the one-tile-per-CTA kernel in its natural tile order (the partition-boundary tiles are
 		// spread over the grid: their pushes travel while the rest computes; the face pass runs them last)
 #define D(G,L) if(grad == G && lim == L) return launch_cell_plain<G,L,false,true>(b, nt, s);
+		D(GM_ZERO,LM_NONE) D(GM_ZERO,LM_BJ) D(GM_ZERO,LM_VENKAT) D(GM_GG,LM_NONE) D(GM_GG,LM_BJ) D(GM_GG,LM_VENKAT)
+		D(GM_WLS,LM_NONE) D(GM_WLS,LM_BJ) D(GM_WLS,LM_VENKAT)
+#undef D
+	}
+	static int fast_perm = -1;
+	if(fast_perm < 0) { const char *e = getenv("FVG_CELL_FASTPERM"); fast_perm = e ? atoi(e) : 1; }
+	if(mode == CM_PERM && fast_perm && !prim_in && b.src_idx && b.halo_src && b.ucopy && !b.ordered) {
+		// single GPU, caller-ordered state: the same one-tile-per-CTA text with the gathers through the permutation
+#define D(G,L) if(grad == G && lim == L) return launch_cell_plain<G,L,false,false,true>(b, nt, s);
 		D(GM_ZERO,LM_NONE) D(GM_ZERO,LM_BJ) D(GM_ZERO,LM_VENKAT) D(GM_GG,LM_NONE) D(GM_GG,LM_BJ) D(GM_GG,LM_VENKAT)
 		D(GM_WLS,LM_NONE) D(GM_WLS,LM_BJ) D(GM_WLS,LM_VENKAT)
 #undef D
