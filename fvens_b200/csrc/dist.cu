@@ -41,8 +41,9 @@ struct fvg_dist {
 	double *d_norm2 = nullptr;         ///< [1] global norm^2 of the most recently gathered step
 	struct Graph { int kind; const void *a, *b, *c; int f0, f1, f2; double x; cudaStream_t s; cudaGraphExec_t exec; long long launches; };
 	cudaStream_t own_stream = nullptr;   ///< stream of fvg_dist_forward_euler_solve (graphs cannot be captured on the default stream)
-	std::vector<Graph> graphs;
-	long long evaluations = 0, graph_replays = 0;
+	std::vector<Graph> graphs;           ///< most recently used last; at most graph_cap entries (FVG_GRAPH_CACHE)
+	size_t graph_cap = 32;
+	long long evaluations = 0, graph_replays = 0, graph_evictions = 0;
 };
 
 namespace fvg {
@@ -197,14 +198,17 @@ template <typename Body>
 static int run_graphed(fvg_dist *D, const fvg_dist::Graph &key, cudaStream_t s, Body body)
 {
 	if(!D->use_graph || D->flow->timing || s == nullptr || s == cudaStreamLegacy) return body();
-	for(const fvg_dist::Graph &g : D->graphs)
+	for(size_t i = 0; i < D->graphs.size(); i++) {
+		const fvg_dist::Graph &g = D->graphs[i];
 		if(g.kind == key.kind && g.a == key.a && g.b == key.b && g.c == key.c && g.f0 == key.f0 && g.f1 == key.f1 && g.f2 == key.f2 &&
 		   g.x == key.x && g.s == key.s) {
 			FVG_CUDA(cudaGraphLaunch(g.exec, s));
 			D->graph_replays++;
 			D->flow->launches += g.launches;
+			if(i + 1 != D->graphs.size()) std::rotate(D->graphs.begin() + (long)i, D->graphs.begin() + (long)i + 1, D->graphs.end());
 			return 0;
 		}
+	}
 	const long long launches0 = D->flow->launches;
 	cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
 	if(e != cudaSuccess) { cudaGetLastError(); return body(); }      // e.g. the stream is already being captured by the caller
@@ -218,6 +222,13 @@ static int run_graphed(fvg_dist *D, const fvg_dist::Graph &key, cudaStream_t s, 
 	cudaGraphDestroy(graph);
 	if(e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
 	g.launches = D->flow->launches - launches0;      // kernels per replay
+	// a caller that hands in new arrays every call would otherwise grow the cache without bound: the least recently used
+	// graph goes (destroying an executable graph whose launch is still in flight is allowed: the work completes first)
+	while(D->graphs.size() >= std::max<size_t>(D->graph_cap, 1)) {
+		cudaGraphExecDestroy(D->graphs.front().exec);
+		D->graphs.erase(D->graphs.begin());
+		D->graph_evictions++;
+	}
 	D->graphs.push_back(g);
 	FVG_CUDA(cudaGraphLaunch(g.exec, s));
 	return 0;
@@ -234,7 +245,8 @@ int fvg_dist_create(fvg_flow *flow, fvg_dist **out)
 	if(m->nranks > MAXRANKS) return dist_fail("fvg_dist_create: at most 16 ranks per box", FVG_ERR_UNSUPPORTED);
 	if(!m->identity_perm && m->nranks > 1) return dist_fail("fvg_dist_create: subdomain meshes are device-ordered", FVG_ERR_INVALID);
 	FVG_CUDA(cudaSetDevice(m->device));
-	std::unique_ptr<fvg_dist> D(new fvg_dist);
+	// (a failed allocation below leaves through FVG_CUDA: the deleter frees what had been allocated)
+	std::unique_ptr<fvg_dist, void(*)(fvg_dist*)> D(new fvg_dist, fvg_dist_destroy);
 	D->flow = flow; D->mesh = m; D->nranks = m->nranks; D->rank = m->rank;
 	D->window_bytes = sizeof(WinHdr) + (size_t)std::max(m->d.nghost, 1)*XAREA_DOUBLES_PER_GHOST*sizeof(double);
 	FVG_CUDA(cudaMalloc((void**)&D->window, D->window_bytes));
@@ -244,6 +256,7 @@ int fvg_dist_create(fvg_flow *flow, fvg_dist **out)
 	FVG_CUDA(cudaMalloc((void**)&D->d_dev, sizeof(DistDev)));
 	FVG_CUDA(cudaMalloc((void**)&D->d_norm2, sizeof(double)));
 	if(const char *e = getenv("FVG_GRAPH")) D->use_graph = e[0] != '0';
+	if(const char *e = getenv("FVG_GRAPH_CACHE")) D->graph_cap = (size_t)std::max(1, atoi(e));
 	FVG_CUDA(cudaDeviceSynchronize());
 	*out = D.release();
 	return 0;

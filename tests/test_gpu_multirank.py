@@ -30,6 +30,13 @@ def test_fused_engine_ranks_on_one_gpu(world, graph, pdl, partition):
     assert r.returncode == 0 and f"MGPU_CHECK OK world {world}" in r.stdout
 
 
+def test_fused_engine_with_a_one_entry_graph_cache():
+    """FVG_GRAPH_CACHE=1: every evaluation with other arrays than the previous one evicts the cached CUDA graph (the cache
+    is bounded, least recently used first, for callers that hand in new arrays all the time) - same bits as ever."""
+    r = _run(2, 29790, FVG_DIST="fused", FVG_GRAPH="1", FVG_GRAPH_CACHE="1")
+    assert r.returncode == 0 and "MGPU_CHECK OK world 2" in r.stdout
+
+
 def test_a_rank_that_withholds_its_rows_is_reported():
     """One rank skips an evaluation: its neighbours' waits time out and fvg_dist_status returns FVG_ERR_COMM (ADVICE round 1:
     a stalled peer must not yield a silently wrong residual)."""
