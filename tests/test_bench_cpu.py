@@ -36,6 +36,14 @@ def test_reference_arm_says_why_it_cannot_run_the_periodic_workload():
     assert d["impl"] == "reference" and "periodic" in d["unavailable"]
 
 
+def test_reference_arm_prints_on_rank_zero_only():
+    """Under torchrun the driver launches N processes: rank 0 alone runs the CPU reference and prints the line."""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1", "--cells", "2e4"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
 def test_numpy_hilbert_order_is_the_library_s():
     for arrs in (synth.bump_channel(90, 34), synth.ogrid_cylinder(96, 40), synth.periodic_square(48, tri_fraction=0.3, jitter=0.1)):
         um = lib.UMesh.from_arrays(*arrs)
